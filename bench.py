@@ -1,0 +1,285 @@
+#!/usr/bin/env python
+"""bench.py -- headline benchmark of the B200-native Xiangqi env + DQN hot path.
+
+Metric (BASELINE.json): env steps/s (movegen + step + terminal/reward, random policy) -- and DQN TD
+updates/s as the `dqn` object -- at 1/2/4/8 B200, next to the reference CPU path on the host cores.
+
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--envs E] [--plies P]
+  torchrun ... bench.py --gpus N ...          (one rank per GPU, env shards, no data-path collective)
+  python bench.py --impl reference ...        (the reference's own ChessBoard path on the host cores)
+
+One "step" = one fused rollout launch: P plies (default 200 = one full-length game) over the E envs of
+this GPU (default 4096 = BASELINE configs[1]).  Scaling is weak: E envs per GPU.
+Timing: W warm-up steps, then exactly K steps, each bracketed by CUDA events on the launching stream
+(the library is pointed at torch's current stream), L2 flushed between steps outside the timed
+intervals; barrier + synchronize on both sides; max over ranks.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+ALGO_BYTES_PER_STEP = 136   # read 64 B record + write 64 B record + 8 B outputs
+
+
+def peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        d = json.load(open(p))
+        return {"hbm_gbs": d["hbm_gbs"], "bf16_tflops": d["bf16_tflops"], "bf16_tflops_sustained": d.get("bf16_tflops_sustained"),
+                "source": "measured (MEASURED_PEAKS.json)"}
+    return {"hbm_gbs": 6650.0, "bf16_tflops": 1590.0, "bf16_tflops_sustained": 1400.0, "source": "fallback (B200_PROFILING.md)"}
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled every 200 ms while the timed region runs"""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.index = index
+        self.rows = []
+        self.proc = None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "200",
+                                          "-i", str(self.index)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except OSError:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(",")])
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.25)
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        for r in self.rows:
+            try:
+                sm.append(float(r[1])); mx.append(float(r[2]))
+            except (ValueError, IndexError):
+                continue
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), r[5:9]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        sm.sort()
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": max(mx) if mx else None, "reasons": sorted(reasons),
+                "samples": len(sm)}
+
+
+def cpu_reference_leg(n_threads, plies_per_thread, seed=1):
+    """the reference's own ChessBoard/ChessAI path (oracle/_ref, compiled unmodified) on the host cores,
+    or the plain-C port when that build is absent.  Returns (steps_per_s, kind, sample description)."""
+    import ctypes as C
+    from oracle import loader as O
+    R = O.ref()
+    tot = C.c_long()
+    if R is not None:
+        s = R.ref_bench_rollout_random(n_threads, plies_per_thread, seed, C.byref(tot))
+        kind = "reference"
+        what = (f"{n_threads} threads x {plies_per_thread} random-policy plies each through the reference's own ChessBoard/ChessAI "
+                "classes compiled unmodified (getAllValidActions -> movePiece -> evaluateBoard -> checkGameOver, reset on terminal)")
+    else:
+        L = O.oracle()
+        s = L.xqo_bench_rollout_random(n_threads, 64, max(1, plies_per_thread // 64), seed, C.byref(tot))
+        kind = "port"
+        what = f"{n_threads} threads x 64 envs x {max(1, plies_per_thread // 64)} plies through oracle/xq_oracle.c (plain-C port)"
+    return tot.value / s, kind, what, tot.value, s
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return 0
+    cores = os.cpu_count() or 1
+    plies = args.ref_plies
+    vals = []
+    for _ in range(args.warmup):
+        cpu_reference_leg(cores, max(1000, plies // 20))
+    t_tot, n_tot, kind, what = 0.0, 0, None, None
+    for _ in range(args.steps):
+        v, kind, what, n, s = cpu_reference_leg(cores, plies)
+        vals.append(v); t_tot += s; n_tot += n
+    value = n_tot / t_tot
+    line = {"impl": "reference", "metric": "env steps/s (movegen+step, random policy)", "value": value, "unit": "steps/s",
+            "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * t_tot / args.steps,
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "int32", "data": "synthetic",
+            "config": {"workload": f"BASELINE configs[1]: {args.envs} envs random-policy rollouts from the opening, {args.plies} plies per step",
+                       "note": "CPU arm: each step is a bounded sample of that workload, one independent board per host thread"},
+            "cpu_baseline": {"value": value, "unit": "steps/s", "cores": cores, "kind": kind, "sample": what},
+            "e2e": {"value": value, "unit": "steps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "gpu_launches": 0}
+    print(json.dumps(line))
+    return 0
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--envs", type=int, default=4096, help="envs per GPU (BASELINE configs[1]: 4096)")
+    ap.add_argument("--plies", type=int, default=200, help="plies per fused launch (= one step)")
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--ref-plies", type=int, default=250000, help="plies per host thread per step of the reference arm")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-aux", action="store_true")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup
+    if args.impl == "reference":
+        return run_reference(args)
+
+    import numpy as np
+    import torch
+    import cn_chess_ai_b200 as xq
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device; the hot path has no CPU fallback (use --impl reference for the CPU arm)")
+    torch.cuda.set_device(local)
+    dist = None
+    if world > 1:
+        import torch.distributed as dist
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+
+    def barrier():
+        if dist is not None:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    L = xq.lib()
+    stream = torch.cuda.current_stream()
+    E, P = args.envs, args.plies
+    env = xq.BatchedEnv(E, device=local, seed=2024, env_id0=rank * E)
+    env.set_stream(stream.cuda_stream)
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")   # > 126 MB L2
+
+    # ---- device-resident leg: `value` ----
+    for _ in range(args.warmup):
+        env.rollout_random_async(P)
+    env.stats(reset=True)
+    barrier()
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    launches0 = L.xq_launch_count()
+    evs = []
+    for _ in range(args.steps):
+        flush.fill_(1)                      # L2 flush, outside the timed interval
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record(stream)
+        env.rollout_random_async(P)
+        b.record(stream)
+        evs.append((a, b))
+    barrier()
+    launches = L.xq_launch_count() - launches0
+    clocks = sampler.stop() if rank == 0 else None
+    ms = sum(a.elapsed_time(b) for a, b in evs)
+    st = env.stats(reset=True)
+    assert int(st["steps"]) == E * P * args.steps, "stats mismatch: kernel did not apply every ply"
+    t = torch.tensor([ms], dtype=torch.float64, device="cuda")
+    if dist is not None:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms_max = float(t.item())
+    total_steps = E * P * args.steps * world
+    value = total_steps / (ms_max * 1e-3)
+
+    # ---- end-to-end leg through the host-buffer C ABI: set_boards -> rollout -> get_boards + stats ----
+    host_in = np.zeros(E, dtype=xq.ENV_DTYPE)
+    host_in[:] = env.get_boards()
+    pin_in = torch.from_numpy(host_in.view(np.uint8)).pin_memory()
+    pin_out = torch.empty_like(pin_in).pin_memory()
+    recs_in = pin_in.numpy().view(xq.ENV_DTYPE)
+    recs_out = pin_out.numpy().view(xq.ENV_DTYPE)
+    for _ in range(2):
+        env.set_boards(recs_in); env.rollout_random(P); env.get_boards(out=recs_out)
+    barrier()
+    t0 = time.perf_counter()
+    e2e_steps = 0
+    for _ in range(args.steps):
+        env.set_boards(recs_in)
+        s, _ = env.rollout_random(P)
+        env.get_boards(out=recs_out)
+        e2e_steps += int(s["steps"])
+    torch.cuda.synchronize()
+    e2e_s = time.perf_counter() - t0
+    t = torch.tensor([e2e_s], dtype=torch.float64, device="cuda")
+    if dist is not None:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    e2e_value = e2e_steps * world / float(t.item())
+    launches += 0
+
+    pk = peaks()
+    kernel_ms = ms_max / args.steps
+    achieved = ALGO_BYTES_PER_STEP * E * P / (kernel_ms * 1e-3) / 1e9
+    traffic = None
+    tp = os.path.join(ROOT, "profiles", "traffic.json")
+    if os.path.exists(tp):
+        traffic = json.load(open(tp)).get("rollout_random_kernel_dram_bytes_per_launch")
+
+    line = {"metric": "env steps/s (movegen+step, random policy)", "value": value, "unit": "steps/s", "n_gpus": world,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": kernel_ms, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "int32", "data": "synthetic",
+            "config": {"workload": f"BASELINE configs[1]: {E} envs/GPU random-policy rollouts from the opening (legal-move gen + step + "
+                                   f"terminal/reward), {P} plies per fused launch (= one step), auto-reset",
+                       "envs_per_gpu": E, "plies_per_step": P, "l2": "flushed between timed steps (256 MiB fill)",
+                       "parallelism": f"env-sharded x{world}, no data-path collective"},
+            "e2e": {"value": e2e_value, "unit": "steps/s", "h2d_bytes_per_step": int(recs_in.nbytes),
+                    "d2h_bytes_per_step": int(recs_out.nbytes) + 64},
+            "gpu_launches": int(launches),
+            "roofline": {"bound": "hbm", "achieved": achieved, "peak": pk["hbm_gbs"], "unit": "GB/s", "frac": achieved / pk["hbm_gbs"],
+                         "traffic": traffic, "kernel": "rollout_random_kernel", "peak_source": pk["source"],
+                         "algorithmic_bytes_per_launch": ALGO_BYTES_PER_STEP * E * P,
+                         "note": "integer/latency-bound by design: boards stay on chip for all plies of a launch (DESIGN.md)"},
+            "clocks": clocks}
+
+    if rank == 0 and world == 1 and not args.no_aux:
+        # BASELINE config 5 size on one GPU, for context (not the headline): 1M envs x 32 plies
+        big = xq.BatchedEnv(1 << 20, device=local, seed=7)
+        big.set_stream(stream.cuda_stream)
+        big.rollout_random_async(8)
+        torch.cuda.synchronize()
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record(stream); big.rollout_random_async(32); b.record(stream)
+        torch.cuda.synchronize()
+        line["aux"] = {"config5_1M_envs_steps_per_s": (1 << 20) * 32 / (a.elapsed_time(b) * 1e-3)}
+        big.close()
+        try:
+            from cn_chess_ai_b200 import bench_dqn
+            line["dqn"] = bench_dqn(stream, pk)
+        except ImportError:
+            pass
+
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        cores = os.cpu_count() or 1
+        v, kind, what, _, _ = cpu_reference_leg(cores, 400000)
+        line["cpu_baseline"] = {"value": v, "unit": "steps/s", "cores": cores, "kind": kind, "sample": what}
+
+    if rank == 0:
+        print(json.dumps(line))
+    if dist is not None:
+        dist.barrier()
+        dist.destroy_process_group()
+    return 0
+
+
+if __name__ == "__main__":
+    sys.exit(main())

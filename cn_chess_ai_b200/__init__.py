@@ -1,0 +1,6 @@
+"""cn_chess_ai_b200: B200-native batched Xiangqi environment + DQN trainer (sm_100a only).
+
+Host-side mirror of the C ABI in include/xq.h; the hot path lives in csrc/ as hand-written CUDA.
+"""
+from ._lib import ENV_DTYPE, MAX_ACTIONS, STATE_SIZE, STATS_DTYPE, TRACE_DTYPE, XQError, lib  # noqa: F401
+from .env import BatchedEnv, action  # noqa: F401

@@ -1,0 +1,526 @@
+// xq_env.cu -- batched Xiangqi environment on sm_100a: ordered legal-move generation, move
+// application, terminal / winner / reward evaluation and the fused random-policy rollout.
+//
+// Data layout in HBM: one 64-byte xq_env_rec per environment (include/xq.h), AoS, 64-B aligned:
+// a warp of the thread-per-board kernels touches 32 consecutive records = 2 KB contiguous.
+// On chip each thread keeps its board as 12 nibble-packed words in shared memory, interleaved by
+// thread (SmemBoard) so that data-dependent square lookups never bank-conflict, and the 16-byte
+// meta in registers.  The rollout kernel loads a record once, plays n_plies plies entirely on
+// chip and stores it once: per ply it touches HBM only for the optional 8-byte trace record.
+//
+// Reference functions replaced: ChessBoard::{getValidMoves,isValidMove,movePiece,checkGameOver,
+// getWinner,reset} (src/chessboard.cpp), ChessAI::{getAllValidActions,evaluateBoard,
+// getStateRepresentation} and the loop body of ChessAI::train (src/chessai.cpp:96-119).
+#include <stdarg.h>
+#include <string.h>
+
+#include <new>
+#include <vector>
+
+#include "xq_common.cuh"
+
+namespace xq {
+
+std::string& last_error() { static thread_local std::string e; return e; }
+unsigned long long g_launches = 0;
+int fail(int code, const char* fmt, ...) {
+    char buf[512];
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(buf, sizeof(buf), fmt, ap);
+    va_end(ap);
+    last_error() = buf;
+    return code;
+}
+
+constexpr int kThreads = 128;          // thread-per-board kernels: boards per CTA
+constexpr int kListStride = 65;        // words per thread of the staged action list (64 + 1 pad)
+
+// ------------------------------------------------------------------------------------------
+// Board summary: material per colour, general presence, first general in index order
+// (ChessBoard::checkGameOver :286-309, getWinner :312-320, ChessAI::evaluateBoard :311-342).
+struct Summary {
+    int mat_red, mat_black;
+    int winner;          // colour of the first General in square order, NOCOLOR if none
+    bool red_alive, black_alive;
+};
+
+template <class B>
+__device__ __forceinline__ Summary summarize(const B& b) {
+    Summary s{0, 0, NOCOLOR, false, false};
+    for (int w = 0; w < 12; ++w) {
+        uint32_t word = b.base[w * b.stride];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+            const int code = (word >> (4 * i)) & 15;
+            if (code == 0) continue;
+            const int sc = piece_score(type_of(code));
+            if (code >= 8) s.mat_black += sc; else s.mat_red += sc;
+            if (code == GENERAL) { s.red_alive = true; if (s.winner == NOCOLOR) s.winner = RED; }
+            if (code == GENERAL + 7) { s.black_alive = true; if (s.winner == NOCOLOR) s.winner = BLACK; }
+        }
+    }
+    return s;
+}
+
+__device__ __forceinline__ void reset_board(SmemBoard& b) {
+#pragma unroll
+    for (int w = 0; w < 12; ++w) b.base[w * b.stride] = kOpening[w];
+}
+
+struct Meta {
+    int move_count, player, red_score, black_score;
+    uint32_t ctr;
+    uint8_t flags;
+    __device__ __forceinline__ void load(const xq_env_rec* r) {
+        const uint4 m = reinterpret_cast<const uint4*>(r)[3];
+        move_count = m.x & 0xFFFF; player = (m.x >> 16) & 0xFF; flags = (uint8_t)(m.x >> 24);
+        red_score = (int)m.y; black_score = (int)m.z; ctr = m.w;
+    }
+    __device__ __forceinline__ void store(xq_env_rec* r) const {
+        reinterpret_cast<uint4*>(r)[3] = make_uint4((uint32_t)(move_count & 0xFFFF) | ((uint32_t)player << 16) | ((uint32_t)flags << 24),
+                                                    (uint32_t)red_score, (uint32_t)black_score, ctr);
+    }
+    __device__ __forceinline__ void reset() { move_count = 0; player = RED; red_score = 0; black_score = 0; }
+};
+
+// ChessBoard::movePiece after validation (src/chessboard.cpp:43-63); returns the captured code
+__device__ __forceinline__ int apply_move(SmemBoard& b, Meta& m, int from, int to) {
+    const int cap = b.get(to);
+    b.set(to, b.get(from));
+    b.set(from, 0);
+    if (cap != 0) {
+        const int sc = piece_score(type_of(cap));
+        if (cap >= 8) m.red_score += sc; else m.black_score += sc;   // captured Black => Red scores (:53-57)
+    }
+    m.move_count++;
+    m.player ^= 1;
+    return cap;
+}
+
+// ------------------------------------------------------------------------------------------
+// K1: ordered legal-action lists (ChessAI::getAllValidActions for the side to move).
+// The list is staged in shared memory (one padded row per thread) and written out with
+// fully coalesced 4-byte stores: 256 B per env.
+__global__ void __launch_bounds__(kThreads) legal_moves_kernel(const xq_env_rec* __restrict__ envs, int64_t n,
+                                                              uint8_t* __restrict__ counts, uint32_t* __restrict__ actions) {
+    __shared__ uint32_t s_board[12 * kThreads];
+    __shared__ uint32_t s_list[kThreads * kListStride];
+    const int tid = threadIdx.x;
+    const int64_t env0 = (int64_t)blockIdx.x * kThreads;
+    const int64_t env = env0 + tid;
+    uint16_t* my = reinterpret_cast<uint16_t*>(&s_list[tid * kListStride]);
+    for (int i = 0; i < 64; ++i) s_list[tid * kListStride + i] = 0xFFFFFFFFu;
+    if (env < n) {
+        SmemBoard b{s_board + tid, kThreads};
+        b.load(envs + env);
+        Meta m; m.load(envs + env);
+        int cnt = 0;
+        all_actions(b, m.player, [&](int from, int to) { if (cnt < XQ_MAX_ACTIONS) my[cnt++] = XQ_ACTION(from, to); });
+        counts[env] = (uint8_t)cnt;
+    }
+    __syncthreads();
+    const int64_t live = min((int64_t)kThreads, n - env0);
+    for (int j = tid; j < live * 64; j += kThreads) actions[env0 * 64 + j] = s_list[(j >> 6) * kListStride + (j & 63)];
+}
+
+// K1b: ChessBoard::getValidMoves(row,col) for one square of every env
+__global__ void __launch_bounds__(kThreads) valid_moves_kernel(const xq_env_rec* __restrict__ envs, int64_t n, int row, int col,
+                                                              uint8_t* __restrict__ counts, uint8_t* __restrict__ to_out) {
+    __shared__ uint32_t s_board[12 * kThreads];
+    const int tid = threadIdx.x;
+    const int64_t env = (int64_t)blockIdx.x * kThreads + tid;
+    if (env >= n) return;
+    SmemBoard b{s_board + tid, kThreads};
+    b.load(envs + env);
+    int cnt = 0;
+    uint8_t* out = to_out + env * 20;
+    for (int i = 0; i < 20; ++i) out[i] = 0xFF;
+    if (inside(row, col)) {
+        const int code = b.get(row * 9 + col);
+        if (code != 0) gen_piece(b, row, col, code, [&](int to) { if (cnt < 20) out[cnt] = (uint8_t)to; ++cnt; });
+    }
+    counts[env] = (uint8_t)cnt;
+}
+
+// K1c: ChessBoard::isValidMove for one (fr,fc,tr,tc) per env
+__global__ void __launch_bounds__(kThreads) is_valid_kernel(const xq_env_rec* __restrict__ envs, int64_t n,
+                                                           const int4* __restrict__ moves, uint8_t* __restrict__ valid) {
+    __shared__ uint32_t s_board[12 * kThreads];
+    const int tid = threadIdx.x;
+    const int64_t env = (int64_t)blockIdx.x * kThreads + tid;
+    if (env >= n) return;
+    SmemBoard b{s_board + tid, kThreads};
+    b.load(envs + env);
+    const int4 mv = moves[env];
+    valid[env] = is_valid_move(b, mv.x, mv.y, mv.z, mv.w) ? 1 : 0;
+}
+
+// K2: one externally chosen action per env: movePiece + evaluateBoard + checkGameOver + getWinner
+__global__ void __launch_bounds__(kThreads) step_kernel(xq_env_rec* __restrict__ envs, int64_t n, const uint16_t* __restrict__ actions,
+                                                       int32_t* __restrict__ reward, uint8_t* __restrict__ done,
+                                                       uint8_t* __restrict__ winner, uint8_t* __restrict__ captured,
+                                                       uint8_t* __restrict__ valid, int auto_reset) {
+    __shared__ uint32_t s_board[12 * kThreads];
+    const int tid = threadIdx.x;
+    const int64_t env = (int64_t)blockIdx.x * kThreads + tid;
+    if (env >= n) return;
+    SmemBoard b{s_board + tid, kThreads};
+    b.load(envs + env);
+    Meta m; m.load(envs + env);
+    const int a = actions[env];
+    const int from = XQ_ACTION_FROM(a), to = XQ_ACTION_TO(a);
+    const int mover = m.player;
+    const bool ok = from < 90 && to < 90 && is_valid_move(b, from / 9, from % 9, to / 9, to % 9);
+    int cap = 0;
+    if (ok) { cap = apply_move(b, m, from, to); m.ctr++; }
+    const Summary s = summarize(b);
+    const int diff = mover == RED ? s.mat_red - s.mat_black : s.mat_black - s.mat_red;
+    const bool over = m.move_count >= XQ_MAX_MOVES || !(s.red_alive && s.black_alive);
+    if (reward) reward[env] = reward_from_material(diff, m.move_count);
+    if (done) done[env] = over ? 1 : 0;
+    if (winner) winner[env] = (uint8_t)s.winner;
+    if (captured) captured[env] = (uint8_t)cap;
+    if (valid) valid[env] = ok ? 1 : 0;
+    if (over && auto_reset) { reset_board(b); m.reset(); }
+    if (ok || (over && auto_reset)) { b.store(envs + env); m.store(envs + env); }
+}
+
+// K3: reset selected envs (ChessBoard::reset)
+__global__ void reset_kernel(xq_env_rec* __restrict__ envs, int64_t n, const uint8_t* __restrict__ mask, int clear_ctr) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;   // one 16-byte quarter record per thread
+    const int64_t env = i >> 2;
+    const int q = (int)(i & 3);
+    if (env >= n || (mask && !mask[env])) return;
+    uint4* p = reinterpret_cast<uint4*>(envs + env) + q;
+    if (q < 3) *p = make_uint4(kOpening[4 * q], kOpening[4 * q + 1], kOpening[4 * q + 2], kOpening[4 * q + 3]);
+    else { const uint32_t ctr = clear_ctr ? 0u : p->w; *p = make_uint4(0u, 0u, 0u, ctr); }
+}
+
+// K4: one-hot state encoding (ChessAI::getStateRepresentation), 1260 doubles per env.
+// One warp per env: lane writes are 8-byte and consecutive -> coalesced 256-B segments.
+__global__ void __launch_bounds__(256) state_onehot_kernel(const xq_env_rec* __restrict__ envs, int64_t n, double* __restrict__ out) {
+    const int64_t env = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int lane = threadIdx.x & 31;
+    if (env >= n) return;
+    const uint32_t w = lane < 12 ? envs[env].sq[lane] : 0u;
+    double* o = out + env * XQ_STATE_SIZE;
+    for (int i = lane; i < XQ_STATE_SIZE; i += 32) {
+        const int s = i / 14, ch = i - s * 14;
+        const uint32_t word = __shfl_sync(0xFFFFFFFFu, w, s >> 3);
+        const int code = (word >> ((s & 7) * 4)) & 15;
+        o[i] = (code == ch + 1) ? 1.0 : 0.0;
+    }
+}
+
+// ------------------------------------------------------------------------------------------
+// K5: fused random-policy rollout, v1: one thread per board, boards resident in shared memory
+// for all n_plies plies.  Per ply: ordered list -> list[idx31 % n] -> apply -> reward ->
+// terminal/winner -> reset on terminal.
+struct StatsAcc {
+    unsigned long long steps, games, red_wins, black_wins, cap_games, captures, legal_sum;
+    long long reward_sum;
+};
+
+__device__ __forceinline__ unsigned long long warp_sum(unsigned long long v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xFFFFFFFFu, v, o);
+    return v;
+}
+
+__global__ void __launch_bounds__(kThreads) rollout_random_kernel(xq_env_rec* __restrict__ envs, int64_t n, uint64_t env_id0,
+                                                                 uint64_t seed, int n_plies, xq_trace_rec* __restrict__ trace,
+                                                                 xq_env_stats* __restrict__ stats) {
+    __shared__ uint32_t s_board[12 * kThreads];
+    __shared__ uint32_t s_list[64 * kThreads];   // action list, u16 pairs, word-interleaved by thread
+    const int tid = threadIdx.x;
+    const int64_t env = (int64_t)blockIdx.x * kThreads + tid;
+    StatsAcc st{0, 0, 0, 0, 0, 0, 0, 0};
+    if (env < n) {
+        SmemBoard b{s_board + tid, kThreads};
+        b.load(envs + env);
+        Meta m; m.load(envs + env);
+        Summary s = summarize(b);
+        if (m.move_count >= XQ_MAX_MOVES || !(s.red_alive && s.black_alive)) {   // injected terminal board: chessai.cpp:90,96
+            reset_board(b); m.reset(); s = summarize(b);
+        }
+        int mat_red = s.mat_red, mat_black = s.mat_black;
+        uint16_t* list = reinterpret_cast<uint16_t*>(s_list);   // entry k of thread t: list[(k>>1)*2*kThreads + 2*t + (k&1)]
+        for (int p = 0; p < n_plies; ++p) {
+            int cnt = 0;
+            all_actions(b, m.player, [&](int from, int to) {
+                if (cnt < XQ_MAX_ACTIONS) { list[(cnt >> 1) * 2 * kThreads + 2 * tid + (cnt & 1)] = XQ_ACTION(from, to); ++cnt; }
+            });
+            xq_trace_rec tr;   // assembled in registers, stored as one 8-byte word pair
+            if (cnt == 0) {   // chessai.cpp:100-103: no action ends the episode; the slot restarts
+                tr.action = XQ_ACTION_NONE; tr.n_legal = 0; tr.flags = 1 | (NOCOLOR << 1); tr.reward = 0;
+                reset_board(b); m.reset(); m.ctr++; mat_red = mat_black = 1480; st.games++;
+            } else {
+                const uint64_t x = rng(seed, env_id0 + (uint64_t)env, m.ctr);
+                const int k = (int)((uint32_t)(x >> 33) % (uint32_t)cnt);
+                const int a = list[(k >> 1) * 2 * kThreads + 2 * tid + (k & 1)];
+                const int mover = m.player;
+                const int cap = apply_move(b, m, XQ_ACTION_FROM(a), XQ_ACTION_TO(a));
+                m.ctr++;
+                if (cap != 0) { const int sc = piece_score(type_of(cap)); if (cap >= 8) mat_black -= sc; else mat_red -= sc; st.captures++; }
+                const int reward = reward_from_material(mover == RED ? mat_red - mat_black : mat_black - mat_red, m.move_count);
+                bool over = m.move_count >= XQ_MAX_MOVES;
+                int win = NOCOLOR;
+                if (over || type_of(cap) == GENERAL) {   // only now can the outcome change: rescan (rare)
+                    const Summary e = summarize(b);
+                    over = over || !(e.red_alive && e.black_alive);
+                    win = e.winner;
+                }
+                tr.action = (uint16_t)a; tr.n_legal = (uint8_t)cnt; tr.reward = reward;
+                tr.flags = (uint8_t)((over ? 1 : 0) | ((over ? win : NOCOLOR) << 1) | (cap << 4));
+                st.steps++; st.legal_sum += cnt; st.reward_sum += reward;
+                if (over) {
+                    st.games++;
+                    if (win == RED) st.red_wins++; else if (win == BLACK) st.black_wins++;
+                    if (m.move_count < XQ_MAX_MOVES) st.cap_games++;
+                    reset_board(b); m.reset(); mat_red = mat_black = 1480;
+                }
+            }
+            if (trace)
+                reinterpret_cast<uint2*>(trace)[(int64_t)p * n + env] =
+                    make_uint2((uint32_t)tr.action | ((uint32_t)tr.n_legal << 16) | ((uint32_t)tr.flags << 24), (uint32_t)tr.reward);
+        }
+        b.store(envs + env);
+        m.store(envs + env);
+    }
+    if (stats) {
+        unsigned long long v[8] = {st.steps, st.games, st.red_wins, st.black_wins, st.cap_games, st.captures,
+                                   (unsigned long long)st.reward_sum, st.legal_sum};
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+            const unsigned long long r = warp_sum(v[i]);
+            if ((tid & 31) == 0 && r != 0) atomicAdd(reinterpret_cast<unsigned long long*>(stats) + i, r);
+        }
+    }
+}
+
+}  // namespace xq
+
+// ==========================================================================================
+// C ABI
+// ==========================================================================================
+using namespace xq;
+
+struct xq_env_s {
+    int64_t n = 0;
+    int device = 0;
+    uint64_t seed = 0, env_id0 = 0;
+    cudaStream_t stream = nullptr;
+    bool own_stream = false;
+    xq_env_rec* d_envs = nullptr;
+    xq_env_stats* d_stats = nullptr;
+    // scratch for the host-pointer API
+    uint8_t* d_u8[5] = {nullptr, nullptr, nullptr, nullptr, nullptr};   // n bytes each
+    uint16_t* d_actions = nullptr;    // n
+    int32_t* d_i32 = nullptr;         // 4n
+    uint32_t* d_lists = nullptr;      // n*64 words, allocated on first use
+    xq_trace_rec* d_trace = nullptr; int64_t trace_cap = 0;
+    double* d_state = nullptr;
+};
+
+static inline unsigned grid_for(int64_t n, int per_block) { return (unsigned)((n + per_block - 1) / per_block); }
+
+extern "C" {
+
+const char* xq_last_error(void) { return last_error().c_str(); }
+const char* xq_version(void) { return "xq-b200 0.1 (sm_100a)"; }
+uint64_t xq_launch_count(void) { return g_launches; }
+uint64_t xq_rng(uint64_t seed, uint64_t env_id, uint32_t ctr) { return rng(seed, env_id, ctr); }
+
+uint32_t xq_eps_threshold(double eps) {
+    const double rm = 2147483647.0;
+    if (!(eps > 0.0)) return 0;
+    if (eps > 1.0) return 0x80000000u;
+    long long t = (long long)(eps * rm);
+    while (t > 0 && !((double)(t - 1) / rm < eps)) --t;
+    while (t <= 2147483647LL && ((double)t / rm < eps)) ++t;
+    return (uint32_t)t;
+}
+
+int xq_device_count(int* count) {
+    if (!count) return fail(XQ_ERR_INVALID, "xq_device_count: null pointer");
+    XQ_CUDA(cudaGetDeviceCount(count));
+    return XQ_OK;
+}
+
+int xq_env_destroy(xq_env_t h) {
+    if (!h) return XQ_OK;
+    cudaSetDevice(h->device);
+    cudaFree(h->d_envs); cudaFree(h->d_stats); cudaFree(h->d_actions); cudaFree(h->d_i32); cudaFree(h->d_lists);
+    cudaFree(h->d_trace); cudaFree(h->d_state);
+    for (auto p : h->d_u8) cudaFree(p);
+    if (h->own_stream && h->stream) cudaStreamDestroy(h->stream);
+    delete h;
+    return XQ_OK;
+}
+
+int xq_env_create(int64_t n_envs, int device, uint64_t seed, uint64_t env_id0, xq_env_t* out) {
+    if (!out || n_envs <= 0) return fail(XQ_ERR_INVALID, "xq_env_create: n_envs must be > 0 and out non-null");
+    int ndev = 0;
+    XQ_CUDA(cudaGetDeviceCount(&ndev));
+    if (device < 0 || device >= ndev) return fail(XQ_ERR_INVALID, "xq_env_create: device %d out of range (%d devices)", device, ndev);
+    XQ_CUDA(cudaSetDevice(device));
+    xq_env_s* h = new (std::nothrow) xq_env_s();
+    if (!h) return fail(XQ_ERR_NOMEM, "xq_env_create: out of host memory");
+    h->n = n_envs; h->device = device; h->seed = seed; h->env_id0 = env_id0;
+    cudaError_t e = cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking);
+    h->own_stream = (e == cudaSuccess);
+    if (e == cudaSuccess) e = cudaMalloc(&h->d_envs, sizeof(xq_env_rec) * n_envs);
+    if (e == cudaSuccess) e = cudaMalloc(&h->d_stats, sizeof(xq_env_stats));
+    if (e == cudaSuccess) e = cudaMalloc(&h->d_actions, sizeof(uint16_t) * n_envs);
+    if (e == cudaSuccess) e = cudaMalloc(&h->d_i32, sizeof(int32_t) * 4 * n_envs);
+    for (auto& p : h->d_u8) if (e == cudaSuccess) e = cudaMalloc(&p, (size_t)n_envs);
+    if (e == cudaSuccess) e = cudaMemsetAsync(h->d_stats, 0, sizeof(xq_env_stats), h->stream);
+    if (e != cudaSuccess) { xq_env_destroy(h); return fail(XQ_ERR_CUDA, "xq_env_create: %s", cudaGetErrorString(e)); }
+    reset_kernel<<<grid_for(4 * n_envs, 256), 256, 0, h->stream>>>(h->d_envs, n_envs, nullptr, 1);
+    ++g_launches;
+    e = cudaGetLastError();
+    if (e == cudaSuccess) e = cudaStreamSynchronize(h->stream);
+    if (e != cudaSuccess) { xq_env_destroy(h); return fail(XQ_ERR_CUDA, "xq_env_create: reset kernel: %s", cudaGetErrorString(e)); }
+    *out = h;
+    return XQ_OK;
+}
+
+#define XQ_ENV_ENTER(h)                                                        \
+    if (!(h)) return fail(XQ_ERR_INVALID, "%s: null handle", __func__);        \
+    XQ_CUDA(cudaSetDevice((h)->device))
+
+int xq_env_count(xq_env_t h, int64_t* n) { if (!h || !n) return fail(XQ_ERR_INVALID, "xq_env_count: null"); *n = h->n; return XQ_OK; }
+
+int xq_env_set_stream(xq_env_t h, void* s) {
+    XQ_ENV_ENTER(h);
+    XQ_CUDA(cudaStreamSynchronize(h->stream));
+    if (h->own_stream) { cudaStreamDestroy(h->stream); h->own_stream = false; }
+    h->stream = (cudaStream_t)s;
+    return XQ_OK;
+}
+int xq_env_sync(xq_env_t h) { XQ_ENV_ENTER(h); XQ_CUDA(cudaStreamSynchronize(h->stream)); return XQ_OK; }
+int xq_env_device_boards(xq_env_t h, void** p) { if (!h || !p) return fail(XQ_ERR_INVALID, "xq_env_device_boards: null"); *p = h->d_envs; return XQ_OK; }
+
+int xq_env_reset(xq_env_t h, const uint8_t* mask_host) {
+    XQ_ENV_ENTER(h);
+    if (mask_host) XQ_CUDA(cudaMemcpyAsync(h->d_u8[0], mask_host, (size_t)h->n, cudaMemcpyHostToDevice, h->stream));
+    reset_kernel<<<grid_for(4 * h->n, 256), 256, 0, h->stream>>>(h->d_envs, h->n, mask_host ? h->d_u8[0] : nullptr, 0);
+    XQ_LAUNCH_CHECK();
+    XQ_CUDA(cudaStreamSynchronize(h->stream));
+    return XQ_OK;
+}
+
+int xq_env_set_boards(xq_env_t h, const xq_env_rec* recs, int64_t first, int64_t n) {
+    XQ_ENV_ENTER(h);
+    if (!recs || first < 0 || n < 0 || first + n > h->n) return fail(XQ_ERR_INVALID, "xq_env_set_boards: range [%lld,+%lld) outside %lld envs", (long long)first, (long long)n, (long long)h->n);
+    XQ_CUDA(cudaMemcpyAsync(h->d_envs + first, recs, sizeof(xq_env_rec) * n, cudaMemcpyHostToDevice, h->stream));
+    XQ_CUDA(cudaStreamSynchronize(h->stream));
+    return XQ_OK;
+}
+int xq_env_get_boards(xq_env_t h, xq_env_rec* recs, int64_t first, int64_t n) {
+    XQ_ENV_ENTER(h);
+    if (!recs || first < 0 || n < 0 || first + n > h->n) return fail(XQ_ERR_INVALID, "xq_env_get_boards: range [%lld,+%lld) outside %lld envs", (long long)first, (long long)n, (long long)h->n);
+    XQ_CUDA(cudaMemcpyAsync(recs, h->d_envs + first, sizeof(xq_env_rec) * n, cudaMemcpyDeviceToHost, h->stream));
+    XQ_CUDA(cudaStreamSynchronize(h->stream));
+    return XQ_OK;
+}
+
+int xq_env_legal_moves(xq_env_t h, uint8_t* counts_host, xq_action* actions_host) {
+    XQ_ENV_ENTER(h);
+    if (!counts_host || !actions_host) return fail(XQ_ERR_INVALID, "xq_env_legal_moves: null output");
+    if (!h->d_lists) XQ_CUDA(cudaMalloc(&h->d_lists, sizeof(uint32_t) * 64 * h->n));
+    legal_moves_kernel<<<grid_for(h->n, kThreads), kThreads, 0, h->stream>>>(h->d_envs, h->n, h->d_u8[0], h->d_lists);
+    XQ_LAUNCH_CHECK();
+    XQ_CUDA(cudaMemcpyAsync(counts_host, h->d_u8[0], (size_t)h->n, cudaMemcpyDeviceToHost, h->stream));
+    XQ_CUDA(cudaMemcpyAsync(actions_host, h->d_lists, sizeof(uint32_t) * 64 * h->n, cudaMemcpyDeviceToHost, h->stream));
+    XQ_CUDA(cudaStreamSynchronize(h->stream));
+    return XQ_OK;
+}
+
+int xq_env_valid_moves(xq_env_t h, int row, int col, uint8_t* counts_host, uint8_t* to_host) {
+    XQ_ENV_ENTER(h);
+    if (!counts_host || !to_host) return fail(XQ_ERR_INVALID, "xq_env_valid_moves: null output");
+    if (!h->d_lists) XQ_CUDA(cudaMalloc(&h->d_lists, sizeof(uint32_t) * 64 * h->n));
+    valid_moves_kernel<<<grid_for(h->n, kThreads), kThreads, 0, h->stream>>>(h->d_envs, h->n, row, col, h->d_u8[0], reinterpret_cast<uint8_t*>(h->d_lists));
+    XQ_LAUNCH_CHECK();
+    XQ_CUDA(cudaMemcpyAsync(counts_host, h->d_u8[0], (size_t)h->n, cudaMemcpyDeviceToHost, h->stream));
+    XQ_CUDA(cudaMemcpyAsync(to_host, h->d_lists, (size_t)20 * h->n, cudaMemcpyDeviceToHost, h->stream));
+    XQ_CUDA(cudaStreamSynchronize(h->stream));
+    return XQ_OK;
+}
+
+int xq_env_is_valid_move(xq_env_t h, const int32_t* moves_host, uint8_t* valid_host) {
+    XQ_ENV_ENTER(h);
+    if (!moves_host || !valid_host) return fail(XQ_ERR_INVALID, "xq_env_is_valid_move: null pointer");
+    XQ_CUDA(cudaMemcpyAsync(h->d_i32, moves_host, sizeof(int32_t) * 4 * h->n, cudaMemcpyHostToDevice, h->stream));
+    is_valid_kernel<<<grid_for(h->n, kThreads), kThreads, 0, h->stream>>>(h->d_envs, h->n, reinterpret_cast<const int4*>(h->d_i32), h->d_u8[0]);
+    XQ_LAUNCH_CHECK();
+    XQ_CUDA(cudaMemcpyAsync(valid_host, h->d_u8[0], (size_t)h->n, cudaMemcpyDeviceToHost, h->stream));
+    XQ_CUDA(cudaStreamSynchronize(h->stream));
+    return XQ_OK;
+}
+
+int xq_env_step(xq_env_t h, const xq_action* actions_host, int32_t* reward_host, uint8_t* done_host, uint8_t* winner_host,
+                uint8_t* captured_host, uint8_t* valid_host, int auto_reset) {
+    XQ_ENV_ENTER(h);
+    if (!actions_host) return fail(XQ_ERR_INVALID, "xq_env_step: null actions");
+    XQ_CUDA(cudaMemcpyAsync(h->d_actions, actions_host, sizeof(uint16_t) * h->n, cudaMemcpyHostToDevice, h->stream));
+    step_kernel<<<grid_for(h->n, kThreads), kThreads, 0, h->stream>>>(h->d_envs, h->n, h->d_actions, h->d_i32, h->d_u8[0], h->d_u8[1],
+                                                                      h->d_u8[2], h->d_u8[3], auto_reset);
+    XQ_LAUNCH_CHECK();
+    if (reward_host) XQ_CUDA(cudaMemcpyAsync(reward_host, h->d_i32, sizeof(int32_t) * h->n, cudaMemcpyDeviceToHost, h->stream));
+    uint8_t* outs[4] = {done_host, winner_host, captured_host, valid_host};
+    for (int i = 0; i < 4; ++i)
+        if (outs[i]) XQ_CUDA(cudaMemcpyAsync(outs[i], h->d_u8[i], (size_t)h->n, cudaMemcpyDeviceToHost, h->stream));
+    XQ_CUDA(cudaStreamSynchronize(h->stream));
+    return XQ_OK;
+}
+
+int xq_env_rollout_random_async(xq_env_t h, int n_plies) {
+    XQ_ENV_ENTER(h);
+    if (n_plies < 0) return fail(XQ_ERR_INVALID, "xq_env_rollout_random_async: n_plies < 0");
+    rollout_random_kernel<<<grid_for(h->n, kThreads), kThreads, 0, h->stream>>>(h->d_envs, h->n, h->env_id0, h->seed, n_plies, nullptr, h->d_stats);
+    XQ_LAUNCH_CHECK();
+    return XQ_OK;
+}
+
+int xq_env_get_stats(xq_env_t h, xq_env_stats* stats_host, int reset) {
+    XQ_ENV_ENTER(h);
+    if (stats_host) XQ_CUDA(cudaMemcpyAsync(stats_host, h->d_stats, sizeof(xq_env_stats), cudaMemcpyDeviceToHost, h->stream));
+    if (reset) XQ_CUDA(cudaMemsetAsync(h->d_stats, 0, sizeof(xq_env_stats), h->stream));
+    XQ_CUDA(cudaStreamSynchronize(h->stream));
+    return XQ_OK;
+}
+
+int xq_env_rollout_random(xq_env_t h, int n_plies, xq_trace_rec* trace_host, xq_env_stats* stats_host) {
+    XQ_ENV_ENTER(h);
+    if (n_plies < 0) return fail(XQ_ERR_INVALID, "xq_env_rollout_random: n_plies < 0");
+    const int64_t need = (int64_t)n_plies * h->n;
+    if (trace_host && need > h->trace_cap) {
+        cudaFree(h->d_trace); h->d_trace = nullptr; h->trace_cap = 0;
+        XQ_CUDA(cudaMalloc(&h->d_trace, sizeof(xq_trace_rec) * need));
+        h->trace_cap = need;
+    }
+    XQ_CUDA(cudaMemsetAsync(h->d_stats, 0, sizeof(xq_env_stats), h->stream));
+    rollout_random_kernel<<<grid_for(h->n, kThreads), kThreads, 0, h->stream>>>(h->d_envs, h->n, h->env_id0, h->seed, n_plies,
+                                                                                trace_host ? h->d_trace : nullptr, h->d_stats);
+    XQ_LAUNCH_CHECK();
+    if (trace_host) XQ_CUDA(cudaMemcpyAsync(trace_host, h->d_trace, sizeof(xq_trace_rec) * need, cudaMemcpyDeviceToHost, h->stream));
+    if (stats_host) XQ_CUDA(cudaMemcpyAsync(stats_host, h->d_stats, sizeof(xq_env_stats), cudaMemcpyDeviceToHost, h->stream));
+    XQ_CUDA(cudaStreamSynchronize(h->stream));
+    return XQ_OK;
+}
+
+int xq_env_state_onehot(xq_env_t h, double* out_host) {
+    XQ_ENV_ENTER(h);
+    if (!out_host) return fail(XQ_ERR_INVALID, "xq_env_state_onehot: null output");
+    if (!h->d_state) XQ_CUDA(cudaMalloc(&h->d_state, sizeof(double) * XQ_STATE_SIZE * h->n));
+    state_onehot_kernel<<<grid_for(32 * h->n, 256), 256, 0, h->stream>>>(h->d_envs, h->n, h->d_state);
+    XQ_LAUNCH_CHECK();
+    XQ_CUDA(cudaMemcpyAsync(out_host, h->d_state, sizeof(double) * XQ_STATE_SIZE * h->n, cudaMemcpyDeviceToHost, h->stream));
+    XQ_CUDA(cudaStreamSynchronize(h->stream));
+    return XQ_OK;
+}
+
+}  // extern "C"

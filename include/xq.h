@@ -1,0 +1,135 @@
+/* xq.h -- C ABI of the B200-native batched Xiangqi environment + DQN trainer.
+ *
+ * This is the drop-in boundary for the self-play training path of Qervas/cn_chess_ai.
+ * The reference has no FFI/plugin interface: its hot path sits behind four C++ headers
+ * (include/chessboard.h, include/action.h, include/chessai.h, include/dqn.h) that
+ * MainWindow/Worker consume directly.  Each entry point below names the reference
+ * member function(s) it replaces (file:line under /root/reference); the Qt-free C++
+ * adapter classes in cn_chess_ai_b200/adapter/ re-expose the original class API
+ * (ChessBoard / Action / ChessAI / DQN) on top of these calls.
+ *
+ * Conventions: extern "C", opaque handles, plain pointers and sizes, int status
+ * (0 = XQ_OK); no exception crosses the boundary; xq_last_error() returns the text of
+ * the last failure on the calling thread.  Pointers named *_host are host memory, the
+ * call copies to/from the device and returns after the result is in the host buffer.
+ * Calls are stream-ordered on the handle's stream (xq_env_set_stream / xq_dqn_set_stream).
+ * There is no CPU fallback: every compute entry point launches sm_100a kernels and
+ * fails with XQ_ERR_CUDA when no device is present.
+ */
+#ifndef XQ_H
+#define XQ_H
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define XQ_ROWS 10
+#define XQ_COLS 9
+#define XQ_SQUARES 90
+#define XQ_STATE_SIZE 1260   /* 90 squares x 14 channels, src/chessai.cpp:268-289,399 */
+#define XQ_MAX_ACTIONS 128   /* hard bound of getAllValidActions is 119 */
+#define XQ_MAX_MOVES 200     /* ChessBoard::maxMovePerGame, include/chessboard.h:63 */
+
+enum { XQ_OK = 0, XQ_ERR_INVALID = 1, XQ_ERR_CUDA = 2, XQ_ERR_NOMEM = 3, XQ_ERR_IO = 4, XQ_ERR_STATE = 5 };
+enum { XQ_RED = 0, XQ_BLACK = 1, XQ_NONE = 2 };  /* PieceColor, include/chessboard.h:12-14 */
+
+/* Packed environment record: the unit of HBM state, 64 B, 64-B aligned.
+ * Replaces ChessBoard's fields (include/chessboard.h:61-64,77-78): QVector<ChessPiece> board,
+ * moveCount, currentPlayer, redScore, blackScore.  Square s = row*9+col is nibble (s&7) of
+ * sq[s>>3]; code 0 empty, 1..7 Red PieceType (General..Soldier, include/chessboard.h:8-10),
+ * 8..14 Black (PieceType+7) = one-hot channel+1 of getStateRepresentation. */
+typedef struct {
+    uint32_t sq[12];
+    uint16_t move_count;
+    uint8_t player;       /* 0 Red, 1 Black */
+    uint8_t flags;        /* reserved, 0 */
+    int32_t red_score;
+    int32_t black_score;
+    uint32_t ctr;         /* plies applied to this env slot since creation: RNG counter */
+} xq_env_rec;
+
+/* Action (include/action.h:4-11) packed as (from<<7)|to, squares 0..89. */
+typedef uint16_t xq_action;
+#define XQ_ACTION(from, to) ((xq_action)(((from) << 7) | (to)))
+#define XQ_ACTION_FROM(a) ((a) >> 7)
+#define XQ_ACTION_TO(a) ((a) & 127)
+#define XQ_ACTION_NONE 0xFFFF
+
+/* One ply of a traced rollout. */
+typedef struct {
+    xq_action action;
+    uint8_t n_legal;   /* size of the ordered action list the action was drawn from */
+    uint8_t flags;     /* bit0 done, bits1-2 winner (PieceColor), bits4-7 captured piece code */
+    int32_t reward;    /* ChessAI::evaluateBoard for the mover, src/chessai.cpp:311-345 */
+} xq_trace_rec;
+
+typedef struct {
+    uint64_t steps, games, red_wins, black_wins, cap_games, captures;
+    int64_t reward_sum;
+    uint64_t legal_sum;
+} xq_env_stats;
+
+typedef struct xq_env_s* xq_env_t;
+
+const char* xq_last_error(void);
+const char* xq_version(void);
+int xq_device_count(int* count);
+
+/* Counter RNG of the framework (the reference is unseedable: std::srand(time) src/chessai.cpp:13,
+ * random_device src/dqn.cu:97).  x = splitmix64-finaliser(seed + env_id*phi + ctr*C);
+ * list index draw = x>>33, explore coin = x & 0x7fffffff (two 31-bit rand() results of
+ * DQN::selectAction, src/dqn.cpp:30-33). */
+uint64_t xq_rng(uint64_t seed, uint64_t env_id, uint32_t ctr);
+/* smallest T such that (double)c/RAND_MAX < eps <=> c < T (src/dqn.cpp:30-31) */
+uint32_t xq_eps_threshold(double eps);
+
+/* ---- batched environment: replaces one ChessBoard + the board-facing half of ChessAI ---- */
+/* n_envs boards on `device`, all at the standard opening (ChessBoard::ChessBoard/initializeBoard,
+ * src/chessboard.cpp:4-29).  env_id0 = global id of env 0 (multi-GPU sharding keeps results
+ * independent of the GPU count). */
+int xq_env_create(int64_t n_envs, int device, uint64_t seed, uint64_t env_id0, xq_env_t* out);
+int xq_env_destroy(xq_env_t h);
+int xq_env_count(xq_env_t h, int64_t* n_envs);
+int xq_env_set_stream(xq_env_t h, void* cuda_stream);
+int xq_env_sync(xq_env_t h);
+/* device address of the xq_env_rec array (for zero-copy consumers, e.g. the Q-network) */
+int xq_env_device_boards(xq_env_t h, void** dev_ptr);
+/* ChessBoard::reset, src/chessboard.cpp:95-102; mask_host[n] != 0 selects, NULL = all */
+int xq_env_reset(xq_env_t h, const uint8_t* mask_host);
+int xq_env_set_boards(xq_env_t h, const xq_env_rec* recs_host, int64_t first, int64_t n);
+int xq_env_get_boards(xq_env_t h, xq_env_rec* recs_host, int64_t first, int64_t n);
+/* ChessAI::getAllValidActions(currentPlayer) for every env, src/chessai.cpp:347-368 over
+ * ChessBoard::getValidMoves + generate*Moves, src/chessboard.cpp:112-283, in reference order.
+ * counts_host[n]; actions_host[n][XQ_MAX_ACTIONS], entries past the count are XQ_ACTION_NONE. */
+int xq_env_legal_moves(xq_env_t h, uint8_t* counts_host, xq_action* actions_host);
+/* ChessBoard::getValidMoves(row,col) for one square of every env (any colour), same order.
+ * to_host[n][20], counts_host[n]. */
+int xq_env_valid_moves(xq_env_t h, int row, int col, uint8_t* counts_host, uint8_t* to_host);
+/* ChessBoard::isValidMove, src/chessboard.cpp:66-93 (+ :328-440): one query per env,
+ * rows/cols may be off-board (=> 0).  moves_host[n][4] = fr,fc,tr,tc. */
+int xq_env_is_valid_move(xq_env_t h, const int32_t* moves_host, uint8_t* valid_host);
+/* ChessBoard::movePiece (src/chessboard.cpp:38-64) + ChessAI::evaluateBoard for the mover with
+ * the post-move moveCount (src/chessai.cpp:115-116,311-345) + checkGameOver (:286-309) +
+ * getWinner (:312-320).  A rejected action changes nothing (valid=0, captured=0).
+ * auto_reset != 0: terminal envs are reset after their outputs are taken (chessai.cpp:90).
+ * Any output pointer may be NULL. */
+int xq_env_step(xq_env_t h, const xq_action* actions_host, int32_t* reward_host, uint8_t* done_host,
+                uint8_t* winner_host, uint8_t* captured_host, uint8_t* valid_host, int auto_reset);
+/* Fused random-policy self-play: n_plies iterations of the ChessAI::train loop body without the
+ * network (src/chessai.cpp:96-119): ordered list -> list[idx31 % n] -> movePiece -> evaluateBoard
+ * -> checkGameOver, reset on terminal.  One launch; boards stay on chip between plies.
+ * trace_host[n_plies][n_envs] and stats_host may be NULL. */
+int xq_env_rollout_random(xq_env_t h, int n_plies, xq_trace_rec* trace_host, xq_env_stats* stats_host);
+/* same, device-resident and asynchronous: no host traffic; stats accumulate on the device */
+int xq_env_rollout_random_async(xq_env_t h, int n_plies);
+int xq_env_get_stats(xq_env_t h, xq_env_stats* stats_host, int reset);
+/* ChessAI::getStateRepresentation, src/chessai.cpp:268-289: out_host[n][1260] doubles */
+int xq_env_state_onehot(xq_env_t h, double* out_host);
+/* number of kernels this library has launched in this process (bench.py's gpu_launches) */
+uint64_t xq_launch_count(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

@@ -151,3 +151,13 @@ def pack_codes(codes):
 def rng_draws(seed, env_id, ctr0, n):
     L = oracle()
     return np.array([L.xqo_rng(seed, env_id, ctr0 + i) for i in range(n)], dtype=np.uint64)
+
+
+def rng_np(seed, env_ids, ctrs):
+    """vectorised xq_rng (numpy uint64 wrap-around arithmetic)"""
+    with np.errstate(over="ignore"):
+        z = (np.uint64(seed) + np.asarray(env_ids, np.uint64) * np.uint64(0x9E3779B97F4A7C15)
+             + np.asarray(ctrs, np.uint64) * np.uint64(0xD1B54A32D192ED03))
+        z = (z ^ (z >> np.uint64(30))) * np.uint64(0xBF58476D1CE4E5B9)
+        z = (z ^ (z >> np.uint64(27))) * np.uint64(0x94D049BB133111EB)
+        return z ^ (z >> np.uint64(31))

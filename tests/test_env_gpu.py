@@ -1,0 +1,221 @@
+"""GPU parity tests (through the C ABI): CUDA env kernels vs the oracle, bit-exact.
+
+Covers BASELINE config 2 (4096 envs random-policy rollouts from the opening: ordered legal list,
+chosen action, next board, moveCount, player, scores, done, winner, reward -- every ply, every env),
+the golden fixtures generated from the unmodified reference, arbitrary injected boards, edge cases
+(rejected moves, terminal boards, masks) and size-independent properties at large N."""
+import numpy as np
+import pytest
+
+from conftest import harvest_positions, random_boards, recs_from_codes
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def xq():
+    import cn_chess_ai_b200 as m
+    return m
+
+
+def oracle_lists(L, recs):
+    n = len(recs)
+    counts = np.zeros(n, np.uint8)
+    acts = np.zeros((n, 128), np.uint16)
+    L.xqo_batch_all_actions(recs.ctypes.data, n, counts, acts)
+    acts[np.arange(128)[None, :] >= counts[:, None]] = 0xFFFF
+    return counts, acts
+
+
+def same_recs(a, b):
+    return a.tobytes() == b.tobytes()
+
+
+def test_create_is_opening(xq, O):
+    env = xq.BatchedEnv(1000, seed=1)
+    got = env.get_boards()
+    assert same_recs(got, O.new_envs(1000))
+    c, a = env.legal_moves()
+    assert (c == 44).all()
+    assert (a[:, 0] == (0 << 7 | 9)).all() and (a[:, 44:] == 0xFFFF).all()
+
+
+def test_golden_positions_and_arbitrary(xq, O, golden):
+    for codes, meta, counts, lists in (
+            (golden["pos_codes"], golden["pos_meta"], golden["pos_counts"], golden["pos_lists"]),
+            (golden["arb_codes"], np.stack([np.zeros(256, np.int32), golden["arb_player"].astype(np.int32), np.zeros(256, np.int32),
+                                            np.zeros(256, np.int32)], 1), golden["arb_counts"], golden["arb_lists"])):
+        recs = recs_from_codes(O, codes, meta)
+        env = xq.BatchedEnv(len(recs))
+        env.set_boards(recs)
+        c, a = env.legal_moves()
+        assert (c == counts).all() and (a == lists).all()
+    # stand-alone predicate, one query per env, off-board queries included
+    recs = recs_from_codes(O, golden["arb_codes"], np.zeros((256, 4), np.int32))
+    env = xq.BatchedEnv(256)
+    env.set_boards(recs)
+    for j in range(golden["arb_q"].shape[1]):
+        v = env.is_valid_move(golden["arb_q"][:, j, :])
+        assert (v == golden["arb_valid"][:, j]).all()
+
+
+def test_golden_traces(xq, O, golden):
+    tr = golden["traces"]
+    n_envs, plies, _ = tr.shape
+    env = xq.BatchedEnv(n_envs, seed=int(golden["seed"]))
+    stats, out = env.rollout_random(plies, trace=True)
+    for e in range(n_envs):
+        assert (out["n_legal"][:, e] == tr[e, :, 0]).all()
+        assert ((out["action"][:, e] >> 7) == tr[e, :, 1]).all() and ((out["action"][:, e] & 127) == tr[e, :, 2]).all()
+        assert (out["reward"][:, e] == tr[e, :, 3]).all()
+        assert ((out["flags"][:, e] & 1) == tr[e, :, 4]).all()
+        assert (((out["flags"][:, e] >> 1) & 3) == tr[e, :, 5]).all()
+    fin = env.get_boards()
+    for e in range(n_envs):
+        assert (O.codes_of(fin[e]) == golden["finals"][e][:90]).all()
+        assert (fin[e]["move_count"], fin[e]["player"], fin[e]["red_score"], fin[e]["black_score"]) == tuple(golden["finals"][e][90:])
+
+
+def test_config2_4096_envs_stepwise(xq, O, oracle_lib):
+    """BASELINE config 2, every ply checked: list -> idx31 % n -> step, 200 plies, auto-reset"""
+    n, plies, seed = 4096, 200, 42
+    env = xq.BatchedEnv(n, seed=seed)
+    ref = O.new_envs(n)
+    ids = np.arange(n, dtype=np.uint64)
+    for p in range(plies):
+        c, a = env.legal_moves()
+        c0, a0 = oracle_lists(oracle_lib, ref)
+        assert (c == c0).all() and (a == a0).all(), f"ply {p}"
+        draws = O.rng_np(seed, ids, ref["ctr"])
+        k = ((draws >> np.uint64(33)).astype(np.uint32) % c).astype(np.int64)
+        chosen = a[np.arange(n), k]
+        rew, done, win, cap, valid = env.step(chosen, auto_reset=True)
+        r0 = np.zeros(n, np.int32)
+        d0, w0, cp0, v0 = (np.zeros(n, np.uint8) for _ in range(4))
+        oracle_lib.xqo_batch_step(ref.ctypes.data, n, chosen, r0, d0, w0, cp0, v0)
+        assert (rew == r0).all() and (done == d0).all() and (win == w0).all() and (cap == cp0).all() and (valid == 1).all()
+        for i in np.nonzero(d0)[0]:
+            oracle_lib.xqo_reset(ref[i:i + 1].ctypes.data)
+        assert same_recs(env.get_boards(), ref), f"ply {p}"
+    assert ref["ctr"].min() == plies
+
+
+def test_config2_fused_rollout_matches_oracle(xq, O, oracle_lib):
+    """the fused kernel: 4096 envs x 200 plies in one launch == oracle trajectories, ply by ply"""
+    n, plies, seed, id0 = 4096, 200, 7, 1000
+    env = xq.BatchedEnv(n, seed=seed, env_id0=id0)
+    stats, tr = env.rollout_random(plies, trace=True)
+    ref = O.new_envs(n)
+    tr0 = np.zeros((plies, n), O.TRACE_DTYPE)
+    st0 = np.zeros(1, O.STATS_DTYPE)
+    oracle_lib.xqo_rollout_random(ref.ctypes.data, n, id0, seed, plies, tr0.ctypes.data, st0.ctypes.data)
+    assert tr.tobytes() == tr0.tobytes()
+    assert same_recs(env.get_boards(), ref)
+    assert stats.tobytes() == st0[0].tobytes()
+    # second launch continues the same trajectories (state + counter carried in HBM)
+    stats2, _ = env.rollout_random(57)
+    oracle_lib.xqo_rollout_random(ref.ctypes.data, n, id0, seed, 57, None, st0.ctypes.data)
+    assert same_recs(env.get_boards(), ref) and stats2.tobytes() == st0[0].tobytes()
+
+
+def test_rollout_from_injected_boards(xq, O, oracle_lib):
+    """mid-game, arbitrary and already-terminal boards as starting points; ragged env count"""
+    recs = np.concatenate([harvest_positions(O, 300, 7, 23), random_boards(O, 601, seed=2)])
+    recs["ctr"] = np.arange(len(recs)) * 3
+    n = len(recs)
+    assert n % 128 != 0
+    env = xq.BatchedEnv(n, seed=5)
+    env.set_boards(recs)
+    stats, tr = env.rollout_random(64, trace=True)
+    ref = recs.copy()
+    tr0 = np.zeros((64, n), O.TRACE_DTYPE)
+    st0 = np.zeros(1, O.STATS_DTYPE)
+    oracle_lib.xqo_rollout_random(ref.ctypes.data, n, 0, 5, 64, tr0.ctypes.data, st0.ctypes.data)
+    bad = np.nonzero((tr.view(np.uint64) != tr0.view(np.uint64)).any(0))[0]
+    assert len(bad) == 0, f"{len(bad)} envs differ, first {bad[:5]}"
+    assert same_recs(env.get_boards(), ref) and stats.tobytes() == st0[0].tobytes()
+
+
+def test_step_rejects_invalid_moves(xq, O, oracle_lib):
+    recs = np.concatenate([harvest_positions(O, 256, 4, 31), random_boards(O, 1024, seed=8)])
+    n = len(recs)
+    rng = np.random.default_rng(0)
+    env = xq.BatchedEnv(n)
+    env.set_boards(recs)
+    ref = recs.copy()
+    for it in range(6):
+        acts = ((rng.integers(0, 92, n) << 7) | rng.integers(0, 92, n)).astype(np.uint16)   # mostly illegal, some off-board
+        c, a = env.legal_moves()
+        pick = rng.random(n) < 0.4
+        k = (rng.integers(0, 1 << 30, n) % np.maximum(c, 1)).astype(np.int64)
+        acts[pick & (c > 0)] = a[np.arange(n), k][pick & (c > 0)]
+        rew, done, win, cap, valid = env.step(acts, auto_reset=False)
+        r0 = np.zeros(n, np.int32)
+        d0, w0, cp0, v0 = (np.zeros(n, np.uint8) for _ in range(4))
+        oracle_lib.xqo_batch_step(ref.ctypes.data, n, acts, r0, d0, w0, cp0, v0)
+        assert (valid == v0).all() and (cap == cp0).all() and (rew == r0).all() and (done == d0).all() and (win == w0).all()
+        assert same_recs(env.get_boards(), ref)
+        assert 0 < valid.sum() < n
+
+
+def test_valid_moves_per_square_and_state(xq, O, oracle_lib):
+    recs = np.concatenate([harvest_positions(O, 128, 3, 40), random_boards(O, 256, seed=12)])
+    n = len(recs)
+    env = xq.BatchedEnv(n)
+    env.set_boards(recs)
+    for sq in list(range(0, 90, 5)) + [89]:
+        c, to = env.valid_moves(sq // 9, sq % 9)
+        for i in range(n):
+            t0 = np.zeros(32, np.uint8)
+            n0 = oracle_lib.xqo_valid_moves(recs[i:i + 1].ctypes.data, sq // 9, sq % 9, t0)
+            assert c[i] == n0 and (to[i, :n0] == t0[:n0]).all()
+    c, _ = env.valid_moves(-1, 3)
+    assert (c == 0).all()
+    st = env.state_onehot()
+    for i in range(0, n, 7):
+        s0 = np.zeros(1260)
+        oracle_lib.xqo_state(recs[i:i + 1].ctypes.data, s0)
+        assert (st[i] == s0).all()
+
+
+def test_reset_mask_and_errors(xq, O):
+    env = xq.BatchedEnv(777, seed=3)
+    env.rollout_random(33)
+    before = env.get_boards()
+    mask = (np.arange(777) % 3 == 0).astype(np.uint8)
+    env.reset(mask)
+    after = env.get_boards()
+    fresh = O.new_envs(1)[0]
+    for i in range(777):
+        if mask[i]:
+            assert after[i]["sq"].tobytes() == fresh["sq"].tobytes() and after[i]["move_count"] == 0 and after[i]["ctr"] == before[i]["ctr"]
+        else:
+            assert after[i].tobytes() == before[i].tobytes()
+    with pytest.raises(xq.XQError):
+        env.set_boards(before, first=5)
+    with pytest.raises(xq.XQError):
+        xq.BatchedEnv(0)
+    with pytest.raises(xq.XQError):
+        xq.BatchedEnv(4, device=99)
+
+
+def test_large_n_properties(xq, O, oracle_lib):
+    """1M envs (BASELINE config 5 size): invariants + an oracle-checked sample of env slots"""
+    n, plies, seed = 1 << 20, 64, 11
+    env = xq.BatchedEnv(n, seed=seed)
+    stats, _ = env.rollout_random(plies)
+    assert stats["steps"] == n * plies
+    recs = env.get_boards()
+    assert (recs["ctr"] == plies).all() and (recs["move_count"] <= 199).all()
+    assert (recs["player"] == recs["move_count"] % 2).all()
+    assert stats["red_wins"] + stats["black_wins"] == stats["games"]
+    idx = np.concatenate([np.arange(0, 300), np.arange(n - 300, n), np.random.default_rng(1).integers(0, n, 400)])
+    for i in idx:
+        ref = O.new_envs(1)
+        st0 = np.zeros(1, O.STATS_DTYPE)
+        oracle_lib.xqo_rollout_random(ref.ctypes.data, 1, int(i), seed, plies, None, st0.ctypes.data)
+        assert ref[0].tobytes() == recs[int(i)].tobytes()
+    # sharding independence: the same global env ids on a differently-offset handle give the same boards
+    env2 = xq.BatchedEnv(1000, seed=seed, env_id0=n - 1000)
+    env2.rollout_random(plies)
+    assert same_recs(env2.get_boards(), recs[n - 1000:])

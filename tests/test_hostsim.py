@@ -1,0 +1,77 @@
+"""CPU suite, part 2: the DEVICE rules source (cn_chess_ai_b200/csrc/xq_rules.cuh), compiled for
+the host by tests/hostsim (test-only, never shipped), diffed against the oracle and the golden
+fixtures.  This is how the kernel logic is proven before any GPU time is spent."""
+import numpy as np
+
+from conftest import harvest_positions, random_boards, recs_from_codes
+
+
+def _lists(H, recs):
+    n = len(recs)
+    counts = np.zeros(n, np.uint8)
+    acts = np.zeros((n, 128), np.uint16)
+    H.hs_all_actions(recs.ctypes.data, n, counts.ctypes.data, acts.ctypes.data)
+    return counts, acts
+
+
+def _oracle_lists(L, recs):
+    n = len(recs)
+    counts = np.zeros(n, np.uint8)
+    acts = np.zeros((n, 128), np.uint16)
+    L.xqo_batch_all_actions(recs.ctypes.data, n, counts, acts)
+    acts[np.arange(128)[None, :] >= counts[:, None]] = 0xFFFF
+    return counts, acts
+
+
+def test_device_rules_reachable_positions(O, oracle_lib, hostsim):
+    recs = harvest_positions(O, 1500, 45, 5)      # 67,500 positions over whole games
+    c1, a1 = _oracle_lists(oracle_lib, recs)
+    c2, a2 = _lists(hostsim, recs)
+    assert (c1 == c2).all() and (a1 == a2).all()
+    assert c1.max() <= 119 and c1.min() >= 1
+
+
+def test_device_rules_arbitrary_boards(O, oracle_lib, hostsim):
+    recs = random_boards(O, 4000, seed=21)
+    c1, a1 = _oracle_lists(oracle_lib, recs)
+    c2, a2 = _lists(hostsim, recs)
+    assert (c1 == c2).all() and (a1 == a2).all()
+    rng = np.random.default_rng(4)
+    for i in range(400):
+        p = recs[i:i + 1].ctypes.data
+        for _ in range(120):
+            q = [int(v) for v in rng.integers(-1, 11, 4)]
+            assert oracle_lib.xqo_is_valid_move(p, *q) == hostsim.hs_is_valid_move(p, *q)
+        for s in range(0, 90, 7):
+            t1 = np.zeros(32, np.uint8)
+            t2 = np.zeros(32, np.uint8)
+            n1 = oracle_lib.xqo_valid_moves(p, s // 9, s % 9, t1)
+            n2 = hostsim.hs_valid_moves(p, s // 9, s % 9, t2.ctypes.data)
+            assert n1 == n2 and (t1[:n1] == t2[:n1]).all()
+
+
+def test_device_rules_golden(O, hostsim, golden):
+    recs = recs_from_codes(O, golden["pos_codes"], golden["pos_meta"])
+    c, a = _lists(hostsim, recs)
+    assert (c == golden["pos_counts"]).all() and (a == golden["pos_lists"]).all()
+    meta = np.zeros((len(golden["arb_codes"]), 4), np.int32)
+    meta[:, 1] = golden["arb_player"]
+    recs = recs_from_codes(O, golden["arb_codes"], meta)
+    c, a = _lists(hostsim, recs)
+    assert (c == golden["arb_counts"]).all() and (a == golden["arb_lists"]).all()
+    for i in range(len(recs)):
+        for q, v in zip(golden["arb_q"][i], golden["arb_valid"][i]):
+            assert hostsim.hs_is_valid_move(recs[i:i + 1].ctypes.data, *[int(x) for x in q]) == v
+
+
+def test_device_scalar_helpers(oracle_lib, hostsim):
+    assert all(hostsim.hs_piece_score(t) == oracle_lib.xqo_piece_score(t) for t in range(8))
+    for s in (0, 1, 2 ** 63 + 5):
+        for e in (0, 1, 99999, 2 ** 40):
+            for c in (0, 1, 2 ** 32 - 1):
+                assert hostsim.hs_rng(s, e, c) == oracle_lib.xqo_rng(s, e, c)
+    for d in range(-2960, 2961, 5):
+        for mc in range(0, 201):
+            num = 10 * d - mc
+            want = int(np.trunc(float(d) - float(mc) * 0.1))
+            assert hostsim.hs_reward(d, mc) == want
