@@ -233,7 +233,7 @@ def main():
     traffic = None
     tp = os.path.join(ROOT, "profiles", "traffic.json")
     if os.path.exists(tp):
-        traffic = json.load(open(tp)).get("rollout_random_kernel_dram_bytes_per_launch")
+        traffic = json.load(open(tp)).get("rollout_slots_kernel_dram_bytes_per_launch")
 
     line = {"metric": "env steps/s (movegen+step, random policy)", "value": value, "unit": "steps/s", "n_gpus": world,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": kernel_ms, "higher_is_better": True, "scaling": "weak",
@@ -246,7 +246,7 @@ def main():
                     "d2h_bytes_per_step": int(recs_out.nbytes) + 64},
             "gpu_launches": int(launches),
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": pk["hbm_gbs"], "unit": "GB/s", "frac": achieved / pk["hbm_gbs"],
-                         "traffic": traffic, "kernel": "rollout_random_kernel", "peak_source": pk["source"],
+                         "traffic": traffic, "kernel": "rollout_slots_kernel", "peak_source": pk["source"],
                          "algorithmic_bytes_per_launch": ALGO_BYTES_PER_STEP * E * P,
                          "note": "integer/latency-bound by design: boards stay on chip for all plies of a launch (DESIGN.md)"},
             "clocks": clocks}

@@ -230,13 +230,13 @@ __device__ __forceinline__ unsigned long long warp_sum(unsigned long long v) {
 
 __global__ void __launch_bounds__(kThreads) rollout_random_kernel(xq_env_rec* __restrict__ envs, int64_t n, uint64_t env_id0,
                                                                  uint64_t seed, int n_plies, xq_trace_rec* __restrict__ trace,
-                                                                 xq_env_stats* __restrict__ stats) {
+                                                                 xq_env_stats* __restrict__ stats, const uint8_t* __restrict__ only) {
     __shared__ uint32_t s_board[12 * kThreads];
     __shared__ uint32_t s_list[64 * kThreads];   // action list, u16 pairs, word-interleaved by thread
     const int tid = threadIdx.x;
     const int64_t env = (int64_t)blockIdx.x * kThreads + tid;
     StatsAcc st{0, 0, 0, 0, 0, 0, 0, 0};
-    if (env < n) {
+    if (env < n && (only == nullptr || only[env] != 0)) {   // `only`: boards the slot kernel could not map
         SmemBoard b{s_board + tid, kThreads};
         b.load(envs + env);
         Meta m; m.load(envs + env);
@@ -321,9 +321,28 @@ struct xq_env_s {
     uint32_t* d_lists = nullptr;      // n*64 words, allocated on first use
     xq_trace_rec* d_trace = nullptr; int64_t trace_cap = 0;
     double* d_state = nullptr;
+    uint8_t* d_nonstd = nullptr;      // n flags written by the slot kernel
+    bool maybe_nonstd = false;        // set once boards were injected (xq_env_set_boards)
 };
 
 static inline unsigned grid_for(int64_t n, int per_block) { return (unsigned)((n + per_block - 1) / per_block); }
+
+namespace xq {
+cudaError_t launch_rollout_slots(xq_env_rec* envs, int64_t n, uint64_t env_id0, uint64_t seed, int n_plies, xq_trace_rec* trace,
+                                 xq_env_stats* stats, uint8_t* nonstd, cudaStream_t stream);
+}
+// Fused rollout = slot-parallel kernel (xq_rollout.cu) for every board with a standard piece set, then the generic
+// thread-per-board kernel for the boards it flagged (only possible after xq_env_set_boards injected exotic positions).
+static int launch_rollout(xq_env_s* h, int n_plies, xq_trace_rec* d_trace) {
+    if (n_plies >= (1 << 24)) return fail(XQ_ERR_INVALID, "rollout: n_plies must be < 2^24 per launch");
+    XQ_CUDA(launch_rollout_slots(h->d_envs, h->n, h->env_id0, h->seed, n_plies, d_trace, h->d_stats, h->d_nonstd, h->stream));
+    if (h->maybe_nonstd) {
+        rollout_random_kernel<<<grid_for(h->n, kThreads), kThreads, 0, h->stream>>>(h->d_envs, h->n, h->env_id0, h->seed, n_plies, d_trace,
+                                                                                    h->d_stats, h->d_nonstd);
+        XQ_LAUNCH_CHECK();
+    }
+    return XQ_OK;
+}
 
 extern "C" {
 
@@ -352,7 +371,7 @@ int xq_env_destroy(xq_env_t h) {
     if (!h) return XQ_OK;
     cudaSetDevice(h->device);
     cudaFree(h->d_envs); cudaFree(h->d_stats); cudaFree(h->d_actions); cudaFree(h->d_i32); cudaFree(h->d_lists);
-    cudaFree(h->d_trace); cudaFree(h->d_state);
+    cudaFree(h->d_trace); cudaFree(h->d_state); cudaFree(h->d_nonstd);
     for (auto p : h->d_u8) cudaFree(p);
     if (h->own_stream && h->stream) cudaStreamDestroy(h->stream);
     delete h;
@@ -375,6 +394,7 @@ int xq_env_create(int64_t n_envs, int device, uint64_t seed, uint64_t env_id0, x
     if (e == cudaSuccess) e = cudaMalloc(&h->d_actions, sizeof(uint16_t) * n_envs);
     if (e == cudaSuccess) e = cudaMalloc(&h->d_i32, sizeof(int32_t) * 4 * n_envs);
     for (auto& p : h->d_u8) if (e == cudaSuccess) e = cudaMalloc(&p, (size_t)n_envs);
+    if (e == cudaSuccess) e = cudaMalloc(&h->d_nonstd, (size_t)n_envs);
     if (e == cudaSuccess) e = cudaMemsetAsync(h->d_stats, 0, sizeof(xq_env_stats), h->stream);
     if (e != cudaSuccess) { xq_env_destroy(h); return fail(XQ_ERR_CUDA, "xq_env_create: %s", cudaGetErrorString(e)); }
     reset_kernel<<<grid_for(4 * n_envs, 256), 256, 0, h->stream>>>(h->d_envs, n_envs, nullptr, 1);
@@ -416,6 +436,7 @@ int xq_env_set_boards(xq_env_t h, const xq_env_rec* recs, int64_t first, int64_t
     if (!recs || first < 0 || n < 0 || first + n > h->n) return fail(XQ_ERR_INVALID, "xq_env_set_boards: range [%lld,+%lld) outside %lld envs", (long long)first, (long long)n, (long long)h->n);
     XQ_CUDA(cudaMemcpyAsync(h->d_envs + first, recs, sizeof(xq_env_rec) * n, cudaMemcpyHostToDevice, h->stream));
     XQ_CUDA(cudaStreamSynchronize(h->stream));
+    h->maybe_nonstd = true;
     return XQ_OK;
 }
 int xq_env_get_boards(xq_env_t h, xq_env_rec* recs, int64_t first, int64_t n) {
@@ -480,8 +501,7 @@ int xq_env_step(xq_env_t h, const xq_action* actions_host, int32_t* reward_host,
 int xq_env_rollout_random_async(xq_env_t h, int n_plies) {
     XQ_ENV_ENTER(h);
     if (n_plies < 0) return fail(XQ_ERR_INVALID, "xq_env_rollout_random_async: n_plies < 0");
-    rollout_random_kernel<<<grid_for(h->n, kThreads), kThreads, 0, h->stream>>>(h->d_envs, h->n, h->env_id0, h->seed, n_plies, nullptr, h->d_stats);
-    XQ_LAUNCH_CHECK();
+    if (int rc = launch_rollout(h, n_plies, nullptr)) return rc;
     return XQ_OK;
 }
 
@@ -503,9 +523,7 @@ int xq_env_rollout_random(xq_env_t h, int n_plies, xq_trace_rec* trace_host, xq_
         h->trace_cap = need;
     }
     XQ_CUDA(cudaMemsetAsync(h->d_stats, 0, sizeof(xq_env_stats), h->stream));
-    rollout_random_kernel<<<grid_for(h->n, kThreads), kThreads, 0, h->stream>>>(h->d_envs, h->n, h->env_id0, h->seed, n_plies,
-                                                                                trace_host ? h->d_trace : nullptr, h->d_stats);
-    XQ_LAUNCH_CHECK();
+    if (int rc = launch_rollout(h, n_plies, trace_host ? h->d_trace : nullptr)) return rc;
     if (trace_host) XQ_CUDA(cudaMemcpyAsync(trace_host, h->d_trace, sizeof(xq_trace_rec) * need, cudaMemcpyDeviceToHost, h->stream));
     if (stats_host) XQ_CUDA(cudaMemcpyAsync(stats_host, h->d_stats, sizeof(xq_env_stats), cudaMemcpyDeviceToHost, h->stream));
     XQ_CUDA(cudaStreamSynchronize(h->stream));

@@ -320,6 +320,7 @@ uint64_t xqo_rng(uint64_t seed, uint64_t env_id, uint32_t ctr) {
  * semantics, :227); train()'s one-ply-early `done` is exposed by the episode driver. */
 static void step_random(xqo_env* e, uint64_t env_id, uint64_t seed, xqo_trace* tr, xqo_stats* st) {
     uint16_t acts[XQO_MAX_ACTIONS];
+    if (xqo_game_over(e)) { uint32_t c = e->ctr; xqo_reset(e); e->ctr = c; }  /* chessai.cpp:90,96: a finished board is never stepped */
     int mover = e->player;
     int n = xqo_all_actions(e, mover, acts);
     if (n == 0) {  /* chessai.cpp:100-103: no action => the episode loop ends; we restart the game */

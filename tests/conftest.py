@@ -44,14 +44,15 @@ def hostsim():
     import ctypes as C
     src = os.path.join(ROOT, "tests", "hostsim", "hostsim.cpp")
     so = os.path.join(ROOT, "tests", "hostsim", "libxq_hostsim.so")
-    hdr = os.path.join(ROOT, "cn_chess_ai_b200", "csrc", "xq_rules.cuh")
-    if not os.path.exists(so) or os.path.getmtime(so) < max(os.path.getmtime(src), os.path.getmtime(hdr)):
+    hdrs = [os.path.join(ROOT, "cn_chess_ai_b200", "csrc", h) for h in ("xq_rules.cuh", "xq_bitboard.cuh")]
+    if not os.path.exists(so) or os.path.getmtime(so) < max([os.path.getmtime(src)] + [os.path.getmtime(h) for h in hdrs]):
         subprocess.run(["g++", "-std=c++17", "-O2", "-fPIC", "-shared", "-Wno-unknown-pragmas", "-o", so, src], check=True)
     H = C.CDLL(so)
     P = C.c_void_p
     H.hs_rng.restype = C.c_uint64
     H.hs_rng.argtypes = [C.c_uint64, C.c_uint64, C.c_uint32]
     H.hs_all_actions.argtypes = [P, C.c_long, P, P]
+    H.hs_bb_all_actions.argtypes = [P, C.c_long, P, P]
     H.hs_valid_moves.argtypes = [P, C.c_int, C.c_int, P]
     H.hs_is_valid_move.argtypes = [P, C.c_int, C.c_int, C.c_int, C.c_int]
     return H

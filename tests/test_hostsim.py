@@ -6,11 +6,11 @@ import numpy as np
 from conftest import harvest_positions, random_boards, recs_from_codes
 
 
-def _lists(H, recs):
+def _lists(H, recs, bitboard=False):
     n = len(recs)
     counts = np.zeros(n, np.uint8)
     acts = np.zeros((n, 128), np.uint16)
-    H.hs_all_actions(recs.ctypes.data, n, counts.ctypes.data, acts.ctypes.data)
+    (H.hs_bb_all_actions if bitboard else H.hs_all_actions)(recs.ctypes.data, n, counts.ctypes.data, acts.ctypes.data)
     return counts, acts
 
 
@@ -75,3 +75,15 @@ def test_device_scalar_helpers(oracle_lib, hostsim):
             num = 10 * d - mc
             want = int(np.trunc(float(d) - float(mc) * 0.1))
             assert hostsim.hs_reward(d, mc) == want
+
+
+def test_bitboard_count_and_decode(O, oracle_lib, hostsim, golden):
+    """xq_bitboard.cuh (slot-parallel rollout kernel): per-piece count + k-th decode == oracle lists"""
+    for recs in (harvest_positions(O, 1500, 45, 5, seed=8), random_boards(O, 6000, seed=33, max_pieces=50)):
+        c1, a1 = _oracle_lists(oracle_lib, recs)
+        c2, a2 = _lists(hostsim, recs, bitboard=True)
+        bad = np.nonzero((c1 != c2) | (a1 != a2).any(1))[0]
+        assert len(bad) == 0, f"{len(bad)} boards differ, first {bad[:4]}"
+    recs = recs_from_codes(O, golden["pos_codes"], golden["pos_meta"])
+    c, a = _lists(hostsim, recs, bitboard=True)
+    assert (c == golden["pos_counts"]).all() and (a == golden["pos_lists"]).all()
