@@ -4,3 +4,4 @@ Host-side mirror of the C ABI in include/xq.h; the hot path lives in csrc/ as ha
 """
 from ._lib import ENV_DTYPE, MAX_ACTIONS, STATE_SIZE, STATS_DTYPE, TRACE_DTYPE, XQError, lib  # noqa: F401
 from .env import BatchedEnv, action  # noqa: F401
+from .dqn import AS_WRITTEN, CORRECTED, DQN  # noqa: F401

@@ -34,6 +34,10 @@ struct Bits90 {
     XQ_HD bool test(int i) const { return (word(i >> 5) >> (i & 31)) & 1u; }
     XQ_HD void set(int i) { const uint32_t b = 1u << (i & 31); const int w = i >> 5; w0 |= w == 0 ? b : 0u; w1 |= w == 1 ? b : 0u; w2 |= w == 2 ? b : 0u; }
     XQ_HD void clear(int i) { const uint32_t b = ~(1u << (i & 31)); const int w = i >> 5; w0 &= w == 0 ? b : ~0u; w1 &= w == 1 ? b : ~0u; w2 &= w == 2 ? b : ~0u; }
+    // single-bit mask of index i spread over the three words (computed once, applied with plain logic ops)
+    static XQ_HD Bits90 bit(int i) { const uint32_t b = 1u << (i & 31); const int w = i >> 5; return Bits90{w == 0 ? b : 0u, w == 1 ? b : 0u, w == 2 ? b : 0u}; }
+    XQ_HD void or_with(const Bits90& m) { w0 |= m.w0; w1 |= m.w1; w2 |= m.w2; }
+    XQ_HD void andnot(const Bits90& m) { w0 &= ~m.w0; w1 &= ~m.w1; w2 &= ~m.w2; }
     // nbits (<= 10) starting at bit pos
     XQ_HD uint32_t field(int pos, int nbits) const {
         const int w = pos >> 5;

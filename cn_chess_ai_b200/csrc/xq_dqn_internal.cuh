@@ -1,0 +1,41 @@
+// xq_dqn_internal.cuh -- the DQN handle shared by the FP64 reference-semantics path (xq_dqn.cu)
+// and the batched BF16 tensor-core path (xq_dqn_fast.cu).
+#pragma once
+#include <cuda_bf16.h>
+
+#include <vector>
+
+#include "xq_common.cuh"
+
+struct xq_dqn_s {
+    std::vector<int> layers;          // layerSizes (include/dqn.h:77)
+    int L = 0;                        // number of weight layers = layers.size()-1
+    std::vector<size_t> wofs, bofs;   // weightOffsets / biasOffsets (src/dqn.cu:125-140)
+    size_t nw = 0, nb = 0;
+    double lr = 0.001, gamma = 0.99;  // include/chessai.h:48-49
+    int device = 0, mode = XQ_DQN_AS_WRITTEN;
+    uint64_t seed = 0;
+    cudaStream_t stream = nullptr;
+    bool own_stream = false;
+
+    // FP64 parameters: online + target (DQN::qNetwork / targetNetwork, include/dqn.h:112-113)
+    double *d_w = nullptr, *d_b = nullptr, *d_tw = nullptr, *d_tb = nullptr;
+    // FP64 scratch: activations / pre-activations / deltas for `cap` samples
+    int64_t cap = 0;
+    size_t act_stride = 0;            // sum of all layer sizes
+    double *d_act = nullptr, *d_z = nullptr, *d_delta = nullptr, *d_target = nullptr, *d_tmp = nullptr;
+    int* d_sel = nullptr;
+    double* d_scalar = nullptr;
+    uint16_t* d_actions = nullptr;
+
+    // which copy of the parameters is current (the two numeric paths keep their own master copy)
+    bool f64_current = true, fast_current = false;
+
+    // ---- batched BF16 path, {1260,128,8100} only (xq_dqn_fast.cu) ----
+    struct Fast* fast = nullptr;
+};
+
+namespace xq {
+int dqn_ensure_f64(xq_dqn_s* h);      // refresh the FP64 parameters from the fast path's FP32 master if it is newer
+void dqn_fast_destroy(xq_dqn_s* h);
+}

@@ -36,6 +36,15 @@ __device__ __forceinline__ Bits90 open_red() { return Bits90{0xAA0801FFu, 0x0000
 __device__ __forceinline__ Bits90 open_black() { return Bits90{0x00000000u, 0x55400000u, 0x03FE0041u}; }
 __device__ __forceinline__ Bits90 open_occT() { return Bits90{0x649A1649u, 0x98064980u, 0x0249A164u}; }
 
+// n % d for n < 2^31, 1 <= d <= 128 without a hardware divide: q = umulhi(n, ceil(2^32/d)) is floor(n/d) or one above
+// (error < n*d/2^32 < 1), so one conditional fix-up makes the remainder exact.
+__device__ __forceinline__ uint32_t mod_small(uint32_t n, uint32_t d) {
+    const uint32_t magic = (0xFFFFFFFFu / d) + 1u;      // ceil(2^32/d) for d not a power of two; 2^32/d for powers of two (d >= 2)
+    const uint32_t q = __umulhi(n, magic);
+    const int32_t r = (int32_t)(n - q * d);
+    return d == 1 ? 0u : (uint32_t)(r < 0 ? r + (int32_t)d : r);
+}
+
 // bytes of qw that are < q (all values <= 127) -> 0xFF, else 0x00
 __device__ __forceinline__ uint32_t bytes_lt(uint32_t qw, uint32_t q) {
     const uint32_t t = (q * 0x01010101u + 0x7F7F7F7Fu) - qw;
@@ -180,7 +189,7 @@ __global__ void __launch_bounds__(kB * kS) rollout_slots_kernel(xq_env_rec* __re
                 z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ull;
                 z = (z ^ (z >> 27)) * 0x94D049BB133111EBull;
                 z ^= z >> 31;
-                const uint32_t k = (uint32_t)(z >> 33) % tot;
+                const uint32_t k = mod_small((uint32_t)(z >> 33), tot);
                 if (cnt > 0 && k >= prefix && k < prefix + (uint32_t)cnt) {
                     int to = 0;
                     piece_moves_dyn(type, P, myq, st.player, (int)(k - prefix), &to);
@@ -203,10 +212,11 @@ __global__ void __launch_bounds__(kB * kS) rollout_slots_kernel(xq_env_rec* __re
             }
             if (myq == from) { if (mover) st.sq_black = to; else st.sq_red = to; }
             const int fr = row_of(from), tr = row_of(to);
-            st.occT.clear(cm_index(fr, from - 9 * fr));
-            st.occT.set(cm_index(tr, to - 9 * tr));
-            if (mover) { st.black.clear(from); st.black.set(to); st.red.clear(to); took_general = to == st.gen_red; if (from == st.gen_black) st.gen_black = to; }
-            else { st.red.clear(from); st.red.set(to); st.black.clear(to); took_general = to == st.gen_black; if (from == st.gen_red) st.gen_red = to; }
+            const Bits90 fm = Bits90::bit(from), tm = Bits90::bit(to);
+            st.occT.andnot(Bits90::bit(cm_index(fr, from - 9 * fr)));
+            st.occT.or_with(Bits90::bit(cm_index(tr, to - 9 * tr)));
+            if (mover) { st.black.andnot(fm); st.black.or_with(tm); st.red.andnot(tm); took_general = to == st.gen_red; if (from == st.gen_black) st.gen_black = to; }
+            else { st.red.andnot(fm); st.red.or_with(tm); st.black.andnot(tm); took_general = to == st.gen_black; if (from == st.gen_red) st.gen_red = to; }
             st.move_count++; st.player ^= 1; st.ctr++;
         }
         __syncthreads();

@@ -126,6 +126,50 @@ int xq_env_rollout_random_async(xq_env_t h, int n_plies);
 int xq_env_get_stats(xq_env_t h, xq_env_stats* stats_host, int reset);
 /* ChessAI::getStateRepresentation, src/chessai.cpp:268-289: out_host[n][1260] doubles */
 int xq_env_state_onehot(xq_env_t h, double* out_host);
+
+/* ---- DQN: replaces DQN (include/dqn.h:97-116, src/dqn.cpp) + NeuralNetwork (include/dqn.h:43-95, src/dqn.cu) ----
+ * Parameters use the reference layout (src/dqn.cu:112-140): weights = layer after layer, each [out][in]
+ * row-major; biases = layer after layer.
+ * Two numeric paths:
+ *  (1) FP64, any layer sizes, per-sample semantics identical to the reference's kernels: xq_dqn_forward,
+ *      xq_dqn_backprop, xq_dqn_select_action, xq_dqn_train.  Tolerance vs the reference: 1e-12 abs
+ *      (summation order and FMA contraction differ in the last ulps).
+ *  (2) batched BF16 tensor-core path for the {1260,128,8100} self-play network, fed by packed boards:
+ *      xq_dqn_forward_boards, xq_dqn_act, xq_dqn_td_update.  FP32 master weights, BF16 MMA operands, FP32
+ *      accumulation.  Tolerance vs the FP64 oracle: |dQ| <= 2e-3 abs. */
+typedef struct xq_dqn_s* xq_dqn_t;
+enum { XQ_DQN_AS_WRITTEN = 0, XQ_DQN_CORRECTED = 1 };   /* hidden-layer delta: src/dqn.cu:406-427 as written, or W^T.delta */
+
+/* NeuralNetwork::NeuralNetwork + initializeHostWeightsAndBiases (src/dqn.cu:14-57,96-146): W ~ U(-0.05,0.05) from
+ * mt19937(seed) (the reference seeds from random_device), b = 0; DQN::DQN (src/dqn.cpp:12-20) copies it to the target. */
+int xq_dqn_create(const int32_t* layer_sizes, int n_layers, double lr, double gamma, int device, uint64_t seed, int mode,
+                  xq_dqn_t* out);
+int xq_dqn_destroy(xq_dqn_t h);
+int xq_dqn_set_stream(xq_dqn_t h, void* cuda_stream);
+int xq_dqn_sync(xq_dqn_t h);
+int xq_dqn_num_params(xq_dqn_t h, int64_t* n_weights, int64_t* n_biases);
+/* host_weights / host_biases + copyToDevice (src/dqn.cu:480-485); also refreshes the target network like DQN::DQN */
+int xq_dqn_set_params(xq_dqn_t h, const double* weights_host, const double* biases_host);
+/* copyFromDevice (src/dqn.cu:487-492): the TRAINED parameters (the reference never calls it) */
+int xq_dqn_get_params(xq_dqn_t h, double* weights_host, double* biases_host);
+/* DQN::getQValues -> NeuralNetwork::forward (src/dqn.cpp:65-68, src/dqn.cu:184-260) for n states: q_host[n][out] */
+int xq_dqn_forward(xq_dqn_t h, const double* states_host, int64_t n, double* q_host);
+/* DQN::backpropagate -> NeuralNetwork::backpropagate (src/dqn.cpp:59-62, src/dqn.cu:275-467): n SEQUENTIAL SGD steps */
+int xq_dqn_backprop(xq_dqn_t h, const double* states_host, const double* targets_host, int64_t n, double lr);
+/* DQN::selectAction (src/dqn.cpp:24-56) with its two rand() results supplied (coin31, idx31); *index_out = list index */
+int xq_dqn_select_action(xq_dqn_t h, const double* state_host, double eps, const xq_action* actions_host, int n_actions,
+                         uint32_t coin31, uint32_t idx31, int* index_out);
+/* one TD step on (s, a, r, s', done): target = Q(s); target[a] = done ? r : r + gamma * max Q'(s'); backprop(s, target).
+ * use_target_net = 0: bootstrap from the online net = the live loop ChessAI::train (src/chessai.cpp:121-131);
+ * use_target_net = 1: DQN::train (src/dqn.cpp:157-172).  lr <= 0 uses the handle's learning rate. */
+int xq_dqn_train(xq_dqn_t h, const double* state_host, int action_index, double reward, const double* next_state_host,
+                 int done, int use_target_net, double lr);
+/* DQN::updateTargetNetwork (src/dqn.cpp:71-73); copies the live device weights (the evident intent) */
+int xq_dqn_sync_target(xq_dqn_t h);
+/* DQN::saveModel / loadModel byte layout (src/dqn.cpp:76-154): raw f64 weights | raw f64 biases | BE u64 n | n x BE i32 */
+int xq_dqn_save(xq_dqn_t h, const char* path);
+int xq_dqn_load(xq_dqn_t h, const char* path);
+
 /* number of kernels this library has launched in this process (bench.py's gpu_launches) */
 uint64_t xq_launch_count(void);
 

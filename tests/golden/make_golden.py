@@ -103,7 +103,7 @@ def rules():
 
 def nn_cases(rng):
     cases = []
-    for layers in ([1260, 128, 8100], [30, 8, 12]):
+    for layers in ([1260, 128, 8100], [12, 8, 30]):
         nw = sum(layers[i] * layers[i + 1] for i in range(len(layers) - 1))
         nb = sum(layers[1:])
         w = rng.uniform(-0.05, 0.05, nw)
