@@ -2,6 +2,8 @@
 
 Host-side mirror of the C ABI in include/xq.h; the hot path lives in csrc/ as hand-written CUDA.
 """
-from ._lib import ENV_DTYPE, MAX_ACTIONS, STATE_SIZE, STATS_DTYPE, TRACE_DTYPE, XQError, lib  # noqa: F401
+from ._lib import (ENV_DTYPE, MAX_ACTIONS, STATE_SIZE, STATS_DTYPE, TRACE_DTYPE, TRANSITION_DTYPE, XQError,  # noqa: F401
+                   lib)
 from .env import BatchedEnv, action  # noqa: F401
 from .dqn import AS_WRITTEN, CORRECTED, DQN  # noqa: F401
+from .replay import ReplayBuffer, act, collect, td_update_replay  # noqa: F401

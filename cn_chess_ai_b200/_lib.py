@@ -15,6 +15,9 @@ ENV_DTYPE = np.dtype([("sq", "<u4", (12,)), ("move_count", "<u2"), ("player", "u
 TRACE_DTYPE = np.dtype([("action", "<u2"), ("n_legal", "u1"), ("flags", "u1"), ("reward", "<i4")])
 STATS_DTYPE = np.dtype([("steps", "<u8"), ("games", "<u8"), ("red_wins", "<u8"), ("black_wins", "<u8"),
                         ("cap_games", "<u8"), ("captures", "<u8"), ("reward_sum", "<i8"), ("legal_sum", "<u8")])
+TRANSITION_DTYPE = np.dtype([("s", "<u4", (12,)), ("s2", "<u4", (12,)), ("action", "<u2"), ("mover", "u1"), ("done", "u1"),
+                             ("reward", "<i4"), ("reserved", "<u4", (6,))])
+assert TRANSITION_DTYPE.itemsize == 128
 MAX_ACTIONS = 128
 STATE_SIZE = 1260
 

@@ -31,6 +31,10 @@ extern unsigned long long g_launches;   // kernels launched by this library (xq_
             return ::xq::fail(XQ_ERR_CUDA, "kernel launch failed: %s (%s:%d)", cudaGetErrorString(e_), __FILE__, __LINE__); \
     } while (0)
 
+// ---- cross-module accessors (handles are opaque outside their own translation unit) ------------
+struct EnvInfo { int64_t n; int device; uint64_t seed, env_id0; cudaStream_t stream; xq_env_rec* d_envs; xq_env_stats* d_stats; };
+int env_info(xq_env_t h, EnvInfo* out);
+
 // ---- device helpers ---------------------------------------------------------------------------
 #if defined(__CUDACC__)
 // One board per thread in shared memory, word-interleaved: word w of thread t lives at

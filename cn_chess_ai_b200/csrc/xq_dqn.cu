@@ -301,6 +301,7 @@ int xq_dqn_sync_target(xq_dqn_t h) {
     if (int rc = dqn_ensure_f64(h)) return rc;
     XQ_CUDA(cudaMemcpyAsync(h->d_tw, h->d_w, sizeof(double) * h->nw, cudaMemcpyDeviceToDevice, h->stream));
     XQ_CUDA(cudaMemcpyAsync(h->d_tb, h->d_b, sizeof(double) * h->nb, cudaMemcpyDeviceToDevice, h->stream));
+    dqn_target_changed(h);
     return XQ_OK;
 }
 

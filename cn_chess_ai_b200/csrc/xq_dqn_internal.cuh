@@ -7,6 +7,8 @@
 
 #include "xq_common.cuh"
 
+namespace xq { struct Fast; }
+
 struct xq_dqn_s {
     std::vector<int> layers;          // layerSizes (include/dqn.h:77)
     int L = 0;                        // number of weight layers = layers.size()-1
@@ -32,10 +34,13 @@ struct xq_dqn_s {
     bool f64_current = true, fast_current = false;
 
     // ---- batched BF16 path, {1260,128,8100} only (xq_dqn_fast.cu) ----
-    struct Fast* fast = nullptr;
+    xq::Fast* fast = nullptr;
 };
 
 namespace xq {
 int dqn_ensure_f64(xq_dqn_s* h);      // refresh the FP64 parameters from the fast path's FP32 master if it is newer
 void dqn_fast_destroy(xq_dqn_s* h);
+void dqn_target_changed(xq_dqn_s* h);
+struct FastWeights { const float *W0T, *b0, *W1, *b1; };
+int dqn_fast_weights(xq_dqn_s* h, FastWeights* out);   // brings the FP32 copies up to date and returns them   // the FP64 target parameters were rewritten
 }

@@ -1,0 +1,365 @@
+// xq_selfplay.cu -- GPU-resident replay buffer, batched epsilon-greedy action selection and the
+// self-play collection loop (BASELINE configs 3 and 4).
+//
+// Reference semantics per transition = the body of ChessAI::train (src/chessai.cpp:96-131):
+//   validActions = getAllValidActions(player)           (:98,  :347-368)
+//   a = dqn->selectAction(state, 0.1, validActions)      (:106, src/dqn.cpp:24-56)
+//   movePiece; reward = evaluateBoard(mover, moveCount)  (:113-116)
+//   done = checkGameOver() || moveCount+1 >= 200         (:119)
+// The reference then trains on that single transition at once; here it is appended to a replay ring in
+// HBM and consumed in batches by the tensor-core TD update (xq_dqn_fast.cu).
+// Q(s)[to] only needs outputs 0..89 of layer 1 (src/dqn.cpp:47 indexes by action.to), so acting costs a
+// <=32-row gather for layer 0 plus 90 dot products of length 128 per env, all in FP32.
+#include <algorithm>
+
+#include "xq_dqn_internal.cuh"
+#include "xq_env_dev.cuh"
+
+namespace xq {
+
+constexpr int kHidden = 128, kQ = 90, kQPad = 96, kInputs = XQ_STATE_SIZE;
+
+struct Transition {
+    uint32_t s[12], s2[12];
+    uint16_t action; uint8_t mover, done;
+    int32_t reward;
+    uint32_t pad[6];
+};
+static_assert(sizeof(Transition) == sizeof(xq_transition), "transition layout");
+
+// Q(s)[0..89] for every env: one warp per env.  Layer 0 = gather-sum of W0^T rows (lane owns 4 hidden units),
+// h staged in shared memory, then lane r computes outputs r, r+32, r+64 from the (L1-resident) first 90 rows of W1.
+__global__ void __launch_bounds__(256) q90_kernel(const xq_env_rec* __restrict__ envs, int64_t n, const float* __restrict__ W0T,
+                                                 const float* __restrict__ b0, const float* __restrict__ W1, const float* __restrict__ b1,
+                                                 float* __restrict__ q90) {
+    __shared__ float s_h[8][kHidden];
+    const int64_t e = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
+    if (e >= n) return;
+    const uint32_t word = lane < 12 ? envs[e].sq[lane] : 0u;
+    float4 acc = reinterpret_cast<const float4*>(b0)[lane];
+    for (int wi = 0; wi < 12; ++wi) {
+        uint32_t v = __shfl_sync(0xFFFFFFFFu, word, wi);
+        while (v) {
+            const int nib = (__ffs((int)v) - 1) >> 2;
+            const int code = (v >> (4 * nib)) & 15;
+            v &= ~(15u << (4 * nib));
+            const int row = (wi * 8 + nib) * 14 + code - 1;
+            if (code < 15 && row < kInputs) {
+                const float4 r = reinterpret_cast<const float4*>(W0T + (size_t)row * kHidden)[lane];
+                acc.x += r.x; acc.y += r.y; acc.z += r.z; acc.w += r.w;
+            }
+        }
+    }
+    reinterpret_cast<float4*>(s_h[wib])[lane] = make_float4(tanhf(acc.x), tanhf(acc.y), tanhf(acc.z), tanhf(acc.w));
+    __syncwarp();
+#pragma unroll
+    for (int k = 0; k < 3; ++k) {
+        const int r = lane + 32 * k;
+        float q = 0.0f;
+        if (r < kQ) {
+            const float4* w = reinterpret_cast<const float4*>(W1 + (size_t)r * kHidden);
+            float z = 0.0f;
+#pragma unroll 8
+            for (int j = 0; j < kHidden / 4; ++j) {
+                const float4 a = w[j];
+                const float4 h = reinterpret_cast<const float4*>(s_h[wib])[j];
+                z += a.x * h.x + a.y * h.y + a.z * h.z + a.w * h.w;
+            }
+            q = tanhf(z + b1[r]);
+        }
+        q90[e * kQPad + r] = q;
+    }
+}
+
+// Action selection (+ optional application) for every env: one thread per board, ordered list staged in shared memory.
+template <bool APPLY>
+__global__ void __launch_bounds__(kThreads) act_kernel(xq_env_rec* __restrict__ envs, int64_t n, uint64_t env_id0, uint64_t seed,
+                                                      const float* __restrict__ q90, uint32_t eps_thr, int train_done,
+                                                      uint16_t* __restrict__ actions_out, Transition* __restrict__ ring, int64_t ring_cap,
+                                                      int64_t ring_pos, xq_env_stats* __restrict__ stats) {
+    __shared__ uint32_t s_board[12 * kThreads];
+    __shared__ uint32_t s_list[64 * kThreads];
+    const int tid = threadIdx.x;
+    const int64_t env = (int64_t)blockIdx.x * kThreads + tid;
+    unsigned long long a_steps = 0, a_games = 0, a_red = 0, a_black = 0, a_capg = 0, a_caps = 0, a_legal = 0;
+    long long a_reward = 0;
+    if (env < n) {
+        SmemBoard b{s_board + tid, kThreads};
+        b.load(envs + env);
+        Meta m; m.load(envs + env);
+        Summary s = summarize(b);
+        if (APPLY && (m.move_count >= XQ_MAX_MOVES || !(s.red_alive && s.black_alive))) { reset_board(b); m.reset(); s = summarize(b); }
+        uint16_t* list = reinterpret_cast<uint16_t*>(s_list);
+        int cnt = 0;
+        all_actions(b, m.player, [&](int from, int to) {
+            if (cnt < XQ_MAX_ACTIONS) { list[(cnt >> 1) * 2 * kThreads + 2 * tid + (cnt & 1)] = XQ_ACTION(from, to); ++cnt; }
+        });
+        int a = XQ_ACTION_NONE;
+        if (cnt > 0) {
+            const uint64_t x = rng(seed, env_id0 + (uint64_t)env, m.ctr);
+            const uint32_t coin31 = (uint32_t)(x & 0x7FFFFFFFu), idx31 = (uint32_t)(x >> 33);
+            int k = 0;
+            if (coin31 < eps_thr) {                                     // rand()/RAND_MAX < epsilon (src/dqn.cpp:30-34)
+                k = (int)(idx31 % (uint32_t)cnt);
+            } else {                                                    // first valid action maximising Q[action.to] (:39-52)
+                const float* q = q90 + env * kQPad;
+                float best = -INFINITY;
+                for (int i = 0; i < cnt; ++i) {
+                    const float v = q[XQ_ACTION_TO(list[(i >> 1) * 2 * kThreads + 2 * tid + (i & 1)])];
+                    if (v > best) { best = v; k = i; }
+                }
+            }
+            a = list[(k >> 1) * 2 * kThreads + 2 * tid + (k & 1)];
+        }
+        if (actions_out) actions_out[env] = (uint16_t)a;
+        if (APPLY) {
+            Transition t;
+#pragma unroll
+            for (int i = 0; i < 12; ++i) t.s[i] = b.base[i * kThreads];
+            t.mover = (uint8_t)m.player;
+            if (cnt == 0) {   // no action: the episode loop ends (chessai.cpp:100-103); recorded as a terminal null transition
+                t.action = 0; t.done = 1; t.reward = 0;
+#pragma unroll
+                for (int i = 0; i < 12; ++i) t.s2[i] = t.s[i];
+                reset_board(b); m.reset(); m.ctr++; a_games++;
+            } else {
+                const int mover = m.player;
+                const int cap = apply_move(b, m, XQ_ACTION_FROM(a), XQ_ACTION_TO(a));
+                m.ctr++;
+                int mat_red = s.mat_red, mat_black = s.mat_black;
+                if (cap != 0) { const int sc = piece_score(type_of(cap)); if (cap >= 8) mat_black -= sc; else mat_red -= sc; a_caps++; }
+                const int reward = reward_from_material(mover == RED ? mat_red - mat_black : mat_black - mat_red, m.move_count);
+                bool over = m.move_count >= XQ_MAX_MOVES;
+                int win = NOCOLOR;
+                if (over || type_of(cap) == GENERAL) { const Summary e2 = summarize(b); over = over || !(e2.red_alive && e2.black_alive); win = e2.winner; }
+#pragma unroll
+                for (int i = 0; i < 12; ++i) t.s2[i] = b.base[i * kThreads];
+                t.action = (uint16_t)a; t.reward = reward;
+                t.done = (uint8_t)((over || (train_done && m.move_count + 1 >= XQ_MAX_MOVES)) ? 1 : 0);     // chessai.cpp:119 / :227
+                a_steps++; a_legal += cnt; a_reward += reward;
+                if (over) {
+                    a_games++;
+                    if (win == RED) a_red++; else if (win == BLACK) a_black++;
+                    if (m.move_count < XQ_MAX_MOVES) a_capg++;
+                    reset_board(b); m.reset();
+                }
+            }
+            if (ring) {
+#pragma unroll
+                for (int i = 0; i < 6; ++i) t.pad[i] = 0;
+                uint4* dst = reinterpret_cast<uint4*>(ring + (ring_pos + env) % ring_cap);
+                const uint4* src = reinterpret_cast<const uint4*>(&t);
+#pragma unroll
+                for (int i = 0; i < 8; ++i) dst[i] = src[i];
+            }
+            b.store(envs + env);
+            m.store(envs + env);
+        }
+    }
+    if (APPLY && stats) {
+        unsigned long long v[8] = {a_steps, a_games, a_red, a_black, a_capg, a_caps, (unsigned long long)a_reward, a_legal};
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+            unsigned long long r = v[i];
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) r += __shfl_xor_sync(0xFFFFFFFFu, r, o);
+            if ((tid & 31) == 0 && r != 0) atomicAdd(reinterpret_cast<unsigned long long*>(stats) + i, r);
+        }
+    }
+}
+
+// uniform sampling with replacement: warp per sample copies one 128-byte record
+__global__ void __launch_bounds__(256) sample_kernel(const Transition* __restrict__ ring, int64_t size, int64_t batch, uint64_t seed,
+                                                    uint32_t counter, Transition* __restrict__ out, int64_t* __restrict__ index_out) {
+    const int64_t i = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int lane = threadIdx.x & 31;
+    if (i >= batch) return;
+    const int64_t idx = (int64_t)((rng(seed, (uint64_t)i, counter) >> 1) % (uint64_t)size);
+    if (lane < 8) reinterpret_cast<uint4*>(out + i)[lane] = reinterpret_cast<const uint4*>(ring + idx)[lane];
+    if (lane == 0 && index_out) index_out[i] = idx;
+}
+
+}  // namespace xq
+
+using namespace xq;
+
+struct xq_replay_s {
+    int64_t capacity = 0, total = 0;      // total transitions ever inserted; head = total % capacity
+    int device = 0;
+    Transition* d_ring = nullptr;
+    Transition* d_batch = nullptr; int64_t batch_cap = 0;
+    int64_t* d_index = nullptr;
+    cudaStream_t stream = nullptr;        // for the host-pointer entry points
+    cudaEvent_t ev = nullptr;
+};
+
+struct SelfplayScratch { float* q90 = nullptr; int64_t cap = 0; uint16_t* actions = nullptr; };
+static SelfplayScratch& scratch_for(int device) { static SelfplayScratch s[64]; return s[device & 63]; }
+
+static inline unsigned blocks(int64_t n, int per) { return (unsigned)((n + per - 1) / per); }
+static int reserve_scratch(int device, int64_t n, SelfplayScratch** out) {
+    SelfplayScratch& s = scratch_for(device);
+    if (n > s.cap) {
+        cudaFree(s.q90); cudaFree(s.actions); s.q90 = nullptr; s.actions = nullptr; s.cap = 0;
+        XQ_CUDA(cudaMalloc(&s.q90, sizeof(float) * kQPad * n));
+        XQ_CUDA(cudaMalloc(&s.actions, sizeof(uint16_t) * n));
+        s.cap = n;
+    }
+    *out = &s;
+    return XQ_OK;
+}
+// make `waiter` see everything already enqueued on `producer`
+static int order_after(cudaStream_t waiter, cudaStream_t producer, cudaEvent_t* ev) {
+    if (waiter == producer) return XQ_OK;
+    if (!*ev) XQ_CUDA(cudaEventCreateWithFlags(ev, cudaEventDisableTiming));
+    XQ_CUDA(cudaEventRecord(*ev, producer));
+    XQ_CUDA(cudaStreamWaitEvent(waiter, *ev, 0));
+    return XQ_OK;
+}
+static cudaEvent_t g_ev[64];
+
+extern "C" {
+
+int xq_replay_destroy(xq_replay_t r) {
+    if (!r) return XQ_OK;
+    cudaSetDevice(r->device);
+    cudaFree(r->d_ring); cudaFree(r->d_batch); cudaFree(r->d_index);
+    if (r->stream) cudaStreamDestroy(r->stream);
+    if (r->ev) cudaEventDestroy(r->ev);
+    delete r;
+    return XQ_OK;
+}
+
+int xq_replay_create(int64_t capacity, int device, xq_replay_t* out) {
+    if (!out || capacity <= 0) return fail(XQ_ERR_INVALID, "xq_replay_create: capacity must be > 0");
+    int ndev = 0;
+    XQ_CUDA(cudaGetDeviceCount(&ndev));
+    if (device < 0 || device >= ndev) return fail(XQ_ERR_INVALID, "xq_replay_create: device %d out of range", device);
+    XQ_CUDA(cudaSetDevice(device));
+    xq_replay_s* r = new (std::nothrow) xq_replay_s();
+    if (!r) return fail(XQ_ERR_NOMEM, "xq_replay_create: out of host memory");
+    r->capacity = capacity; r->device = device;
+    cudaError_t e = cudaMalloc(&r->d_ring, sizeof(Transition) * capacity);
+    if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&r->stream, cudaStreamNonBlocking);
+    if (e == cudaSuccess) e = cudaMemsetAsync(r->d_ring, 0, sizeof(Transition) * capacity, r->stream);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(r->stream);
+    if (e != cudaSuccess) { xq_replay_destroy(r); return fail(e == cudaErrorMemoryAllocation ? XQ_ERR_NOMEM : XQ_ERR_CUDA, "xq_replay_create: %s", cudaGetErrorString(e)); }
+    *out = r;
+    return XQ_OK;
+}
+
+int xq_replay_info(xq_replay_t r, int64_t* size, int64_t* capacity, int64_t* total) {
+    if (!r) return fail(XQ_ERR_INVALID, "xq_replay_info: null handle");
+    if (size) *size = r->total < r->capacity ? r->total : r->capacity;
+    if (capacity) *capacity = r->capacity;
+    if (total) *total = r->total;
+    return XQ_OK;
+}
+
+int xq_replay_insert(xq_replay_t r, const xq_transition* batch, int64_t n) {
+    if (!r || !batch || n < 0) return fail(XQ_ERR_INVALID, "xq_replay_insert: bad arguments");
+    XQ_CUDA(cudaSetDevice(r->device));
+    XQ_CUDA(cudaDeviceSynchronize());     // host-pointer convenience path: order against any stream that touched the ring
+    int64_t done = 0;
+    while (done < n) {
+        const int64_t head = (r->total + done) % r->capacity;
+        const int64_t m = std::min(n - done, r->capacity - head);
+        XQ_CUDA(cudaMemcpyAsync(r->d_ring + head, batch + done, sizeof(Transition) * m, cudaMemcpyHostToDevice, r->stream));
+        done += m;
+    }
+    XQ_CUDA(cudaStreamSynchronize(r->stream));
+    r->total += n;
+    return XQ_OK;
+}
+
+int xq_replay_get(xq_replay_t r, int64_t first, int64_t n, xq_transition* out) {
+    if (!r || !out || first < 0 || n < 0 || first + n > r->capacity) return fail(XQ_ERR_INVALID, "xq_replay_get: bad range");
+    XQ_CUDA(cudaSetDevice(r->device));
+    XQ_CUDA(cudaDeviceSynchronize());
+    XQ_CUDA(cudaMemcpy(out, r->d_ring + first, sizeof(Transition) * n, cudaMemcpyDeviceToHost));
+    return XQ_OK;
+}
+
+static int replay_sample_dev(xq_replay_t r, int64_t batch, uint64_t seed, uint32_t counter, cudaStream_t stream, bool want_index) {
+    const int64_t size = r->total < r->capacity ? r->total : r->capacity;
+    if (size <= 0) return fail(XQ_ERR_STATE, "xq_replay_sample: the buffer is empty");
+    if (batch > r->batch_cap) {
+        cudaFree(r->d_batch); cudaFree(r->d_index); r->d_batch = nullptr; r->d_index = nullptr; r->batch_cap = 0;
+        XQ_CUDA(cudaMalloc(&r->d_batch, sizeof(Transition) * batch));
+        XQ_CUDA(cudaMalloc(&r->d_index, sizeof(int64_t) * batch));
+        r->batch_cap = batch;
+    }
+    sample_kernel<<<blocks(batch * 32, 256), 256, 0, stream>>>(r->d_ring, size, batch, seed, counter, r->d_batch, want_index ? r->d_index : nullptr);
+    XQ_LAUNCH_CHECK();
+    return XQ_OK;
+}
+
+int xq_replay_sample(xq_replay_t r, int64_t batch, uint64_t seed, uint32_t counter, xq_transition* out, int64_t* index) {
+    if (!r || batch <= 0) return fail(XQ_ERR_INVALID, "xq_replay_sample: bad arguments");
+    XQ_CUDA(cudaSetDevice(r->device));
+    XQ_CUDA(cudaDeviceSynchronize());
+    if (int rc = replay_sample_dev(r, batch, seed, counter, r->stream, true)) return rc;
+    if (out) XQ_CUDA(cudaMemcpyAsync(out, r->d_batch, sizeof(Transition) * batch, cudaMemcpyDeviceToHost, r->stream));
+    if (index) XQ_CUDA(cudaMemcpyAsync(index, r->d_index, sizeof(int64_t) * batch, cudaMemcpyDeviceToHost, r->stream));
+    XQ_CUDA(cudaStreamSynchronize(r->stream));
+    return XQ_OK;
+}
+
+int xq_dqn_act(xq_dqn_t h, xq_env_t env, double eps, xq_action* actions_host, float* q_host) {
+    if (!h || !env || !actions_host) return fail(XQ_ERR_INVALID, "xq_dqn_act: null argument");
+    EnvInfo ei;
+    if (int rc = env_info(env, &ei)) return rc;
+    if (ei.device != h->device) return fail(XQ_ERR_INVALID, "xq_dqn_act: env and network live on different devices");
+    XQ_CUDA(cudaSetDevice(h->device));
+    FastWeights fw;
+    if (int rc = dqn_fast_weights(h, &fw)) return rc;
+    SelfplayScratch* sc;
+    if (int rc = reserve_scratch(h->device, ei.n, &sc)) return rc;
+    if (int rc = order_after(ei.stream, h->stream, &g_ev[h->device & 63])) return rc;
+    q90_kernel<<<blocks(ei.n * 32, 256), 256, 0, ei.stream>>>(ei.d_envs, ei.n, fw.W0T, fw.b0, fw.W1, fw.b1, sc->q90);
+    XQ_LAUNCH_CHECK();
+    act_kernel<false><<<blocks(ei.n, kThreads), kThreads, 0, ei.stream>>>(ei.d_envs, ei.n, ei.env_id0, ei.seed, sc->q90, xq_eps_threshold(eps), 0,
+                                                                         sc->actions, nullptr, 1, 0, nullptr);
+    XQ_LAUNCH_CHECK();
+    XQ_CUDA(cudaMemcpyAsync(actions_host, sc->actions, sizeof(uint16_t) * ei.n, cudaMemcpyDeviceToHost, ei.stream));
+    if (q_host) XQ_CUDA(cudaMemcpyAsync(q_host, sc->q90, sizeof(float) * kQPad * ei.n, cudaMemcpyDeviceToHost, ei.stream));
+    XQ_CUDA(cudaStreamSynchronize(ei.stream));
+    return XQ_OK;
+}
+
+int xq_selfplay_collect(xq_dqn_t h, xq_env_t env, xq_replay_t r, int n_plies, double eps, int train_done) {
+    if (!h || !env || n_plies < 0) return fail(XQ_ERR_INVALID, "xq_selfplay_collect: bad arguments");
+    EnvInfo ei;
+    if (int rc = env_info(env, &ei)) return rc;
+    if (ei.device != h->device || (r && r->device != h->device)) return fail(XQ_ERR_INVALID, "xq_selfplay_collect: handles live on different devices");
+    XQ_CUDA(cudaSetDevice(h->device));
+    FastWeights fw;
+    if (int rc = dqn_fast_weights(h, &fw)) return rc;
+    SelfplayScratch* sc;
+    if (int rc = reserve_scratch(h->device, ei.n, &sc)) return rc;
+    if (int rc = order_after(ei.stream, h->stream, &g_ev[h->device & 63])) return rc;    // see the latest weights
+    xq_env_stats* d_stats = ei.d_stats;
+    const uint32_t thr = xq_eps_threshold(eps);
+    for (int p = 0; p < n_plies; ++p) {
+        q90_kernel<<<blocks(ei.n * 32, 256), 256, 0, ei.stream>>>(ei.d_envs, ei.n, fw.W0T, fw.b0, fw.W1, fw.b1, sc->q90);
+        XQ_LAUNCH_CHECK();
+        act_kernel<true><<<blocks(ei.n, kThreads), kThreads, 0, ei.stream>>>(ei.d_envs, ei.n, ei.env_id0, ei.seed, sc->q90, thr, train_done, nullptr,
+                                                                            r ? r->d_ring : nullptr, r ? r->capacity : 1,
+                                                                            r ? r->total % r->capacity : 0, d_stats);
+        XQ_LAUNCH_CHECK();
+        if (r) r->total += ei.n;
+    }
+    if (int rc = order_after(h->stream, ei.stream, &g_ev[h->device & 63])) return rc;    // later TD updates see the new transitions
+    return XQ_OK;
+}
+
+int xq_dqn_td_update_replay(xq_dqn_t h, xq_replay_t r, int64_t batch, uint64_t seed, uint32_t counter, int use_target_net, double lr, int apply) {
+    if (!h || !r || batch <= 0) return fail(XQ_ERR_INVALID, "xq_dqn_td_update_replay: bad arguments");
+    if (r->device != h->device) return fail(XQ_ERR_INVALID, "xq_dqn_td_update_replay: handles live on different devices");
+    XQ_CUDA(cudaSetDevice(h->device));
+    if (int rc = replay_sample_dev(r, batch, seed, counter, h->stream, false)) return rc;
+    return xq_dqn_td_update_device(h, r->d_batch, batch, use_target_net, lr, apply);
+}
+
+}  // extern "C"

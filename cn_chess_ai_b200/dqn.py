@@ -7,7 +7,7 @@ import ctypes as C
 
 import numpy as np
 
-from ._lib import check, lib, ptr
+from ._lib import ENV_DTYPE, TRANSITION_DTYPE, check, lib, ptr
 
 AS_WRITTEN, CORRECTED = 0, 1
 _P = C.c_void_p
@@ -30,6 +30,11 @@ def _bind():
     L.xq_dqn_backprop.argtypes = [_P, _P, _P, C.c_int64, C.c_double]
     L.xq_dqn_select_action.argtypes = [_P, _P, C.c_double, _P, C.c_int, C.c_uint32, C.c_uint32, C.POINTER(C.c_int)]
     L.xq_dqn_train.argtypes = [_P, _P, C.c_int, C.c_double, _P, C.c_int, C.c_int, C.c_double]
+    L.xq_dqn_forward_boards.argtypes = [_P, _P, C.c_int64, _P]
+    L.xq_dqn_td_update.argtypes = [_P, _P, C.c_int64, C.c_int, C.c_double, _P]
+    L.xq_dqn_td_update_device.argtypes = [_P, _P, C.c_int64, C.c_int, C.c_double, C.c_int]
+    L.xq_dqn_grad_buffer.argtypes = [_P, C.POINTER(_P), C.POINTER(C.c_int64)]
+    L.xq_dqn_apply_grads.argtypes = [_P, C.c_double]
     L.xq_dqn_save.argtypes = [_P, C.c_char_p]
     L.xq_dqn_load.argtypes = [_P, C.c_char_p]
     _bound = True
@@ -115,3 +120,29 @@ class DQN:
 
     def load_model(self, path):
         check(self._L.xq_dqn_load(self._h, str(path).encode()))
+
+    # ---- batched tensor-core path ({1260,128,8100}) ----
+    def forward_boards(self, recs):
+        """Q(s) of packed boards through the tcgen05 path: float32 [n, 8100]"""
+        recs = np.ascontiguousarray(recs, dtype=ENV_DTYPE)
+        q = np.empty((len(recs), int(self.layers[-1])), dtype=np.float32)
+        check(self._L.xq_dqn_forward_boards(self._h, ptr(recs), len(recs), ptr(q)))
+        return q
+
+    def td_update(self, batch, use_target_net=False, lr=0.0):
+        """one batched TD update on host transitions; returns (loss_sum, q_sum, target_sum)"""
+        batch = np.ascontiguousarray(batch, dtype=TRANSITION_DTYPE)
+        info = np.zeros(4, dtype=np.float32)
+        check(self._L.xq_dqn_td_update(self._h, ptr(batch), len(batch), 1 if use_target_net else 0, lr, ptr(info)))
+        return info
+
+    def td_update_device(self, batch_ptr, n, use_target_net=False, lr=0.0, apply=True):
+        check(self._L.xq_dqn_td_update_device(self._h, _P(batch_ptr), n, 1 if use_target_net else 0, lr, 1 if apply else 0))
+
+    def grad_buffer(self):
+        p, n = _P(), C.c_int64()
+        check(self._L.xq_dqn_grad_buffer(self._h, C.byref(p), C.byref(n)))
+        return p.value, n.value
+
+    def apply_grads(self, lr=0.0):
+        check(self._L.xq_dqn_apply_grads(self._h, lr))

@@ -170,6 +170,63 @@ int xq_dqn_sync_target(xq_dqn_t h);
 int xq_dqn_save(xq_dqn_t h, const char* path);
 int xq_dqn_load(xq_dqn_t h, const char* path);
 
+/* ---- batched tensor-core path ({1260,128,8100} only) ---- */
+/* One replay transition, 128 B: packed board before (s) and after (s2) the move, the action, the mover's
+ * colour, done and ChessAI::evaluateBoard's reward (src/chessai.cpp:113-119).  `done` follows the caller's
+ * loop: checkGameOver() (startSelfPlay :227) or checkGameOver() || moveCount+1 >= 200 (train :119). */
+typedef struct {
+    uint32_t s[12];
+    uint32_t s2[12];
+    xq_action action;
+    uint8_t mover;
+    uint8_t done;
+    int32_t reward;
+    uint32_t reserved[6];
+} xq_transition;
+
+/* Q(s) for n packed boards through the tensor-core path: q_host[n][8100] FP32 (parity / debugging;
+ * the training kernels never materialise Q) */
+int xq_dqn_forward_boards(xq_dqn_t h, const xq_env_rec* boards_host, int64_t n, float* q_host);
+/* One batched TD update (the body of ChessAI::train, src/chessai.cpp:121-131, for n transitions at once):
+ * target_b = done ? r : r + gamma * max_a Q'(s2_b)[a]; loss 1/2 (Q(s_b)[to_b] - target_b)^2; gradients of all
+ * samples are taken at the same weights and SUMMED, then W -= lr * grad (n = 1 is one reference step).
+ * use_target_net: Q' = target network (DQN::train, src/dqn.cpp:157-172) instead of the online one.
+ * lr <= 0 uses the handle's rate.  info_host[4] = {sum of losses, sum Q(s)[to], sum target, 0}. */
+int xq_dqn_td_update(xq_dqn_t h, const xq_transition* batch_host, int64_t n, int use_target_net, double lr, float* info_host);
+/* same on a device-resident batch, asynchronous; apply = 0 only accumulates the gradient (multi-GPU:
+ * all-reduce xq_dqn_grad_buffer across ranks, then xq_dqn_apply_grads on every rank) */
+int xq_dqn_td_update_device(xq_dqn_t h, const void* batch_dev, int64_t n, int use_target_net, double lr, int apply);
+/* compact gradient of a TD step: [dW0^T 1260x128 | db0 128 | dW1 rows 0..89 x128 | db1 0..89] = 173,018 FP32 */
+int xq_dqn_grad_buffer(xq_dqn_t h, void** dev_ptr, int64_t* n_floats);
+int xq_dqn_apply_grads(xq_dqn_t h, double lr);
+
+/* ---- GPU-resident replay buffer + epsilon-greedy self-play (new capabilities: the reference trains online at
+ * batch 1 and has no replay buffer; semantics are per transition those of ChessAI::train) ---- */
+typedef struct xq_replay_s* xq_replay_t;
+/* ring of `capacity` xq_transition records (128 B each: 1M transitions = 128 MB of HBM) */
+int xq_replay_create(int64_t capacity, int device, xq_replay_t* out);
+int xq_replay_destroy(xq_replay_t r);
+int xq_replay_info(xq_replay_t r, int64_t* size, int64_t* capacity, int64_t* total_inserted);
+/* batched insert of n host transitions at the ring head */
+int xq_replay_insert(xq_replay_t r, const xq_transition* batch_host, int64_t n);
+/* raw ring slots [first, first+n) (tests / checkpointing) */
+int xq_replay_get(xq_replay_t r, int64_t first, int64_t n, xq_transition* out_host);
+/* uniform sampling with replacement: index_i = (xq_rng(seed, i, counter) >> 1) % size.  Either output may be NULL. */
+int xq_replay_sample(xq_replay_t r, int64_t batch, uint64_t seed, uint32_t counter, xq_transition* out_host, int64_t* index_host);
+
+/* DQN::selectAction for every env at once (src/dqn.cpp:24-56 over ChessAI::getAllValidActions): coin31/idx31 come from
+ * xq_rng(seed, env_id, ctr); explore: list[idx31 % n]; exploit: FIRST action maximising Q(s)[action.to] (strict >).
+ * Nothing is applied.  q_host (optional) [n][96]: Q(s)[0..89] as used for the choice. */
+int xq_dqn_act(xq_dqn_t h, xq_env_t env, double eps, xq_action* actions_host, float* q_host);
+/* n_plies of epsilon-greedy self-play on every env, device-resident and asynchronous: per ply the body of ChessAI::train
+ * (src/chessai.cpp:96-119) up to the transition (s, a, r, s', done), which is written to the replay ring (r may be NULL);
+ * terminal envs restart.  train_done != 0: done = checkGameOver() || moveCount+1 >= 200 (train, :119), else checkGameOver()
+ * (startSelfPlay, :227).  Env statistics accumulate in the env handle (xq_env_get_stats). */
+int xq_selfplay_collect(xq_dqn_t h, xq_env_t env, xq_replay_t r, int n_plies, double eps, int train_done);
+/* sample `batch` transitions from the ring and run xq_dqn_td_update_device on them, all on the device */
+int xq_dqn_td_update_replay(xq_dqn_t h, xq_replay_t r, int64_t batch, uint64_t seed, uint32_t counter, int use_target_net, double lr,
+                            int apply);
+
 /* number of kernels this library has launched in this process (bench.py's gpu_launches) */
 uint64_t xq_launch_count(void);
 

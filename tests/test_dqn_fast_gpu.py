@@ -1,0 +1,143 @@
+"""GPU parity tests of the batched tensor-core DQN path (tcgen05 GEMM + fused TD update) against the
+FP64 oracle.  Stated tolerance: |dQ| <= 2e-3 abs (BF16 MMA operands, FP32 accumulation, FP32 master
+weights); parameter updates: 1% of the largest reference update (+1e-7)."""
+import numpy as np
+import pytest
+
+from conftest import harvest_positions
+
+pytestmark = pytest.mark.gpu
+LAYERS = [1260, 128, 8100]
+LA = np.array(LAYERS, np.int32)
+QTOL = 2e-3
+
+
+@pytest.fixture(scope="module")
+def xq():
+    import cn_chess_ai_b200 as m
+    return m
+
+
+def rand_params(seed):
+    rng = np.random.default_rng(seed)
+    return rng.uniform(-0.05, 0.05, 1260 * 128 + 128 * 8100), rng.uniform(-0.05, 0.05, 128 + 8100)
+
+
+def states_of(O, L, recs):
+    out = np.zeros((len(recs), 1260))
+    for i in range(len(recs)):
+        L.xqo_state(recs[i:i + 1].ctypes.data, out[i])
+    return out
+
+
+def make_batch(O, L, xq, n, seed, train_done=False):
+    """transitions from oracle-driven random play: (s, action, reward, s2, done, mover)"""
+    envs = harvest_positions(O, n, 1, 0, seed=seed)            # n openings
+    st = np.zeros(1, O.STATS_DTYPE)
+    rng = np.random.default_rng(seed)
+    for i in range(n):                                        # desynchronise the games
+        L.xqo_rollout_random(envs[i:i + 1].ctypes.data, 1, i, seed, int(rng.integers(0, 199)), None, st.ctypes.data)
+    before = envs.copy()
+    tr = np.zeros((1, n), O.TRACE_DTYPE)
+    # one traced ply WITHOUT letting the oracle hide s2 behind a reset: step through xqo_batch_step
+    counts = np.zeros(n, np.uint8); acts = np.zeros((n, 128), np.uint16)
+    L.xqo_batch_all_actions(envs.ctypes.data, n, counts, acts)
+    pick = acts[np.arange(n), rng.integers(0, 1 << 30, n) % counts]
+    rew = np.zeros(n, np.int32); done, win, cap, valid = (np.zeros(n, np.uint8) for _ in range(4))
+    L.xqo_batch_step(envs.ctypes.data, n, pick, rew, done, win, cap, valid)
+    assert valid.all()
+    batch = np.zeros(n, xq.TRANSITION_DTYPE)
+    batch["s"] = before["sq"]; batch["s2"] = envs["sq"]; batch["action"] = pick
+    batch["mover"] = before["player"]; batch["reward"] = rew
+    batch["done"] = done | ((envs["move_count"] + 1 >= 200).astype(np.uint8) if train_done else 0)
+    return batch, before, envs
+
+
+@pytest.mark.parametrize("n", [1, 77, 300, 1024])
+def test_forward_boards_vs_fp64_oracle(xq, O, oracle_lib, n):
+    w, b = rand_params(1)
+    net = xq.DQN(LAYERS)
+    net.set_params(w, b)
+    recs = harvest_positions(O, 64, (n + 63) // 64, 9, seed=n)[:n]
+    q = net.forward_boards(recs)
+    assert q.shape == (n, 8100) and np.isfinite(q).all()
+    x = states_of(O, oracle_lib, recs)
+    idx = np.unique(np.concatenate([np.arange(min(n, 6)), np.arange(max(0, n - 6), n), np.arange(0, n, 37)]))
+    worst = 0.0
+    for i in idx:
+        ref = np.zeros(8100)
+        oracle_lib.xqo_nn_forward(LA, 3, w, b, x[i], ref)
+        worst = max(worst, np.abs(q[i] - ref).max())
+    assert worst < QTOL, worst
+    q64 = net.get_q_values(x[idx])                          # the library's own FP64 path agrees too
+    assert np.abs(q[idx] - q64).max() < QTOL
+
+
+def oracle_td_reference(L, w, b, tw, tb, batch, x, x2, gamma, mode):
+    gw = np.zeros_like(w); gb = np.zeros_like(b)
+    g1 = np.zeros_like(w); g2 = np.zeros_like(b)
+    loss = 0.0
+    for i in range(len(batch)):
+        qs = np.zeros(8100); qn = np.zeros(8100); tgt = np.zeros(8100)
+        L.xqo_nn_forward(LA, 3, w, b, x[i], qs)
+        L.xqo_nn_forward(LA, 3, tw, tb, x2[i], qn)
+        to = int(batch["action"][i]) & 127
+        L.xqo_td_target(qs, qn, 8100, to, float(batch["reward"][i]), int(batch["done"][i]), gamma, tgt)
+        L.xqo_nn_grad(LA, 3, w, b, x[i], tgt, mode, g1, g2)
+        gw += g1; gb += g2
+        loss += 0.5 * (qs[to] - tgt[to]) ** 2
+    return gw, gb, loss
+
+
+@pytest.mark.parametrize("n,mode,use_target", [(1, 0, False), (1, 1, False), (96, 0, False), (200, 1, True), (130, 0, True)])
+def test_td_update_vs_fp64_oracle(xq, O, oracle_lib, n, mode, use_target):
+    w, b = rand_params(2)
+    tw, tb = rand_params(3) if use_target else (w, b)
+    net = xq.DQN(LAYERS, lr=0.001, gamma=0.99, mode=mode)
+    if use_target:
+        net.set_params(tw, tb)          # set_params refreshes the target with these ...
+        net.update_target_network()
+        net_w = w
+        # ... then load the online parameters without touching the target
+        import tempfile, os
+        tmp = xq.DQN(LAYERS); tmp.set_params(w, b)
+        path = os.path.join(tempfile.mkdtemp(), "m.bin"); tmp.save_model(path); net.load_model(path)
+    else:
+        net.set_params(w, b)
+    batch, before, after = make_batch(O, oracle_lib, xq, n, seed=10 + n, train_done=(mode == 1))
+    x, x2 = states_of(O, oracle_lib, before), states_of(O, oracle_lib, after)
+    lr = 1e-6                                             # rewards are O(10..1000): keep the step small
+    info = net.td_update(batch, use_target_net=use_target, lr=lr)
+    gw, gb, loss = oracle_td_reference(oracle_lib, w, b, tw, tb, batch, x, x2, 0.99, mode)
+    w1, b1 = net.get_params()
+    dw_ref, db_ref = -lr * gw, -lr * gb
+    dw, db = w1 - w, b1 - b
+    scale = max(np.abs(dw_ref).max(), np.abs(db_ref).max())
+    assert scale > 0
+    assert np.abs(dw - dw_ref).max() <= 1e-2 * scale + 1e-7, (np.abs(dw - dw_ref).max(), scale)
+    assert np.abs(db - db_ref).max() <= 1e-2 * scale + 1e-7
+    # only W0, b0 and rows < 90 of W1 / b1 may change (Q is indexed by action.to); everything else is
+    # bit-identical to the FP32 master copy of the parameters that were loaded
+    w32, b32 = w.astype(np.float32).astype(np.float64), b.astype(np.float32).astype(np.float64)
+    assert np.array_equal(w1[1260 * 128 + 90 * 128:], w32[1260 * 128 + 90 * 128:]) and np.array_equal(b1[128 + 90:], b32[128 + 90:])
+    assert abs(info[0] - loss) <= 1e-3 * abs(loss) + 1e-3
+
+
+def test_td_update_b1_equals_reference_backprop_step(xq, O, oracle_lib):
+    """n = 1 is one step of the reference loop: getQValues x2 + backpropagate (src/chessai.cpp:121-131)"""
+    w, b = rand_params(5)
+    net = xq.DQN(LAYERS, mode=xq.AS_WRITTEN)
+    net.set_params(w, b)
+    batch, before, after = make_batch(O, oracle_lib, xq, 1, seed=99)
+    x, x2 = states_of(O, oracle_lib, before)[0], states_of(O, oracle_lib, after)[0]
+    qs = np.zeros(8100); qn = np.zeros(8100); tgt = np.zeros(8100)
+    oracle_lib.xqo_nn_forward(LA, 3, w, b, x, qs); oracle_lib.xqo_nn_forward(LA, 3, w, b, x2, qn)
+    to = int(batch["action"][0]) & 127
+    oracle_lib.xqo_td_target(qs, qn, 8100, to, float(batch["reward"][0]), int(batch["done"][0]), 0.99, tgt)
+    w0, b0 = w.copy(), b.copy()
+    oracle_lib.xqo_nn_backprop(LA, 3, w0, b0, x, tgt, 1e-5, 0)
+    net.td_update(batch, lr=1e-5)
+    w1, b1 = net.get_params()
+    scale = np.abs(w0 - w).max()
+    assert np.abs((w1 - w) - (w0 - w)).max() <= 1e-2 * scale + 1e-7
+    assert np.abs((b1 - b) - (b0 - b)).max() <= 1e-2 * scale + 1e-7

@@ -1,0 +1,135 @@
+"""GPU tests of the replay buffer, batched epsilon-greedy action selection and the self-play collector
+(BASELINE configs 3/4).  Selection parity is checked GIVEN identical Q inputs (last bullet):
+the Q-values the GPU used are fed to the oracle's restatement of DQN::selectAction with the same draws."""
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+LAYERS = [1260, 128, 8100]
+LA = np.array(LAYERS, np.int32)
+
+
+@pytest.fixture(scope="module")
+def xq():
+    import cn_chess_ai_b200 as m
+    return m
+
+
+def rand_params(seed):
+    rng = np.random.default_rng(seed)
+    return rng.uniform(-0.05, 0.05, 1260 * 128 + 128 * 8100), rng.uniform(-0.05, 0.05, 128 + 8100)
+
+
+def oracle_lists(L, recs):
+    n = len(recs)
+    counts = np.zeros(n, np.uint8)
+    acts = np.zeros((n, 128), np.uint16)
+    L.xqo_batch_all_actions(recs.ctypes.data, n, counts, acts)
+    return counts, acts
+
+
+def test_replay_ring_and_sampling(xq, O):
+    rb = xq.ReplayBuffer(1000)
+    rng = np.random.default_rng(0)
+    def mk(n, tag):
+        b = np.zeros(n, xq.TRANSITION_DTYPE)
+        b["s"] = rng.integers(0, 2 ** 32, (n, 12), dtype=np.uint64).astype(np.uint32)
+        b["reward"] = tag + np.arange(n)
+        return b
+    a = mk(600, 0); rb.insert(a)
+    assert rb.info() == (600, 1000, 600)
+    assert rb.get(0, 600).tobytes() == a.tobytes()
+    b = mk(700, 10000); rb.insert(b)                         # wraps: slots 600..999 then 0..299
+    assert rb.info() == (1000, 1000, 1300)
+    ring = rb.get()
+    assert ring[600:].tobytes() == b[:400].tobytes() and ring[:300].tobytes() == b[400:].tobytes() and ring[300:600].tobytes() == a[300:600].tobytes()
+    out, idx = rb.sample(4096, seed=7, counter=3)
+    want = ((O.rng_np(7, np.arange(4096, dtype=np.uint64), np.full(4096, 3, np.uint32)) >> np.uint64(1)) % np.uint64(1000)).astype(np.int64)
+    assert (idx == want).all() and out.tobytes() == ring[idx].tobytes()
+    assert len(np.unique(idx)) > 900                         # uniform over the ring
+    with pytest.raises(xq.XQError):
+        xq.ReplayBuffer(10).sample(4, 0, 0)                  # empty
+    with pytest.raises(xq.XQError):
+        xq.ReplayBuffer(0)
+
+
+def test_act_stepwise_vs_oracle(xq, O, oracle_lib):
+    """config 3 in small: eps-greedy choice per env per ply == oracle selectAction on the same Q and draws"""
+    n, plies, seed, eps = 700, 25, 11, 0.1
+    w, b = rand_params(4)
+    net = xq.DQN(LAYERS); net.set_params(w, b)
+    env = xq.BatchedEnv(n, seed=seed, env_id0=50)
+    ref = O.new_envs(n)
+    thr = oracle_lib.xqo_eps_threshold(eps)
+    explored = 0
+    for p in range(plies):
+        actions, q = xq.act(net, env, eps, want_q=True)
+        counts, lists = oracle_lists(oracle_lib, ref)
+        x = O.rng_np(seed, np.arange(n, dtype=np.uint64) + np.uint64(50), ref["ctr"])
+        coin, idx = (x & np.uint64(0x7FFFFFFF)).astype(np.uint32), (x >> np.uint64(33)).astype(np.uint32)
+        explored += int((coin < thr).sum())
+        for i in range(n):
+            qi = np.zeros(8100); qi[:90] = q[i, :90]
+            k = oracle_lib.xqo_select_action(qi, lists[i], int(counts[i]), int(coin[i]), int(idx[i]), eps)
+            assert actions[i] == lists[i, k], (p, i)
+        if p == 0:   # Q used for acting vs the FP64 oracle (FP32 path: layer-0 gather + 90 dots)
+            st = np.zeros(1260); qq = np.zeros(8100)
+            for i in range(0, n, 97):
+                oracle_lib.xqo_state(ref[i:i + 1].ctypes.data, st)
+                oracle_lib.xqo_nn_forward(LA, 3, w, b, st, qq)
+                assert np.abs(q[i, :90] - qq[:90]).max() < 1e-5
+        rew, done, win, cap, valid = env.step(actions, auto_reset=True)
+        r0 = np.zeros(n, np.int32); d0, w0, c0, v0 = (np.zeros(n, np.uint8) for _ in range(4))
+        oracle_lib.xqo_batch_step(ref.ctypes.data, n, actions, r0, d0, w0, c0, v0)
+        assert (valid == 1).all() and (rew == r0).all() and (done == d0).all()
+        for i in np.nonzero(d0)[0]:
+            oracle_lib.xqo_reset(ref[i:i + 1].ctypes.data)
+        assert env.get_boards().tobytes() == ref.tobytes()
+    assert 0.05 * n * plies < explored < 0.15 * n * plies
+
+
+@pytest.mark.parametrize("train_done", [True, False])
+def test_collect_fills_replay_like_the_train_loop(xq, O, oracle_lib, train_done):
+    n, plies, seed, eps = 300, 230, 5, 0.1              # > 200 plies: crosses the move cap and the done-one-ply-early quirk
+    w, b = rand_params(6)
+    net = xq.DQN(LAYERS); net.set_params(w, b)
+    envA = xq.BatchedEnv(n, seed=seed)
+    rb = xq.ReplayBuffer(n * plies + 17)
+    xq.collect(net, envA, rb, plies, eps, train_done=train_done)
+    envA.sync()
+    stats = envA.stats()
+    assert rb.info()[2] == n * plies and stats["steps"] == n * plies
+    ring = rb.get(0, n * plies).reshape(plies, n)
+    # replay the same policy step by step: GPU act (same Q, same draws) + oracle rules
+    envB = xq.BatchedEnv(n, seed=seed)
+    ref = O.new_envs(n)
+    for p in range(plies):
+        actions = xq.act(net, envB, eps)
+        before = ref.copy()
+        r0 = np.zeros(n, np.int32); d0, w0, c0, v0 = (np.zeros(n, np.uint8) for _ in range(4))
+        oracle_lib.xqo_batch_step(ref.ctypes.data, n, actions, r0, d0, w0, c0, v0)
+        t = ring[p]
+        assert (t["action"] == actions).all() and (t["reward"] == r0).all() and (t["mover"] == before["player"]).all()
+        assert t["s"].tobytes() == before["sq"].tobytes() and t["s2"].tobytes() == ref["sq"].tobytes()
+        want_done = d0 | ((ref["move_count"] + 1 >= 200).astype(np.uint8) if train_done else 0)
+        assert (t["done"] == want_done).all(), p
+        for i in np.nonzero(d0)[0]:
+            oracle_lib.xqo_reset(ref[i:i + 1].ctypes.data)
+        envB.step(actions, auto_reset=True)
+    assert envA.get_boards().tobytes() == ref.tobytes()
+    assert stats["games"] >= n                              # every env finished at least one game
+
+
+def test_td_update_from_replay_matches_host_batch(xq, O):
+    w, b = rand_params(8)
+    net1 = xq.DQN(LAYERS); net1.set_params(w, b)
+    net2 = xq.DQN(LAYERS); net2.set_params(w, b)
+    env = xq.BatchedEnv(512, seed=9)
+    rb = xq.ReplayBuffer(4096)
+    xq.collect(net1, env, rb, 8, 0.3)
+    batch, idx = rb.sample(1000, seed=1, counter=2)
+    xq.td_update_replay(net1, rb, 1000, seed=1, counter=2, lr=1e-6)
+    net2.td_update(batch, lr=1e-6)
+    w1, b1 = net1.get_params(); w2, b2 = net2.get_params()
+    scale = np.abs(w2 - w).max()
+    assert scale > 0 and np.abs(w1 - w2).max() <= 1e-4 * scale + 1e-9 and np.abs(b1 - b2).max() <= 1e-4 * scale + 1e-9
