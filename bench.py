@@ -140,6 +140,7 @@ def main():
     ap.add_argument("--ref-plies", type=int, default=250000, help="plies per host thread per step of the reference arm")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-aux", action="store_true")
+    ap.add_argument("--no-dqn", action="store_true")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup
     if args.impl == "reference":
@@ -262,11 +263,13 @@ def main():
         torch.cuda.synchronize()
         line["aux"] = {"config5_1M_envs_steps_per_s": (1 << 20) * 32 / (a.elapsed_time(b) * 1e-3)}
         big.close()
-        try:
-            from cn_chess_ai_b200 import bench_dqn
-            line["dqn"] = bench_dqn(stream, pk)
-        except ImportError:
-            pass
+
+    if not args.no_dqn:
+        # the DQN half of the metric: every rank takes part (gradient all-reduce at N > 1), rank 0 reports
+        d = xq.bench_dqn(stream, pk, world=world, local=local, dist=dist)
+        line["dqn"] = d
+        launches_total = L.xq_launch_count()
+        line["gpu_launches_total"] = int(launches_total)
 
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         cores = os.cpu_count() or 1

@@ -7,3 +7,4 @@ from ._lib import (ENV_DTYPE, MAX_ACTIONS, STATE_SIZE, STATS_DTYPE, TRACE_DTYPE,
 from .env import BatchedEnv, action  # noqa: F401
 from .dqn import AS_WRITTEN, CORRECTED, DQN  # noqa: F401
 from .replay import ReplayBuffer, act, collect, td_update_replay  # noqa: F401
+from .benchmarks import bench_dqn, smoke_dqn  # noqa: F401

@@ -1,0 +1,70 @@
+"""Multi-GPU plumbing: one process per GPU (torch.distributed), env / replay shards per rank with no
+data-path collective, and ONE exchange step per TD update: a sum all-reduce (NCCL over NVLink/NVSwitch)
+of the compact gradient buffer (173,018 FP32 = 0.69 MB), followed by the identical SGD step on every
+rank.  torch is plumbing here (process group, stream, the collective); the kernels are the library's."""
+import os
+
+
+def shard(n_total, rank, world):
+    """contiguous block partition of n_total units: (first, count); counts differ by at most one"""
+    base, rem = divmod(int(n_total), int(world))
+    first = rank * base + min(rank, rem)
+    return first, base + (1 if rank < rem else 0)
+
+
+def rank_world():
+    return int(os.environ.get("RANK", "0")), int(os.environ.get("WORLD_SIZE", "1")), int(os.environ.get("LOCAL_RANK", "0"))
+
+
+class DeviceArray:
+    """zero-copy view of a device buffer owned by libxq_b200 (for torch.as_tensor)"""
+
+    def __init__(self, ptr, n, typestr="<f4"):
+        self.__cuda_array_interface__ = {"shape": (int(n),), "typestr": typestr, "data": (int(ptr), False), "version": 2}
+
+
+def grad_tensor(dqn, device):
+    import torch
+    ptr, n = dqn.grad_buffer()
+    return torch.as_tensor(DeviceArray(ptr, n), device=device)
+
+
+def allreduce_sum_(tensor, group=None):
+    """in-place sum over ranks; no-op without an initialised process group"""
+    import torch.distributed as dist
+    if dist.is_available() and dist.is_initialized() and dist.get_world_size(group) > 1:
+        dist.all_reduce(tensor, op=dist.ReduceOp.SUM, group=group)
+    return tensor
+
+
+class DataParallelLearner:
+    """Config 4: every rank owns envs [first, first+count) (global ids keep trajectories independent of the GPU
+    count), its own replay shard and a replica of the Q-network initialised from the same seed.  A training
+    step = local self-play, local TD gradients at batch `batch` per GPU, all-reduce, identical update."""
+
+    def __init__(self, total_envs, replay_capacity, batch, seed=0, eps=0.1, lr=0.001, gamma=0.99, mode=0, train_done=True):
+        import torch
+        from . import BatchedEnv, DQN, ReplayBuffer
+        self.rank, self.world, self.local = rank_world()
+        self.device = torch.device("cuda", self.local)
+        first, count = shard(total_envs, self.rank, self.world)
+        stream = torch.cuda.current_stream(self.device).cuda_stream
+        self.env = BatchedEnv(count, device=self.local, seed=seed, env_id0=first)
+        self.dqn = DQN((1260, 128, 8100), lr=lr, gamma=gamma, device=self.local, seed=seed, mode=mode)
+        self.replay = ReplayBuffer(shard(replay_capacity, self.rank, self.world)[1], device=self.local)
+        self.env.set_stream(stream)
+        self.dqn.set_stream(stream)
+        self.batch, self.eps, self.lr, self.seed, self.train_done = batch, eps, lr, seed, train_done
+        self.updates = 0
+        self.grads = grad_tensor(self.dqn, self.device)
+
+    def collect(self, n_plies):
+        from . import collect
+        collect(self.dqn, self.env, self.replay, n_plies, self.eps, self.train_done)
+
+    def update(self, use_target_net=True):
+        from . import td_update_replay
+        td_update_replay(self.dqn, self.replay, self.batch, self.seed + 1000003 * self.rank, self.updates, use_target_net, self.lr, apply=False)
+        allreduce_sum_(self.grads)
+        self.dqn.apply_grads(self.lr)
+        self.updates += 1
