@@ -12,7 +12,8 @@
 //   TD error  the live loop's target equals Q(s) except at index `to` (src/chessai.cpp:122-128), so delta1 is
 //             one-hot per sample: q(s)[to] is a 128-long dot product, dW1 touches row `to` only, delta0 is one
 //             row of W1 (as written: src/dqn.cu:406-423; or corrected)            [td_delta_kernel]
-//   dW0       sum_b delta0_b (x) x_b accumulated per board square in shared memory            [dw0_kernel]
+//   dW0       X^T . delta0 on tcgen05: the transposed one-hot operand tile is built in shared memory from the packed
+//             boards, delta0^T (BF16 hi+lo) arrives by TMA; db0 rides along as a constant-one feature    [dw0_gemm_kernel]
 //   SGD       W -= lr * sum of per-sample gradients (B = 1 reproduces one reference step)     [apply_kernel]
 // FP32 master weights; BF16 only as MMA operands.  Tolerance vs the FP64 oracle: |dQ| <= 2e-3.
 #include <cuda.h>
@@ -37,7 +38,9 @@ constexpr int kNTiles = (kOut + BN - 1) / BN;       // 37
 constexpr uint32_t kABytes = BM * kHid * 2;         // 32 KB: one A tile (both k-blocks)
 constexpr uint32_t kBBytes = BN * kHid * 2;         // 56 KB: the stationary W1 tile
 constexpr uint32_t kTmemCols = 512;                 // 2 accumulator stages x BN columns (power of two >= 448)
-constexpr int kGemmThreads = 256;                   // warp 0 TMA, 1 MMA, 2 TMEM alloc, 3 bias, 4-7 epilogue
+constexpr int kGemmThreads = 384;                   // warp 0 TMA, 1 MMA, 2 TMEM alloc, 3 bias, 4-11 epilogue
+constexpr int kEpiWarps = 8;                        // two warps per TMEM lane quarter, each drains half of the BN columns
+constexpr int kParts = 2 * kNTiles;                 // row-max partials per sample (74)
 constexpr size_t kGemmSmem = 1024 + kBBytes + kAStages * kABytes + BN * 4 + 256;
 
 struct Fast {
@@ -52,12 +55,15 @@ struct Fast {
     xq_env_rec* boards = nullptr;                      // staging for xq_dqn_forward_boards
     __nv_bfloat16 *Hbf = nullptr, *H2bf = nullptr;     // h(s), h(s') as MMA A operands [cap][128]
     float* Hf = nullptr;                               // h(s) FP32 [cap][128]
-    float* zpart = nullptr;                            // [kNTiles][cap] row-max partials
-    float* delta0 = nullptr;                           // [cap][128]
+    float* zpart = nullptr;                            // [kParts][cap] row-max partials
+    float* d1 = nullptr;                               // [cap] delta1 of the taken action
+    uint8_t* to8 = nullptr;                            // [cap] action.to
+    __nv_bfloat16 *d0hi = nullptr, *d0lo = nullptr;    // delta0^T [128][ld] BF16 hi / lo (B operand of the dW0 contraction)
+    float* part = nullptr;                             // [kDwSplits][1280][128] FP32 partials of dW0^T
     float* q = nullptr;                                // [cap][8100] (debug path only, allocated on demand)
     int64_t q_cap = 0;
     float* info = nullptr;                             // 4 floats
-    CUtensorMap tmW1, tmTW1, tmH, tmH2;
+    CUtensorMap tmW1, tmTW1, tmH, tmH2, tmD0hi, tmD0lo;
     int64_t tm_rows = 0;
 };
 
@@ -126,7 +132,7 @@ __global__ void __launch_bounds__(kGemmThreads, 1) l1_gemm_kernel(const __grid_c
     if (threadIdx.x == 0) {
         tc::mbar_init(b_full, 1);
         for (int i = 0; i < kAStages; ++i) { tc::mbar_init(a_full + i, 1); tc::mbar_init(a_empty + i, 1); }
-        for (int i = 0; i < 2; ++i) { tc::mbar_init(acc_full + i, 1); tc::mbar_init(acc_empty + i, 4); }
+        for (int i = 0; i < 2; ++i) { tc::mbar_init(acc_full + i, 1); tc::mbar_init(acc_empty + i, kEpiWarps); }
         tc::fence_barrier_init();
     }
     if (warp == 2) tc::tmem_alloc<kTmemCols>(tmem_slot);
@@ -170,32 +176,55 @@ __global__ void __launch_bounds__(kGemmThreads, 1) l1_gemm_kernel(const __grid_c
                 tc::umma_commit(acc_full + acc);    // accumulator ready for the epilogue
             }
         }
-    } else if (warp >= 4) {   // ===== epilogue: warp w drains TMEM lanes 32*(w-4) .. +31 =====
-        const int quarter = warp - 4;
+    } else if (warp >= 4) {   // ===== epilogue: warps w and w+4 drain TMEM lanes 32*(w&3).. +31, one half of the columns each =====
+        const int quarter = warp & 3, half = (warp - 4) >> 2;
+        constexpr int kHalfCols = BN / 2;                                   // 112 = 7 chunks of 16 columns
         for (int i = 0; i < my_tiles; ++i) {
             const int acc = i & 1;
             const int row = (split + i * n_splits) * BM + quarter * 32 + lane;
             tc::mbar_wait(acc_full + acc, (i >> 1) & 1);
             tc::tc_fence_after();
-            float best = -INFINITY;
+            const uint32_t t0 = tmem_base + ((uint32_t)(quarter * 32) << 16) + acc * BN + half * kHalfCols;
+            const float* bias = sBias + half * kHalfCols;
+            float best[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY};
 #pragma unroll 1
-            for (int c = 0; c < BN / 32; ++c) {
-                float v[32];
-                tc::tmem_ld32(tmem_base + ((uint32_t)(quarter * 32) << 16) + acc * BN + c * 32, v);
+            for (int c = 0; c < kHalfCols / 16; c += 2) {
+                uint32_t r0[16], r1[16];
+                const bool two = c + 1 < kHalfCols / 16;
+                tc::tmem_ld16_nowait(t0 + c * 16, r0);
+                if (two) tc::tmem_ld16_nowait(t0 + (c + 1) * 16, r1);      // warp-uniform
+                tc::tmem_wait_ld();
                 if (MODE == EPI_ROWMAX) {
 #pragma unroll
-                    for (int j = 0; j < 32; ++j) best = fmaxf(best, v[j] + sBias[c * 32 + j]);
-                } else if (row < M) {
-                    float* out = Q + (size_t)row * kOut + n0 + c * 32;
+                    for (int j = 0; j < 16; j += 4) {
+                        const float4 b4 = *reinterpret_cast<const float4*>(bias + c * 16 + j);
+                        best[0] = fmaxf(best[0], __uint_as_float(r0[j + 0]) + b4.x); best[1] = fmaxf(best[1], __uint_as_float(r0[j + 1]) + b4.y);
+                        best[2] = fmaxf(best[2], __uint_as_float(r0[j + 2]) + b4.z); best[3] = fmaxf(best[3], __uint_as_float(r0[j + 3]) + b4.w);
+                    }
+                    if (two) {
 #pragma unroll
-                    for (int j = 0; j < 32; ++j)
-                        if (n0 + c * 32 + j < kOut) out[j] = tanhf(v[j] + sBias[c * 32 + j]);
+                        for (int j = 0; j < 16; j += 4) {
+                            const float4 b4 = *reinterpret_cast<const float4*>(bias + (c + 1) * 16 + j);
+                            best[0] = fmaxf(best[0], __uint_as_float(r1[j + 0]) + b4.x); best[1] = fmaxf(best[1], __uint_as_float(r1[j + 1]) + b4.y);
+                            best[2] = fmaxf(best[2], __uint_as_float(r1[j + 2]) + b4.z); best[3] = fmaxf(best[3], __uint_as_float(r1[j + 3]) + b4.w);
+                        }
+                    }
+                } else if (row < M) {
+                    float* out = Q + (size_t)row * kOut + n0 + half * kHalfCols + c * 16;
+#pragma unroll
+                    for (int j = 0; j < 16; ++j)
+                        if (n0 + half * kHalfCols + c * 16 + j < kOut) out[j] = tanhf(__uint_as_float(r0[j]) + bias[c * 16 + j]);
+                    if (two) {
+#pragma unroll
+                        for (int j = 0; j < 16; ++j)
+                            if (n0 + half * kHalfCols + (c + 1) * 16 + j < kOut) out[16 + j] = tanhf(__uint_as_float(r1[j]) + bias[(c + 1) * 16 + j]);
+                    }
                 }
             }
             tc::tc_fence_before();
             __syncwarp();
             if (lane == 0) tc::mbar_arrive(acc_empty + acc);
-            if (MODE == EPI_ROWMAX && row < M) zpart[(int64_t)n_tile * zstride + row] = best;
+            if (MODE == EPI_ROWMAX && row < M) zpart[(int64_t)(n_tile * 2 + half) * zstride + row] = fmaxf(fmaxf(best[0], best[1]), fmaxf(best[2], best[3]));
         }
     }
     tc::tc_fence_before();
@@ -213,70 +242,253 @@ struct Transition {
 };
 static_assert(sizeof(Transition) == 128 && sizeof(xq_transition) == 128, "transition record must be 128 bytes");
 
-// TD error, one warp per transition (src/chessai.cpp:121-131 + src/dqn.cu:288-308 specialised to a one-hot delta1)
+// TD error, one warp per transition (src/chessai.cpp:121-131 + src/dqn.cu:288-308 specialised to a one-hot delta1).
+// Outputs per sample: delta1, its row `to`, delta0 as FP32 and, transposed and split into BF16 hi + lo, as the
+// K-major B operand of the dW0 contraction.  No global atomics except 3 per CTA for the loss statistics.
 __global__ void __launch_bounds__(256) td_delta_kernel(const Transition* __restrict__ batch, int64_t n, const float* __restrict__ Hf,
                                                       const float* __restrict__ W1, const float* __restrict__ b1,
-                                                      const float* __restrict__ zpart, int64_t zstride, int n_tiles, float gamma, int mode,
-                                                      float* __restrict__ delta0, float* __restrict__ grad, float* __restrict__ info) {
+                                                      const float* __restrict__ zpart, int64_t zstride, int n_parts, float gamma, int mode,
+                                                      float* __restrict__ d1_out, uint8_t* __restrict__ to_out,
+                                                      __nv_bfloat16* __restrict__ d0hi, __nv_bfloat16* __restrict__ d0lo, int64_t ld,
+                                                      float* __restrict__ info) {
+    __shared__ float s_info[8][3];
+    __shared__ __align__(16) float s_d0[8][kHid];          // delta0 of the CTA's 8 consecutive samples, for the transposed store
     const int64_t s = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-    const int lane = threadIdx.x & 31;
-    if (s >= n) return;
-    const Transition* t = batch + s;
-    const int to = XQ_ACTION_TO(t->action);                // the Q index of the taken action is action.to (:124,:127)
-    const float4 h = reinterpret_cast<const float4*>(Hf + s * kHid)[lane];
-    const float4 w = reinterpret_cast<const float4*>(W1 + (size_t)to * kHid)[lane];
-    float z = h.x * w.x + h.y * w.y + h.z * w.z + h.w * w.w;
-    float zmax = -INFINITY;
-    if (!t->done) for (int i = lane; i < n_tiles; i += 32) zmax = fmaxf(zmax, zpart[(int64_t)i * zstride + s]);
+    const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
+    float loss = 0.0f, qv = 0.0f, tv = 0.0f;
+    reinterpret_cast<float4*>(s_d0[wib])[lane] = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (s < n) {
+        const Transition* t = batch + s;
+        const int to = XQ_ACTION_TO(t->action);                // the Q index of the taken action is action.to (:124,:127)
+        const float4 h = reinterpret_cast<const float4*>(Hf + s * kHid)[lane];
+        const float4 w = reinterpret_cast<const float4*>(W1 + (size_t)to * kHid)[lane];
+        float z = h.x * w.x + h.y * w.y + h.z * w.z + h.w * w.w;
+        float zmax = -INFINITY;
+        if (!t->done) for (int i = lane; i < n_parts; i += 32) zmax = fmaxf(zmax, zpart[(int64_t)i * zstride + s]);
 #pragma unroll
-    for (int k = 16; k > 0; k >>= 1) { z += __shfl_xor_sync(0xFFFFFFFFu, z, k); zmax = fmaxf(zmax, __shfl_xor_sync(0xFFFFFFFFu, zmax, k)); }
-    const float q = tanhf(z + b1[to]);
-    const float target = t->done ? (float)t->reward : (float)t->reward + gamma * tanhf(zmax);
-    const float d1 = (q - target) * (1.0f - q * q);        // outputLayerDeltaKernel, src/dqn.cu:288-295
-    // hidden delta: as written W1flat[i*1260 + j] with i = to (only i < 128 is summed and delta1 is one-hot), or W1[to][j]
-    const float* wrow = mode == XQ_DQN_AS_WRITTEN ? W1 + (size_t)to * kIn : W1 + (size_t)to * kHid;
-    const float4 wd = reinterpret_cast<const float4*>(wrow)[lane];
-    float4 d0;
-    d0.x = wd.x * d1 * (1.0f - h.x * h.x); d0.y = wd.y * d1 * (1.0f - h.y * h.y);
-    d0.z = wd.z * d1 * (1.0f - h.z * h.z); d0.w = wd.w * d1 * (1.0f - h.w * h.w);
-    reinterpret_cast<float4*>(delta0 + s * kHid)[lane] = d0;
-    float* gw1 = grad + kGradW1 + to * kHid + 4 * lane;    // dW1[to][:] += delta1 * h   (updateWeightsBiasesKernel, :310-319)
-    atomicAdd(gw1 + 0, d1 * h.x); atomicAdd(gw1 + 1, d1 * h.y); atomicAdd(gw1 + 2, d1 * h.z); atomicAdd(gw1 + 3, d1 * h.w);
-    if (lane == 0) {
-        atomicAdd(grad + kGradB1 + to, d1);
-        atomicAdd(info + 0, 0.5f * (q - target) * (q - target));
-        atomicAdd(info + 1, q);
-        atomicAdd(info + 2, target);
+        for (int k = 16; k > 0; k >>= 1) { z += __shfl_xor_sync(0xFFFFFFFFu, z, k); zmax = fmaxf(zmax, __shfl_xor_sync(0xFFFFFFFFu, zmax, k)); }
+        const float q = tanhf(z + b1[to]);
+        const float target = t->done ? (float)t->reward : (float)t->reward + gamma * tanhf(zmax);
+        const float d1 = (q - target) * (1.0f - q * q);        // outputLayerDeltaKernel, src/dqn.cu:288-295
+        // hidden delta: as written W1flat[i*1260 + j] with i = to (only i < 128 is summed and delta1 is one-hot), or W1[to][j]
+        const float* wrow = mode == XQ_DQN_AS_WRITTEN ? W1 + (size_t)to * kIn : W1 + (size_t)to * kHid;
+        const float4 wd = reinterpret_cast<const float4*>(wrow)[lane];
+        const float d0[4] = {wd.x * d1 * (1.0f - h.x * h.x), wd.y * d1 * (1.0f - h.y * h.y), wd.z * d1 * (1.0f - h.z * h.z),
+                             wd.w * d1 * (1.0f - h.w * h.w)};
+        reinterpret_cast<float4*>(s_d0[wib])[lane] = make_float4(d0[0], d0[1], d0[2], d0[3]);
+        if (lane == 0) { d1_out[s] = d1; to_out[s] = (uint8_t)to; }
+        loss = 0.5f * (q - target) * (q - target); qv = q; tv = target;
+    }
+    if (lane == 0) { s_info[wib][0] = loss; s_info[wib][1] = qv; s_info[wib][2] = tv; }
+    __syncthreads();
+    {   // delta0^T[j][s0..s0+7] as BF16 hi (threads 0..127) / lo (128..255): one 16-byte store per (unit, array)
+        const int j = threadIdx.x & (kHid - 1);
+        const bool want_lo = threadIdx.x >= kHid;
+        const int64_t s0 = (int64_t)blockIdx.x * 8;
+        uint32_t packed[4];
+#pragma unroll
+        for (int p = 0; p < 4; ++p) {
+            float v0 = s_d0[2 * p][j], v1 = s_d0[2 * p + 1][j];
+            const __nv_bfloat16 h0 = __float2bfloat16_rn(v0), h1 = __float2bfloat16_rn(v1);
+            __nv_bfloat162 o;
+            if (want_lo) { o.x = __float2bfloat16_rn(v0 - __bfloat162float(h0)); o.y = __float2bfloat16_rn(v1 - __bfloat162float(h1)); }
+            else { o.x = h0; o.y = h1; }
+            packed[p] = *reinterpret_cast<uint32_t*>(&o);
+        }
+        if (s0 < ld) *reinterpret_cast<uint4*>((want_lo ? d0lo : d0hi) + (int64_t)j * ld + s0) = make_uint4(packed[0], packed[1], packed[2], packed[3]);
+    }
+    if (threadIdx.x < 3) {
+        float a = 0.0f;
+#pragma unroll
+        for (int k = 0; k < 8; ++k) a += s_info[k][threadIdx.x];
+        atomicAdd(info + threadIdx.x, a);
     }
 }
 
-// dW0^T[feature][:] += delta0_b for every set feature of x_b, and db0 += delta0_b.
-// CTA (square q in 0..90, chunk c): 128 threads = hidden units; the 14 feature rows of square q (or the bias
-// row for the pseudo-square 90) are accumulated in registers over the chunk's samples without atomics, then
-// merged into the gradient with one atomicAdd per non-zero (row, unit).
-constexpr int kDw0Chunk = 256;
-__global__ void __launch_bounds__(kHid) dw0_kernel(const Transition* __restrict__ batch, int64_t n, const float* __restrict__ delta0,
-                                                  float* __restrict__ grad) {
-    __shared__ uint8_t s_code[kDw0Chunk];
-    const int q = blockIdx.x, j = threadIdx.x;
-    const int64_t b0 = (int64_t)blockIdx.y * kDw0Chunk;
-    const int cnt = (int)min((int64_t)kDw0Chunk, n - b0);
-    for (int i = j; i < cnt; i += kHid) s_code[i] = q == 90 ? 1 : (uint8_t)((batch[b0 + i].s[q >> 3] >> (4 * (q & 7))) & 15);
-    __syncthreads();
-    float acc[14];
+// dW1[r][:] = sum over the samples whose action.to == r of delta1 * h, db1[r] = sum delta1 (updateWeightsBiasesKernel,
+// src/dqn.cu:310-319, for a one-hot delta1).  CTA (r, slice) scans its slice of the batch in blocks of 1024 samples:
+// matches are compacted into shared memory, then accumulated 8 loads at a time; one atomicAdd per (row, unit, slice).
+// Robust to skew (a greedy policy can put most of a batch on one square).
+constexpr int kDw1Slices = 4;
+__global__ void __launch_bounds__(kHid) dw1_kernel(const float* __restrict__ d1, const uint8_t* __restrict__ to, int64_t n,
+                                                  const float* __restrict__ Hf, float* __restrict__ grad) {
+    __shared__ int s_list[1024];
+    __shared__ float s_d1[1024];
+    __shared__ int s_cnt;
+    const int r = blockIdx.x, j = threadIdx.x;
+    const int64_t per = (n + kDw1Slices - 1) / kDw1Slices;
+    const int64_t lo = blockIdx.y * per, hi_all = min(n, lo + per);
+    float acc[4] = {0.f, 0.f, 0.f, 0.f}, bsum = 0.0f;
+    for (int64_t base = lo; base < hi_all; base += 1024) {
+        if (j == 0) s_cnt = 0;
+        __syncthreads();
+        const int64_t hi = min(hi_all, base + 1024);
+        for (int64_t i = base + j; i < hi; i += kHid)
+            if (to[i] == r) { const int p = atomicAdd(&s_cnt, 1); s_list[p] = (int)(i - base); s_d1[p] = d1[i]; }
+        __syncthreads();
+        const int cnt = s_cnt;
+        int k = 0;
+        for (; k + 4 <= cnt; k += 4) {
 #pragma unroll
-    for (int c = 0; c < 14; ++c) acc[c] = 0.0f;
-    for (int i = 0; i < cnt; ++i) {
-        const int code = s_code[i];                         // block-uniform
-        if (code == 0 || code == 15) continue;
-        const float d = delta0[(b0 + i) * kHid + j];
-#pragma unroll
-        for (int c = 0; c < 14; ++c) if (code == c + 1) acc[c] += d;
+            for (int u = 0; u < 4; ++u) acc[u] += s_d1[k + u] * Hf[(base + s_list[k + u]) * kHid + j];
+        }
+        for (; k < cnt; ++k) acc[0] += s_d1[k] * Hf[(base + s_list[k]) * kHid + j];
+        if (j == 0) for (int q = 0; q < cnt; ++q) bsum += s_d1[q];
+        __syncthreads();
     }
-    if (q == 90) { if (acc[0] != 0.0f) atomicAdd(grad + kGradB0 + j, acc[0]); return; }
+    const float a = (acc[0] + acc[1]) + (acc[2] + acc[3]);
+    if (a != 0.0f) atomicAdd(grad + kGradW1 + r * kHid + j, a);
+    if (j == 0 && bsum != 0.0f) atomicAdd(grad + kGradB1 + r, bsum);
+}
+
+// ---------------------------------------------------------------------------------------------
+// dW0^T = X^T . delta0 on tcgen05: C[feature 0..1279][hidden 0..127] = sum_b onehot_b[feature] * delta0_b[hidden].
+// (updateWeightsBiasesKernel for layer 0, src/dqn.cu:310-319, summed over the batch.)  Feature 1260 is a constant
+// one, so row 1260 of C is db0.  A operand: the transposed one-hot tile [128 features x 64 samples] is BUILT in
+// shared memory (128-byte-swizzled K-major layout) by 8 warps straight from the packed boards -- the 1260-wide
+// one-hot matrix never exists in HBM.  B operand: delta0^T as BF16 hi + lo (two MMAs, ~16 mantissa bits) by TMA.
+// CTA (m_tile, k_split) accumulates its sample range in TMEM and writes an FP32 partial; dw0_reduce_kernel sums them.
+constexpr int kFeatPad = 1280, kBiasFeat = kIn;
+constexpr int kDwMTiles = kFeatPad / BM;                 // 10
+constexpr int kDwStages = 3;
+constexpr uint32_t kDwABytes = BM * BK * 2;              // 16 KB
+constexpr uint32_t kDwBBytes = 2 * kHid * BK * 2;        // 32 KB (hi, lo)
+constexpr int kDwThreads = 384;                          // warp 0 TMA, 1 MMA, 2 TMEM alloc, 4-11 one-hot builders (4-7 also epilogue)
+constexpr size_t kDwSmem = 1024 + kDwStages * (kDwABytes + kDwBBytes) + 256;
+
+__device__ __forceinline__ uint32_t sw128_offset(int row, int col) {   // byte offset of bf16 (row, col) in a [rows x 64] SW128 K-major tile
+    return (uint32_t)((row >> 3) * 1024 + (row & 7) * 128 + ((((col >> 3) ^ row) & 7) << 4) + (col & 7) * 2);
+}
+
+__global__ void __launch_bounds__(kDwThreads, 1) dw0_gemm_kernel(const __grid_constant__ CUtensorMap tmHi, const __grid_constant__ CUtensorMap tmLo,
+                                                                const Transition* __restrict__ batch, int n, int k_splits,
+                                                                float* __restrict__ part) {
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+    uint8_t* sA = smem;                                        // [stage][128 features][64 samples]
+    uint8_t* sB = smem + kDwStages * kDwABytes;                // [stage][hi|lo][128 hidden][64 samples]
+    uint64_t* bars = reinterpret_cast<uint64_t*>(sB + kDwStages * kDwBBytes);
+    uint64_t* full = bars;                 // kDwStages: 1 TMA arrive(+tx) + 8 builder warps
+    uint64_t* empty = bars + kDwStages;    // kDwStages: MMA commit
+    uint64_t* acc_full = bars + 2 * kDwStages;
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * kDwStages + 1);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int mt = blockIdx.x, ks = blockIdx.y;
+    const int total_kb = (n + BK - 1) / BK;
+    const int my_kb = (total_kb - ks + k_splits - 1) / k_splits;     // k-blocks ks, ks + k_splits, ...
+    const int f0 = mt * BM;
+
+    if (threadIdx.x == 0) {
+        for (int i = 0; i < kDwStages; ++i) { tc::mbar_init(full + i, 9); tc::mbar_init(empty + i, 1); }
+        tc::mbar_init(acc_full, 1);
+        tc::fence_barrier_init();
+    }
+    if (warp == 2) tc::tmem_alloc<128>(tmem_slot);
+    tc::tc_fence_before();
+    __syncthreads();
+    tc::tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+
+    if (warp == 0) {
+        if (lane == 0) {   // ===== TMA producer: delta0^T hi / lo tiles =====
+            tc::prefetch_tmap(&tmHi); tc::prefetch_tmap(&tmLo);
+            for (int i = 0; i < my_kb; ++i) {
+                const int st = i % kDwStages, kb = ks + i * k_splits;
+                tc::mbar_wait(empty + st, ((i / kDwStages) & 1) ^ 1);
+                tc::mbar_expect_tx(full + st, kDwBBytes);
+                tc::tma_load_2d(sB + st * kDwBBytes, &tmHi, kb * BK, 0, full + st);
+                tc::tma_load_2d(sB + st * kDwBBytes + kDwBBytes / 2, &tmLo, kb * BK, 0, full + st);
+            }
+        }
+    } else if (warp == 1) {
+        if (lane == 0) {   // ===== MMA issuer =====
+            constexpr uint32_t idesc = tc::umma_idesc_bf16(BM, kHid);
+            for (int i = 0; i < my_kb; ++i) {
+                const int st = i % kDwStages;
+                tc::mbar_wait(full + st, (i / kDwStages) & 1);
+                tc::tc_fence_after();
 #pragma unroll
-    for (int c = 0; c < 14; ++c)
-        if (acc[c] != 0.0f) atomicAdd(grad + kGradW0 + (size_t)(q * 14 + c) * kHid + j, acc[c]);
+                for (int k = 0; k < BK / 16; ++k) {
+                    const uint64_t da = tc::umma_desc_sw128(tc::smem_u32(sA + st * kDwABytes) + k * 32);
+                    const uint64_t dh = tc::umma_desc_sw128(tc::smem_u32(sB + st * kDwBBytes) + k * 32);
+                    const uint64_t dl = tc::umma_desc_sw128(tc::smem_u32(sB + st * kDwBBytes + kDwBBytes / 2) + k * 32);
+                    tc::umma_bf16(tmem_base, da, dh, idesc, (i | k) != 0);
+                    tc::umma_bf16(tmem_base, da, dl, idesc, 1);
+                }
+                tc::umma_commit(empty + st);
+            }
+            tc::umma_commit(acc_full);
+        }
+    } else if (warp >= 4) {
+        // ===== one-hot^T builders: thread = (sample of the k-block, group of <= 3 squares of this feature tile) =====
+        const int bt = threadIdx.x - 128, sample = bt & 63, grp = bt >> 6;
+        const int q0 = f0 / 14;
+        for (int i = 0; i < my_kb; ++i) {
+            const int st = i % kDwStages, kb = ks + i * k_splits;
+            const int b = kb * BK + sample;
+            uint32_t off[3] = {0xFFFFFFFFu, 0xFFFFFFFFu, 0xFFFFFFFFu};
+            if (b < n) {
+                const uint32_t* sq = batch[b].s;
+#pragma unroll
+                for (int u = 0; u < 3; ++u) {
+                    const int q = q0 + grp + 4 * u;
+                    if (q < XQ_SQUARES) {
+                        const int code = (sq[q >> 3] >> (4 * (q & 7))) & 15;
+                        const int f = q * 14 + code - 1 - f0;
+                        if (code >= 1 && code <= 14 && f >= 0 && f < BM) off[u] = sw128_offset(f, sample);
+                    }
+                }
+                if (mt == kDwMTiles - 1 && grp == 3) off[2] = sw128_offset(kBiasFeat - f0, sample);      // constant-one feature -> db0
+            }
+            tc::mbar_wait(empty + st, ((i / kDwStages) & 1) ^ 1);
+            uint8_t* tile = sA + st * kDwABytes;
+            uint4* z = reinterpret_cast<uint4*>(tile + bt * 64);
+#pragma unroll
+            for (int u = 0; u < 4; ++u) z[u] = make_uint4(0u, 0u, 0u, 0u);
+            asm volatile("bar.sync 1, 256;" ::: "memory");                       // the 8 builder warps only
+#pragma unroll
+            for (int u = 0; u < 3; ++u)
+                if (off[u] != 0xFFFFFFFFu) *reinterpret_cast<uint16_t*>(tile + off[u]) = 0x3F80;    // BF16 1.0
+            tc::fence_proxy_async();                                             // generic-proxy stores -> visible to the tensor core
+            __syncwarp();
+            if (lane == 0) tc::mbar_arrive(full + st);
+        }
+        if (warp < 8) {   // ===== epilogue: TMEM -> FP32 partial [k_split][feature][hidden] =====
+            const int quarter = warp & 3;
+            tc::mbar_wait(acc_full, 0);
+            tc::tc_fence_after();
+            float* out = part + ((size_t)ks * kFeatPad + f0 + quarter * 32 + lane) * kHid;
+#pragma unroll 1
+            for (int c = 0; c < kHid / 16; ++c) {
+                uint32_t r[16];
+                tc::tmem_ld16_nowait(tmem_base + ((uint32_t)(quarter * 32) << 16) + c * 16, r);
+                tc::tmem_wait_ld();
+#pragma unroll
+                for (int j = 0; j < 16; j += 4)
+                    *reinterpret_cast<float4*>(out + c * 16 + j) = make_float4(__uint_as_float(r[j]), __uint_as_float(r[j + 1]),
+                                                                              __uint_as_float(r[j + 2]), __uint_as_float(r[j + 3]));
+            }
+        }
+    }
+    tc::tc_fence_before();
+    __syncthreads();
+    if (warp == 2) { tc::tc_fence_after(); tc::tmem_dealloc<128>(tmem_base); }
+}
+
+// grad[dW0^T | db0] += sum over the k-splits of the partials
+__global__ void __launch_bounds__(256) dw0_reduce_kernel(const float* __restrict__ part, int k_splits, float* __restrict__ grad) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;           // float4 index over (kIn + 1) rows x 128
+    if (i >= (kIn + 1) * kHid / 4) return;
+    float4 a = make_float4(0.f, 0.f, 0.f, 0.f);
+    for (int s = 0; s < k_splits; ++s) {
+        const float4 v = reinterpret_cast<const float4*>(part + (size_t)s * kFeatPad * kHid)[i];
+        a.x += v.x; a.y += v.y; a.z += v.z; a.w += v.w;
+    }
+    float4* g = reinterpret_cast<float4*>(grad) + i;               // rows 0..1259 = dW0^T, row 1260 = db0: contiguous in the compact gradient
+    float4 o = *g;
+    o.x += a.x; o.y += a.y; o.z += a.z; o.w += a.w;
+    *g = o;
 }
 
 // SGD: W -= lr * grad on the compact gradient (src/dqn.cu:310-319), refresh the BF16 operand rows, clear the gradient
@@ -326,11 +538,11 @@ static EncodeTiledFn encode_fn() {
     return fn;
 }
 // [rows][128] BF16 row-major, box = 64 columns x box_rows, 128-byte swizzle, out-of-range rows read as zero
-static int make_tmap(CUtensorMap* m, const void* base, int64_t rows, int box_rows) {
+static int make_tmap(CUtensorMap* m, const void* base, int64_t rows, int box_rows, int64_t cols = kHid, int64_t ld = kHid) {
     EncodeTiledFn fn = encode_fn();
     if (!fn) return fail(XQ_ERR_CUDA, "cuTensorMapEncodeTiled is not available from this driver");
-    cuuint64_t dims[2] = {(cuuint64_t)kHid, (cuuint64_t)rows};
-    cuuint64_t strides[1] = {(cuuint64_t)kHid * 2};
+    cuuint64_t dims[2] = {(cuuint64_t)cols, (cuuint64_t)rows};
+    cuuint64_t strides[1] = {(cuuint64_t)ld * 2};
     cuuint32_t box[2] = {(cuuint32_t)BK, (cuuint32_t)box_rows};
     cuuint32_t estr[2] = {1, 1};
     CUresult r = fn(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(base), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
@@ -340,6 +552,7 @@ static int make_tmap(CUtensorMap* m, const void* base, int64_t rows, int box_row
 }
 
 static inline unsigned blocks(int64_t n, int per) { return (unsigned)((n + per - 1) / per); }
+constexpr int kDwSplits = 14;                       // 10 feature tiles x 14 sample splits = 140 CTAs
 
 void dqn_fast_destroy(xq_dqn_s* h) {
     Fast* f = h->fast;
@@ -347,7 +560,7 @@ void dqn_fast_destroy(xq_dqn_s* h) {
     cudaFree(f->W0T); cudaFree(f->b0); cudaFree(f->W1); cudaFree(f->b1); cudaFree(f->W1bf);
     cudaFree(f->tW0T); cudaFree(f->tb0); cudaFree(f->tW1); cudaFree(f->tb1); cudaFree(f->tW1bf);
     cudaFree(f->grad); cudaFree(f->boards); cudaFree(f->Hbf); cudaFree(f->H2bf); cudaFree(f->Hf); cudaFree(f->zpart);
-    cudaFree(f->delta0); cudaFree(f->q); cudaFree(f->info);
+    cudaFree(f->d1); cudaFree(f->to8); cudaFree(f->d0hi); cudaFree(f->d0lo); cudaFree(f->part); cudaFree(f->q); cudaFree(f->info);
     delete f;
     h->fast = nullptr;
 }
@@ -371,22 +584,37 @@ static int fast_init(xq_dqn_s* h) {
     if (int rc = make_tmap(&f->tmTW1, f->tW1bf, kOut, BN)) return rc;
     XQ_CUDA(cudaFuncSetAttribute(l1_gemm_kernel<EPI_ROWMAX>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kGemmSmem));
     XQ_CUDA(cudaFuncSetAttribute(l1_gemm_kernel<EPI_STORE_TANH>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kGemmSmem));
+    XQ_CUDA(cudaFuncSetAttribute(dw0_gemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kDwSmem));
+    XQ_CUDA(cudaMalloc(&f->part, sizeof(float) * kDwSplits * kFeatPad * kHid));
     return XQ_OK;
 }
 
 static int fast_reserve(xq_dqn_s* h, int64_t n) {
     Fast* f = h->fast;
     if (n <= f->cap) return XQ_OK;
-    cudaFree(f->boards); cudaFree(f->Hbf); cudaFree(f->H2bf); cudaFree(f->Hf); cudaFree(f->zpart); cudaFree(f->delta0);
-    f->boards = nullptr; f->Hbf = f->H2bf = nullptr; f->Hf = f->zpart = f->delta0 = nullptr; f->cap = 0;
+    cudaFree(f->boards); cudaFree(f->Hbf); cudaFree(f->H2bf); cudaFree(f->Hf); cudaFree(f->zpart); cudaFree(f->d1); cudaFree(f->to8);
+    cudaFree(f->d0hi); cudaFree(f->d0lo);
+    f->boards = nullptr; f->Hbf = f->H2bf = nullptr; f->Hf = f->zpart = f->d1 = nullptr; f->to8 = nullptr; f->d0hi = f->d0lo = nullptr; f->cap = 0;
     const int64_t rows = (n + BM - 1) / BM * BM;
     XQ_CUDA(cudaMalloc(&f->boards, sizeof(Transition) * n));
     XQ_CUDA(cudaMalloc(&f->Hbf, sizeof(__nv_bfloat16) * rows * kHid)); XQ_CUDA(cudaMalloc(&f->H2bf, sizeof(__nv_bfloat16) * rows * kHid));
-    XQ_CUDA(cudaMalloc(&f->Hf, sizeof(float) * rows * kHid)); XQ_CUDA(cudaMalloc(&f->zpart, sizeof(float) * kNTiles * rows));
-    XQ_CUDA(cudaMalloc(&f->delta0, sizeof(float) * rows * kHid));
+    XQ_CUDA(cudaMalloc(&f->Hf, sizeof(float) * rows * kHid)); XQ_CUDA(cudaMalloc(&f->zpart, sizeof(float) * kParts * rows));
+    XQ_CUDA(cudaMalloc(&f->d1, sizeof(float) * rows)); XQ_CUDA(cudaMalloc(&f->to8, (size_t)rows));
+    XQ_CUDA(cudaMalloc(&f->d0hi, sizeof(__nv_bfloat16) * rows * kHid)); XQ_CUDA(cudaMalloc(&f->d0lo, sizeof(__nv_bfloat16) * rows * kHid));
+    f->cap = n; f->tm_rows = 0;
+    return XQ_OK;
+}
+
+// tensor maps whose extents follow the batch size (out-of-range rows / samples read as zero)
+static int fast_maps(xq_dqn_s* h, int64_t n) {
+    Fast* f = h->fast;
+    if (n == f->tm_rows) return XQ_OK;
+    const int64_t ld = (f->cap + BM - 1) / BM * BM;
     if (int rc = make_tmap(&f->tmH, f->Hbf, n, BM)) return rc;
     if (int rc = make_tmap(&f->tmH2, f->H2bf, n, BM)) return rc;
-    f->cap = n; f->tm_rows = n;
+    if (int rc = make_tmap(&f->tmD0hi, f->d0hi, kHid, kHid, n, ld)) return rc;     // delta0^T [128 hidden][n samples], row stride ld
+    if (int rc = make_tmap(&f->tmD0lo, f->d0lo, kHid, kHid, n, ld)) return rc;
+    f->tm_rows = n;
     return XQ_OK;
 }
 
@@ -457,7 +685,7 @@ int xq_dqn_forward_boards(xq_dqn_t h, const xq_env_rec* boards_host, int64_t n, 
     XQ_CUDA(cudaMemcpyAsync(f->boards, boards_host, sizeof(xq_env_rec) * n, cudaMemcpyHostToDevice, h->stream));
     l0_forward_kernel<<<blocks(n * 32, 256), 256, 0, h->stream>>>(reinterpret_cast<const uint8_t*>(f->boards), sizeof(xq_env_rec), n, f->W0T, f->b0, f->Hbf, nullptr);
     XQ_LAUNCH_CHECK();
-    if (n != f->tm_rows) { if (int rc = make_tmap(&f->tmH, f->Hbf, n, BM)) return rc; if (int rc = make_tmap(&f->tmH2, f->H2bf, n, BM)) return rc; f->tm_rows = n; }
+    if (int rc = fast_maps(h, n)) return rc;
     if (int rc = launch_gemm(h, EPI_STORE_TANH, f->tmH, f->tmW1, f->b1, n, f->q)) return rc;
     XQ_CUDA(cudaMemcpyAsync(q_host, f->q, sizeof(float) * n * kOut, cudaMemcpyDeviceToHost, h->stream));
     XQ_CUDA(cudaStreamSynchronize(h->stream));
@@ -471,7 +699,7 @@ int xq_dqn_td_update_device(xq_dqn_t h, const void* batch_dev, int64_t n, int us
     if (int rc = ensure_fast(h)) return rc;
     if (int rc = fast_reserve(h, n)) return rc;
     Fast* f = h->fast;
-    if (n != f->tm_rows) { if (int rc = make_tmap(&f->tmH, f->Hbf, n, BM)) return rc; if (int rc = make_tmap(&f->tmH2, f->H2bf, n, BM)) return rc; f->tm_rows = n; }
+    if (int rc = fast_maps(h, n)) return rc;
     const Transition* batch = reinterpret_cast<const Transition*>(batch_dev);
     const uint8_t* base = reinterpret_cast<const uint8_t*>(batch);
     if (lr <= 0) lr = h->lr;
@@ -484,10 +712,17 @@ int xq_dqn_td_update_device(xq_dqn_t h, const void* batch_dev, int64_t n, int us
     if (int rc = launch_gemm(h, EPI_ROWMAX, f->tmH2, use_target_net ? f->tmTW1 : f->tmW1, use_target_net ? f->tb1 : f->b1, n, nullptr)) return rc;
     XQ_CUDA(cudaMemsetAsync(f->info, 0, sizeof(float) * 4, h->stream));
     const int64_t zstride = (f->cap + BM - 1) / BM * BM;
-    td_delta_kernel<<<blocks(n * 32, 256), 256, 0, h->stream>>>(batch, n, f->Hf, f->W1, f->b1, f->zpart, zstride, kNTiles, (float)h->gamma, h->mode,
-                                                                f->delta0, f->grad, f->info);
+    const int64_t ld = zstride;
+    td_delta_kernel<<<blocks(n * 32, 256), 256, 0, h->stream>>>(batch, n, f->Hf, f->W1, f->b1, f->zpart, zstride, kParts, (float)h->gamma, h->mode,
+                                                                f->d1, f->to8, f->d0hi, f->d0lo, ld, f->info);
     XQ_LAUNCH_CHECK();
-    dw0_kernel<<<dim3(91, blocks(n, kDw0Chunk)), kHid, 0, h->stream>>>(batch, n, f->delta0, f->grad);
+    dw1_kernel<<<dim3(kQRows, kDw1Slices), kHid, 0, h->stream>>>(f->d1, f->to8, n, f->Hf, f->grad);
+    XQ_LAUNCH_CHECK();
+    const int total_kb = (int)((n + BK - 1) / BK);
+    const int k_splits = total_kb < kDwSplits ? total_kb : kDwSplits;
+    dw0_gemm_kernel<<<dim3(kDwMTiles, k_splits), kDwThreads, kDwSmem, h->stream>>>(f->tmD0hi, f->tmD0lo, batch, (int)n, k_splits, f->part);
+    XQ_LAUNCH_CHECK();
+    dw0_reduce_kernel<<<blocks((kIn + 1) * kHid / 4, 256), 256, 0, h->stream>>>(f->part, k_splits, f->grad);
     XQ_LAUNCH_CHECK();
     if (apply) {
         apply_kernel<<<blocks(kGradSize, 256), 256, 0, h->stream>>>(f->W0T, f->b0, f->W1, f->b1, f->W1bf, f->grad, (float)lr);
