@@ -25,7 +25,8 @@
 namespace xq {
 
 constexpr int kIn = XQ_STATE_SIZE, kHid = 128, kOut = 8100, kQRows = 90;   // Q is indexed by `to` < 90 (src/dqn.cpp:47)
-constexpr int kGradW0 = 0, kGradB0 = kIn * kHid, kGradW1 = kGradB0 + kHid, kGradB1 = kGradW1 + kQRows * kHid;
+[[maybe_unused]] constexpr int kGradW0 = 0;
+constexpr int kGradB0 = kIn * kHid, kGradW1 = kGradB0 + kHid, kGradB1 = kGradW1 + kQRows * kHid;
 constexpr int kGradSize = kGradB1 + kQRows;   // 173,018 floats: the only non-zero gradient entries of a TD step
 
 // ---- GEMM tile configuration ----------------------------------------------------------------
@@ -56,26 +57,34 @@ struct Fast {
     __nv_bfloat16 *Hbf = nullptr, *H2bf = nullptr;     // h(s), h(s') as MMA A operands [cap][128]
     float* Hf = nullptr;                               // h(s) FP32 [cap][128]
     float* zpart = nullptr;                            // [kParts][cap] row-max partials
-    float* d1 = nullptr;                               // [cap] delta1 of the taken action
     uint8_t* to8 = nullptr;                            // [cap] action.to
     __nv_bfloat16 *d0hi = nullptr, *d0lo = nullptr;    // delta0^T [128][ld] BF16 hi / lo (B operand of the dW0 contraction)
+    __nv_bfloat16 *ghi = nullptr, *glo = nullptr;      // (delta1 h)^T [128][ld] BF16 hi / lo (B operand of the dW1 contraction)
     float* part = nullptr;                             // [kDwSplits][1280][128] FP32 partials of dW0^T
     float* q = nullptr;                                // [cap][8100] (debug path only, allocated on demand)
     int64_t q_cap = 0;
     float* info = nullptr;                             // 4 floats
-    CUtensorMap tmW1, tmTW1, tmH, tmH2, tmD0hi, tmD0lo;
+    CUtensorMap tmW1, tmTW1, tmH, tmH2, tmD0hi, tmD0lo, tmGhi, tmGlo;
     int64_t tm_rows = 0;
+};
+
+// A TD batch is either a contiguous array of transitions or `n` uniform draws from a replay ring, resolved in place:
+// index_b = (xq_rng(seed, b, counter) >> 1) % size   (include/xq.h: xq_replay_sample).  No gather pass, no copy.
+struct BatchRef {
+    const uint8_t* base;      // transitions (128 B each)
+    int64_t size;             // ring size when sampled
+    uint64_t seed;
+    uint32_t counter;
+    int sampled;
+    __device__ __forceinline__ const uint8_t* at(int64_t b) const {
+        const int64_t i = sampled ? (int64_t)((rng(seed, (uint64_t)b, counter) >> 1) % (uint64_t)size) : b;
+        return base + i * 128;
+    }
 };
 
 // ---------------------------------------------------------------------------------------------
 // layer 0: one warp per board, lane owns 4 hidden units; <= 32 coalesced 512-byte row reads of W0^T
-__global__ void __launch_bounds__(256) l0_forward_kernel(const uint8_t* __restrict__ boards, int64_t stride_bytes, int64_t n,
-                                                        const float* __restrict__ W0T, const float* __restrict__ b0,
-                                                        __nv_bfloat16* __restrict__ Hbf, float* __restrict__ Hf) {
-    const int64_t s = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-    const int lane = threadIdx.x & 31;
-    if (s >= n) return;
-    const uint32_t* w = reinterpret_cast<const uint32_t*>(boards + s * stride_bytes);
+__device__ __forceinline__ float4 l0_gather(const uint32_t* __restrict__ w, int lane, const float* __restrict__ W0T, const float* __restrict__ b0) {
     const uint32_t word = lane < 12 ? w[lane] : 0u;
     float4 acc = reinterpret_cast<const float4*>(b0)[lane];
     for (int wi = 0; wi < 12; ++wi) {
@@ -91,12 +100,38 @@ __global__ void __launch_bounds__(256) l0_forward_kernel(const uint8_t* __restri
             }
         }
     }
-    const float4 h = make_float4(tanhf(acc.x), tanhf(acc.y), tanhf(acc.z), tanhf(acc.w));
-    if (Hf) reinterpret_cast<float4*>(Hf + s * kHid)[lane] = h;
+    return make_float4(tanhf(acc.x), tanhf(acc.y), tanhf(acc.z), tanhf(acc.w));
+}
+__device__ __forceinline__ void store_h_bf16(__nv_bfloat16* __restrict__ Hbf, int64_t s, int lane, const float4& h) {
     __nv_bfloat162 lo = __floats2bfloat162_rn(h.x, h.y), hi = __floats2bfloat162_rn(h.z, h.w);
     uint2 packed;
     packed.x = *reinterpret_cast<uint32_t*>(&lo); packed.y = *reinterpret_cast<uint32_t*>(&hi);
     reinterpret_cast<uint2*>(Hbf + s * kHid)[lane] = packed;
+}
+__global__ void __launch_bounds__(256) l0_forward_kernel(const uint8_t* __restrict__ boards, int64_t stride_bytes, int64_t n,
+                                                        const float* __restrict__ W0T, const float* __restrict__ b0,
+                                                        __nv_bfloat16* __restrict__ Hbf, float* __restrict__ Hf) {
+    const int64_t s = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int lane = threadIdx.x & 31;
+    if (s >= n) return;
+    const float4 h = l0_gather(reinterpret_cast<const uint32_t*>(boards + s * stride_bytes), lane, W0T, b0);
+    if (Hf) reinterpret_cast<float4*>(Hf + s * kHid)[lane] = h;
+    store_h_bf16(Hbf, s, lane, h);
+}
+// both states of every transition in one launch: warps [0,n) -> h(s) with the online net (BF16 + FP32),
+// warps [n,2n) -> h(s') with the bootstrap net (online: ChessAI::train; target: DQN::train)
+__global__ void __launch_bounds__(256) l0_pair_kernel(BatchRef batch, int64_t n, const float* __restrict__ W0T, const float* __restrict__ b0,
+                                                     const float* __restrict__ W0T2, const float* __restrict__ b02,
+                                                     __nv_bfloat16* __restrict__ Hbf, float* __restrict__ Hf, __nv_bfloat16* __restrict__ H2bf) {
+    const int64_t w = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int lane = threadIdx.x & 31;
+    if (w >= 2 * n) return;
+    const bool second = w >= n;
+    const int64_t s = second ? w - n : w;
+    const uint8_t* t = batch.at(s);
+    const float4 h = l0_gather(reinterpret_cast<const uint32_t*>(t + (second ? 48 : 0)), lane, second ? W0T2 : W0T, second ? b02 : b0);
+    if (!second) reinterpret_cast<float4*>(Hf + s * kHid)[lane] = h;
+    store_h_bf16(second ? H2bf : Hbf, s, lane, h);
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -245,20 +280,26 @@ static_assert(sizeof(Transition) == 128 && sizeof(xq_transition) == 128, "transi
 // TD error, one warp per transition (src/chessai.cpp:121-131 + src/dqn.cu:288-308 specialised to a one-hot delta1).
 // Outputs per sample: delta1, its row `to`, delta0 as FP32 and, transposed and split into BF16 hi + lo, as the
 // K-major B operand of the dW0 contraction.  No global atomics except 3 per CTA for the loss statistics.
-__global__ void __launch_bounds__(256) td_delta_kernel(const Transition* __restrict__ batch, int64_t n, const float* __restrict__ Hf,
+__global__ void __launch_bounds__(256) td_delta_kernel(BatchRef batch, int64_t n, const float* __restrict__ Hf,
                                                       const float* __restrict__ W1, const float* __restrict__ b1,
                                                       const float* __restrict__ zpart, int64_t zstride, int n_parts, float gamma, int mode,
-                                                      float* __restrict__ d1_out, uint8_t* __restrict__ to_out,
-                                                      __nv_bfloat16* __restrict__ d0hi, __nv_bfloat16* __restrict__ d0lo, int64_t ld,
-                                                      float* __restrict__ info) {
+                                                      uint8_t* __restrict__ to_out,
+                                                      __nv_bfloat16* __restrict__ d0hi, __nv_bfloat16* __restrict__ d0lo,
+                                                      __nv_bfloat16* __restrict__ ghi, __nv_bfloat16* __restrict__ glo, int64_t ld,
+                                                      float* __restrict__ gb1, float* __restrict__ info) {
     __shared__ float s_info[8][3];
-    __shared__ __align__(16) float s_d0[8][kHid];          // delta0 of the CTA's 8 consecutive samples, for the transposed store
+    __shared__ __align__(16) float s_d0[8][kHid];          // delta0 of the CTA's 8 consecutive samples, for the transposed stores
+    __shared__ __align__(16) float s_g[8][kHid];           // delta1 * h (the dW1 contraction's B operand)
+    __shared__ float s_d1[8];
+    __shared__ int s_to[8];
     const int64_t s = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
     float loss = 0.0f, qv = 0.0f, tv = 0.0f;
     reinterpret_cast<float4*>(s_d0[wib])[lane] = make_float4(0.f, 0.f, 0.f, 0.f);
+    reinterpret_cast<float4*>(s_g[wib])[lane] = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (lane == 0) { s_d1[wib] = 0.0f; s_to[wib] = -1; }
     if (s < n) {
-        const Transition* t = batch + s;
+        const Transition* t = reinterpret_cast<const Transition*>(batch.at(s));
         const int to = XQ_ACTION_TO(t->action);                // the Q index of the taken action is action.to (:124,:127)
         const float4 h = reinterpret_cast<const float4*>(Hf + s * kHid)[lane];
         const float4 w = reinterpret_cast<const float4*>(W1 + (size_t)to * kHid)[lane];
@@ -276,26 +317,39 @@ __global__ void __launch_bounds__(256) td_delta_kernel(const Transition* __restr
         const float d0[4] = {wd.x * d1 * (1.0f - h.x * h.x), wd.y * d1 * (1.0f - h.y * h.y), wd.z * d1 * (1.0f - h.z * h.z),
                              wd.w * d1 * (1.0f - h.w * h.w)};
         reinterpret_cast<float4*>(s_d0[wib])[lane] = make_float4(d0[0], d0[1], d0[2], d0[3]);
-        if (lane == 0) { d1_out[s] = d1; to_out[s] = (uint8_t)to; }
+        reinterpret_cast<float4*>(s_g[wib])[lane] = make_float4(d1 * h.x, d1 * h.y, d1 * h.z, d1 * h.w);
+        if (lane == 0) { to_out[s] = (uint8_t)to; s_d1[wib] = d1; s_to[wib] = to; }
         loss = 0.5f * (q - target) * (q - target); qv = q; tv = target;
     }
     if (lane == 0) { s_info[wib][0] = loss; s_info[wib][1] = qv; s_info[wib][2] = tv; }
     __syncthreads();
-    {   // delta0^T[j][s0..s0+7] as BF16 hi (threads 0..127) / lo (128..255): one 16-byte store per (unit, array)
+    {   // delta0^T[j][s0..s0+7] and (delta1 h)^T[j][s0..s0+7] as BF16 hi (threads 0..127) / lo (128..255): 16-byte stores
         const int j = threadIdx.x & (kHid - 1);
         const bool want_lo = threadIdx.x >= kHid;
         const int64_t s0 = (int64_t)blockIdx.x * 8;
-        uint32_t packed[4];
 #pragma unroll
-        for (int p = 0; p < 4; ++p) {
-            float v0 = s_d0[2 * p][j], v1 = s_d0[2 * p + 1][j];
-            const __nv_bfloat16 h0 = __float2bfloat16_rn(v0), h1 = __float2bfloat16_rn(v1);
-            __nv_bfloat162 o;
-            if (want_lo) { o.x = __float2bfloat16_rn(v0 - __bfloat162float(h0)); o.y = __float2bfloat16_rn(v1 - __bfloat162float(h1)); }
-            else { o.x = h0; o.y = h1; }
-            packed[p] = *reinterpret_cast<uint32_t*>(&o);
+        for (int which = 0; which < 2; ++which) {
+            uint32_t packed[4];
+#pragma unroll
+            for (int p = 0; p < 4; ++p) {
+                const float v0 = which ? s_g[2 * p][j] : s_d0[2 * p][j], v1 = which ? s_g[2 * p + 1][j] : s_d0[2 * p + 1][j];
+                const __nv_bfloat16 h0 = __float2bfloat16_rn(v0), h1 = __float2bfloat16_rn(v1);
+                __nv_bfloat162 o;
+                if (want_lo) { o.x = __float2bfloat16_rn(v0 - __bfloat162float(h0)); o.y = __float2bfloat16_rn(v1 - __bfloat162float(h1)); }
+                else { o.x = h0; o.y = h1; }
+                packed[p] = *reinterpret_cast<uint32_t*>(&o);
+            }
+            __nv_bfloat16* dst = which ? (want_lo ? glo : ghi) : (want_lo ? d0lo : d0hi);
+            if (s0 < ld) *reinterpret_cast<uint4*>(dst + (int64_t)j * ld + s0) = make_uint4(packed[0], packed[1], packed[2], packed[3]);
         }
-        if (s0 < ld) *reinterpret_cast<uint4*>((want_lo ? d0lo : d0hi) + (int64_t)j * ld + s0) = make_uint4(packed[0], packed[1], packed[2], packed[3]);
+    }
+    if (threadIdx.x < 8) {   // db1[to] += delta1, equal rows of the CTA's 8 samples merged first (a greedy policy concentrates them)
+        const int to = s_to[threadIdx.x];
+        const float d = s_d1[threadIdx.x];
+        const unsigned peers = __match_any_sync(0xFFu, to);
+        float sum = 0.0f;
+        for (int k = 0; k < 8; ++k) if (peers >> k & 1u) sum += __shfl_sync(0xFFu, d, k);
+        if (to >= 0 && to < kQRows && (int)(__ffs(peers) - 1) == (int)threadIdx.x) atomicAdd(gb1 + to, sum);
     }
     if (threadIdx.x < 3) {
         float a = 0.0f;
@@ -303,42 +357,6 @@ __global__ void __launch_bounds__(256) td_delta_kernel(const Transition* __restr
         for (int k = 0; k < 8; ++k) a += s_info[k][threadIdx.x];
         atomicAdd(info + threadIdx.x, a);
     }
-}
-
-// dW1[r][:] = sum over the samples whose action.to == r of delta1 * h, db1[r] = sum delta1 (updateWeightsBiasesKernel,
-// src/dqn.cu:310-319, for a one-hot delta1).  CTA (r, slice) scans its slice of the batch in blocks of 1024 samples:
-// matches are compacted into shared memory, then accumulated 8 loads at a time; one atomicAdd per (row, unit, slice).
-// Robust to skew (a greedy policy can put most of a batch on one square).
-constexpr int kDw1Slices = 4;
-__global__ void __launch_bounds__(kHid) dw1_kernel(const float* __restrict__ d1, const uint8_t* __restrict__ to, int64_t n,
-                                                  const float* __restrict__ Hf, float* __restrict__ grad) {
-    __shared__ int s_list[1024];
-    __shared__ float s_d1[1024];
-    __shared__ int s_cnt;
-    const int r = blockIdx.x, j = threadIdx.x;
-    const int64_t per = (n + kDw1Slices - 1) / kDw1Slices;
-    const int64_t lo = blockIdx.y * per, hi_all = min(n, lo + per);
-    float acc[4] = {0.f, 0.f, 0.f, 0.f}, bsum = 0.0f;
-    for (int64_t base = lo; base < hi_all; base += 1024) {
-        if (j == 0) s_cnt = 0;
-        __syncthreads();
-        const int64_t hi = min(hi_all, base + 1024);
-        for (int64_t i = base + j; i < hi; i += kHid)
-            if (to[i] == r) { const int p = atomicAdd(&s_cnt, 1); s_list[p] = (int)(i - base); s_d1[p] = d1[i]; }
-        __syncthreads();
-        const int cnt = s_cnt;
-        int k = 0;
-        for (; k + 4 <= cnt; k += 4) {
-#pragma unroll
-            for (int u = 0; u < 4; ++u) acc[u] += s_d1[k + u] * Hf[(base + s_list[k + u]) * kHid + j];
-        }
-        for (; k < cnt; ++k) acc[0] += s_d1[k] * Hf[(base + s_list[k]) * kHid + j];
-        if (j == 0) for (int q = 0; q < cnt; ++q) bsum += s_d1[q];
-        __syncthreads();
-    }
-    const float a = (acc[0] + acc[1]) + (acc[2] + acc[3]);
-    if (a != 0.0f) atomicAdd(grad + kGradW1 + r * kHid + j, a);
-    if (j == 0 && bsum != 0.0f) atomicAdd(grad + kGradB1 + r, bsum);
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -349,7 +367,8 @@ __global__ void __launch_bounds__(kHid) dw1_kernel(const float* __restrict__ d1,
 // one-hot matrix never exists in HBM.  B operand: delta0^T as BF16 hi + lo (two MMAs, ~16 mantissa bits) by TMA.
 // CTA (m_tile, k_split) accumulates its sample range in TMEM and writes an FP32 partial; dw0_reduce_kernel sums them.
 constexpr int kFeatPad = 1280, kBiasFeat = kIn;
-constexpr int kDwMTiles = kFeatPad / BM;                 // 10
+constexpr int kDwMTiles = kFeatPad / BM + 1;             // 10 feature tiles of dW0^T (+ db0) and one tile for dW1 (rows = action.to)
+constexpr int kDwRows = kDwMTiles * BM;                  // 1408 rows per partial
 constexpr int kDwStages = 3;
 constexpr uint32_t kDwABytes = BM * BK * 2;              // 16 KB
 constexpr uint32_t kDwBBytes = 2 * kHid * BK * 2;        // 32 KB (hi, lo)
@@ -360,8 +379,9 @@ __device__ __forceinline__ uint32_t sw128_offset(int row, int col) {   // byte o
     return (uint32_t)((row >> 3) * 1024 + (row & 7) * 128 + ((((col >> 3) ^ row) & 7) << 4) + (col & 7) * 2);
 }
 
-__global__ void __launch_bounds__(kDwThreads, 1) dw0_gemm_kernel(const __grid_constant__ CUtensorMap tmHi, const __grid_constant__ CUtensorMap tmLo,
-                                                                const Transition* __restrict__ batch, int n, int k_splits,
+__global__ void __launch_bounds__(kDwThreads, 1) dw0_gemm_kernel(const __grid_constant__ CUtensorMap tmD0Hi, const __grid_constant__ CUtensorMap tmD0Lo,
+                                                                const __grid_constant__ CUtensorMap tmGHi, const __grid_constant__ CUtensorMap tmGLo,
+                                                                BatchRef batch, const uint8_t* __restrict__ to8, int n, int k_splits,
                                                                 float* __restrict__ part) {
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
@@ -378,6 +398,9 @@ __global__ void __launch_bounds__(kDwThreads, 1) dw0_gemm_kernel(const __grid_co
     const int total_kb = (n + BK - 1) / BK;
     const int my_kb = (total_kb - ks + k_splits - 1) / k_splits;     // k-blocks ks, ks + k_splits, ...
     const int f0 = mt * BM;
+    const bool w1_tile = mt == kDwMTiles - 1;            // the dW1 tile: A = one-hot of action.to, B = (delta1 h)^T
+    const CUtensorMap& tmHi = w1_tile ? tmGHi : tmD0Hi;
+    const CUtensorMap& tmLo = w1_tile ? tmGLo : tmD0Lo;
 
     if (threadIdx.x == 0) {
         for (int i = 0; i < kDwStages; ++i) { tc::mbar_init(full + i, 9); tc::mbar_init(empty + i, 1); }
@@ -428,8 +451,10 @@ __global__ void __launch_bounds__(kDwThreads, 1) dw0_gemm_kernel(const __grid_co
             const int st = i % kDwStages, kb = ks + i * k_splits;
             const int b = kb * BK + sample;
             uint32_t off[3] = {0xFFFFFFFFu, 0xFFFFFFFFu, 0xFFFFFFFFu};
-            if (b < n) {
-                const uint32_t* sq = batch[b].s;
+            if (b < n && w1_tile) {
+                if (grp == 0) off[0] = sw128_offset(to8[b], sample);                                      // row = action.to (< 128)
+            } else if (b < n) {
+                const uint32_t* sq = reinterpret_cast<const uint32_t*>(batch.at(b));
 #pragma unroll
                 for (int u = 0; u < 3; ++u) {
                     const int q = q0 + grp + 4 * u;
@@ -439,7 +464,7 @@ __global__ void __launch_bounds__(kDwThreads, 1) dw0_gemm_kernel(const __grid_co
                         if (code >= 1 && code <= 14 && f >= 0 && f < BM) off[u] = sw128_offset(f, sample);
                     }
                 }
-                if (mt == kDwMTiles - 1 && grp == 3) off[2] = sw128_offset(kBiasFeat - f0, sample);      // constant-one feature -> db0
+                if (mt == kDwMTiles - 2 && grp == 3) off[2] = sw128_offset(kBiasFeat - f0, sample);      // constant-one feature -> db0
             }
             tc::mbar_wait(empty + st, ((i / kDwStages) & 1) ^ 1);
             uint8_t* tile = sA + st * kDwABytes;
@@ -458,7 +483,7 @@ __global__ void __launch_bounds__(kDwThreads, 1) dw0_gemm_kernel(const __grid_co
             const int quarter = warp & 3;
             tc::mbar_wait(acc_full, 0);
             tc::tc_fence_after();
-            float* out = part + ((size_t)ks * kFeatPad + f0 + quarter * 32 + lane) * kHid;
+            float* out = part + ((size_t)ks * kDwRows + f0 + quarter * 32 + lane) * kHid;
 #pragma unroll 1
             for (int c = 0; c < kHid / 16; ++c) {
                 uint32_t r[16];
@@ -476,19 +501,37 @@ __global__ void __launch_bounds__(kDwThreads, 1) dw0_gemm_kernel(const __grid_co
     if (warp == 2) { tc::tc_fence_after(); tc::tmem_dealloc<128>(tmem_base); }
 }
 
-// grad[dW0^T | db0] += sum over the k-splits of the partials
-__global__ void __launch_bounds__(256) dw0_reduce_kernel(const float* __restrict__ part, int k_splits, float* __restrict__ grad) {
-    const int i = blockIdx.x * blockDim.x + threadIdx.x;           // float4 index over (kIn + 1) rows x 128
-    if (i >= (kIn + 1) * kHid / 4) return;
-    float4 a = make_float4(0.f, 0.f, 0.f, 0.f);
-    for (int s = 0; s < k_splits; ++s) {
-        const float4 v = reinterpret_cast<const float4*>(part + (size_t)s * kFeatPad * kHid)[i];
-        a.x += v.x; a.y += v.y; a.z += v.z; a.w += v.w;
+// gradient = sum over the k-splits of the partials: rows 0..1259 dW0^T, row 1260 db0, rows 1280..1369 dW1 rows 0..89 (db1 was
+// accumulated by td_delta_kernel).  APPLY: the SGD step W -= lr * grad (updateWeightsBiasesKernel, src/dqn.cu:310-319) is fused
+// and the BF16 operand copy of the touched W1 rows refreshed; otherwise the compact gradient is written for the all-reduce.
+template <bool APPLY>
+__global__ void __launch_bounds__(256) dw_reduce_kernel(const float* __restrict__ part, int k_splits, float* __restrict__ grad, float* __restrict__ W0T,
+                                                       float* __restrict__ b0, float* __restrict__ W1, float* __restrict__ b1,
+                                                       __nv_bfloat16* __restrict__ W1bf, float lr) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;           // float4 index over the compact gradient (without db1)
+    if (i < kGradB1 / 4) {
+        const int e = 4 * i;                                        // element of the compact gradient
+        const int row = e < kGradW1 ? e / kHid : kFeatPad + (e - kGradW1) / kHid;      // row of the partial
+        const int col = e % kHid;
+        float4 a = make_float4(0.f, 0.f, 0.f, 0.f);
+        for (int s = 0; s < k_splits; ++s) {
+            const float4 v = *reinterpret_cast<const float4*>(part + ((size_t)s * kDwRows + row) * kHid + col);
+            a.x += v.x; a.y += v.y; a.z += v.z; a.w += v.w;
+        }
+        if (!APPLY) { reinterpret_cast<float4*>(grad)[i] = a; return; }
+        float* dst = e < kGradB0 ? W0T + e : (e < kGradW1 ? b0 + (e - kGradB0) : W1 + (e - kGradW1));
+        float4 w = *reinterpret_cast<float4*>(dst);
+        w.x -= lr * a.x; w.y -= lr * a.y; w.z -= lr * a.z; w.w -= lr * a.w;
+        *reinterpret_cast<float4*>(dst) = w;
+        if (e >= kGradW1) {
+            __nv_bfloat162 p0 = __floats2bfloat162_rn(w.x, w.y), p1 = __floats2bfloat162_rn(w.z, w.w);
+            uint2 pk; pk.x = *reinterpret_cast<uint32_t*>(&p0); pk.y = *reinterpret_cast<uint32_t*>(&p1);
+            *reinterpret_cast<uint2*>(W1bf + (e - kGradW1)) = pk;
+        }
+    } else if (APPLY) {
+        const int r = i - kGradB1 / 4;                              // db1: one thread per row
+        if (r < kQRows) { b1[r] -= lr * grad[kGradB1 + r]; }
     }
-    float4* g = reinterpret_cast<float4*>(grad) + i;               // rows 0..1259 = dW0^T, row 1260 = db0: contiguous in the compact gradient
-    float4 o = *g;
-    o.x += a.x; o.y += a.y; o.z += a.z; o.w += a.w;
-    *g = o;
 }
 
 // SGD: W -= lr * grad on the compact gradient (src/dqn.cu:310-319), refresh the BF16 operand rows, clear the gradient
@@ -552,7 +595,7 @@ static int make_tmap(CUtensorMap* m, const void* base, int64_t rows, int box_row
 }
 
 static inline unsigned blocks(int64_t n, int per) { return (unsigned)((n + per - 1) / per); }
-constexpr int kDwSplits = 14;                       // 10 feature tiles x 14 sample splits = 140 CTAs
+constexpr int kDwSplits = 13;                       // 11 row tiles x 13 sample splits = 143 CTAs
 
 void dqn_fast_destroy(xq_dqn_s* h) {
     Fast* f = h->fast;
@@ -560,7 +603,7 @@ void dqn_fast_destroy(xq_dqn_s* h) {
     cudaFree(f->W0T); cudaFree(f->b0); cudaFree(f->W1); cudaFree(f->b1); cudaFree(f->W1bf);
     cudaFree(f->tW0T); cudaFree(f->tb0); cudaFree(f->tW1); cudaFree(f->tb1); cudaFree(f->tW1bf);
     cudaFree(f->grad); cudaFree(f->boards); cudaFree(f->Hbf); cudaFree(f->H2bf); cudaFree(f->Hf); cudaFree(f->zpart);
-    cudaFree(f->d1); cudaFree(f->to8); cudaFree(f->d0hi); cudaFree(f->d0lo); cudaFree(f->part); cudaFree(f->q); cudaFree(f->info);
+    cudaFree(f->to8); cudaFree(f->d0hi); cudaFree(f->d0lo); cudaFree(f->ghi); cudaFree(f->glo); cudaFree(f->part); cudaFree(f->q);
     delete f;
     h->fast = nullptr;
 }
@@ -578,29 +621,31 @@ static int fast_init(xq_dqn_s* h) {
     XQ_CUDA(cudaMalloc(&f->tW0T, sizeof(float) * kIn * kHid)); XQ_CUDA(cudaMalloc(&f->tb0, sizeof(float) * kHid));
     XQ_CUDA(cudaMalloc(&f->tW1, sizeof(float) * kOut * kHid)); XQ_CUDA(cudaMalloc(&f->tb1, sizeof(float) * kOut));
     XQ_CUDA(cudaMalloc(&f->tW1bf, sizeof(__nv_bfloat16) * kOut * kHid));
-    XQ_CUDA(cudaMalloc(&f->grad, sizeof(float) * kGradSize)); XQ_CUDA(cudaMalloc(&f->info, sizeof(float) * 4));
-    XQ_CUDA(cudaMemsetAsync(f->grad, 0, sizeof(float) * kGradSize, h->stream));
+    XQ_CUDA(cudaMalloc(&f->grad, sizeof(float) * (kGradSize + 8)));      // + 4 floats of loss statistics right behind db1
+    f->info = f->grad + kGradSize;
+    XQ_CUDA(cudaMemsetAsync(f->grad, 0, sizeof(float) * (kGradSize + 8), h->stream));
     if (int rc = make_tmap(&f->tmW1, f->W1bf, kOut, BN)) return rc;
     if (int rc = make_tmap(&f->tmTW1, f->tW1bf, kOut, BN)) return rc;
     XQ_CUDA(cudaFuncSetAttribute(l1_gemm_kernel<EPI_ROWMAX>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kGemmSmem));
     XQ_CUDA(cudaFuncSetAttribute(l1_gemm_kernel<EPI_STORE_TANH>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kGemmSmem));
     XQ_CUDA(cudaFuncSetAttribute(dw0_gemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kDwSmem));
-    XQ_CUDA(cudaMalloc(&f->part, sizeof(float) * kDwSplits * kFeatPad * kHid));
+    XQ_CUDA(cudaMalloc(&f->part, sizeof(float) * kDwSplits * kDwRows * kHid));
     return XQ_OK;
 }
 
 static int fast_reserve(xq_dqn_s* h, int64_t n) {
     Fast* f = h->fast;
     if (n <= f->cap) return XQ_OK;
-    cudaFree(f->boards); cudaFree(f->Hbf); cudaFree(f->H2bf); cudaFree(f->Hf); cudaFree(f->zpart); cudaFree(f->d1); cudaFree(f->to8);
-    cudaFree(f->d0hi); cudaFree(f->d0lo);
-    f->boards = nullptr; f->Hbf = f->H2bf = nullptr; f->Hf = f->zpart = f->d1 = nullptr; f->to8 = nullptr; f->d0hi = f->d0lo = nullptr; f->cap = 0;
+    cudaFree(f->boards); cudaFree(f->Hbf); cudaFree(f->H2bf); cudaFree(f->Hf); cudaFree(f->zpart); cudaFree(f->to8);
+    cudaFree(f->d0hi); cudaFree(f->d0lo); cudaFree(f->ghi); cudaFree(f->glo);
+    f->boards = nullptr; f->Hbf = f->H2bf = nullptr; f->Hf = f->zpart = nullptr; f->to8 = nullptr; f->d0hi = f->d0lo = f->ghi = f->glo = nullptr; f->cap = 0;
     const int64_t rows = (n + BM - 1) / BM * BM;
     XQ_CUDA(cudaMalloc(&f->boards, sizeof(Transition) * n));
     XQ_CUDA(cudaMalloc(&f->Hbf, sizeof(__nv_bfloat16) * rows * kHid)); XQ_CUDA(cudaMalloc(&f->H2bf, sizeof(__nv_bfloat16) * rows * kHid));
     XQ_CUDA(cudaMalloc(&f->Hf, sizeof(float) * rows * kHid)); XQ_CUDA(cudaMalloc(&f->zpart, sizeof(float) * kParts * rows));
-    XQ_CUDA(cudaMalloc(&f->d1, sizeof(float) * rows)); XQ_CUDA(cudaMalloc(&f->to8, (size_t)rows));
+    XQ_CUDA(cudaMalloc(&f->to8, (size_t)rows));
     XQ_CUDA(cudaMalloc(&f->d0hi, sizeof(__nv_bfloat16) * rows * kHid)); XQ_CUDA(cudaMalloc(&f->d0lo, sizeof(__nv_bfloat16) * rows * kHid));
+    XQ_CUDA(cudaMalloc(&f->ghi, sizeof(__nv_bfloat16) * rows * kHid)); XQ_CUDA(cudaMalloc(&f->glo, sizeof(__nv_bfloat16) * rows * kHid));
     f->cap = n; f->tm_rows = 0;
     return XQ_OK;
 }
@@ -614,6 +659,8 @@ static int fast_maps(xq_dqn_s* h, int64_t n) {
     if (int rc = make_tmap(&f->tmH2, f->H2bf, n, BM)) return rc;
     if (int rc = make_tmap(&f->tmD0hi, f->d0hi, kHid, kHid, n, ld)) return rc;     // delta0^T [128 hidden][n samples], row stride ld
     if (int rc = make_tmap(&f->tmD0lo, f->d0lo, kHid, kHid, n, ld)) return rc;
+    if (int rc = make_tmap(&f->tmGhi, f->ghi, kHid, kHid, n, ld)) return rc;
+    if (int rc = make_tmap(&f->tmGlo, f->glo, kHid, kHid, n, ld)) return rc;
     f->tm_rows = n;
     return XQ_OK;
 }
@@ -692,44 +739,56 @@ int xq_dqn_forward_boards(xq_dqn_t h, const xq_env_rec* boards_host, int64_t n, 
     return XQ_OK;
 }
 
-// device-resident TD update on n transitions already in device memory
-int xq_dqn_td_update_device(xq_dqn_t h, const void* batch_dev, int64_t n, int use_target_net, double lr, int apply) {
-    XQ_DQN_ENTER(h);
-    if (!batch_dev || n <= 0) return fail(XQ_ERR_INVALID, "xq_dqn_td_update_device: bad arguments");
+}  // extern "C" (reopened below)
+namespace xq {
+// one batched TD update on the batch described by `ref` (contiguous transitions or in-place replay draws): 5 launches
+int td_update_core(xq_dqn_s* h, const BatchRef& ref, int64_t n, int use_target_net, double lr, int apply) {
     if (int rc = ensure_fast(h)) return rc;
     if (int rc = fast_reserve(h, n)) return rc;
     Fast* f = h->fast;
     if (int rc = fast_maps(h, n)) return rc;
-    const Transition* batch = reinterpret_cast<const Transition*>(batch_dev);
-    const uint8_t* base = reinterpret_cast<const uint8_t*>(batch);
     if (lr <= 0) lr = h->lr;
+    const int64_t ld = (f->cap + BM - 1) / BM * BM;
     // h(s) with the online net; h(s') with the online (ChessAI::train) or target (DQN::train) net
-    l0_forward_kernel<<<blocks(n * 32, 256), 256, 0, h->stream>>>(base, sizeof(Transition), n, f->W0T, f->b0, f->Hbf, f->Hf);
-    XQ_LAUNCH_CHECK();
-    l0_forward_kernel<<<blocks(n * 32, 256), 256, 0, h->stream>>>(base + 48, sizeof(Transition), n, use_target_net ? f->tW0T : f->W0T,
-                                                                  use_target_net ? f->tb0 : f->b0, f->H2bf, nullptr);
+    l0_pair_kernel<<<blocks(2 * n * 32, 256), 256, 0, h->stream>>>(ref, n, f->W0T, f->b0, use_target_net ? f->tW0T : f->W0T,
+                                                                 use_target_net ? f->tb0 : f->b0, f->Hbf, f->Hf, f->H2bf);
     XQ_LAUNCH_CHECK();
     if (int rc = launch_gemm(h, EPI_ROWMAX, f->tmH2, use_target_net ? f->tmTW1 : f->tmW1, use_target_net ? f->tb1 : f->b1, n, nullptr)) return rc;
-    XQ_CUDA(cudaMemsetAsync(f->info, 0, sizeof(float) * 4, h->stream));
-    const int64_t zstride = (f->cap + BM - 1) / BM * BM;
-    const int64_t ld = zstride;
-    td_delta_kernel<<<blocks(n * 32, 256), 256, 0, h->stream>>>(batch, n, f->Hf, f->W1, f->b1, f->zpart, zstride, kParts, (float)h->gamma, h->mode,
-                                                                f->d1, f->to8, f->d0hi, f->d0lo, ld, f->info);
-    XQ_LAUNCH_CHECK();
-    dw1_kernel<<<dim3(kQRows, kDw1Slices), kHid, 0, h->stream>>>(f->d1, f->to8, n, f->Hf, f->grad);
+    XQ_CUDA(cudaMemsetAsync(f->grad + kGradB1, 0, sizeof(float) * (kQRows + 8), h->stream));      // db1 and the loss statistics
+    td_delta_kernel<<<blocks(n * 32, 256), 256, 0, h->stream>>>(ref, n, f->Hf, f->W1, f->b1, f->zpart, ld, kParts, (float)h->gamma, h->mode,
+                                                                f->to8, f->d0hi, f->d0lo, f->ghi, f->glo, ld, f->grad + kGradB1, f->info);
     XQ_LAUNCH_CHECK();
     const int total_kb = (int)((n + BK - 1) / BK);
     const int k_splits = total_kb < kDwSplits ? total_kb : kDwSplits;
-    dw0_gemm_kernel<<<dim3(kDwMTiles, k_splits), kDwThreads, kDwSmem, h->stream>>>(f->tmD0hi, f->tmD0lo, batch, (int)n, k_splits, f->part);
+    dw0_gemm_kernel<<<dim3(kDwMTiles, k_splits), kDwThreads, kDwSmem, h->stream>>>(f->tmD0hi, f->tmD0lo, f->tmGhi, f->tmGlo, ref, f->to8, (int)n,
+                                                                                   k_splits, f->part);
     XQ_LAUNCH_CHECK();
-    dw0_reduce_kernel<<<blocks((kIn + 1) * kHid / 4, 256), 256, 0, h->stream>>>(f->part, k_splits, f->grad);
-    XQ_LAUNCH_CHECK();
+    const unsigned rb = blocks(kGradB1 / 4 + kQRows, 256);
     if (apply) {
-        apply_kernel<<<blocks(kGradSize, 256), 256, 0, h->stream>>>(f->W0T, f->b0, f->W1, f->b1, f->W1bf, f->grad, (float)lr);
-        XQ_LAUNCH_CHECK();
+        dw_reduce_kernel<true><<<rb, 256, 0, h->stream>>>(f->part, k_splits, f->grad, f->W0T, f->b0, f->W1, f->b1, f->W1bf, (float)lr);
         h->f64_current = false;
+    } else {
+        dw_reduce_kernel<false><<<rb, 256, 0, h->stream>>>(f->part, k_splits, f->grad, f->W0T, f->b0, f->W1, f->b1, f->W1bf, (float)lr);
     }
+    XQ_LAUNCH_CHECK();
     return XQ_OK;
+}
+
+int dqn_td_update_sampled(xq_dqn_s* h, const void* ring, int64_t size, uint64_t seed, uint32_t counter, int64_t n, int use_target_net,
+                          double lr, int apply) {
+    const BatchRef ref{reinterpret_cast<const uint8_t*>(ring), size, seed, counter, 1};
+    return td_update_core(h, ref, n, use_target_net, lr, apply);
+}
+
+}  // namespace xq
+using namespace xq;
+extern "C" {
+
+int xq_dqn_td_update_device(xq_dqn_t h, const void* batch_dev, int64_t n, int use_target_net, double lr, int apply) {
+    XQ_DQN_ENTER(h);
+    if (!batch_dev || n <= 0) return fail(XQ_ERR_INVALID, "xq_dqn_td_update_device: bad arguments");
+    const BatchRef ref{reinterpret_cast<const uint8_t*>(batch_dev), n, 0, 0, 0};
+    return td_update_core(h, ref, n, use_target_net, lr, apply);
 }
 
 int xq_dqn_td_update(xq_dqn_t h, const xq_transition* batch_host, int64_t n, int use_target_net, double lr, float* info_host) {

@@ -42,5 +42,8 @@ int dqn_ensure_f64(xq_dqn_s* h);      // refresh the FP64 parameters from the fa
 void dqn_fast_destroy(xq_dqn_s* h);
 void dqn_target_changed(xq_dqn_s* h);
 struct FastWeights { const float *W0T, *b0, *W1, *b1; };
-int dqn_fast_weights(xq_dqn_s* h, FastWeights* out);   // brings the FP32 copies up to date and returns them   // the FP64 target parameters were rewritten
+int dqn_fast_weights(xq_dqn_s* h, FastWeights* out);
+// TD update on n uniform draws from a replay ring, resolved in place (no gather pass)
+int dqn_td_update_sampled(xq_dqn_s* h, const void* ring, int64_t size, uint64_t seed, uint32_t counter, int64_t n, int use_target_net,
+                          double lr, int apply);   // brings the FP32 copies up to date and returns them   // the FP64 target parameters were rewritten
 }

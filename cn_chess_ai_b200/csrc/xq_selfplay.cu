@@ -358,8 +358,9 @@ int xq_dqn_td_update_replay(xq_dqn_t h, xq_replay_t r, int64_t batch, uint64_t s
     if (!h || !r || batch <= 0) return fail(XQ_ERR_INVALID, "xq_dqn_td_update_replay: bad arguments");
     if (r->device != h->device) return fail(XQ_ERR_INVALID, "xq_dqn_td_update_replay: handles live on different devices");
     XQ_CUDA(cudaSetDevice(h->device));
-    if (int rc = replay_sample_dev(r, batch, seed, counter, h->stream, false)) return rc;
-    return xq_dqn_td_update_device(h, r->d_batch, batch, use_target_net, lr, apply);
+    const int64_t size = r->total < r->capacity ? r->total : r->capacity;
+    if (size <= 0) return fail(XQ_ERR_STATE, "xq_dqn_td_update_replay: the buffer is empty");
+    return dqn_td_update_sampled(h, r->d_ring, size, seed, counter, batch, use_target_net, lr, apply);
 }
 
 }  // extern "C"
