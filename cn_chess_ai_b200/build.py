@@ -31,7 +31,7 @@ def build_native(force=False, verbose=False):
     """Compile every .cu under csrc/ into libxq_b200.so for sm_100a.  Returns the library path."""
     if not force and not stale():
         return LIB
-    cmd = [NVCC] + FLAGS + ["-o", LIB] + sources() + ["-lcuda"]
+    cmd = [NVCC] + FLAGS + os.environ.get("XQ_NVCC_EXTRA", "").split() + ["-o", LIB] + sources() + ["-lcuda"]
     r = subprocess.run(cmd, capture_output=True, text=True)
     if verbose or r.returncode != 0:
         sys.stderr.write(r.stdout + r.stderr)

@@ -13,7 +13,7 @@
 //             one-hot per sample: q(s)[to] is a 128-long dot product, dW1 touches row `to` only, delta0 is one
 //             row of W1 (as written: src/dqn.cu:406-423; or corrected)            [td_delta_kernel]
 //   dW0       X^T . delta0 on tcgen05: the transposed one-hot operand tile is built in shared memory from the packed
-//             boards, delta0^T (BF16 hi+lo) arrives by TMA; db0 rides along as a constant-one feature    [dw0_gemm_kernel]
+//             boards, delta0^T (BF16 hi+lo) arrives by TMA; db0 rides along as a constant-one feature    [dw_gemm_kernel]
 //   SGD       W -= lr * sum of per-sample gradients (B = 1 reproduces one reference step)     [apply_kernel]
 // FP32 master weights; BF16 only as MMA operands.  Tolerance vs the FP64 oracle: |dQ| <= 2e-3.
 #include <cuda.h>
@@ -23,6 +23,15 @@
 #include "xq_tc.cuh"
 
 namespace xq {
+
+// -DXQ_TIMELINE: per-CTA clock64 timestamps of the pipeline events of the two tcgen05 kernels (profiling builds only;
+// scripts/tl_dump.py reads them back through xq_debug_timeline)
+#ifdef XQ_TIMELINE
+__device__ long long g_tl[2 * 160 * 64];
+#define XQ_TL(kern, slot) (g_tl[((kern) * 160 + blockIdx.y * gridDim.x + blockIdx.x) * 64 + (slot)] = clock64())
+#else
+#define XQ_TL(kern, slot) ((void)0)
+#endif
 
 constexpr int kIn = XQ_STATE_SIZE, kHid = 128, kOut = 8100, kQRows = 90;   // Q is indexed by `to` < 90 (src/dqn.cpp:47)
 [[maybe_unused]] constexpr int kGradW0 = 0;
@@ -39,10 +48,12 @@ constexpr int kNTiles = (kOut + BN - 1) / BN;       // 37
 constexpr uint32_t kABytes = BM * kHid * 2;         // 32 KB: one A tile (both k-blocks)
 constexpr uint32_t kBBytes = BN * kHid * 2;         // 56 KB: the stationary W1 tile
 constexpr uint32_t kTmemCols = 512;                 // 2 accumulator stages x BN columns (power of two >= 448)
-constexpr int kGemmThreads = 384;                   // warp 0 TMA, 1 MMA, 2 TMEM alloc, 3 bias, 4-11 epilogue
+constexpr int kGemmThreads = 384;                   // warp 0 TMA, 1 MMA, 2 TMEM alloc, 2-3 bias-step operands, 4-11 epilogue
 constexpr int kEpiWarps = 8;                        // two warps per TMEM lane quarter, each drains half of the BN columns
 constexpr int kParts = 2 * kNTiles;                 // row-max partials per sample (74)
-constexpr size_t kGemmSmem = 1024 + kBBytes + kAStages * kABytes + BN * 4 + 256;
+constexpr uint32_t kBiasBBytes = BN * BK * 2;       // 28 KB: b1 as the B operand of the bias step
+constexpr uint32_t kOnesBytes = BM * BK * 2;        // 16 KB: the constant-one A operand of the bias step
+constexpr size_t kGemmSmem = 1024 + kBBytes + kBiasBBytes + kOnesBytes + kAStages * kABytes + 256;
 
 struct Fast {
     int64_t cap = 0;                                   // batch capacity of the workspace
@@ -57,14 +68,14 @@ struct Fast {
     __nv_bfloat16 *Hbf = nullptr, *H2bf = nullptr;     // h(s), h(s') as MMA A operands [cap][128]
     float* Hf = nullptr;                               // h(s) FP32 [cap][128]
     float* zpart = nullptr;                            // [kParts][cap] row-max partials
-    uint8_t* to8 = nullptr;                            // [cap] action.to
+    float* part = nullptr;                             // [11 row tiles][8 splits][128][128] FP32 partials of the gradient contraction (L2 scratch)
+    uint32_t* cb = nullptr;                            // [14][ld] compact batch, word-major: 12 board words of s | action,mover,done | reward
     __nv_bfloat16 *d0hi = nullptr, *d0lo = nullptr;    // delta0^T [128][ld] BF16 hi / lo (B operand of the dW0 contraction)
     __nv_bfloat16 *ghi = nullptr, *glo = nullptr;      // (delta1 h)^T [128][ld] BF16 hi / lo (B operand of the dW1 contraction)
-    float* part = nullptr;                             // [kDwSplits][1280][128] FP32 partials of dW0^T
     float* q = nullptr;                                // [cap][8100] (debug path only, allocated on demand)
     int64_t q_cap = 0;
     float* info = nullptr;                             // 4 floats
-    CUtensorMap tmW1, tmTW1, tmH, tmH2, tmD0hi, tmD0lo, tmGhi, tmGlo;
+    CUtensorMap tmW1, tmTW1, tmH, tmH2, tmD0hi, tmD0lo, tmGhi, tmGlo, tmCb;
     int64_t tm_rows = 0;
 };
 
@@ -84,8 +95,7 @@ struct BatchRef {
 
 // ---------------------------------------------------------------------------------------------
 // layer 0: one warp per board, lane owns 4 hidden units; <= 32 coalesced 512-byte row reads of W0^T
-__device__ __forceinline__ float4 l0_gather(const uint32_t* __restrict__ w, int lane, const float* __restrict__ W0T, const float* __restrict__ b0) {
-    const uint32_t word = lane < 12 ? w[lane] : 0u;
+__device__ __forceinline__ float4 l0_gather(uint32_t word, int lane, const float* __restrict__ W0T, const float* __restrict__ b0) {   // word = board word `lane` (lanes 0..11)
     float4 acc = reinterpret_cast<const float4*>(b0)[lane];
     for (int wi = 0; wi < 12; ++wi) {
         uint32_t v = __shfl_sync(0xFFFFFFFFu, word, wi);
@@ -114,32 +124,48 @@ __global__ void __launch_bounds__(256) l0_forward_kernel(const uint8_t* __restri
     const int64_t s = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     const int lane = threadIdx.x & 31;
     if (s >= n) return;
-    const float4 h = l0_gather(reinterpret_cast<const uint32_t*>(boards + s * stride_bytes), lane, W0T, b0);
+    const float4 h = l0_gather(lane < 12 ? reinterpret_cast<const uint32_t*>(boards + s * stride_bytes)[lane] : 0u, lane, W0T, b0);
     if (Hf) reinterpret_cast<float4*>(Hf + s * kHid)[lane] = h;
     store_h_bf16(Hbf, s, lane, h);
 }
 // both states of every transition in one launch: warps [0,n) -> h(s) with the online net (BF16 + FP32),
-// warps [n,2n) -> h(s') with the bootstrap net (online: ChessAI::train; target: DQN::train)
+// warps [n,2n) -> h(s') with the bootstrap net (online: ChessAI::train; target: DQN::train).
+// The first-state warps also write the compact batch record (board of s, action, reward, done) that the
+// later kernels of the update read: the replay ring is touched by this kernel only.
 __global__ void __launch_bounds__(256) l0_pair_kernel(BatchRef batch, int64_t n, const float* __restrict__ W0T, const float* __restrict__ b0,
                                                      const float* __restrict__ W0T2, const float* __restrict__ b02,
-                                                     __nv_bfloat16* __restrict__ Hbf, float* __restrict__ Hf, __nv_bfloat16* __restrict__ H2bf) {
+                                                     __nv_bfloat16* __restrict__ Hbf, float* __restrict__ Hf, __nv_bfloat16* __restrict__ H2bf,
+                                                     uint32_t* __restrict__ cb, int64_t ld) {
     const int64_t w = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     const int lane = threadIdx.x & 31;
     if (w >= 2 * n) return;
     const bool second = w >= n;
     const int64_t s = second ? w - n : w;
-    const uint8_t* t = batch.at(s);
-    const float4 h = l0_gather(reinterpret_cast<const uint32_t*>(t + (second ? 48 : 0)), lane, second ? W0T2 : W0T, second ? b02 : b0);
+    const uint32_t* t = reinterpret_cast<const uint32_t*>(batch.at(s));
+    // transition words: 0..11 board of s, 12..23 board of s', 24 = action | mover << 16 | done << 24, 25 = reward
+    uint32_t word = 0u;
+    if (second) { if (lane < 12) word = t[12 + lane]; }
+    else if (lane < 14) word = t[lane < 12 ? lane : lane + 12];
+    if (!second && lane < 14) cb[lane * ld + s] = word;       // word-major: the readers walk consecutive samples
+    const float4 h = l0_gather(lane < 12 ? word : 0u, lane, second ? W0T2 : W0T, second ? b02 : b0);
     if (!second) reinterpret_cast<float4*>(Hf + s * kHid)[lane] = h;
     store_h_bf16(second ? H2bf : Hbf, s, lane, h);
 }
 
 // ---------------------------------------------------------------------------------------------
-// layer 1 on tcgen05: Z[M x 8100] = H[M x 128] * W1[8100 x 128]^T (+ b1), W1 tile stationary.
+// layer 1 on tcgen05: Z[M x 8100] = H[M x 128] * W1[8100 x 128]^T + b1, W1 tile stationary.
 // CTA (n_tile, split): loads its [BN x 128] BF16 slice of W1 once, then streams the A tiles of its row range
-// through a 3-stage TMA ring; one elected thread issues 8 UMMA (M128 x N224 x K16) per tile into one of two
-// TMEM accumulator stages; 4 epilogue warps (one per TMEM lane quarter) drain the other stage meanwhile.
+// through a 3-stage TMA ring; one elected thread issues 9 UMMA (M128 x N224 x K16) per tile into one of two
+// TMEM accumulator stages: 8 over the hidden units and ONE more whose A operand is a constant tile of ones and
+// whose B operand holds b1 split into three BF16 terms (hi + lo + lo2 = 24 mantissa bits) -- the bias comes out
+// of the tensor core, so the row-max epilogue is pure FMNMX straight out of TMEM (it was issue-bound on the
+// bias adds: 1.5 k cycles per tile against 0.9 k of MMA).  8 epilogue warps (two per TMEM lane quarter) pull
+// their 112 columns with four in-flight tcgen05.ld, release the accumulator stage, then reduce.
 enum { EPI_ROWMAX = 0, EPI_STORE_TANH = 1 };
+
+__device__ __forceinline__ uint32_t sw128_offset(int row, int col) {   // byte offset of bf16 (row, col) in a [rows x 64] SW128 K-major tile
+    return (uint32_t)((row >> 3) * 1024 + (row & 7) * 128 + ((((col >> 3) ^ row) & 7) << 4) + (col & 7) * 2);
+}
 
 template <int MODE>
 __global__ void __launch_bounds__(kGemmThreads, 1) l1_gemm_kernel(const __grid_constant__ CUtensorMap tmH, const __grid_constant__ CUtensorMap tmW1,
@@ -148,41 +174,84 @@ __global__ void __launch_bounds__(kGemmThreads, 1) l1_gemm_kernel(const __grid_c
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);   // SW128 tiles need 1024-B alignment
     uint8_t* sB = smem;                                    // [kKBlocks][BN][64] bf16
-    uint8_t* sA = smem + kBBytes;                          // [kAStages][kKBlocks][BM][64] bf16
-    float* sBias = reinterpret_cast<float*>(sA + kAStages * kABytes);
-    uint64_t* bars = reinterpret_cast<uint64_t*>(sBias + BN);
+    uint8_t* sBb = sB + kBBytes;                           // [BN][64] bf16: k = 0,1,2 hold b1 as hi, lo, lo2; only k < 16 is ever read
+    uint8_t* sAo = sBb + kBiasBBytes;                      // [BM][64] bf16: k = 0,1,2 are 1.0
+    uint8_t* sA = sAo + kOnesBytes;                        // [kAStages][kKBlocks][BM][64] bf16
+    uint64_t* bars = reinterpret_cast<uint64_t*>(sA + kAStages * kABytes);
     uint64_t* b_full = bars;              // 1
     uint64_t* a_full = bars + 1;          // kAStages
     uint64_t* a_empty = bars + 4;         // kAStages
     uint64_t* acc_full = bars + 7;        // 2
     uint64_t* acc_empty = bars + 9;       // 2
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 11);
+    uint64_t* c_full = bars + 11;         // bias / ones tiles written (warps 2, 3)
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 12);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int n_tile = blockIdx.x, split = blockIdx.y;
     const int n0 = n_tile * BN;
     // rows of this CTA: m-tiles split, split + n_splits, ...
     const int my_tiles = (m_tiles - split + n_splits - 1) / n_splits;
+    if (threadIdx.x == 0) XQ_TL(0, 0);
 
     if (threadIdx.x == 0) {
         tc::mbar_init(b_full, 1);
         for (int i = 0; i < kAStages; ++i) { tc::mbar_init(a_full + i, 1); tc::mbar_init(a_empty + i, 1); }
         for (int i = 0; i < 2; ++i) { tc::mbar_init(acc_full + i, 1); tc::mbar_init(acc_empty + i, kEpiWarps); }
+        tc::mbar_init(c_full, 2);
         tc::fence_barrier_init();
+        // the operand loads do not depend on the rest of the set-up: start them before the CTA-wide barrier
+        tc::prefetch_tmap(&tmH); tc::prefetch_tmap(&tmW1);
+        tc::mbar_expect_tx(b_full, kBBytes);
+        for (int kb = 0; kb < kKBlocks; ++kb) tc::tma_load_2d(sB + kb * (BN * BK * 2), &tmW1, kb * BK, n0, b_full);
+        for (int i = 0; i < kAStages && i < my_tiles; ++i) {
+            tc::mbar_expect_tx(a_full + i, kABytes);
+            const int row0 = (split + i * n_splits) * BM;
+            for (int kb = 0; kb < kKBlocks; ++kb) tc::tma_load_2d(sA + i * kABytes + kb * (BM * BK * 2), &tmH, kb * BK, row0, a_full + i);
+        }
     }
     if (warp == 2) tc::tmem_alloc<kTmemCols>(tmem_slot);
-    if (warp == 3) for (int i = lane; i < BN; i += 32) sBias[i] = (n0 + i < kOut) ? b1[n0 + i] : -INFINITY;   // padded outputs never win the max
+    if (warp == 2 || warp == 3) {   // constant operand tiles of the bias step: b1 -> (hi, lo, lo2) rows of sBb, ones into sAo
+        constexpr int kRowsPerThread = (BN + BM + 63) / 64;
+        const int t = threadIdx.x - 64;
+        float bv[kRowsPerThread];
+#pragma unroll
+        for (int u = 0; u < kRowsPerThread; ++u) {           // all loads in flight at once
+            const int r = t + 64 * u;
+            bv[u] = (r < BN && n0 + r < kOut) ? b1[n0 + r] : 0.0f;
+        }
+#pragma unroll
+        for (int u = 0; u < kRowsPerThread; ++u) {
+            const int r = t + 64 * u;
+            if (r >= BN + BM) break;
+            const bool is_b = r < BN;
+            const int row = is_b ? r : r - BN;
+            uint8_t* tile = is_b ? sBb : sAo;
+            __nv_bfloat16 v0, v1, v2;
+            if (is_b) {
+                const bool real = n0 + row < kOut;
+                const float b = real ? bv[u] : -1e30f;                               // padded outputs never win the max
+                v0 = __float2bfloat16_rn(b);
+                const float r1 = real ? b - __bfloat162float(v0) : 0.0f;
+                v1 = __float2bfloat16_rn(r1);
+                v2 = __float2bfloat16_rn(r1 - __bfloat162float(v1));
+            } else {
+                v0 = v1 = v2 = __float2bfloat16_rn(1.0f);
+            }
+            const uint32_t w0 = (uint32_t)__bfloat16_as_ushort(v0) | ((uint32_t)__bfloat16_as_ushort(v1) << 16);
+            const uint32_t w1 = (uint32_t)__bfloat16_as_ushort(v2);
+            *reinterpret_cast<uint4*>(tile + sw128_offset(row, 0)) = make_uint4(w0, w1, 0u, 0u);     // k = 0..7
+            *reinterpret_cast<uint4*>(tile + sw128_offset(row, 8)) = make_uint4(0u, 0u, 0u, 0u);     // k = 8..15
+        }
+    }
     tc::tc_fence_before();
     __syncthreads();
     tc::tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
+    if (threadIdx.x == 0) XQ_TL(0, 1);
 
     if (warp == 0) {
-        if (lane == 0) {   // ===== TMA producer =====
-            tc::prefetch_tmap(&tmH); tc::prefetch_tmap(&tmW1);
-            tc::mbar_expect_tx(b_full, kBBytes);
-            for (int kb = 0; kb < kKBlocks; ++kb) tc::tma_load_2d(sB + kb * (BN * BK * 2), &tmW1, kb * BK, n0, b_full);
-            for (int i = 0; i < my_tiles; ++i) {
+        if (lane == 0) {   // ===== TMA producer (stages 0..kAStages-1 were filled above) =====
+            for (int i = kAStages; i < my_tiles; ++i) {
                 const int st = i % kAStages;
                 tc::mbar_wait(a_empty + st, ((i / kAStages) & 1) ^ 1);
                 tc::mbar_expect_tx(a_full + st, kABytes);
@@ -190,14 +259,19 @@ __global__ void __launch_bounds__(kGemmThreads, 1) l1_gemm_kernel(const __grid_c
                 for (int kb = 0; kb < kKBlocks; ++kb) tc::tma_load_2d(sA + st * kABytes + kb * (BM * BK * 2), &tmH, kb * BK, row0, a_full + st);
             }
         }
+        __syncwarp();      // the whole warp reaches the closing __syncthreads together (bar.sync is warp-aligned)
     } else if (warp == 1) {
         if (lane == 0) {   // ===== MMA issuer =====
             constexpr uint32_t idesc = tc::umma_idesc_bf16(BM, BN);
+            const uint64_t d_ones = tc::umma_desc_sw128(tc::smem_u32(sAo)), d_bias = tc::umma_desc_sw128(tc::smem_u32(sBb));
             tc::mbar_wait(b_full, 0);
+            XQ_TL(0, 2);
             for (int i = 0; i < my_tiles; ++i) {
                 const int st = i % kAStages, acc = i & 1;
                 tc::mbar_wait(acc_empty + acc, ((i >> 1) & 1) ^ 1);
+                if (i < 8) XQ_TL(0, 4 + i);
                 tc::mbar_wait(a_full + st, (i / kAStages) & 1);
+                if (i < 8) XQ_TL(0, 12 + i);
                 tc::tc_fence_after();
 #pragma unroll
                 for (int kb = 0; kb < kKBlocks; ++kb)
@@ -208,62 +282,67 @@ __global__ void __launch_bounds__(kGemmThreads, 1) l1_gemm_kernel(const __grid_c
                         tc::umma_bf16(tmem_base + acc * BN, da, db, idesc, (kb | k) != 0);
                     }
                 tc::umma_commit(a_empty + st);      // A stage free once these MMAs have read it
+                if (i == 0) { tc::mbar_wait(c_full, 0); tc::tc_fence_after(); }
+                tc::umma_bf16(tmem_base + acc * BN, d_ones, d_bias, idesc, 1);      // + 1 * (b1_hi + b1_lo + b1_lo2)
                 tc::umma_commit(acc_full + acc);    // accumulator ready for the epilogue
             }
         }
-    } else if (warp >= 4) {   // ===== epilogue: warps w and w+4 drain TMEM lanes 32*(w&3).. +31, one half of the columns each =====
+        __syncwarp();
+    } else if (warp < 4) {   // ===== warps 2, 3: the bias-step operand tiles were written before the barrier =====
+        tc::fence_proxy_async();            // generic-proxy stores -> visible to the tensor core
+        __syncwarp();
+        if (lane == 0) tc::mbar_arrive(c_full);
+    } else {   // ===== epilogue: warps w and w+4 drain TMEM lanes 32*(w&3).. +31, one half of the columns each =====
         const int quarter = warp & 3, half = (warp - 4) >> 2;
-        constexpr int kHalfCols = BN / 2;                                   // 112 = 7 chunks of 16 columns
+        constexpr int kHalfCols = BN / 2;                                   // 112 = 3 x 32 + 16 columns
         for (int i = 0; i < my_tiles; ++i) {
             const int acc = i & 1;
             const int row = (split + i * n_splits) * BM + quarter * 32 + lane;
             tc::mbar_wait(acc_full + acc, (i >> 1) & 1);
+            if (warp == 4 && lane == 0 && i < 8) XQ_TL(0, 20 + i);
             tc::tc_fence_after();
             const uint32_t t0 = tmem_base + ((uint32_t)(quarter * 32) << 16) + acc * BN + half * kHalfCols;
-            const float* bias = sBias + half * kHalfCols;
-            float best[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY};
-#pragma unroll 1
-            for (int c = 0; c < kHalfCols / 16; c += 2) {
-                uint32_t r0[16], r1[16];
-                const bool two = c + 1 < kHalfCols / 16;
-                tc::tmem_ld16_nowait(t0 + c * 16, r0);
-                if (two) tc::tmem_ld16_nowait(t0 + (c + 1) * 16, r1);      // warp-uniform
+            if (MODE == EPI_ROWMAX) {
+                uint32_t r[kHalfCols];
+                tc::tmem_ld32_nowait(t0, r); tc::tmem_ld32_nowait(t0 + 32, r + 32); tc::tmem_ld32_nowait(t0 + 64, r + 64);
+                tc::tmem_ld16_nowait(t0 + 96, r + 96);
                 tc::tmem_wait_ld();
-                if (MODE == EPI_ROWMAX) {
+                tc::tc_fence_before();
+                __syncwarp();
+                if (lane == 0) tc::mbar_arrive(acc_empty + acc);             // the values are in registers: the stage is free
+                if (warp == 4 && lane == 0 && i < 8) XQ_TL(0, 28 + i);
+                float best[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY};
 #pragma unroll
-                    for (int j = 0; j < 16; j += 4) {
-                        const float4 b4 = *reinterpret_cast<const float4*>(bias + c * 16 + j);
-                        best[0] = fmaxf(best[0], __uint_as_float(r0[j + 0]) + b4.x); best[1] = fmaxf(best[1], __uint_as_float(r0[j + 1]) + b4.y);
-                        best[2] = fmaxf(best[2], __uint_as_float(r0[j + 2]) + b4.z); best[3] = fmaxf(best[3], __uint_as_float(r0[j + 3]) + b4.w);
-                    }
-                    if (two) {
-#pragma unroll
-                        for (int j = 0; j < 16; j += 4) {
-                            const float4 b4 = *reinterpret_cast<const float4*>(bias + (c + 1) * 16 + j);
-                            best[0] = fmaxf(best[0], __uint_as_float(r1[j + 0]) + b4.x); best[1] = fmaxf(best[1], __uint_as_float(r1[j + 1]) + b4.y);
-                            best[2] = fmaxf(best[2], __uint_as_float(r1[j + 2]) + b4.z); best[3] = fmaxf(best[3], __uint_as_float(r1[j + 3]) + b4.w);
-                        }
-                    }
-                } else if (row < M) {
-                    float* out = Q + (size_t)row * kOut + n0 + half * kHalfCols + c * 16;
-#pragma unroll
-                    for (int j = 0; j < 16; ++j)
-                        if (n0 + half * kHalfCols + c * 16 + j < kOut) out[j] = tanhf(__uint_as_float(r0[j]) + bias[c * 16 + j]);
-                    if (two) {
+                for (int j = 0; j < kHalfCols; j += 4) {
+                    best[0] = fmaxf(best[0], __uint_as_float(r[j])); best[1] = fmaxf(best[1], __uint_as_float(r[j + 1]));
+                    best[2] = fmaxf(best[2], __uint_as_float(r[j + 2])); best[3] = fmaxf(best[3], __uint_as_float(r[j + 3]));
+                }
+                if (row < M) zpart[(int64_t)(n_tile * 2 + half) * zstride + row] = fmaxf(fmaxf(best[0], best[1]), fmaxf(best[2], best[3]));
+            } else {
+#pragma unroll 1
+                for (int c = 0; c < kHalfCols / 16; ++c) {
+                    uint32_t r[16];
+                    tc::tmem_ld16_nowait(t0 + c * 16, r);
+                    tc::tmem_wait_ld();
+                    if (row < M) {
+                        const int col0 = n0 + half * kHalfCols + c * 16;
+                        float* out = Q + (size_t)row * kOut + col0;
 #pragma unroll
                         for (int j = 0; j < 16; ++j)
-                            if (n0 + half * kHalfCols + (c + 1) * 16 + j < kOut) out[16 + j] = tanhf(__uint_as_float(r1[j]) + bias[(c + 1) * 16 + j]);
+                            if (col0 + j < kOut) out[j] = tanhf(__uint_as_float(r[j]));
                     }
                 }
+                tc::tc_fence_before();
+                __syncwarp();
+                if (lane == 0) tc::mbar_arrive(acc_empty + acc);
             }
-            tc::tc_fence_before();
-            __syncwarp();
-            if (lane == 0) tc::mbar_arrive(acc_empty + acc);
-            if (MODE == EPI_ROWMAX && row < M) zpart[(int64_t)(n_tile * 2 + half) * zstride + row] = fmaxf(fmaxf(best[0], best[1]), fmaxf(best[2], best[3]));
         }
     }
     tc::tc_fence_before();
     __syncthreads();
+    if (threadIdx.x == 0) XQ_TL(0, 3);
+    if (threadIdx.x == 128) XQ_TL(0, 36);
+    if (threadIdx.x == 32) XQ_TL(0, 37);
     if (warp == 2) { tc::tc_fence_after(); tc::tmem_dealloc<kTmemCols>(tmem_base); }
 }
 
@@ -280,10 +359,9 @@ static_assert(sizeof(Transition) == 128 && sizeof(xq_transition) == 128, "transi
 // TD error, one warp per transition (src/chessai.cpp:121-131 + src/dqn.cu:288-308 specialised to a one-hot delta1).
 // Outputs per sample: delta1, its row `to`, delta0 as FP32 and, transposed and split into BF16 hi + lo, as the
 // K-major B operand of the dW0 contraction.  No global atomics except 3 per CTA for the loss statistics.
-__global__ void __launch_bounds__(256) td_delta_kernel(BatchRef batch, int64_t n, const float* __restrict__ Hf,
+__global__ void __launch_bounds__(256) td_delta_kernel(const uint32_t* __restrict__ cb, int64_t n, const float* __restrict__ Hf,
                                                       const float* __restrict__ W1, const float* __restrict__ b1,
                                                       const float* __restrict__ zpart, int64_t zstride, int n_parts, float gamma, int mode,
-                                                      uint8_t* __restrict__ to_out,
                                                       __nv_bfloat16* __restrict__ d0hi, __nv_bfloat16* __restrict__ d0lo,
                                                       __nv_bfloat16* __restrict__ ghi, __nv_bfloat16* __restrict__ glo, int64_t ld,
                                                       float* __restrict__ gb1, float* __restrict__ info) {
@@ -299,17 +377,19 @@ __global__ void __launch_bounds__(256) td_delta_kernel(BatchRef batch, int64_t n
     reinterpret_cast<float4*>(s_g[wib])[lane] = make_float4(0.f, 0.f, 0.f, 0.f);
     if (lane == 0) { s_d1[wib] = 0.0f; s_to[wib] = -1; }
     if (s < n) {
-        const Transition* t = reinterpret_cast<const Transition*>(batch.at(s));
-        const int to = XQ_ACTION_TO(t->action);                // the Q index of the taken action is action.to (:124,:127)
+        const uint32_t meta = cb[12 * ld + s];
+        const int to = XQ_ACTION_TO(meta & 0xFFFFu);           // the Q index of the taken action is action.to (:124,:127)
+        const bool done = (meta >> 24) != 0;
+        const float reward = (float)(int32_t)cb[13 * ld + s];
         const float4 h = reinterpret_cast<const float4*>(Hf + s * kHid)[lane];
         const float4 w = reinterpret_cast<const float4*>(W1 + (size_t)to * kHid)[lane];
         float z = h.x * w.x + h.y * w.y + h.z * w.z + h.w * w.w;
         float zmax = -INFINITY;
-        if (!t->done) for (int i = lane; i < n_parts; i += 32) zmax = fmaxf(zmax, zpart[(int64_t)i * zstride + s]);
+        if (!done) for (int i = lane; i < n_parts; i += 32) zmax = fmaxf(zmax, zpart[(int64_t)i * zstride + s]);
 #pragma unroll
         for (int k = 16; k > 0; k >>= 1) { z += __shfl_xor_sync(0xFFFFFFFFu, z, k); zmax = fmaxf(zmax, __shfl_xor_sync(0xFFFFFFFFu, zmax, k)); }
         const float q = tanhf(z + b1[to]);
-        const float target = t->done ? (float)t->reward : (float)t->reward + gamma * tanhf(zmax);
+        const float target = done ? reward : reward + gamma * tanhf(zmax);
         const float d1 = (q - target) * (1.0f - q * q);        // outputLayerDeltaKernel, src/dqn.cu:288-295
         // hidden delta: as written W1flat[i*1260 + j] with i = to (only i < 128 is summed and delta1 is one-hot), or W1[to][j]
         const float* wrow = mode == XQ_DQN_AS_WRITTEN ? W1 + (size_t)to * kIn : W1 + (size_t)to * kHid;
@@ -318,7 +398,7 @@ __global__ void __launch_bounds__(256) td_delta_kernel(BatchRef batch, int64_t n
                              wd.w * d1 * (1.0f - h.w * h.w)};
         reinterpret_cast<float4*>(s_d0[wib])[lane] = make_float4(d0[0], d0[1], d0[2], d0[3]);
         reinterpret_cast<float4*>(s_g[wib])[lane] = make_float4(d1 * h.x, d1 * h.y, d1 * h.z, d1 * h.w);
-        if (lane == 0) { to_out[s] = (uint8_t)to; s_d1[wib] = d1; s_to[wib] = to; }
+        if (lane == 0) { s_d1[wib] = d1; s_to[wib] = to; }
         loss = 0.5f * (q - target) * (q - target); qv = q; tv = target;
     }
     if (lane == 0) { s_info[wib][0] = loss; s_info[wib][1] = qv; s_info[wib][2] = tv; }
@@ -362,176 +442,250 @@ __global__ void __launch_bounds__(256) td_delta_kernel(BatchRef batch, int64_t n
 // ---------------------------------------------------------------------------------------------
 // dW0^T = X^T . delta0 on tcgen05: C[feature 0..1279][hidden 0..127] = sum_b onehot_b[feature] * delta0_b[hidden].
 // (updateWeightsBiasesKernel for layer 0, src/dqn.cu:310-319, summed over the batch.)  Feature 1260 is a constant
-// one, so row 1260 of C is db0.  A operand: the transposed one-hot tile [128 features x 64 samples] is BUILT in
-// shared memory (128-byte-swizzled K-major layout) by 8 warps straight from the packed boards -- the 1260-wide
-// one-hot matrix never exists in HBM.  B operand: delta0^T as BF16 hi + lo (two MMAs, ~16 mantissa bits) by TMA.
-// CTA (m_tile, k_split) accumulates its sample range in TMEM and writes an FP32 partial; dw0_reduce_kernel sums them.
+// one, so row 1260 of C is db0; an 11th row tile contracts one-hot(action.to) with delta1*h = dW1 rows 0..89.
+// A operand: the transposed one-hot tile [128 features x 64 samples] is BUILT in shared memory (128-byte-swizzled
+// K-major layout) by 8 warps straight from the compact batch -- the 1260-wide one-hot matrix never exists in HBM.
+// B operand: delta0^T as BF16 hi + lo (two MMAs, ~16 mantissa bits) by TMA.
+// Grid (11 row tiles, 8 sample splits); the 8 CTAs of a row tile form a thread-block CLUSTER: each accumulates its
+// sample range in TMEM and writes its FP32 partial to an L2-resident scratch (distributed shared memory moves only
+// ~20 B/clk per SM, far too slow for 64 KB per CTA); after ONE cluster barrier (release / acquire at cluster scope)
+// each CTA sums the 8 partials of its 16 rows (fixed order: deterministic) and applies the SGD step (or writes the
+// compact gradient for the all-reduce).  No second kernel.
 constexpr int kFeatPad = 1280, kBiasFeat = kIn;
 constexpr int kDwMTiles = kFeatPad / BM + 1;             // 10 feature tiles of dW0^T (+ db0) and one tile for dW1 (rows = action.to)
-constexpr int kDwRows = kDwMTiles * BM;                  // 1408 rows per partial
-constexpr int kDwStages = 3;
+constexpr int kDwSplits = 8;                             // sample splits = cluster size (portable maximum)
+constexpr int kDwStages = 4;
 constexpr uint32_t kDwABytes = BM * BK * 2;              // 16 KB
-constexpr uint32_t kDwBBytes = 2 * kHid * BK * 2;        // 32 KB (hi, lo)
+constexpr uint32_t kDwBBytes = 2 * kHid * BK * 2;        // 32 KB: rows 0..127 = hi, rows 128..255 = lo -> ONE N = 256 operand
 constexpr int kDwThreads = 384;                          // warp 0 TMA, 1 MMA, 2 TMEM alloc, 4-11 one-hot builders (4-7 also epilogue)
-constexpr size_t kDwSmem = 1024 + kDwStages * (kDwABytes + kDwBBytes) + 256;
+constexpr uint32_t kDwCBytes = 14 * BK * 4;              // 3.5 KB: the compact-batch words of the k-block's 64 samples, [word][sample]
+constexpr uint32_t kDwCStride = 4096;
+constexpr size_t kDwSmem = 1024 + kDwStages * (kDwABytes + kDwBBytes + kDwCStride) + 256;
+static_assert(kDwStages * (kDwABytes + kDwBBytes) >= BM * kHid * 4, "the epilogue stages the FP32 tile in the operand buffers");
+constexpr int kRowsPerCta = BM / kDwSplits;              // 16 rows of the tile are reduced and applied by each CTA of the cluster
 
-__device__ __forceinline__ uint32_t sw128_offset(int row, int col) {   // byte offset of bf16 (row, col) in a [rows x 64] SW128 K-major tile
-    return (uint32_t)((row >> 3) * 1024 + (row & 7) * 128 + ((((col >> 3) ^ row) & 7) << 4) + (col & 7) * 2);
+__device__ __forceinline__ uint32_t cluster_rank() { uint32_t r; asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r)); return r; }
+__device__ __forceinline__ void cluster_sync_all() {
+    asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
 }
 
-__global__ void __launch_bounds__(kDwThreads, 1) dw0_gemm_kernel(const __grid_constant__ CUtensorMap tmD0Hi, const __grid_constant__ CUtensorMap tmD0Lo,
-                                                                const __grid_constant__ CUtensorMap tmGHi, const __grid_constant__ CUtensorMap tmGLo,
-                                                                BatchRef batch, const uint8_t* __restrict__ to8, int n, int k_splits,
-                                                                float* __restrict__ part) {
+__global__ void __launch_bounds__(kDwThreads, 1) dw_gemm_kernel(const __grid_constant__ CUtensorMap tmD0Hi, const __grid_constant__ CUtensorMap tmD0Lo,
+                                                               const __grid_constant__ CUtensorMap tmGHi, const __grid_constant__ CUtensorMap tmGLo,
+                                                               const __grid_constant__ CUtensorMap tmCb, int n, float* __restrict__ part,
+                                                               float* __restrict__ grad,
+                                                               float* __restrict__ W0T, float* __restrict__ b0, float* __restrict__ W1,
+                                                               float* __restrict__ b1, __nv_bfloat16* __restrict__ W1bf, float lr, int apply) {
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
     uint8_t* sA = smem;                                        // [stage][128 features][64 samples]
-    uint8_t* sB = smem + kDwStages * kDwABytes;                // [stage][hi|lo][128 hidden][64 samples]
-    uint64_t* bars = reinterpret_cast<uint64_t*>(sB + kDwStages * kDwBBytes);
+    uint8_t* sB = smem + kDwStages * kDwABytes;                // [stage][hi rows | lo rows][64 samples]
+    uint8_t* sC = sB + kDwStages * kDwBBytes;                  // [stage][14 words][64 samples] compact-batch words
+    uint64_t* bars = reinterpret_cast<uint64_t*>(sC + kDwStages * kDwCStride);
     uint64_t* full = bars;                 // kDwStages: 1 TMA arrive(+tx) + 8 builder warps
     uint64_t* empty = bars + kDwStages;    // kDwStages: MMA commit
-    uint64_t* acc_full = bars + 2 * kDwStages;
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * kDwStages + 1);
+    uint64_t* cfull = bars + 2 * kDwStages;   // kDwStages: board words landed
+    uint64_t* acc_full = bars + 3 * kDwStages;
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 3 * kDwStages + 1);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int mt = blockIdx.x, ks = blockIdx.y;
+    const int mt = blockIdx.x, ks = (int)cluster_rank();     // cluster = the kDwSplits CTAs (blockIdx.y) of one row tile
     const int total_kb = (n + BK - 1) / BK;
-    const int my_kb = (total_kb - ks + k_splits - 1) / k_splits;     // k-blocks ks, ks + k_splits, ...
+    const int my_kb = ks < total_kb ? (total_kb - ks + kDwSplits - 1) / kDwSplits : 0;     // k-blocks ks, ks + kDwSplits, ...
     const int f0 = mt * BM;
     const bool w1_tile = mt == kDwMTiles - 1;            // the dW1 tile: A = one-hot of action.to, B = (delta1 h)^T
     const CUtensorMap& tmHi = w1_tile ? tmGHi : tmD0Hi;
     const CUtensorMap& tmLo = w1_tile ? tmGLo : tmD0Lo;
+    if (threadIdx.x == 0) XQ_TL(1, 0);
 
+    auto issue_stage = [&](int i) {        // operands of k-block i -> stage i % kDwStages
+        const int st = i % kDwStages, kb = ks + i * kDwSplits;
+        tc::mbar_expect_tx(cfull + st, kDwCBytes);
+        tc::tma_load_2d(sC + st * kDwCStride, &tmCb, kb * BK, 0, cfull + st);
+        tc::mbar_expect_tx(full + st, kDwBBytes);
+        tc::tma_load_2d(sB + st * kDwBBytes, &tmHi, kb * BK, 0, full + st);
+        tc::tma_load_2d(sB + st * kDwBBytes + kDwBBytes / 2, &tmLo, kb * BK, 0, full + st);
+    };
     if (threadIdx.x == 0) {
-        for (int i = 0; i < kDwStages; ++i) { tc::mbar_init(full + i, 9); tc::mbar_init(empty + i, 1); }
+        for (int i = 0; i < kDwStages; ++i) { tc::mbar_init(full + i, 9); tc::mbar_init(empty + i, 1); tc::mbar_init(cfull + i, 1); }
         tc::mbar_init(acc_full, 1);
         tc::fence_barrier_init();
+        tc::prefetch_tmap(&tmCb); tc::prefetch_tmap(&tmHi); tc::prefetch_tmap(&tmLo);
+        for (int i = 0; i < kDwStages && i < my_kb; ++i) issue_stage(i);      // the first stages need no `empty` wait: start them before the CTA barrier
     }
-    if (warp == 2) tc::tmem_alloc<128>(tmem_slot);
+    if (warp == 2) tc::tmem_alloc<256>(tmem_slot);
+
+    // the reducing threads (0..255, two 16-byte chunks each of the 16 rows this CTA owns) fetch the old weights now:
+    // they do not depend on anything this kernel computes
+    static_assert(kRowsPerCta * (kHid / 4) == 2 * 256, "two chunks per reducing thread");
+    int e[2];                                                   // element of the compact gradient, -1 = padding row
+    const float* src[2];
+    float4 wold[2];
+#pragma unroll
+    for (int u = 0; u < 2; ++u) {
+        const int item = (int)threadIdx.x + 256 * u;
+        const int row = ks * kRowsPerCta + ((item >> 5) % kRowsPerCta), chunk = item & 31;
+        src[u] = part + ((size_t)(mt * kDwSplits) * BM + row) * kHid + chunk * 4;
+        const int f = f0 + row;
+        e[u] = -1;
+        if (threadIdx.x < 256) {
+            if (w1_tile) { if (row < kQRows) e[u] = kGradW1 + row * kHid + chunk * 4; }
+            else if (f < kIn) e[u] = f * kHid + chunk * 4;
+            else if (f == kBiasFeat) e[u] = kGradB0 + chunk * 4;
+        }
+        wold[u] = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (apply && e[u] >= 0)
+            wold[u] = *reinterpret_cast<const float4*>(e[u] < kGradB0 ? W0T + e[u] : (e[u] < kGradW1 ? b0 + (e[u] - kGradB0) : W1 + (e[u] - kGradW1)));
+    }
+    const int bt = threadIdx.x - 128;
+    if (warp >= 4)                                             // the one-hot stages start from all-zero
+        for (int u = bt; u < (int)(kDwStages * kDwABytes / 16); u += 256) reinterpret_cast<uint4*>(sA)[u] = make_uint4(0u, 0u, 0u, 0u);
     tc::tc_fence_before();
     __syncthreads();
     tc::tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
+    if (threadIdx.x == 0) XQ_TL(1, 1);
 
     if (warp == 0) {
-        if (lane == 0) {   // ===== TMA producer: delta0^T hi / lo tiles =====
-            tc::prefetch_tmap(&tmHi); tc::prefetch_tmap(&tmLo);
-            for (int i = 0; i < my_kb; ++i) {
-                const int st = i % kDwStages, kb = ks + i * k_splits;
-                tc::mbar_wait(empty + st, ((i / kDwStages) & 1) ^ 1);
-                tc::mbar_expect_tx(full + st, kDwBBytes);
-                tc::tma_load_2d(sB + st * kDwBBytes, &tmHi, kb * BK, 0, full + st);
-                tc::tma_load_2d(sB + st * kDwBBytes + kDwBBytes / 2, &tmLo, kb * BK, 0, full + st);
+        if (lane == 0) {   // ===== TMA producer: board words + delta0^T hi / lo tiles =====
+            for (int i = kDwStages; i < my_kb; ++i) {
+                tc::mbar_wait(empty + i % kDwStages, ((i / kDwStages) & 1) ^ 1);
+                issue_stage(i);
             }
         }
+        __syncwarp();
     } else if (warp == 1) {
-        if (lane == 0) {   // ===== MMA issuer =====
-            constexpr uint32_t idesc = tc::umma_idesc_bf16(BM, kHid);
+        if (lane == 0) {   // ===== MMA issuer: M128 x N256 (hi | lo) x K16, the one-hot operand is read once per step =====
+            constexpr uint32_t idesc = tc::umma_idesc_bf16(BM, 2 * kHid);
             for (int i = 0; i < my_kb; ++i) {
                 const int st = i % kDwStages;
                 tc::mbar_wait(full + st, (i / kDwStages) & 1);
+                if (i < 8) XQ_TL(1, 4 + i);
                 tc::tc_fence_after();
 #pragma unroll
                 for (int k = 0; k < BK / 16; ++k) {
                     const uint64_t da = tc::umma_desc_sw128(tc::smem_u32(sA + st * kDwABytes) + k * 32);
-                    const uint64_t dh = tc::umma_desc_sw128(tc::smem_u32(sB + st * kDwBBytes) + k * 32);
-                    const uint64_t dl = tc::umma_desc_sw128(tc::smem_u32(sB + st * kDwBBytes + kDwBBytes / 2) + k * 32);
-                    tc::umma_bf16(tmem_base, da, dh, idesc, (i | k) != 0);
-                    tc::umma_bf16(tmem_base, da, dl, idesc, 1);
+                    const uint64_t db = tc::umma_desc_sw128(tc::smem_u32(sB + st * kDwBBytes) + k * 32);
+                    tc::umma_bf16(tmem_base, da, db, idesc, (i | k) != 0);
                 }
                 tc::umma_commit(empty + st);
             }
-            tc::umma_commit(acc_full);
+            if (my_kb > 0) tc::umma_commit(acc_full);
         }
+        __syncwarp();
     } else if (warp >= 4) {
-        // ===== one-hot^T builders: thread = (sample of the k-block, group of <= 3 squares of this feature tile) =====
-        const int bt = threadIdx.x - 128, sample = bt & 63, grp = bt >> 6;
+        // ===== one-hot^T builders: thread = (sample of the k-block, group of <= 3 squares of this feature tile).  A thread owns
+        // column `sample` of its squares' feature rows in every stage: it clears the (<= 3) ones it set kDwStages k-blocks ago and
+        // sets the new ones -- no tile-wide zeroing, no barrier between the warps.  The stage is free for rewriting once its board
+        // words have landed: the producer issued them only after the MMAs of the stage's previous use had completed.
+        const int sample = bt & 63, grp = bt >> 6;
         const int q0 = f0 / 14;
-        for (int i = 0; i < my_kb; ++i) {
-            const int st = i % kDwStages, kb = ks + i * k_splits;
-            const int b = kb * BK + sample;
-            uint32_t off[3] = {0xFFFFFFFFu, 0xFFFFFFFFu, 0xFFFFFFFFu};
-            if (b < n && w1_tile) {
-                if (grp == 0) off[0] = sw128_offset(to8[b], sample);                                      // row = action.to (< 128)
-            } else if (b < n) {
-                const uint32_t* sq = reinterpret_cast<const uint32_t*>(batch.at(b));
+        uint32_t prev[kDwStages][3];
+#pragma unroll
+        for (int a = 0; a < kDwStages; ++a) prev[a][0] = prev[a][1] = prev[a][2] = 0xFFFFFFFFu;
+        for (int i0 = 0; i0 < my_kb; i0 += kDwStages) {
+#pragma unroll
+            for (int st = 0; st < kDwStages; ++st) {
+                const int i = i0 + st;
+                if (i >= my_kb) break;
+                const int b = (ks + i * kDwSplits) * BK + sample;
+                const uint32_t* words = reinterpret_cast<const uint32_t*>(sC + st * kDwCStride) + sample;     // word w at words[w * 64]
+                tc::mbar_wait(cfull + st, (i / kDwStages) & 1);
+                uint32_t off[3] = {0xFFFFFFFFu, 0xFFFFFFFFu, 0xFFFFFFFFu};
+                if (b < n && w1_tile) {
+                    if (grp == 0) off[0] = sw128_offset((int)XQ_ACTION_TO(words[12 * BK] & 0xFFFFu), sample);      // row = action.to (< 128)
+                } else if (b < n) {
+#pragma unroll
+                    for (int u = 0; u < 3; ++u) {
+                        const int q = q0 + grp + 4 * u;
+                        if (q < XQ_SQUARES) {
+                            const int code = (words[(q >> 3) * BK] >> (4 * (q & 7))) & 15;
+                            const int f = q * 14 + code - 1 - f0;
+                            if (code >= 1 && code <= 14 && f >= 0 && f < BM) off[u] = sw128_offset(f, sample);
+                        }
+                    }
+                    if (mt == kDwMTiles - 2 && grp == 3) off[2] = sw128_offset(kBiasFeat - f0, sample);      // constant-one feature -> db0
+                }
+                if (bt == 0 && i < 8) XQ_TL(1, 12 + i);
+                uint8_t* tile = sA + st * kDwABytes;
 #pragma unroll
                 for (int u = 0; u < 3; ++u) {
-                    const int q = q0 + grp + 4 * u;
-                    if (q < XQ_SQUARES) {
-                        const int code = (sq[q >> 3] >> (4 * (q & 7))) & 15;
-                        const int f = q * 14 + code - 1 - f0;
-                        if (code >= 1 && code <= 14 && f >= 0 && f < BM) off[u] = sw128_offset(f, sample);
-                    }
+                    if (prev[st][u] != 0xFFFFFFFFu) *reinterpret_cast<uint16_t*>(tile + prev[st][u]) = 0;
+                    if (off[u] != 0xFFFFFFFFu) *reinterpret_cast<uint16_t*>(tile + off[u]) = 0x3F80;        // BF16 1.0
+                    prev[st][u] = off[u];
                 }
-                if (mt == kDwMTiles - 2 && grp == 3) off[2] = sw128_offset(kBiasFeat - f0, sample);      // constant-one feature -> db0
+                tc::fence_proxy_async();                                             // generic-proxy stores -> visible to the tensor core
+                __syncwarp();
+                if (lane == 0) tc::mbar_arrive(full + st);
+                if (bt == 0 && i < 8) XQ_TL(1, 20 + i);
             }
-            tc::mbar_wait(empty + st, ((i / kDwStages) & 1) ^ 1);
-            uint8_t* tile = sA + st * kDwABytes;
-            uint4* z = reinterpret_cast<uint4*>(tile + bt * 64);
-#pragma unroll
-            for (int u = 0; u < 4; ++u) z[u] = make_uint4(0u, 0u, 0u, 0u);
-            asm volatile("bar.sync 1, 256;" ::: "memory");                       // the 8 builder warps only
-#pragma unroll
-            for (int u = 0; u < 3; ++u)
-                if (off[u] != 0xFFFFFFFFu) *reinterpret_cast<uint16_t*>(tile + off[u]) = 0x3F80;    // BF16 1.0
-            tc::fence_proxy_async();                                             // generic-proxy stores -> visible to the tensor core
-            __syncwarp();
-            if (lane == 0) tc::mbar_arrive(full + st);
         }
-        if (warp < 8) {   // ===== epilogue: TMEM -> FP32 partial [k_split][feature][hidden] =====
-            const int quarter = warp & 3;
-            tc::mbar_wait(acc_full, 0);
-            tc::tc_fence_after();
-            float* out = part + ((size_t)ks * kDwRows + f0 + quarter * 32 + lane) * kHid;
-#pragma unroll 1
-            for (int c = 0; c < kHid / 16; ++c) {
-                uint32_t r[16];
-                tc::tmem_ld16_nowait(tmem_base + ((uint32_t)(quarter * 32) << 16) + c * 16, r);
-                tc::tmem_wait_ld();
+        if (warp < 8) {   // ===== epilogue: hi + lo halves out of TMEM -> this warp's 32 rows staged in shared memory (16-byte chunks
+                          // XOR-swizzled by row); the whole CTA then writes coalesced 512-byte rows of the FP32 partial =====
+            const int quarter = warp & 3, row = quarter * 32 + lane;
+            if (my_kb > 0) { tc::mbar_wait(acc_full, 0); tc::tc_fence_after(); }
+            if (bt == 0) XQ_TL(1, 2);
 #pragma unroll
-                for (int j = 0; j < 16; j += 4)
-                    *reinterpret_cast<float4*>(out + c * 16 + j) = make_float4(__uint_as_float(r[j]), __uint_as_float(r[j + 1]),
-                                                                              __uint_as_float(r[j + 2]), __uint_as_float(r[j + 3]));
+            for (int c0 = 0; c0 < kHid; c0 += 32) {
+                uint32_t rh[32], rlo[32];
+                if (my_kb > 0) {
+                    tc::tmem_ld32_nowait(tmem_base + ((uint32_t)(quarter * 32) << 16) + c0, rh);
+                    tc::tmem_ld32_nowait(tmem_base + ((uint32_t)(quarter * 32) << 16) + kHid + c0, rlo);
+                    tc::tmem_wait_ld();
+                } else {
+#pragma unroll
+                    for (int j = 0; j < 32; ++j) rh[j] = rlo[j] = 0u;
+                }
+#pragma unroll
+                for (int j = 0; j < 8; ++j)
+                    *reinterpret_cast<float4*>(smem + row * (kHid * 4) + (((c0 / 4 + j) ^ row) & 31) * 16) =
+                        make_float4(__uint_as_float(rh[4 * j]) + __uint_as_float(rlo[4 * j]), __uint_as_float(rh[4 * j + 1]) + __uint_as_float(rlo[4 * j + 1]),
+                                    __uint_as_float(rh[4 * j + 2]) + __uint_as_float(rlo[4 * j + 2]), __uint_as_float(rh[4 * j + 3]) + __uint_as_float(rlo[4 * j + 3]));
+            }
+            if (bt == 0) XQ_TL(1, 38);
+        }
+    }
+    __syncthreads();               // the FP32 tile is staged
+    {   // all 12 warps push it to L2 (a warp keeps only a few stores in flight: the more warps, the shorter this phase)
+        float* out = part + (size_t)(mt * kDwSplits + ks) * BM * kHid;
+#pragma unroll 4
+        for (int rr = warp; rr < BM; rr += kDwThreads / 32)     // lane = 16-byte chunk of row rr
+            reinterpret_cast<float4*>(out + rr * kHid)[lane] = *reinterpret_cast<const float4*>(smem + rr * (kHid * 4) + ((lane ^ rr) & 31) * 16);
+    }
+    if (threadIdx.x == 128) XQ_TL(1, 40);
+    // ===== cluster reduction + SGD: this CTA owns rows [16 ks, 16 ks + 16) of the tile =====
+    tc::tc_fence_before();
+    __syncwarp();
+    cluster_sync_all();            // all 8 partials of the row tile are visible (release / acquire at cluster scope); also a CTA-wide barrier
+    if (threadIdx.x == 0) XQ_TL(1, 3);
+    if (warp == 2) { tc::tc_fence_after(); tc::tmem_dealloc<256>(tmem_base); }
+    float4 acc[2];
+#pragma unroll
+    for (int u = 0; u < 2; ++u) {
+        acc[u] = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (e[u] >= 0) {
+#pragma unroll
+            for (int p = 0; p < kDwSplits; ++p) {               // fixed order: the sum is deterministic
+                const float4 v = __ldcg(reinterpret_cast<const float4*>(src[u] + (size_t)p * BM * kHid));
+                acc[u].x += v.x; acc[u].y += v.y; acc[u].z += v.z; acc[u].w += v.w;
             }
         }
     }
-    tc::tc_fence_before();
-    __syncthreads();
-    if (warp == 2) { tc::tc_fence_after(); tc::tmem_dealloc<128>(tmem_base); }
-}
-
-// gradient = sum over the k-splits of the partials: rows 0..1259 dW0^T, row 1260 db0, rows 1280..1369 dW1 rows 0..89 (db1 was
-// accumulated by td_delta_kernel).  APPLY: the SGD step W -= lr * grad (updateWeightsBiasesKernel, src/dqn.cu:310-319) is fused
-// and the BF16 operand copy of the touched W1 rows refreshed; otherwise the compact gradient is written for the all-reduce.
-template <bool APPLY>
-__global__ void __launch_bounds__(256) dw_reduce_kernel(const float* __restrict__ part, int k_splits, float* __restrict__ grad, float* __restrict__ W0T,
-                                                       float* __restrict__ b0, float* __restrict__ W1, float* __restrict__ b1,
-                                                       __nv_bfloat16* __restrict__ W1bf, float lr) {
-    const int i = blockIdx.x * blockDim.x + threadIdx.x;           // float4 index over the compact gradient (without db1)
-    if (i < kGradB1 / 4) {
-        const int e = 4 * i;                                        // element of the compact gradient
-        const int row = e < kGradW1 ? e / kHid : kFeatPad + (e - kGradW1) / kHid;      // row of the partial
-        const int col = e % kHid;
-        float4 a = make_float4(0.f, 0.f, 0.f, 0.f);
-        for (int s = 0; s < k_splits; ++s) {
-            const float4 v = *reinterpret_cast<const float4*>(part + ((size_t)s * kDwRows + row) * kHid + col);
-            a.x += v.x; a.y += v.y; a.z += v.z; a.w += v.w;
-        }
-        if (!APPLY) { reinterpret_cast<float4*>(grad)[i] = a; return; }
-        float* dst = e < kGradB0 ? W0T + e : (e < kGradW1 ? b0 + (e - kGradB0) : W1 + (e - kGradW1));
-        float4 w = *reinterpret_cast<float4*>(dst);
-        w.x -= lr * a.x; w.y -= lr * a.y; w.z -= lr * a.z; w.w -= lr * a.w;
+#pragma unroll
+    for (int u = 0; u < 2; ++u) {
+        if (e[u] < 0) continue;
+        if (!apply) { *reinterpret_cast<float4*>(grad + e[u]) = acc[u]; continue; }
+        float* dst = e[u] < kGradB0 ? W0T + e[u] : (e[u] < kGradW1 ? b0 + (e[u] - kGradB0) : W1 + (e[u] - kGradW1));
+        float4 w = wold[u];
+        w.x -= lr * acc[u].x; w.y -= lr * acc[u].y; w.z -= lr * acc[u].z; w.w -= lr * acc[u].w;
         *reinterpret_cast<float4*>(dst) = w;
-        if (e >= kGradW1) {
+        if (e[u] >= kGradW1) {                                  // refresh the BF16 operand copy of the touched W1 row
             __nv_bfloat162 p0 = __floats2bfloat162_rn(w.x, w.y), p1 = __floats2bfloat162_rn(w.z, w.w);
             uint2 pk; pk.x = *reinterpret_cast<uint32_t*>(&p0); pk.y = *reinterpret_cast<uint32_t*>(&p1);
-            *reinterpret_cast<uint2*>(W1bf + (e - kGradW1)) = pk;
+            *reinterpret_cast<uint2*>(W1bf + (e[u] - kGradW1)) = pk;
         }
-    } else if (APPLY) {
-        const int r = i - kGradB1 / 4;                              // db1: one thread per row
-        if (r < kQRows) { b1[r] -= lr * grad[kGradB1 + r]; }
     }
+    if (apply && w1_tile && ks == 0 && threadIdx.x < kQRows) b1[threadIdx.x] -= lr * grad[kGradB1 + threadIdx.x];     // db1 came from td_delta_kernel
+    if (threadIdx.x == 32) XQ_TL(1, 37);
 }
 
 // SGD: W -= lr * grad on the compact gradient (src/dqn.cu:310-319), refresh the BF16 operand rows, clear the gradient
@@ -594,8 +748,21 @@ static int make_tmap(CUtensorMap* m, const void* base, int64_t rows, int box_row
     return XQ_OK;
 }
 
+// compact batch [14 words][ld samples] u32, box = 64 samples x 14 words, no swizzle, out-of-range samples read as zero
+static int make_tmap_cb(CUtensorMap* m, const void* base, int64_t n, int64_t ld) {
+    EncodeTiledFn fn = encode_fn();
+    if (!fn) return fail(XQ_ERR_CUDA, "cuTensorMapEncodeTiled is not available from this driver");
+    cuuint64_t dims[2] = {(cuuint64_t)n, 14};
+    cuuint64_t strides[1] = {(cuuint64_t)ld * 4};
+    cuuint32_t box[2] = {(cuuint32_t)BK, 14};
+    cuuint32_t estr[2] = {1, 1};
+    CUresult r = fn(m, CU_TENSOR_MAP_DATA_TYPE_UINT32, 2, const_cast<void*>(base), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                    CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) return fail(XQ_ERR_CUDA, "cuTensorMapEncodeTiled (compact batch) failed with CUresult %d", (int)r);
+    return XQ_OK;
+}
+
 static inline unsigned blocks(int64_t n, int per) { return (unsigned)((n + per - 1) / per); }
-constexpr int kDwSplits = 13;                       // 11 row tiles x 13 sample splits = 143 CTAs
 
 void dqn_fast_destroy(xq_dqn_s* h) {
     Fast* f = h->fast;
@@ -603,7 +770,7 @@ void dqn_fast_destroy(xq_dqn_s* h) {
     cudaFree(f->W0T); cudaFree(f->b0); cudaFree(f->W1); cudaFree(f->b1); cudaFree(f->W1bf);
     cudaFree(f->tW0T); cudaFree(f->tb0); cudaFree(f->tW1); cudaFree(f->tb1); cudaFree(f->tW1bf);
     cudaFree(f->grad); cudaFree(f->boards); cudaFree(f->Hbf); cudaFree(f->H2bf); cudaFree(f->Hf); cudaFree(f->zpart);
-    cudaFree(f->to8); cudaFree(f->d0hi); cudaFree(f->d0lo); cudaFree(f->ghi); cudaFree(f->glo); cudaFree(f->part); cudaFree(f->q);
+    cudaFree(f->cb); cudaFree(f->d0hi); cudaFree(f->d0lo); cudaFree(f->ghi); cudaFree(f->glo); cudaFree(f->q); cudaFree(f->part);
     delete f;
     h->fast = nullptr;
 }
@@ -628,22 +795,22 @@ static int fast_init(xq_dqn_s* h) {
     if (int rc = make_tmap(&f->tmTW1, f->tW1bf, kOut, BN)) return rc;
     XQ_CUDA(cudaFuncSetAttribute(l1_gemm_kernel<EPI_ROWMAX>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kGemmSmem));
     XQ_CUDA(cudaFuncSetAttribute(l1_gemm_kernel<EPI_STORE_TANH>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kGemmSmem));
-    XQ_CUDA(cudaFuncSetAttribute(dw0_gemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kDwSmem));
-    XQ_CUDA(cudaMalloc(&f->part, sizeof(float) * kDwSplits * kDwRows * kHid));
+    XQ_CUDA(cudaFuncSetAttribute(dw_gemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kDwSmem));
+    XQ_CUDA(cudaMalloc(&f->part, sizeof(float) * kDwMTiles * kDwSplits * BM * kHid));
     return XQ_OK;
 }
 
 static int fast_reserve(xq_dqn_s* h, int64_t n) {
     Fast* f = h->fast;
     if (n <= f->cap) return XQ_OK;
-    cudaFree(f->boards); cudaFree(f->Hbf); cudaFree(f->H2bf); cudaFree(f->Hf); cudaFree(f->zpart); cudaFree(f->to8);
+    cudaFree(f->boards); cudaFree(f->Hbf); cudaFree(f->H2bf); cudaFree(f->Hf); cudaFree(f->zpart); cudaFree(f->cb);
     cudaFree(f->d0hi); cudaFree(f->d0lo); cudaFree(f->ghi); cudaFree(f->glo);
-    f->boards = nullptr; f->Hbf = f->H2bf = nullptr; f->Hf = f->zpart = nullptr; f->to8 = nullptr; f->d0hi = f->d0lo = f->ghi = f->glo = nullptr; f->cap = 0;
+    f->boards = nullptr; f->Hbf = f->H2bf = nullptr; f->Hf = f->zpart = nullptr; f->cb = nullptr; f->d0hi = f->d0lo = f->ghi = f->glo = nullptr; f->cap = 0;
     const int64_t rows = (n + BM - 1) / BM * BM;
     XQ_CUDA(cudaMalloc(&f->boards, sizeof(Transition) * n));
     XQ_CUDA(cudaMalloc(&f->Hbf, sizeof(__nv_bfloat16) * rows * kHid)); XQ_CUDA(cudaMalloc(&f->H2bf, sizeof(__nv_bfloat16) * rows * kHid));
     XQ_CUDA(cudaMalloc(&f->Hf, sizeof(float) * rows * kHid)); XQ_CUDA(cudaMalloc(&f->zpart, sizeof(float) * kParts * rows));
-    XQ_CUDA(cudaMalloc(&f->to8, (size_t)rows));
+    XQ_CUDA(cudaMalloc(&f->cb, sizeof(uint32_t) * 14 * rows));
     XQ_CUDA(cudaMalloc(&f->d0hi, sizeof(__nv_bfloat16) * rows * kHid)); XQ_CUDA(cudaMalloc(&f->d0lo, sizeof(__nv_bfloat16) * rows * kHid));
     XQ_CUDA(cudaMalloc(&f->ghi, sizeof(__nv_bfloat16) * rows * kHid)); XQ_CUDA(cudaMalloc(&f->glo, sizeof(__nv_bfloat16) * rows * kHid));
     f->cap = n; f->tm_rows = 0;
@@ -661,6 +828,7 @@ static int fast_maps(xq_dqn_s* h, int64_t n) {
     if (int rc = make_tmap(&f->tmD0lo, f->d0lo, kHid, kHid, n, ld)) return rc;
     if (int rc = make_tmap(&f->tmGhi, f->ghi, kHid, kHid, n, ld)) return rc;
     if (int rc = make_tmap(&f->tmGlo, f->glo, kHid, kHid, n, ld)) return rc;
+    if (int rc = make_tmap_cb(&f->tmCb, f->cb, n, ld)) return rc;
     f->tm_rows = n;
     return XQ_OK;
 }
@@ -741,7 +909,7 @@ int xq_dqn_forward_boards(xq_dqn_t h, const xq_env_rec* boards_host, int64_t n, 
 
 }  // extern "C" (reopened below)
 namespace xq {
-// one batched TD update on the batch described by `ref` (contiguous transitions or in-place replay draws): 5 launches
+// one batched TD update on the batch described by `ref` (contiguous transitions or in-place replay draws): 4 kernels
 int td_update_core(xq_dqn_s* h, const BatchRef& ref, int64_t n, int use_target_net, double lr, int apply) {
     if (int rc = ensure_fast(h)) return rc;
     if (int rc = fast_reserve(h, n)) return rc;
@@ -751,25 +919,25 @@ int td_update_core(xq_dqn_s* h, const BatchRef& ref, int64_t n, int use_target_n
     const int64_t ld = (f->cap + BM - 1) / BM * BM;
     // h(s) with the online net; h(s') with the online (ChessAI::train) or target (DQN::train) net
     l0_pair_kernel<<<blocks(2 * n * 32, 256), 256, 0, h->stream>>>(ref, n, f->W0T, f->b0, use_target_net ? f->tW0T : f->W0T,
-                                                                 use_target_net ? f->tb0 : f->b0, f->Hbf, f->Hf, f->H2bf);
+                                                                 use_target_net ? f->tb0 : f->b0, f->Hbf, f->Hf, f->H2bf, f->cb, ld);
     XQ_LAUNCH_CHECK();
     if (int rc = launch_gemm(h, EPI_ROWMAX, f->tmH2, use_target_net ? f->tmTW1 : f->tmW1, use_target_net ? f->tb1 : f->b1, n, nullptr)) return rc;
     XQ_CUDA(cudaMemsetAsync(f->grad + kGradB1, 0, sizeof(float) * (kQRows + 8), h->stream));      // db1 and the loss statistics
-    td_delta_kernel<<<blocks(n * 32, 256), 256, 0, h->stream>>>(ref, n, f->Hf, f->W1, f->b1, f->zpart, ld, kParts, (float)h->gamma, h->mode,
-                                                                f->to8, f->d0hi, f->d0lo, f->ghi, f->glo, ld, f->grad + kGradB1, f->info);
+    td_delta_kernel<<<blocks(n * 32, 256), 256, 0, h->stream>>>(f->cb, n, f->Hf, f->W1, f->b1, f->zpart, ld, kParts, (float)h->gamma, h->mode,
+                                                                f->d0hi, f->d0lo, f->ghi, f->glo, ld, f->grad + kGradB1, f->info);
     XQ_LAUNCH_CHECK();
-    const int total_kb = (int)((n + BK - 1) / BK);
-    const int k_splits = total_kb < kDwSplits ? total_kb : kDwSplits;
-    dw0_gemm_kernel<<<dim3(kDwMTiles, k_splits), kDwThreads, kDwSmem, h->stream>>>(f->tmD0hi, f->tmD0lo, f->tmGhi, f->tmGlo, ref, f->to8, (int)n,
-                                                                                   k_splits, f->part);
-    XQ_LAUNCH_CHECK();
-    const unsigned rb = blocks(kGradB1 / 4 + kQRows, 256);
-    if (apply) {
-        dw_reduce_kernel<true><<<rb, 256, 0, h->stream>>>(f->part, k_splits, f->grad, f->W0T, f->b0, f->W1, f->b1, f->W1bf, (float)lr);
-        h->f64_current = false;
-    } else {
-        dw_reduce_kernel<false><<<rb, 256, 0, h->stream>>>(f->part, k_splits, f->grad, f->W0T, f->b0, f->W1, f->b1, f->W1bf, (float)lr);
+    {   // dW0 / db0 / dW1 contraction, cluster reduction and the SGD step (or the compact gradient) in one launch
+        cudaLaunchConfig_t cfg = {};
+        cfg.gridDim = dim3(kDwMTiles, kDwSplits); cfg.blockDim = dim3(kDwThreads); cfg.dynamicSmemBytes = kDwSmem; cfg.stream = h->stream;
+        cudaLaunchAttribute at[1];
+        at[0].id = cudaLaunchAttributeClusterDimension;
+        at[0].val.clusterDim.x = 1; at[0].val.clusterDim.y = kDwSplits; at[0].val.clusterDim.z = 1;
+        cfg.attrs = at; cfg.numAttrs = 1;
+        XQ_CUDA(cudaLaunchKernelEx(&cfg, dw_gemm_kernel, f->tmD0hi, f->tmD0lo, f->tmGhi, f->tmGlo, f->tmCb, (int)n, f->part, f->grad, f->W0T,
+                                   f->b0, f->W1, f->b1, f->W1bf, (float)lr, apply ? 1 : 0));
+        ++g_launches;
     }
+    if (apply) h->f64_current = false;
     XQ_LAUNCH_CHECK();
     return XQ_OK;
 }
@@ -822,5 +990,14 @@ int xq_dqn_apply_grads(xq_dqn_t h, double lr) {
     h->f64_current = false;
     return XQ_OK;
 }
+
+#ifdef XQ_TIMELINE
+int xq_debug_timeline(long long* out_host, int64_t n) {   // profiling builds only
+    if (n > (int64_t)(sizeof(long long) * 2 * 160 * 64)) n = sizeof(long long) * 2 * 160 * 64;
+    XQ_CUDA(cudaDeviceSynchronize());
+    XQ_CUDA(cudaMemcpyFromSymbol(out_host, g_tl, (size_t)n));
+    return XQ_OK;
+}
+#endif
 
 }  // extern "C"
