@@ -69,7 +69,9 @@ struct Fast {
     float* Hf = nullptr;                               // h(s) FP32 [cap][128]
     float* zpart = nullptr;                            // [kParts][cap] row-max partials
     float* part = nullptr;                             // [11 row tiles][8 splits][128][128] FP32 partials of the gradient contraction (L2 scratch)
-    uint32_t* cb = nullptr;                            // [14][ld] compact batch, word-major: 12 board words of s | action,mover,done | reward
+    uint32_t* cb = nullptr;                            // [15][ld] compact batch, word-major: 12 board words of s | action,mover,done | reward | delta1
+    float* dbpart = nullptr;                           // [8 splits][128] per-CTA sums of delta1 per action.to
+    float* info_slots = nullptr;                       // [16][4] loss statistics accumulated by td_delta_kernel
     __nv_bfloat16 *d0hi = nullptr, *d0lo = nullptr;    // delta0^T [128][ld] BF16 hi / lo (B operand of the dW0 contraction)
     __nv_bfloat16 *ghi = nullptr, *glo = nullptr;      // (delta1 h)^T [128][ld] BF16 hi / lo (B operand of the dW1 contraction)
     float* q = nullptr;                                // [cap][8100] (debug path only, allocated on demand)
@@ -128,28 +130,65 @@ __global__ void __launch_bounds__(256) l0_forward_kernel(const uint8_t* __restri
     if (Hf) reinterpret_cast<float4*>(Hf + s * kHid)[lane] = h;
     store_h_bf16(Hbf, s, lane, h);
 }
-// both states of every transition in one launch: warps [0,n) -> h(s) with the online net (BF16 + FP32),
-// warps [n,2n) -> h(s') with the bootstrap net (online: ChessAI::train; target: DQN::train).
-// The first-state warps also write the compact batch record (board of s, action, reward, done) that the
-// later kernels of the update read: the replay ring is touched by this kernel only.
-__global__ void __launch_bounds__(256) l0_pair_kernel(BatchRef batch, int64_t n, const float* __restrict__ W0T, const float* __restrict__ b0,
-                                                     const float* __restrict__ W0T2, const float* __restrict__ b02,
-                                                     __nv_bfloat16* __restrict__ Hbf, float* __restrict__ Hf, __nv_bfloat16* __restrict__ H2bf,
-                                                     uint32_t* __restrict__ cb, int64_t ld) {
-    const int64_t w = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-    const int lane = threadIdx.x & 31;
-    if (w >= 2 * n) return;
-    const bool second = w >= n;
-    const int64_t s = second ? w - n : w;
-    const uint32_t* t = reinterpret_cast<const uint32_t*>(batch.at(s));
+// Both states of every transition in one launch, ONE WARP PER TRANSITION: the 128-byte replay record is read once
+// (one coalesced line); lane l decodes squares l, l+32, l+64 of both boards, ballots compact the occupied squares into
+// two row lists in shared memory (padded with the all-zero row kIn), and the two gather-sums -- h(s) with the online
+// net, h(s') with the bootstrap net (online: ChessAI::train; target: DQN::train) -- run interleaved, four rows of
+// each in flight, ~9 instructions per piece.  The warp also writes the compact batch record (board of s, action,
+// reward, done; word-major) that the later kernels of the update read: the replay ring is touched here only.
+// Block 0 clears db1 and the loss statistics (td_delta_kernel accumulates into them).
+constexpr int kL0Warps = 8;
+__global__ void __launch_bounds__(kL0Warps * 32) l0_pair_kernel(BatchRef batch, int64_t n, const float* __restrict__ W0T, const float* __restrict__ b0,
+                                                               const float* __restrict__ W0T2, const float* __restrict__ b02,
+                                                               float* __restrict__ Hf, __nv_bfloat16* __restrict__ H2bf,
+                                                               uint32_t* __restrict__ cb, int64_t ld, float* __restrict__ zero_me, int n_zero) {
+    __shared__ uint16_t s_rows[kL0Warps][2][96];               // any board: up to 90 occupied squares (a legal one has <= 32)
+    const int wib = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int64_t s = (int64_t)blockIdx.x * kL0Warps + wib;
+    if (blockIdx.x == 0) for (int i = threadIdx.x; i < n_zero; i += blockDim.x) zero_me[i] = 0.0f;
+    if (s >= n) return;
     // transition words: 0..11 board of s, 12..23 board of s', 24 = action | mover << 16 | done << 24, 25 = reward
-    uint32_t word = 0u;
-    if (second) { if (lane < 12) word = t[12 + lane]; }
-    else if (lane < 14) word = t[lane < 12 ? lane : lane + 12];
-    if (!second && lane < 14) cb[lane * ld + s] = word;       // word-major: the readers walk consecutive samples
-    const float4 h = l0_gather(lane < 12 ? word : 0u, lane, second ? W0T2 : W0T, second ? b02 : b0);
-    if (!second) reinterpret_cast<float4*>(Hf + s * kHid)[lane] = h;
-    store_h_bf16(second ? H2bf : Hbf, s, lane, h);
+    const uint32_t word = lane < 26 ? reinterpret_cast<const uint32_t*>(batch.at(s))[lane] : 0u;
+    if (lane < 12) cb[lane * ld + s] = word;                   // word-major: the readers walk consecutive samples
+    else if (lane >= 24 && lane < 26) cb[(lane - 12) * ld + s] = word;
+#pragma unroll
+    for (int r = 0; r < 3; ++r) { s_rows[wib][0][lane + 32 * r] = (uint16_t)kIn; s_rows[wib][1][lane + 32 * r] = (uint16_t)kIn; }
+    __syncwarp();
+    int cnt[2] = {0, 0};
+#pragma unroll
+    for (int r = 0; r < 3; ++r) {
+        const int q = lane + 32 * r;                            // square; q < 90 in the last round only for lanes < 26
+        const uint32_t wa = __shfl_sync(0xFFFFFFFFu, word, (q >> 3) % 12), wb = __shfl_sync(0xFFFFFFFFu, word, 12 + (q >> 3) % 12);
+#pragma unroll
+        for (int which = 0; which < 2; ++which) {
+            const int code = ((which ? wb : wa) >> (4 * (q & 7))) & 15;
+            const bool piece = q < XQ_SQUARES && code >= 1 && code <= 14;
+            const unsigned m = __ballot_sync(0xFFFFFFFFu, piece);
+            const int rank = cnt[which] + __popc(m & ((1u << lane) - 1u));
+            if (piece) s_rows[wib][which][rank] = (uint16_t)(q * 14 + code - 1);      // getStateRepresentation index, src/chessai.cpp:278-282
+            cnt[which] += __popc(m);
+        }
+    }
+    __syncwarp();
+    const int steps = max(cnt[0], cnt[1]);                      // <= 90; the lists are padded to a multiple of 4 with the zero row
+    float4 a = reinterpret_cast<const float4*>(b0)[lane], b = reinterpret_cast<const float4*>(b02)[lane];
+    const float4* Wa = reinterpret_cast<const float4*>(W0T) + lane;
+    const float4* Wb = reinterpret_cast<const float4*>(W0T2) + lane;
+    for (int k = 0; k < steps; k += 4) {
+        float4 ra[4], rb[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            ra[u] = Wa[(size_t)s_rows[wib][0][k + u] * (kHid / 4)];
+            rb[u] = Wb[(size_t)s_rows[wib][1][k + u] * (kHid / 4)];
+        }
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            a.x += ra[u].x; a.y += ra[u].y; a.z += ra[u].z; a.w += ra[u].w;
+            b.x += rb[u].x; b.y += rb[u].y; b.z += rb[u].z; b.w += rb[u].w;
+        }
+    }
+    reinterpret_cast<float4*>(Hf + s * kHid)[lane] = make_float4(tanhf(a.x), tanhf(a.y), tanhf(a.z), tanhf(a.w));
+    store_h_bf16(H2bf, s, lane, make_float4(tanhf(b.x), tanhf(b.y), tanhf(b.z), tanhf(b.w)));
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -358,24 +397,24 @@ static_assert(sizeof(Transition) == 128 && sizeof(xq_transition) == 128, "transi
 
 // TD error, one warp per transition (src/chessai.cpp:121-131 + src/dqn.cu:288-308 specialised to a one-hot delta1).
 // Outputs per sample: delta1, its row `to`, delta0 as FP32 and, transposed and split into BF16 hi + lo, as the
-// K-major B operand of the dW0 contraction.  No global atomics except 3 per CTA for the loss statistics.
-__global__ void __launch_bounds__(256) td_delta_kernel(const uint32_t* __restrict__ cb, int64_t n, const float* __restrict__ Hf,
+// K-major B operand of the dW0 contraction; delta1 itself goes into row 14 of the compact batch (db1 is summed by
+// dw_gemm_kernel).  Global atomics: 3 per CTA for the loss statistics, spread over 16 slots (same-address L2
+// atomics serialise at ~27 cycles each: 512 CTAs on one address were 14 k cycles, the whole kernel).
+constexpr int kInfoSlots = 16;
+__global__ void __launch_bounds__(256) td_delta_kernel(uint32_t* __restrict__ cb, int64_t n, const float* __restrict__ Hf,
                                                       const float* __restrict__ W1, const float* __restrict__ b1,
                                                       const float* __restrict__ zpart, int64_t zstride, int n_parts, float gamma, int mode,
                                                       __nv_bfloat16* __restrict__ d0hi, __nv_bfloat16* __restrict__ d0lo,
                                                       __nv_bfloat16* __restrict__ ghi, __nv_bfloat16* __restrict__ glo, int64_t ld,
-                                                      float* __restrict__ gb1, float* __restrict__ info) {
+                                                      float* __restrict__ info_slots) {
     __shared__ float s_info[8][3];
     __shared__ __align__(16) float s_d0[8][kHid];          // delta0 of the CTA's 8 consecutive samples, for the transposed stores
     __shared__ __align__(16) float s_g[8][kHid];           // delta1 * h (the dW1 contraction's B operand)
-    __shared__ float s_d1[8];
-    __shared__ int s_to[8];
     const int64_t s = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
     float loss = 0.0f, qv = 0.0f, tv = 0.0f;
     reinterpret_cast<float4*>(s_d0[wib])[lane] = make_float4(0.f, 0.f, 0.f, 0.f);
     reinterpret_cast<float4*>(s_g[wib])[lane] = make_float4(0.f, 0.f, 0.f, 0.f);
-    if (lane == 0) { s_d1[wib] = 0.0f; s_to[wib] = -1; }
     if (s < n) {
         const uint32_t meta = cb[12 * ld + s];
         const int to = XQ_ACTION_TO(meta & 0xFFFFu);           // the Q index of the taken action is action.to (:124,:127)
@@ -398,7 +437,7 @@ __global__ void __launch_bounds__(256) td_delta_kernel(const uint32_t* __restric
                              wd.w * d1 * (1.0f - h.w * h.w)};
         reinterpret_cast<float4*>(s_d0[wib])[lane] = make_float4(d0[0], d0[1], d0[2], d0[3]);
         reinterpret_cast<float4*>(s_g[wib])[lane] = make_float4(d1 * h.x, d1 * h.y, d1 * h.z, d1 * h.w);
-        if (lane == 0) { s_d1[wib] = d1; s_to[wib] = to; }
+        if (lane == 0) cb[14 * ld + s] = __float_as_uint(d1);
         loss = 0.5f * (q - target) * (q - target); qv = q; tv = target;
     }
     if (lane == 0) { s_info[wib][0] = loss; s_info[wib][1] = qv; s_info[wib][2] = tv; }
@@ -423,19 +462,11 @@ __global__ void __launch_bounds__(256) td_delta_kernel(const uint32_t* __restric
             if (s0 < ld) *reinterpret_cast<uint4*>(dst + (int64_t)j * ld + s0) = make_uint4(packed[0], packed[1], packed[2], packed[3]);
         }
     }
-    if (threadIdx.x < 8) {   // db1[to] += delta1, equal rows of the CTA's 8 samples merged first (a greedy policy concentrates them)
-        const int to = s_to[threadIdx.x];
-        const float d = s_d1[threadIdx.x];
-        const unsigned peers = __match_any_sync(0xFFu, to);
-        float sum = 0.0f;
-        for (int k = 0; k < 8; ++k) if (peers >> k & 1u) sum += __shfl_sync(0xFFu, d, k);
-        if (to >= 0 && to < kQRows && (int)(__ffs(peers) - 1) == (int)threadIdx.x) atomicAdd(gb1 + to, sum);
-    }
     if (threadIdx.x < 3) {
         float a = 0.0f;
 #pragma unroll
         for (int k = 0; k < 8; ++k) a += s_info[k][threadIdx.x];
-        atomicAdd(info + threadIdx.x, a);
+        atomicAdd(info_slots + (blockIdx.x % kInfoSlots) * 4 + threadIdx.x, a);
     }
 }
 
@@ -458,7 +489,8 @@ constexpr int kDwStages = 4;
 constexpr uint32_t kDwABytes = BM * BK * 2;              // 16 KB
 constexpr uint32_t kDwBBytes = 2 * kHid * BK * 2;        // 32 KB: rows 0..127 = hi, rows 128..255 = lo -> ONE N = 256 operand
 constexpr int kDwThreads = 384;                          // warp 0 TMA, 1 MMA, 2 TMEM alloc, 4-11 one-hot builders (4-7 also epilogue)
-constexpr uint32_t kDwCBytes = 14 * BK * 4;              // 3.5 KB: the compact-batch words of the k-block's 64 samples, [word][sample]
+constexpr int kCbRows = 15;                              // compact batch rows: 12 board words | action,mover,done | reward | delta1 (FP32 bits)
+constexpr uint32_t kDwCBytes = kCbRows * BK * 4;         // 3.75 KB: the compact-batch words of the k-block's 64 samples, [word][sample]
 constexpr uint32_t kDwCStride = 4096;
 constexpr size_t kDwSmem = 1024 + kDwStages * (kDwABytes + kDwBBytes + kDwCStride) + 256;
 static_assert(kDwStages * (kDwABytes + kDwBBytes) >= BM * kHid * 4, "the epilogue stages the FP32 tile in the operand buffers");
@@ -472,6 +504,7 @@ __device__ __forceinline__ void cluster_sync_all() {
 __global__ void __launch_bounds__(kDwThreads, 1) dw_gemm_kernel(const __grid_constant__ CUtensorMap tmD0Hi, const __grid_constant__ CUtensorMap tmD0Lo,
                                                                const __grid_constant__ CUtensorMap tmGHi, const __grid_constant__ CUtensorMap tmGLo,
                                                                const __grid_constant__ CUtensorMap tmCb, int n, float* __restrict__ part,
+                                                               float* __restrict__ dbpart, float* __restrict__ info_slots, float* __restrict__ info,
                                                                float* __restrict__ grad,
                                                                float* __restrict__ W0T, float* __restrict__ b0, float* __restrict__ W1,
                                                                float* __restrict__ b1, __nv_bfloat16* __restrict__ W1bf, float lr, int apply) {
@@ -486,6 +519,7 @@ __global__ void __launch_bounds__(kDwThreads, 1) dw_gemm_kernel(const __grid_con
     uint64_t* cfull = bars + 2 * kDwStages;   // kDwStages: board words landed
     uint64_t* acc_full = bars + 3 * kDwStages;
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 3 * kDwStages + 1);
+    __shared__ float s_db1[BM];            // the dW1 tile's CTAs: sum of delta1 per action.to over this CTA's samples
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int mt = blockIdx.x, ks = (int)cluster_rank();     // cluster = the kDwSplits CTAs (blockIdx.y) of one row tile
@@ -539,6 +573,7 @@ __global__ void __launch_bounds__(kDwThreads, 1) dw_gemm_kernel(const __grid_con
     const int bt = threadIdx.x - 128;
     if (warp >= 4)                                             // the one-hot stages start from all-zero
         for (int u = bt; u < (int)(kDwStages * kDwABytes / 16); u += 256) reinterpret_cast<uint4*>(sA)[u] = make_uint4(0u, 0u, 0u, 0u);
+    if (threadIdx.x < BM) s_db1[threadIdx.x] = 0.0f;
     tc::tc_fence_before();
     __syncthreads();
     tc::tc_fence_after();
@@ -592,7 +627,11 @@ __global__ void __launch_bounds__(kDwThreads, 1) dw_gemm_kernel(const __grid_con
                 tc::mbar_wait(cfull + st, (i / kDwStages) & 1);
                 uint32_t off[3] = {0xFFFFFFFFu, 0xFFFFFFFFu, 0xFFFFFFFFu};
                 if (b < n && w1_tile) {
-                    if (grp == 0) off[0] = sw128_offset((int)XQ_ACTION_TO(words[12 * BK] & 0xFFFFu), sample);      // row = action.to (< 128)
+                    if (grp == 0) {
+                        const int to = (int)XQ_ACTION_TO(words[12 * BK] & 0xFFFFu);
+                        off[0] = sw128_offset(to, sample);                                                   // row = action.to (< 128)
+                        atomicAdd(&s_db1[to], __uint_as_float(words[14 * BK]));                             // db1[to] += delta1 (src/dqn.cu:310-319)
+                    }
                 } else if (b < n) {
 #pragma unroll
                     for (int u = 0; u < 3; ++u) {
@@ -650,6 +689,7 @@ __global__ void __launch_bounds__(kDwThreads, 1) dw_gemm_kernel(const __grid_con
 #pragma unroll 4
         for (int rr = warp; rr < BM; rr += kDwThreads / 32)     // lane = 16-byte chunk of row rr
             reinterpret_cast<float4*>(out + rr * kHid)[lane] = *reinterpret_cast<const float4*>(smem + rr * (kHid * 4) + ((lane ^ rr) & 31) * 16);
+        if (w1_tile && threadIdx.x < BM) dbpart[ks * BM + threadIdx.x] = s_db1[threadIdx.x];
     }
     if (threadIdx.x == 128) XQ_TL(1, 40);
     // ===== cluster reduction + SGD: this CTA owns rows [16 ks, 16 ks + 16) of the tile =====
@@ -684,7 +724,19 @@ __global__ void __launch_bounds__(kDwThreads, 1) dw_gemm_kernel(const __grid_con
             *reinterpret_cast<uint2*>(W1bf + (e[u] - kGradW1)) = pk;
         }
     }
-    if (apply && w1_tile && ks == 0 && threadIdx.x < kQRows) b1[threadIdx.x] -= lr * grad[kGradB1 + threadIdx.x];     // db1 came from td_delta_kernel
+    if (w1_tile && ks == 0) {
+        if (threadIdx.x < kQRows) {                             // db1: the 8 per-CTA sums in fixed order
+            float g = 0.0f;
+#pragma unroll
+            for (int p = 0; p < kDwSplits; ++p) g += __ldcg(dbpart + p * BM + threadIdx.x);
+            grad[kGradB1 + threadIdx.x] = g;
+            if (apply) b1[threadIdx.x] -= lr * g;
+        } else if (threadIdx.x >= 128 && threadIdx.x < 131) {   // loss statistics: fold the slots td_delta_kernel accumulated into
+            float a = 0.0f;
+            for (int p = 0; p < kInfoSlots; ++p) a += __ldcg(info_slots + p * 4 + (threadIdx.x - 128));
+            info[threadIdx.x - 128] = a;
+        }
+    }
     if (threadIdx.x == 32) XQ_TL(1, 37);
 }
 
@@ -748,13 +800,13 @@ static int make_tmap(CUtensorMap* m, const void* base, int64_t rows, int box_row
     return XQ_OK;
 }
 
-// compact batch [14 words][ld samples] u32, box = 64 samples x 14 words, no swizzle, out-of-range samples read as zero
+// compact batch [15 words][ld samples] u32, box = 64 samples x 15 words, no swizzle, out-of-range samples read as zero
 static int make_tmap_cb(CUtensorMap* m, const void* base, int64_t n, int64_t ld) {
     EncodeTiledFn fn = encode_fn();
     if (!fn) return fail(XQ_ERR_CUDA, "cuTensorMapEncodeTiled is not available from this driver");
-    cuuint64_t dims[2] = {(cuuint64_t)n, 14};
+    cuuint64_t dims[2] = {(cuuint64_t)n, (cuuint64_t)kCbRows};
     cuuint64_t strides[1] = {(cuuint64_t)ld * 4};
-    cuuint32_t box[2] = {(cuuint32_t)BK, 14};
+    cuuint32_t box[2] = {(cuuint32_t)BK, (cuuint32_t)kCbRows};
     cuuint32_t estr[2] = {1, 1};
     CUresult r = fn(m, CU_TENSOR_MAP_DATA_TYPE_UINT32, 2, const_cast<void*>(base), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
                     CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
@@ -770,7 +822,7 @@ void dqn_fast_destroy(xq_dqn_s* h) {
     cudaFree(f->W0T); cudaFree(f->b0); cudaFree(f->W1); cudaFree(f->b1); cudaFree(f->W1bf);
     cudaFree(f->tW0T); cudaFree(f->tb0); cudaFree(f->tW1); cudaFree(f->tb1); cudaFree(f->tW1bf);
     cudaFree(f->grad); cudaFree(f->boards); cudaFree(f->Hbf); cudaFree(f->H2bf); cudaFree(f->Hf); cudaFree(f->zpart);
-    cudaFree(f->cb); cudaFree(f->d0hi); cudaFree(f->d0lo); cudaFree(f->ghi); cudaFree(f->glo); cudaFree(f->q); cudaFree(f->part);
+    cudaFree(f->cb); cudaFree(f->d0hi); cudaFree(f->d0lo); cudaFree(f->ghi); cudaFree(f->glo); cudaFree(f->q); cudaFree(f->part); cudaFree(f->dbpart); cudaFree(f->info_slots);
     delete f;
     h->fast = nullptr;
 }
@@ -782,21 +834,25 @@ static int fast_init(xq_dqn_s* h) {
     Fast* f = new (std::nothrow) Fast();
     if (!f) return fail(XQ_ERR_NOMEM, "out of host memory");
     h->fast = f;
-    XQ_CUDA(cudaMalloc(&f->W0T, sizeof(float) * kIn * kHid)); XQ_CUDA(cudaMalloc(&f->b0, sizeof(float) * kHid));
+    XQ_CUDA(cudaMalloc(&f->W0T, sizeof(float) * (kIn + 1) * kHid)); XQ_CUDA(cudaMalloc(&f->b0, sizeof(float) * kHid));
     XQ_CUDA(cudaMalloc(&f->W1, sizeof(float) * kOut * kHid)); XQ_CUDA(cudaMalloc(&f->b1, sizeof(float) * kOut));
     XQ_CUDA(cudaMalloc(&f->W1bf, sizeof(__nv_bfloat16) * kOut * kHid));
-    XQ_CUDA(cudaMalloc(&f->tW0T, sizeof(float) * kIn * kHid)); XQ_CUDA(cudaMalloc(&f->tb0, sizeof(float) * kHid));
+    XQ_CUDA(cudaMalloc(&f->tW0T, sizeof(float) * (kIn + 1) * kHid)); XQ_CUDA(cudaMalloc(&f->tb0, sizeof(float) * kHid));
     XQ_CUDA(cudaMalloc(&f->tW1, sizeof(float) * kOut * kHid)); XQ_CUDA(cudaMalloc(&f->tb1, sizeof(float) * kOut));
     XQ_CUDA(cudaMalloc(&f->tW1bf, sizeof(__nv_bfloat16) * kOut * kHid));
     XQ_CUDA(cudaMalloc(&f->grad, sizeof(float) * (kGradSize + 8)));      // + 4 floats of loss statistics right behind db1
     f->info = f->grad + kGradSize;
     XQ_CUDA(cudaMemsetAsync(f->grad, 0, sizeof(float) * (kGradSize + 8), h->stream));
+    XQ_CUDA(cudaMemsetAsync(f->W0T + (size_t)kIn * kHid, 0, sizeof(float) * kHid, h->stream));      // row kIn = zeros: the padding row of the gather lists
+    XQ_CUDA(cudaMemsetAsync(f->tW0T + (size_t)kIn * kHid, 0, sizeof(float) * kHid, h->stream));
     if (int rc = make_tmap(&f->tmW1, f->W1bf, kOut, BN)) return rc;
     if (int rc = make_tmap(&f->tmTW1, f->tW1bf, kOut, BN)) return rc;
     XQ_CUDA(cudaFuncSetAttribute(l1_gemm_kernel<EPI_ROWMAX>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kGemmSmem));
     XQ_CUDA(cudaFuncSetAttribute(l1_gemm_kernel<EPI_STORE_TANH>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kGemmSmem));
     XQ_CUDA(cudaFuncSetAttribute(dw_gemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kDwSmem));
     XQ_CUDA(cudaMalloc(&f->part, sizeof(float) * kDwMTiles * kDwSplits * BM * kHid));
+    XQ_CUDA(cudaMalloc(&f->dbpart, sizeof(float) * kDwSplits * BM));
+    XQ_CUDA(cudaMalloc(&f->info_slots, sizeof(float) * kInfoSlots * 4));
     return XQ_OK;
 }
 
@@ -810,7 +866,7 @@ static int fast_reserve(xq_dqn_s* h, int64_t n) {
     XQ_CUDA(cudaMalloc(&f->boards, sizeof(Transition) * n));
     XQ_CUDA(cudaMalloc(&f->Hbf, sizeof(__nv_bfloat16) * rows * kHid)); XQ_CUDA(cudaMalloc(&f->H2bf, sizeof(__nv_bfloat16) * rows * kHid));
     XQ_CUDA(cudaMalloc(&f->Hf, sizeof(float) * rows * kHid)); XQ_CUDA(cudaMalloc(&f->zpart, sizeof(float) * kParts * rows));
-    XQ_CUDA(cudaMalloc(&f->cb, sizeof(uint32_t) * 14 * rows));
+    XQ_CUDA(cudaMalloc(&f->cb, sizeof(uint32_t) * kCbRows * rows));
     XQ_CUDA(cudaMalloc(&f->d0hi, sizeof(__nv_bfloat16) * rows * kHid)); XQ_CUDA(cudaMalloc(&f->d0lo, sizeof(__nv_bfloat16) * rows * kHid));
     XQ_CUDA(cudaMalloc(&f->ghi, sizeof(__nv_bfloat16) * rows * kHid)); XQ_CUDA(cudaMalloc(&f->glo, sizeof(__nv_bfloat16) * rows * kHid));
     f->cap = n; f->tm_rows = 0;
@@ -918,13 +974,13 @@ int td_update_core(xq_dqn_s* h, const BatchRef& ref, int64_t n, int use_target_n
     if (lr <= 0) lr = h->lr;
     const int64_t ld = (f->cap + BM - 1) / BM * BM;
     // h(s) with the online net; h(s') with the online (ChessAI::train) or target (DQN::train) net
-    l0_pair_kernel<<<blocks(2 * n * 32, 256), 256, 0, h->stream>>>(ref, n, f->W0T, f->b0, use_target_net ? f->tW0T : f->W0T,
-                                                                 use_target_net ? f->tb0 : f->b0, f->Hbf, f->Hf, f->H2bf, f->cb, ld);
+    l0_pair_kernel<<<blocks(n, kL0Warps), kL0Warps * 32, 0, h->stream>>>(ref, n, f->W0T, f->b0, use_target_net ? f->tW0T : f->W0T,
+                                                                        use_target_net ? f->tb0 : f->b0, f->Hf, f->H2bf, f->cb, ld,
+                                                                        f->info_slots, kInfoSlots * 4);      // also clears the loss-statistics slots
     XQ_LAUNCH_CHECK();
     if (int rc = launch_gemm(h, EPI_ROWMAX, f->tmH2, use_target_net ? f->tmTW1 : f->tmW1, use_target_net ? f->tb1 : f->b1, n, nullptr)) return rc;
-    XQ_CUDA(cudaMemsetAsync(f->grad + kGradB1, 0, sizeof(float) * (kQRows + 8), h->stream));      // db1 and the loss statistics
     td_delta_kernel<<<blocks(n * 32, 256), 256, 0, h->stream>>>(f->cb, n, f->Hf, f->W1, f->b1, f->zpart, ld, kParts, (float)h->gamma, h->mode,
-                                                                f->d0hi, f->d0lo, f->ghi, f->glo, ld, f->grad + kGradB1, f->info);
+                                                                f->d0hi, f->d0lo, f->ghi, f->glo, ld, f->info_slots);
     XQ_LAUNCH_CHECK();
     {   // dW0 / db0 / dW1 contraction, cluster reduction and the SGD step (or the compact gradient) in one launch
         cudaLaunchConfig_t cfg = {};
@@ -933,7 +989,7 @@ int td_update_core(xq_dqn_s* h, const BatchRef& ref, int64_t n, int use_target_n
         at[0].id = cudaLaunchAttributeClusterDimension;
         at[0].val.clusterDim.x = 1; at[0].val.clusterDim.y = kDwSplits; at[0].val.clusterDim.z = 1;
         cfg.attrs = at; cfg.numAttrs = 1;
-        XQ_CUDA(cudaLaunchKernelEx(&cfg, dw_gemm_kernel, f->tmD0hi, f->tmD0lo, f->tmGhi, f->tmGlo, f->tmCb, (int)n, f->part, f->grad, f->W0T,
+        XQ_CUDA(cudaLaunchKernelEx(&cfg, dw_gemm_kernel, f->tmD0hi, f->tmD0lo, f->tmGhi, f->tmGlo, f->tmCb, (int)n, f->part, f->dbpart, f->info_slots, f->info, f->grad, f->W0T,
                                    f->b0, f->W1, f->b1, f->W1bf, (float)lr, apply ? 1 : 0));
         ++g_launches;
     }
