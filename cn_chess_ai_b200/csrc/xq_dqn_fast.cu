@@ -51,6 +51,7 @@ constexpr uint32_t kTmemCols = 512;                 // 2 accumulator stages x BN
 constexpr int kGemmThreads = 384;                   // warp 0 TMA, 1 MMA, 2 TMEM alloc, 2-3 bias-step operands, 4-11 epilogue
 constexpr int kEpiWarps = 8;                        // two warps per TMEM lane quarter, each drains half of the BN columns
 constexpr int kParts = 2 * kNTiles;                 // row-max partials per sample (74)
+constexpr int kPartsPad = 96;                       // zpart is [row][96]: a sample's partials are 3 coalesced 128-byte reads
 constexpr uint32_t kBiasBBytes = BN * BK * 2;       // 28 KB: b1 as the B operand of the bias step
 constexpr uint32_t kOnesBytes = BM * BK * 2;        // 16 KB: the constant-one A operand of the bias step
 constexpr size_t kGemmSmem = 1024 + kBBytes + kBiasBBytes + kOnesBytes + kAStages * kABytes + 256;
@@ -67,7 +68,7 @@ struct Fast {
     xq_env_rec* boards = nullptr;                      // staging for xq_dqn_forward_boards
     __nv_bfloat16 *Hbf = nullptr, *H2bf = nullptr;     // h(s), h(s') as MMA A operands [cap][128]
     float* Hf = nullptr;                               // h(s) FP32 [cap][128]
-    float* zpart = nullptr;                            // [kParts][cap] row-max partials
+    float* zpart = nullptr;                            // [cap][kPartsPad] row-max partials
     float* part = nullptr;                             // [11 row tiles][8 splits][128][128] FP32 partials of the gradient contraction (L2 scratch)
     uint32_t* cb = nullptr;                            // [15][ld] compact batch, word-major: 12 board words of s | action,mover,done | reward | delta1
     float* dbpart = nullptr;                           // [8 splits][128] per-CTA sums of delta1 per action.to
@@ -142,15 +143,12 @@ __global__ void __launch_bounds__(kL0Warps * 32) l0_pair_kernel(BatchRef batch, 
                                                                const float* __restrict__ W0T2, const float* __restrict__ b02,
                                                                float* __restrict__ Hf, __nv_bfloat16* __restrict__ H2bf,
                                                                uint32_t* __restrict__ cb, int64_t ld, float* __restrict__ zero_me, int n_zero) {
-    __shared__ uint16_t s_rows[kL0Warps][2][96];               // any board: up to 90 occupied squares (a legal one has <= 32)
+    __shared__ __align__(8) uint16_t s_rows[kL0Warps][2][96];   // any board: up to 90 occupied squares (a legal one has <= 32)
     const int wib = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int64_t s = (int64_t)blockIdx.x * kL0Warps + wib;
-    if (blockIdx.x == 0) for (int i = threadIdx.x; i < n_zero; i += blockDim.x) zero_me[i] = 0.0f;
-    if (s >= n) return;
     // transition words: 0..11 board of s, 12..23 board of s', 24 = action | mover << 16 | done << 24, 25 = reward
-    const uint32_t word = lane < 26 ? reinterpret_cast<const uint32_t*>(batch.at(s))[lane] : 0u;
-    if (lane < 12) cb[lane * ld + s] = word;                   // word-major: the readers walk consecutive samples
-    else if (lane >= 24 && lane < 26) cb[(lane - 12) * ld + s] = word;
+    // (the replay ring is not written by the kernels of an update: it may be read before the PDL wait)
+    const uint32_t word = (s < n && lane < 26) ? reinterpret_cast<const uint32_t*>(batch.at(s))[lane] : 0u;
 #pragma unroll
     for (int r = 0; r < 3; ++r) { s_rows[wib][0][lane + 32 * r] = (uint16_t)kIn; s_rows[wib][1][lane + 32 * r] = (uint16_t)kIn; }
     __syncwarp();
@@ -170,16 +168,24 @@ __global__ void __launch_bounds__(kL0Warps * 32) l0_pair_kernel(BatchRef batch, 
         }
     }
     __syncwarp();
+    tc::pdl_wait();                 // the previous update's SGD step (W0T) and its readers of cb / the statistics slots are complete
+    tc::pdl_launch_dependents();
+    if (blockIdx.x == 0) for (int i = threadIdx.x; i < n_zero; i += blockDim.x) zero_me[i] = 0.0f;
+    if (s >= n) return;
+    if (lane < 12) cb[lane * ld + s] = word;                   // word-major: the readers walk consecutive samples
+    else if (lane >= 24 && lane < 26) cb[(lane - 12) * ld + s] = word;
     const int steps = max(cnt[0], cnt[1]);                      // <= 90; the lists are padded to a multiple of 4 with the zero row
     float4 a = reinterpret_cast<const float4*>(b0)[lane], b = reinterpret_cast<const float4*>(b02)[lane];
     const float4* Wa = reinterpret_cast<const float4*>(W0T) + lane;
     const float4* Wb = reinterpret_cast<const float4*>(W0T2) + lane;
     for (int k = 0; k < steps; k += 4) {
         float4 ra[4], rb[4];
+        const uint2 la = *reinterpret_cast<const uint2*>(&s_rows[wib][0][k]), lb = *reinterpret_cast<const uint2*>(&s_rows[wib][1][k]);     // 4 rows each
+        const uint32_t ia[4] = {la.x & 0xFFFFu, la.x >> 16, la.y & 0xFFFFu, la.y >> 16}, ib[4] = {lb.x & 0xFFFFu, lb.x >> 16, lb.y & 0xFFFFu, lb.y >> 16};
 #pragma unroll
         for (int u = 0; u < 4; ++u) {
-            ra[u] = Wa[(size_t)s_rows[wib][0][k + u] * (kHid / 4)];
-            rb[u] = Wb[(size_t)s_rows[wib][1][k + u] * (kHid / 4)];
+            ra[u] = Wa[(size_t)ia[u] * (kHid / 4)];
+            rb[u] = Wb[(size_t)ib[u] * (kHid / 4)];
         }
 #pragma unroll
         for (int u = 0; u < 4; ++u) {
@@ -242,6 +248,7 @@ __global__ void __launch_bounds__(kGemmThreads, 1) l1_gemm_kernel(const __grid_c
         tc::prefetch_tmap(&tmH); tc::prefetch_tmap(&tmW1);
         tc::mbar_expect_tx(b_full, kBBytes);
         for (int kb = 0; kb < kKBlocks; ++kb) tc::tma_load_2d(sB + kb * (BN * BK * 2), &tmW1, kb * BK, n0, b_full);
+        tc::pdl_wait();             // W1 / b1 were final before the producer of H started; H itself is the predecessor's output
         for (int i = 0; i < kAStages && i < my_tiles; ++i) {
             tc::mbar_expect_tx(a_full + i, kABytes);
             const int row0 = (split + i * n_splits) * BM;
@@ -285,6 +292,8 @@ __global__ void __launch_bounds__(kGemmThreads, 1) l1_gemm_kernel(const __grid_c
     tc::tc_fence_before();
     __syncthreads();
     tc::tc_fence_after();
+    tc::pdl_wait();
+    tc::pdl_launch_dependents();
     const uint32_t tmem_base = *tmem_slot;
     if (threadIdx.x == 0) XQ_TL(0, 1);
 
@@ -356,7 +365,7 @@ __global__ void __launch_bounds__(kGemmThreads, 1) l1_gemm_kernel(const __grid_c
                     best[0] = fmaxf(best[0], __uint_as_float(r[j])); best[1] = fmaxf(best[1], __uint_as_float(r[j + 1]));
                     best[2] = fmaxf(best[2], __uint_as_float(r[j + 2])); best[3] = fmaxf(best[3], __uint_as_float(r[j + 3]));
                 }
-                if (row < M) zpart[(int64_t)(n_tile * 2 + half) * zstride + row] = fmaxf(fmaxf(best[0], best[1]), fmaxf(best[2], best[3]));
+                if (row < M) zpart[(int64_t)row * kPartsPad + n_tile * 2 + half] = fmaxf(fmaxf(best[0], best[1]), fmaxf(best[2], best[3]));
             } else {
 #pragma unroll 1
                 for (int c = 0; c < kHalfCols / 16; ++c) {
@@ -412,6 +421,8 @@ __global__ void __launch_bounds__(256) td_delta_kernel(uint32_t* __restrict__ cb
     __shared__ __align__(16) float s_g[8][kHid];           // delta1 * h (the dW1 contraction's B operand)
     const int64_t s = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
+    tc::pdl_wait();
+    tc::pdl_launch_dependents();
     float loss = 0.0f, qv = 0.0f, tv = 0.0f;
     reinterpret_cast<float4*>(s_d0[wib])[lane] = make_float4(0.f, 0.f, 0.f, 0.f);
     reinterpret_cast<float4*>(s_g[wib])[lane] = make_float4(0.f, 0.f, 0.f, 0.f);
@@ -424,7 +435,7 @@ __global__ void __launch_bounds__(256) td_delta_kernel(uint32_t* __restrict__ cb
         const float4 w = reinterpret_cast<const float4*>(W1 + (size_t)to * kHid)[lane];
         float z = h.x * w.x + h.y * w.y + h.z * w.z + h.w * w.w;
         float zmax = -INFINITY;
-        if (!done) for (int i = lane; i < n_parts; i += 32) zmax = fmaxf(zmax, zpart[(int64_t)i * zstride + s]);
+        if (!done) for (int i = lane; i < n_parts; i += 32) zmax = fmaxf(zmax, zpart[s * kPartsPad + i]);
 #pragma unroll
         for (int k = 16; k > 0; k >>= 1) { z += __shfl_xor_sync(0xFFFFFFFFu, z, k); zmax = fmaxf(zmax, __shfl_xor_sync(0xFFFFFFFFu, zmax, k)); }
         const float q = tanhf(z + b1[to]);
@@ -544,6 +555,7 @@ __global__ void __launch_bounds__(kDwThreads, 1) dw_gemm_kernel(const __grid_con
         tc::mbar_init(acc_full, 1);
         tc::fence_barrier_init();
         tc::prefetch_tmap(&tmCb); tc::prefetch_tmap(&tmHi); tc::prefetch_tmap(&tmLo);
+        tc::pdl_wait();             // delta0 / delta1 h / the compact batch are the predecessor's outputs
         for (int i = 0; i < kDwStages && i < my_kb; ++i) issue_stage(i);      // the first stages need no `empty` wait: start them before the CTA barrier
     }
     if (warp == 2) tc::tmem_alloc<256>(tmem_slot);
@@ -577,6 +589,8 @@ __global__ void __launch_bounds__(kDwThreads, 1) dw_gemm_kernel(const __grid_con
     tc::tc_fence_before();
     __syncthreads();
     tc::tc_fence_after();
+    tc::pdl_wait();
+    tc::pdl_launch_dependents();
     const uint32_t tmem_base = *tmem_slot;
     if (threadIdx.x == 0) XQ_TL(1, 1);
 
@@ -814,6 +828,20 @@ static int make_tmap_cb(CUtensorMap* m, const void* base, int64_t n, int64_t ld)
     return XQ_OK;
 }
 
+// launch with programmatic stream serialization (PDL), optionally as thread-block clusters along y
+template <typename... KArgs, typename... Args>
+static cudaError_t launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t stream, int cluster_y, Args&&... args) {
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = grid; cfg.blockDim = block; cfg.dynamicSmemBytes = smem; cfg.stream = stream;
+    cudaLaunchAttribute at[2];
+    int na = 0;
+    at[na].id = cudaLaunchAttributeProgrammaticStreamSerialization; at[na].val.programmaticStreamSerializationAllowed = 1; ++na;
+    if (cluster_y > 1) { at[na].id = cudaLaunchAttributeClusterDimension; at[na].val.clusterDim.x = 1; at[na].val.clusterDim.y = cluster_y; at[na].val.clusterDim.z = 1; ++na; }
+    cfg.attrs = at; cfg.numAttrs = na;
+    ++g_launches;
+    return cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);
+}
+
 static inline unsigned blocks(int64_t n, int per) { return (unsigned)((n + per - 1) / per); }
 
 void dqn_fast_destroy(xq_dqn_s* h) {
@@ -865,7 +893,7 @@ static int fast_reserve(xq_dqn_s* h, int64_t n) {
     const int64_t rows = (n + BM - 1) / BM * BM;
     XQ_CUDA(cudaMalloc(&f->boards, sizeof(Transition) * n));
     XQ_CUDA(cudaMalloc(&f->Hbf, sizeof(__nv_bfloat16) * rows * kHid)); XQ_CUDA(cudaMalloc(&f->H2bf, sizeof(__nv_bfloat16) * rows * kHid));
-    XQ_CUDA(cudaMalloc(&f->Hf, sizeof(float) * rows * kHid)); XQ_CUDA(cudaMalloc(&f->zpart, sizeof(float) * kParts * rows));
+    XQ_CUDA(cudaMalloc(&f->Hf, sizeof(float) * rows * kHid)); XQ_CUDA(cudaMalloc(&f->zpart, sizeof(float) * kPartsPad * rows));
     XQ_CUDA(cudaMalloc(&f->cb, sizeof(uint32_t) * kCbRows * rows));
     XQ_CUDA(cudaMalloc(&f->d0hi, sizeof(__nv_bfloat16) * rows * kHid)); XQ_CUDA(cudaMalloc(&f->d0lo, sizeof(__nv_bfloat16) * rows * kHid));
     XQ_CUDA(cudaMalloc(&f->ghi, sizeof(__nv_bfloat16) * rows * kHid)); XQ_CUDA(cudaMalloc(&f->glo, sizeof(__nv_bfloat16) * rows * kHid));
@@ -929,10 +957,11 @@ static int launch_gemm(xq_dqn_s* h, int mode, const CUtensorMap& tmA, const CUte
     const dim3 grid(kNTiles, n_splits);
     const int64_t zstride = (f->cap + BM - 1) / BM * BM;
     if (mode == EPI_ROWMAX)
-        l1_gemm_kernel<EPI_ROWMAX><<<grid, kGemmThreads, kGemmSmem, h->stream>>>(tmA, tmB, b1, (int)n, m_tiles, n_splits, f->zpart, zstride, nullptr);
+        XQ_CUDA(launch_pdl(l1_gemm_kernel<EPI_ROWMAX>, grid, dim3(kGemmThreads), kGemmSmem, h->stream, 1, tmA, tmB, b1, (int)n, m_tiles, n_splits,
+                           f->zpart, zstride, (float*)nullptr));
     else
-        l1_gemm_kernel<EPI_STORE_TANH><<<grid, kGemmThreads, kGemmSmem, h->stream>>>(tmA, tmB, b1, (int)n, m_tiles, n_splits, nullptr, zstride, q);
-    XQ_LAUNCH_CHECK();
+        XQ_CUDA(launch_pdl(l1_gemm_kernel<EPI_STORE_TANH>, grid, dim3(kGemmThreads), kGemmSmem, h->stream, 1, tmA, tmB, b1, (int)n, m_tiles, n_splits,
+                           (float*)nullptr, zstride, q));
     return XQ_OK;
 }
 
@@ -973,28 +1002,22 @@ int td_update_core(xq_dqn_s* h, const BatchRef& ref, int64_t n, int use_target_n
     if (int rc = fast_maps(h, n)) return rc;
     if (lr <= 0) lr = h->lr;
     const int64_t ld = (f->cap + BM - 1) / BM * BM;
-    // h(s) with the online net; h(s') with the online (ChessAI::train) or target (DQN::train) net
-    l0_pair_kernel<<<blocks(n, kL0Warps), kL0Warps * 32, 0, h->stream>>>(ref, n, f->W0T, f->b0, use_target_net ? f->tW0T : f->W0T,
-                                                                        use_target_net ? f->tb0 : f->b0, f->Hf, f->H2bf, f->cb, ld,
-                                                                        f->info_slots, kInfoSlots * 4);      // also clears the loss-statistics slots
-    XQ_LAUNCH_CHECK();
+    // Four kernels chained with programmatic dependent launch: each one's set-up (barriers, TMEM, operand tiles that do not
+    // depend on its predecessor) overlaps the predecessor's tail.
+    // 1. h(s) with the online net; h(s') with the online (ChessAI::train) or target (DQN::train) net; compact batch
+    XQ_CUDA(launch_pdl(l0_pair_kernel, dim3(blocks(n, kL0Warps)), dim3(kL0Warps * 32), 0, h->stream, 1, ref, n, f->W0T, f->b0,
+                       use_target_net ? f->tW0T : f->W0T, use_target_net ? f->tb0 : f->b0, f->Hf, f->H2bf, f->cb, ld, f->info_slots,
+                       kInfoSlots * 4));
+    // 2. max_a z(s')[a] over all 8100 outputs
     if (int rc = launch_gemm(h, EPI_ROWMAX, f->tmH2, use_target_net ? f->tmTW1 : f->tmW1, use_target_net ? f->tb1 : f->b1, n, nullptr)) return rc;
-    td_delta_kernel<<<blocks(n * 32, 256), 256, 0, h->stream>>>(f->cb, n, f->Hf, f->W1, f->b1, f->zpart, ld, kParts, (float)h->gamma, h->mode,
-                                                                f->d0hi, f->d0lo, f->ghi, f->glo, ld, f->info_slots);
-    XQ_LAUNCH_CHECK();
-    {   // dW0 / db0 / dW1 contraction, cluster reduction and the SGD step (or the compact gradient) in one launch
-        cudaLaunchConfig_t cfg = {};
-        cfg.gridDim = dim3(kDwMTiles, kDwSplits); cfg.blockDim = dim3(kDwThreads); cfg.dynamicSmemBytes = kDwSmem; cfg.stream = h->stream;
-        cudaLaunchAttribute at[1];
-        at[0].id = cudaLaunchAttributeClusterDimension;
-        at[0].val.clusterDim.x = 1; at[0].val.clusterDim.y = kDwSplits; at[0].val.clusterDim.z = 1;
-        cfg.attrs = at; cfg.numAttrs = 1;
-        XQ_CUDA(cudaLaunchKernelEx(&cfg, dw_gemm_kernel, f->tmD0hi, f->tmD0lo, f->tmGhi, f->tmGlo, f->tmCb, (int)n, f->part, f->dbpart, f->info_slots, f->info, f->grad, f->W0T,
-                                   f->b0, f->W1, f->b1, f->W1bf, (float)lr, apply ? 1 : 0));
-        ++g_launches;
-    }
+    // 3. TD error, delta0, delta1 h
+    XQ_CUDA(launch_pdl(td_delta_kernel, dim3(blocks(n * 32, 256)), dim3(256), 0, h->stream, 1, f->cb, n, f->Hf, f->W1, f->b1, f->zpart, ld, kParts,
+                       (float)h->gamma, h->mode, f->d0hi, f->d0lo, f->ghi, f->glo, ld, f->info_slots));
+    // 4. dW0 / db0 / dW1 / db1 contraction, cluster reduction and the SGD step (or the compact gradient)
+    XQ_CUDA(launch_pdl(dw_gemm_kernel, dim3(kDwMTiles, kDwSplits), dim3(kDwThreads), kDwSmem, h->stream, kDwSplits, f->tmD0hi, f->tmD0lo, f->tmGhi,
+                       f->tmGlo, f->tmCb, (int)n, f->part, f->dbpart, f->info_slots, f->info, f->grad, f->W0T, f->b0, f->W1, f->b1, f->W1bf,
+                       (float)lr, apply ? 1 : 0));
     if (apply) h->f64_current = false;
-    XQ_LAUNCH_CHECK();
     return XQ_OK;
 }
 
