@@ -79,6 +79,11 @@ struct Fast {
     int64_t q_cap = 0;
     float* info = nullptr;                             // 4 floats
     CUtensorMap tmW1, tmTW1, tmH, tmH2, tmD0hi, tmD0lo, tmGhi, tmGlo, tmCb;
+    // acting (Q(s)[0..89] for every env of a self-play shard): split-precision operands, see q90_gemm_kernel
+    __nv_bfloat16* W1lo = nullptr;                     // [96][128] BF16 residual of W1 rows 0..95 (W1 = W1bf + W1lo to ~16 mantissa bits)
+    __nv_bfloat16 *actHhi = nullptr, *actHlo = nullptr;   // [act_cap][128] h(s) as BF16 hi + lo
+    int64_t act_cap = 0, act_rows = 0;
+    CUtensorMap tmActHi, tmActLo, tmW1q, tmW1loq;
     int64_t tm_rows = 0;
 };
 
@@ -131,6 +136,48 @@ __global__ void __launch_bounds__(256) l0_forward_kernel(const uint8_t* __restri
     if (Hf) reinterpret_cast<float4*>(Hf + s * kHid)[lane] = h;
     store_h_bf16(Hbf, s, lane, h);
 }
+// Acting: h(s) for every env of a shard, one warp per board (ballot-compacted row list, 8 rows in flight), written as
+// BF16 hi + lo (h = hi + lo to ~16 mantissa bits) for the split-precision layer-1 contraction of q90_gemm_kernel.
+__global__ void __launch_bounds__(256) l0_act_kernel(const xq_env_rec* __restrict__ envs, int64_t n, const float* __restrict__ W0T,
+                                                    const float* __restrict__ b0, __nv_bfloat16* __restrict__ Hhi, __nv_bfloat16* __restrict__ Hlo) {
+    __shared__ __align__(16) uint16_t s_rows[8][96];
+    const int wib = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int64_t e = (int64_t)blockIdx.x * 8 + wib;
+    if (e >= n) return;
+    const uint32_t word = lane < 12 ? envs[e].sq[lane] : 0u;
+#pragma unroll
+    for (int r = 0; r < 3; ++r) s_rows[wib][lane + 32 * r] = (uint16_t)kIn;
+    __syncwarp();
+    int cnt = 0;
+#pragma unroll
+    for (int r = 0; r < 3; ++r) {
+        const int q = lane + 32 * r;
+        const uint32_t w = __shfl_sync(0xFFFFFFFFu, word, (q >> 3) % 12);
+        const int code = (w >> (4 * (q & 7))) & 15;
+        const bool piece = q < XQ_SQUARES && code >= 1 && code <= 14;
+        const unsigned m = __ballot_sync(0xFFFFFFFFu, piece);
+        if (piece) s_rows[wib][cnt + __popc(m & ((1u << lane) - 1u))] = (uint16_t)(q * 14 + code - 1);      // src/chessai.cpp:278-282
+        cnt += __popc(m);
+    }
+    __syncwarp();
+    float4 a = reinterpret_cast<const float4*>(b0)[lane];
+    const float4* W = reinterpret_cast<const float4*>(W0T) + lane;
+    for (int k = 0; k < cnt; k += 8) {                          // the list is padded with the zero row kIn
+        const uint4 l = *reinterpret_cast<const uint4*>(&s_rows[wib][k]);
+        const uint32_t idx[8] = {l.x & 0xFFFFu, l.x >> 16, l.y & 0xFFFFu, l.y >> 16, l.z & 0xFFFFu, l.z >> 16, l.w & 0xFFFFu, l.w >> 16};
+        float4 r[8];
+#pragma unroll
+        for (int u = 0; u < 8; ++u) r[u] = W[(size_t)idx[u] * (kHid / 4)];
+#pragma unroll
+        for (int u = 0; u < 8; ++u) { a.x += r[u].x; a.y += r[u].y; a.z += r[u].z; a.w += r[u].w; }
+    }
+    const float4 h = make_float4(tanhf(a.x), tanhf(a.y), tanhf(a.z), tanhf(a.w));
+    store_h_bf16(Hhi, e, lane, h);
+    const __nv_bfloat162 h01 = __floats2bfloat162_rn(h.x, h.y), h23 = __floats2bfloat162_rn(h.z, h.w);
+    store_h_bf16(Hlo, e, lane, make_float4(h.x - __bfloat162float(h01.x), h.y - __bfloat162float(h01.y), h.z - __bfloat162float(h23.x),
+                                           h.w - __bfloat162float(h23.y)));
+}
+
 // Both states of every transition in one launch, ONE WARP PER TRANSITION: the 128-byte replay record is read once
 // (one coalesced line); lane l decodes squares l, l+32, l+64 of both boards, ballots compact the occupied squares into
 // two row lists in shared memory (padded with the all-zero row kIn), and the two gather-sums -- h(s) with the online
@@ -395,6 +442,140 @@ __global__ void __launch_bounds__(kGemmThreads, 1) l1_gemm_kernel(const __grid_c
 }
 
 // ---------------------------------------------------------------------------------------------
+// Acting: Q(s)[0..95] = tanh(W1[0..95] h + b1) for every env -- DQN::selectAction indexes Q by action.to < 90 only
+// (src/dqn.cpp:47), so 96 of the 8100 outputs are enough.  The reference's argmax is over FP64 Q-values; to keep
+// near-ties where they are, the contraction runs in SPLIT precision on the tensor cores: h = h_hi + h_lo and
+// W = W_hi + W_lo in BF16, z = h_hi W_hi + h_lo W_hi + h_hi W_lo (FP32 accumulate; the dropped lo*lo term is
+// < 2^-17 relative) -- 24 UMMA (M128 x N96 x K16) per 128-env tile.  Persistent CTAs stride over the tiles;
+// 8 epilogue warps add the FP32 bias, apply tanhf and write FP32 rows [env][96] through a small per-warp
+// shared-memory transpose so that every store instruction covers contiguous 96-byte row pieces.
+constexpr int QN = 96;
+constexpr int kQStages = 2;
+constexpr uint32_t kQBBytes = QN * kHid * 2;             // 24 KB per precision part of W1[0..95]
+constexpr uint32_t kQABytes = BM * kHid * 2;             // 32 KB per precision part of an A tile
+constexpr uint32_t kQXposeBytes = 8 * 32 * 24 * 4;       // 24 KB: per epilogue warp 32 rows x 24 columns FP32
+constexpr size_t kQSmem = 1024 + 2 * kQBBytes + kQStages * 2 * kQABytes + kQXposeBytes + QN * 4 + 256;
+
+__global__ void __launch_bounds__(kGemmThreads, 1) q90_gemm_kernel(const __grid_constant__ CUtensorMap tmHhi, const __grid_constant__ CUtensorMap tmHlo,
+                                                                  const __grid_constant__ CUtensorMap tmWhi, const __grid_constant__ CUtensorMap tmWlo,
+                                                                  const float* __restrict__ b1, int M, int m_tiles, float* __restrict__ q90) {
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+    uint8_t* sB = smem;                                    // [hi | lo][2 k-blocks][96][64] bf16
+    uint8_t* sA = sB + 2 * kQBBytes;                       // [stage][hi | lo][2 k-blocks][128][64] bf16
+    float* sX = reinterpret_cast<float*>(sA + kQStages * 2 * kQABytes);     // [8 warps][32][24]
+    float* sBias = sX + kQXposeBytes / 4;
+    uint64_t* bars = reinterpret_cast<uint64_t*>(sBias + QN);
+    uint64_t* b_full = bars;              // 1
+    uint64_t* a_full = bars + 1;          // kQStages
+    uint64_t* a_empty = bars + 3;         // kQStages
+    uint64_t* acc_full = bars + 5;        // 2
+    uint64_t* acc_empty = bars + 7;       // 2
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 9);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int my_tiles = (m_tiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;     // tiles blockIdx.x, + gridDim.x, ...
+    auto load_a = [&](int i) {
+        const int st = i % kQStages, row0 = ((int)blockIdx.x + i * (int)gridDim.x) * BM;
+        tc::mbar_expect_tx(a_full + st, 2 * kQABytes);
+        for (int kb = 0; kb < kKBlocks; ++kb) {
+            tc::tma_load_2d(sA + st * 2 * kQABytes + kb * (BM * BK * 2), &tmHhi, kb * BK, row0, a_full + st);
+            tc::tma_load_2d(sA + st * 2 * kQABytes + kQABytes + kb * (BM * BK * 2), &tmHlo, kb * BK, row0, a_full + st);
+        }
+    };
+    if (threadIdx.x == 0) {
+        tc::mbar_init(b_full, 1);
+        for (int i = 0; i < kQStages; ++i) { tc::mbar_init(a_full + i, 1); tc::mbar_init(a_empty + i, 1); }
+        for (int i = 0; i < 2; ++i) { tc::mbar_init(acc_full + i, 1); tc::mbar_init(acc_empty + i, kEpiWarps); }
+        tc::fence_barrier_init();
+        tc::prefetch_tmap(&tmHhi); tc::prefetch_tmap(&tmHlo); tc::prefetch_tmap(&tmWhi); tc::prefetch_tmap(&tmWlo);
+        tc::mbar_expect_tx(b_full, 2 * kQBBytes);
+        for (int kb = 0; kb < kKBlocks; ++kb) {
+            tc::tma_load_2d(sB + kb * (QN * BK * 2), &tmWhi, kb * BK, 0, b_full);
+            tc::tma_load_2d(sB + kQBBytes + kb * (QN * BK * 2), &tmWlo, kb * BK, 0, b_full);
+        }
+        tc::pdl_wait();             // h(s) is the predecessor's output
+        for (int i = 0; i < kQStages && i < my_tiles; ++i) load_a(i);
+    }
+    if (warp == 2) tc::tmem_alloc<256>(tmem_slot);
+    if (warp == 3) for (int i = lane; i < QN; i += 32) sBias[i] = b1[i];
+    tc::tc_fence_before();
+    __syncthreads();
+    tc::tc_fence_after();
+    tc::pdl_wait();
+    const uint32_t tmem_base = *tmem_slot;
+
+    if (warp == 0) {
+        if (lane == 0)     // ===== TMA producer =====
+            for (int i = kQStages; i < my_tiles; ++i) { tc::mbar_wait(a_empty + i % kQStages, ((i / kQStages) & 1) ^ 1); load_a(i); }
+        __syncwarp();
+    } else if (warp == 1) {
+        if (lane == 0) {   // ===== MMA issuer: (h_hi, W_hi) + (h_lo, W_hi) + (h_hi, W_lo) =====
+            constexpr uint32_t idesc = tc::umma_idesc_bf16(BM, QN);
+            tc::mbar_wait(b_full, 0);
+            for (int i = 0; i < my_tiles; ++i) {
+                const int st = i % kQStages, acc = i & 1;
+                tc::mbar_wait(acc_empty + acc, ((i >> 1) & 1) ^ 1);
+                tc::mbar_wait(a_full + st, (i / kQStages) & 1);
+                tc::tc_fence_after();
+#pragma unroll
+                for (int part = 0; part < 3; ++part) {
+                    const uint8_t* a = sA + st * 2 * kQABytes + (part == 1 ? kQABytes : 0);
+                    const uint8_t* b = sB + (part == 2 ? kQBBytes : 0);
+#pragma unroll
+                    for (int kb = 0; kb < kKBlocks; ++kb)
+#pragma unroll
+                        for (int k = 0; k < BK / 16; ++k)
+                            tc::umma_bf16(tmem_base + acc * QN, tc::umma_desc_sw128(tc::smem_u32(a + kb * (BM * BK * 2)) + k * 32),
+                                          tc::umma_desc_sw128(tc::smem_u32(b + kb * (QN * BK * 2)) + k * 32), idesc, (part | kb | k) != 0);
+                }
+                tc::umma_commit(a_empty + st);
+                tc::umma_commit(acc_full + acc);
+            }
+        }
+        __syncwarp();
+    } else if (warp >= 4) {   // ===== epilogue: warps w and w+4 share TMEM lanes 32*(w&3).. +31, 48 columns each =====
+        const int quarter = warp & 3, half = (warp - 4) >> 2;
+        float* xw = sX + (warp - 4) * (32 * 24);
+        for (int i = 0; i < my_tiles; ++i) {
+            const int acc = i & 1;
+            const int row0 = ((int)blockIdx.x + i * (int)gridDim.x) * BM + quarter * 32;
+            tc::mbar_wait(acc_full + acc, (i >> 1) & 1);
+            tc::tc_fence_after();
+            uint32_t r[48];
+            const uint32_t t0 = tmem_base + ((uint32_t)(quarter * 32) << 16) + acc * QN + half * 48;
+            tc::tmem_ld32_nowait(t0, r); tc::tmem_ld16_nowait(t0 + 32, r + 32);
+            tc::tmem_wait_ld();
+            tc::tc_fence_before();
+            __syncwarp();
+            if (lane == 0) tc::mbar_arrive(acc_empty + acc);
+#pragma unroll
+            for (int c0 = 0; c0 < 48; c0 += 24) {             // two rounds of 24 columns through the warp's transpose buffer
+#pragma unroll
+                for (int j = 0; j < 24; j += 4) {
+                    const float4 b4 = *reinterpret_cast<const float4*>(sBias + half * 48 + c0 + j);
+                    *reinterpret_cast<float4*>(xw + lane * 24 + j) = make_float4(tanhf(__uint_as_float(r[c0 + j]) + b4.x), tanhf(__uint_as_float(r[c0 + j + 1]) + b4.y),
+                                                                                 tanhf(__uint_as_float(r[c0 + j + 2]) + b4.z), tanhf(__uint_as_float(r[c0 + j + 3]) + b4.w));
+                }
+                __syncwarp();
+                // lane = (row within a group of 5 rows, 16-byte chunk): 30 lanes move 5 rows x 96 bytes per step
+                const int rr = lane / 6, ch = lane % 6;
+                if (lane < 30)
+                    for (int rb = 0; rb < 32; rb += 5) {
+                        const int row = rb + rr;
+                        if (row < 32 && row0 + row < M)
+                            *reinterpret_cast<float4*>(q90 + (size_t)(row0 + row) * QN + half * 48 + c0 + ch * 4) = *reinterpret_cast<const float4*>(xw + row * 24 + ch * 4);
+                    }
+                __syncwarp();
+            }
+        }
+    }
+    tc::tc_fence_before();
+    __syncthreads();
+    if (warp == 2) { tc::tc_fence_after(); tc::tmem_dealloc<256>(tmem_base); }
+}
+
+// ---------------------------------------------------------------------------------------------
 // Transition record of the replay buffer / TD batch (include/xq.h: xq_transition, 128 B)
 struct Transition {
     uint32_t s[12], s2[12];
@@ -518,7 +699,8 @@ __global__ void __launch_bounds__(kDwThreads, 1) dw_gemm_kernel(const __grid_con
                                                                float* __restrict__ dbpart, float* __restrict__ info_slots, float* __restrict__ info,
                                                                float* __restrict__ grad,
                                                                float* __restrict__ W0T, float* __restrict__ b0, float* __restrict__ W1,
-                                                               float* __restrict__ b1, __nv_bfloat16* __restrict__ W1bf, float lr, int apply) {
+                                                               float* __restrict__ b1, __nv_bfloat16* __restrict__ W1bf,
+                                                               __nv_bfloat16* __restrict__ W1lo, float lr, int apply) {
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
     uint8_t* sA = smem;                                        // [stage][128 features][64 samples]
@@ -736,6 +918,10 @@ __global__ void __launch_bounds__(kDwThreads, 1) dw_gemm_kernel(const __grid_con
             __nv_bfloat162 p0 = __floats2bfloat162_rn(w.x, w.y), p1 = __floats2bfloat162_rn(w.z, w.w);
             uint2 pk; pk.x = *reinterpret_cast<uint32_t*>(&p0); pk.y = *reinterpret_cast<uint32_t*>(&p1);
             *reinterpret_cast<uint2*>(W1bf + (e[u] - kGradW1)) = pk;
+            __nv_bfloat162 q0 = __floats2bfloat162_rn(w.x - __bfloat162float(p0.x), w.y - __bfloat162float(p0.y));
+            __nv_bfloat162 q1 = __floats2bfloat162_rn(w.z - __bfloat162float(p1.x), w.w - __bfloat162float(p1.y));
+            pk.x = *reinterpret_cast<uint32_t*>(&q0); pk.y = *reinterpret_cast<uint32_t*>(&q1);
+            *reinterpret_cast<uint2*>(W1lo + (e[u] - kGradW1)) = pk;       // rows 0..89 < 96: the acting path's residual operand
         }
     }
     if (w1_tile && ks == 0) {
@@ -756,7 +942,7 @@ __global__ void __launch_bounds__(kDwThreads, 1) dw_gemm_kernel(const __grid_con
 
 // SGD: W -= lr * grad on the compact gradient (src/dqn.cu:310-319), refresh the BF16 operand rows, clear the gradient
 __global__ void __launch_bounds__(256) apply_kernel(float* __restrict__ W0T, float* __restrict__ b0, float* __restrict__ W1, float* __restrict__ b1,
-                                                   __nv_bfloat16* __restrict__ W1bf, float* __restrict__ grad, float lr) {
+                                                   __nv_bfloat16* __restrict__ W1bf, __nv_bfloat16* __restrict__ W1lo, float* __restrict__ grad, float lr) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= kGradSize) return;
     const float g = grad[i];
@@ -764,16 +950,25 @@ __global__ void __launch_bounds__(256) apply_kernel(float* __restrict__ W0T, flo
     if (g == 0.0f) return;
     if (i < kGradB0) W0T[i] -= lr * g;
     else if (i < kGradW1) b0[i - kGradB0] -= lr * g;
-    else if (i < kGradB1) { const int e = i - kGradW1; const float v = W1[e] - lr * g; W1[e] = v; W1bf[e] = __float2bfloat16_rn(v); }
+    else if (i < kGradB1) {
+        const int e = i - kGradW1; const float v = W1[e] - lr * g; W1[e] = v;
+        const __nv_bfloat16 hi = __float2bfloat16_rn(v);
+        W1bf[e] = hi; W1lo[e] = __float2bfloat16_rn(v - __bfloat162float(hi));
+    }
     else b1[i - kGradB1] -= lr * g;
 }
 
 // ---- FP64 (reference layout) <-> fast-path layouts ----------------------------------------------
 __global__ void f64_to_fast_kernel(const double* __restrict__ w, const double* __restrict__ b, float* __restrict__ W0T, float* __restrict__ b0,
-                                   float* __restrict__ W1, float* __restrict__ b1, __nv_bfloat16* __restrict__ W1bf) {
+                                   float* __restrict__ W1, float* __restrict__ b1, __nv_bfloat16* __restrict__ W1bf, __nv_bfloat16* __restrict__ W1lo) {
     const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i < (int64_t)kIn * kHid) { const int o = (int)(i / kIn), in = (int)(i % kIn); W0T[(size_t)in * kHid + o] = (float)w[i]; }   // W0[o][in] -> W0T[in][o]
-    if (i < (int64_t)kOut * kHid) { const float v = (float)w[(size_t)kIn * kHid + i]; W1[i] = v; W1bf[i] = __float2bfloat16_rn(v); }
+    if (i < (int64_t)kOut * kHid) {
+        const float v = (float)w[(size_t)kIn * kHid + i]; W1[i] = v;
+        const __nv_bfloat16 hi = __float2bfloat16_rn(v);
+        W1bf[i] = hi;
+        if (W1lo && i < (int64_t)QN * kHid) W1lo[i] = __float2bfloat16_rn(v - __bfloat162float(hi));
+    }
     if (i < kHid) b0[i] = (float)b[i];
     if (i < kOut) b1[i] = (float)b[kHid + i];
 }
@@ -847,7 +1042,7 @@ static inline unsigned blocks(int64_t n, int per) { return (unsigned)((n + per -
 void dqn_fast_destroy(xq_dqn_s* h) {
     Fast* f = h->fast;
     if (!f) return;
-    cudaFree(f->W0T); cudaFree(f->b0); cudaFree(f->W1); cudaFree(f->b1); cudaFree(f->W1bf);
+    cudaFree(f->W0T); cudaFree(f->b0); cudaFree(f->W1); cudaFree(f->b1); cudaFree(f->W1bf); cudaFree(f->W1lo); cudaFree(f->actHhi); cudaFree(f->actHlo);
     cudaFree(f->tW0T); cudaFree(f->tb0); cudaFree(f->tW1); cudaFree(f->tb1); cudaFree(f->tW1bf);
     cudaFree(f->grad); cudaFree(f->boards); cudaFree(f->Hbf); cudaFree(f->H2bf); cudaFree(f->Hf); cudaFree(f->zpart);
     cudaFree(f->cb); cudaFree(f->d0hi); cudaFree(f->d0lo); cudaFree(f->ghi); cudaFree(f->glo); cudaFree(f->q); cudaFree(f->part); cudaFree(f->dbpart); cudaFree(f->info_slots);
@@ -865,6 +1060,7 @@ static int fast_init(xq_dqn_s* h) {
     XQ_CUDA(cudaMalloc(&f->W0T, sizeof(float) * (kIn + 1) * kHid)); XQ_CUDA(cudaMalloc(&f->b0, sizeof(float) * kHid));
     XQ_CUDA(cudaMalloc(&f->W1, sizeof(float) * kOut * kHid)); XQ_CUDA(cudaMalloc(&f->b1, sizeof(float) * kOut));
     XQ_CUDA(cudaMalloc(&f->W1bf, sizeof(__nv_bfloat16) * kOut * kHid));
+    XQ_CUDA(cudaMalloc(&f->W1lo, sizeof(__nv_bfloat16) * QN * kHid));
     XQ_CUDA(cudaMalloc(&f->tW0T, sizeof(float) * (kIn + 1) * kHid)); XQ_CUDA(cudaMalloc(&f->tb0, sizeof(float) * kHid));
     XQ_CUDA(cudaMalloc(&f->tW1, sizeof(float) * kOut * kHid)); XQ_CUDA(cudaMalloc(&f->tb1, sizeof(float) * kOut));
     XQ_CUDA(cudaMalloc(&f->tW1bf, sizeof(__nv_bfloat16) * kOut * kHid));
@@ -875,6 +1071,9 @@ static int fast_init(xq_dqn_s* h) {
     XQ_CUDA(cudaMemsetAsync(f->tW0T + (size_t)kIn * kHid, 0, sizeof(float) * kHid, h->stream));
     if (int rc = make_tmap(&f->tmW1, f->W1bf, kOut, BN)) return rc;
     if (int rc = make_tmap(&f->tmTW1, f->tW1bf, kOut, BN)) return rc;
+    if (int rc = make_tmap(&f->tmW1q, f->W1bf, QN, QN)) return rc;
+    if (int rc = make_tmap(&f->tmW1loq, f->W1lo, QN, QN)) return rc;
+    XQ_CUDA(cudaFuncSetAttribute(q90_gemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kQSmem));
     XQ_CUDA(cudaFuncSetAttribute(l1_gemm_kernel<EPI_ROWMAX>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kGemmSmem));
     XQ_CUDA(cudaFuncSetAttribute(l1_gemm_kernel<EPI_STORE_TANH>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kGemmSmem));
     XQ_CUDA(cudaFuncSetAttribute(dw_gemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kDwSmem));
@@ -922,12 +1121,12 @@ static int ensure_fast(xq_dqn_s* h) {
     if (int rc = fast_init(h)) return rc;
     Fast* f = h->fast;
     if (!h->fast_current) {
-        f64_to_fast_kernel<<<blocks((int64_t)kOut * kHid, 256), 256, 0, h->stream>>>(h->d_w, h->d_b, f->W0T, f->b0, f->W1, f->b1, f->W1bf);
+        f64_to_fast_kernel<<<blocks((int64_t)kOut * kHid, 256), 256, 0, h->stream>>>(h->d_w, h->d_b, f->W0T, f->b0, f->W1, f->b1, f->W1bf, f->W1lo);
         XQ_LAUNCH_CHECK();
         h->fast_current = true;
     }
     if (!f->target_current) {
-        f64_to_fast_kernel<<<blocks((int64_t)kOut * kHid, 256), 256, 0, h->stream>>>(h->d_tw, h->d_tb, f->tW0T, f->tb0, f->tW1, f->tb1, f->tW1bf);
+        f64_to_fast_kernel<<<blocks((int64_t)kOut * kHid, 256), 256, 0, h->stream>>>(h->d_tw, h->d_tb, f->tW0T, f->tb0, f->tW1, f->tb1, f->tW1bf, (__nv_bfloat16*)nullptr);
         XQ_LAUNCH_CHECK();
         f->target_current = true;
     }
@@ -962,6 +1161,30 @@ static int launch_gemm(xq_dqn_s* h, int mode, const CUtensorMap& tmA, const CUte
     else
         XQ_CUDA(launch_pdl(l1_gemm_kernel<EPI_STORE_TANH>, grid, dim3(kGemmThreads), kGemmSmem, h->stream, 1, tmA, tmB, b1, (int)n, m_tiles, n_splits,
                            (float*)nullptr, zstride, q));
+    return XQ_OK;
+}
+
+// Q(s)[0..95] (row-major [n][96] FP32, device) for n env records resident on the device, on `stream`:
+// layer-0 gather (FP32) + split-precision tensor-core contraction with W1 rows 0..95
+int dqn_q90_device(xq_dqn_s* h, const xq_env_rec* envs_dev, int64_t n, float* q90_dev, cudaStream_t stream) {
+    if (int rc = ensure_fast(h)) return rc;
+    Fast* f = h->fast;
+    if (n > f->act_cap) {
+        cudaFree(f->actHhi); cudaFree(f->actHlo); f->actHhi = f->actHlo = nullptr; f->act_cap = 0; f->act_rows = 0;
+        const int64_t rows = (n + BM - 1) / BM * BM;
+        XQ_CUDA(cudaMalloc(&f->actHhi, sizeof(__nv_bfloat16) * rows * kHid)); XQ_CUDA(cudaMalloc(&f->actHlo, sizeof(__nv_bfloat16) * rows * kHid));
+        f->act_cap = n;
+    }
+    if (n != f->act_rows) {
+        if (int rc = make_tmap(&f->tmActHi, f->actHhi, n, BM)) return rc;
+        if (int rc = make_tmap(&f->tmActLo, f->actHlo, n, BM)) return rc;
+        f->act_rows = n;
+    }
+    l0_act_kernel<<<blocks(n, 8), 256, 0, stream>>>(envs_dev, n, f->W0T, f->b0, f->actHhi, f->actHlo);
+    XQ_LAUNCH_CHECK();
+    const int m_tiles = (int)((n + BM - 1) / BM);
+    XQ_CUDA(launch_pdl(q90_gemm_kernel, dim3(m_tiles < 148 ? m_tiles : 148), dim3(kGemmThreads), kQSmem, stream, 1, f->tmActHi, f->tmActLo, f->tmW1q,
+                       f->tmW1loq, (const float*)f->b1, (int)n, m_tiles, q90_dev));
     return XQ_OK;
 }
 
@@ -1016,7 +1239,7 @@ int td_update_core(xq_dqn_s* h, const BatchRef& ref, int64_t n, int use_target_n
     // 4. dW0 / db0 / dW1 / db1 contraction, cluster reduction and the SGD step (or the compact gradient)
     XQ_CUDA(launch_pdl(dw_gemm_kernel, dim3(kDwMTiles, kDwSplits), dim3(kDwThreads), kDwSmem, h->stream, kDwSplits, f->tmD0hi, f->tmD0lo, f->tmGhi,
                        f->tmGlo, f->tmCb, (int)n, f->part, f->dbpart, f->info_slots, f->info, f->grad, f->W0T, f->b0, f->W1, f->b1, f->W1bf,
-                       (float)lr, apply ? 1 : 0));
+                       f->W1lo, (float)lr, apply ? 1 : 0));
     if (apply) h->f64_current = false;
     return XQ_OK;
 }
@@ -1064,7 +1287,7 @@ int xq_dqn_apply_grads(xq_dqn_t h, double lr) {
     if (int rc = ensure_fast(h)) return rc;
     Fast* f = h->fast;
     if (lr <= 0) lr = h->lr;
-    apply_kernel<<<blocks(kGradSize, 256), 256, 0, h->stream>>>(f->W0T, f->b0, f->W1, f->b1, f->W1bf, f->grad, (float)lr);
+    apply_kernel<<<blocks(kGradSize, 256), 256, 0, h->stream>>>(f->W0T, f->b0, f->W1, f->b1, f->W1bf, f->W1lo, f->grad, (float)lr);
     XQ_LAUNCH_CHECK();
     h->f64_current = false;
     return XQ_OK;

@@ -9,7 +9,8 @@
 // The reference then trains on that single transition at once; here it is appended to a replay ring in
 // HBM and consumed in batches by the tensor-core TD update (xq_dqn_fast.cu).
 // Q(s)[to] only needs outputs 0..89 of layer 1 (src/dqn.cpp:47 indexes by action.to), so acting costs a
-// <=32-row gather for layer 0 plus 90 dot products of length 128 per env, all in FP32.
+// <=32-row FP32 gather for layer 0 plus a [n x 128] x [128 x 96] split-precision tensor-core contraction
+// (dqn_q90_device in xq_dqn_fast.cu), then one thread per board picks the action.
 #include <algorithm>
 
 #include "xq_dqn_internal.cuh"
@@ -26,51 +27,6 @@ struct Transition {
     uint32_t pad[6];
 };
 static_assert(sizeof(Transition) == sizeof(xq_transition), "transition layout");
-
-// Q(s)[0..89] for every env: one warp per env.  Layer 0 = gather-sum of W0^T rows (lane owns 4 hidden units),
-// h staged in shared memory, then lane r computes outputs r, r+32, r+64 from the (L1-resident) first 90 rows of W1.
-__global__ void __launch_bounds__(256) q90_kernel(const xq_env_rec* __restrict__ envs, int64_t n, const float* __restrict__ W0T,
-                                                 const float* __restrict__ b0, const float* __restrict__ W1, const float* __restrict__ b1,
-                                                 float* __restrict__ q90) {
-    __shared__ float s_h[8][kHidden];
-    const int64_t e = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-    const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
-    if (e >= n) return;
-    const uint32_t word = lane < 12 ? envs[e].sq[lane] : 0u;
-    float4 acc = reinterpret_cast<const float4*>(b0)[lane];
-    for (int wi = 0; wi < 12; ++wi) {
-        uint32_t v = __shfl_sync(0xFFFFFFFFu, word, wi);
-        while (v) {
-            const int nib = (__ffs((int)v) - 1) >> 2;
-            const int code = (v >> (4 * nib)) & 15;
-            v &= ~(15u << (4 * nib));
-            const int row = (wi * 8 + nib) * 14 + code - 1;
-            if (code < 15 && row < kInputs) {
-                const float4 r = reinterpret_cast<const float4*>(W0T + (size_t)row * kHidden)[lane];
-                acc.x += r.x; acc.y += r.y; acc.z += r.z; acc.w += r.w;
-            }
-        }
-    }
-    reinterpret_cast<float4*>(s_h[wib])[lane] = make_float4(tanhf(acc.x), tanhf(acc.y), tanhf(acc.z), tanhf(acc.w));
-    __syncwarp();
-#pragma unroll
-    for (int k = 0; k < 3; ++k) {
-        const int r = lane + 32 * k;
-        float q = 0.0f;
-        if (r < kQ) {
-            const float4* w = reinterpret_cast<const float4*>(W1 + (size_t)r * kHidden);
-            float z = 0.0f;
-#pragma unroll 8
-            for (int j = 0; j < kHidden / 4; ++j) {
-                const float4 a = w[j];
-                const float4 h = reinterpret_cast<const float4*>(s_h[wib])[j];
-                z += a.x * h.x + a.y * h.y + a.z * h.z + a.w * h.w;
-            }
-            q = tanhf(z + b1[r]);
-        }
-        q90[e * kQPad + r] = q;
-    }
-}
 
 // Action selection (+ optional application) for every env: one thread per board, ordered list staged in shared memory.
 template <bool APPLY>
@@ -312,13 +268,11 @@ int xq_dqn_act(xq_dqn_t h, xq_env_t env, double eps, xq_action* actions_host, fl
     if (int rc = env_info(env, &ei)) return rc;
     if (ei.device != h->device) return fail(XQ_ERR_INVALID, "xq_dqn_act: env and network live on different devices");
     XQ_CUDA(cudaSetDevice(h->device));
-    FastWeights fw;
-    if (int rc = dqn_fast_weights(h, &fw)) return rc;
+    { FastWeights fw; if (int rc = dqn_fast_weights(h, &fw)) return rc; }      // refresh the FP32 / BF16 copies on h->stream before ordering after it
     SelfplayScratch* sc;
     if (int rc = reserve_scratch(h->device, ei.n, &sc)) return rc;
     if (int rc = order_after(ei.stream, h->stream, &g_ev[h->device & 63])) return rc;
-    q90_kernel<<<blocks(ei.n * 32, 256), 256, 0, ei.stream>>>(ei.d_envs, ei.n, fw.W0T, fw.b0, fw.W1, fw.b1, sc->q90);
-    XQ_LAUNCH_CHECK();
+    if (int rc = dqn_q90_device(h, ei.d_envs, ei.n, sc->q90, ei.stream)) return rc;
     act_kernel<false><<<blocks(ei.n, kThreads), kThreads, 0, ei.stream>>>(ei.d_envs, ei.n, ei.env_id0, ei.seed, sc->q90, xq_eps_threshold(eps), 0,
                                                                          sc->actions, nullptr, 1, 0, nullptr);
     XQ_LAUNCH_CHECK();
@@ -334,16 +288,14 @@ int xq_selfplay_collect(xq_dqn_t h, xq_env_t env, xq_replay_t r, int n_plies, do
     if (int rc = env_info(env, &ei)) return rc;
     if (ei.device != h->device || (r && r->device != h->device)) return fail(XQ_ERR_INVALID, "xq_selfplay_collect: handles live on different devices");
     XQ_CUDA(cudaSetDevice(h->device));
-    FastWeights fw;
-    if (int rc = dqn_fast_weights(h, &fw)) return rc;
+    { FastWeights fw; if (int rc = dqn_fast_weights(h, &fw)) return rc; }      // refresh the FP32 / BF16 copies on h->stream before ordering after it
     SelfplayScratch* sc;
     if (int rc = reserve_scratch(h->device, ei.n, &sc)) return rc;
     if (int rc = order_after(ei.stream, h->stream, &g_ev[h->device & 63])) return rc;    // see the latest weights
     xq_env_stats* d_stats = ei.d_stats;
     const uint32_t thr = xq_eps_threshold(eps);
     for (int p = 0; p < n_plies; ++p) {
-        q90_kernel<<<blocks(ei.n * 32, 256), 256, 0, ei.stream>>>(ei.d_envs, ei.n, fw.W0T, fw.b0, fw.W1, fw.b1, sc->q90);
-        XQ_LAUNCH_CHECK();
+        if (int rc = dqn_q90_device(h, ei.d_envs, ei.n, sc->q90, ei.stream)) return rc;
         act_kernel<true><<<blocks(ei.n, kThreads), kThreads, 0, ei.stream>>>(ei.d_envs, ei.n, ei.env_id0, ei.seed, sc->q90, thr, train_done, nullptr,
                                                                             r ? r->d_ring : nullptr, r ? r->capacity : 1,
                                                                             r ? r->total % r->capacity : 0, d_stats);

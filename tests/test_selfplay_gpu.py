@@ -72,12 +72,12 @@ def test_act_stepwise_vs_oracle(xq, O, oracle_lib):
             qi = np.zeros(8100); qi[:90] = q[i, :90]
             k = oracle_lib.xqo_select_action(qi, lists[i], int(counts[i]), int(coin[i]), int(idx[i]), eps)
             assert actions[i] == lists[i, k], (p, i)
-        if p == 0:   # Q used for acting vs the FP64 oracle (FP32 path: layer-0 gather + 90 dots)
+        if p == 0:   # Q used for acting vs the FP64 oracle: FP32 layer-0 gather + split-precision (BF16 hi+lo, 3 MMAs) layer 1
             st = np.zeros(1260); qq = np.zeros(8100)
             for i in range(0, n, 97):
                 oracle_lib.xqo_state(ref[i:i + 1].ctypes.data, st)
                 oracle_lib.xqo_nn_forward(LA, 3, w, b, st, qq)
-                assert np.abs(q[i, :90] - qq[:90]).max() < 1e-5
+                assert np.abs(q[i, :90] - qq[:90]).max() < 2e-5
         rew, done, win, cap, valid = env.step(actions, auto_reset=True)
         r0 = np.zeros(n, np.int32); d0, w0, c0, v0 = (np.zeros(n, np.uint8) for _ in range(4))
         oracle_lib.xqo_batch_step(ref.ctypes.data, n, actions, r0, d0, w0, c0, v0)
