@@ -18,7 +18,7 @@
 
 namespace xq {
 
-constexpr int kHidden = 128, kQ = 90, kQPad = 96, kInputs = XQ_STATE_SIZE;
+constexpr int kQPad = 96;      // Q(s)[0..95] per env, row-major (dqn_q90_device)
 
 struct Transition {
     uint32_t s[12], s2[12];
