@@ -10,7 +10,8 @@ def bench_dqn(stream, peaks, world=1, local=0, dist=None, envs=65536, replay_cap
     With world > 1 every update all-reduces the compact gradient over NCCL before the identical SGD step."""
     import torch
     from . import BatchedEnv, DQN, ReplayBuffer, collect, td_update_replay
-    from .dist import allreduce_sum_, grad_tensor
+    import os
+    from .dist import allreduce_sum_, connect_peers, grad_tensor
     dev = torch.device("cuda", local)
     env = BatchedEnv(envs, device=local, seed=31, env_id0=local * envs)
     net = DQN((1260, 128, 8100), lr=1e-6, device=local, seed=31)
@@ -26,10 +27,16 @@ def bench_dqn(stream, peaks, world=1, local=0, dist=None, envs=65536, replay_cap
     b.record(stream)
     torch.cuda.synchronize()
     collect_ms = a.elapsed_time(b)
-    grads = grad_tensor(net, dev) if world > 1 else None
+    fused = world > 1 and os.environ.get("XQ_DIST", "fused") != "nccl"
+    if fused:
+        connect_peers(net, dev)                        # gradient exchange over peer memory, fused with the SGD step
+    grads = grad_tensor(net, dev) if world > 1 and not fused else None
 
     def one(i):
-        if world > 1:
+        if fused:
+            td_update_replay(net, rb, batch, 1000 + local, i, True, 1e-6, apply=False)
+            net.dist_allreduce_apply(1e-6)
+        elif world > 1:
             td_update_replay(net, rb, batch, 1000 + local, i, True, 1e-6, apply=False)
             allreduce_sum_(grads)
             net.apply_grads(1e-6)
@@ -49,6 +56,8 @@ def bench_dqn(stream, peaks, world=1, local=0, dist=None, envs=65536, replay_cap
         dist.barrier()
     torch.cuda.synchronize()
     ms = a.elapsed_time(b)
+    if fused and net.dist_timed_out():
+        raise RuntimeError("gradient exchange: a peer never signalled (dist_timed_out)")
     t = torch.tensor([ms, collect_ms], dtype=torch.float64, device=dev)
     if dist is not None:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
@@ -57,7 +66,8 @@ def bench_dqn(stream, peaks, world=1, local=0, dist=None, envs=65536, replay_cap
     tflops = FLOP_PER_TRANSITION * batch / (us * 1e-6) / 1e12          # per GPU
     out = {"metric": "DQN TD updates/s (batch 4096 per GPU, target-net bootstrap, SGD applied)",
            "td_updates_per_s": 1e6 / us, "transitions_per_s": 1e6 / us * batch * world, "us_per_update": us, "batch_per_gpu": batch,
-           "replay_transitions_per_gpu": replay_cap, "grad_allreduce": world > 1,
+           "replay_transitions_per_gpu": replay_cap,
+           "grad_allreduce": ("peer-memory kernel fused with the SGD step" if fused else "nccl all_reduce + apply kernel") if world > 1 else False,
            "selfplay_eps_greedy_steps_per_s": envs * plies * world / (collect_ms * 1e-3), "selfplay_envs_per_gpu": envs,
            "roofline": {"bound": "tensor", "achieved": tflops, "peak": peaks["bf16_tflops"], "unit": "TFLOP/s", "frac": tflops / peaks["bf16_tflops"],
                         "traffic": None, "peak_source": peaks["source"],

@@ -18,6 +18,7 @@
 // FP32 master weights; BF16 only as MMA operands.  Tolerance vs the FP64 oracle: |dQ| <= 2e-3.
 #include <cuda.h>
 #include <math.h>
+#include <string.h>
 
 #include "xq_dqn_internal.cuh"
 #include "xq_tc.cuh"
@@ -79,6 +80,13 @@ struct Fast {
     int64_t q_cap = 0;
     float* info = nullptr;                             // 4 floats
     CUtensorMap tmW1, tmTW1, tmH, tmH2, tmD0hi, tmD0lo, tmGhi, tmGlo, tmCb;
+    // multi-GPU gradient exchange over peer memory (xq_dqn_dist_*): when connected, the compact gradient of an update is written
+    // into slot `parity` of this rank's exchange buffer, which every peer maps through CUDA IPC
+    uint8_t* exch = nullptr;                           // [2][kGradPad] FP32 gradient slots | flags[kMaxRanks] u32 | status u32
+    uint8_t* peer[16] = {};                            // exchange buffers of all ranks (peer[rank] == exch)
+    int rank = 0, world = 1, parity = 0;
+    uint32_t epoch = 0;
+    bool connected = false;
     // acting (Q(s)[0..89] for every env of a self-play shard): split-precision operands, see q90_gemm_kernel
     __nv_bfloat16* W1lo = nullptr;                     // [96][128] BF16 residual of W1 rows 0..95 (W1 = W1bf + W1lo to ~16 mantissa bits)
     __nv_bfloat16 *actHhi = nullptr, *actHlo = nullptr;   // [act_cap][128] h(s) as BF16 hi + lo
@@ -813,6 +821,7 @@ __global__ void __launch_bounds__(kDwThreads, 1) dw_gemm_kernel(const __grid_con
         uint32_t prev[kDwStages][3];
 #pragma unroll
         for (int a = 0; a < kDwStages; ++a) prev[a][0] = prev[a][1] = prev[a][2] = 0xFFFFFFFFu;
+        float db1_acc = 0.0f;           // dW1 tile, builder threads 128..255: db1 of row (bt - 128) over this CTA's samples (src/dqn.cu:310-319)
         for (int i0 = 0; i0 < my_kb; i0 += kDwStages) {
 #pragma unroll
             for (int st = 0; st < kDwStages; ++st) {
@@ -823,11 +832,7 @@ __global__ void __launch_bounds__(kDwThreads, 1) dw_gemm_kernel(const __grid_con
                 tc::mbar_wait(cfull + st, (i / kDwStages) & 1);
                 uint32_t off[3] = {0xFFFFFFFFu, 0xFFFFFFFFu, 0xFFFFFFFFu};
                 if (b < n && w1_tile) {
-                    if (grp == 0) {
-                        const int to = (int)XQ_ACTION_TO(words[12 * BK] & 0xFFFFu);
-                        off[0] = sw128_offset(to, sample);                                                   // row = action.to (< 128)
-                        atomicAdd(&s_db1[to], __uint_as_float(words[14 * BK]));                             // db1[to] += delta1 (src/dqn.cu:310-319)
-                    }
+                    if (grp == 0) off[0] = sw128_offset((int)XQ_ACTION_TO(words[12 * BK] & 0xFFFFu), sample);      // row = action.to (< 128)
                 } else if (b < n) {
 #pragma unroll
                     for (int u = 0; u < 3; ++u) {
@@ -839,6 +844,12 @@ __global__ void __launch_bounds__(kDwThreads, 1) dw_gemm_kernel(const __grid_con
                         }
                     }
                     if (mt == kDwMTiles - 2 && grp == 3) off[2] = sw128_offset(kBiasFeat - f0, sample);      // constant-one feature -> db0
+                }
+                if (w1_tile && grp >= 2) {      // db1[r] += delta1 of the samples with action.to == r, in sample order: deterministic, no atomics
+                    const uint32_t* cw = reinterpret_cast<const uint32_t*>(sC + st * kDwCStride);              // (samples >= n read as to = 0, delta1 = 0)
+#pragma unroll 8
+                    for (int j = 0; j < BK; ++j)
+                        if ((int)XQ_ACTION_TO(cw[12 * BK + j] & 0xFFFFu) == bt - 128) db1_acc += __uint_as_float(cw[14 * BK + j]);
                 }
                 if (bt == 0 && i < 8) XQ_TL(1, 12 + i);
                 uint8_t* tile = sA + st * kDwABytes;
@@ -854,6 +865,7 @@ __global__ void __launch_bounds__(kDwThreads, 1) dw_gemm_kernel(const __grid_con
                 if (bt == 0 && i < 8) XQ_TL(1, 20 + i);
             }
         }
+        if (w1_tile && grp >= 2) s_db1[bt - 128] = db1_acc;
         if (warp < 8) {   // ===== epilogue: hi + lo halves out of TMEM -> this warp's 32 rows staged in shared memory (16-byte chunks
                           // XOR-swizzled by row); the whole CTA then writes coalesced 512-byte rows of the FP32 partial =====
             const int quarter = warp & 3, row = quarter * 32 + lane;
@@ -958,6 +970,72 @@ __global__ void __launch_bounds__(256) apply_kernel(float* __restrict__ W0T, flo
     else b1[i - kGradB1] -= lr * g;
 }
 
+// ---------------------------------------------------------------------------------------------
+// Multi-GPU TD update, the ONE exchange step of the path, fused with the SGD step: every rank has written its compact
+// gradient into slot `parity` of its exchange buffer (IPC-mapped by all peers).  This kernel (same launch on every rank)
+//   1. signals "gradient `epoch` of rank r is complete" into EVERY rank's flag array (release, system scope, over NVLink),
+//   2. waits until all `world` flags in its OWN memory carry `epoch` (acquire, system scope; the spin is local),
+//   3. sums the `world` gradients in rank order straight out of peer memory (volatile 16-byte loads over NVLink / NVSwitch)
+//      -- the order is the same on every rank, so the replicas stay bit-identical -- and applies W -= lr * g.
+// Two gradient slots alternate: a rank can only reach the signal of epoch e+1 after its own kernel of epoch e has finished
+// reading, so when all flags of e+1 are in, slot (e+2)&1 == e&1 is free to be rewritten.  No NCCL call, no separate apply.
+constexpr int kMaxRanks = 16;
+constexpr int kGradPad = (kGradSize + 3) / 4 * 4;
+constexpr size_t kExchFlagsOff = sizeof(float) * 2 * kGradPad;                 // 16-byte aligned
+constexpr size_t kExchBytes = kExchFlagsOff + sizeof(uint32_t) * (kMaxRanks + 4);
+struct PeerPtrs { uint8_t* p[kMaxRanks]; };
+
+__device__ __forceinline__ float4 ld_peer_f4(const float* p) {
+    float4 v;
+    asm volatile("ld.volatile.global.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "l"(p) : "memory");
+    return v;
+}
+
+__global__ void __launch_bounds__(256) grad_exchange_apply_kernel(PeerPtrs peers, int rank, int world, int parity, uint32_t epoch,
+                                                                 float* __restrict__ W0T, float* __restrict__ b0, float* __restrict__ W1,
+                                                                 float* __restrict__ b1, __nv_bfloat16* __restrict__ W1bf,
+                                                                 __nv_bfloat16* __restrict__ W1lo, float lr) {
+    uint32_t* my_flags = reinterpret_cast<uint32_t*>(peers.p[rank] + kExchFlagsOff);
+    if (blockIdx.x == 0 && (int)threadIdx.x < world) {         // 1. my gradient (written by the previous kernel of this stream) is complete
+        __threadfence_system();
+        uint32_t* f = reinterpret_cast<uint32_t*>(peers.p[threadIdx.x] + kExchFlagsOff) + rank;
+        asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(f), "r"(epoch) : "memory");
+    }
+    if ((int)threadIdx.x < world) {                            // 2. all gradients of this epoch are complete
+        const long long t0 = clock64();
+        uint32_t v;
+        do {
+            asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(my_flags + threadIdx.x) : "memory");
+            if ((int32_t)(v - epoch) >= 0) break;
+            if (clock64() - t0 > (1ll << 32)) { my_flags[kMaxRanks] = 1u; break; }      // ~2 s: a peer never arrived; flag it, do not hang the GPU
+        } while (true);
+    }
+    __syncthreads();
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;       // 3. float4 index over the compact gradient
+    if (i >= kGradPad / 4) return;
+    const size_t off = sizeof(float) * ((size_t)parity * kGradPad + 4 * (size_t)i);
+    float4 g = make_float4(0.f, 0.f, 0.f, 0.f);
+    for (int r = 0; r < world; ++r) {
+        const float4 v = ld_peer_f4(reinterpret_cast<const float*>(peers.p[r] + off));
+        g.x += v.x; g.y += v.y; g.z += v.z; g.w += v.w;
+    }
+    const float gv[4] = {g.x, g.y, g.z, g.w};
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {                              // the segment boundaries of the compact layout are not all multiples of 4
+        const int e = 4 * i + k;
+        if (e >= kGradSize) break;
+        if (e < kGradB0) W0T[e] -= lr * gv[k];
+        else if (e < kGradW1) b0[e - kGradB0] -= lr * gv[k];
+        else if (e < kGradB1) {
+            const int j = e - kGradW1;
+            const float v = W1[j] - lr * gv[k];
+            W1[j] = v;
+            const __nv_bfloat16 hi = __float2bfloat16_rn(v);
+            W1bf[j] = hi; W1lo[j] = __float2bfloat16_rn(v - __bfloat162float(hi));
+        } else b1[e - kGradB1] -= lr * gv[k];
+    }
+}
+
 // ---- FP64 (reference layout) <-> fast-path layouts ----------------------------------------------
 __global__ void f64_to_fast_kernel(const double* __restrict__ w, const double* __restrict__ b, float* __restrict__ W0T, float* __restrict__ b0,
                                    float* __restrict__ W1, float* __restrict__ b1, __nv_bfloat16* __restrict__ W1bf, __nv_bfloat16* __restrict__ W1lo) {
@@ -1037,11 +1115,16 @@ static cudaError_t launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, s
     return cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);
 }
 
+// where the compact gradient of the current update goes: the rank's exchange slot once xq_dqn_dist_connect has run
+static inline float* cur_grad(Fast* f) { return f->connected ? reinterpret_cast<float*>(f->exch) + (size_t)f->parity * kGradPad : f->grad; }
+
 static inline unsigned blocks(int64_t n, int per) { return (unsigned)((n + per - 1) / per); }
 
 void dqn_fast_destroy(xq_dqn_s* h) {
     Fast* f = h->fast;
     if (!f) return;
+    for (int r = 0; r < f->world; ++r) if (f->connected && r != f->rank && f->peer[r]) cudaIpcCloseMemHandle(f->peer[r]);
+    cudaFree(f->exch);
     cudaFree(f->W0T); cudaFree(f->b0); cudaFree(f->W1); cudaFree(f->b1); cudaFree(f->W1bf); cudaFree(f->W1lo); cudaFree(f->actHhi); cudaFree(f->actHlo);
     cudaFree(f->tW0T); cudaFree(f->tb0); cudaFree(f->tW1); cudaFree(f->tb1); cudaFree(f->tW1bf);
     cudaFree(f->grad); cudaFree(f->boards); cudaFree(f->Hbf); cudaFree(f->H2bf); cudaFree(f->Hf); cudaFree(f->zpart);
@@ -1238,7 +1321,7 @@ int td_update_core(xq_dqn_s* h, const BatchRef& ref, int64_t n, int use_target_n
                        (float)h->gamma, h->mode, f->d0hi, f->d0lo, f->ghi, f->glo, ld, f->info_slots));
     // 4. dW0 / db0 / dW1 / db1 contraction, cluster reduction and the SGD step (or the compact gradient)
     XQ_CUDA(launch_pdl(dw_gemm_kernel, dim3(kDwMTiles, kDwSplits), dim3(kDwThreads), kDwSmem, h->stream, kDwSplits, f->tmD0hi, f->tmD0lo, f->tmGhi,
-                       f->tmGlo, f->tmCb, (int)n, f->part, f->dbpart, f->info_slots, f->info, f->grad, f->W0T, f->b0, f->W1, f->b1, f->W1bf,
+                       f->tmGlo, f->tmCb, (int)n, f->part, f->dbpart, f->info_slots, f->info, cur_grad(f), f->W0T, f->b0, f->W1, f->b1, f->W1bf,
                        f->W1lo, (float)lr, apply ? 1 : 0));
     if (apply) h->f64_current = false;
     return XQ_OK;
@@ -1277,7 +1360,7 @@ int xq_dqn_td_update(xq_dqn_t h, const xq_transition* batch_host, int64_t n, int
 int xq_dqn_grad_buffer(xq_dqn_t h, void** dev_ptr, int64_t* n_floats) {
     XQ_DQN_ENTER(h);
     if (int rc = ensure_fast(h)) return rc;
-    if (dev_ptr) *dev_ptr = h->fast->grad;
+    if (dev_ptr) *dev_ptr = cur_grad(h->fast);
     if (n_floats) *n_floats = kGradSize;
     return XQ_OK;
 }
@@ -1287,9 +1370,71 @@ int xq_dqn_apply_grads(xq_dqn_t h, double lr) {
     if (int rc = ensure_fast(h)) return rc;
     Fast* f = h->fast;
     if (lr <= 0) lr = h->lr;
-    apply_kernel<<<blocks(kGradSize, 256), 256, 0, h->stream>>>(f->W0T, f->b0, f->W1, f->b1, f->W1bf, f->W1lo, f->grad, (float)lr);
+    apply_kernel<<<blocks(kGradSize, 256), 256, 0, h->stream>>>(f->W0T, f->b0, f->W1, f->b1, f->W1bf, f->W1lo, cur_grad(f), (float)lr);
     XQ_LAUNCH_CHECK();
     h->f64_current = false;
+    return XQ_OK;
+}
+
+int xq_dqn_dist_export(xq_dqn_t h, void* handle_out) {
+    XQ_DQN_ENTER(h);
+    if (!handle_out) return fail(XQ_ERR_INVALID, "xq_dqn_dist_export: null handle buffer");
+    if (int rc = ensure_fast(h)) return rc;
+    Fast* f = h->fast;
+    if (!f->exch) {
+        XQ_CUDA(cudaMalloc(&f->exch, kExchBytes));
+        XQ_CUDA(cudaMemset(f->exch, 0, kExchBytes));
+    }
+    static_assert(sizeof(cudaIpcMemHandle_t) == XQ_IPC_HANDLE_BYTES, "CUDA IPC handle size");
+    cudaIpcMemHandle_t ipc;
+    XQ_CUDA(cudaIpcGetMemHandle(&ipc, f->exch));
+    memcpy(handle_out, &ipc, sizeof(ipc));
+    return XQ_OK;
+}
+
+int xq_dqn_dist_connect(xq_dqn_t h, int rank, int world, const void* handles) {
+    XQ_DQN_ENTER(h);
+    if (!handles || world < 1 || world > kMaxRanks || rank < 0 || rank >= world)
+        return fail(XQ_ERR_INVALID, "xq_dqn_dist_connect: bad arguments (world must be 1..%d)", kMaxRanks);
+    if (int rc = ensure_fast(h)) return rc;
+    Fast* f = h->fast;
+    if (!f->exch) return fail(XQ_ERR_STATE, "xq_dqn_dist_connect: call xq_dqn_dist_export first");
+    if (f->connected) return fail(XQ_ERR_STATE, "xq_dqn_dist_connect: already connected");
+    for (int r = 0; r < world; ++r) {
+        if (r == rank) { f->peer[r] = f->exch; continue; }
+        cudaIpcMemHandle_t ipc;
+        memcpy(&ipc, static_cast<const uint8_t*>(handles) + (size_t)r * XQ_IPC_HANDLE_BYTES, sizeof(ipc));
+        void* p = nullptr;
+        XQ_CUDA(cudaIpcOpenMemHandle(&p, ipc, cudaIpcMemLazyEnablePeerAccess));
+        f->peer[r] = static_cast<uint8_t*>(p);
+    }
+    f->rank = rank; f->world = world; f->parity = 0; f->epoch = 0; f->connected = true;
+    return XQ_OK;
+}
+
+int xq_dqn_dist_allreduce_apply(xq_dqn_t h, double lr) {
+    XQ_DQN_ENTER(h);
+    if (!h->fast || !h->fast->connected) return fail(XQ_ERR_STATE, "xq_dqn_dist_allreduce_apply: not connected (xq_dqn_dist_connect)");
+    Fast* f = h->fast;
+    if (lr <= 0) lr = h->lr;
+    PeerPtrs pp;
+    for (int r = 0; r < kMaxRanks; ++r) pp.p[r] = f->peer[r];
+    ++f->epoch;
+    grad_exchange_apply_kernel<<<blocks(kGradPad / 4, 256), 256, 0, h->stream>>>(pp, f->rank, f->world, f->parity, f->epoch, f->W0T, f->b0, f->W1, f->b1,
+                                                                                f->W1bf, f->W1lo, (float)lr);
+    XQ_LAUNCH_CHECK();
+    f->parity ^= 1;
+    h->f64_current = false;
+    return XQ_OK;
+}
+
+int xq_dqn_dist_status(xq_dqn_t h, int* timed_out) {
+    XQ_DQN_ENTER(h);
+    if (!h->fast || !h->fast->exch || !timed_out) return fail(XQ_ERR_STATE, "xq_dqn_dist_status: no exchange buffer");
+    uint32_t v = 0;
+    XQ_CUDA(cudaStreamSynchronize(h->stream));
+    XQ_CUDA(cudaMemcpy(&v, h->fast->exch + kExchFlagsOff + sizeof(uint32_t) * kMaxRanks, sizeof(v), cudaMemcpyDeviceToHost));
+    *timed_out = (int)v;
     return XQ_OK;
 }
 

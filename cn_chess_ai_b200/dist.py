@@ -1,7 +1,10 @@
 """Multi-GPU plumbing: one process per GPU (torch.distributed), env / replay shards per rank with no
-data-path collective, and ONE exchange step per TD update: a sum all-reduce (NCCL over NVLink/NVSwitch)
-of the compact gradient buffer (173,018 FP32 = 0.69 MB), followed by the identical SGD step on every
-rank.  torch is plumbing here (process group, stream, the collective); the kernels are the library's."""
+data-path collective, and ONE exchange step per TD update: the sum of the compact gradient buffers
+(173,018 FP32 = 0.69 MB) over the ranks followed by the identical SGD step on every rank.  Two ways:
+  * fused (default): the library's own kernel reads the peers' gradients over NVLink / NVSwitch peer memory (CUDA IPC),
+    sums them in rank order and applies the step -- connect_peers() + DQN.dist_allreduce_apply();
+  * baseline: ncclAllReduce through torch.distributed + DQN.apply_grads().
+torch is plumbing here (process group, stream, handle exchange); the kernels are the library's."""
 import os
 
 
@@ -37,6 +40,21 @@ def allreduce_sum_(tensor, group=None):
     return tensor
 
 
+def connect_peers(dqn, device, group=None):
+    """exchange the CUDA IPC handles of the gradient exchange buffers over the process group and map the peers' buffers:
+    afterwards dqn.dist_allreduce_apply() replaces all_reduce + apply_grads with one fused peer-memory kernel per rank"""
+    import torch
+    import torch.distributed as dist
+    world, rank = dist.get_world_size(group), dist.get_rank(group)
+    mine = torch.from_numpy(dqn.dist_export()).to(device)
+    gathered = [torch.empty_like(mine) for _ in range(world)]
+    dist.all_gather(gathered, mine, group=group)
+    handles = torch.stack(gathered).cpu().numpy()
+    dqn.dist_connect(rank, world, handles)
+    dist.barrier(group)             # every rank has mapped every buffer before the first flag is written
+    return world
+
+
 class DataParallelLearner:
     """Config 4: every rank owns envs [first, first+count) (global ids keep trajectories independent of the GPU
     count), its own replay shard and a replica of the Q-network initialised from the same seed.  A training
@@ -56,7 +74,10 @@ class DataParallelLearner:
         self.dqn.set_stream(stream)
         self.batch, self.eps, self.lr, self.seed, self.train_done = batch, eps, lr, seed, train_done
         self.updates = 0
-        self.grads = grad_tensor(self.dqn, self.device)
+        self.fused = self.world > 1 and os.environ.get("XQ_DIST", "fused") != "nccl"
+        if self.fused:
+            connect_peers(self.dqn, self.device)
+        self.grads = None if self.fused else grad_tensor(self.dqn, self.device)
 
     def collect(self, n_plies):
         from . import collect
@@ -65,6 +86,9 @@ class DataParallelLearner:
     def update(self, use_target_net=True):
         from . import td_update_replay
         td_update_replay(self.dqn, self.replay, self.batch, self.seed + 1000003 * self.rank, self.updates, use_target_net, self.lr, apply=False)
-        allreduce_sum_(self.grads)
-        self.dqn.apply_grads(self.lr)
+        if self.fused:
+            self.dqn.dist_allreduce_apply(self.lr)
+        else:
+            allreduce_sum_(self.grads)
+            self.dqn.apply_grads(self.lr)
         self.updates += 1

@@ -35,6 +35,10 @@ def _bind():
     L.xq_dqn_td_update_device.argtypes = [_P, _P, C.c_int64, C.c_int, C.c_double, C.c_int]
     L.xq_dqn_grad_buffer.argtypes = [_P, C.POINTER(_P), C.POINTER(C.c_int64)]
     L.xq_dqn_apply_grads.argtypes = [_P, C.c_double]
+    L.xq_dqn_dist_export.argtypes = [_P, _P]
+    L.xq_dqn_dist_connect.argtypes = [_P, C.c_int, C.c_int, _P]
+    L.xq_dqn_dist_allreduce_apply.argtypes = [_P, C.c_double]
+    L.xq_dqn_dist_status.argtypes = [_P, C.POINTER(C.c_int)]
     L.xq_dqn_save.argtypes = [_P, C.c_char_p]
     L.xq_dqn_load.argtypes = [_P, C.c_char_p]
     _bound = True
@@ -146,3 +150,24 @@ class DQN:
 
     def apply_grads(self, lr=0.0):
         check(self._L.xq_dqn_apply_grads(self._h, lr))
+
+    # ---- multi-GPU gradient exchange over peer memory (one process per GPU) ----
+    def dist_export(self):
+        """64-byte CUDA IPC handle of this rank's gradient exchange buffer"""
+        buf = np.zeros(64, dtype=np.uint8)
+        check(self._L.xq_dqn_dist_export(self._h, ptr(buf)))
+        return buf
+
+    def dist_connect(self, rank, world, handles):
+        """handles: uint8 [world, 64], the dist_export() results of all ranks in rank order"""
+        hs = np.ascontiguousarray(handles, dtype=np.uint8).reshape(world, 64)
+        check(self._L.xq_dqn_dist_connect(self._h, rank, world, ptr(hs)))
+
+    def dist_allreduce_apply(self, lr=0.0):
+        """ONE kernel: signal / wait through peer memory, sum the world gradients in rank order over NVLink, apply the SGD step"""
+        check(self._L.xq_dqn_dist_allreduce_apply(self._h, lr))
+
+    def dist_timed_out(self):
+        v = C.c_int()
+        check(self._L.xq_dqn_dist_status(self._h, C.byref(v)))
+        return bool(v.value)

@@ -200,6 +200,19 @@ int xq_dqn_td_update_device(xq_dqn_t h, const void* batch_dev, int64_t n, int us
 int xq_dqn_grad_buffer(xq_dqn_t h, void** dev_ptr, int64_t* n_floats);
 int xq_dqn_apply_grads(xq_dqn_t h, double lr);
 
+/* ---- multi-GPU: the one exchange step of the path, fused with the SGD step, over peer memory ----
+ * One process per GPU.  xq_dqn_dist_export returns the 64-byte CUDA IPC handle of this rank's gradient exchange buffer; the
+ * ranks gather each other's handles with whatever transport they have (torch.distributed, MPI, a file) and pass all `world`
+ * of them, in rank order, to xq_dqn_dist_connect.  From then on xq_dqn_td_update_*(apply = 0) leaves the compact gradient in
+ * the exchange buffer and xq_dqn_dist_allreduce_apply launches ONE kernel per rank that signals / waits through flags in
+ * peer memory, sums the world gradients in rank order over NVLink (bit-identical on every rank) and applies W -= lr * sum.
+ * It replaces ncclAllReduce + xq_dqn_apply_grads.  xq_dqn_dist_status: timed_out != 0 if a peer never arrived (~2 s). */
+#define XQ_IPC_HANDLE_BYTES 64
+int xq_dqn_dist_export(xq_dqn_t h, void* handle_out);
+int xq_dqn_dist_connect(xq_dqn_t h, int rank, int world, const void* handles);
+int xq_dqn_dist_allreduce_apply(xq_dqn_t h, double lr);
+int xq_dqn_dist_status(xq_dqn_t h, int* timed_out);
+
 /* ---- GPU-resident replay buffer + epsilon-greedy self-play (new capabilities: the reference trains online at
  * batch 1 and has no replay buffer; semantics are per transition those of ChessAI::train) ---- */
 typedef struct xq_replay_s* xq_replay_t;
