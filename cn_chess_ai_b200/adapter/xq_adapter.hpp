@@ -267,3 +267,64 @@ private:
     double learningRate = 0.001, gamma = 0.99;
     uint32_t fallback_ = 0;
 };
+
+// ---- ChessAI for N boards at once: what a Worker thread (mainwindow.h:130-147) calls when it wants throughput --------------
+// Same slots / signals as ChessAI (train, startSelfPlay, gameCompleted, trainingFinished, selfPlayFinished, saveModel / loadModel),
+// but the games run side by side on the device: the epsilon-greedy collector with tensor-core inference fills a GPU replay ring,
+// batched TD updates train from it, and every finished game is reported in (ply, board) order through the same callback, the
+// same game_log.txt line (chessai.cpp:370-393) and the same autosave cadence (:165-167) -- xq_train_run (include/xq.h).
+class BatchedChessAI {
+public:
+    explicit BatchedChessAI(int64_t n_boards, uint64_t seed = 0, int device = 0, int64_t replay_capacity = 1 << 20) {
+        xq_adapter::check(xq_env_create(n_boards, device, seed, 0, &env_));
+        xq_adapter::check(xq_replay_create(replay_capacity, device, &replay_));
+    }
+    ~BatchedChessAI() { if (replay_) xq_replay_destroy(replay_); if (env_) xq_env_destroy(env_); }
+    BatchedChessAI(const BatchedChessAI&) = delete;
+    BatchedChessAI& operator=(const BatchedChessAI&) = delete;
+
+    std::function<void(int, int, int)> on_game_completed;   // gameCompleted(gameNumber, redScore, blackScore)
+    std::function<void()> on_training_finished, on_self_play_finished;
+    std::string log_path;                                   // "game_log.txt" in the reference (chessai.cpp:196); empty = no log
+    int plies_per_round = 16, updates_per_round = 4, target_sync_plies = 100, autosave_games = 100;
+    int64_t batch = 4096;
+
+    void initializeDQN() { if (!dqn) dqn.reset(new DQN(std::vector<int>{90 * 14, 128, 90 * 90})); }
+    bool isDQNInitialized() const { return dqn != nullptr; }
+    void saveModel(const std::string& f) { if (dqn) dqn->saveModel(f); }
+    void loadModel(const std::string& f) { if (dqn) dqn->loadModel(f); }
+    DQN* network() { return dqn.get(); }
+
+    xq_train_report train(int numEpisodes) {                // ChessAI::train, chessai.cpp:85-170
+        initializeDQN();
+        const xq_train_report r = run(numEpisodes, updates_per_round, 1);
+        if (on_training_finished) on_training_finished();
+        return r;
+    }
+    xq_train_report startSelfPlay(int numGames) {           // ChessAI::startSelfPlay, chessai.cpp:191-266 (it trains online too, :229-239)
+        initializeDQN();
+        const xq_train_report r = run(numGames, updates_per_round, 0);
+        if (on_self_play_finished) on_self_play_finished();
+        return r;
+    }
+
+private:
+    static void trampoline(void* user, int64_t g, int32_t r, int32_t b) {
+        auto* self = static_cast<BatchedChessAI*>(user);
+        if (self->on_game_completed) self->on_game_completed((int)g, r, b);
+    }
+    xq_train_report run(int games, int updates, int train_done) {
+        xq_train_config cfg = {};
+        cfg.n_games = games; cfg.plies_per_round = plies_per_round; cfg.updates_per_round = updates; cfg.batch = batch;
+        cfg.eps = 0.1; cfg.lr = learningRate; cfg.use_target_net = 1; cfg.target_sync_plies = target_sync_plies; cfg.train_done = train_done;
+        cfg.autosave_games = autosave_games; cfg.autosave_prefix = nullptr; cfg.log_path = log_path.empty() ? nullptr : log_path.c_str();
+        cfg.sample_seed = 0x5eed;
+        xq_train_report rep = {};
+        xq_adapter::check(xq_train_run(dqn->handle(), env_, replay_, &cfg, &BatchedChessAI::trampoline, this, &rep));
+        return rep;
+    }
+    xq_env_t env_ = nullptr;
+    xq_replay_t replay_ = nullptr;
+    std::unique_ptr<DQN> dqn;
+    double learningRate = 0.001;
+};

@@ -18,6 +18,8 @@
 #include <vector>
 
 #include "xq_common.cuh"
+#include <algorithm>
+
 #include "xq_env_dev.cuh"
 
 namespace xq {
@@ -260,6 +262,8 @@ struct xq_env_s {
     double* d_state = nullptr;
     uint8_t* d_nonstd = nullptr;      // n flags written by the slot kernel
     bool maybe_nonstd = false;        // set once boards were injected (xq_env_set_boards)
+    // finished-game events of the self-play collector (xq_env_enable_game_events)
+    xq_game_event* d_events = nullptr; unsigned long long* d_event_count = nullptr; int64_t event_cap = 0; uint32_t event_ply = 0;
 };
 
 static inline unsigned grid_for(int64_t n, int per_block) { return (unsigned)((n + per_block - 1) / per_block); }
@@ -285,8 +289,10 @@ namespace xq {
 int env_info(xq_env_t h, EnvInfo* out) {
     if (!h || !out) return fail(XQ_ERR_INVALID, "env_info: null handle");
     out->n = h->n; out->device = h->device; out->seed = h->seed; out->env_id0 = h->env_id0; out->stream = h->stream; out->d_envs = h->d_envs; out->d_stats = h->d_stats;
+    out->d_events = h->d_events; out->d_event_count = h->d_event_count; out->event_cap = h->event_cap; out->event_ply = h->event_ply;
     return XQ_OK;
 }
+void env_advance_event_ply(xq_env_t h, uint32_t plies) { if (h) h->event_ply += plies; }
 }  // namespace xq
 
 extern "C" {
@@ -316,7 +322,7 @@ int xq_env_destroy(xq_env_t h) {
     if (!h) return XQ_OK;
     cudaSetDevice(h->device);
     cudaFree(h->d_envs); cudaFree(h->d_stats); cudaFree(h->d_actions); cudaFree(h->d_i32); cudaFree(h->d_lists);
-    cudaFree(h->d_trace); cudaFree(h->d_state); cudaFree(h->d_nonstd);
+    cudaFree(h->d_trace); cudaFree(h->d_state); cudaFree(h->d_nonstd); cudaFree(h->d_events); cudaFree(h->d_event_count);
     for (auto p : h->d_u8) cudaFree(p);
     if (h->own_stream && h->stream) cudaStreamDestroy(h->stream);
     delete h;
@@ -455,6 +461,36 @@ int xq_env_get_stats(xq_env_t h, xq_env_stats* stats_host, int reset) {
     if (stats_host) XQ_CUDA(cudaMemcpyAsync(stats_host, h->d_stats, sizeof(xq_env_stats), cudaMemcpyDeviceToHost, h->stream));
     if (reset) XQ_CUDA(cudaMemsetAsync(h->d_stats, 0, sizeof(xq_env_stats), h->stream));
     XQ_CUDA(cudaStreamSynchronize(h->stream));
+    return XQ_OK;
+}
+
+int xq_env_enable_game_events(xq_env_t h, int64_t capacity) {
+    XQ_ENV_ENTER(h);
+    if (capacity <= 0) return fail(XQ_ERR_INVALID, "xq_env_enable_game_events: capacity must be > 0");
+    XQ_CUDA(cudaStreamSynchronize(h->stream));
+    cudaFree(h->d_events); cudaFree(h->d_event_count); h->d_events = nullptr; h->d_event_count = nullptr; h->event_cap = 0;
+    XQ_CUDA(cudaMalloc(&h->d_events, sizeof(xq_game_event) * capacity));
+    XQ_CUDA(cudaMalloc(&h->d_event_count, sizeof(unsigned long long)));
+    XQ_CUDA(cudaMemset(h->d_event_count, 0, sizeof(unsigned long long)));
+    h->event_cap = capacity; h->event_ply = 0;
+    return XQ_OK;
+}
+
+int xq_env_drain_game_events(xq_env_t h, xq_game_event* out_host, int64_t max_events, int64_t* n_out, int64_t* n_dropped) {
+    XQ_ENV_ENTER(h);
+    if (!h->d_events) return fail(XQ_ERR_STATE, "xq_env_drain_game_events: call xq_env_enable_game_events first");
+    if (!out_host || !n_out || max_events < h->event_cap) return fail(XQ_ERR_INVALID, "xq_env_drain_game_events: the output must hold the ring's capacity");
+    unsigned long long count = 0;
+    XQ_CUDA(cudaMemcpyAsync(&count, h->d_event_count, sizeof(count), cudaMemcpyDeviceToHost, h->stream));
+    XQ_CUDA(cudaStreamSynchronize(h->stream));
+    const int64_t n = (int64_t)count < h->event_cap ? (int64_t)count : h->event_cap;
+    if (n > 0) XQ_CUDA(cudaMemcpyAsync(out_host, h->d_events, sizeof(xq_game_event) * n, cudaMemcpyDeviceToHost, h->stream));
+    XQ_CUDA(cudaMemsetAsync(h->d_event_count, 0, sizeof(unsigned long long), h->stream));
+    XQ_CUDA(cudaStreamSynchronize(h->stream));
+    // slots were claimed with an atomic counter: restore the order of the batched loop, (ply, env)
+    std::sort(out_host, out_host + n, [](const xq_game_event& a, const xq_game_event& b) { return a.ply != b.ply ? a.ply < b.ply : a.env < b.env; });
+    *n_out = n;
+    if (n_dropped) *n_dropped = (int64_t)count - n;
     return XQ_OK;
 }
 

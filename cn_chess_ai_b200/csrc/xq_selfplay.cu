@@ -33,7 +33,8 @@ template <bool APPLY>
 __global__ void __launch_bounds__(kThreads) act_kernel(xq_env_rec* __restrict__ envs, int64_t n, uint64_t env_id0, uint64_t seed,
                                                       const float* __restrict__ q90, uint32_t eps_thr, int train_done,
                                                       uint16_t* __restrict__ actions_out, Transition* __restrict__ ring, int64_t ring_cap,
-                                                      int64_t ring_pos, xq_env_stats* __restrict__ stats) {
+                                                      int64_t ring_pos, xq_env_stats* __restrict__ stats, xq_game_event* __restrict__ events,
+                                                      unsigned long long* __restrict__ event_count, int64_t event_cap, uint32_t event_ply) {
     __shared__ uint32_t s_board[12 * kThreads];
     __shared__ uint32_t s_list[64 * kThreads];
     const int tid = threadIdx.x;
@@ -78,6 +79,11 @@ __global__ void __launch_bounds__(kThreads) act_kernel(xq_env_rec* __restrict__ 
                 t.action = 0; t.done = 1; t.reward = 0;
 #pragma unroll
                 for (int i = 0; i < 12; ++i) t.s2[i] = t.s[i];
+                if (events) {   // the episode loop breaks without a move (chessai.cpp:100-103); gameCompleted still fires (:161)
+                    const unsigned long long slot = atomicAdd(event_count, 1ull);
+                    if ((int64_t)slot < event_cap)
+                        events[slot] = xq_game_event{event_ply, (uint32_t)env, m.red_score, m.black_score, (uint16_t)m.move_count, (uint8_t)s.winner, 2, 0u};
+                }
                 reset_board(b); m.reset(); m.ctr++; a_games++;
             } else {
                 const int mover = m.player;
@@ -98,6 +104,12 @@ __global__ void __launch_bounds__(kThreads) act_kernel(xq_env_rec* __restrict__ 
                     a_games++;
                     if (win == RED) a_red++; else if (win == BLACK) a_black++;
                     if (m.move_count < XQ_MAX_MOVES) a_capg++;
+                    if (events) {   // gameCompleted(game, board->getRedScore(), board->getBlackScore()), chessai.cpp:161
+                        const unsigned long long slot = atomicAdd(event_count, 1ull);
+                        if ((int64_t)slot < event_cap)
+                            events[slot] = xq_game_event{event_ply, (uint32_t)env, m.red_score, m.black_score, (uint16_t)m.move_count, (uint8_t)win,
+                                                         (uint8_t)(type_of(cap) == GENERAL ? 0 : 1), 0u};
+                    }
                     reset_board(b); m.reset();
                 }
             }
@@ -274,7 +286,7 @@ int xq_dqn_act(xq_dqn_t h, xq_env_t env, double eps, xq_action* actions_host, fl
     if (int rc = order_after(ei.stream, h->stream, &g_ev[h->device & 63])) return rc;
     if (int rc = dqn_q90_device(h, ei.d_envs, ei.n, sc->q90, ei.stream)) return rc;
     act_kernel<false><<<blocks(ei.n, kThreads), kThreads, 0, ei.stream>>>(ei.d_envs, ei.n, ei.env_id0, ei.seed, sc->q90, xq_eps_threshold(eps), 0,
-                                                                         sc->actions, nullptr, 1, 0, nullptr);
+                                                                         sc->actions, nullptr, 1, 0, nullptr, nullptr, nullptr, 0, 0u);
     XQ_LAUNCH_CHECK();
     XQ_CUDA(cudaMemcpyAsync(actions_host, sc->actions, sizeof(uint16_t) * ei.n, cudaMemcpyDeviceToHost, ei.stream));
     if (q_host) XQ_CUDA(cudaMemcpyAsync(q_host, sc->q90, sizeof(float) * kQPad * ei.n, cudaMemcpyDeviceToHost, ei.stream));
@@ -298,10 +310,12 @@ int xq_selfplay_collect(xq_dqn_t h, xq_env_t env, xq_replay_t r, int n_plies, do
         if (int rc = dqn_q90_device(h, ei.d_envs, ei.n, sc->q90, ei.stream)) return rc;
         act_kernel<true><<<blocks(ei.n, kThreads), kThreads, 0, ei.stream>>>(ei.d_envs, ei.n, ei.env_id0, ei.seed, sc->q90, thr, train_done, nullptr,
                                                                             r ? r->d_ring : nullptr, r ? r->capacity : 1,
-                                                                            r ? r->total % r->capacity : 0, d_stats);
+                                                                            r ? r->total % r->capacity : 0, d_stats, ei.d_events, ei.d_event_count,
+                                                                            ei.event_cap, ei.event_ply + (uint32_t)p);
         XQ_LAUNCH_CHECK();
         if (r) r->total += ei.n;
     }
+    env_advance_event_ply(env, (uint32_t)n_plies);
     if (int rc = order_after(h->stream, ei.stream, &g_ev[h->device & 63])) return rc;    // later TD updates see the new transitions
     return XQ_OK;
 }

@@ -240,6 +240,50 @@ int xq_selfplay_collect(xq_dqn_t h, xq_env_t env, xq_replay_t r, int n_plies, do
 int xq_dqn_td_update_replay(xq_dqn_t h, xq_replay_t r, int64_t batch, uint64_t seed, uint32_t counter, int use_target_net, double lr,
                             int apply);
 
+/* ---- episode driver: the batched equivalent of ChessAI::train / startSelfPlay (src/chessai.cpp:85-170, :191-266) ----
+ * One finished game of the self-play collector = the arguments of the reference's gameCompleted(game, redScore, blackScore)
+ * signal (src/chessai.cpp:161) plus what its log line and statistics need. */
+typedef struct {
+    uint32_t ply;          /* collector ply (counted since xq_env_enable_game_events) at which the game ended */
+    uint32_t env;          /* env index within this handle */
+    int32_t red_score;     /* ChessBoard::getRedScore / getBlackScore when the game ended */
+    int32_t black_score;
+    uint16_t moves;        /* ChessBoard::getMoveCount */
+    uint8_t winner;        /* ChessBoard::getWinner: 0 Red, 1 Black, 2 None */
+    uint8_t reason;        /* 0 a General was captured, 1 move cap (200), 2 no legal action (:100-103) */
+    uint32_t reserved;
+} xq_game_event;           /* 24 B */
+/* device ring of `capacity` finished-game events filled by xq_selfplay_collect; xq_env_drain_game_events copies the pending
+ * events out SORTED by (ply, env) -- the deterministic game order of the batched loop -- and empties the ring;
+ * *n_dropped = events lost because the ring was full since the last drain */
+int xq_env_enable_game_events(xq_env_t h, int64_t capacity);
+int xq_env_drain_game_events(xq_env_t h, xq_game_event* out_host, int64_t max_events, int64_t* n_out, int64_t* n_dropped);
+
+typedef void (*xq_game_completed_fn)(void* user, int64_t game_number, int32_t red_score, int32_t black_score);
+typedef struct {
+    int64_t n_games;           /* stop after this many finished games (numEpisodes / numGames) */
+    int plies_per_round;       /* self-play plies collected between two learning phases */
+    int updates_per_round;     /* TD updates (batch `batch`) per learning phase; 0 = self-play only (startSelfPlay without training) */
+    int64_t batch;
+    double eps;                /* 0.1 in the reference (:106, :210) */
+    double lr;                 /* <= 0: the network's rate (0.001, include/chessai.h:48) */
+    int use_target_net;        /* 1: DQN::train bootstrap (src/dqn.cpp:157-172); 0: online net (ChessAI::train, :119-128) */
+    int target_sync_plies;     /* updateTargetNetwork cadence in collector plies (the reference: every 100 plies, :140) */
+    int train_done;            /* 1: done also when moveCount + 1 >= 200 (train, :119); 0: checkGameOver only (startSelfPlay, :227) */
+    int autosave_games;        /* saveModel every this many games (100 in the reference, :165-167); 0 = never */
+    const char* autosave_prefix;   /* file = "<prefix><games>_games.bin" ("model_after_" in the reference); NULL = that default */
+    const char* log_path;      /* game_log.txt sink in ChessAI::onGameCompleted's line format (:370-393); NULL = none */
+    uint64_t sample_seed;      /* replay sampling seed (xq_replay_sample) */
+} xq_train_config;
+typedef struct {
+    int64_t games, plies, transitions, updates, target_syncs, autosaves, events_dropped;
+    int64_t red_wins, black_wins;      /* by score, as the log line decides ("Red wins!" / "Black wins!" / "It's a draw!") */
+    double seconds;
+} xq_train_report;
+/* Runs rounds of [collect plies_per_round plies over all envs -> updates_per_round TD updates -> drain the finished games in
+ * (ply, env) order: callback (gameCompleted), log line, autosave] until n_games games have finished.  Synchronous. */
+int xq_train_run(xq_dqn_t h, xq_env_t env, xq_replay_t r, const xq_train_config* cfg, xq_game_completed_fn cb, void* user, xq_train_report* report);
+
 /* number of kernels this library has launched in this process (bench.py's gpu_launches) */
 uint64_t xq_launch_count(void);
 

@@ -31,5 +31,15 @@ int main() {
     std::printf("trained_games %d red_score_nonneg %d dqn %d\n", games, (int)(last_red >= 0), (int)ai.isDQNInitialized());
     auto mv = ai.getAIMove(board.getCurrentPlayer());
     std::printf("ai_move_valid %d\n", (int)board.isValidMove(mv.first.first, mv.first.second, mv.second.first, mv.second.second));
+    {   // the batched episode driver behind the same slots / signals
+        BatchedChessAI many(256, 11, 0, 1 << 15);
+        many.batch = 512; many.autosave_games = 0; many.log_path = "game_log.txt";
+        int n = 0, last = 0;
+        many.on_game_completed = [&](int g, int, int) { ++n; last = g; };
+        bool finished = false;
+        many.on_training_finished = [&] { finished = true; };
+        const xq_train_report rep = many.train(300);
+        std::printf("batched_games %d last %d finished %d report %lld updates_positive %d\n", n, last, (int)finished, (long long)rep.games, (int)(rep.updates > 0));
+    }
     return 0;
 }
