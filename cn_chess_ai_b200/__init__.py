@@ -6,6 +6,6 @@ from ._lib import (ENV_DTYPE, MAX_ACTIONS, STATE_SIZE, STATS_DTYPE, TRACE_DTYPE,
                    lib)
 from .env import BatchedEnv, action  # noqa: F401
 from .dqn import AS_WRITTEN, CORRECTED, DQN  # noqa: F401
-from .replay import ReplayBuffer, act, collect, td_update_replay  # noqa: F401
+from .replay import ReplayBuffer, act, collect, td_update_replay, td_update_replay_n  # noqa: F401
 from .trainer import GAME_EVENT_DTYPE, drain_game_events, enable_game_events, train  # noqa: F401
 from .benchmarks import bench_dqn, smoke_dqn  # noqa: F401

@@ -9,7 +9,7 @@ def bench_dqn(stream, peaks, world=1, local=0, dist=None, envs=65536, replay_cap
     replay ring, then batch-4096 TD updates (per GPU) are timed with CUDA events on `stream`.
     With world > 1 every update all-reduces the compact gradient over NCCL before the identical SGD step."""
     import torch
-    from . import BatchedEnv, DQN, ReplayBuffer, collect, td_update_replay
+    from . import BatchedEnv, DQN, ReplayBuffer, collect, td_update_replay, td_update_replay_n
     import os
     from .dist import allreduce_sum_, connect_peers, grad_tensor
     dev = torch.device("cuda", local)
@@ -48,9 +48,16 @@ def bench_dqn(stream, peaks, world=1, local=0, dist=None, envs=65536, replay_cap
     if dist is not None:
         dist.barrier()
     torch.cuda.synchronize()
+    pipelined = world == 1 and os.environ.get("XQ_TD_PIPELINE", "1") != "0"
+    if pipelined:
+        td_update_replay_n(net, rb, batch, 1000, 10000, warmup, True, 1e-6)      # warm the second stream / both buffer slots
+        torch.cuda.synchronize()
     a.record(stream)
-    for i in range(updates):
-        one(warmup + i)
+    if pipelined:      # one call = `updates` sequential updates, the target-net branch of update i+1 under the online branch of update i
+        td_update_replay_n(net, rb, batch, 1000, warmup, updates, True, 1e-6)
+    else:
+        for i in range(updates):
+            one(warmup + i)
     b.record(stream)
     if dist is not None:
         dist.barrier()
@@ -65,7 +72,7 @@ def bench_dqn(stream, peaks, world=1, local=0, dist=None, envs=65536, replay_cap
     us = 1e3 * ms / updates
     tflops = FLOP_PER_TRANSITION * batch / (us * 1e-6) / 1e12          # per GPU
     out = {"metric": "DQN TD updates/s (batch 4096 per GPU, target-net bootstrap, SGD applied)",
-           "td_updates_per_s": 1e6 / us, "transitions_per_s": 1e6 / us * batch * world, "us_per_update": us, "batch_per_gpu": batch,
+           "td_updates_per_s": 1e6 / us, "pipelined_over_two_streams": pipelined, "transitions_per_s": 1e6 / us * batch * world, "us_per_update": us, "batch_per_gpu": batch,
            "replay_transitions_per_gpu": replay_cap,
            "grad_allreduce": ("peer-memory kernel fused with the SGD step" if fused else "nccl all_reduce + apply kernel") if world > 1 else False,
            "selfplay_eps_greedy_steps_per_s": envs * plies * world / (collect_ms * 1e-3), "selfplay_envs_per_gpu": envs,

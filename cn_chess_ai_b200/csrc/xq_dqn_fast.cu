@@ -18,6 +18,7 @@
 // FP32 master weights; BF16 only as MMA operands.  Tolerance vs the FP64 oracle: |dQ| <= 2e-3.
 #include <cuda.h>
 #include <math.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include "xq_dqn_internal.cuh"
@@ -80,6 +81,13 @@ struct Fast {
     int64_t q_cap = 0;
     float* info = nullptr;                             // 4 floats
     CUtensorMap tmW1, tmTW1, tmH, tmH2, tmD0hi, tmD0lo, tmGhi, tmGlo, tmCb;
+    // pipelined multi-update path (td_update_pipelined): the bootstrap branch [h(s') -> row-max GEMM] of update i+1 / i+2 runs on
+    // an auxiliary stream while the online branch of update i runs on the handle's stream; two slots of its buffers alternate
+    __nv_bfloat16* H2bf_b = nullptr;
+    float* zpart_b = nullptr;
+    CUtensorMap tmH2_b;
+    cudaStream_t aux = nullptr;
+    cudaEvent_t ev_fork = nullptr, ev_aux[2] = {nullptr, nullptr}, ev_free[2] = {nullptr, nullptr};
     // multi-GPU gradient exchange over peer memory (xq_dqn_dist_*): when connected, the compact gradient of an update is written
     // into slot `parity` of this rank's exchange buffer, which every peer maps through CUDA IPC
     uint8_t* exch = nullptr;                           // [2][kGradPad] FP32 gradient slots | flags[kMaxRanks] u32 | status u32
@@ -197,7 +205,8 @@ constexpr int kL0Warps = 8;
 __global__ void __launch_bounds__(kL0Warps * 32) l0_pair_kernel(BatchRef batch, int64_t n, const float* __restrict__ W0T, const float* __restrict__ b0,
                                                                const float* __restrict__ W0T2, const float* __restrict__ b02,
                                                                float* __restrict__ Hf, __nv_bfloat16* __restrict__ H2bf,
-                                                               uint32_t* __restrict__ cb, int64_t ld, float* __restrict__ zero_me, int n_zero) {
+                                                               uint32_t* __restrict__ cb, int64_t ld, float* __restrict__ zero_me, int n_zero,
+                                                               int which /* bit 0: h(s) + compact batch, bit 1: h(s') */) {
     __shared__ __align__(8) uint16_t s_rows[kL0Warps][2][96];   // any board: up to 90 occupied squares (a legal one has <= 32)
     const int wib = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int64_t s = (int64_t)blockIdx.x * kL0Warps + wib;
@@ -225,11 +234,14 @@ __global__ void __launch_bounds__(kL0Warps * 32) l0_pair_kernel(BatchRef batch, 
     __syncwarp();
     tc::pdl_wait();                 // the previous update's SGD step (W0T) and its readers of cb / the statistics slots are complete
     tc::pdl_launch_dependents();
-    if (blockIdx.x == 0) for (int i = threadIdx.x; i < n_zero; i += blockDim.x) zero_me[i] = 0.0f;
+    const bool do_a = which & 1, do_b = which & 2;              // the pipelined multi-update path runs the two halves on two streams
+    if (do_a && blockIdx.x == 0) for (int i = threadIdx.x; i < n_zero; i += blockDim.x) zero_me[i] = 0.0f;
     if (s >= n) return;
-    if (lane < 12) cb[lane * ld + s] = word;                   // word-major: the readers walk consecutive samples
-    else if (lane >= 24 && lane < 26) cb[(lane - 12) * ld + s] = word;
-    const int steps = max(cnt[0], cnt[1]);                      // <= 90; the lists are padded to a multiple of 4 with the zero row
+    if (do_a) {
+        if (lane < 12) cb[lane * ld + s] = word;               // word-major: the readers walk consecutive samples
+        else if (lane >= 24 && lane < 26) cb[(lane - 12) * ld + s] = word;
+    }
+    const int steps = max(do_a ? cnt[0] : 0, do_b ? cnt[1] : 0);    // <= 90; the lists are padded to a multiple of 4 with the zero row
     float4 a = reinterpret_cast<const float4*>(b0)[lane], b = reinterpret_cast<const float4*>(b02)[lane];
     const float4* Wa = reinterpret_cast<const float4*>(W0T) + lane;
     const float4* Wb = reinterpret_cast<const float4*>(W0T2) + lane;
@@ -239,8 +251,8 @@ __global__ void __launch_bounds__(kL0Warps * 32) l0_pair_kernel(BatchRef batch, 
         const uint32_t ia[4] = {la.x & 0xFFFFu, la.x >> 16, la.y & 0xFFFFu, la.y >> 16}, ib[4] = {lb.x & 0xFFFFu, lb.x >> 16, lb.y & 0xFFFFu, lb.y >> 16};
 #pragma unroll
         for (int u = 0; u < 4; ++u) {
-            ra[u] = Wa[(size_t)ia[u] * (kHid / 4)];
-            rb[u] = Wb[(size_t)ib[u] * (kHid / 4)];
+            ra[u] = do_a ? Wa[(size_t)ia[u] * (kHid / 4)] : make_float4(0.f, 0.f, 0.f, 0.f);
+            rb[u] = do_b ? Wb[(size_t)ib[u] * (kHid / 4)] : make_float4(0.f, 0.f, 0.f, 0.f);
         }
 #pragma unroll
         for (int u = 0; u < 4; ++u) {
@@ -248,8 +260,8 @@ __global__ void __launch_bounds__(kL0Warps * 32) l0_pair_kernel(BatchRef batch, 
             b.x += rb[u].x; b.y += rb[u].y; b.z += rb[u].z; b.w += rb[u].w;
         }
     }
-    reinterpret_cast<float4*>(Hf + s * kHid)[lane] = make_float4(tanhf(a.x), tanhf(a.y), tanhf(a.z), tanhf(a.w));
-    store_h_bf16(H2bf, s, lane, make_float4(tanhf(b.x), tanhf(b.y), tanhf(b.z), tanhf(b.w)));
+    if (do_a) reinterpret_cast<float4*>(Hf + s * kHid)[lane] = make_float4(tanhf(a.x), tanhf(a.y), tanhf(a.z), tanhf(a.w));
+    if (do_b) store_h_bf16(H2bf, s, lane, make_float4(tanhf(b.x), tanhf(b.y), tanhf(b.z), tanhf(b.w)));
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -720,7 +732,7 @@ __global__ void __launch_bounds__(kDwThreads, 1) dw_gemm_kernel(const __grid_con
     uint64_t* cfull = bars + 2 * kDwStages;   // kDwStages: board words landed
     uint64_t* acc_full = bars + 3 * kDwStages;
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 3 * kDwStages + 1);
-    __shared__ float s_db1[BM];            // the dW1 tile's CTAs: sum of delta1 per action.to over this CTA's samples
+    __shared__ float s_db1[2 * BM];        // the dW1 tile's CTAs: sum of delta1 per action.to over this CTA's samples, one row per builder warp of samples
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int mt = blockIdx.x, ks = (int)cluster_rank();     // cluster = the kDwSplits CTAs (blockIdx.y) of one row tile
@@ -775,7 +787,7 @@ __global__ void __launch_bounds__(kDwThreads, 1) dw_gemm_kernel(const __grid_con
     const int bt = threadIdx.x - 128;
     if (warp >= 4)                                             // the one-hot stages start from all-zero
         for (int u = bt; u < (int)(kDwStages * kDwABytes / 16); u += 256) reinterpret_cast<uint4*>(sA)[u] = make_uint4(0u, 0u, 0u, 0u);
-    if (threadIdx.x < BM) s_db1[threadIdx.x] = 0.0f;
+    if (threadIdx.x < 2 * BM) s_db1[threadIdx.x] = 0.0f;
     tc::tc_fence_before();
     __syncthreads();
     tc::tc_fence_after();
@@ -821,7 +833,6 @@ __global__ void __launch_bounds__(kDwThreads, 1) dw_gemm_kernel(const __grid_con
         uint32_t prev[kDwStages][3];
 #pragma unroll
         for (int a = 0; a < kDwStages; ++a) prev[a][0] = prev[a][1] = prev[a][2] = 0xFFFFFFFFu;
-        float db1_acc = 0.0f;           // dW1 tile, builder threads 128..255: db1 of row (bt - 128) over this CTA's samples (src/dqn.cu:310-319)
         for (int i0 = 0; i0 < my_kb; i0 += kDwStages) {
 #pragma unroll
             for (int st = 0; st < kDwStages; ++st) {
@@ -845,11 +856,15 @@ __global__ void __launch_bounds__(kDwThreads, 1) dw_gemm_kernel(const __grid_con
                     }
                     if (mt == kDwMTiles - 2 && grp == 3) off[2] = sw128_offset(kBiasFeat - f0, sample);      // constant-one feature -> db0
                 }
-                if (w1_tile && grp >= 2) {      // db1[r] += delta1 of the samples with action.to == r, in sample order: deterministic, no atomics
-                    const uint32_t* cw = reinterpret_cast<const uint32_t*>(sC + st * kDwCStride);              // (samples >= n read as to = 0, delta1 = 0)
-#pragma unroll 8
-                    for (int j = 0; j < BK; ++j)
-                        if ((int)XQ_ACTION_TO(cw[12 * BK + j] & 0xFFFFu) == bt - 128) db1_acc += __uint_as_float(cw[14 * BK + j]);
+                if (w1_tile && grp == 0) {      // db1[to] += delta1 (src/dqn.cu:310-319): lanes with equal `to` are summed in lane order, the lowest
+                    const int to = (int)XQ_ACTION_TO(words[12 * BK] & 0xFFFFu);          // lane of a group adds to this WARP's row -> deterministic, no atomics
+                    const float d1 = b < n ? __uint_as_float(words[14 * BK]) : 0.0f;
+                    const unsigned peers = __match_any_sync(0xFFFFFFFFu, to);
+                    float sum = 0.0f;
+#pragma unroll
+                    for (int k = 0; k < 32; ++k) { const float v = __shfl_sync(0xFFFFFFFFu, d1, k); if (peers >> k & 1u) sum += v; }
+                    if (lane == __ffs((int)peers) - 1) s_db1[(warp - 4) * BM + to] += sum;
+                    __syncwarp();
                 }
                 if (bt == 0 && i < 8) XQ_TL(1, 12 + i);
                 uint8_t* tile = sA + st * kDwABytes;
@@ -865,7 +880,6 @@ __global__ void __launch_bounds__(kDwThreads, 1) dw_gemm_kernel(const __grid_con
                 if (bt == 0 && i < 8) XQ_TL(1, 20 + i);
             }
         }
-        if (w1_tile && grp >= 2) s_db1[bt - 128] = db1_acc;
         if (warp < 8) {   // ===== epilogue: hi + lo halves out of TMEM -> this warp's 32 rows staged in shared memory (16-byte chunks
                           // XOR-swizzled by row); the whole CTA then writes coalesced 512-byte rows of the FP32 partial =====
             const int quarter = warp & 3, row = quarter * 32 + lane;
@@ -897,7 +911,7 @@ __global__ void __launch_bounds__(kDwThreads, 1) dw_gemm_kernel(const __grid_con
 #pragma unroll 4
         for (int rr = warp; rr < BM; rr += kDwThreads / 32)     // lane = 16-byte chunk of row rr
             reinterpret_cast<float4*>(out + rr * kHid)[lane] = *reinterpret_cast<const float4*>(smem + rr * (kHid * 4) + ((lane ^ rr) & 31) * 16);
-        if (w1_tile && threadIdx.x < BM) dbpart[ks * BM + threadIdx.x] = s_db1[threadIdx.x];
+        if (w1_tile && threadIdx.x < BM) dbpart[ks * BM + threadIdx.x] = s_db1[threadIdx.x] + s_db1[BM + threadIdx.x];
     }
     if (threadIdx.x == 128) XQ_TL(1, 40);
     // ===== cluster reduction + SGD: this CTA owns rows [16 ks, 16 ks + 16) of the tile =====
@@ -1170,12 +1184,14 @@ static int fast_reserve(xq_dqn_s* h, int64_t n) {
     Fast* f = h->fast;
     if (n <= f->cap) return XQ_OK;
     cudaFree(f->boards); cudaFree(f->Hbf); cudaFree(f->H2bf); cudaFree(f->Hf); cudaFree(f->zpart); cudaFree(f->cb);
+    cudaFree(f->H2bf_b); cudaFree(f->zpart_b); f->H2bf_b = nullptr; f->zpart_b = nullptr;
     cudaFree(f->d0hi); cudaFree(f->d0lo); cudaFree(f->ghi); cudaFree(f->glo);
     f->boards = nullptr; f->Hbf = f->H2bf = nullptr; f->Hf = f->zpart = nullptr; f->cb = nullptr; f->d0hi = f->d0lo = f->ghi = f->glo = nullptr; f->cap = 0;
     const int64_t rows = (n + BM - 1) / BM * BM;
     XQ_CUDA(cudaMalloc(&f->boards, sizeof(Transition) * n));
     XQ_CUDA(cudaMalloc(&f->Hbf, sizeof(__nv_bfloat16) * rows * kHid)); XQ_CUDA(cudaMalloc(&f->H2bf, sizeof(__nv_bfloat16) * rows * kHid));
     XQ_CUDA(cudaMalloc(&f->Hf, sizeof(float) * rows * kHid)); XQ_CUDA(cudaMalloc(&f->zpart, sizeof(float) * kPartsPad * rows));
+    XQ_CUDA(cudaMalloc(&f->H2bf_b, sizeof(__nv_bfloat16) * rows * kHid)); XQ_CUDA(cudaMalloc(&f->zpart_b, sizeof(float) * kPartsPad * rows));
     XQ_CUDA(cudaMalloc(&f->cb, sizeof(uint32_t) * kCbRows * rows));
     XQ_CUDA(cudaMalloc(&f->d0hi, sizeof(__nv_bfloat16) * rows * kHid)); XQ_CUDA(cudaMalloc(&f->d0lo, sizeof(__nv_bfloat16) * rows * kHid));
     XQ_CUDA(cudaMalloc(&f->ghi, sizeof(__nv_bfloat16) * rows * kHid)); XQ_CUDA(cudaMalloc(&f->glo, sizeof(__nv_bfloat16) * rows * kHid));
@@ -1190,6 +1206,7 @@ static int fast_maps(xq_dqn_s* h, int64_t n) {
     const int64_t ld = (f->cap + BM - 1) / BM * BM;
     if (int rc = make_tmap(&f->tmH, f->Hbf, n, BM)) return rc;
     if (int rc = make_tmap(&f->tmH2, f->H2bf, n, BM)) return rc;
+    if (int rc = make_tmap(&f->tmH2_b, f->H2bf_b, n, BM)) return rc;
     if (int rc = make_tmap(&f->tmD0hi, f->d0hi, kHid, kHid, n, ld)) return rc;     // delta0^T [128 hidden][n samples], row stride ld
     if (int rc = make_tmap(&f->tmD0lo, f->d0lo, kHid, kHid, n, ld)) return rc;
     if (int rc = make_tmap(&f->tmGhi, f->ghi, kHid, kHid, n, ld)) return rc;
@@ -1231,18 +1248,21 @@ int dqn_fast_weights(xq_dqn_s* h, FastWeights* out) {
 }
 void dqn_target_changed(xq_dqn_s* h) { if (h->fast) h->fast->target_current = false; }
 
-static int launch_gemm(xq_dqn_s* h, int mode, const CUtensorMap& tmA, const CUtensorMap& tmB, const float* b1, int64_t n, float* q) {
+static int launch_gemm(xq_dqn_s* h, int mode, const CUtensorMap& tmA, const CUtensorMap& tmB, const float* b1, int64_t n, float* q,
+                       cudaStream_t stream = nullptr, float* zpart = nullptr) {
     Fast* f = h->fast;
+    if (!stream) stream = h->stream;
+    if (!zpart) zpart = f->zpart;
     const int m_tiles = (int)((n + BM - 1) / BM);
     int n_splits = 148 / kNTiles;                  // 4 row splits x 37 column tiles = 148 CTAs
     if (n_splits > m_tiles) n_splits = m_tiles;
     const dim3 grid(kNTiles, n_splits);
     const int64_t zstride = (f->cap + BM - 1) / BM * BM;
     if (mode == EPI_ROWMAX)
-        XQ_CUDA(launch_pdl(l1_gemm_kernel<EPI_ROWMAX>, grid, dim3(kGemmThreads), kGemmSmem, h->stream, 1, tmA, tmB, b1, (int)n, m_tiles, n_splits,
-                           f->zpart, zstride, (float*)nullptr));
+        XQ_CUDA(launch_pdl(l1_gemm_kernel<EPI_ROWMAX>, grid, dim3(kGemmThreads), kGemmSmem, stream, 1, tmA, tmB, b1, (int)n, m_tiles, n_splits,
+                           zpart, zstride, (float*)nullptr));
     else
-        XQ_CUDA(launch_pdl(l1_gemm_kernel<EPI_STORE_TANH>, grid, dim3(kGemmThreads), kGemmSmem, h->stream, 1, tmA, tmB, b1, (int)n, m_tiles, n_splits,
+        XQ_CUDA(launch_pdl(l1_gemm_kernel<EPI_STORE_TANH>, grid, dim3(kGemmThreads), kGemmSmem, stream, 1, tmA, tmB, b1, (int)n, m_tiles, n_splits,
                            (float*)nullptr, zstride, q));
     return XQ_OK;
 }
@@ -1313,7 +1333,7 @@ int td_update_core(xq_dqn_s* h, const BatchRef& ref, int64_t n, int use_target_n
     // 1. h(s) with the online net; h(s') with the online (ChessAI::train) or target (DQN::train) net; compact batch
     XQ_CUDA(launch_pdl(l0_pair_kernel, dim3(blocks(n, kL0Warps)), dim3(kL0Warps * 32), 0, h->stream, 1, ref, n, f->W0T, f->b0,
                        use_target_net ? f->tW0T : f->W0T, use_target_net ? f->tb0 : f->b0, f->Hf, f->H2bf, f->cb, ld, f->info_slots,
-                       kInfoSlots * 4));
+                       kInfoSlots * 4, 3));
     // 2. max_a z(s')[a] over all 8100 outputs
     if (int rc = launch_gemm(h, EPI_ROWMAX, f->tmH2, use_target_net ? f->tmTW1 : f->tmW1, use_target_net ? f->tb1 : f->b1, n, nullptr)) return rc;
     // 3. TD error, delta0, delta1 h
@@ -1331,6 +1351,66 @@ int dqn_td_update_sampled(xq_dqn_s* h, const void* ring, int64_t size, uint64_t 
                           double lr, int apply) {
     const BatchRef ref{reinterpret_cast<const uint8_t*>(ring), size, seed, counter, 1};
     return td_update_core(h, ref, n, use_target_net, lr, apply);
+}
+
+// n_updates sequential TD updates on replay draws (counters counter0, counter0 + 1, ...), bit-identical to n_updates calls of
+// dqn_td_update_sampled(..., use_target_net = 1, apply = 1), but software-pipelined over two streams: between two target syncs the
+// bootstrap branch of an update -- h(s') with the TARGET net and the [B x 128] x [128 x 8100] row-max GEMM -- does not depend on the
+// online weights, so for update i+1 (and i+2) it runs on an auxiliary stream underneath update i's online branch
+// [h(s) -> TD error -> gradient contraction + SGD], which alone stays on the critical path.  Two slots of (h(s'), row-max partials).
+int dqn_td_update_pipelined(xq_dqn_s* h, const void* ring, int64_t size, uint64_t seed, uint32_t counter0, int64_t n, int n_updates, double lr) {
+    if (int rc = ensure_fast(h)) return rc;
+    if (int rc = fast_reserve(h, n)) return rc;
+    Fast* f = h->fast;
+    if (int rc = fast_maps(h, n)) return rc;
+    if (lr <= 0) lr = h->lr;
+    if (!f->aux) {
+        int lo = 0, hi = 0;
+        XQ_CUDA(cudaDeviceGetStreamPriorityRange(&lo, &hi));
+        XQ_CUDA(cudaStreamCreateWithPriority(&f->aux, cudaStreamNonBlocking, lo));       // lowest priority: the online branch is the critical path
+        XQ_CUDA(cudaEventCreateWithFlags(&f->ev_fork, cudaEventDisableTiming));
+        for (int i = 0; i < 2; ++i) { XQ_CUDA(cudaEventCreateWithFlags(&f->ev_aux[i], cudaEventDisableTiming)); XQ_CUDA(cudaEventCreateWithFlags(&f->ev_free[i], cudaEventDisableTiming)); }
+    }
+    const int64_t ld = (f->cap + BM - 1) / BM * BM;
+    cudaStream_t main = h->stream, aux = f->aux;
+    XQ_CUDA(cudaEventRecord(f->ev_fork, main));                  // the target net and the ring are final for the aux stream
+    XQ_CUDA(cudaStreamWaitEvent(aux, f->ev_fork, 0));
+    // bootstrap branch of update i into slot i & 1, in two parts.  h(s') (small CTAs) is enqueued early and runs under the online branch of
+    // update i-1; the row-max GEMM needs a whole SM's shared memory per CTA, exactly like the gradient contraction of the online branch, so it
+    // is released only when update i-1 is complete and then runs next to update i's h(s) gather (which leaves the shared memory free).
+    auto aux_l0 = [&](int i) -> int {
+        const int slot = i & 1;
+        const BatchRef ref{reinterpret_cast<const uint8_t*>(ring), size, seed, counter0 + (uint32_t)i, 1};
+        XQ_CUDA(launch_pdl(l0_pair_kernel, dim3(blocks(n, kL0Warps)), dim3(kL0Warps * 32), 0, aux, 1, ref, n, f->W0T, f->b0, f->tW0T, f->tb0, f->Hf,
+                           slot ? f->H2bf_b : f->H2bf, f->cb, ld, f->info_slots, 0, 2));
+        return XQ_OK;
+    };
+    auto aux_gemm = [&](int i) -> int {
+        const int slot = i & 1;
+        if (i >= 1) XQ_CUDA(cudaStreamWaitEvent(aux, f->ev_free[(i - 1) & 1], 0));      // update i-1 complete (so update i-2 has consumed this slot)
+        if (int rc = launch_gemm(h, EPI_ROWMAX, slot ? f->tmH2_b : f->tmH2, f->tmTW1, f->tb1, n, nullptr, aux, slot ? f->zpart_b : f->zpart)) return rc;
+        XQ_CUDA(cudaEventRecord(f->ev_aux[slot], aux));
+        return XQ_OK;
+    };
+    if (int rc = aux_l0(0)) return rc;
+    if (int rc = aux_gemm(0)) return rc;
+    for (int i = 0; i < n_updates; ++i) {
+        const int slot = i & 1;
+        const BatchRef ref{reinterpret_cast<const uint8_t*>(ring), size, seed, counter0 + (uint32_t)i, 1};
+        if (i + 1 < n_updates) if (int rc = aux_l0(i + 1)) return rc;
+        XQ_CUDA(launch_pdl(l0_pair_kernel, dim3(blocks(n, kL0Warps)), dim3(kL0Warps * 32), 0, main, 1, ref, n, f->W0T, f->b0, f->tW0T, f->tb0, f->Hf,
+                           f->H2bf, f->cb, ld, f->info_slots, kInfoSlots * 4, 1));
+        XQ_CUDA(cudaStreamWaitEvent(main, f->ev_aux[slot], 0));  // the row-max partials of this update
+        XQ_CUDA(launch_pdl(td_delta_kernel, dim3(blocks(n * 32, 256)), dim3(256), 0, main, 1, f->cb, n, f->Hf, f->W1, f->b1, slot ? f->zpart_b : f->zpart,
+                           ld, kParts, (float)h->gamma, h->mode, f->d0hi, f->d0lo, f->ghi, f->glo, ld, f->info_slots));
+        XQ_CUDA(launch_pdl(dw_gemm_kernel, dim3(kDwMTiles, kDwSplits), dim3(kDwThreads), kDwSmem, main, kDwSplits, f->tmD0hi, f->tmD0lo, f->tmGhi,
+                           f->tmGlo, f->tmCb, (int)n, f->part, f->dbpart, f->info_slots, f->info, cur_grad(f), f->W0T, f->b0, f->W1, f->b1, f->W1bf,
+                           f->W1lo, (float)lr, 1));
+        XQ_CUDA(cudaEventRecord(f->ev_free[slot], main));
+        if (i + 1 < n_updates) if (int rc = aux_gemm(i + 1)) return rc;
+    }
+    h->f64_current = false;
+    return XQ_OK;
 }
 
 }  // namespace xq

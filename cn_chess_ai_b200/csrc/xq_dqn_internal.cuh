@@ -48,4 +48,6 @@ int dqn_q90_device(xq_dqn_s* h, const xq_env_rec* envs_dev, int64_t n, float* q9
 // TD update on n uniform draws from a replay ring, resolved in place (no gather pass)
 int dqn_td_update_sampled(xq_dqn_s* h, const void* ring, int64_t size, uint64_t seed, uint32_t counter, int64_t n, int use_target_net,
                           double lr, int apply);   // brings the FP32 copies up to date and returns them   // the FP64 target parameters were rewritten
+// n_updates sequential target-net TD updates on replay draws, software-pipelined over two streams (same results as n_updates single calls)
+int dqn_td_update_pipelined(xq_dqn_s* h, const void* ring, int64_t size, uint64_t seed, uint32_t counter0, int64_t n, int n_updates, double lr);
 }

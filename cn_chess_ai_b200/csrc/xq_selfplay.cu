@@ -329,4 +329,18 @@ int xq_dqn_td_update_replay(xq_dqn_t h, xq_replay_t r, int64_t batch, uint64_t s
     return dqn_td_update_sampled(h, r->d_ring, size, seed, counter, batch, use_target_net, lr, apply);
 }
 
+int xq_dqn_td_update_replay_n(xq_dqn_t h, xq_replay_t r, int64_t batch, uint64_t seed, uint32_t counter0, int n_updates, int use_target_net,
+                              double lr) {
+    if (!h || !r || batch <= 0 || n_updates < 0) return fail(XQ_ERR_INVALID, "xq_dqn_td_update_replay_n: bad arguments");
+    if (r->device != h->device) return fail(XQ_ERR_INVALID, "xq_dqn_td_update_replay_n: handles live on different devices");
+    XQ_CUDA(cudaSetDevice(h->device));
+    const int64_t size = r->total < r->capacity ? r->total : r->capacity;
+    if (size <= 0) return fail(XQ_ERR_STATE, "xq_dqn_td_update_replay_n: the buffer is empty");
+    if (n_updates == 0) return XQ_OK;
+    if (use_target_net && n_updates > 1) return dqn_td_update_pipelined(h, r->d_ring, size, seed, counter0, batch, n_updates, lr);
+    for (int i = 0; i < n_updates; ++i)      // the online-net bootstrap depends on the previous update: nothing to pipeline
+        if (int rc = dqn_td_update_sampled(h, r->d_ring, size, seed, counter0 + (uint32_t)i, batch, use_target_net, lr, 1)) return rc;
+    return XQ_OK;
+}
+
 }  // extern "C"

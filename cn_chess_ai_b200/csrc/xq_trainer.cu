@@ -46,9 +46,11 @@ extern "C" int xq_train_run(xq_dqn_t h, xq_env_t env, xq_replay_t r, const xq_tr
         if (cfg->updates_per_round > 0) {
             int64_t size = 0;
             if ((rc = xq_replay_info(r, &size, nullptr, nullptr))) break;
-            for (int u = 0; u < cfg->updates_per_round && size > 0 && rc == XQ_OK; ++u, ++rep.updates)
-                rc = xq_dqn_td_update_replay(h, r, cfg->batch, cfg->sample_seed, (uint32_t)rep.updates, cfg->use_target_net, cfg->lr, 1);
-            if (rc) break;
+            if (size > 0) {      // counters rep.updates, +1, ...; pipelined over two streams when the bootstrap net is the target net
+                if ((rc = xq_dqn_td_update_replay_n(h, r, cfg->batch, cfg->sample_seed, (uint32_t)rep.updates, cfg->updates_per_round, cfg->use_target_net,
+                                                    cfg->lr))) break;
+                rep.updates += cfg->updates_per_round;
+            }
         }
         while (next_sync > 0 && rep.plies >= next_sync) {            // dqn->updateTargetNetwork() every target_sync_plies plies
             if ((rc = xq_dqn_sync_target(h))) break;

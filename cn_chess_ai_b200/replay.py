@@ -23,6 +23,7 @@ def _bind():
     L.xq_dqn_act.argtypes = [_P, _P, C.c_double, _P, _P]
     L.xq_selfplay_collect.argtypes = [_P, _P, _P, C.c_int, C.c_double, C.c_int]
     L.xq_dqn_td_update_replay.argtypes = [_P, _P, C.c_int64, C.c_uint64, C.c_uint32, C.c_int, C.c_double, C.c_int]
+    L.xq_dqn_td_update_replay_n.argtypes = [_P, _P, C.c_int64, C.c_uint64, C.c_uint32, C.c_int, C.c_int, C.c_double]
     _bound = True
     return L
 
@@ -93,3 +94,10 @@ def collect(dqn, env, replay, n_plies, eps=0.1, train_done=True):
 def td_update_replay(dqn, replay, batch, seed, counter, use_target_net=False, lr=0.0, apply=True):
     L = _bind()
     check(L.xq_dqn_td_update_replay(dqn.handle, replay.handle, batch, seed, counter, 1 if use_target_net else 0, lr, 1 if apply else 0))
+
+
+def td_update_replay_n(dqn, replay, batch, seed, counter0, n_updates, use_target_net=True, lr=0.0):
+    """n_updates consecutive TD updates (counters counter0, counter0 + 1, ...), software-pipelined over two streams when the
+    bootstrap comes from the target net; bit-identical to n_updates calls of td_update_replay"""
+    L = _bind()
+    check(L.xq_dqn_td_update_replay_n(dqn.handle, replay.handle, batch, seed, counter0, n_updates, 1 if use_target_net else 0, lr))

@@ -133,3 +133,31 @@ def test_td_update_from_replay_matches_host_batch(xq, O):
     w1, b1 = net1.get_params(); w2, b2 = net2.get_params()
     scale = np.abs(w2 - w).max()
     assert scale > 0 and np.abs(w1 - w2).max() <= 1e-4 * scale + 1e-9 and np.abs(b1 - b2).max() <= 1e-4 * scale + 1e-9
+
+
+def test_pipelined_updates_equal_sequential_updates(xq):
+    """xq_dqn_td_update_replay_n (bootstrap branch of update i+1 on a second stream under update i) == n single updates, bit for bit"""
+    w, b = rand_params(12)
+    env = xq.BatchedEnv(2048, seed=4)
+    rb = xq.ReplayBuffer(1 << 15)
+    nets = [xq.DQN(LAYERS, lr=1e-4) for _ in range(3)]
+    for n in nets:
+        n.set_params(w, b)
+    xq.collect(nets[0], env, rb, 12, 0.3)
+    env.sync()
+    for u in range(7):
+        xq.td_update_replay(nets[0], rb, 1500, 77, 40 + u, True, 1e-4)
+    xq.td_update_replay_n(nets[1], rb, 1500, 77, 40, 7, True, 1e-4)
+    xq.td_update_replay_n(nets[2], rb, 1500, 77, 40, 3, True, 1e-4)           # split in two calls + a target sync in between
+    xq.td_update_replay_n(nets[2], rb, 1500, 77, 43, 4, True, 1e-4)
+    p = [n.get_params() for n in nets]
+    assert np.abs(p[0][0] - w).max() > 0
+    for k in (1, 2):
+        assert p[k][0].tobytes() == p[0][0].tobytes() and p[k][1].tobytes() == p[0][1].tobytes()
+    # online-net bootstrap: the sequential fallback of the same entry point
+    a, c = xq.DQN(LAYERS, lr=1e-4), xq.DQN(LAYERS, lr=1e-4)
+    a.set_params(w, b); c.set_params(w, b)
+    for u in range(3):
+        xq.td_update_replay(a, rb, 1024, 5, u, False, 1e-4)
+    xq.td_update_replay_n(c, rb, 1024, 5, 0, 3, False, 1e-4)
+    assert a.get_params()[0].tobytes() == c.get_params()[0].tobytes()
