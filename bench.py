@@ -232,10 +232,12 @@ def main():
     pk = peaks()
     kernel_ms = ms_max / args.steps
     achieved = ALGO_BYTES_PER_STEP * E * P / (kernel_ms * 1e-3) / 1e9
-    traffic = None
+    traffic, inst_per_step = None, None
     tp = os.path.join(ROOT, "profiles", "traffic.json")
     if os.path.exists(tp):
-        traffic = json.load(open(tp)).get("rollout_slots_kernel_dram_bytes_per_launch")
+        tj = json.load(open(tp))
+        traffic = tj.get("rollout_slots_kernel_dram_bytes_per_launch")
+        inst_per_step = tj.get("rollout_slots_kernel_warp_inst_per_step")
 
     line = {"metric": "env steps/s (movegen+step, random policy)", "value": value, "unit": "steps/s", "n_gpus": world,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": kernel_ms, "higher_is_better": True, "scaling": "weak",
@@ -252,6 +254,14 @@ def main():
                          "algorithmic_bytes_per_launch": ALGO_BYTES_PER_STEP * E * P,
                          "note": "integer/latency-bound by design: boards stay on chip for all plies of a launch (DESIGN.md)"},
             "clocks": clocks}
+    if inst_per_step and clocks and clocks.get("sm_mhz"):
+        # the bound that actually binds this kernel: warp-instruction issue slots, 148 SMs x 4 schedulers x SM clock
+        issue_peak = 148 * 4 * clocks["sm_mhz"] * 1e6
+        issued = value / world * inst_per_step
+        line["roofline"]["secondary"] = {"bound": "warp-instruction issue", "achieved": issued, "peak": issue_peak, "unit": "warp-inst/s",
+                                         "frac": issued / issue_peak, "warp_inst_per_env_step": inst_per_step,
+                                         "source": "instructions per step from the ncu capture in profiles/ (smsp__inst_executed.sum / steps); "
+                                                   "peak = 148 SMs x 4 schedulers x the SM clock sampled during the run"}
 
     if rank == 0 and world == 1 and not args.no_aux:
         # BASELINE config 5 size on one GPU, for context (not the headline): 1M envs x 32 plies

@@ -48,13 +48,15 @@ def bench_dqn(stream, peaks, world=1, local=0, dist=None, envs=65536, replay_cap
     if dist is not None:
         dist.barrier()
     torch.cuda.synchronize()
-    pipelined = world == 1 and os.environ.get("XQ_TD_PIPELINE", "1") != "0"
+    pipelined = (world == 1 or fused) and os.environ.get("XQ_TD_PIPELINE", "1") != "0"
     if pipelined:
-        td_update_replay_n(net, rb, batch, 1000, 10000, warmup, True, 1e-6)      # warm the second stream / both buffer slots
+        td_update_replay_n(net, rb, batch, 1000 + local, 10000, warmup, True, 1e-6)      # warm the second stream / both buffer slots
+        if dist is not None:
+            dist.barrier()
         torch.cuda.synchronize()
     a.record(stream)
-    if pipelined:      # one call = `updates` sequential updates, the target-net branch of update i+1 under the online branch of update i
-        td_update_replay_n(net, rb, batch, 1000, warmup, updates, True, 1e-6)
+    if pipelined:      # one call = `updates` sequential updates (each with its gradient exchange when world > 1), the target-net branch of
+        td_update_replay_n(net, rb, batch, 1000 + local, warmup, updates, True, 1e-6)      # update i+1 under the online branch of update i
     else:
         for i in range(updates):
             one(warmup + i)

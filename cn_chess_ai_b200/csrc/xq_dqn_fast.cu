@@ -1353,6 +1353,8 @@ int dqn_td_update_sampled(xq_dqn_s* h, const void* ring, int64_t size, uint64_t 
     return td_update_core(h, ref, n, use_target_net, lr, apply);
 }
 
+int dqn_exchange_apply(xq_dqn_s* h, double lr);
+
 // n_updates sequential TD updates on replay draws (counters counter0, counter0 + 1, ...), bit-identical to n_updates calls of
 // dqn_td_update_sampled(..., use_target_net = 1, apply = 1), but software-pipelined over two streams: between two target syncs the
 // bootstrap branch of an update -- h(s') with the TARGET net and the [B x 128] x [128 x 8100] row-max GEMM -- does not depend on the
@@ -1405,7 +1407,8 @@ int dqn_td_update_pipelined(xq_dqn_s* h, const void* ring, int64_t size, uint64_
                            ld, kParts, (float)h->gamma, h->mode, f->d0hi, f->d0lo, f->ghi, f->glo, ld, f->info_slots));
         XQ_CUDA(launch_pdl(dw_gemm_kernel, dim3(kDwMTiles, kDwSplits), dim3(kDwThreads), kDwSmem, main, kDwSplits, f->tmD0hi, f->tmD0lo, f->tmGhi,
                            f->tmGlo, f->tmCb, (int)n, f->part, f->dbpart, f->info_slots, f->info, cur_grad(f), f->W0T, f->b0, f->W1, f->b1, f->W1bf,
-                           f->W1lo, (float)lr, 1));
+                           f->W1lo, (float)lr, f->connected ? 0 : 1));
+        if (f->connected) if (int rc = dqn_exchange_apply(h, lr)) return rc;      // multi-GPU: sum the ranks' gradients over peer memory + SGD, one kernel
         XQ_CUDA(cudaEventRecord(f->ev_free[slot], main));
         if (i + 1 < n_updates) if (int rc = aux_gemm(i + 1)) return rc;
     }
@@ -1495,6 +1498,12 @@ int xq_dqn_dist_connect(xq_dqn_t h, int rank, int world, const void* handles) {
 int xq_dqn_dist_allreduce_apply(xq_dqn_t h, double lr) {
     XQ_DQN_ENTER(h);
     if (!h->fast || !h->fast->connected) return fail(XQ_ERR_STATE, "xq_dqn_dist_allreduce_apply: not connected (xq_dqn_dist_connect)");
+    return dqn_exchange_apply(h, lr);
+}
+
+}  // extern "C" (reopened below)
+namespace xq {
+int dqn_exchange_apply(xq_dqn_s* h, double lr) {
     Fast* f = h->fast;
     if (lr <= 0) lr = h->lr;
     PeerPtrs pp;
@@ -1507,6 +1516,8 @@ int xq_dqn_dist_allreduce_apply(xq_dqn_t h, double lr) {
     h->f64_current = false;
     return XQ_OK;
 }
+}  // namespace xq
+extern "C" {
 
 int xq_dqn_dist_status(xq_dqn_t h, int* timed_out) {
     XQ_DQN_ENTER(h);

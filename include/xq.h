@@ -243,7 +243,8 @@ int xq_dqn_td_update_replay(xq_dqn_t h, xq_replay_t r, int64_t batch, uint64_t s
 /* n_updates consecutive updates, counters counter0, counter0 + 1, ...: the same result, bit for bit, as n_updates calls of
  * xq_dqn_td_update_replay(..., apply = 1).  With use_target_net != 0 the updates are software-pipelined: the bootstrap branch
  * (h(s') with the target net + the [batch x 128] x [128 x 8100] row-max GEMM) of the next updates does not depend on the online
- * weights and runs on a second stream underneath the online branch of the current one. */
+ * weights and runs on a second stream underneath the online branch of the current one.  On a handle connected to its peers
+ * (xq_dqn_dist_connect) every update exchanges its gradient: gradient kernels -> xq_dqn_dist_allreduce_apply, per update. */
 int xq_dqn_td_update_replay_n(xq_dqn_t h, xq_replay_t r, int64_t batch, uint64_t seed, uint32_t counter0, int n_updates, int use_target_net,
                               double lr);
 

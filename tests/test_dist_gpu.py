@@ -26,7 +26,7 @@ WORKER = textwrap.dedent("""
     s = torch.cuda.current_stream()
     rng = np.random.default_rng(3)
     w, b = rng.uniform(-0.05, 0.05, 1260 * 128 + 128 * 8100), rng.uniform(-0.05, 0.05, 128 + 8100)
-    nets = [xq.DQN(device=local, lr=1e-4) for _ in range(2)]
+    nets = [xq.DQN(device=local, lr=1e-4) for _ in range(3)]
     for n in nets:
         n.set_params(w, b); n.set_stream(s.cuda_stream)
     env = xq.BatchedEnv(2048, device=local, seed=5, env_id0=rank * 2048)
@@ -34,6 +34,7 @@ WORKER = textwrap.dedent("""
     rb = xq.ReplayBuffer(1 << 15, device=local)
     xq.collect(nets[0], env, rb, 12, 0.3)                  # rank-local transitions: the ranks' gradients differ
     connect_peers(nets[0], dev)
+    connect_peers(nets[2], dev)
     g1 = grad_tensor(nets[1], dev)
     for u in range(5):
         xq.td_update_replay(nets[0], rb, 1024, 100 + rank, u, True, 1e-4, apply=False)
@@ -41,11 +42,14 @@ WORKER = textwrap.dedent("""
         xq.td_update_replay(nets[1], rb, 1024, 100 + rank, u, True, 1e-4, apply=False)
         allreduce_sum_(g1)                                 # baseline: NCCL
         nets[1].apply_grads(1e-4)
+    xq.td_update_replay_n(nets[2], rb, 1024, 100 + rank, 0, 5, True, 1e-4)     # the same 5 updates, software-pipelined, exchange per update
     torch.cuda.synchronize()
-    assert not nets[0].dist_timed_out()
+    assert not nets[0].dist_timed_out() and not nets[2].dist_timed_out()
+    w2, b2 = nets[2].get_params()
     w0, b0 = nets[0].get_params(); w1, b1 = nets[1].get_params()
     assert np.abs(w0 - w).max() > 0, "the updates changed nothing"
     assert w0.tobytes() == w1.tobytes() and b0.tobytes() == b1.tobytes(), ("fused exchange differs from NCCL", float(np.abs(w0 - w1).max()))
+    assert w2.tobytes() == w0.tobytes() and b2.tobytes() == b0.tobytes(), "pipelined multi-GPU updates differ from single updates"
     digest = torch.tensor([float(np.sum(w0 * np.arange(1, w0.size + 1) %% 977)), float(b0.sum())], dtype=torch.float64, device=dev)
     all_d = [torch.empty_like(digest) for _ in range(world)]
     dist.all_gather(all_d, digest)
