@@ -141,3 +141,36 @@ def test_td_update_b1_equals_reference_backprop_step(xq, O, oracle_lib):
     scale = np.abs(w0 - w).max()
     assert np.abs((w1 - w) - (w0 - w)).max() <= 1e-2 * scale + 1e-7
     assert np.abs((b1 - b) - (b0 - b)).max() <= 1e-2 * scale + 1e-7
+
+
+def test_td_gradient_is_linear_in_the_batch_at_full_size(xq):
+    """BASELINE's batch size (4096) is beyond what the FP64 oracle finishes in seconds; the size-independent property is linearity:
+    per-sample gradients are taken at the same weights and summed, so grad(4096 transitions) == sum of grad over 8 chunks of 512
+    (each of a size the oracle tests pin).  Exercises every k-block / stage-reuse path of the gradient kernel and the in-place draws."""
+    import torch
+    from cn_chess_ai_b200.dist import grad_tensor
+    w, b = rand_params(21)
+    net = xq.DQN(LAYERS, lr=1e-3)
+    net.set_params(w, b)
+    env = xq.BatchedEnv(4096, seed=13)
+    rb = xq.ReplayBuffer(1 << 16)
+    xq.collect(net, env, rb, 16, 0.5)
+    env.sync()
+    ring = rb.get()
+    idx = ((np.arange(4096) * 2654435761) % len(ring)).astype(np.int64)
+    batch = ring[idx]
+    dev = torch.device("cuda", 0)
+    stage = torch.from_numpy(batch.view(np.uint8).reshape(4096, 128)).to(dev)
+
+    def grad_of(first, count):
+        net.td_update_device(stage[first:first + count].data_ptr(), count, use_target_net=True, lr=1e-3, apply=False)
+        net.sync()
+        return grad_tensor(net, dev).double().cpu().numpy().copy()
+
+    full = grad_of(0, 4096)
+    parts = sum(grad_of(k * 512, 512) for k in range(8))
+    scale = np.abs(full).max()
+    assert scale > 0 and np.isfinite(full).all()
+    assert np.abs(full - parts).max() <= 2e-5 * scale, (np.abs(full - parts).max(), scale)
+    w1, b1 = net.get_params()
+    assert w1.tobytes() == w.astype(np.float32).astype(np.float64).tobytes() or np.abs(w1 - w).max() < 1e-7      # apply=False changed nothing
