@@ -51,6 +51,15 @@ __device__ __forceinline__ uint32_t bytes_lt(uint32_t qw, uint32_t q) {
     return ((t & 0x80808080u) >> 7) * 0xFFu;
 }
 
+// -DXQ_TIMELINE: cycles every warp (= piece slot) of block 0 spends in the four phases of a ply and at the three barriers,
+// summed over the plies of the launch (profiling builds only; scripts/tl_rollout.py reads them through xq_debug_rollout_phases)
+#ifdef XQ_TIMELINE
+__device__ long long g_phase[16][8];
+#define XQ_PH(k) do { if (blockIdx.x == 0 && lane == 0) { const long long t_ = clock64(); g_phase[slot][k] += t_ - ph_t; ph_t = t_; } } while (0)
+#else
+#define XQ_PH(k) ((void)0)
+#endif
+
 struct SlotState {
     int sq_red, sq_black;
     Bits90 red, black, occT;
@@ -156,6 +165,10 @@ __global__ void __launch_bounds__(kB * kS) rollout_slots_kernel(xq_env_rec* __re
     uint8_t* pubc8 = reinterpret_cast<uint8_t*>(s_pubc);
     const int pub_off = (slot >> 2) * (kB * 4) + lane * 4 + (slot & 3);
 
+#ifdef XQ_TIMELINE
+    long long ph_t = clock64();
+    if (blockIdx.x == 0 && lane == 0) for (int k = 0; k < 8; ++k) g_phase[slot][k] = 0;
+#endif
     for (int p = 0; p < n_plies; ++p) {
         // ---- A: count my moves, publish (square, count) ------------------------------------
         int myq = kDeadSq, cnt = 0;
@@ -172,7 +185,9 @@ __global__ void __launch_bounds__(kB * kS) rollout_slots_kernel(xq_env_rec* __re
             pubc8[pub_off] = (uint8_t)cnt;
             if (slot == 0) s_cap[(p & 1) * kB + lane] = 0;
         }
+        XQ_PH(0);
         __syncthreads();
+        XQ_PH(1);
         // ---- B: reference-order prefix, list size, draw, owner decodes ------------------------
         int total = 0;
         if (active) {
@@ -197,7 +212,9 @@ __global__ void __launch_bounds__(kB * kS) rollout_slots_kernel(xq_env_rec* __re
                 }
             }
         }
+        XQ_PH(2);
         __syncthreads();
+        XQ_PH(3);
         // ---- C: apply the move to the replicated state ------------------------------------------
         int from = 0, to = 0, mover = 0;
         bool took_general = false;
@@ -219,7 +236,9 @@ __global__ void __launch_bounds__(kB * kS) rollout_slots_kernel(xq_env_rec* __re
             else { st.red.andnot(fm); st.red.or_with(tm); st.black.andnot(tm); took_general = to == st.gen_black; if (from == st.gen_red) st.gen_red = to; }
             st.move_count++; st.player ^= 1; st.ctr++;
         }
+        XQ_PH(4);
         __syncthreads();
+        XQ_PH(5);
         // ---- D: scores, reward, terminal, outputs ----------------------------------------------
         if (active) {
             uint32_t tr0 = 0, capcode = 0; int reward = 0;
@@ -247,6 +266,7 @@ __global__ void __launch_bounds__(kB * kS) rollout_slots_kernel(xq_env_rec* __re
             if (slot == 0 && trace)   // flags bits 4-7 = captured piece code (published by the captured slot)
                 reinterpret_cast<uint2*>(trace)[(int64_t)p * n + env] = make_uint2(tr0 | (capcode << 28), (uint32_t)reward);
         }
+        XQ_PH(6);
     }
 
     // ---- store: slots -> nibble board -----------------------------------------------------------
@@ -290,3 +310,10 @@ cudaError_t launch_rollout_slots(xq_env_rec* envs, int64_t n, uint64_t env_id0, 
 }
 
 }  // namespace xq
+
+#ifdef XQ_TIMELINE
+extern "C" int xq_debug_rollout_phases(long long* out_host) {   // profiling builds only: [16 slots][8]
+    if (cudaDeviceSynchronize() != cudaSuccess) return XQ_ERR_CUDA;
+    return cudaMemcpyFromSymbol(out_host, xq::g_phase, sizeof(long long) * 16 * 8) == cudaSuccess ? XQ_OK : XQ_ERR_CUDA;
+}
+#endif
