@@ -38,8 +38,8 @@ __device__ __forceinline__ Bits90 open_occT() { return Bits90{0x649A1649u, 0x980
 
 // n % d for n < 2^31, 1 <= d <= 128 without a hardware divide: q = umulhi(n, ceil(2^32/d)) is floor(n/d) or one above
 // (error < n*d/2^32 < 1), so one conditional fix-up makes the remainder exact.
-__device__ __forceinline__ uint32_t mod_small(uint32_t n, uint32_t d) {
-    const uint32_t magic = (0xFFFFFFFFu / d) + 1u;      // ceil(2^32/d) for d not a power of two; 2^32/d for powers of two (d >= 2)
+__device__ __forceinline__ uint32_t mod_magic(uint32_t d) { return (0xFFFFFFFFu / d) + 1u; }   // ceil(2^32/d) (2^32/d for powers of two, d >= 2)
+__device__ __forceinline__ uint32_t mod_small(uint32_t n, uint32_t d, uint32_t magic) {          // magic = mod_magic(d), tabulated by the kernel
     const uint32_t q = __umulhi(n, magic);
     const int32_t r = (int32_t)(n - q * d);
     return d == 1 ? 0u : (uint32_t)(r < 0 ? r + (int32_t)d : r);
@@ -65,17 +65,15 @@ struct SlotState {
     Bits90 red, black, occT;
     int gen_red, gen_black;
     int move_count, player;
-    int red_score, black_score, mat_red, mat_black;
     uint32_t ctr;
     __device__ __forceinline__ void reset(int slot) {
         sq_red = kOpenSq[slot]; sq_black = kOpenSq[16 + slot];
         red = open_red(); black = open_black(); occT = open_occT();
         gen_red = 4; gen_black = 85; move_count = 0; player = RED;
-        red_score = black_score = 0; mat_red = mat_black = 1480;
     }
 };
 
-__global__ void __launch_bounds__(kB * kS) rollout_slots_kernel(xq_env_rec* __restrict__ envs, int64_t n, uint64_t env_id0, uint64_t seed,
+__global__ void __launch_bounds__(kB * kS, 2) rollout_slots_kernel(xq_env_rec* __restrict__ envs, int64_t n, uint64_t env_id0, uint64_t seed,
                                                                 int n_plies, xq_trace_rec* __restrict__ trace,
                                                                 xq_env_stats* __restrict__ stats, uint8_t* __restrict__ nonstd) {
     __shared__ uint8_t s_slot[32 * kB];        // [slot 0..31][board]   load/store conversion
@@ -87,10 +85,12 @@ __global__ void __launch_bounds__(kB * kS) rollout_slots_kernel(xq_env_rec* __re
     __shared__ uint32_t s_move[kB];
     __shared__ uint32_t s_cap[2 * kB];
     __shared__ uint8_t s_active[kB];
+    __shared__ uint32_t s_magic[XQ_MAX_ACTIONS + 1];   // mod_magic(d) for every possible list size: one shared load instead of a division per ply
 
     const int tid = threadIdx.x, lane = tid & 31, slot = tid >> 5;
     const int64_t env = (int64_t)blockIdx.x * kB + lane;
     const int type = slot_type(slot);
+    if (tid >= 1 && tid <= XQ_MAX_ACTIONS) s_magic[tid] = mod_magic((uint32_t)tid);
 
     // ---- load: warp 0 converts 32 records to slots + bitboards -------------------------------
     if (slot == 0) {
@@ -137,6 +137,7 @@ __global__ void __launch_bounds__(kB * kS) rollout_slots_kernel(xq_env_rec* __re
     const bool active = s_active[lane] != 0;
     SlotState st;
     st.reset(slot);
+    int bk_red = 0, bk_black = 0, bk_mat_red = 1480, bk_mat_black = 1480;      // scores / material: used by slot 0 only (see below)
     uint64_t rng_base = 0;
     if (active) {
         st.sq_red = s_slot[slot * kB + lane]; st.sq_black = s_slot[(16 + slot) * kB + lane];
@@ -146,7 +147,7 @@ __global__ void __launch_bounds__(kB * kS) rollout_slots_kernel(xq_env_rec* __re
         st.gen_red = s_slot[8 * kB + lane]; st.gen_black = s_slot[24 * kB + lane];
         const uint32_t m0 = s_meta[0 * kB + lane];
         st.move_count = m0 & 0xFFFF; st.player = (m0 >> 16) & 0xFF;
-        st.red_score = (int)s_meta[1 * kB + lane]; st.black_score = (int)s_meta[2 * kB + lane]; st.ctr = s_meta[3 * kB + lane];
+        bk_red = (int)s_meta[1 * kB + lane]; bk_black = (int)s_meta[2 * kB + lane]; st.ctr = s_meta[3 * kB + lane];
         // material per side from the slots (ChessAI::evaluateBoard :313-341)
         int mr = 0, mb = 0;
         for (int i = 0; i < 16; ++i) {
@@ -154,9 +155,12 @@ __global__ void __launch_bounds__(kB * kS) rollout_slots_kernel(xq_env_rec* __re
             if (s_slot[i * kB + lane] != kDeadSq) mr += sc;
             if (s_slot[(16 + i) * kB + lane] != kDeadSq) mb += sc;
         }
-        st.mat_red = mr; st.mat_black = mb;
+        bk_mat_red = mr; bk_mat_black = mb;
         // a finished board is never stepped (chessai.cpp:90,96): restart it
-        if (st.move_count >= XQ_MAX_MOVES || st.gen_red == kDeadSq || st.gen_black == kDeadSq) { const uint32_t c = st.ctr; st.reset(slot); st.ctr = c; }
+        if (st.move_count >= XQ_MAX_MOVES || st.gen_red == kDeadSq || st.gen_black == kDeadSq) {
+            const uint32_t c = st.ctr; st.reset(slot); st.ctr = c;
+            bk_red = bk_black = 0; bk_mat_red = bk_mat_black = 1480;
+        }
         rng_base = seed + (env_id0 + (uint64_t)env) * 0x9E3779B97F4A7C15ull;
     }
     uint32_t a_steps = 0, a_games = 0, a_red = 0, a_black = 0, a_capg = 0, a_caps = 0, a_legal = 0;   // per launch: n_plies < 2^24
@@ -165,6 +169,35 @@ __global__ void __launch_bounds__(kB * kS) rollout_slots_kernel(xq_env_rec* __re
     uint8_t* pubc8 = reinterpret_cast<uint8_t*>(s_pubc);
     const int pub_off = (slot >> 2) * (kB * 4) + lane * 4 + (slot & 3);
 
+    // Bookkeeping of a ply (scores, material, reward, statistics, trace record) belongs to slot 0 alone and runs ONE BARRIER LATE:
+    // the captured slot publishes its piece value in phase C of ply p, slot 0 picks it up after the first barrier of ply p+1 (or after
+    // the closing barrier).  Terminal test and winner need no captured value, so no thread waits for the scores: 2 barriers per ply.
+    // pending ply, packed: kind (0 none, 1 a move, 2 no legal action) | mover << 2 | over << 3 | win << 4 | move_count << 8 | total << 16
+    uint32_t pend = 0, pend_tr0 = 0;
+    int pend_p = 0;
+    auto finalize = [&]() {
+        if (pend == 0) return;
+        const int pend_mover = (pend >> 2) & 1, pend_win = (pend >> 4) & 3, pend_mc = (pend >> 8) & 0xFF, pend_total = pend >> 16;
+        const bool pend_over = (pend >> 3) & 1;
+        uint32_t capcode = 0; int reward = 0;
+        if ((pend & 3) == 1) {
+            const uint32_t capw = s_cap[(pend_p & 1) * kB + lane];
+            const int capscore = (int)(capw & 0xFFFFu);
+            capcode = capw >> 16;
+            if (capscore) {
+                if (pend_mover == RED) { bk_red += capscore; bk_mat_black -= capscore; } else { bk_black += capscore; bk_mat_red -= capscore; }
+            }
+            reward = reward_from_material(pend_mover == RED ? bk_mat_red - bk_mat_black : bk_mat_black - bk_mat_red, pend_mc);
+            a_steps++; a_legal += pend_total; a_reward += reward; if (capscore) a_caps++;
+            if (pend_over) { a_games++; if (pend_win == RED) a_red++; else a_black++; if (pend_mc < XQ_MAX_MOVES) a_capg++; }
+        } else {
+            a_games++;
+        }
+        if (trace)   // flags bits 4-7 = captured piece code (published by the captured slot)
+            reinterpret_cast<uint2*>(trace)[(int64_t)pend_p * n + env] = make_uint2(pend_tr0 | (capcode << 28), (uint32_t)reward);
+        if ((pend & 3) == 2 || pend_over) { bk_red = bk_black = 0; bk_mat_red = bk_mat_black = 1480; }     // ChessBoard::reset
+        pend = 0;
+    };
 #ifdef XQ_TIMELINE
     long long ph_t = clock64();
     if (blockIdx.x == 0 && lane == 0) for (int k = 0; k < 8; ++k) g_phase[slot][k] = 0;
@@ -190,6 +223,7 @@ __global__ void __launch_bounds__(kB * kS) rollout_slots_kernel(xq_env_rec* __re
         XQ_PH(1);
         // ---- B: reference-order prefix, list size, draw, owner decodes ------------------------
         int total = 0;
+        if (slot == 0 && active) finalize();       // the previous ply's scores / reward / trace (its captured value is visible now)
         if (active) {
             uint32_t prefix = 0, tot = 0;
 #pragma unroll
@@ -204,7 +238,7 @@ __global__ void __launch_bounds__(kB * kS) rollout_slots_kernel(xq_env_rec* __re
                 z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ull;
                 z = (z ^ (z >> 27)) * 0x94D049BB133111EBull;
                 z ^= z >> 31;
-                const uint32_t k = mod_small((uint32_t)(z >> 33), tot);
+                const uint32_t k = mod_small((uint32_t)(z >> 33), tot, s_magic[tot]);
                 if (cnt > 0 && k >= prefix && k < prefix + (uint32_t)cnt) {
                     int to = 0;
                     piece_moves_dyn(type, P, myq, st.player, (int)(k - prefix), &to);
@@ -215,58 +249,42 @@ __global__ void __launch_bounds__(kB * kS) rollout_slots_kernel(xq_env_rec* __re
         XQ_PH(2);
         __syncthreads();
         XQ_PH(3);
-        // ---- C: apply the move to the replicated state ------------------------------------------
-        int from = 0, to = 0, mover = 0;
-        bool took_general = false;
-        if (active && total > 0) {
-            const uint32_t mv = s_move[lane];
-            from = mv & 0xFF; to = (mv >> 8) & 0xFF;
-            mover = st.player;
-            const int oq = mover ? st.sq_red : st.sq_black;          // my piece of the side NOT moving
-            if (oq == to) {                                          // it is captured
-                s_cap[(p & 1) * kB + lane] = (uint32_t)piece_score(type) | ((uint32_t)(type + (mover ? 0 : 7)) << 16);   // value | code
-                if (mover) st.sq_red = kDeadSq; else st.sq_black = kDeadSq;
-            }
-            if (myq == from) { if (mover) st.sq_black = to; else st.sq_red = to; }
-            const int fr = row_of(from), tr = row_of(to);
-            const Bits90 fm = Bits90::bit(from), tm = Bits90::bit(to);
-            st.occT.andnot(Bits90::bit(cm_index(fr, from - 9 * fr)));
-            st.occT.or_with(Bits90::bit(cm_index(tr, to - 9 * tr)));
-            if (mover) { st.black.andnot(fm); st.black.or_with(tm); st.red.andnot(tm); took_general = to == st.gen_red; if (from == st.gen_black) st.gen_black = to; }
-            else { st.red.andnot(fm); st.red.or_with(tm); st.black.andnot(tm); took_general = to == st.gen_black; if (from == st.gen_red) st.gen_red = to; }
-            st.move_count++; st.player ^= 1; st.ctr++;
-        }
-        XQ_PH(4);
-        __syncthreads();
-        XQ_PH(5);
-        // ---- D: scores, reward, terminal, outputs ----------------------------------------------
+        // ---- C: apply the move to the replicated state; the captured slot publishes its piece ---------
         if (active) {
-            uint32_t tr0 = 0, capcode = 0; int reward = 0;
             if (total > 0) {
-                const uint32_t capw = s_cap[(p & 1) * kB + lane];
-                const int capscore = (int)(capw & 0xFFFFu);
-                capcode = capw >> 16;
-                if (capscore) {
-                    if (mover == RED) { st.red_score += capscore; st.mat_black -= capscore; } else { st.black_score += capscore; st.mat_red -= capscore; }
+                const uint32_t mv = s_move[lane];
+                const int from = mv & 0xFF, to = (mv >> 8) & 0xFF;
+                const int mover = st.player;
+                const int oq = mover ? st.sq_red : st.sq_black;          // my piece of the side NOT moving
+                if (oq == to) {                                          // it is captured
+                    s_cap[(p & 1) * kB + lane] = (uint32_t)piece_score(type) | ((uint32_t)(type + (mover ? 0 : 7)) << 16);   // value | code
+                    if (mover) st.sq_red = kDeadSq; else st.sq_black = kDeadSq;
                 }
-                reward = reward_from_material(mover == RED ? st.mat_red - st.mat_black : st.mat_black - st.mat_red, st.move_count);
+                if (myq == from) { if (mover) st.sq_black = to; else st.sq_red = to; }
+                const int fr = row_of(from), tr = row_of(to);
+                const Bits90 fm = Bits90::bit(from), tm = Bits90::bit(to);
+                st.occT.andnot(Bits90::bit(cm_index(fr, from - 9 * fr)));
+                st.occT.or_with(Bits90::bit(cm_index(tr, to - 9 * tr)));
+                bool took_general;
+                if (mover) { st.black.andnot(fm); st.black.or_with(tm); st.red.andnot(tm); took_general = to == st.gen_red; if (from == st.gen_black) st.gen_black = to; }
+                else { st.red.andnot(fm); st.red.or_with(tm); st.black.andnot(tm); took_general = to == st.gen_black; if (from == st.gen_red) st.gen_red = to; }
+                st.move_count++; st.player ^= 1; st.ctr++;
+                // terminal test and winner need no captured VALUE: every thread decides locally, the scores follow one barrier later
                 const bool over = took_general || st.move_count >= XQ_MAX_MOVES;
-                // getWinner: colour of the first General in square order
-                const int win = took_general ? mover : (st.gen_red < st.gen_black ? RED : BLACK);
                 if (slot == 0) {
-                    a_steps++; a_legal += total; a_reward += reward; if (capscore) a_caps++;
-                    if (over) { a_games++; if (win == RED) a_red++; else a_black++; if (st.move_count < XQ_MAX_MOVES) a_capg++; }
-                    tr0 = (uint32_t)XQ_ACTION(from, to) | ((uint32_t)total << 16) | ((uint32_t)((over ? 1 : 0) | ((over ? win : NOCOLOR) << 1)) << 24);
+                    // getWinner: colour of the first General in square order
+                    const int win = took_general ? mover : (st.gen_red < st.gen_black ? RED : BLACK);
+                    pend = 1u | ((uint32_t)mover << 2) | ((uint32_t)over << 3) | ((uint32_t)win << 4) | ((uint32_t)st.move_count << 8) | ((uint32_t)total << 16);
+                    pend_p = p;
+                    pend_tr0 = (uint32_t)XQ_ACTION(from, to) | ((uint32_t)total << 16) | ((uint32_t)((over ? 1 : 0) | ((over ? win : NOCOLOR) << 1)) << 24);
                 }
                 if (over) { const uint32_t c = st.ctr; st.reset(slot); st.ctr = c; }
             } else {   // no legal action: the episode loop ends (chessai.cpp:100-103); the slot restarts
                 const uint32_t c = st.ctr + 1; st.reset(slot); st.ctr = c;
-                if (slot == 0) { a_games++; tr0 = (uint32_t)XQ_ACTION_NONE | ((uint32_t)(1 | (NOCOLOR << 1)) << 24); }
+                if (slot == 0) { pend = 2; pend_p = p; pend_tr0 = (uint32_t)XQ_ACTION_NONE | ((uint32_t)(1 | (NOCOLOR << 1)) << 24); }
             }
-            if (slot == 0 && trace)   // flags bits 4-7 = captured piece code (published by the captured slot)
-                reinterpret_cast<uint2*>(trace)[(int64_t)p * n + env] = make_uint2(tr0 | (capcode << 28), (uint32_t)reward);
         }
-        XQ_PH(6);
+        XQ_PH(4);
     }
 
     // ---- store: slots -> nibble board -----------------------------------------------------------
@@ -274,6 +292,7 @@ __global__ void __launch_bounds__(kB * kS) rollout_slots_kernel(xq_env_rec* __re
     __syncthreads();
     if (slot == 0) {
         if (active) {
+            finalize();                           // the last ply
             for (int i = 0; i < 12; ++i) s_words[i * kB + lane] = 0;
             for (int i = 0; i < 32; ++i) {
                 const int q = s_slot[i * kB + lane];
@@ -285,8 +304,7 @@ __global__ void __launch_bounds__(kB * kS) rollout_slots_kernel(xq_env_rec* __re
                 rec[i] = make_uint4(s_words[(4 * i) * kB + lane], s_words[(4 * i + 1) * kB + lane], s_words[(4 * i + 2) * kB + lane],
                                     s_words[(4 * i + 3) * kB + lane]);
             const uint32_t flags = s_meta[0 * kB + lane] & 0xFF000000u;
-            rec[3] = make_uint4((uint32_t)(st.move_count & 0xFFFF) | ((uint32_t)st.player << 16) | flags, (uint32_t)st.red_score,
-                                (uint32_t)st.black_score, st.ctr);
+            rec[3] = make_uint4((uint32_t)(st.move_count & 0xFFFF) | ((uint32_t)st.player << 16) | flags, (uint32_t)bk_red, (uint32_t)bk_black, st.ctr);
         }
         if (stats) {
             unsigned long long v[8] = {a_steps, a_games, a_red, a_black, a_capg, a_caps, (unsigned long long)a_reward, a_legal};   // zero-extended counters
