@@ -21,3 +21,9 @@ print("pipelined us/update", 1e3 * t(lambda: xq.td_update_replay_n(net, rb, 4096
 def seq():
     for i in range(N): xq.td_update_replay(net, rb, 4096, 5, 100 + i, True, 1e-6)
 print("sequential us/update", 1e3 * t(seq) / N)
+import time
+torch.cuda.synchronize()
+t0 = time.perf_counter(); xq.td_update_replay_n(net, rb, 4096, 5, 300, N, True, 1e-6); t1 = time.perf_counter(); torch.cuda.synchronize(); t2 = time.perf_counter()
+print("pipelined: CPU enqueue us/update", 1e6 * (t1 - t0) / N, " total us/update", 1e6 * (t2 - t0) / N)
+t0 = time.perf_counter(); seq(); t1 = time.perf_counter(); torch.cuda.synchronize(); t2 = time.perf_counter()
+print("sequential: CPU enqueue us/update", 1e6 * (t1 - t0) / N, " total us/update", 1e6 * (t2 - t0) / N)
