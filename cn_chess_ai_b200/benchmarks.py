@@ -4,6 +4,14 @@ import numpy as np
 FLOP_PER_TRANSITION = 9_262_080      # fwd Q(s) + fwd Q'(s') + dense bwd of the {1260,128,8100} MLP
 
 
+def _td_traffic():
+    """DRAM bytes of one TD update from the ncu capture in profiles/ (None if the file is absent)"""
+    import json
+    import os
+    p = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "profiles", "traffic.json")
+    return json.load(open(p)).get("td_update_dram_bytes_per_update") if os.path.exists(p) else None
+
+
 def bench_dqn(stream, peaks, world=1, local=0, dist=None, envs=65536, replay_cap=1 << 20, batch=4096, updates=30, warmup=5):
     """BASELINE configs 3+4 on this rank: eps-greedy self-play with batched Q-net inference fills a 1M-transition
     replay ring, then batch-4096 TD updates (per GPU) are timed with CUDA events on `stream`.
@@ -79,7 +87,7 @@ def bench_dqn(stream, peaks, world=1, local=0, dist=None, envs=65536, replay_cap
            "grad_allreduce": ("peer-memory kernel fused with the SGD step" if fused else "nccl all_reduce + apply kernel") if world > 1 else False,
            "selfplay_eps_greedy_steps_per_s": envs * plies * world / (collect_ms * 1e-3), "selfplay_envs_per_gpu": envs,
            "roofline": {"bound": "tensor", "achieved": tflops, "peak": peaks["bf16_tflops"], "unit": "TFLOP/s", "frac": tflops / peaks["bf16_tflops"],
-                        "traffic": None, "peak_source": peaks["source"],
+                        "traffic": _td_traffic(), "peak_source": peaks["source"],
                         "note": "achieved = ALGORITHMIC dense FLOPs (9,262,080 per transition) / time of the whole update (4 kernels chained by programmatic dependent launch, replay draws resolved in place); "
                                 "the kernels exploit the one-hot input and one-hot TD error, so far fewer FLOPs are issued (DESIGN.md)"}}
     env.close(); net.close(); rb.close()
