@@ -201,7 +201,7 @@ __global__ void __launch_bounds__(256) l0_act_kernel(const xq_env_rec* __restric
 // each in flight, ~9 instructions per piece.  The warp also writes the compact batch record (board of s, action,
 // reward, done; word-major) that the later kernels of the update read: the replay ring is touched here only.
 // Block 0 clears db1 and the loss statistics (td_delta_kernel accumulates into them).
-constexpr int kL0Warps = 8;
+constexpr int kL0Warps = 4;
 __global__ void __launch_bounds__(kL0Warps * 32) l0_pair_kernel(BatchRef batch, int64_t n, const float* __restrict__ W0T, const float* __restrict__ b0,
                                                                const float* __restrict__ W0T2, const float* __restrict__ b02,
                                                                float* __restrict__ Hf, __nv_bfloat16* __restrict__ H2bf,
