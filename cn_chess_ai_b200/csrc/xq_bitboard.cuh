@@ -1,4 +1,4 @@
-// xq_bitboard.cuh -- per-piece move COUNT and k-th-move DECODE on 90-bit occupancy bitboards.
+// xq_bitboard.cuh -- per-piece move COUNT (+ a 32-bit descriptor) and k-th-move DECODE (from the descriptor) on 90-bit occupancy bitboards.
 //
 // Used by the slot-parallel rollout kernel (xq_rollout.cu): one thread owns one piece, warps are
 // piece-type uniform, so every function here runs without divergence across a warp.  Sliders are
@@ -80,29 +80,41 @@ XQ_HD Ray ray_down(uint32_t L, int p, int) {       // towards lower index
 
 // Sliders.  IS_CANNON: capture target is the SECOND blocker (src/chessboard.cpp:220-246, :399-421),
 // else the first (:198-218, :382-397).  Ray order E, W, S(row+1), N = (0,1),(0,-1),(1,0),(-1,0).
-// Returns the count; when want >= 0 also writes the want-th destination (reference order) to *to.
+// The generator runs ONCE per ply: it returns the count and a 32-bit DESCRIPTOR -- per ray k a byte
+// (number of empty squares before the first blocker) | (distance of the capture square, 0 = none) << 4 --
+// from which the k-th destination (reference order) is decoded without touching the board again.
 template <bool IS_CANNON>
-XQ_HD int slider(const Pos& P, int sq, int want, int* to) {
+XQ_HD int slider_desc(const Pos& P, int sq, uint32_t* desc) {
     const int r = row_of(sq), c = sq - 9 * r;
     const uint32_t rank = P.occ.field(9 * r, 9), file = P.occT.field(10 * c, 10);
     int total = 0;
+    uint32_t d = 0;
 #pragma unroll
     for (int k = 0; k < 4; ++k) {
         const bool horiz = k < 2;
-        const Ray ray = (k & 1) ? ray_down(horiz ? rank : file, horiz ? c : r, horiz ? 9 : 10)
-                                : ray_up(horiz ? rank : file, horiz ? c : r, horiz ? 9 : 10);
+        const int p = horiz ? c : r;
+        const Ray ray = (k & 1) ? ray_down(horiz ? rank : file, p, horiz ? 9 : 10)
+                                : ray_up(horiz ? rank : file, p, horiz ? 9 : 10);
         const int tgt = IS_CANNON ? ray.second : ray.first;
-        int capsq = -1;
-        if (tgt >= 0) { const int s = horiz ? 9 * r + tgt : 9 * tgt + c; if (!P.own.test(s)) capsq = s; }
-        const int cnt = ray.empties + (capsq >= 0 ? 1 : 0);
-        if (want >= total && want < total + cnt) {
-            const int j = want - total;
-            const int step = horiz ? ((k & 1) ? -1 : 1) : ((k & 1) ? -9 : 9);
-            *to = j < ray.empties ? sq + step * (j + 1) : capsq;
-        }
-        total += cnt;
+        int capdist = 0;
+        if (tgt >= 0) { const int s = horiz ? 9 * r + tgt : 9 * tgt + c; if (!P.own.test(s)) capdist = (k & 1) ? p - tgt : tgt - p; }
+        d |= ((uint32_t)ray.empties | ((uint32_t)capdist << 4)) << (8 * k);
+        total += ray.empties + (capdist ? 1 : 0);
     }
+    *desc = d;
     return total;
+}
+XQ_HD int slider_decode(uint32_t desc, int sq, int want) {
+    int to = sq;
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+        const int e = (desc >> (8 * k)) & 15, capdist = (desc >> (8 * k + 4)) & 15;
+        const int cnt = e + (capdist ? 1 : 0);
+        const int step = k == 0 ? 1 : (k == 1 ? -1 : (k == 2 ? 9 : -9));
+        if (want >= 0 && want < cnt) to = sq + step * (want < e ? want + 1 : capdist);
+        want -= cnt;                      // once negative it stays negative: exactly one ray matches
+    }
+    return to;
 }
 
 // Leapers: bit k of the returned mask = direction k (reference order) is playable; dest[k] squares
@@ -178,42 +190,64 @@ XQ_HD int nth_set_bit(uint32_t m, int j) {
     return ffs32(m) - 1;
 }
 
-// Uniform entry point: count of moves of the piece of `type`/`color` on `sq`, and (want >= 0) the
-// want-th destination in reference order.
+// Uniform entry points.  piece_count<TYPE>: number of moves of the piece of `type` / `color` on `sq` plus the descriptor
+// (sliders: see slider_desc; leapers: the direction mask).  piece_decode<TYPE>: the want-th destination in reference
+// order from the descriptor alone.
 template <int TYPE>
-XQ_HD int piece_moves(const Pos& P, int sq, int color, int want, int* to) {
-    if (TYPE == CHARIOT) return slider<false>(P, sq, want, to);
-    if (TYPE == CANNON) return slider<true>(P, sq, want, to);
+XQ_HD int piece_count(const Pos& P, int sq, int color, uint32_t* desc) {
+    if (TYPE == CHARIOT) return slider_desc<false>(P, sq, desc);
+    if (TYPE == CANNON) return slider_desc<true>(P, sq, desc);
     uint32_t m;
     if (TYPE == GENERAL) m = general_mask(P, sq);
     else if (TYPE == ADVISOR) m = advisor_mask(P, sq, color);
     else if (TYPE == ELEPHANT) m = elephant_mask(P, sq, color);
     else if (TYPE == HORSE) m = horse_mask(P, sq);
     else m = soldier_mask(P, sq, color);
-    if (want >= 0) {
-        const int k = nth_set_bit(m, want);
-        int d;
-        if (TYPE == GENERAL) d = general_dir(k);
-        else if (TYPE == ADVISOR) d = advisor_dir(k);
-        else if (TYPE == ELEPHANT) d = elephant_dir(k);
-        else if (TYPE == HORSE) d = horse_dir(k);
-        else d = soldier_dir(k, color);
-        *to = sq + d;
-    }
+    *desc = m;
     return popc32(m);
 }
+template <int TYPE>
+XQ_HD int piece_decode(uint32_t desc, int sq, int color, int want) {
+    if (TYPE == CHARIOT || TYPE == CANNON) return slider_decode(desc, sq, want);
+    const int k = nth_set_bit(desc, want);
+    int d;
+    if (TYPE == GENERAL) d = general_dir(k);
+    else if (TYPE == ADVISOR) d = advisor_dir(k);
+    else if (TYPE == ELEPHANT) d = elephant_dir(k);
+    else if (TYPE == HORSE) d = horse_dir(k);
+    else d = soldier_dir(k, color);
+    return sq + d;
+}
 
-XQ_HD int piece_moves_dyn(int type, const Pos& P, int sq, int color, int want, int* to) {
+XQ_HD int piece_count_dyn(int type, const Pos& P, int sq, int color, uint32_t* desc) {
     switch (type) {
-        case GENERAL: return piece_moves<GENERAL>(P, sq, color, want, to);
-        case ADVISOR: return piece_moves<ADVISOR>(P, sq, color, want, to);
-        case ELEPHANT: return piece_moves<ELEPHANT>(P, sq, color, want, to);
-        case HORSE: return piece_moves<HORSE>(P, sq, color, want, to);
-        case CHARIOT: return piece_moves<CHARIOT>(P, sq, color, want, to);
-        case CANNON: return piece_moves<CANNON>(P, sq, color, want, to);
-        case SOLDIER: return piece_moves<SOLDIER>(P, sq, color, want, to);
-        default: return 0;
+        case GENERAL: return piece_count<GENERAL>(P, sq, color, desc);
+        case ADVISOR: return piece_count<ADVISOR>(P, sq, color, desc);
+        case ELEPHANT: return piece_count<ELEPHANT>(P, sq, color, desc);
+        case HORSE: return piece_count<HORSE>(P, sq, color, desc);
+        case CHARIOT: return piece_count<CHARIOT>(P, sq, color, desc);
+        case CANNON: return piece_count<CANNON>(P, sq, color, desc);
+        case SOLDIER: return piece_count<SOLDIER>(P, sq, color, desc);
+        default: *desc = 0; return 0;
     }
+}
+XQ_HD int piece_decode_dyn(int type, uint32_t desc, int sq, int color, int want) {
+    switch (type) {
+        case GENERAL: return piece_decode<GENERAL>(desc, sq, color, want);
+        case ADVISOR: return piece_decode<ADVISOR>(desc, sq, color, want);
+        case ELEPHANT: return piece_decode<ELEPHANT>(desc, sq, color, want);
+        case HORSE: return piece_decode<HORSE>(desc, sq, color, want);
+        case CHARIOT: case CANNON: return slider_decode(desc, sq, want);
+        case SOLDIER: return piece_decode<SOLDIER>(desc, sq, color, want);
+        default: return sq;
+    }
+}
+// count, and (want >= 0) the want-th destination: the two steps above in one call (host differential tests)
+XQ_HD int piece_moves_dyn(int type, const Pos& P, int sq, int color, int want, int* to) {
+    uint32_t desc;
+    const int n = piece_count_dyn(type, P, sq, color, &desc);
+    if (want >= 0) *to = piece_decode_dyn(type, desc, sq, color, want);
+    return n;
 }
 
 // Piece slots: every side has 16 fixed slots (no promotion in Xiangqi); slot -> type is static,

@@ -205,15 +205,15 @@ __global__ void __launch_bounds__(kB * kS, 2) rollout_slots_kernel(xq_env_rec* _
     for (int p = 0; p < n_plies; ++p) {
         // ---- A: count my moves, publish (square, count) ------------------------------------
         int myq = kDeadSq, cnt = 0;
-        Pos P;
+        uint32_t desc = 0;             // everything phase B needs to decode my k-th move (xq_bitboard.cuh): the generator runs once per ply
         if (active) {
             const int color = st.player;
             myq = color ? st.sq_black : st.sq_red;
+            Pos P;
             P.own = color ? st.black : st.red;
             P.occ = Bits90{st.red.w0 | st.black.w0, st.red.w1 | st.black.w1, st.red.w2 | st.black.w2};
             P.occT = st.occT;
-            int dummy;
-            if (myq != kDeadSq) cnt = piece_moves_dyn(type, P, myq, color, -1, &dummy);   // warp-uniform type
+            if (myq != kDeadSq) cnt = piece_count_dyn(type, P, myq, color, &desc);         // warp-uniform type
             pubq8[pub_off] = (uint8_t)myq;
             pubc8[pub_off] = (uint8_t)cnt;
             if (slot == 0) s_cap[(p & 1) * kB + lane] = 0;
@@ -240,8 +240,7 @@ __global__ void __launch_bounds__(kB * kS, 2) rollout_slots_kernel(xq_env_rec* _
                 z ^= z >> 31;
                 const uint32_t k = mod_small((uint32_t)(z >> 33), tot, s_magic[tot]);
                 if (cnt > 0 && k >= prefix && k < prefix + (uint32_t)cnt) {
-                    int to = 0;
-                    piece_moves_dyn(type, P, myq, st.player, (int)(k - prefix), &to);
+                    const int to = piece_decode_dyn(type, desc, myq, st.player, (int)(k - prefix));
                     s_move[lane] = (uint32_t)myq | ((uint32_t)to << 8);
                 }
             }
