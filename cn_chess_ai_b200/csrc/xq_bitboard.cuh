@@ -117,41 +117,61 @@ XQ_HD int slider_decode(uint32_t desc, int sq, int want) {
     return to;
 }
 
-// Leapers: bit k of the returned mask = direction k (reference order) is playable; dest[k] squares
-// are recomputed by leaper_to().  color: RED/BLACK of the piece.
+// Leapers: bit k of the returned mask = direction k (reference order) is playable; the destinations are recomputed by
+// *_dir().  color: RED/BLACK of the piece.
+// Every square a leaper looks at lies within +-20 of its own square, so instead of a dynamic 3-word bit test per
+// square (two selects + shift + and, 16 of them for a horse) the 41 bits around the piece are pulled out of a
+// bitboard ONCE with two funnel shifts; after that every test is a compile-time bit position.  Squares beyond the
+// board read as empty -- the row / column bounds are tested separately, as the reference does (isInsideBoard).
+struct Win41 {
+    uint32_t lo, hi;                     // bit (off + 20) = board bit (sq + off), off in [-20, 20]
+    XQ_HD uint32_t at(int off) const { const int p = off + 20; return (p < 32 ? lo >> p : hi >> (p - 32)) & 1u; }
+};
+XQ_HD Win41 window(const Bits90& b, int sq) {
+    const int q = sq + 12;               // (sq - 20) + 32: bit index into the padded word array {0, w0, w1, w2, 0, 0}
+    const int wi = q >> 5, sh = q & 31;
+    const uint32_t x0 = wi == 0 ? 0u : (wi == 1 ? b.w0 : (wi == 2 ? b.w1 : b.w2));
+    const uint32_t x1 = wi == 0 ? b.w0 : (wi == 1 ? b.w1 : (wi == 2 ? b.w2 : 0u));
+    const uint32_t x2 = wi == 0 ? b.w1 : (wi == 1 ? b.w2 : 0u);
+    return Win41{funnel_r(x0, x1, sh), funnel_r(x1, x2, sh)};
+}
 XQ_HD int general_dir(int k) { return k == 0 ? 9 : (k == 1 ? -9 : (k == 2 ? 1 : -1)); }           // :150
 XQ_HD uint32_t general_mask(const Pos& P, int sq) {                                               // :149-160, :328-343
     const int r = row_of(sq), c = sq - 9 * r;
     if (!in_any_palace(r, c)) return 0;
+    const Win41 own = window(P.own, sq);
     uint32_t m = 0;
 #pragma unroll
     for (int k = 0; k < 4; ++k) {
         const int nr = r + (k == 0 ? 1 : (k == 1 ? -1 : 0)), nc = c + (k == 2 ? 1 : (k == 3 ? -1 : 0));
-        if (in_any_palace(nr, nc) && !P.own.test(nr * 9 + nc)) m |= 1u << k;
+        if (in_any_palace(nr, nc) && !own.at(k == 0 ? 9 : (k == 1 ? -9 : (k == 2 ? 1 : -1)))) m |= 1u << k;
     }
     return m;
 }
 XQ_HD int advisor_dir(int k) { return k == 0 ? 10 : (k == 1 ? 8 : (k == 2 ? -8 : -10)); }         // :163
 XQ_HD uint32_t advisor_mask(const Pos& P, int sq, int color) {                                    // :162-177
     const int r = row_of(sq), c = sq - 9 * r;
+    const Win41 own = window(P.own, sq);
     uint32_t m = 0;
 #pragma unroll
     for (int k = 0; k < 4; ++k) {
         const int nr = r + (k < 2 ? 1 : -1), nc = c + ((k & 1) ? -1 : 1);
-        if (in_palace_of(color, nr, nc) && !P.own.test(nr * 9 + nc)) m |= 1u << k;
+        if (in_palace_of(color, nr, nc) && !own.at(k == 0 ? 10 : (k == 1 ? 8 : (k == 2 ? -8 : -10)))) m |= 1u << k;
     }
     return m;
 }
 XQ_HD int elephant_dir(int k) { return k == 0 ? 20 : (k == 1 ? 16 : (k == 2 ? -16 : -20)); }      // :180
 XQ_HD uint32_t elephant_mask(const Pos& P, int sq, int color) {                                   // :179-196, :355-367
     const int r = row_of(sq), c = sq - 9 * r;
+    const Win41 own = window(P.own, sq), occ = window(P.occ, sq);
     uint32_t m = 0;
 #pragma unroll
     for (int k = 0; k < 4; ++k) {
         const int dr = k < 2 ? 2 : -2, dc = (k & 1) ? -2 : 2;
         const int nr = r + dr, nc = c + dc;
         const bool side_ok = color == RED ? (nr <= 4 && r < 5) : (nr >= 5 && r >= 5);
-        if (inside(nr, nc) && side_ok && !P.occ.test((r + dr / 2) * 9 + c + dc / 2) && !P.own.test(nr * 9 + nc)) m |= 1u << k;
+        const int d = k == 0 ? 20 : (k == 1 ? 16 : (k == 2 ? -16 : -20));
+        if (inside(nr, nc) && side_ok && !occ.at(d / 2) && !own.at(d)) m |= 1u << k;
     }
     return m;
 }
@@ -161,25 +181,27 @@ XQ_HD int horse_dir(int k) {                                                    
 }
 XQ_HD uint32_t horse_mask(const Pos& P, int sq) {                                                 // :248-263, :369-380
     const int r = row_of(sq), c = sq - 9 * r;
+    const Win41 own = window(P.own, sq), occ = window(P.occ, sq);
     uint32_t m = 0;
 #pragma unroll
     for (int k = 0; k < 8; ++k) {
         const int a = (k & 2) ? -1 : 1, b = (k & 1) ? -1 : 1;
         const int nr = r + (k < 4 ? a : 2 * a), nc = c + (k < 4 ? 2 * b : b);
-        const int leg = k < 4 ? sq + b : sq + 9 * a;
-        if (inside(nr, nc) && !P.occ.test(leg) && !P.own.test(nr * 9 + nc)) m |= 1u << k;
+        const int leg = k < 4 ? b : 9 * a, dest = k < 4 ? 9 * a + 2 * b : 18 * a + b;       // offsets from sq: compile-time after unrolling
+        if (inside(nr, nc) && !occ.at(leg) && !own.at(dest)) m |= 1u << k;
     }
     return m;
 }
 XQ_HD int soldier_dir(int k, int color) { return k == 0 ? (color == RED ? 9 : -9) : (k == 1 ? -1 : 1); }   // :267-281
 XQ_HD uint32_t soldier_mask(const Pos& P, int sq, int color) {                                    // :265-283
     const int r = row_of(sq), c = sq - 9 * r;
+    const Win41 own = window(P.own, sq);
     uint32_t m = 0;
     const int nr = r + (color == RED ? 1 : -1);
-    if ((unsigned)nr < 10u && !P.own.test(nr * 9 + c)) m |= 1u;
+    if ((unsigned)nr < 10u && !(color == RED ? own.at(9) : own.at(-9))) m |= 1u;
     if (color == RED ? r > 4 : r < 5) {
-        if (c > 0 && !P.own.test(sq - 1)) m |= 2u;
-        if (c < 8 && !P.own.test(sq + 1)) m |= 4u;
+        if (c > 0 && !own.at(-1)) m |= 2u;
+        if (c < 8 && !own.at(1)) m |= 4u;
     }
     return m;
 }
