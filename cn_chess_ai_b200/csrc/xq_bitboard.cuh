@@ -20,28 +20,39 @@ XQ_HD int ffs32(uint32_t x) { return __ffs((int)x); }          // 1-based, 0 if 
 XQ_HD int clz32(uint32_t x) { return __clz((int)x); }
 XQ_HD int popc32(uint32_t x) { return __popc(x); }
 XQ_HD uint32_t funnel_r(uint32_t lo, uint32_t hi, int sh) { return __funnelshift_r(lo, hi, sh); }
+// PTX shl.b32 clamps the shift amount (n > 31 gives 0): the three words of a single-bit mask without selects
+XQ_HD uint32_t shl_clamp(uint32_t x, uint32_t n) { uint32_t r; asm("shl.b32 %0, %1, %2;" : "=r"(r) : "r"(x), "r"(n)); return r; }
 #else
 XQ_HD int ffs32(uint32_t x) { return __builtin_ffs((int)x); }
 XQ_HD int clz32(uint32_t x) { return x ? __builtin_clz(x) : 32; }
 XQ_HD int popc32(uint32_t x) { return __builtin_popcount(x); }
 XQ_HD uint32_t funnel_r(uint32_t lo, uint32_t hi, int sh) { return (uint32_t)((((uint64_t)hi << 32) | lo) >> (sh & 31)); }
+XQ_HD uint32_t shl_clamp(uint32_t x, uint32_t n) { return n > 31u ? 0u : x << n; }
 #endif
+
+// Branch-free word multiplexer: m = all ones picks b, m = 0 picks a (one LOP3).  Nested ternaries on a run-time word index were
+// compiled into branch regions with predicated moves (21 BSSY regions per ply in the generator); masks taken from the index bits
+// with two shifts are plain arithmetic.
+XQ_HD uint32_t mux(uint32_t a, uint32_t b, uint32_t m) { return a ^ ((a ^ b) & m); }
+XQ_HD uint32_t bit_to_mask(int x, int bit) { return (uint32_t)((int32_t)((uint32_t)x << (31 - bit)) >> 31); }   // all ones iff bit `bit` of x is set
 
 // 90-bit set in three words.  Row-major index = row*9+col; column-major index = col*10+row.
 struct Bits90 {
     uint32_t w0, w1, w2;
-    XQ_HD uint32_t word(int i) const { return i == 0 ? w0 : (i == 1 ? w1 : w2); }
-    XQ_HD bool test(int i) const { return (word(i >> 5) >> (i & 31)) & 1u; }
+    // word (i >> 5) for a bit index i in [0, 96); indices outside read w0..w2 of some word (callers discard the result)
+    XQ_HD uint32_t word_of_bit(int i) const { return mux(mux(w0, w1, bit_to_mask(i, 5)), w2, bit_to_mask(i, 6)); }
+    XQ_HD uint32_t word(int i) const { return mux(mux(w0, w1, bit_to_mask(i, 0)), w2, bit_to_mask(i, 1)); }
+    XQ_HD bool test(int i) const { return (word_of_bit(i) >> (i & 31)) & 1u; }
     XQ_HD void set(int i) { const uint32_t b = 1u << (i & 31); const int w = i >> 5; w0 |= w == 0 ? b : 0u; w1 |= w == 1 ? b : 0u; w2 |= w == 2 ? b : 0u; }
     XQ_HD void clear(int i) { const uint32_t b = ~(1u << (i & 31)); const int w = i >> 5; w0 &= w == 0 ? b : ~0u; w1 &= w == 1 ? b : ~0u; w2 &= w == 2 ? b : ~0u; }
     // single-bit mask of index i spread over the three words (computed once, applied with plain logic ops)
-    static XQ_HD Bits90 bit(int i) { const uint32_t b = 1u << (i & 31); const int w = i >> 5; return Bits90{w == 0 ? b : 0u, w == 1 ? b : 0u, w == 2 ? b : 0u}; }
+    static XQ_HD Bits90 bit(int i) { return Bits90{shl_clamp(1u, (uint32_t)i), shl_clamp(1u, (uint32_t)(i - 32)), shl_clamp(1u, (uint32_t)(i - 64))}; }
     XQ_HD void or_with(const Bits90& m) { w0 |= m.w0; w1 |= m.w1; w2 |= m.w2; }
     XQ_HD void andnot(const Bits90& m) { w0 &= ~m.w0; w1 &= ~m.w1; w2 &= ~m.w2; }
-    // nbits (<= 10) starting at bit pos
+    // nbits (<= 10) starting at bit pos (0 <= pos < 96)
     XQ_HD uint32_t field(int pos, int nbits) const {
-        const int w = pos >> 5;
-        const uint32_t lo = word(w), hi = w == 0 ? w1 : (w == 1 ? w2 : 0u);
+        const uint32_t m1 = bit_to_mask(pos, 5), m2 = bit_to_mask(pos, 6);
+        const uint32_t lo = mux(mux(w0, w1, m1), w2, m2), hi = mux(w1, w2, m1) & ~m2;
         return funnel_r(lo, hi, pos & 31) & ((1u << nbits) - 1u);
     }
 };
@@ -57,24 +68,25 @@ struct Pos {
 // One slider ray on a line occupancy L (nb bits) from index p: number of empty squares before the
 // first blocker, index of the first blocker (-1: none) and of the second blocker (-1: none).
 struct Ray { int empties, first, second; };
+// (written with selects only: a ray is ~12 straight-line instructions, no branch for the "no blocker" case)
 XQ_HD Ray ray_up(uint32_t L, int p, int nb) {      // towards higher index
     const uint32_t m = L >> (p + 1);
-    Ray r;
-    if (m == 0) { r.empties = nb - 1 - p; r.first = -1; r.second = -1; return r; }
-    const int d = ffs32(m);
-    r.empties = d - 1; r.first = p + d;
+    const int d = ffs32(m);                          // 0: no blocker
     const uint32_t m2 = m & (m - 1);
+    Ray r;
+    r.empties = m ? d - 1 : nb - 1 - p;
+    r.first = m ? p + d : -1;
     r.second = m2 ? p + ffs32(m2) : -1;
     return r;
 }
 XQ_HD Ray ray_down(uint32_t L, int p, int) {       // towards lower index
     const uint32_t m = L & ((1u << p) - 1u);
+    const int top = 31 - clz32(m);                   // -1: no blocker
+    const uint32_t m2 = m & ~(1u << (top & 31));
     Ray r;
-    if (m == 0) { r.empties = p; r.first = -1; r.second = -1; return r; }
-    const int top = 31 - clz32(m);
-    r.empties = p - top - 1; r.first = top;
-    const uint32_t m2 = m ^ (1u << top);
-    r.second = m2 ? 31 - clz32(m2) : -1;
+    r.empties = p - top - 1;
+    r.first = top;
+    r.second = m2 ? 31 - clz32(m2) : -1;             // m == 0 gives m2 == 0
     return r;
 }
 
@@ -96,10 +108,11 @@ XQ_HD int slider_desc(const Pos& P, int sq, uint32_t* desc) {
         const Ray ray = (k & 1) ? ray_down(horiz ? rank : file, p, horiz ? 9 : 10)
                                 : ray_up(horiz ? rank : file, p, horiz ? 9 : 10);
         const int tgt = IS_CANNON ? ray.second : ray.first;
-        int capdist = 0;
-        if (tgt >= 0) { const int s = horiz ? 9 * r + tgt : 9 * tgt + c; if (!P.own.test(s)) capdist = (k & 1) ? p - tgt : tgt - p; }
+        const int s = horiz ? 9 * r + tgt : 9 * tgt + c;                      // tgt == -1 reads some bit: discarded
+        const bool cap = (tgt >= 0) & !P.own.test(s);
+        const int capdist = cap ? ((k & 1) ? p - tgt : tgt - p) : 0;
         d |= ((uint32_t)ray.empties | ((uint32_t)capdist << 4)) << (8 * k);
-        total += ray.empties + (capdist ? 1 : 0);
+        total += ray.empties + (cap ? 1 : 0);
     }
     *desc = d;
     return total;
@@ -128,25 +141,23 @@ struct Win41 {
     XQ_HD uint32_t at(int off) const { const int p = off + 20; return (p < 32 ? lo >> p : hi >> (p - 32)) & 1u; }
 };
 XQ_HD Win41 window(const Bits90& b, int sq) {
-    const int q = sq + 12;               // (sq - 20) + 32: bit index into the padded word array {0, w0, w1, w2, 0, 0}
-    const int wi = q >> 5, sh = q & 31;
-    const uint32_t x0 = wi == 0 ? 0u : (wi == 1 ? b.w0 : (wi == 2 ? b.w1 : b.w2));
-    const uint32_t x1 = wi == 0 ? b.w0 : (wi == 1 ? b.w1 : (wi == 2 ? b.w2 : 0u));
-    const uint32_t x2 = wi == 0 ? b.w1 : (wi == 1 ? b.w2 : 0u);
-    return Win41{funnel_r(x0, x1, sh), funnel_r(x1, x2, sh)};
+    const int q = sq + 12;               // (sq - 20) + 32: bit index into the padded word array A = {0, w0, w1, w2, 0, 0}
+    const uint32_t m1 = bit_to_mask(q, 5), m2 = bit_to_mask(q, 6);      // word index q >> 5 in 0..3; wanted: A[wi], A[wi+1], A[wi+2]
+    const uint32_t b0 = b.w1 & m2, b1 = mux(b.w0, b.w2, m2), b2 = b.w1 & ~m2, b3 = b.w2 & ~m2;      // A[wi & 2 ...]
+    const uint32_t x0 = mux(b0, b1, m1), x1 = mux(b1, b2, m1), x2 = mux(b2, b3, m1);
+    return Win41{funnel_r(x0, x1, q & 31), funnel_r(x1, x2, q & 31)};
 }
 XQ_HD int general_dir(int k) { return k == 0 ? 9 : (k == 1 ? -9 : (k == 2 ? 1 : -1)); }           // :150
 XQ_HD uint32_t general_mask(const Pos& P, int sq) {                                               // :149-160, :328-343
     const int r = row_of(sq), c = sq - 9 * r;
-    if (!in_any_palace(r, c)) return 0;
     const Win41 own = window(P.own, sq);
     uint32_t m = 0;
 #pragma unroll
     for (int k = 0; k < 4; ++k) {
         const int nr = r + (k == 0 ? 1 : (k == 1 ? -1 : 0)), nc = c + (k == 2 ? 1 : (k == 3 ? -1 : 0));
-        if (in_any_palace(nr, nc) && !own.at(k == 0 ? 9 : (k == 1 ? -9 : (k == 2 ? 1 : -1)))) m |= 1u << k;
+        m |= ((in_any_palace(nr, nc) ? 1u : 0u) & ~own.at(k == 0 ? 9 : (k == 1 ? -9 : (k == 2 ? 1 : -1)))) << k;
     }
-    return m;
+    return in_any_palace(r, c) ? m : 0u;
 }
 XQ_HD int advisor_dir(int k) { return k == 0 ? 10 : (k == 1 ? 8 : (k == 2 ? -8 : -10)); }         // :163
 XQ_HD uint32_t advisor_mask(const Pos& P, int sq, int color) {                                    // :162-177
@@ -156,7 +167,7 @@ XQ_HD uint32_t advisor_mask(const Pos& P, int sq, int color) {                  
 #pragma unroll
     for (int k = 0; k < 4; ++k) {
         const int nr = r + (k < 2 ? 1 : -1), nc = c + ((k & 1) ? -1 : 1);
-        if (in_palace_of(color, nr, nc) && !own.at(k == 0 ? 10 : (k == 1 ? 8 : (k == 2 ? -8 : -10)))) m |= 1u << k;
+        m |= ((in_palace_of(color, nr, nc) ? 1u : 0u) & ~own.at(k == 0 ? 10 : (k == 1 ? 8 : (k == 2 ? -8 : -10)))) << k;
     }
     return m;
 }
@@ -171,7 +182,7 @@ XQ_HD uint32_t elephant_mask(const Pos& P, int sq, int color) {                 
         const int nr = r + dr, nc = c + dc;
         const bool side_ok = color == RED ? (nr <= 4 && r < 5) : (nr >= 5 && r >= 5);
         const int d = k == 0 ? 20 : (k == 1 ? 16 : (k == 2 ? -16 : -20));
-        if (inside(nr, nc) && side_ok && !occ.at(d / 2) && !own.at(d)) m |= 1u << k;
+        m |= (((inside(nr, nc) & side_ok) ? 1u : 0u) & ~occ.at(d / 2) & ~own.at(d)) << k;
     }
     return m;
 }
@@ -188,7 +199,7 @@ XQ_HD uint32_t horse_mask(const Pos& P, int sq) {                               
         const int a = (k & 2) ? -1 : 1, b = (k & 1) ? -1 : 1;
         const int nr = r + (k < 4 ? a : 2 * a), nc = c + (k < 4 ? 2 * b : b);
         const int leg = k < 4 ? b : 9 * a, dest = k < 4 ? 9 * a + 2 * b : 18 * a + b;       // offsets from sq: compile-time after unrolling
-        if (inside(nr, nc) && !occ.at(leg) && !own.at(dest)) m |= 1u << k;
+        m |= ((inside(nr, nc) ? 1u : 0u) & ~occ.at(leg) & ~own.at(dest)) << k;
     }
     return m;
 }
@@ -198,11 +209,10 @@ XQ_HD uint32_t soldier_mask(const Pos& P, int sq, int color) {                  
     const Win41 own = window(P.own, sq);
     uint32_t m = 0;
     const int nr = r + (color == RED ? 1 : -1);
-    if ((unsigned)nr < 10u && !(color == RED ? own.at(9) : own.at(-9))) m |= 1u;
-    if (color == RED ? r > 4 : r < 5) {
-        if (c > 0 && !own.at(-1)) m |= 2u;
-        if (c < 8 && !own.at(1)) m |= 4u;
-    }
+    m |= ((unsigned)nr < 10u ? 1u : 0u) & ~(color == RED ? own.at(9) : own.at(-9));
+    const uint32_t crossed = (color == RED ? r > 4 : r < 5) ? 1u : 0u;
+    m |= (crossed & (c > 0 ? 1u : 0u) & ~own.at(-1)) << 1;
+    m |= (crossed & (c < 8 ? 1u : 0u) & ~own.at(1)) << 2;
     return m;
 }
 // index of the j-th (0-based) set bit of an 8-bit mask

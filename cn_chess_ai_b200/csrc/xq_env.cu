@@ -17,6 +17,8 @@
 #include <new>
 #include <vector>
 
+#include <stdlib.h>
+
 #include "xq_common.cuh"
 #include <algorithm>
 
@@ -271,12 +273,22 @@ static inline unsigned grid_for(int64_t n, int per_block) { return (unsigned)((n
 namespace xq {
 cudaError_t launch_rollout_slots(xq_env_rec* envs, int64_t n, uint64_t env_id0, uint64_t seed, int n_plies, xq_trace_rec* trace,
                                  xq_env_stats* stats, uint8_t* nonstd, cudaStream_t stream);
+cudaError_t launch_rollout_team(xq_env_rec* envs, int64_t n, uint64_t env_id0, uint64_t seed, int n_plies, xq_trace_rec* trace,
+                                xq_env_stats* stats, uint8_t* nonstd, cudaStream_t stream);
 }
-// Fused rollout = slot-parallel kernel (xq_rollout.cu) for every board with a standard piece set, then the generic
+// threads per board of the fused rollout kernel: 4 = rollout_team_kernel (xq_rollout_team.cu, the default: faster at every env
+// count measured, 4096 .. 1M), 16 = rollout_slots_kernel (xq_rollout.cu, kept for A/B runs: XQ_ROLLOUT_TEAM=16).  Bit-identical.
+static int rollout_team() {
+    static const int forced = [] { const char* e = getenv("XQ_ROLLOUT_TEAM"); return e ? atoi(e) : 0; }();
+    return forced == 16 ? 16 : 4;
+}
+// Fused rollout = team kernel (xq_rollout_team.cu; or the 16-thread slot kernel, xq_rollout.cu) for every board with a standard piece set, then the generic
 // thread-per-board kernel for the boards it flagged (only possible after xq_env_set_boards injected exotic positions).
 static int launch_rollout(xq_env_s* h, int n_plies, xq_trace_rec* d_trace) {
     if (n_plies >= (1 << 24)) return fail(XQ_ERR_INVALID, "rollout: n_plies must be < 2^24 per launch");
-    XQ_CUDA(launch_rollout_slots(h->d_envs, h->n, h->env_id0, h->seed, n_plies, d_trace, h->d_stats, h->d_nonstd, h->stream));
+    const int team = rollout_team();
+    if (team == 16) XQ_CUDA(launch_rollout_slots(h->d_envs, h->n, h->env_id0, h->seed, n_plies, d_trace, h->d_stats, h->d_nonstd, h->stream));
+    else XQ_CUDA(launch_rollout_team(h->d_envs, h->n, h->env_id0, h->seed, n_plies, d_trace, h->d_stats, h->d_nonstd, h->stream));
     if (h->maybe_nonstd) {
         rollout_random_kernel<<<grid_for(h->n, kThreads), kThreads, 0, h->stream>>>(h->d_envs, h->n, h->env_id0, h->seed, n_plies, d_trace,
                                                                                     h->d_stats, h->d_nonstd);

@@ -1,0 +1,365 @@
+// xq_rollout_team.cuh -- one ply of the fused random-policy rollout for a TEAM of 4 threads per board, each thread owning 4 piece
+// slots of either side.  The three phases of a ply are host-compilable functions (tests/hostsim runs the 4 threads of a board one
+// after the other, phase by phase, and diffs the whole trace against the oracle before any GPU time); the kernel in
+// xq_rollout_team.cu is these phases with two __syncthreads per ply between them.
+//
+// Why teams: in the 16-threads-per-board kernel (rollout_slots_kernel) every thread keeps a replica of the board and repeats the
+// selection and the apply step -- ncu attributes 136 of its 407 warp-instructions per ply to move generation and 235 to the
+// replicated part.  With 4 slots per thread the replicated part is paid 4 times per board instead of 16 times, and warps stay
+// piece-type uniform: role = warp, lane = board, and position i of every lane of a warp holds the same piece type.
+//
+// State is kept RELATIVE to the side to move (own / opp) and swapped after every ply, so neither the generator nor the apply
+// step selects on the mover's colour.  The 4 squares of a side are packed one per byte (127 = captured); capture detection, the
+// move of the own piece and the reference-order prefix (sum of the move counts of the pieces on lower squares,
+// ChessAI::getAllValidActions scans squares row-major: src/chessai.cpp:347-368) are byte-SIMD on those words.
+#pragma once
+#include <stdint.h>
+
+#include "../../include/xq.h"
+#include "xq_bitboard.cuh"
+
+namespace xq {
+
+#if defined(__CUDA_ARCH__)
+XQ_HD uint32_t dp4a_u(uint32_t a, uint32_t b, uint32_t c) { return __dp4a(a, b, c); }
+XQ_HD uint32_t umulhi_u(uint32_t a, uint32_t b) { return __umulhi(a, b); }
+#else
+XQ_HD uint32_t dp4a_u(uint32_t a, uint32_t b, uint32_t c) {
+    for (int i = 0; i < 4; ++i) c += ((a >> (8 * i)) & 0xFFu) * ((b >> (8 * i)) & 0xFFu);
+    return c;
+}
+XQ_HD uint32_t umulhi_u(uint32_t a, uint32_t b) { return (uint32_t)(((uint64_t)a * b) >> 32); }
+#endif
+XQ_HD Bits90 bit_mask(int i) { return Bits90::bit(i); }
+
+// ---- the team: 4 threads per board, 4 piece slots per thread, ONE code path for all four roles ---------------------------------
+// position:   0 (slider)        1                 2                  3
+// role 0:     Chariot  slot 0   Horse    slot 2   Soldier  slot 11   Soldier slot 12
+// role 1:     Chariot  slot 1   Horse    slot 3   Soldier  slot 13   Soldier slot 14
+// role 2:     Cannon   slot 9   Advisor  slot 6   Elephant slot 4    General slot 8
+// role 3:     Cannon   slot 10  Advisor  slot 7   Elephant slot 5    Soldier slot 15
+// The piece type of a position is a warp-uniform RUN-TIME value (role = warp): a select for the sliders, a two-way branch for the
+// leapers.  Every warp therefore runs the same ~14 KB loop body -- a first version with one template instantiation per role
+// (4 x 30 KB of straight-line code) spent most of its cycles in `no_instruction` stalls (ncu), the instruction cache being 32 KB.
+constexpr int kTeam = 4;
+struct TeamRole {
+    int role;
+    bool hi;                       // roles 2, 3
+    uint32_t slots;                // slot of position i in byte i
+    uint32_t types;                // PieceType of position i in byte i
+    uint32_t score5;               // piece value / 5
+    uint32_t open_red, open_black; // opening squares of my slots (ChessBoard::initializeBoard, src/chessboard.cpp:13-28)
+};
+constexpr int open_sq_c(int s) {   // opening square of slot s (0..15 Red, 16..31 Black)
+    constexpr uint8_t t[32] = {0, 8, 1, 7, 2, 6, 3, 5, 4, 19, 25, 27, 29, 31, 33, 35, 81, 89, 82, 88, 83, 87, 84, 86, 85, 64, 70, 54, 56, 58, 60, 62};
+    return t[s];
+}
+constexpr uint32_t team_slots_c(int role) { return role == 0 ? 0x0C0B0200u : (role == 1 ? 0x0E0D0301u : (role == 2 ? 0x08040609u : 0x0F05070Au)); }
+constexpr uint32_t team_open_c(int role, int side) {
+    uint32_t w = 0;
+    for (int i = 0; i < 4; ++i) w |= (uint32_t)open_sq_c(side * 16 + (int)((team_slots_c(role) >> (8 * i)) & 0xFFu)) << (8 * i);
+    return w;
+}
+constexpr int piece_score_c(int type) { return type == GENERAL ? 1000 : (type == ADVISOR || type == ELEPHANT ? 20 : (type == HORSE ? 40 : (type == CHARIOT ? 90 : (type == CANNON ? 45 : 10)))); }
+constexpr uint32_t team_types_c(int role) {
+    return role < 2 ? (uint32_t)(CHARIOT | HORSE << 8 | SOLDIER << 16 | SOLDIER << 24)
+                    : (uint32_t)(CANNON | ADVISOR << 8 | ELEPHANT << 16 | (role == 2 ? GENERAL : SOLDIER) << 24);
+}
+constexpr uint32_t team_score5_c(int role) {
+    uint32_t w = 0;
+    for (int i = 0; i < 4; ++i) w |= (uint32_t)(piece_score_c((int)((team_types_c(role) >> (8 * i)) & 0xFFu)) / 5) << (8 * i);
+    return w;
+}
+#define XQ_TEAM_SEL(f) (role == 0 ? f(0) : (role == 1 ? f(1) : (role == 2 ? f(2) : f(3))))
+XQ_HD TeamRole team_role(int role) {
+    TeamRole r;
+    r.role = role; r.hi = role >= 2;
+#define XQ_F_OPEN_R(i) team_open_c(i, 0)
+#define XQ_F_OPEN_B(i) team_open_c(i, 1)
+    r.slots = XQ_TEAM_SEL(team_slots_c); r.types = XQ_TEAM_SEL(team_types_c); r.score5 = XQ_TEAM_SEL(team_score5_c);
+    r.open_red = XQ_TEAM_SEL(XQ_F_OPEN_R); r.open_black = XQ_TEAM_SEL(XQ_F_OPEN_B);
+#undef XQ_F_OPEN_R
+#undef XQ_F_OPEN_B
+    return r;
+}
+#undef XQ_TEAM_SEL
+XQ_HD Bits90 team_open_red() { return Bits90{0xAA0801FFu, 0x0000000Au, 0x00000000u}; }
+XQ_HD Bits90 team_open_black() { return Bits90{0x00000000u, 0x55400000u, 0x03FE0041u}; }
+XQ_HD Bits90 team_open_occT() { return Bits90{0x649A1649u, 0x98064980u, 0x0249A164u}; }
+
+// shared memory of a CTA of KB boards, every array [item][board]: lane == bank
+template <int KB>
+struct TeamShared {
+    uint32_t q[4 * KB];            // [role][board]: squares of the mover's 16 slots, one byte each
+    uint32_t c[4 * KB];            // their move counts
+    uint32_t move[KB];             // from | to << 8
+    uint32_t cap[2 * KB];          // value | code << 16 of the captured piece, double-buffered by ply parity
+    uint32_t rng[2 * 16 * KB];     // idx31 draws of 16 plies, double-buffered by chunk parity
+    uint32_t magic[XQ_MAX_ACTIONS + 1];
+};
+
+struct TeamState {
+    uint32_t sq_own, sq_opp;       // packed squares of my 4 slots: side to move / the other side
+    Bits90 own, opp, occT;
+    int gen_own, gen_opp;
+    int move_count, player;
+    uint32_t ctr;
+};
+struct TeamPly {                   // scratch of one ply, phase A -> B -> C
+    uint32_t desc[4];
+    uint32_t cntw;
+    uint32_t total;
+};
+// scores / material / reward / statistics / trace: role 0 alone, one barrier late (see rollout_slots_kernel)
+struct TeamBook {
+    int red, black, mat_red, mat_black;
+    uint32_t pend, pend_tr0;
+    int pend_p;
+    uint32_t a_steps, a_games, a_red, a_black, a_capg, a_caps, a_legal;
+    long long a_reward;
+};
+
+XQ_HD void team_reset(const TeamRole& R, TeamState& st) {
+    st.sq_own = R.open_red; st.sq_opp = R.open_black;
+    st.own = team_open_red(); st.opp = team_open_black(); st.occT = team_open_occT();
+    st.gen_own = 4; st.gen_opp = 85; st.move_count = 0; st.player = RED;
+}
+
+XQ_HD uint32_t team_draw(uint64_t rng_base, uint32_t ctr) {       // idx31 of xq_rng (include/xq.h)
+    uint64_t z = rng_base + (uint64_t)ctr * 0xD1B54A32D192ED03ull;
+    z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ull;
+    z = (z ^ (z >> 27)) * 0x94D049BB133111EBull;
+    z ^= z >> 31;
+    return (uint32_t)(z >> 33);
+}
+// the draws of plies [16*chunk, 16*chunk+16): thread (role, lane) computes 4 of them.  The RNG counter of ply p is ctr0 + p
+// whatever happens in between (a move and a no-action restart both advance it by one).
+template <int KB>
+XQ_HD void team_rng_chunk(const TeamRole& R, TeamShared<KB>& sh, int lane, int chunk, uint64_t rng_base, uint32_t ctr0) {
+#pragma unroll 1
+    for (int i = 0; i < 4; ++i) {
+        const int j = R.role * 4 + i;
+        sh.rng[((chunk & 1) * 16 + j) * KB + lane] = team_draw(rng_base, ctr0 + (uint32_t)(chunk * 16 + j));
+    }
+}
+
+XQ_HD uint32_t team_mod_magic(uint32_t d) { return (0xFFFFFFFFu / d) + 1u; }
+XQ_HD uint32_t team_mod(uint32_t n, uint32_t d, uint32_t magic) {     // n % d, n < 2^31, 1 <= d <= 128 (see mod_small in xq_rollout.cu)
+    const uint32_t q = umulhi_u(n, magic);
+    const int32_t r = (int32_t)(n - q * d);
+    return d == 1 ? 0u : (uint32_t)(r < 0 ? r + (int32_t)d : r);
+}
+
+// sliders with the piece type at run time: the capture square is the second blocker for a Cannon, the first for a Chariot
+XQ_HD int slider_desc_rt(const Pos& P, int sq, bool cannon, uint32_t* desc) {
+    const int r = row_of(sq), c = sq - 9 * r;
+    const uint32_t rank = P.occ.field(9 * r, 9), file = P.occT.field(10 * c, 10);
+    int total = 0;
+    uint32_t d = 0;
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+        const bool horiz = k < 2;
+        const int p = horiz ? c : r;
+        const Ray ray = (k & 1) ? ray_down(horiz ? rank : file, p, horiz ? 9 : 10) : ray_up(horiz ? rank : file, p, horiz ? 9 : 10);
+        const int tgt = cannon ? ray.second : ray.first;
+        const int s = horiz ? 9 * r + tgt : 9 * tgt + c;                      // tgt == -1 reads some bit: discarded
+        const bool cap = (tgt >= 0) & !P.own.test(s);
+        const int capdist = cap ? ((k & 1) ? p - tgt : tgt - p) : 0;
+        d |= ((uint32_t)ray.empties | ((uint32_t)capdist << 4)) << (8 * k);
+        total += ray.empties + (cap ? 1 : 0);
+    }
+    *desc = d;
+    return total;
+}
+// index of the j-th (0-based) set bit of an 8-bit mask with at least j+1 bits set: three halving steps
+XQ_HD int nth_set_bit8(uint32_t m, int j) {
+    int c = popc32(m & 0xFu);
+    const bool h4 = j >= c;
+    j -= h4 ? c : 0; m = h4 ? m >> 4 : m;
+    c = popc32(m & 0x3u);
+    const bool h2 = j >= c;
+    j -= h2 ? c : 0; m = h2 ? m >> 2 : m;
+    return (h4 ? 4 : 0) + (h2 ? 2 : 0) + ((j >= (int)(m & 1u)) ? 1 : 0);
+}
+// destination of direction k of a leaper of `type` (direction tables of generate*Moves, src/chessboard.cpp:150,163,180,249,267-281)
+XQ_HD int leaper_dir(int type, int k, int color) {
+    const uint64_t tab = type == HORSE ? 0xEDEF1113F5F9070Bull            // 11,7,-7,-11,19,17,-17,-19
+                       : (type == ELEPHANT ? 0xECF01014ull                   // 20,16,-16,-20
+                       : (type == ADVISOR ? 0xF6F8080Aull                    // 10,8,-8,-10
+                       : 0xFF01F709ull));                                    // General: 9,-9,1,-1
+    const int d = (int)(int8_t)(uint8_t)(tab >> (8 * k));
+    return type == SOLDIER ? soldier_dir(k, color) : d;
+}
+
+// ---- phase A: every thread counts the moves of its 4 pieces of the side to move and publishes (squares, counts) -------------
+template <int KB>
+XQ_HD void team_phase_a(const TeamRole& R, const TeamState& st, TeamPly& pl, TeamShared<KB>& sh, int lane, int p) {
+    Pos P;
+    P.own = st.own;
+    P.occ = Bits90{st.own.w0 | st.opp.w0, st.own.w1 | st.opp.w1, st.own.w2 | st.opp.w2};
+    P.occT = st.occT;
+    const int color = st.player;
+    const int q0 = (int)(st.sq_own & 0xFFu), q1 = (int)((st.sq_own >> 8) & 0xFFu), q2 = (int)((st.sq_own >> 16) & 0xFFu), q3 = (int)(st.sq_own >> 24);
+    // a captured piece (square 127) reads garbage bits: its count is discarded
+    int c0 = slider_desc_rt(P, q0, R.hi, &pl.desc[0]);
+    uint32_t m1, m2, m3;
+    if (!R.hi) { m1 = horse_mask(P, q1); m2 = soldier_mask(P, q2, color); m3 = soldier_mask(P, q3, color); }
+    else {
+        m1 = advisor_mask(P, q1, color); m2 = elephant_mask(P, q2, color);
+        m3 = R.role == 2 ? general_mask(P, q3) : soldier_mask(P, q3, color);
+    }
+    pl.desc[1] = m1; pl.desc[2] = m2; pl.desc[3] = m3;
+    c0 = q0 == kDeadSq ? 0 : c0;
+    const int c1 = q1 == kDeadSq ? 0 : popc32(m1), c2 = q2 == kDeadSq ? 0 : popc32(m2), c3 = q3 == kDeadSq ? 0 : popc32(m3);
+    pl.cntw = (uint32_t)c0 | ((uint32_t)c1 << 8) | ((uint32_t)c2 << 16) | ((uint32_t)c3 << 24);
+    sh.q[R.role * KB + lane] = st.sq_own;
+    sh.c[R.role * KB + lane] = pl.cntw;
+    if (R.role == 0) sh.cap[(p & 1) * KB + lane] = 0;
+}
+
+// ---- bookkeeping of the previous ply (role 0): the captured value published in its phase C is visible now ---------------------
+template <int KB>
+XQ_HD void team_finalize(TeamBook& bk, const TeamShared<KB>& sh, int lane, xq_trace_rec* trace, int64_t n, int64_t env) {
+    if (bk.pend == 0) return;
+    const int mover = (bk.pend >> 2) & 1, win = (bk.pend >> 4) & 3, mc = (bk.pend >> 8) & 0xFF, total = (int)(bk.pend >> 16);
+    const bool over = (bk.pend >> 3) & 1;
+    uint32_t capcode = 0;
+    int reward = 0;
+    if ((bk.pend & 3) == 1) {
+        const uint32_t capw = sh.cap[(bk.pend_p & 1) * KB + lane];
+        const int capscore = (int)(capw & 0xFFFFu);
+        capcode = capw >> 16;
+        if (capscore) {      // ChessBoard::movePiece, src/chessboard.cpp:51-58
+            if (mover == RED) { bk.red += capscore; bk.mat_black -= capscore; } else { bk.black += capscore; bk.mat_red -= capscore; }
+        }
+        reward = reward_from_material(mover == RED ? bk.mat_red - bk.mat_black : bk.mat_black - bk.mat_red, mc);
+        bk.a_steps++; bk.a_legal += (uint32_t)total; bk.a_reward += reward; if (capscore) bk.a_caps++;
+        if (over) { bk.a_games++; if (win == RED) bk.a_red++; else bk.a_black++; if (mc < XQ_MAX_MOVES) bk.a_capg++; }
+    } else {
+        bk.a_games++;
+    }
+    if (trace) {   // one 8-byte record: action | n_legal << 16 | flags << 24 (bits 4-7 of flags = captured piece code), reward
+        uint32_t* t = reinterpret_cast<uint32_t*>(trace) + 2 * ((int64_t)bk.pend_p * n + env);
+        t[0] = bk.pend_tr0 | (capcode << 28);
+        t[1] = (uint32_t)reward;
+    }
+    if ((bk.pend & 3) == 2 || over) { bk.red = bk.black = 0; bk.mat_red = bk.mat_black = 1480; }     // ChessBoard::reset
+    bk.pend = 0;
+}
+
+// ---- phase B: list size, draw, reference-order prefix of my pieces; the owner of the k-th action decodes it ------------------
+template <int KB>
+XQ_HD void team_phase_b(const TeamRole& R, const TeamState& st, TeamPly& pl, TeamShared<KB>& sh, int lane, int p) {
+    uint32_t qw[4], cw[4], tot = 0;
+#pragma unroll
+    for (int w = 0; w < 4; ++w) { qw[w] = sh.q[w * KB + lane]; cw[w] = sh.c[w * KB + lane]; tot = dp4a_u(cw[w], 0x01010101u, tot); }
+    pl.total = tot;
+    if (tot > 0) {
+        const uint32_t draw = sh.rng[(((p >> 4) & 1) * 16 + (p & 15)) * KB + lane];
+        const uint32_t k = team_mod(draw, tot, sh.magic[tot]);
+        // which of my pieces (if any) owns the k-th action of the reference-ordered list: selects only, then ONE decode
+        uint32_t hsq = 0, hdesc = 0, hwant = 0, htype = 0;
+        bool hit = false;
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            const uint32_t sq = (st.sq_own >> (8 * i)) & 0xFFu;
+            // byte j of (base - qw) has bit 7 set iff square_j < sq (bytes <= 127, so no borrow crosses a byte); dp4a sums 128 * count_j over them
+            const uint32_t base = sq * 0x01010101u + 0x7F7F7F7Fu;
+            uint32_t acc = 0;
+#pragma unroll
+            for (int w = 0; w < 4; ++w) acc = dp4a_u(cw[w], (base - qw[w]) & 0x80808080u, acc);
+            const uint32_t want = k - (acc >> 7), cnt = (pl.cntw >> (8 * i)) & 0xFFu;
+            const bool h = want < cnt;
+            hit |= h;
+            hsq = h ? sq : hsq; hdesc = h ? pl.desc[i] : hdesc; hwant = h ? want : hwant; htype = h ? (i == 0 ? 0u : (R.types >> (8 * i)) & 0xFFu) : htype;
+        }
+        if (hit) {
+            const int to_s = slider_decode(hdesc, (int)hsq, (int)hwant);
+            const int to_l = (int)hsq + leaper_dir((int)htype, nth_set_bit8(hdesc & 0xFFu, (int)hwant & 7), st.player);
+            sh.move[lane] = hsq | ((uint32_t)(htype == 0 ? to_s : to_l) << 8);
+        }
+    }
+}
+
+// ---- phase C: every thread applies the move to its replica; the thread owning the captured slot publishes value | code -------
+// ChessBoard::movePiece (src/chessboard.cpp:38-64), checkGameOver / getWinner (:286-320), reset (:95-102)
+template <int KB>
+XQ_HD void team_phase_c(const TeamRole& R, TeamState& st, const TeamPly& pl, TeamShared<KB>& sh, TeamBook& bk, int lane, int p) {
+    if (pl.total > 0) {
+        const uint32_t mv = sh.move[lane];
+        const int from = (int)(mv & 0xFFu), to = (int)((mv >> 8) & 0xFFu);
+        const int mover = st.player;
+        // is one of my pieces of the side NOT moving on `to`?  x has a zero byte there; bytes <= 127, so 0x80 - byte never borrows
+        uint32_t z = (0x80808080u - (st.sq_opp ^ ((uint32_t)to * 0x01010101u))) & 0x80808080u;
+        if (z) {
+            const int sh8 = ffs32(z) - 8;                                   // 8 * position
+            const uint32_t type = (R.types >> sh8) & 0xFFu, sc5 = (R.score5 >> sh8) & 0xFFu;
+            sh.cap[(p & 1) * KB + lane] = (sc5 * 5u) | ((type + (mover ? 0u : 7u)) << 16);
+            st.sq_opp |= (z >> 7) * 0x7Fu;                                 // captured: square 127
+        }
+        z = (0x80808080u - (st.sq_own ^ ((uint32_t)from * 0x01010101u))) & 0x80808080u;
+        const uint32_t m8 = (z >> 7) * 0xFFu;
+        st.sq_own = (st.sq_own & ~m8) | (((uint32_t)to * 0x01010101u) & m8);
+        const int fr = row_of(from), tr = row_of(to);
+        const Bits90 fm = bit_mask(from), tm = bit_mask(to);
+        const Bits90 cf = bit_mask(cm_index(fr, from - 9 * fr)), ct = bit_mask(cm_index(tr, to - 9 * tr));
+        st.own = Bits90{(st.own.w0 & ~fm.w0) | tm.w0, (st.own.w1 & ~fm.w1) | tm.w1, (st.own.w2 & ~fm.w2) | tm.w2};
+        st.opp.andnot(tm);
+        st.occT = Bits90{(st.occT.w0 & ~cf.w0) | ct.w0, (st.occT.w1 & ~cf.w1) | ct.w1, (st.occT.w2 & ~cf.w2) | ct.w2};
+        const bool took_general = to == st.gen_opp;
+        if (from == st.gen_own) st.gen_own = to;
+        st.move_count++; st.ctr++;
+        const bool over = took_general || st.move_count >= XQ_MAX_MOVES;
+        if (R.role == 0) {
+            // getWinner: colour of the first General in square order
+            const int gen_red = mover ? st.gen_opp : st.gen_own, gen_black = mover ? st.gen_own : st.gen_opp;
+            const int win = took_general ? mover : (gen_red < gen_black ? RED : BLACK);
+            bk.pend = 1u | ((uint32_t)mover << 2) | ((uint32_t)over << 3) | ((uint32_t)win << 4) | ((uint32_t)st.move_count << 8) | (pl.total << 16);
+            bk.pend_p = p;
+            bk.pend_tr0 = (uint32_t)XQ_ACTION(from, to) | (pl.total << 16) | ((uint32_t)((over ? 1 : 0) | ((over ? win : NOCOLOR) << 1)) << 24);
+        }
+        if (over) {
+            const uint32_t c = st.ctr; team_reset(R, st); st.ctr = c;
+        } else {   // the other side is to move
+            const uint32_t s = st.sq_own; st.sq_own = st.sq_opp; st.sq_opp = s;
+            const Bits90 b = st.own; st.own = st.opp; st.opp = b;
+            const int g = st.gen_own; st.gen_own = st.gen_opp; st.gen_opp = g;
+            st.player ^= 1;
+        }
+    } else {   // no legal action: the episode loop ends (chessai.cpp:100-103); the slot restarts
+        const uint32_t c = st.ctr + 1; team_reset(R, st); st.ctr = c;
+        if (R.role == 0) { bk.pend = 2; bk.pend_p = p; bk.pend_tr0 = (uint32_t)XQ_ACTION_NONE | ((uint32_t)(1 | (NOCOLOR << 1)) << 24); }
+    }
+}
+
+// ---- record <-> slots (once per launch) ---------------------------------------------------------------------------------------
+// put(slot 0..31, square); returns false for a board whose piece counts exceed a standard set (left to the generic kernel)
+template <class PUT>
+XQ_HD bool team_unpack_record(const uint32_t (&w)[12], Bits90& red, Bits90& black, Bits90& occT, PUT&& put) {
+    bool ok = true;
+    uint64_t cnt = 0;   // 4-bit counter per piece code
+    red = black = occT = Bits90{0, 0, 0};
+#pragma unroll
+    for (int wi = 0; wi < 12; ++wi) {
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+            const int s = wi * 8 + i;
+            const int code = (int)((w[wi] >> (4 * i)) & 15u);
+            if (s < 90 && code != 0) {
+                const int t = type_of(code);
+                const int ord = (int)((cnt >> (4 * code)) & 15);
+                if (code == 15 || ord >= slot_cap(t)) { ok = false; }
+                else {
+                    put((code >= 8 ? 16 : 0) + slot_base(t) + ord, s);
+                    cnt += 1ull << (4 * code);
+                    if (code >= 8) black.set(s); else red.set(s);
+                    const int r = row_of(s);
+                    occT.set(cm_index(r, s - 9 * r));
+                }
+            }
+        }
+    }
+    return ok;
+}
+
+}  // namespace xq

@@ -6,6 +6,7 @@
 #include <cstring>
 #include "../../cn_chess_ai_b200/csrc/xq_rules.cuh"
 #include "../../cn_chess_ai_b200/csrc/xq_bitboard.cuh"
+#include "../../cn_chess_ai_b200/csrc/xq_rollout_team.cuh"
 #include "../../include/xq.h"
 
 namespace {
@@ -15,7 +16,89 @@ struct RecBoard {
 };
 }
 
+// ---- the team rollout kernel's ply (xq_rollout_team.cuh), one board at a time: the 4 threads of a board run phase by phase ----
+namespace {
+using namespace xq;
+int team_rollout_host(xq_env_rec* recs, long n, uint64_t env_id0, uint64_t seed, int n_plies, xq_trace_rec* trace, xq_env_stats* stats) {
+    constexpr int T = kTeam;
+    int nonstd = 0;
+    for (long env = 0; env < n; ++env) {
+        TeamShared<1> sh;
+        for (int d = 1; d <= XQ_MAX_ACTIONS; ++d) sh.magic[d] = team_mod_magic((uint32_t)d);
+        uint8_t slot[32];
+        for (int i = 0; i < 32; ++i) slot[i] = kDeadSq;
+        uint32_t w[12];
+        std::memcpy(w, recs[env].sq, 48);
+        Bits90 red, black, occT;
+        if (!team_unpack_record(w, red, black, occT, [&](int s, int q) { slot[s] = (uint8_t)q; })) { ++nonstd; continue; }
+        TeamRole R[T];
+        TeamState st[T];
+        TeamPly pl[T];
+        TeamBook bk{0, 0, 1480, 1480, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0};
+        bk.red = recs[env].red_score; bk.black = recs[env].black_score;
+        bk.mat_red = bk.mat_black = 0;
+        for (int i = 0; i < 16; ++i) {
+            if (slot[i] != kDeadSq) bk.mat_red += piece_score(slot_type(i));
+            if (slot[16 + i] != kDeadSq) bk.mat_black += piece_score(slot_type(i));
+        }
+        const bool finished = recs[env].move_count >= XQ_MAX_MOVES || slot[8] == kDeadSq || slot[24] == kDeadSq;
+        if (finished) { bk.red = bk.black = 0; bk.mat_red = bk.mat_black = 1480; }
+        for (int r = 0; r < T; ++r) {
+            R[r] = team_role(r);
+            team_reset(R[r], st[r]);
+            st[r].ctr = recs[env].ctr;
+            if (finished) continue;
+            uint32_t wr = 0, wb = 0;
+            for (int i = 0; i < 4; ++i) {
+                const int s = (int)((R[r].slots >> (8 * i)) & 0xFFu);
+                wr |= (uint32_t)slot[s] << (8 * i);
+                wb |= (uint32_t)slot[16 + s] << (8 * i);
+            }
+            st[r].occT = occT; st[r].move_count = recs[env].move_count; st[r].player = recs[env].player;
+            const bool redp = recs[env].player == 0;
+            st[r].sq_own = redp ? wr : wb; st[r].sq_opp = redp ? wb : wr;
+            st[r].own = redp ? red : black; st[r].opp = redp ? black : red;
+            st[r].gen_own = redp ? slot[8] : slot[24]; st[r].gen_opp = redp ? slot[24] : slot[8];
+        }
+        const uint64_t base = seed + (env_id0 + (uint64_t)env) * 0x9E3779B97F4A7C15ull;
+        const uint32_t ctr0 = st[0].ctr;
+        for (int r = 0; r < T; ++r) team_rng_chunk<1>(R[r], sh, 0, 0, base, ctr0);
+        for (int p = 0; p < n_plies; ++p) {
+            if ((p & 15) == 0) for (int r = 0; r < T; ++r) team_rng_chunk<1>(R[r], sh, 0, (p >> 4) + 1, base, ctr0);
+            for (int r = 0; r < T; ++r) team_phase_a<1>(R[r], st[r], pl[r], sh, 0, p);
+            team_finalize<1>(bk, sh, 0, trace, n, env);
+            for (int r = 0; r < T; ++r) team_phase_b<1>(R[r], st[r], pl[r], sh, 0, p);
+            for (int r = 0; r < T; ++r) team_phase_c<1>(R[r], st[r], pl[r], sh, bk, 0, p);
+        }
+        team_finalize<1>(bk, sh, 0, trace, n, env);
+        // store
+        for (int r = 0; r < T; ++r) {
+            const uint32_t wr = st[r].player == 0 ? st[r].sq_own : st[r].sq_opp, wb = st[r].player == 0 ? st[r].sq_opp : st[r].sq_own;
+            for (int i = 0; i < 4; ++i) {
+                const int s = (int)((R[r].slots >> (8 * i)) & 0xFFu);
+                slot[s] = (uint8_t)(wr >> (8 * i)); slot[16 + s] = (uint8_t)(wb >> (8 * i));
+            }
+        }
+        uint32_t words[12] = {0};
+        for (int i = 0; i < 32; ++i)
+            if (slot[i] != kDeadSq) words[slot[i] >> 3] |= (uint32_t)(slot_type(i & 15) + (i >= 16 ? 7 : 0)) << (4 * (slot[i] & 7));
+        std::memcpy(recs[env].sq, words, 48);
+        recs[env].move_count = (uint16_t)st[0].move_count; recs[env].player = (uint8_t)st[0].player;
+        recs[env].red_score = bk.red; recs[env].black_score = bk.black; recs[env].ctr = st[0].ctr;
+        if (stats) {
+            stats->steps += bk.a_steps; stats->games += bk.a_games; stats->red_wins += bk.a_red; stats->black_wins += bk.a_black;
+            stats->cap_games += bk.a_capg; stats->captures += bk.a_caps; stats->reward_sum += bk.a_reward; stats->legal_sum += bk.a_legal;
+        }
+    }
+    return nonstd;
+}
+}
+
 extern "C" {
+// whole fused rollout through the team kernel's phases; returns the number of boards it does not handle (non-standard piece sets)
+int hs_team_rollout(xq_env_rec* recs, long n, uint64_t env_id0, uint64_t seed, int n_plies, xq_trace_rec* trace, xq_env_stats* stats) {
+    return team_rollout_host(recs, n, env_id0, seed, n_plies, trace, stats);
+}
 void hs_all_actions(const xq_env_rec* recs, long n, uint8_t* counts, uint16_t* actions) {
     for (long i = 0; i < n; ++i) {
         RecBoard b{recs[i].sq};
