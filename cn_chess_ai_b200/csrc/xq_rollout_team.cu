@@ -31,6 +31,7 @@ __global__ void __launch_bounds__(kTB * kTeam) rollout_team_kernel(xq_env_rec* _
     const TeamRole R = team_role(tid >> 5);
     const int64_t env = (int64_t)blockIdx.x * kTB + lane;
     for (int d = tid + 1; d <= XQ_MAX_ACTIONS; d += kTB * kTeam) sh.magic[d] = team_mod_magic((uint32_t)d);
+    if (tid < kTB) sh.move[tid] = 0;
 
     // ---- load: warp 0 converts 32 records to slots + bitboards ----------------------------------
     if (R.role == 0) {
@@ -96,23 +97,22 @@ __global__ void __launch_bounds__(kTB * kTeam) rollout_team_kernel(xq_env_rec* _
         }
         rng_base = seed + (env_id0 + (uint64_t)env) * 0x9E3779B97F4A7C15ull;
     }
+    // lanes without a board (tail of the last CTA, non-standard piece sets) play a private game from the opening: the ply loop has no
+    // `active` test; they get no trace, no statistics and no store
+    xq_trace_rec* const my_trace = active ? trace : nullptr;
     const uint32_t ctr0 = st.ctr;
-    if (active) team_rng_chunk<kTB>(R, sh, lane, 0, rng_base, ctr0);
+    team_rng_chunk<kTB>(R, sh, lane, 0, rng_base, ctr0);
     __syncthreads();
     TeamPly pl;
 #pragma unroll 1
     for (int p = 0; p < n_plies; ++p) {
-        if (active) {
-            if ((p & 15) == 0) team_rng_chunk<kTB>(R, sh, lane, (p >> 4) + 1, rng_base, ctr0);   // read from ply p + 16 on
-            team_phase_a<kTB>(R, st, pl, sh, lane, p);
-        }
+        if ((p & 15) == 0) team_rng_chunk<kTB>(R, sh, lane, (p >> 4) + 1, rng_base, ctr0);   // read from ply p + 16 on
+        team_phase_a<kTB>(R, st, pl, sh, lane, p);
         __syncthreads();
-        if (active) {
-            if (R.role == 0) team_finalize<kTB>(bk, sh, lane, trace, n, env);
-            team_phase_b<kTB>(R, st, pl, sh, lane, p);
-        }
+        if (R.role == 0) team_finalize<kTB>(bk, sh, lane, my_trace, n, env);
+        team_phase_b<kTB>(R, st, pl, sh, lane, p);
         __syncthreads();
-        if (active) team_phase_c<kTB>(R, st, pl, sh, bk, lane, p);
+        team_phase_c<kTB>(R, st, pl, sh, bk, lane, p);
     }
     if (active) {
         const uint32_t wr = st.player == RED ? st.sq_own : st.sq_opp, wb = st.player == RED ? st.sq_opp : st.sq_own;
@@ -128,7 +128,7 @@ __global__ void __launch_bounds__(kTB * kTeam) rollout_team_kernel(xq_env_rec* _
     // ---- store: slots -> nibble board ---------------------------------------------------------------
     if (R.role == 0) {
         if (active) {
-            team_finalize<kTB>(bk, sh, lane, trace, n, env);      // the last ply
+            team_finalize<kTB>(bk, sh, lane, my_trace, n, env);      // the last ply
             for (int i = 0; i < 12; ++i) io.words[i * kTB + lane] = 0;
             for (int i = 0; i < 32; ++i) {
                 const int q = io.slot[i * kTB + lane];

@@ -49,6 +49,9 @@ struct TeamRole {
     uint32_t types;                // PieceType of position i in byte i
     uint32_t score5;               // piece value / 5
     uint32_t open_red, open_black; // opening squares of my slots (ChessBoard::initializeBoard, src/chessboard.cpp:13-28)
+    // destination offsets of the leaper at position 1..3, one signed byte per direction in the order of generate*Moves
+    // (src/chessboard.cpp:150,163,180,249,267-281); a Soldier's table is Red's, `sold` has 0xFE in its byte 0 to flip 9 into -9
+    uint32_t tab1_lo, tab1_hi, tab2, tab3, sold2, sold3;
 };
 constexpr int open_sq_c(int s) {   // opening square of slot s (0..15 Red, 16..31 Black)
     constexpr uint8_t t[32] = {0, 8, 1, 7, 2, 6, 3, 5, 4, 19, 25, 27, 29, 31, 33, 35, 81, 89, 82, 88, 83, 87, 84, 86, 85, 64, 70, 54, 56, 58, 60, 62};
@@ -78,6 +81,11 @@ XQ_HD TeamRole team_role(int role) {
 #define XQ_F_OPEN_B(i) team_open_c(i, 1)
     r.slots = XQ_TEAM_SEL(team_slots_c); r.types = XQ_TEAM_SEL(team_types_c); r.score5 = XQ_TEAM_SEL(team_score5_c);
     r.open_red = XQ_TEAM_SEL(XQ_F_OPEN_R); r.open_black = XQ_TEAM_SEL(XQ_F_OPEN_B);
+    constexpr uint32_t kHorseLo = 0xF5F9070Bu, kHorseHi = 0xEDEF1113u;      // 11,7,-7,-11 | 19,17,-17,-19
+    constexpr uint32_t kAdvisor = 0xF6F8080Au, kElephant = 0xECF01014u, kGeneral = 0xFF01F709u, kSoldier = 0x0001FF09u;   // Soldier (Red): 9,-1,1
+    r.tab1_lo = r.hi ? kAdvisor : kHorseLo; r.tab1_hi = r.hi ? 0u : kHorseHi;
+    r.tab2 = r.hi ? kElephant : kSoldier; r.sold2 = r.hi ? 0u : 0xFEu;
+    r.tab3 = role == 2 ? kGeneral : kSoldier; r.sold3 = role == 2 ? 0u : 0xFEu;
 #undef XQ_F_OPEN_R
 #undef XQ_F_OPEN_B
     return r;
@@ -181,16 +189,6 @@ XQ_HD int nth_set_bit8(uint32_t m, int j) {
     j -= h2 ? c : 0; m = h2 ? m >> 2 : m;
     return (h4 ? 4 : 0) + (h2 ? 2 : 0) + ((j >= (int)(m & 1u)) ? 1 : 0);
 }
-// destination of direction k of a leaper of `type` (direction tables of generate*Moves, src/chessboard.cpp:150,163,180,249,267-281)
-XQ_HD int leaper_dir(int type, int k, int color) {
-    const uint64_t tab = type == HORSE ? 0xEDEF1113F5F9070Bull            // 11,7,-7,-11,19,17,-17,-19
-                       : (type == ELEPHANT ? 0xECF01014ull                   // 20,16,-16,-20
-                       : (type == ADVISOR ? 0xF6F8080Aull                    // 10,8,-8,-10
-                       : 0xFF01F709ull));                                    // General: 9,-9,1,-1
-    const int d = (int)(int8_t)(uint8_t)(tab >> (8 * k));
-    return type == SOLDIER ? soldier_dir(k, color) : d;
-}
-
 // ---- phase A: every thread counts the moves of its 4 pieces of the side to move and publishes (squares, counts) -------------
 template <int KB>
 XQ_HD void team_phase_a(const TeamRole& R, const TeamState& st, TeamPly& pl, TeamShared<KB>& sh, int lane, int p) {
@@ -258,8 +256,9 @@ XQ_HD void team_phase_b(const TeamRole& R, const TeamState& st, TeamPly& pl, Tea
         const uint32_t draw = sh.rng[(((p >> 4) & 1) * 16 + (p & 15)) * KB + lane];
         const uint32_t k = team_mod(draw, tot, sh.magic[tot]);
         // which of my pieces (if any) owns the k-th action of the reference-ordered list: selects only, then ONE decode
-        uint32_t hsq = 0, hdesc = 0, hwant = 0, htype = 0;
-        bool hit = false;
+        uint32_t hsq = 0, hdesc = 0, hwant = 0, hlo = 0, hhi = 0;
+        bool hit = false, hslider = false;
+        const uint32_t flip = st.player ? 0xFFFFFFFFu : 0u;          // a Black Soldier moves towards row 0
 #pragma unroll
         for (int i = 0; i < 4; ++i) {
             const uint32_t sq = (st.sq_own >> (8 * i)) & 0xFFu;
@@ -271,12 +270,17 @@ XQ_HD void team_phase_b(const TeamRole& R, const TeamState& st, TeamPly& pl, Tea
             const uint32_t want = k - (acc >> 7), cnt = (pl.cntw >> (8 * i)) & 0xFFu;
             const bool h = want < cnt;
             hit |= h;
-            hsq = h ? sq : hsq; hdesc = h ? pl.desc[i] : hdesc; hwant = h ? want : hwant; htype = h ? (i == 0 ? 0u : (R.types >> (8 * i)) & 0xFFu) : htype;
+            hsq = h ? sq : hsq; hdesc = h ? pl.desc[i] : hdesc; hwant = h ? want : hwant;
+            if (i == 0) hslider = h;
+            if (i == 1) { hlo = h ? R.tab1_lo : hlo; hhi = h ? R.tab1_hi : hhi; }
+            if (i == 2) hlo = h ? (R.tab2 ^ (R.sold2 & flip)) : hlo;
+            if (i == 3) hlo = h ? (R.tab3 ^ (R.sold3 & flip)) : hlo;
         }
         if (hit) {
             const int to_s = slider_decode(hdesc, (int)hsq, (int)hwant);
-            const int to_l = (int)hsq + leaper_dir((int)htype, nth_set_bit8(hdesc & 0xFFu, (int)hwant & 7), st.player);
-            sh.move[lane] = hsq | ((uint32_t)(htype == 0 ? to_s : to_l) << 8);
+            const int dk = nth_set_bit8(hdesc & 0xFFu, (int)hwant & 7);
+            const int to_l = (int)hsq + (int)(int8_t)(uint8_t)((((uint64_t)hhi << 32) | hlo) >> (8 * dk));
+            sh.move[lane] = hsq | ((uint32_t)(hslider ? to_s : to_l) << 8);
         }
     }
 }
@@ -285,49 +289,50 @@ XQ_HD void team_phase_b(const TeamRole& R, const TeamState& st, TeamPly& pl, Tea
 // ChessBoard::movePiece (src/chessboard.cpp:38-64), checkGameOver / getWinner (:286-320), reset (:95-102)
 template <int KB>
 XQ_HD void team_phase_c(const TeamRole& R, TeamState& st, const TeamPly& pl, TeamShared<KB>& sh, TeamBook& bk, int lane, int p) {
-    if (pl.total > 0) {
-        const uint32_t mv = sh.move[lane];
-        const int from = (int)(mv & 0xFFu), to = (int)((mv >> 8) & 0xFFu);
-        const int mover = st.player;
-        // is one of my pieces of the side NOT moving on `to`?  x has a zero byte there; bytes <= 127, so 0x80 - byte never borrows
-        uint32_t z = (0x80808080u - (st.sq_opp ^ ((uint32_t)to * 0x01010101u))) & 0x80808080u;
-        if (z) {
-            const int sh8 = ffs32(z) - 8;                                   // 8 * position
-            const uint32_t type = (R.types >> sh8) & 0xFFu, sc5 = (R.score5 >> sh8) & 0xFFu;
-            sh.cap[(p & 1) * KB + lane] = (sc5 * 5u) | ((type + (mover ? 0u : 7u)) << 16);
-            st.sq_opp |= (z >> 7) * 0x7Fu;                                 // captured: square 127
-        }
-        z = (0x80808080u - (st.sq_own ^ ((uint32_t)from * 0x01010101u))) & 0x80808080u;
-        const uint32_t m8 = (z >> 7) * 0xFFu;
-        st.sq_own = (st.sq_own & ~m8) | (((uint32_t)to * 0x01010101u) & m8);
-        const int fr = row_of(from), tr = row_of(to);
-        const Bits90 fm = bit_mask(from), tm = bit_mask(to);
-        const Bits90 cf = bit_mask(cm_index(fr, from - 9 * fr)), ct = bit_mask(cm_index(tr, to - 9 * tr));
-        st.own = Bits90{(st.own.w0 & ~fm.w0) | tm.w0, (st.own.w1 & ~fm.w1) | tm.w1, (st.own.w2 & ~fm.w2) | tm.w2};
-        st.opp.andnot(tm);
-        st.occT = Bits90{(st.occT.w0 & ~cf.w0) | ct.w0, (st.occT.w1 & ~cf.w1) | ct.w1, (st.occT.w2 & ~cf.w2) | ct.w2};
-        const bool took_general = to == st.gen_opp;
-        if (from == st.gen_own) st.gen_own = to;
-        st.move_count++; st.ctr++;
-        const bool over = took_general || st.move_count >= XQ_MAX_MOVES;
-        if (R.role == 0) {
-            // getWinner: colour of the first General in square order
-            const int gen_red = mover ? st.gen_opp : st.gen_own, gen_black = mover ? st.gen_own : st.gen_opp;
-            const int win = took_general ? mover : (gen_red < gen_black ? RED : BLACK);
-            bk.pend = 1u | ((uint32_t)mover << 2) | ((uint32_t)over << 3) | ((uint32_t)win << 4) | ((uint32_t)st.move_count << 8) | (pl.total << 16);
-            bk.pend_p = p;
-            bk.pend_tr0 = (uint32_t)XQ_ACTION(from, to) | (pl.total << 16) | ((uint32_t)((over ? 1 : 0) | ((over ? win : NOCOLOR) << 1)) << 24);
-        }
-        if (over) {
-            const uint32_t c = st.ctr; team_reset(R, st); st.ctr = c;
-        } else {   // the other side is to move
-            const uint32_t s = st.sq_own; st.sq_own = st.sq_opp; st.sq_opp = s;
-            const Bits90 b = st.own; st.own = st.opp; st.opp = b;
-            const int g = st.gen_own; st.gen_own = st.gen_opp; st.gen_opp = g;
-            st.player ^= 1;
-        }
-    } else {   // no legal action: the episode loop ends (chessai.cpp:100-103); the slot restarts
-        const uint32_t c = st.ctr + 1; team_reset(R, st); st.ctr = c;
+    // straight-line for the common case; with no legal action (pl.total == 0, below) the stale move read here is discarded
+    const uint32_t mv = sh.move[lane];
+    const int from = (int)(mv & 0xFFu), to = (int)((mv >> 8) & 0xFFu);
+    const int mover = st.player;
+    // is one of my pieces of the side NOT moving on `to`?  x has a zero byte there; bytes <= 127, so 0x80 - byte never borrows
+    uint32_t z = (0x80808080u - (st.sq_opp ^ ((uint32_t)to * 0x01010101u))) & 0x80808080u;
+    if (z) {
+        const int sh8 = ffs32(z) - 8;                                   // 8 * position
+        const uint32_t type = (R.types >> sh8) & 0xFFu, sc5 = (R.score5 >> sh8) & 0xFFu;
+        sh.cap[(p & 1) * KB + lane] = (sc5 * 5u) | ((type + (mover ? 0u : 7u)) << 16);
+    }
+    const uint32_t sq_opp = st.sq_opp | (z >> 7) * 0x7Fu;                 // captured: square 127
+    z = (0x80808080u - (st.sq_own ^ ((uint32_t)from * 0x01010101u))) & 0x80808080u;
+    const uint32_t m8 = (z >> 7) * 0xFFu;
+    const uint32_t sq_own = (st.sq_own & ~m8) | (((uint32_t)to * 0x01010101u) & m8);
+    const int fr = row_of(from), tr = row_of(to);
+    const Bits90 fm = bit_mask(from), tm = bit_mask(to);
+    const Bits90 cf = bit_mask(cm_index(fr, from - 9 * fr)), ct = bit_mask(cm_index(tr, to - 9 * tr));
+    const Bits90 own{(st.own.w0 & ~fm.w0) | tm.w0, (st.own.w1 & ~fm.w1) | tm.w1, (st.own.w2 & ~fm.w2) | tm.w2};
+    const Bits90 opp{st.opp.w0 & ~tm.w0, st.opp.w1 & ~tm.w1, st.opp.w2 & ~tm.w2};
+    const Bits90 occT{(st.occT.w0 & ~cf.w0) | ct.w0, (st.occT.w1 & ~cf.w1) | ct.w1, (st.occT.w2 & ~cf.w2) | ct.w2};
+    const bool took_general = to == st.gen_opp;
+    const int gen_own = from == st.gen_own ? to : st.gen_own;
+    const int mc = st.move_count + 1;
+    st.ctr++;
+    const bool over = took_general | (mc >= XQ_MAX_MOVES);
+    if (R.role == 0) {
+        // getWinner: colour of the first General in square order
+        const int gen_red = mover ? st.gen_opp : gen_own, gen_black = mover ? gen_own : st.gen_opp;
+        const int win = took_general ? mover : (gen_red < gen_black ? RED : BLACK);
+        bk.pend = 1u | ((uint32_t)mover << 2) | ((uint32_t)over << 3) | ((uint32_t)win << 4) | ((uint32_t)mc << 8) | (pl.total << 16);
+        bk.pend_p = p;
+        bk.pend_tr0 = (uint32_t)XQ_ACTION(from, to) | (pl.total << 16) | ((uint32_t)((over ? 1 : 0) | ((over ? win : NOCOLOR) << 1)) << 24);
+    }
+    // the other side is to move -- or, after the last move of a game, Red from the opening (ChessBoard::reset): selects, no branch
+    const Bits90 o_red = team_open_red(), o_black = team_open_black(), o_occT = team_open_occT();
+    st.sq_own = over ? R.open_red : sq_opp; st.sq_opp = over ? R.open_black : sq_own;
+    st.own = Bits90{over ? o_red.w0 : opp.w0, over ? o_red.w1 : opp.w1, over ? o_red.w2 : opp.w2};
+    st.opp = Bits90{over ? o_black.w0 : own.w0, over ? o_black.w1 : own.w1, over ? o_black.w2 : own.w2};
+    st.occT = Bits90{over ? o_occT.w0 : occT.w0, over ? o_occT.w1 : occT.w1, over ? o_occT.w2 : occT.w2};
+    st.gen_own = over ? 4 : st.gen_opp; st.gen_opp = over ? 85 : gen_own;
+    st.move_count = over ? 0 : mc; st.player = over ? RED : (mover ^ 1);
+    if (pl.total == 0) {   // no legal action: the episode loop ends (chessai.cpp:100-103); the slot restarts (the counter advanced above)
+        const uint32_t c = st.ctr; team_reset(R, st); st.ctr = c;
         if (R.role == 0) { bk.pend = 2; bk.pend_p = p; bk.pend_tr0 = (uint32_t)XQ_ACTION_NONE | ((uint32_t)(1 | (NOCOLOR << 1)) << 24); }
     }
 }
