@@ -204,7 +204,7 @@ def main():
     total_steps = E * P * args.steps * world
     value = total_steps / (ms_max * 1e-3)
 
-    # ---- end-to-end leg through the host-buffer C ABI: set_boards -> rollout -> get_boards + stats ----
+    # ---- end-to-end leg through the host-buffer C ABI: xq_env_rollout_random_io = set_boards -> rollout -> get_boards + stats ----
     host_in = np.zeros(E, dtype=xq.ENV_DTYPE)
     host_in[:] = env.get_boards()
     pin_in = torch.from_numpy(host_in.view(np.uint8)).pin_memory()
@@ -212,14 +212,12 @@ def main():
     recs_in = pin_in.numpy().view(xq.ENV_DTYPE)
     recs_out = pin_out.numpy().view(xq.ENV_DTYPE)
     for _ in range(2):
-        env.set_boards(recs_in); env.rollout_random(P); env.get_boards(out=recs_out)
+        env.rollout_random_io(recs_in, P, recs_out)
     barrier()
     t0 = time.perf_counter()
     e2e_steps = 0
     for _ in range(args.steps):
-        env.set_boards(recs_in)
-        s, _ = env.rollout_random(P)
-        env.get_boards(out=recs_out)
+        s, _ = env.rollout_random_io(recs_in, P, recs_out)      # pinned host boards in, pinned host boards + stats out
         e2e_steps += int(s["steps"])
     torch.cuda.synchronize()
     e2e_s = time.perf_counter() - t0
@@ -236,8 +234,9 @@ def main():
     tp = os.path.join(ROOT, "profiles", "traffic.json")
     if os.path.exists(tp):
         tj = json.load(open(tp))
-        traffic = tj.get("rollout_slots_kernel_dram_bytes_per_launch")
-        inst_per_step = tj.get("rollout_slots_kernel_warp_inst_per_step")
+        if (E, P) == (4096, 200):       # the capture is of this workload
+            traffic = tj.get("rollout_kernel_dram_bytes_per_launch")
+        inst_per_step = tj.get("rollout_kernel_warp_inst_per_step")
 
     line = {"metric": "env steps/s (movegen+step, random policy)", "value": value, "unit": "steps/s", "n_gpus": world,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": kernel_ms, "higher_is_better": True, "scaling": "weak",
@@ -250,7 +249,7 @@ def main():
                     "d2h_bytes_per_step": int(recs_out.nbytes) + 64},
             "gpu_launches": int(launches),
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": pk["hbm_gbs"], "unit": "GB/s", "frac": achieved / pk["hbm_gbs"],
-                         "traffic": traffic, "kernel": "rollout_slots_kernel", "peak_source": pk["source"],
+                         "traffic": traffic, "kernel": "rollout_team_kernel", "peak_source": pk["source"],
                          "algorithmic_bytes_per_launch": ALGO_BYTES_PER_STEP * E * P,
                          "note": "integer/latency-bound by design: boards stay on chip for all plies of a launch (DESIGN.md)"},
             "clocks": clocks}

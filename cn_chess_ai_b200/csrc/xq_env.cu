@@ -273,14 +273,15 @@ static inline unsigned grid_for(int64_t n, int per_block) { return (unsigned)((n
 namespace xq {
 cudaError_t launch_rollout_slots(xq_env_rec* envs, int64_t n, uint64_t env_id0, uint64_t seed, int n_plies, xq_trace_rec* trace,
                                  xq_env_stats* stats, uint8_t* nonstd, cudaStream_t stream);
-cudaError_t launch_rollout_team(xq_env_rec* envs, int64_t n, uint64_t env_id0, uint64_t seed, int n_plies, xq_trace_rec* trace,
+cudaError_t launch_rollout_team(int team, xq_env_rec* envs, int64_t n, uint64_t env_id0, uint64_t seed, int n_plies, xq_trace_rec* trace,
                                 xq_env_stats* stats, uint8_t* nonstd, cudaStream_t stream);
 }
-// threads per board of the fused rollout kernel: 4 = rollout_team_kernel (xq_rollout_team.cu, the default: faster at every env
-// count measured, 4096 .. 1M), 16 = rollout_slots_kernel (xq_rollout.cu, kept for A/B runs: XQ_ROLLOUT_TEAM=16).  Bit-identical.
+// threads per board of the fused rollout kernel: 4 = rollout_team_kernel<4> (xq_rollout_team.cu), the default at every env count;
+// 8 = rollout_team_kernel<8> (twice the warps per board: measured equal at 4096 envs, slower from 8192 envs on) and
+// 16 = rollout_slots_kernel (xq_rollout.cu) are kept for A/B runs: XQ_ROLLOUT_TEAM=8|16.  All three are bit-identical.
 static int rollout_team() {
     static const int forced = [] { const char* e = getenv("XQ_ROLLOUT_TEAM"); return e ? atoi(e) : 0; }();
-    return forced == 16 ? 16 : 4;
+    return forced == 8 || forced == 16 ? forced : 4;
 }
 // Fused rollout = team kernel (xq_rollout_team.cu; or the 16-thread slot kernel, xq_rollout.cu) for every board with a standard piece set, then the generic
 // thread-per-board kernel for the boards it flagged (only possible after xq_env_set_boards injected exotic positions).
@@ -288,7 +289,7 @@ static int launch_rollout(xq_env_s* h, int n_plies, xq_trace_rec* d_trace) {
     if (n_plies >= (1 << 24)) return fail(XQ_ERR_INVALID, "rollout: n_plies must be < 2^24 per launch");
     const int team = rollout_team();
     if (team == 16) XQ_CUDA(launch_rollout_slots(h->d_envs, h->n, h->env_id0, h->seed, n_plies, d_trace, h->d_stats, h->d_nonstd, h->stream));
-    else XQ_CUDA(launch_rollout_team(h->d_envs, h->n, h->env_id0, h->seed, n_plies, d_trace, h->d_stats, h->d_nonstd, h->stream));
+    else XQ_CUDA(launch_rollout_team(team, h->d_envs, h->n, h->env_id0, h->seed, n_plies, d_trace, h->d_stats, h->d_nonstd, h->stream));
     if (h->maybe_nonstd) {
         rollout_random_kernel<<<grid_for(h->n, kThreads), kThreads, 0, h->stream>>>(h->d_envs, h->n, h->env_id0, h->seed, n_plies, d_trace,
                                                                                     h->d_stats, h->d_nonstd);
@@ -506,7 +507,8 @@ int xq_env_drain_game_events(xq_env_t h, xq_game_event* out_host, int64_t max_ev
     return XQ_OK;
 }
 
-int xq_env_rollout_random(xq_env_t h, int n_plies, xq_trace_rec* trace_host, xq_env_stats* stats_host) {
+int xq_env_rollout_random_io(xq_env_t h, const xq_env_rec* boards_in_host, int n_plies, xq_env_rec* boards_out_host,
+                             xq_trace_rec* trace_host, xq_env_stats* stats_host) {
     XQ_ENV_ENTER(h);
     if (n_plies < 0) return fail(XQ_ERR_INVALID, "xq_env_rollout_random: n_plies < 0");
     const int64_t need = (int64_t)n_plies * h->n;
@@ -515,12 +517,20 @@ int xq_env_rollout_random(xq_env_t h, int n_plies, xq_trace_rec* trace_host, xq_
         XQ_CUDA(cudaMalloc(&h->d_trace, sizeof(xq_trace_rec) * need));
         h->trace_cap = need;
     }
+    if (boards_in_host) {
+        XQ_CUDA(cudaMemcpyAsync(h->d_envs, boards_in_host, sizeof(xq_env_rec) * h->n, cudaMemcpyHostToDevice, h->stream));
+        h->maybe_nonstd = true;
+    }
     XQ_CUDA(cudaMemsetAsync(h->d_stats, 0, sizeof(xq_env_stats), h->stream));
     if (int rc = launch_rollout(h, n_plies, trace_host ? h->d_trace : nullptr)) return rc;
+    if (boards_out_host) XQ_CUDA(cudaMemcpyAsync(boards_out_host, h->d_envs, sizeof(xq_env_rec) * h->n, cudaMemcpyDeviceToHost, h->stream));
     if (trace_host) XQ_CUDA(cudaMemcpyAsync(trace_host, h->d_trace, sizeof(xq_trace_rec) * need, cudaMemcpyDeviceToHost, h->stream));
     if (stats_host) XQ_CUDA(cudaMemcpyAsync(stats_host, h->d_stats, sizeof(xq_env_stats), cudaMemcpyDeviceToHost, h->stream));
     XQ_CUDA(cudaStreamSynchronize(h->stream));
     return XQ_OK;
+}
+int xq_env_rollout_random(xq_env_t h, int n_plies, xq_trace_rec* trace_host, xq_env_stats* stats_host) {
+    return xq_env_rollout_random_io(h, nullptr, n_plies, nullptr, trace_host, stats_host);
 }
 
 int xq_env_state_onehot(xq_env_t h, double* out_host) {

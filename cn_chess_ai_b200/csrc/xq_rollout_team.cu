@@ -22,15 +22,16 @@ struct TeamIo {           // conversion buffers, [item][board]
     uint8_t active[kTB];
 };
 
-__global__ void __launch_bounds__(kTB * kTeam) rollout_team_kernel(xq_env_rec* __restrict__ envs, int64_t n, uint64_t env_id0, uint64_t seed, int n_plies,
+template <int T>
+__global__ void __launch_bounds__(kTB * T) rollout_team_kernel(xq_env_rec* __restrict__ envs, int64_t n, uint64_t env_id0, uint64_t seed, int n_plies,
                                                                   xq_trace_rec* __restrict__ trace, xq_env_stats* __restrict__ stats,
                                                                   uint8_t* __restrict__ nonstd) {
     __shared__ TeamShared<kTB> sh;
     __shared__ TeamIo io;
     const int tid = threadIdx.x, lane = tid & 31;
-    const TeamRole R = team_role(tid >> 5);
+    const TeamRole R = team_role<T>(tid >> 5);
     const int64_t env = (int64_t)blockIdx.x * kTB + lane;
-    for (int d = tid + 1; d <= XQ_MAX_ACTIONS; d += kTB * kTeam) sh.magic[d] = team_mod_magic((uint32_t)d);
+    for (int d = tid + 1; d <= XQ_MAX_ACTIONS; d += kTB * T) sh.magic[d] = team_mod_magic((uint32_t)d);
     if (tid < kTB) sh.move[tid] = 0;
 
     // ---- load: warp 0 converts 32 records to slots + bitboards ----------------------------------
@@ -66,8 +67,8 @@ __global__ void __launch_bounds__(kTB * kTeam) rollout_team_kernel(xq_env_rec* _
 #pragma unroll
         for (int i = 0; i < 4; ++i) {
             const int s = (int)((R.slots >> (8 * i)) & 0xFFu);
-            wr |= (uint32_t)io.slot[s * kTB + lane] << (8 * i);
-            wb |= (uint32_t)io.slot[(16 + s) * kTB + lane] << (8 * i);
+            wr |= (uint32_t)(i < 16 / T ? io.slot[s * kTB + lane] : kDeadSq) << (8 * i);
+            wb |= (uint32_t)(i < 16 / T ? io.slot[(16 + s) * kTB + lane] : kDeadSq) << (8 * i);
         }
         const Bits90 red{io.bb[0 * kTB + lane], io.bb[1 * kTB + lane], io.bb[2 * kTB + lane]};
         const Bits90 black{io.bb[3 * kTB + lane], io.bb[4 * kTB + lane], io.bb[5 * kTB + lane]};
@@ -101,23 +102,23 @@ __global__ void __launch_bounds__(kTB * kTeam) rollout_team_kernel(xq_env_rec* _
     // `active` test; they get no trace, no statistics and no store
     xq_trace_rec* const my_trace = active ? trace : nullptr;
     const uint32_t ctr0 = st.ctr;
-    team_rng_chunk<kTB>(R, sh, lane, 0, rng_base, ctr0);
+    team_rng_chunk<T, kTB>(R, sh, lane, 0, rng_base, ctr0);
     __syncthreads();
     TeamPly pl;
 #pragma unroll 1
     for (int p = 0; p < n_plies; ++p) {
-        if ((p & 15) == 0) team_rng_chunk<kTB>(R, sh, lane, (p >> 4) + 1, rng_base, ctr0);   // read from ply p + 16 on
-        team_phase_a<kTB>(R, st, pl, sh, lane, p);
+        if ((p & 15) == 0) team_rng_chunk<T, kTB>(R, sh, lane, (p >> 4) + 1, rng_base, ctr0);   // read from ply p + 16 on
+        team_phase_a<T, kTB>(R, st, pl, sh, lane, p);
         __syncthreads();
         if (R.role == 0) team_finalize<kTB>(bk, sh, lane, my_trace, n, env);
-        team_phase_b<kTB>(R, st, pl, sh, lane, p);
+        team_phase_b<T, kTB>(R, st, pl, sh, lane, p);
         __syncthreads();
         team_phase_c<kTB>(R, st, pl, sh, bk, lane, p);
     }
     if (active) {
         const uint32_t wr = st.player == RED ? st.sq_own : st.sq_opp, wb = st.player == RED ? st.sq_opp : st.sq_own;
 #pragma unroll
-        for (int i = 0; i < 4; ++i) {
+        for (int i = 0; i < 16 / T; ++i) {
             const int s = (int)((R.slots >> (8 * i)) & 0xFFu);
             io.slot[s * kTB + lane] = (uint8_t)(wr >> (8 * i));
             io.slot[(16 + s) * kTB + lane] = (uint8_t)(wb >> (8 * i));
@@ -157,10 +158,11 @@ __global__ void __launch_bounds__(kTB * kTeam) rollout_team_kernel(xq_env_rec* _
     }
 }
 
-cudaError_t launch_rollout_team(xq_env_rec* envs, int64_t n, uint64_t env_id0, uint64_t seed, int n_plies, xq_trace_rec* trace,
+cudaError_t launch_rollout_team(int team, xq_env_rec* envs, int64_t n, uint64_t env_id0, uint64_t seed, int n_plies, xq_trace_rec* trace,
                                 xq_env_stats* stats, uint8_t* nonstd, cudaStream_t stream) {
     const unsigned grid = (unsigned)((n + kTB - 1) / kTB);
-    rollout_team_kernel<<<grid, kTB * kTeam, 0, stream>>>(envs, n, env_id0, seed, n_plies, trace, stats, nonstd);
+    if (team == 8) rollout_team_kernel<8><<<grid, kTB * 8, 0, stream>>>(envs, n, env_id0, seed, n_plies, trace, stats, nonstd);
+    else rollout_team_kernel<4><<<grid, kTB * 4, 0, stream>>>(envs, n, env_id0, seed, n_plies, trace, stats, nonstd);
     ++g_launches;
     return cudaGetLastError();
 }

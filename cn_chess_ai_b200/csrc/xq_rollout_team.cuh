@@ -32,65 +32,76 @@ XQ_HD uint32_t umulhi_u(uint32_t a, uint32_t b) { return (uint32_t)(((uint64_t)a
 #endif
 XQ_HD Bits90 bit_mask(int i) { return Bits90::bit(i); }
 
-// ---- the team: 4 threads per board, 4 piece slots per thread, ONE code path for all four roles ---------------------------------
-// position:   0 (slider)        1                 2                  3
-// role 0:     Chariot  slot 0   Horse    slot 2   Soldier  slot 11   Soldier slot 12
-// role 1:     Chariot  slot 1   Horse    slot 3   Soldier  slot 13   Soldier slot 14
-// role 2:     Cannon   slot 9   Advisor  slot 6   Elephant slot 4    General slot 8
-// role 3:     Cannon   slot 10  Advisor  slot 7   Elephant slot 5    Soldier slot 15
-// The piece type of a position is a warp-uniform RUN-TIME value (role = warp): a select for the sliders, a two-way branch for the
+// ---- the team: T threads per board, S = 16/T piece slots per thread, ONE code path for all roles ---------------------------------
+// T = 4 (the throughput shape)                                                    T = 8 (small env counts: twice the warps per board)
+// position:   0 (slider)        1                 2                  3            position:  0                 1
+// role 0:     Chariot  slot 0   Horse    slot 2   Soldier  slot 11   Soldier 12   role 0,1:  Chariot 0,1       Soldier 11,12
+// role 1:     Chariot  slot 1   Horse    slot 3   Soldier  slot 13   Soldier 14   role 2,3:  Cannon  9,10      Soldier 13,14
+// role 2:     Cannon   slot 9   Advisor  slot 6   Elephant slot 4    General 8    role 4,5:  Horse   2,3       Advisor 6,7
+// role 3:     Cannon   slot 10  Advisor  slot 7   Elephant slot 5    Soldier 15   role 6,7:  Elephant 4,5      General 8 / Soldier 15
+// The piece type of a position is a warp-uniform RUN-TIME value (role = warp): a select for the sliders, a short branch for the
 // leapers.  Every warp therefore runs the same ~14 KB loop body -- a first version with one template instantiation per role
 // (4 x 30 KB of straight-line code) spent most of its cycles in `no_instruction` stalls (ncu), the instruction cache being 32 KB.
-constexpr int kTeam = 4;
 struct TeamRole {
     int role;
-    bool hi;                       // roles 2, 3
-    uint32_t slots;                // slot of position i in byte i
-    uint32_t types;                // PieceType of position i in byte i
+    uint32_t slots;                // slot of position i in byte i (unused positions: 0xFF)
+    uint32_t types;                // PieceType of position i in byte i (unused: 0)
     uint32_t score5;               // piece value / 5
-    uint32_t open_red, open_black; // opening squares of my slots (ChessBoard::initializeBoard, src/chessboard.cpp:13-28)
-    // destination offsets of the leaper at position 1..3, one signed byte per direction in the order of generate*Moves
-    // (src/chessboard.cpp:150,163,180,249,267-281); a Soldier's table is Red's, `sold` has 0xFE in its byte 0 to flip 9 into -9
-    uint32_t tab1_lo, tab1_hi, tab2, tab3, sold2, sold3;
+    uint32_t open_red, open_black; // opening squares of my slots (ChessBoard::initializeBoard, src/chessboard.cpp:13-28); unused bytes 127
+    // destination offsets of a leaper at position i, one signed byte per direction in the order of generate*Moves
+    // (src/chessboard.cpp:150,163,180,249,267-281); a Horse has eight (tab_hi); a Soldier's table is Red's and sold[i] = 0xFE
+    // flips its 9 into -9 for Black
+    uint32_t tab_lo[4], tab_hi, sold[4];
 };
 constexpr int open_sq_c(int s) {   // opening square of slot s (0..15 Red, 16..31 Black)
     constexpr uint8_t t[32] = {0, 8, 1, 7, 2, 6, 3, 5, 4, 19, 25, 27, 29, 31, 33, 35, 81, 89, 82, 88, 83, 87, 84, 86, 85, 64, 70, 54, 56, 58, 60, 62};
     return t[s];
 }
-constexpr uint32_t team_slots_c(int role) { return role == 0 ? 0x0C0B0200u : (role == 1 ? 0x0E0D0301u : (role == 2 ? 0x08040609u : 0x0F05070Au)); }
-constexpr uint32_t team_open_c(int role, int side) {
-    uint32_t w = 0;
-    for (int i = 0; i < 4; ++i) w |= (uint32_t)open_sq_c(side * 16 + (int)((team_slots_c(role) >> (8 * i)) & 0xFFu)) << (8 * i);
-    return w;
+constexpr int slot_type_c(int s) {
+    return s < 2 ? CHARIOT : (s < 4 ? HORSE : (s < 6 ? ELEPHANT : (s < 8 ? ADVISOR : (s == 8 ? GENERAL : (s < 11 ? CANNON : SOLDIER)))));
 }
 constexpr int piece_score_c(int type) { return type == GENERAL ? 1000 : (type == ADVISOR || type == ELEPHANT ? 20 : (type == HORSE ? 40 : (type == CHARIOT ? 90 : (type == CANNON ? 45 : 10)))); }
-constexpr uint32_t team_types_c(int role) {
-    return role < 2 ? (uint32_t)(CHARIOT | HORSE << 8 | SOLDIER << 16 | SOLDIER << 24)
-                    : (uint32_t)(CANNON | ADVISOR << 8 | ELEPHANT << 16 | (role == 2 ? GENERAL : SOLDIER) << 24);
+constexpr int team_slot_c(int T, int role, int pos) {      // -1: unused position
+    constexpr int8_t t4[4][4] = {{0, 2, 11, 12}, {1, 3, 13, 14}, {9, 6, 4, 8}, {10, 7, 5, 15}};
+    constexpr int8_t t8[8][2] = {{0, 11}, {1, 12}, {9, 13}, {10, 14}, {2, 6}, {3, 7}, {4, 8}, {5, 15}};
+    return T == 4 ? t4[role][pos] : (pos < 2 ? t8[role][pos] : -1);
 }
-constexpr uint32_t team_score5_c(int role) {
-    uint32_t w = 0;
-    for (int i = 0; i < 4; ++i) w |= (uint32_t)(piece_score_c((int)((team_types_c(role) >> (8 * i)) & 0xFFu)) / 5) << (8 * i);
-    return w;
-}
-#define XQ_TEAM_SEL(f) (role == 0 ? f(0) : (role == 1 ? f(1) : (role == 2 ? f(2) : f(3))))
-XQ_HD TeamRole team_role(int role) {
-    TeamRole r;
-    r.role = role; r.hi = role >= 2;
-#define XQ_F_OPEN_R(i) team_open_c(i, 0)
-#define XQ_F_OPEN_B(i) team_open_c(i, 1)
-    r.slots = XQ_TEAM_SEL(team_slots_c); r.types = XQ_TEAM_SEL(team_types_c); r.score5 = XQ_TEAM_SEL(team_score5_c);
-    r.open_red = XQ_TEAM_SEL(XQ_F_OPEN_R); r.open_black = XQ_TEAM_SEL(XQ_F_OPEN_B);
-    constexpr uint32_t kHorseLo = 0xF5F9070Bu, kHorseHi = 0xEDEF1113u;      // 11,7,-7,-11 | 19,17,-17,-19
-    constexpr uint32_t kAdvisor = 0xF6F8080Au, kElephant = 0xECF01014u, kGeneral = 0xFF01F709u, kSoldier = 0x0001FF09u;   // Soldier (Red): 9,-1,1
-    r.tab1_lo = r.hi ? kAdvisor : kHorseLo; r.tab1_hi = r.hi ? 0u : kHorseHi;
-    r.tab2 = r.hi ? kElephant : kSoldier; r.sold2 = r.hi ? 0u : 0xFEu;
-    r.tab3 = role == 2 ? kGeneral : kSoldier; r.sold3 = role == 2 ? 0u : 0xFEu;
-#undef XQ_F_OPEN_R
-#undef XQ_F_OPEN_B
+constexpr TeamRole team_role_c(int T, int role) {
+    TeamRole r{};
+    r.role = role;
+    for (int i = 0; i < 4; ++i) {
+        const int slot = team_slot_c(T, role, i);
+        const int type = slot < 0 ? 0 : slot_type_c(slot);
+        r.slots |= (uint32_t)(slot < 0 ? 0xFF : slot) << (8 * i);
+        r.types |= (uint32_t)type << (8 * i);
+        r.score5 |= (uint32_t)(slot < 0 ? 0 : piece_score_c(type) / 5) << (8 * i);
+        r.open_red |= (uint32_t)(slot < 0 ? 127 : open_sq_c(slot)) << (8 * i);
+        r.open_black |= (uint32_t)(slot < 0 ? 127 : open_sq_c(16 + slot)) << (8 * i);
+        r.tab_lo[i] = type == HORSE ? 0xF5F9070Bu          // 11,7,-7,-11 (| 19,17,-17,-19 in tab_hi)
+                    : (type == ADVISOR ? 0xF6F8080Au       // 10,8,-8,-10
+                    : (type == ELEPHANT ? 0xECF01014u      // 20,16,-16,-20
+                    : (type == GENERAL ? 0xFF01F709u       // 9,-9,1,-1
+                    : (type == SOLDIER ? 0x0001FF09u : 0u))));   // Red: 9,-1,1
+        if (type == HORSE) r.tab_hi = 0xEDEF1113u;
+        r.sold[i] = type == SOLDIER ? 0xFEu : 0u;
+    }
     return r;
 }
-#undef XQ_TEAM_SEL
+template <int T>
+XQ_HD TeamRole team_role(int role) {      // once per thread
+    constexpr TeamRole r0 = team_role_c(T, 0), r1 = team_role_c(T, 1), r2 = team_role_c(T, 2), r3 = team_role_c(T, 3);
+    constexpr TeamRole r4 = team_role_c(T, T == 8 ? 4 : 0), r5 = team_role_c(T, T == 8 ? 5 : 0), r6 = team_role_c(T, T == 8 ? 6 : 0), r7 = team_role_c(T, T == 8 ? 7 : 0);
+    switch (role) {
+        case 0: return r0;
+        case 1: return r1;
+        case 2: return r2;
+        case 3: return r3;
+        case 4: return r4;
+        case 5: return r5;
+        case 6: return r6;
+        default: return r7;
+    }
+}
 XQ_HD Bits90 team_open_red() { return Bits90{0xAA0801FFu, 0x0000000Au, 0x00000000u}; }
 XQ_HD Bits90 team_open_black() { return Bits90{0x00000000u, 0x55400000u, 0x03FE0041u}; }
 XQ_HD Bits90 team_open_occT() { return Bits90{0x649A1649u, 0x98064980u, 0x0249A164u}; }
@@ -142,11 +153,11 @@ XQ_HD uint32_t team_draw(uint64_t rng_base, uint32_t ctr) {       // idx31 of xq
 }
 // the draws of plies [16*chunk, 16*chunk+16): thread (role, lane) computes 4 of them.  The RNG counter of ply p is ctr0 + p
 // whatever happens in between (a move and a no-action restart both advance it by one).
-template <int KB>
+template <int T, int KB>
 XQ_HD void team_rng_chunk(const TeamRole& R, TeamShared<KB>& sh, int lane, int chunk, uint64_t rng_base, uint32_t ctr0) {
 #pragma unroll 1
-    for (int i = 0; i < 4; ++i) {
-        const int j = R.role * 4 + i;
+    for (int i = 0; i < 16 / T; ++i) {
+        const int j = R.role * (16 / T) + i;
         sh.rng[((chunk & 1) * 16 + j) * KB + lane] = team_draw(rng_base, ctr0 + (uint32_t)(chunk * 16 + j));
     }
 }
@@ -189,29 +200,46 @@ XQ_HD int nth_set_bit8(uint32_t m, int j) {
     j -= h2 ? c : 0; m = h2 ? m >> 2 : m;
     return (h4 ? 4 : 0) + (h2 ? 2 : 0) + ((j >= (int)(m & 1u)) ? 1 : 0);
 }
-// ---- phase A: every thread counts the moves of its 4 pieces of the side to move and publishes (squares, counts) -------------
-template <int KB>
+// ---- phase A: every thread counts the moves of its S pieces of the side to move and publishes (squares, counts) -------------
+template <int T, int KB>
 XQ_HD void team_phase_a(const TeamRole& R, const TeamState& st, TeamPly& pl, TeamShared<KB>& sh, int lane, int p) {
     Pos P;
     P.own = st.own;
     P.occ = Bits90{st.own.w0 | st.opp.w0, st.own.w1 | st.opp.w1, st.own.w2 | st.opp.w2};
     P.occT = st.occT;
     const int color = st.player;
-    const int q0 = (int)(st.sq_own & 0xFFu), q1 = (int)((st.sq_own >> 8) & 0xFFu), q2 = (int)((st.sq_own >> 16) & 0xFFu), q3 = (int)(st.sq_own >> 24);
+    const int q0 = (int)(st.sq_own & 0xFFu), q1 = (int)((st.sq_own >> 8) & 0xFFu);
     // a captured piece (square 127) reads garbage bits: its count is discarded
-    int c0 = slider_desc_rt(P, q0, R.hi, &pl.desc[0]);
-    uint32_t m1, m2, m3;
-    if (!R.hi) { m1 = horse_mask(P, q1); m2 = soldier_mask(P, q2, color); m3 = soldier_mask(P, q3, color); }
-    else {
-        m1 = advisor_mask(P, q1, color); m2 = elephant_mask(P, q2, color);
-        m3 = R.role == 2 ? general_mask(P, q3) : soldier_mask(P, q3, color);
+    if (T == 4) {
+        const bool hi = R.role >= 2;
+        const int q2 = (int)((st.sq_own >> 16) & 0xFFu), q3 = (int)(st.sq_own >> 24);
+        int c0 = slider_desc_rt(P, q0, hi, &pl.desc[0]);
+        uint32_t m1, m2, m3;
+        if (!hi) { m1 = horse_mask(P, q1); m2 = soldier_mask(P, q2, color); m3 = soldier_mask(P, q3, color); }
+        else {
+            m1 = advisor_mask(P, q1, color); m2 = elephant_mask(P, q2, color);
+            m3 = R.role == 2 ? general_mask(P, q3) : soldier_mask(P, q3, color);
+        }
+        pl.desc[1] = m1; pl.desc[2] = m2; pl.desc[3] = m3;
+        c0 = q0 == kDeadSq ? 0 : c0;
+        const int c1 = q1 == kDeadSq ? 0 : popc32(m1), c2 = q2 == kDeadSq ? 0 : popc32(m2), c3 = q3 == kDeadSq ? 0 : popc32(m3);
+        pl.cntw = (uint32_t)c0 | ((uint32_t)c1 << 8) | ((uint32_t)c2 << 16) | ((uint32_t)c3 << 24);
+        sh.q[R.role * KB + lane] = st.sq_own;
+        sh.c[R.role * KB + lane] = pl.cntw;
+    } else {
+        int c0;
+        uint32_t d0, m1;
+        if (R.role < 4) c0 = slider_desc_rt(P, q0, R.role >= 2, &d0);
+        else { d0 = R.role < 6 ? horse_mask(P, q0) : elephant_mask(P, q0, color); c0 = popc32(d0); }
+        if (R.role < 4 || R.role == 7) m1 = soldier_mask(P, q1, color);
+        else m1 = R.role < 6 ? advisor_mask(P, q1, color) : general_mask(P, q1);
+        pl.desc[0] = d0; pl.desc[1] = m1;
+        c0 = q0 == kDeadSq ? 0 : c0;
+        const int c1 = q1 == kDeadSq ? 0 : popc32(m1);
+        pl.cntw = (uint32_t)c0 | ((uint32_t)c1 << 8);
+        reinterpret_cast<uint16_t*>(sh.q)[((R.role >> 1) * KB + lane) * 2 + (R.role & 1)] = (uint16_t)st.sq_own;      // half a word per role
+        reinterpret_cast<uint16_t*>(sh.c)[((R.role >> 1) * KB + lane) * 2 + (R.role & 1)] = (uint16_t)pl.cntw;
     }
-    pl.desc[1] = m1; pl.desc[2] = m2; pl.desc[3] = m3;
-    c0 = q0 == kDeadSq ? 0 : c0;
-    const int c1 = q1 == kDeadSq ? 0 : popc32(m1), c2 = q2 == kDeadSq ? 0 : popc32(m2), c3 = q3 == kDeadSq ? 0 : popc32(m3);
-    pl.cntw = (uint32_t)c0 | ((uint32_t)c1 << 8) | ((uint32_t)c2 << 16) | ((uint32_t)c3 << 24);
-    sh.q[R.role * KB + lane] = st.sq_own;
-    sh.c[R.role * KB + lane] = pl.cntw;
     if (R.role == 0) sh.cap[(p & 1) * KB + lane] = 0;
 }
 
@@ -246,7 +274,7 @@ XQ_HD void team_finalize(TeamBook& bk, const TeamShared<KB>& sh, int lane, xq_tr
 }
 
 // ---- phase B: list size, draw, reference-order prefix of my pieces; the owner of the k-th action decodes it ------------------
-template <int KB>
+template <int T, int KB>
 XQ_HD void team_phase_b(const TeamRole& R, const TeamState& st, TeamPly& pl, TeamShared<KB>& sh, int lane, int p) {
     uint32_t qw[4], cw[4], tot = 0;
 #pragma unroll
@@ -260,7 +288,7 @@ XQ_HD void team_phase_b(const TeamRole& R, const TeamState& st, TeamPly& pl, Tea
         bool hit = false, hslider = false;
         const uint32_t flip = st.player ? 0xFFFFFFFFu : 0u;          // a Black Soldier moves towards row 0
 #pragma unroll
-        for (int i = 0; i < 4; ++i) {
+        for (int i = 0; i < 16 / T; ++i) {
             const uint32_t sq = (st.sq_own >> (8 * i)) & 0xFFu;
             // byte j of (base - qw) has bit 7 set iff square_j < sq (bytes <= 127, so no borrow crosses a byte); dp4a sums 128 * count_j over them
             const uint32_t base = sq * 0x01010101u + 0x7F7F7F7Fu;
@@ -271,10 +299,9 @@ XQ_HD void team_phase_b(const TeamRole& R, const TeamState& st, TeamPly& pl, Tea
             const bool h = want < cnt;
             hit |= h;
             hsq = h ? sq : hsq; hdesc = h ? pl.desc[i] : hdesc; hwant = h ? want : hwant;
-            if (i == 0) hslider = h;
-            if (i == 1) { hlo = h ? R.tab1_lo : hlo; hhi = h ? R.tab1_hi : hhi; }
-            if (i == 2) hlo = h ? (R.tab2 ^ (R.sold2 & flip)) : hlo;
-            if (i == 3) hlo = h ? (R.tab3 ^ (R.sold3 & flip)) : hlo;
+            hlo = h ? (R.tab_lo[i] ^ (R.sold[i] & flip)) : hlo;
+            if (i == 0) hslider = h & (T == 4 || R.role < 4);
+            if (i == (T == 4 ? 1 : 0)) hhi = h ? R.tab_hi : 0u;      // the only position that can hold a Horse
         }
         if (hit) {
             const int to_s = slider_decode(hdesc, (int)hsq, (int)hwant);

@@ -96,6 +96,15 @@ class BatchedEnv:
         check(self._L.xq_env_rollout_random(self._h, n_plies, ptr(tr), ptr(stats)))
         return stats[0], tr
 
+    def rollout_random_io(self, boards_in, n_plies, boards_out, trace=False):
+        """host boards in -> n_plies of random-policy self-play -> host boards out, one C-ABI call (one synchronisation)"""
+        assert boards_in is None or boards_in.shape == (self.n,)
+        assert boards_out is None or boards_out.shape == (self.n,)
+        tr = np.empty((n_plies, self.n), dtype=TRACE_DTYPE) if trace else None
+        stats = np.zeros(1, dtype=STATS_DTYPE)
+        check(self._L.xq_env_rollout_random_io(self._h, ptr(boards_in), n_plies, ptr(boards_out), ptr(tr), ptr(stats)))
+        return stats[0], tr
+
     def rollout_random_async(self, n_plies):
         check(self._L.xq_env_rollout_random_async(self._h, n_plies))
 

@@ -121,6 +121,11 @@ int xq_env_step(xq_env_t h, const xq_action* actions_host, int32_t* reward_host,
  * -> checkGameOver, reset on terminal.  One launch; boards stay on chip between plies.
  * trace_host[n_plies][n_envs] and stats_host may be NULL. */
 int xq_env_rollout_random(xq_env_t h, int n_plies, xq_trace_rec* trace_host, xq_env_stats* stats_host);
+/* Host boards in, host boards out, ONE call: xq_env_set_boards(boards_in) + xq_env_rollout_random + xq_env_get_boards(boards_out)
+ * enqueued back to back on the handle's stream with a single synchronisation at the end (three calls = three).  All n_envs boards;
+ * boards_in_host may be NULL (continue from the boards on the device), as may boards_out_host, trace_host and stats_host. */
+int xq_env_rollout_random_io(xq_env_t h, const xq_env_rec* boards_in_host, int n_plies, xq_env_rec* boards_out_host,
+                             xq_trace_rec* trace_host, xq_env_stats* stats_host);
 /* same, device-resident and asynchronous: no host traffic; stats accumulate on the device */
 int xq_env_rollout_random_async(xq_env_t h, int n_plies);
 int xq_env_get_stats(xq_env_t h, xq_env_stats* stats_host, int reset);

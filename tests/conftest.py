@@ -55,7 +55,7 @@ def hostsim():
     H.hs_bb_all_actions.argtypes = [P, C.c_long, P, P]
     H.hs_valid_moves.argtypes = [P, C.c_int, C.c_int, P]
     H.hs_is_valid_move.argtypes = [P, C.c_int, C.c_int, C.c_int, C.c_int]
-    H.hs_team_rollout.argtypes = [P, C.c_long, C.c_uint64, C.c_uint64, C.c_int, P, P]
+    H.hs_team_rollout.argtypes = [C.c_int, P, C.c_long, C.c_uint64, C.c_uint64, C.c_int, P, P]
     return H
 
 

@@ -19,8 +19,9 @@ struct RecBoard {
 // ---- the team rollout kernel's ply (xq_rollout_team.cuh), one board at a time: the 4 threads of a board run phase by phase ----
 namespace {
 using namespace xq;
+template <int T>
 int team_rollout_host(xq_env_rec* recs, long n, uint64_t env_id0, uint64_t seed, int n_plies, xq_trace_rec* trace, xq_env_stats* stats) {
-    constexpr int T = kTeam;
+    constexpr int S = 16 / T;
     int nonstd = 0;
     for (long env = 0; env < n; ++env) {
         TeamShared<1> sh;
@@ -44,15 +45,15 @@ int team_rollout_host(xq_env_rec* recs, long n, uint64_t env_id0, uint64_t seed,
         const bool finished = recs[env].move_count >= XQ_MAX_MOVES || slot[8] == kDeadSq || slot[24] == kDeadSq;
         if (finished) { bk.red = bk.black = 0; bk.mat_red = bk.mat_black = 1480; }
         for (int r = 0; r < T; ++r) {
-            R[r] = team_role(r);
+            R[r] = team_role<T>(r);
             team_reset(R[r], st[r]);
             st[r].ctr = recs[env].ctr;
             if (finished) continue;
             uint32_t wr = 0, wb = 0;
             for (int i = 0; i < 4; ++i) {
                 const int s = (int)((R[r].slots >> (8 * i)) & 0xFFu);
-                wr |= (uint32_t)slot[s] << (8 * i);
-                wb |= (uint32_t)slot[16 + s] << (8 * i);
+                wr |= (uint32_t)(i < S ? slot[s] : kDeadSq) << (8 * i);
+                wb |= (uint32_t)(i < S ? slot[16 + s] : kDeadSq) << (8 * i);
             }
             st[r].occT = occT; st[r].move_count = recs[env].move_count; st[r].player = recs[env].player;
             const bool redp = recs[env].player == 0;
@@ -62,19 +63,19 @@ int team_rollout_host(xq_env_rec* recs, long n, uint64_t env_id0, uint64_t seed,
         }
         const uint64_t base = seed + (env_id0 + (uint64_t)env) * 0x9E3779B97F4A7C15ull;
         const uint32_t ctr0 = st[0].ctr;
-        for (int r = 0; r < T; ++r) team_rng_chunk<1>(R[r], sh, 0, 0, base, ctr0);
+        for (int r = 0; r < T; ++r) team_rng_chunk<T, 1>(R[r], sh, 0, 0, base, ctr0);
         for (int p = 0; p < n_plies; ++p) {
-            if ((p & 15) == 0) for (int r = 0; r < T; ++r) team_rng_chunk<1>(R[r], sh, 0, (p >> 4) + 1, base, ctr0);
-            for (int r = 0; r < T; ++r) team_phase_a<1>(R[r], st[r], pl[r], sh, 0, p);
+            if ((p & 15) == 0) for (int r = 0; r < T; ++r) team_rng_chunk<T, 1>(R[r], sh, 0, (p >> 4) + 1, base, ctr0);
+            for (int r = 0; r < T; ++r) team_phase_a<T, 1>(R[r], st[r], pl[r], sh, 0, p);
             team_finalize<1>(bk, sh, 0, trace, n, env);
-            for (int r = 0; r < T; ++r) team_phase_b<1>(R[r], st[r], pl[r], sh, 0, p);
+            for (int r = 0; r < T; ++r) team_phase_b<T, 1>(R[r], st[r], pl[r], sh, 0, p);
             for (int r = 0; r < T; ++r) team_phase_c<1>(R[r], st[r], pl[r], sh, bk, 0, p);
         }
         team_finalize<1>(bk, sh, 0, trace, n, env);
         // store
         for (int r = 0; r < T; ++r) {
             const uint32_t wr = st[r].player == 0 ? st[r].sq_own : st[r].sq_opp, wb = st[r].player == 0 ? st[r].sq_opp : st[r].sq_own;
-            for (int i = 0; i < 4; ++i) {
+            for (int i = 0; i < S; ++i) {
                 const int s = (int)((R[r].slots >> (8 * i)) & 0xFFu);
                 slot[s] = (uint8_t)(wr >> (8 * i)); slot[16 + s] = (uint8_t)(wb >> (8 * i));
             }
@@ -96,8 +97,8 @@ int team_rollout_host(xq_env_rec* recs, long n, uint64_t env_id0, uint64_t seed,
 
 extern "C" {
 // whole fused rollout through the team kernel's phases; returns the number of boards it does not handle (non-standard piece sets)
-int hs_team_rollout(xq_env_rec* recs, long n, uint64_t env_id0, uint64_t seed, int n_plies, xq_trace_rec* trace, xq_env_stats* stats) {
-    return team_rollout_host(recs, n, env_id0, seed, n_plies, trace, stats);
+int hs_team_rollout(int team, xq_env_rec* recs, long n, uint64_t env_id0, uint64_t seed, int n_plies, xq_trace_rec* trace, xq_env_stats* stats) {
+    return team == 8 ? team_rollout_host<8>(recs, n, env_id0, seed, n_plies, trace, stats) : team_rollout_host<4>(recs, n, env_id0, seed, n_plies, trace, stats);
 }
 void hs_all_actions(const xq_env_rec* recs, long n, uint8_t* counts, uint16_t* actions) {
     for (long i = 0; i < n; ++i) {

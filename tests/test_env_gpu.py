@@ -219,3 +219,22 @@ def test_large_n_properties(xq, O, oracle_lib):
     env2 = xq.BatchedEnv(1000, seed=seed, env_id0=n - 1000)
     env2.rollout_random(plies)
     assert same_recs(env2.get_boards(), recs[n - 1000:])
+
+
+def test_rollout_random_io_one_call(xq, O, oracle_lib):
+    """xq_env_rollout_random_io (host boards in, host boards + trace + stats out, one synchronisation) == set_boards + rollout + get_boards
+    == the oracle, resumed from mid-game positions with both colours to move"""
+    n, plies, seed = 1500, 60, 19
+    start = harvest_positions(O, n // 3, 3, 41, seed=6)
+    env = xq.BatchedEnv(n, seed=seed, env_id0=77)
+    out = np.empty(n, xq.ENV_DTYPE)
+    st, tr = env.rollout_random_io(start, plies, out, trace=True)
+    ref = start.copy()
+    tr0 = np.zeros((plies, n), O.TRACE_DTYPE)
+    st0 = np.zeros(1, O.STATS_DTYPE)
+    oracle_lib.xqo_rollout_random(ref.ctypes.data, n, 77, seed, plies, tr0.ctypes.data, st0.ctypes.data)
+    assert tr.tobytes() == tr0.tobytes() and same_recs(out, ref) and st.tobytes() == st0[0].tobytes()
+    assert same_recs(env.get_boards(), ref)
+    st2, _ = env.rollout_random_io(None, 5, None)          # continue on the device, nothing copied back
+    oracle_lib.xqo_rollout_random(ref.ctypes.data, n, 77, seed, 5, None, st0.ctypes.data)
+    assert same_recs(env.get_boards(), ref) and int(st2["steps"]) == 5 * n

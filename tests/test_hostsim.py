@@ -89,7 +89,7 @@ def test_bitboard_count_and_decode(O, oracle_lib, hostsim, golden):
     assert (c == golden["pos_counts"]).all() and (a == golden["pos_lists"]).all()
 
 
-def _team_vs_oracle(O, L, H, recs, seed, id0, plies):
+def _team_vs_oracle(O, L, H, team, recs, seed, id0, plies):
     n = len(recs)
     a, b = recs.copy(), recs.copy()
     tr0 = np.zeros((plies, n), O.TRACE_DTYPE)
@@ -97,22 +97,23 @@ def _team_vs_oracle(O, L, H, recs, seed, id0, plies):
     L.xqo_rollout_random(a.ctypes.data, n, id0, seed, plies, tr0.ctypes.data, st0.ctypes.data)
     tr1 = np.zeros((plies, n), O.TRACE_DTYPE)
     st1 = np.zeros(1, O.STATS_DTYPE)
-    assert H.hs_team_rollout(b.ctypes.data, n, id0, seed, plies, tr1.ctypes.data, st1.ctypes.data) == 0
+    assert H.hs_team_rollout(team, b.ctypes.data, n, id0, seed, plies, tr1.ctypes.data, st1.ctypes.data) == 0
     bad = np.nonzero((tr0.view(np.uint64) != tr1.view(np.uint64)).any(0))[0]
-    assert len(bad) == 0, f"{len(bad)} envs differ, first env {bad[:3]}, first ply {np.nonzero(tr0.view(np.uint64)[:, bad[0]] != tr1.view(np.uint64)[:, bad[0]])[0][:3]}"
+    assert len(bad) == 0, f"team {team}: {len(bad)} envs differ, first env {bad[:3]}, first ply {np.nonzero(tr0.view(np.uint64)[:, bad[0]] != tr1.view(np.uint64)[:, bad[0]])[0][:3]}"
     assert a.tobytes() == b.tobytes()
     assert st0.tobytes() == st1.tobytes()
 
 
 def test_team_rollout_phases(O, oracle_lib, hostsim):
-    """xq_rollout_team.cuh (rollout_team_kernel): the three phases of a ply, run thread by thread on the host, reproduce the
+    """xq_rollout_team.cuh (rollout_team_kernel<4>, <8>): the three phases of a ply, run thread by thread on the host, reproduce the
     oracle's fused rollout record for record -- from the opening over several games, resumed in the middle of games (Black to
     move, captured pieces, non-zero scores and counters) and from finished boards"""
-    _team_vs_oracle(O, oracle_lib, hostsim, O.new_envs(1500), 11, 5000, 450)
     mid = harvest_positions(O, 600, 6, 37, seed=5)       # snapshots after 37, 74, ... plies: both colours to move
-    _team_vs_oracle(O, oracle_lib, hostsim, mid, 77, 0, 230)
-    _team_vs_oracle(O, oracle_lib, hostsim, mid, 78, 123456789012, 1)
     fin = O.new_envs(8)
     fin["move_count"][:4] = 200
     fin["sq"][4:, 0] &= np.uint32(0xFFF0FFFF)           # Red general gone: never stepped, restarted (chessai.cpp:90,96)
-    _team_vs_oracle(O, oracle_lib, hostsim, fin, 3, 9, 40)
+    for team in (4, 8):
+        _team_vs_oracle(O, oracle_lib, hostsim, team, O.new_envs(1500), 11, 5000, 450)
+        _team_vs_oracle(O, oracle_lib, hostsim, team, mid, 77, 0, 230)
+        _team_vs_oracle(O, oracle_lib, hostsim, team, mid, 78, 123456789012, 1)
+        _team_vs_oracle(O, oracle_lib, hostsim, team, fin, 3, 9, 40)
