@@ -35,6 +35,7 @@ extern unsigned long long g_launches;   // kernels launched by this library (xq_
 struct EnvInfo {
     int64_t n; int device; uint64_t seed, env_id0; cudaStream_t stream; xq_env_rec* d_envs; xq_env_stats* d_stats;
     xq_game_event* d_events; unsigned long long* d_event_count; int64_t event_cap; uint32_t event_ply;     // finished-game ring (optional)
+    uint8_t* d_nonstd; bool maybe_nonstd;      // per-env flags of the team kernels (board left to the generic kernel); boards were injected
 };
 int env_info(xq_env_t h, EnvInfo* out);
 void env_advance_event_ply(xq_env_t h, uint32_t plies);   // the collector applied `plies` more plies

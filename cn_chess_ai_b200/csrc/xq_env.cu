@@ -303,6 +303,7 @@ int env_info(xq_env_t h, EnvInfo* out) {
     if (!h || !out) return fail(XQ_ERR_INVALID, "env_info: null handle");
     out->n = h->n; out->device = h->device; out->seed = h->seed; out->env_id0 = h->env_id0; out->stream = h->stream; out->d_envs = h->d_envs; out->d_stats = h->d_stats;
     out->d_events = h->d_events; out->d_event_count = h->d_event_count; out->event_cap = h->event_cap; out->event_ply = h->event_ply;
+    out->d_nonstd = h->d_nonstd; out->maybe_nonstd = h->maybe_nonstd;
     return XQ_OK;
 }
 void env_advance_event_ply(xq_env_t h, uint32_t plies) { if (h) h->event_ply += plies; }

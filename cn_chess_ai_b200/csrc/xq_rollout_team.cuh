@@ -373,21 +373,57 @@ XQ_HD bool team_unpack_record(const uint32_t (&w)[12], Bits90& red, Bits90& blac
     red = black = occT = Bits90{0, 0, 0};
 #pragma unroll
     for (int wi = 0; wi < 12; ++wi) {
+        // one iteration per OCCUPIED square of the word (a board holds <= 32 pieces on 90 squares), lowest square first
+        uint32_t nz = (w[wi] | (w[wi] >> 1) | (w[wi] >> 2) | (w[wi] >> 3)) & 0x11111111u;
+        if (wi == 11) nz &= 0x00000011u;            // squares 88, 89; the rest of the last word is padding
+        while (nz) {
+            const int sh = ffs32(nz) - 1;           // 4 * (square within the word)
+            nz &= nz - 1;
+            const int s = wi * 8 + (sh >> 2);
+            const int code = (int)((w[wi] >> sh) & 15u);
+            const int t = type_of(code);
+            const int ord = (int)((cnt >> (4 * code)) & 15);
+            if (code == 15 || ord >= slot_cap(t)) { ok = false; }
+            else {
+                put((code >= 8 ? 16 : 0) + slot_base(t) + ord, s);
+                cnt += 1ull << (4 * code);
+                const Bits90 b = Bits90::bit(s);
+                if (code >= 8) black.or_with(b); else red.or_with(b);
+                const int r = row_of(s);
+                occT.or_with(Bits90::bit(cm_index(r, s - 9 * r)));
+            }
+        }
+    }
+    return ok;
+}
+
+// one colour only (side 0 Red, 1 Black): its 16 slots put(slot 0..15, square), its bitboard and its part of the column-major
+// occupancy -- the two colours of a board can be unpacked by two warps at once (act_team_kernel)
+template <class PUT>
+XQ_HD bool team_unpack_side(const uint32_t (&w)[12], int side, Bits90& bb, Bits90& occT, PUT&& put) {
+    bool ok = true;
+    uint32_t cnt = 0;   // 4-bit counter per piece type
+    bb = occT = Bits90{0, 0, 0};
 #pragma unroll
-        for (int i = 0; i < 8; ++i) {
-            const int s = wi * 8 + i;
-            const int code = (int)((w[wi] >> (4 * i)) & 15u);
-            if (s < 90 && code != 0) {
-                const int t = type_of(code);
-                const int ord = (int)((cnt >> (4 * code)) & 15);
-                if (code == 15 || ord >= slot_cap(t)) { ok = false; }
-                else {
-                    put((code >= 8 ? 16 : 0) + slot_base(t) + ord, s);
-                    cnt += 1ull << (4 * code);
-                    if (code >= 8) black.set(s); else red.set(s);
-                    const int r = row_of(s);
-                    occT.set(cm_index(r, s - 9 * r));
-                }
+    for (int wi = 0; wi < 12; ++wi) {
+        const uint32_t hi = (w[wi] >> 3) & 0x11111111u;                                      // nibble >= 8: Black (or the invalid code 15)
+        uint32_t nz = (w[wi] | (w[wi] >> 1) | (w[wi] >> 2)) & 0x11111111u;                   // nibble & 7 != 0
+        nz = side ? hi : (nz & ~hi);
+        if (wi == 11) nz &= 0x00000011u;
+        while (nz) {
+            const int sh = ffs32(nz) - 1;
+            nz &= nz - 1;
+            const int s = wi * 8 + (sh >> 2);
+            const int code = (int)((w[wi] >> sh) & 15u);
+            const int t = code - (side ? 7 : 0);                                             // 1..7, or 8 for code 15, or 1 for code 8 = Black General
+            const int ord = (int)((cnt >> (4 * (t & 7))) & 15u);
+            if (t > 7 || ord >= slot_cap(t)) { ok = false; }
+            else {
+                put(slot_base(t) + ord, s);
+                cnt += 1u << (4 * t);
+                bb.or_with(Bits90::bit(s));
+                const int r = row_of(s);
+                occT.or_with(Bits90::bit(cm_index(r, s - 9 * r)));
             }
         }
     }

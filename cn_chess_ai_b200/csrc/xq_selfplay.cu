@@ -11,6 +11,8 @@
 // Q(s)[to] only needs outputs 0..89 of layer 1 (src/dqn.cpp:47 indexes by action.to), so acting costs a
 // <=32-row FP32 gather for layer 0 plus a [n x 128] x [128 x 96] split-precision tensor-core contraction
 // (dqn_q90_device in xq_dqn_fast.cu), then one thread per board picks the action.
+#include <stdlib.h>
+
 #include <algorithm>
 
 #include "xq_dqn_internal.cuh"
@@ -28,20 +30,26 @@ struct Transition {
 };
 static_assert(sizeof(Transition) == sizeof(xq_transition), "transition layout");
 
-// Action selection (+ optional application) for every env: one thread per board, ordered list staged in shared memory.
+cudaError_t launch_act_team(bool apply, xq_env_rec* envs, int64_t n, uint64_t env_id0, uint64_t seed, const float* q90, uint32_t eps_thr, int train_done,
+                            uint16_t* actions_out, void* ring, int64_t ring_cap, int64_t ring_pos, xq_env_stats* stats, xq_game_event* events,
+                            unsigned long long* event_count, int64_t event_cap, uint32_t event_ply, uint8_t* nonstd, cudaStream_t stream);
+
+// Action selection (+ optional application), generic thread-per-board version (ordered list staged in shared memory): the fallback
+// of act_team_kernel (xq_act_team.cu) for boards with non-standard piece sets, or for every env with XQ_ACT_TEAM=0 (A/B runs).
 template <bool APPLY>
 __global__ void __launch_bounds__(kThreads) act_kernel(xq_env_rec* __restrict__ envs, int64_t n, uint64_t env_id0, uint64_t seed,
                                                       const float* __restrict__ q90, uint32_t eps_thr, int train_done,
                                                       uint16_t* __restrict__ actions_out, Transition* __restrict__ ring, int64_t ring_cap,
                                                       int64_t ring_pos, xq_env_stats* __restrict__ stats, xq_game_event* __restrict__ events,
-                                                      unsigned long long* __restrict__ event_count, int64_t event_cap, uint32_t event_ply) {
+                                                      unsigned long long* __restrict__ event_count, int64_t event_cap, uint32_t event_ply,
+                                                      const uint8_t* __restrict__ only) {
     __shared__ uint32_t s_board[12 * kThreads];
     __shared__ uint32_t s_list[64 * kThreads];
     const int tid = threadIdx.x;
     const int64_t env = (int64_t)blockIdx.x * kThreads + tid;
     unsigned long long a_steps = 0, a_games = 0, a_red = 0, a_black = 0, a_capg = 0, a_caps = 0, a_legal = 0;
     long long a_reward = 0;
-    if (env < n) {
+    if (env < n && (only == nullptr || only[env] != 0)) {   // `only`: boards the team kernel could not map
         SmemBoard b{s_board + tid, kThreads};
         b.load(envs + env);
         Meta m; m.load(envs + env);
@@ -187,6 +195,27 @@ static int order_after(cudaStream_t waiter, cudaStream_t producer, cudaEvent_t* 
 }
 static cudaEvent_t g_ev[64];
 
+// One ply of selection (+ application) for every env: the team kernel (xq_act_team.cu) for boards with a standard piece set, then
+// the generic thread-per-board kernel for the boards it flagged (only possible after xq_env_set_boards injected exotic positions).
+// XQ_ACT_TEAM=0 runs the generic kernel on every env (A/B runs); both give the same results.
+static int launch_act(bool apply, const EnvInfo& ei, const float* q90, uint32_t thr, int train_done, uint16_t* actions, Transition* ring, int64_t ring_cap,
+                      int64_t ring_pos, xq_env_stats* stats, uint32_t event_ply) {
+    static const bool team = [] { const char* e = getenv("XQ_ACT_TEAM"); return !(e && atoi(e) == 0); }();
+    if (team) XQ_CUDA(launch_act_team(apply, ei.d_envs, ei.n, ei.env_id0, ei.seed, q90, thr, train_done, actions, ring, ring_cap, ring_pos, stats,
+                                      ei.d_events, ei.d_event_count, ei.event_cap, event_ply, ei.d_nonstd, ei.stream));
+    if (!team || ei.maybe_nonstd) {
+        const uint8_t* only = team ? ei.d_nonstd : nullptr;
+        if (apply)
+            act_kernel<true><<<blocks(ei.n, kThreads), kThreads, 0, ei.stream>>>(ei.d_envs, ei.n, ei.env_id0, ei.seed, q90, thr, train_done, actions, ring, ring_cap,
+                                                                                ring_pos, stats, ei.d_events, ei.d_event_count, ei.event_cap, event_ply, only);
+        else
+            act_kernel<false><<<blocks(ei.n, kThreads), kThreads, 0, ei.stream>>>(ei.d_envs, ei.n, ei.env_id0, ei.seed, q90, thr, train_done, actions, ring, ring_cap,
+                                                                                 ring_pos, stats, ei.d_events, ei.d_event_count, ei.event_cap, event_ply, only);
+        XQ_LAUNCH_CHECK();
+    }
+    return XQ_OK;
+}
+
 extern "C" {
 
 int xq_replay_destroy(xq_replay_t r) {
@@ -285,9 +314,7 @@ int xq_dqn_act(xq_dqn_t h, xq_env_t env, double eps, xq_action* actions_host, fl
     if (int rc = reserve_scratch(h->device, ei.n, &sc)) return rc;
     if (int rc = order_after(ei.stream, h->stream, &g_ev[h->device & 63])) return rc;
     if (int rc = dqn_q90_device(h, ei.d_envs, ei.n, sc->q90, ei.stream)) return rc;
-    act_kernel<false><<<blocks(ei.n, kThreads), kThreads, 0, ei.stream>>>(ei.d_envs, ei.n, ei.env_id0, ei.seed, sc->q90, xq_eps_threshold(eps), 0,
-                                                                         sc->actions, nullptr, 1, 0, nullptr, nullptr, nullptr, 0, 0u);
-    XQ_LAUNCH_CHECK();
+    if (int rc = launch_act(false, ei, sc->q90, xq_eps_threshold(eps), 0, sc->actions, nullptr, 1, 0, nullptr, 0u)) return rc;
     XQ_CUDA(cudaMemcpyAsync(actions_host, sc->actions, sizeof(uint16_t) * ei.n, cudaMemcpyDeviceToHost, ei.stream));
     if (q_host) XQ_CUDA(cudaMemcpyAsync(q_host, sc->q90, sizeof(float) * kQPad * ei.n, cudaMemcpyDeviceToHost, ei.stream));
     XQ_CUDA(cudaStreamSynchronize(ei.stream));
@@ -308,11 +335,8 @@ int xq_selfplay_collect(xq_dqn_t h, xq_env_t env, xq_replay_t r, int n_plies, do
     const uint32_t thr = xq_eps_threshold(eps);
     for (int p = 0; p < n_plies; ++p) {
         if (int rc = dqn_q90_device(h, ei.d_envs, ei.n, sc->q90, ei.stream)) return rc;
-        act_kernel<true><<<blocks(ei.n, kThreads), kThreads, 0, ei.stream>>>(ei.d_envs, ei.n, ei.env_id0, ei.seed, sc->q90, thr, train_done, nullptr,
-                                                                            r ? r->d_ring : nullptr, r ? r->capacity : 1,
-                                                                            r ? r->total % r->capacity : 0, d_stats, ei.d_events, ei.d_event_count,
-                                                                            ei.event_cap, ei.event_ply + (uint32_t)p);
-        XQ_LAUNCH_CHECK();
+        if (int rc = launch_act(true, ei, sc->q90, thr, train_done, nullptr, r ? r->d_ring : nullptr, r ? r->capacity : 1, r ? r->total % r->capacity : 0,
+                                d_stats, ei.event_ply + (uint32_t)p)) return rc;
         if (r) r->total += ei.n;
     }
     env_advance_event_ply(env, (uint32_t)n_plies);

@@ -1,5 +1,5 @@
 cd $GRAFT_REPO_ROOT
-timeout 600 ncu --metrics gpu__time_duration.sum --cache-control none --clock-control none -k regex:"q90|act_kernel" -s 8 -c 24 --csv --log-file gpurun_out/launches_selfplay.csv python scripts/td_only.py > gpurun_out/ncu_selfplay.log 2>&1
+timeout 600 ncu --metrics gpu__time_duration.sum --cache-control none --clock-control none -k regex:"q90|act_" -s 8 -c 24 --csv --log-file gpurun_out/launches_selfplay.csv python scripts/td_only.py > gpurun_out/ncu_selfplay.log 2>&1
 python - <<'PY'
 import csv, collections
 rows=list(csv.reader(open('gpurun_out/launches_selfplay.csv')))

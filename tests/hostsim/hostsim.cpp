@@ -7,6 +7,7 @@
 #include "../../cn_chess_ai_b200/csrc/xq_rules.cuh"
 #include "../../cn_chess_ai_b200/csrc/xq_bitboard.cuh"
 #include "../../cn_chess_ai_b200/csrc/xq_rollout_team.cuh"
+#include "../../cn_chess_ai_b200/csrc/xq_act_team.cuh"
 #include "../../include/xq.h"
 
 namespace {
@@ -95,7 +96,54 @@ int team_rollout_host(xq_env_rec* recs, long n, uint64_t env_id0, uint64_t seed,
 }
 }
 
+// ---- DQN::selectAction through the team act phases (xq_act_team.cuh), one board at a time ----
+namespace {
+int act_team_host(const xq_env_rec* recs, long n, uint64_t env_id0, uint64_t seed, const float* q90, uint32_t eps_thr, uint16_t* actions) {
+    int nonstd = 0;
+    for (long env = 0; env < n; ++env) {
+        actions[env] = XQ_ACTION_NONE;
+        TeamShared<1> sh;
+        ActShared<1> as;
+        for (int d = 1; d <= XQ_MAX_ACTIONS; ++d) sh.magic[d] = team_mod_magic((uint32_t)d);
+        for (int t = 0; t < kQStride; ++t) as.qt[t * 2] = q90[env * kQStride + t];
+        uint8_t slot[32];
+        for (int i = 0; i < 32; ++i) slot[i] = kDeadSq;
+        uint32_t w[12];
+        std::memcpy(w, recs[env].sq, 48);
+        Bits90 red, black, occT;
+        if (!team_unpack_record(w, red, black, occT, [&](int s, int q) { slot[s] = (uint8_t)q; })) { ++nonstd; continue; }
+        TeamRole R[4];
+        TeamState st[4];
+        TeamPly pl[4];
+        uint32_t kbest[4][4];
+        for (int r = 0; r < 4; ++r) {
+            R[r] = team_role<4>(r);
+            uint32_t wr = 0, wb = 0;
+            for (int i = 0; i < 4; ++i) {
+                const int s = (int)((R[r].slots >> (8 * i)) & 0xFFu);
+                wr |= (uint32_t)slot[s] << (8 * i);
+                wb |= (uint32_t)slot[16 + s] << (8 * i);
+            }
+            const bool redp = recs[env].player == 0;
+            st[r].occT = occT; st[r].move_count = recs[env].move_count; st[r].player = recs[env].player; st[r].ctr = recs[env].ctr;
+            st[r].sq_own = redp ? wr : wb; st[r].sq_opp = redp ? wb : wr;
+            st[r].own = redp ? red : black; st[r].opp = redp ? black : red;
+            st[r].gen_own = redp ? slot[8] : slot[24]; st[r].gen_opp = redp ? slot[24] : slot[8];
+        }
+        for (int r = 0; r < 4; ++r) { team_phase_a<4, 1>(R[r], st[r], pl[r], sh, 0, 0); act_best<1>(R[r], st[r], pl[r], as, 0, kbest[r]); }
+        const uint64_t x = rng(seed, env_id0 + (uint64_t)env, recs[env].ctr);
+        uint32_t tot = 0;
+        for (int r = 0; r < 4; ++r) tot = act_select<1>(R[r], st[r], pl[r], sh, as, 0, kbest[r], x, eps_thr);
+        if (tot > 0) { const uint32_t mv = sh.move[0]; actions[env] = XQ_ACTION(mv & 0xFFu, (mv >> 8) & 0xFFu); }
+    }
+    return nonstd;
+}
+}
+
 extern "C" {
+int hs_act_team(const xq_env_rec* recs, long n, uint64_t env_id0, uint64_t seed, const float* q90, uint32_t eps_thr, uint16_t* actions) {
+    return act_team_host(recs, n, env_id0, seed, q90, eps_thr, actions);
+}
 // whole fused rollout through the team kernel's phases; returns the number of boards it does not handle (non-standard piece sets)
 int hs_team_rollout(int team, xq_env_rec* recs, long n, uint64_t env_id0, uint64_t seed, int n_plies, xq_trace_rec* trace, xq_env_stats* stats) {
     return team == 8 ? team_rollout_host<8>(recs, n, env_id0, seed, n_plies, trace, stats) : team_rollout_host<4>(recs, n, env_id0, seed, n_plies, trace, stats);

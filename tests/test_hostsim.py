@@ -117,3 +117,30 @@ def test_team_rollout_phases(O, oracle_lib, hostsim):
         _team_vs_oracle(O, oracle_lib, hostsim, team, mid, 77, 0, 230)
         _team_vs_oracle(O, oracle_lib, hostsim, team, mid, 78, 123456789012, 1)
         _team_vs_oracle(O, oracle_lib, hostsim, team, fin, 3, 9, 40)
+
+
+def test_team_act_selection(O, oracle_lib, hostsim):
+    """xq_act_team.cuh (act_team_kernel): eps-greedy choice of the team phases == the oracle's selectAction restatement on the same
+    Q values and draws -- random Q, heavily tied Q (first maximum in list order must win), reachable and arbitrary standard boards"""
+    recs = harvest_positions(O, 500, 8, 23, seed=12)
+    n = len(recs)
+    counts, lists = _oracle_lists(oracle_lib, recs)
+    rng = np.random.default_rng(9)
+    ids = np.arange(n, dtype=np.uint64) + np.uint64(31)
+    for case, eps in (("random", 0.1), ("ties", 0.0), ("coarse", 0.3), ("signed zero", 0.0), ("explore", 1.0)):
+        q = rng.uniform(-0.3, 0.3, (n, 96)).astype(np.float32)
+        if case == "ties":
+            q[:] = 0.125
+        elif case == "coarse":
+            q = np.round(q * 8).astype(np.float32) / 8
+        elif case == "signed zero":
+            q = np.where(rng.integers(0, 2, (n, 96)) == 1, np.float32(0.0), np.float32(-0.0)).astype(np.float32)
+        thr = oracle_lib.xqo_eps_threshold(eps)
+        got = np.zeros(n, np.uint16)
+        assert hostsim.hs_act_team(recs.ctypes.data, n, 31, 77, q.ctypes.data, thr, got.ctypes.data) == 0
+        x = O.rng_np(77, ids, recs["ctr"])
+        coin, idx = (x & np.uint64(0x7FFFFFFF)).astype(np.uint32), (x >> np.uint64(33)).astype(np.uint32)
+        for i in range(n):
+            qi = np.zeros(8100); qi[:96] = q[i]
+            k = oracle_lib.xqo_select_action(qi, lists[i], int(counts[i]), int(coin[i]), int(idx[i]), eps)
+            assert got[i] == lists[i, k], (case, i, int(got[i]) >> 7, int(got[i]) & 127, int(lists[i, k]) >> 7, int(lists[i, k]) & 127)
