@@ -125,8 +125,20 @@ def run_reference(args):
             "cpu_baseline": {"value": value, "unit": "steps/s", "cores": cores, "kind": kind, "sample": what},
             "e2e": {"value": value, "unit": "steps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0}
-    print(json.dumps(line))
+    emit(line)
     return 0
+
+
+_REAL_STDOUT = None
+
+
+def emit(line):
+    """the one JSON line of this run, on the process's real stdout"""
+    data = (json.dumps(line) + "\n").encode()
+    if _REAL_STDOUT is None:
+        sys.stdout.write(data.decode()); sys.stdout.flush()
+    else:
+        os.write(_REAL_STDOUT, data)
 
 
 def main():
@@ -142,6 +154,12 @@ def main():
     ap.add_argument("--no-aux", action="store_true")
     ap.add_argument("--no-dqn", action="store_true")
     args = ap.parse_args()
+    # stdout carries exactly ONE JSON line: libraries that write to fd 1 on their own (NCCL prints "NCCL version ..." there) are sent to
+    # stderr for the whole run, and the line goes to the saved descriptor at the end
+    global _REAL_STDOUT
+    sys.stdout.flush()
+    _REAL_STDOUT = os.dup(1)
+    os.dup2(2, 1)
     args.warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup
     if args.impl == "reference":
         return run_reference(args)
@@ -287,7 +305,7 @@ def main():
         line["cpu_baseline"] = {"value": v, "unit": "steps/s", "cores": cores, "kind": kind, "sample": what}
 
     if rank == 0:
-        print(json.dumps(line))
+        emit(line)
     if dist is not None:
         dist.barrier()
         dist.destroy_process_group()

@@ -144,3 +144,18 @@ def test_team_act_selection(O, oracle_lib, hostsim):
             qi = np.zeros(8100); qi[:96] = q[i]
             k = oracle_lib.xqo_select_action(qi, lists[i], int(counts[i]), int(coin[i]), int(idx[i]), eps)
             assert got[i] == lists[i, k], (case, i, int(got[i]) >> 7, int(got[i]) & 127, int(lists[i, k]) >> 7, int(lists[i, k]) & 127)
+
+
+def test_team_phases_under_sanitizers(tmp_path):
+    """the device source of the team kernels, compiled for the host with -fsanitize=address,undefined, runs clean"""
+    import os
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    so = str(tmp_path / "libxq_hostsim_asan.so")
+    subprocess.run(["g++", "-std=c++17", "-O1", "-g", "-fsanitize=address,undefined", "-fno-sanitize-recover=undefined", "-fPIC", "-shared",
+                    "-Wno-unknown-pragmas", "-o", so, os.path.join(root, "tests", "hostsim", "hostsim.cpp")], check=True)
+    pre = ":".join(subprocess.run(["g++", f"-print-file-name={n}"], capture_output=True, text=True, check=True).stdout.strip() for n in ("libasan.so", "libubsan.so"))
+    env = dict(os.environ, LD_PRELOAD=pre, ASAN_OPTIONS="detect_leaks=0")
+    r = subprocess.run([sys.executable, os.path.join(root, "tests", "hostsim", "asan_run.py"), so], env=env, capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0 and "asan/ubsan clean" in r.stdout, r.stdout[-2000:] + r.stderr[-4000:]
