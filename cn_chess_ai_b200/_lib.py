@@ -58,6 +58,7 @@ def lib():
     L.xq_env_set_boards.argtypes = [_P, _P, C.c_int64, C.c_int64]
     L.xq_env_get_boards.argtypes = [_P, _P, C.c_int64, C.c_int64]
     L.xq_env_legal_moves.argtypes = [_P, _P, _P]
+    L.xq_env_legal_moves_strict.argtypes = [_P, _P, _P]
     L.xq_env_valid_moves.argtypes = [_P, C.c_int, C.c_int, _P, _P]
     L.xq_env_is_valid_move.argtypes = [_P, _P, _P]
     L.xq_env_step.argtypes = [_P, _P, _P, _P, _P, _P, _P, C.c_int]

@@ -65,6 +65,34 @@ __global__ void __launch_bounds__(kThreads) legal_moves_kernel(const xq_env_rec*
     for (int j = tid; j < live * 64; j += kThreads) actions[env0 * 64 + j] = s_list[(j >> 6) * kListStride + (j & 63)];
 }
 
+// K1s: the same list filtered by the opt-in strict legality test (xq_rules.cuh: leaves_general_safe): self-check and
+// flying-general rejection, which the reference does not have.  Every pseudo-legal action is tried on the shared-memory board.
+__global__ void __launch_bounds__(kThreads) legal_moves_strict_kernel(const xq_env_rec* __restrict__ envs, int64_t n,
+                                                                     uint8_t* __restrict__ counts, uint32_t* __restrict__ actions) {
+    __shared__ uint32_t s_board[12 * kThreads];
+    __shared__ uint32_t s_list[kThreads * kListStride];
+    const int tid = threadIdx.x;
+    const int64_t env0 = (int64_t)blockIdx.x * kThreads;
+    const int64_t env = env0 + tid;
+    uint16_t* my = reinterpret_cast<uint16_t*>(&s_list[tid * kListStride]);
+    if (env < n) {
+        SmemBoard b{s_board + tid, kThreads};
+        b.load(envs + env);
+        Meta m; m.load(envs + env);
+        int cnt = 0, kept = 0;
+        all_actions(b, m.player, [&](int from, int to) { if (cnt < XQ_MAX_ACTIONS) my[cnt++] = XQ_ACTION(from, to); });
+        for (int k = 0; k < cnt; ++k) {
+            const int a = my[k];
+            if (leaves_general_safe(b, m.player, XQ_ACTION_FROM(a), XQ_ACTION_TO(a))) my[kept++] = (uint16_t)a;
+        }
+        for (int k = kept; k < XQ_MAX_ACTIONS; ++k) my[k] = XQ_ACTION_NONE;
+        counts[env] = (uint8_t)kept;
+    }
+    __syncthreads();
+    const int64_t live = min((int64_t)kThreads, n - env0);
+    for (int j = tid; j < live * 64; j += kThreads) actions[env0 * 64 + j] = s_list[(j >> 6) * kListStride + (j & 63)];
+}
+
 // K1b: ChessBoard::getValidMoves(row,col) for one square of every env
 __global__ void __launch_bounds__(kThreads) valid_moves_kernel(const xq_env_rec* __restrict__ envs, int64_t n, int row, int col,
                                                               uint8_t* __restrict__ counts, uint8_t* __restrict__ to_out) {
@@ -417,6 +445,18 @@ int xq_env_legal_moves(xq_env_t h, uint8_t* counts_host, xq_action* actions_host
     if (!counts_host || !actions_host) return fail(XQ_ERR_INVALID, "xq_env_legal_moves: null output");
     if (!h->d_lists) XQ_CUDA(cudaMalloc(&h->d_lists, sizeof(uint32_t) * 64 * h->n));
     legal_moves_kernel<<<grid_for(h->n, kThreads), kThreads, 0, h->stream>>>(h->d_envs, h->n, h->d_u8[0], h->d_lists);
+    XQ_LAUNCH_CHECK();
+    XQ_CUDA(cudaMemcpyAsync(counts_host, h->d_u8[0], (size_t)h->n, cudaMemcpyDeviceToHost, h->stream));
+    XQ_CUDA(cudaMemcpyAsync(actions_host, h->d_lists, sizeof(uint32_t) * 64 * h->n, cudaMemcpyDeviceToHost, h->stream));
+    XQ_CUDA(cudaStreamSynchronize(h->stream));
+    return XQ_OK;
+}
+
+int xq_env_legal_moves_strict(xq_env_t h, uint8_t* counts_host, xq_action* actions_host) {
+    XQ_ENV_ENTER(h);
+    if (!counts_host || !actions_host) return fail(XQ_ERR_INVALID, "xq_env_legal_moves_strict: null output");
+    if (!h->d_lists) XQ_CUDA(cudaMalloc(&h->d_lists, sizeof(uint32_t) * 64 * h->n));
+    legal_moves_strict_kernel<<<grid_for(h->n, kThreads), kThreads, 0, h->stream>>>(h->d_envs, h->n, h->d_u8[0], h->d_lists);
     XQ_LAUNCH_CHECK();
     XQ_CUDA(cudaMemcpyAsync(counts_host, h->d_u8[0], (size_t)h->n, cudaMemcpyDeviceToHost, h->stream));
     XQ_CUDA(cudaMemcpyAsync(actions_host, h->d_lists, sizeof(uint32_t) * 64 * h->n, cudaMemcpyDeviceToHost, h->stream));

@@ -190,6 +190,39 @@ XQ_HD void all_actions(const B& b, int player, F&& emit) {
         }
 }
 
+// ---- opt-in STRICT legality (xq_env_legal_moves_strict) -- NOT the reference's rules --------------------------------------------
+// The reference plays "capture the General": it has no king-safety test and no flying-general rule, and every
+// parity path of this library follows it.  Standard Xiangqi additionally forbids a move after which the mover's own General could
+// be taken.  This predicate states that on top of the reference's own generators: the pseudo-legal action (from, to) of `player`
+// is kept iff, on the board after it, (a) no enemy piece has `g` among the destinations ChessBoard::getValidMoves generates for it,
+// g = the mover's first General in square order ("self-check"), and (b) the two first Generals do not stand on one file with
+// nothing between them ("flying general").  A side without a General has nothing to protect: all its actions are kept.
+// The board is modified and restored.
+template <class B>
+XQ_HD bool leaves_general_safe(B& b, int player, int from, int to) {
+    const int code = b.get(from), cap = b.get(to);
+    b.set(to, code);
+    b.set(from, 0);
+    const int own_gen = player == RED ? GENERAL : GENERAL + 7, opp_gen = player == RED ? GENERAL + 7 : GENERAL;
+    int g = -1, eg = -1;
+    for (int s = 0; s < 90; ++s) {
+        const int c = b.get(s);
+        if (c == own_gen && g < 0) g = s;
+        if (c == opp_gen && eg < 0) eg = s;
+    }
+    bool safe = true;
+    if (g >= 0) {
+        for (int s = 0; s < 90 && safe; ++s) {
+            const int c = b.get(s);
+            if (c != 0 && (c >= 8) != (player == BLACK)) gen_piece(b, s / 9, s % 9, c, [&](int t) { if (t == g) safe = false; });
+        }
+        if (safe && eg >= 0 && g % 9 == eg % 9) safe = count_between(b, g / 9, g % 9, eg / 9, eg % 9) != 0;
+    }
+    b.set(from, code);
+    b.set(to, cap);
+    return safe;
+}
+
 // ChessAI::evaluateBoard's last two lines (src/chessai.cpp:343-344): (int)(score - moveCount*0.1) with
 // IEEE double mul-then-sub equals this truncating integer division for every reachable
 // (score, moveCount) (re-proved by tests/test_oracle.py).  No floating point on device.

@@ -63,10 +63,11 @@ class BatchedEnv:
         check(self._L.xq_env_get_boards(self._h, ptr(out), first, n))
         return out
 
-    def legal_moves(self):
+    def legal_moves(self, strict=False):
+        """reference-ordered action lists; strict=True (opt-in, not the reference's rules) drops self-check and flying-general moves"""
         counts = np.empty(self.n, dtype=np.uint8)
         actions = np.empty((self.n, MAX_ACTIONS), dtype=np.uint16)
-        check(self._L.xq_env_legal_moves(self._h, ptr(counts), ptr(actions)))
+        check((self._L.xq_env_legal_moves_strict if strict else self._L.xq_env_legal_moves)(self._h, ptr(counts), ptr(actions)))
         return counts, actions
 
     def valid_moves(self, row, col):

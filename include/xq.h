@@ -103,6 +103,12 @@ int xq_env_get_boards(xq_env_t h, xq_env_rec* recs_host, int64_t first, int64_t 
  * ChessBoard::getValidMoves + generate*Moves, src/chessboard.cpp:112-283, in reference order.
  * counts_host[n]; actions_host[n][XQ_MAX_ACTIONS], entries past the count are XQ_ACTION_NONE. */
 int xq_env_legal_moves(xq_env_t h, uint8_t* counts_host, xq_action* actions_host);
+/* OPT-IN, not a rule of the reference (which plays "capture the General": no king-safety test, no flying-general rule, SURVEY F1/F2;
+ * every other entry point follows it bit-exactly): the list of xq_env_legal_moves, same order and layout, without the actions that
+ * standard Xiangqi forbids -- after the action (a) some enemy piece would have the mover's General among the destinations
+ * ChessBoard::getValidMoves generates for it (self-check), or (b) the two Generals would face each other on a file with nothing
+ * between them (flying general).  "General" = the side's first General in square order; a side without one keeps every action. */
+int xq_env_legal_moves_strict(xq_env_t h, uint8_t* counts_host, xq_action* actions_host);
 /* ChessBoard::getValidMoves(row,col) for one square of every env (any colour), same order.
  * to_host[n][20], counts_host[n]. */
 int xq_env_valid_moves(xq_env_t h, int row, int col, uint8_t* counts_host, uint8_t* to_host);

@@ -54,6 +54,7 @@ def oracle():
         L.xqo_bench_rollout_random.argtypes = [C.c_int, C.c_long, C.c_int, C.c_uint64, C.POINTER(C.c_long)]
         L.xqo_rollout_random.argtypes = [_P, C.c_long, C.c_uint64, C.c_uint64, C.c_int, _P, _P]
         L.xqo_batch_all_actions.argtypes = [_P, C.c_long, _u8p, _u16p]
+        L.xqo_batch_all_actions_strict.argtypes = [_P, C.c_long, _u8p, _u16p]
         L.xqo_batch_step.argtypes = [_P, C.c_long, _u16p, _i32p, _u8p, _u8p, _u8p, _u8p]
         L.xqo_eps_threshold.restype = C.c_uint32
         L.xqo_eps_threshold.argtypes = [C.c_double]
@@ -101,6 +102,7 @@ def ref():
         L.ref_env_is_valid_move.argtypes = [_P, C.c_int, C.c_int, C.c_int, C.c_int]
         L.ref_env_valid_moves.argtypes = [_P, C.c_int, C.c_int, _i32p]
         L.ref_env_all_actions.argtypes = [_P, C.c_int, _i32p]
+        L.ref_env_all_actions_strict.argtypes = [_P, C.c_int, _i32p]
         L.ref_env_move.argtypes = [_P, C.c_int, C.c_int]
         L.ref_env_evaluate.argtypes = [_P, C.c_int, C.c_int]
         L.ref_env_state.argtypes = [_P, _f64p]

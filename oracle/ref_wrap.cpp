@@ -93,6 +93,37 @@ int ref_env_all_actions(void* h, int player, int* from_to) {
     auto v = e->ai->getAllValidActions(player == 0 ? PieceColor::Red : PieceColor::Black);
     int n = 0; for (const auto& a : v) { from_to[2 * n] = a.from; from_to[2 * n + 1] = a.to; ++n; } return n;
 }
+// Strict legality stated with the reference's OWN classes (the pin of xqo_all_actions_strict): every action of getAllValidActions is
+// played on a copy of the board with ChessBoard::movePiece; it is kept iff no action of the other side's getAllValidActions lands on
+// the mover's first General and the two first Generals do not face each other on an empty file.
+int ref_env_all_actions_strict(void* h, int player, int* from_to) {
+    Env* e = static_cast<Env*>(h);
+    const PieceColor me = player == 0 ? PieceColor::Red : PieceColor::Black, other = player == 0 ? PieceColor::Black : PieceColor::Red;
+    auto v = e->ai->getAllValidActions(me);
+    int n = 0;
+    for (const auto& a : v) {
+        ChessBoard c = e->board;
+        c.movePiece(a.from / 9, a.from % 9, a.to / 9, a.to % 9);
+        int g = -1, eg = -1;
+        for (int s = 0; s < 90; ++s) {
+            const ChessPiece p = c.getPieceAt(s / 9, s % 9);
+            if (p.type == PieceType::General && p.color == me && g < 0) g = s;
+            if (p.type == PieceType::General && p.color == other && eg < 0) eg = s;
+        }
+        bool safe = true;
+        if (g >= 0) {
+            ChessAI ai2(&c);
+            for (const auto& r : ai2.getAllValidActions(other)) if (r.to == g) safe = false;
+            if (safe && eg >= 0 && g % 9 == eg % 9) {
+                int between = 0;
+                for (int s = std::min(g, eg) + 9; s < std::max(g, eg); s += 9) between += c.getPieceAt(s / 9, s % 9).type != PieceType::Empty;
+                if (between == 0) safe = false;
+            }
+        }
+        if (safe) { from_to[2 * n] = a.from; from_to[2 * n + 1] = a.to; ++n; }
+    }
+    return n;
+}
 // ChessBoard::movePiece (src/chessboard.cpp:38-64); returns code of captured piece (0 also for a rejected move)
 int ref_env_move(void* h, int from, int to) {
     return code_of(static_cast<Env*>(h)->board.movePiece(from / 9, from % 9, to / 9, to % 9));

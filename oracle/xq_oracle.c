@@ -381,6 +381,51 @@ double xqo_bench_rollout_random(int n_threads, long envs_per_thread, int n_plies
     return (double)(t1.tv_sec - t0.tv_sec) + 1e-9 * (double)(t1.tv_nsec - t0.tv_nsec);
 }
 
+/* Opt-in STRICT legality (include/xq.h: xq_env_legal_moves_strict) -- not a rule of the reference, stated on top of its generators:
+ * the action is kept iff after it (a) no enemy piece has the mover's first General (square order) among the destinations
+ * ChessBoard::getValidMoves generates for it, and (b) the two first Generals do not face each other on a file with nothing between.
+ * Pinned against the reference's own classes composed the same way (ref_wrap.cpp: ref_env_all_actions_strict). */
+int xqo_all_actions_strict(const xqo_env* e0, int player, uint16_t* actions) {
+    uint16_t all[XQO_MAX_ACTIONS];
+    uint8_t to[32];
+    int n = xqo_all_actions(e0, player, all), kept = 0;
+    for (int k = 0; k < n; ++k) {
+        xqo_env e = *e0;
+        int from = all[k] >> 7, t = all[k] & 127;
+        set_code(&e, t, get_code(&e, from));
+        set_code(&e, from, 0);
+        int g = -1, eg = -1, safe = 1;
+        for (int s = 0; s < 90; ++s) {
+            int c = get_code(&e, s);
+            if (type_of(c) == GENERAL && color_of(c) == player && g < 0) g = s;
+            if (type_of(c) == GENERAL && color_of(c) != player && eg < 0) eg = s;
+        }
+        if (g >= 0) {
+            for (int s = 0; s < 90 && safe; ++s) {
+                int c = get_code(&e, s);
+                if (c != 0 && color_of(c) != player) {
+                    int m = xqo_valid_moves(&e, s / COLS, s % COLS, to);
+                    for (int j = 0; j < m; ++j) if (to[j] == g) safe = 0;
+                }
+            }
+            if (safe && eg >= 0 && g % COLS == eg % COLS) {
+                int lo = g < eg ? g : eg, hi = g < eg ? eg : g, between = 0;
+                for (int s = lo + COLS; s < hi; s += COLS) between += get_code(&e, s) != 0;
+                if (between == 0) safe = 0;
+            }
+        }
+        if (safe) actions[kept++] = all[k];
+    }
+    return kept;
+}
+void xqo_batch_all_actions_strict(const xqo_env* envs, long n, uint8_t* counts, uint16_t* actions) {
+    for (long i = 0; i < n; ++i) {
+        uint16_t* a = actions + i * XQO_MAX_ACTIONS;
+        memset(a, 0xFF, XQO_MAX_ACTIONS * sizeof(uint16_t));
+        counts[i] = (uint8_t)xqo_all_actions_strict(&envs[i], envs[i].player, a);
+    }
+}
+
 void xqo_batch_all_actions(const xqo_env* envs, long n, uint8_t* counts, uint16_t* actions) {
     for (long i = 0; i < n; ++i) {
         uint16_t* a = actions + i * XQO_MAX_ACTIONS;

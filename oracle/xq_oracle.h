@@ -77,6 +77,9 @@ double xqo_bench_rollout_random(int n_threads, long envs_per_thread, int n_plies
 
 /* batched per-position queries (for differential tests) */
 void xqo_batch_all_actions(const xqo_env* envs, long n, uint8_t* counts, uint16_t* actions /* [n][128] */);
+/* opt-in strict legality (not a rule of the reference): self-check and flying-general rejection on top of its generators */
+int xqo_all_actions_strict(const xqo_env* e, int player, uint16_t* actions);
+void xqo_batch_all_actions_strict(const xqo_env* envs, long n, uint8_t* counts, uint16_t* actions /* [n][128], 0xFFFF past the count */);
 void xqo_batch_step(xqo_env* envs, long n, const uint16_t* actions, int32_t* reward, uint8_t* done, uint8_t* winner,
                     uint8_t* captured, uint8_t* valid);
 

@@ -52,6 +52,7 @@ def hostsim():
     H.hs_rng.restype = C.c_uint64
     H.hs_rng.argtypes = [C.c_uint64, C.c_uint64, C.c_uint32]
     H.hs_all_actions.argtypes = [P, C.c_long, P, P]
+    H.hs_all_actions_strict.argtypes = [P, C.c_long, P, P]
     H.hs_bb_all_actions.argtypes = [P, C.c_long, P, P]
     H.hs_valid_moves.argtypes = [P, C.c_int, C.c_int, P]
     H.hs_is_valid_move.argtypes = [P, C.c_int, C.c_int, C.c_int, C.c_int]

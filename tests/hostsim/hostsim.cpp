@@ -148,6 +148,27 @@ int hs_act_team(const xq_env_rec* recs, long n, uint64_t env_id0, uint64_t seed,
 int hs_team_rollout(int team, xq_env_rec* recs, long n, uint64_t env_id0, uint64_t seed, int n_plies, xq_trace_rec* trace, xq_env_stats* stats) {
     return team == 8 ? team_rollout_host<8>(recs, n, env_id0, seed, n_plies, trace, stats) : team_rollout_host<4>(recs, n, env_id0, seed, n_plies, trace, stats);
 }
+// opt-in strict legality (xq_rules.cuh: leaves_general_safe): the reference-ordered list filtered
+void hs_all_actions_strict(const xq_env_rec* recs, long n, uint8_t* counts, uint16_t* actions) {
+    struct MutBoard {
+        uint32_t w[12];
+        int get(int s) const { return (w[s >> 3] >> ((s & 7) * 4)) & 15; }
+        void set(int s, int code) { w[s >> 3] = (w[s >> 3] & ~(15u << ((s & 7) * 4))) | ((uint32_t)code << ((s & 7) * 4)); }
+    };
+    for (long i = 0; i < n; ++i) {
+        MutBoard b;
+        std::memcpy(b.w, recs[i].sq, 48);
+        uint16_t* out = actions + i * XQ_MAX_ACTIONS;
+        for (int k = 0; k < XQ_MAX_ACTIONS; ++k) out[k] = XQ_ACTION_NONE;
+        uint16_t all[XQ_MAX_ACTIONS];
+        int cnt = 0, kept = 0;
+        const MutBoard& cb = b;
+        xq::all_actions(cb, recs[i].player, [&](int from, int to) { if (cnt < XQ_MAX_ACTIONS) all[cnt++] = XQ_ACTION(from, to); });
+        for (int k = 0; k < cnt; ++k)
+            if (xq::leaves_general_safe(b, recs[i].player, XQ_ACTION_FROM(all[k]), XQ_ACTION_TO(all[k]))) out[kept++] = all[k];
+        counts[i] = (uint8_t)kept;
+    }
+}
 void hs_all_actions(const xq_env_rec* recs, long n, uint8_t* counts, uint16_t* actions) {
     for (long i = 0; i < n; ++i) {
         RecBoard b{recs[i].sq};
