@@ -99,6 +99,13 @@ struct Fast {
     __nv_bfloat16* W1lo = nullptr;                     // [96][128] BF16 residual of W1 rows 0..95 (W1 = W1bf + W1lo to ~16 mantissa bits)
     __nv_bfloat16 *actHhi = nullptr, *actHlo = nullptr;   // [act_cap][128] h(s) as BF16 hi + lo
     int64_t act_cap = 0, act_rows = 0;
+    // fixed-point layer-0 sums carried from ply to ply (l0_act_kernel)
+    int32_t *W0Q = nullptr, *b0Q = nullptr;            // [(1260 + 1)][128], [128]: rint(W0^T * 2^k), rint(b0 * 2^k)
+    uint32_t* actMax = nullptr;                        // two slots of max |w| bits (alternating per weight version) | inv_scale (float) at [2]
+    int32_t* actZ = nullptr;                           // [act_cap][128] fixed-point z0 of the board in actPrev
+    uint32_t* actPrev = nullptr;                       // [act_cap][12] board words actZ belongs to
+    uint64_t w_version = 1, actq_version = 0, actz_version = 0;   // online W0 / b0 version; version W0Q / actZ were built from
+    int act_slot = 0;
     CUtensorMap tmActHi, tmActLo, tmW1q, tmW1loq;
     int64_t tm_rows = 0;
 };
@@ -152,46 +159,166 @@ __global__ void __launch_bounds__(256) l0_forward_kernel(const uint8_t* __restri
     if (Hf) reinterpret_cast<float4*>(Hf + s * kHid)[lane] = h;
     store_h_bf16(Hbf, s, lane, h);
 }
-// Acting: h(s) for every env of a shard, one warp per board (ballot-compacted row list, 8 rows in flight), written as
-// BF16 hi + lo (h = hi + lo to ~16 mantissa bits) for the split-precision layer-1 contraction of q90_gemm_kernel.
-__global__ void __launch_bounds__(256) l0_act_kernel(const xq_env_rec* __restrict__ envs, int64_t n, const float* __restrict__ W0T,
-                                                    const float* __restrict__ b0, __nv_bfloat16* __restrict__ Hhi, __nv_bfloat16* __restrict__ Hlo) {
-    __shared__ __align__(16) uint16_t s_rows[8][96];
-    const int wib = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int64_t e = (int64_t)blockIdx.x * 8 + wib;
-    if (e >= n) return;
-    const uint32_t word = lane < 12 ? envs[e].sq[lane] : 0u;
+// Acting: h(s) for every env of a shard, one warp per board, written as BF16 hi + lo (h = hi + lo to ~16 mantissa bits) for the
+// split-precision layer-1 contraction of q90_gemm_kernel.
+//
+// The pre-activation z0 = b0 + (sum of the <= 32 rows of W0^T a board selects, src/chessai.cpp:268-289) is kept PER ENV between plies
+// and UPDATED from the squares a ply changed (a quiet move: -row(from, piece) +row(to, piece); a capture: one more subtraction), the
+// way an efficiently-updatable evaluation network does it: 2-3 rows per ply instead of ~30.  For the update to be exact -- Q(s) must stay
+// a pure function of (board, weights), or two runs that reach a position along different paths would break arg-max ties differently --
+// the sum is carried in 32-bit FIXED POINT: W0Q = rint(W0 * 2^k), k chosen per weight version from max |W0|, |b0| so that 92 terms
+// cannot overflow (act_quant_*_kernel).  Integer addition is associative, so "previous sum - old rows + new rows" IS the fresh sum,
+// bit for bit (and wrap-around in an intermediate value is harmless).  With the reference's U(-0.05, 0.05) initialisation k = 28: a
+// quantum of 3.7e-9 = the FP32 ulp of the larger weights, so the fixed-point sum is closer to the FP64 oracle than a sequential FP32 sum.
+// Per env the kernel keeps the sum (512 B) and the board it belongs to (48 B); a board that differs from the remembered one in more than
+// 4 squares (reset, xq_env_set_boards, another env handle) or a new weight version (`fresh_all`) takes the gather path over all rows.
+__global__ void __launch_bounds__(256) act_quant_max_kernel(const float* __restrict__ W0T, const float* __restrict__ b0, uint32_t* __restrict__ slot) {
+    uint32_t m = 0;
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < kIn * kHid + kHid; i += gridDim.x * blockDim.x)
+        m = max(m, __float_as_uint(i < kIn * kHid ? W0T[i] : b0[i - kIn * kHid]) & 0x7FFFFFFFu);      // |w| as ordered bits (NaN sorts above inf)
 #pragma unroll
-    for (int r = 0; r < 3; ++r) s_rows[wib][lane + 32 * r] = (uint16_t)kIn;
-    __syncwarp();
-    int cnt = 0;
-#pragma unroll
-    for (int r = 0; r < 3; ++r) {
-        const int q = lane + 32 * r;
-        const uint32_t w = __shfl_sync(0xFFFFFFFFu, word, (q >> 3) % 12);
-        const int code = (w >> (4 * (q & 7))) & 15;
-        const bool piece = q < XQ_SQUARES && code >= 1 && code <= 14;
-        const unsigned m = __ballot_sync(0xFFFFFFFFu, piece);
-        if (piece) s_rows[wib][cnt + __popc(m & ((1u << lane) - 1u))] = (uint16_t)(q * 14 + code - 1);      // src/chessai.cpp:278-282
-        cnt += __popc(m);
+    for (int o = 16; o > 0; o >>= 1) m = max(m, __shfl_xor_sync(0xFFFFFFFFu, m, o));
+    if ((threadIdx.x & 31) == 0 && m) atomicMax(slot, m);
+}
+__device__ __forceinline__ int act_quant_shift(uint32_t max_bits) {
+    int e = 0;
+    const float top = 92.0f * __uint_as_float(max_bits);      // 90 squares + bias + slack
+    if (top > 0.0f && top < INFINITY) frexpf(top, &e); else e = top > 0.0f || top != top ? 120 : -60;     // top < 2^e
+    return min(max(30 - e, -90), 90);                          // |sum| * 2^k < 2^30
+}
+__global__ void __launch_bounds__(256) act_quant_kernel(const float* __restrict__ W0T, const float* __restrict__ b0, const uint32_t* __restrict__ slot,
+                                                       uint32_t* __restrict__ next_slot, int32_t* __restrict__ W0Q, int32_t* __restrict__ b0Q,
+                                                       float* __restrict__ inv_scale) {
+    const int k = act_quant_shift(*slot);
+    const float scale = ldexpf(1.0f, k);
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < (kIn + 1) * kHid + kHid; i += gridDim.x * blockDim.x) {
+        if (i < kIn * kHid) W0Q[i] = __float2int_rn(W0T[i] * scale);
+        else if (i < (kIn + 1) * kHid) W0Q[i] = 0;                                     // row kIn = zeros: the padding row of the lists
+        else b0Q[i - (kIn + 1) * kHid] = __float2int_rn(b0[i - (kIn + 1) * kHid] * scale);
     }
-    __syncwarp();
-    float4 a = reinterpret_cast<const float4*>(b0)[lane];
-    const float4* W = reinterpret_cast<const float4*>(W0T) + lane;
-    for (int k = 0; k < cnt; k += 8) {                          // the list is padded with the zero row kIn
-        const uint4 l = *reinterpret_cast<const uint4*>(&s_rows[wib][k]);
-        const uint32_t idx[8] = {l.x & 0xFFFFu, l.x >> 16, l.y & 0xFFFFu, l.y >> 16, l.z & 0xFFFFu, l.z >> 16, l.w & 0xFFFFu, l.w >> 16};
-        float4 r[8];
+    if (blockIdx.x == 0 && threadIdx.x == 0) { *inv_scale = ldexpf(1.0f, -k); *next_slot = 0u; }     // the other slot serves the next weight version
+}
+// Mapping: 8 lanes per env, 4 envs per warp (the bookkeeping that finds the changed squares is warp-uniform work: 8 lanes amortise it
+// four times better than 32), lane `sub` owns hidden units (i*8 + sub)*4 .. +3 for i < 4, so one load instruction reads 128
+// contiguous bytes of a row per env.  tanh is evaluated as 1 - 2 / (1 + 2^(2 log2(e) |z|)) on the SFU (absolute error ~1e-7, below
+// the 2^-17 relative error of the hi + lo operand split that follows).
+__device__ __forceinline__ uint32_t act_sanitize(uint32_t w) {      // code 15 is not a piece (getStateRepresentation has no channel for it)
+    const uint32_t t = w & (w >> 1) & (w >> 2) & (w >> 3) & 0x11111111u;
+    return w & ~(t * 15u);
+}
+__device__ __forceinline__ uint32_t act_nibble_flags(uint32_t x) { return (x | (x >> 1) | (x >> 2) | (x >> 3)) & 0x11111111u; }     // bit 4i: nibble i != 0
+__device__ __forceinline__ float act_tanh(float z) {
+    float e, r;
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e) : "f"(fabsf(z) * 2.8853900817779268f));
+    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(e + 1.0f));
+    return copysignf(fmaf(-2.0f, r, 1.0f), z);
+}
+__global__ void __launch_bounds__(256) l0_act_kernel(const xq_env_rec* __restrict__ envs, int64_t n, const int32_t* __restrict__ W0Q,
+                                                    const int32_t* __restrict__ b0Q, const float* __restrict__ inv_scale_p,
+                                                    int32_t* __restrict__ Z, uint32_t* __restrict__ Prev, int fresh_all,
+                                                    __nv_bfloat16* __restrict__ Hhi, __nv_bfloat16* __restrict__ Hlo) {
+    __shared__ __align__(8) uint16_t s_rows[32][100];                 // per env: rows entering (+) / leaving (bit 15) the sum, padded with the zero row kIn
+    const int lane = threadIdx.x & 31, sub = lane & 7, slot = threadIdx.x >> 3;
+    const int64_t e0 = ((int64_t)blockIdx.x * 256 + threadIdx.x) >> 3;
+    const bool live = e0 < n;                                         // tail lanes idle along (the shuffles need whole warps)
+    const int64_t e = live ? e0 : 0;
+    const uint4* W = reinterpret_cast<const uint4*>(W0Q) + sub;       // unsigned: wrap-around is defined
+    // board words sub and 8 + sub (sub < 4); word 11 holds squares 88, 89 only
+    uint32_t w[2], pv[2];
+    w[0] = live ? envs[e].sq[sub] : 0u;
+    w[1] = (live && sub < 4) ? envs[e].sq[8 + sub] : 0u;
+    pv[0] = (live && !fresh_all) ? Prev[e * 12 + sub] : 0u;
+    pv[1] = (live && !fresh_all && sub < 4) ? Prev[e * 12 + 8 + sub] : 0u;
+    uint4 a[4];
 #pragma unroll
-        for (int u = 0; u < 8; ++u) r[u] = W[(size_t)idx[u] * (kHid / 4)];
+    for (int i = 0; i < 4; ++i)      // issued before the board is looked at: one memory round trip less on the carried path
+        a[i] = (live && !fresh_all) ? reinterpret_cast<const uint4*>(Z + e * kHid)[i * 8 + sub] : make_uint4(0u, 0u, 0u, 0u);
+    w[0] = act_sanitize(w[0]); w[1] = act_sanitize(w[1]) & (sub == 3 ? 0xFFu : 0xFFFFFFFFu);
+    const uint32_t x[2] = {act_nibble_flags(w[0] ^ pv[0]), act_nibble_flags(w[1] ^ pv[1])};
+    int changed = __popc(x[0]) + __popc(x[1]);
 #pragma unroll
-        for (int u = 0; u < 8; ++u) { a.x += r[u].x; a.y += r[u].y; a.z += r[u].z; a.w += r[u].w; }
+    for (int o = 4; o > 0; o >>= 1) changed += __shfl_xor_sync(0xFFFFFFFFu, changed, o);
+    const bool fresh = live && (fresh_all || changed > 4);            // uniform over the env's 8 lanes
+    // rows that leave (old piece on a changed square) and rows that enter (new piece on a changed square; every piece on the gather path)
+    uint32_t leave[2], enter[2];
+#pragma unroll
+    for (int r = 0; r < 2; ++r) {
+        leave[r] = fresh ? 0u : x[r] & act_nibble_flags(pv[r]);
+        enter[r] = (fresh ? 0x11111111u : x[r]) & act_nibble_flags(w[r]);
     }
-    const float4 h = make_float4(tanhf(a.x), tanhf(a.y), tanhf(a.z), tanhf(a.w));
-    store_h_bf16(Hhi, e, lane, h);
-    const __nv_bfloat162 h01 = __floats2bfloat162_rn(h.x, h.y), h23 = __floats2bfloat162_rn(h.z, h.w);
-    store_h_bf16(Hlo, e, lane, make_float4(h.x - __bfloat162float(h01.x), h.y - __bfloat162float(h01.y), h.z - __bfloat162float(h23.x),
-                                           h.w - __bfloat162float(h23.y)));
+    const int mine = __popc(leave[0]) + __popc(leave[1]) + __popc(enter[0]) + __popc(enter[1]);
+    int pos = mine;                                                   // inclusive scan over the env's 8 lanes
+#pragma unroll
+    for (int o = 1; o < 8; o <<= 1) { const int t = __shfl_up_sync(0xFFFFFFFFu, pos, o, 8); if (sub >= o) pos += t; }
+    const int total = __shfl_sync(0xFFFFFFFFu, pos, 7, 8);
+    pos -= mine;
+#pragma unroll
+    for (int r = 0; r < 2; ++r) {
+        const int sq0 = (r * 8 + sub) * 8;
+        for (uint32_t v = leave[r]; v; v &= v - 1u) {
+            const int sh = (__ffs((int)v) - 1) & 28;
+            s_rows[slot][pos++] = (uint16_t)(0x8000 | ((sq0 + (sh >> 2)) * 14 + (int)((pv[r] >> sh) & 15u) - 1));
+        }
+        for (uint32_t v = enter[r]; v; v &= v - 1u) {
+            const int sh = (__ffs((int)v) - 1) & 28;
+            s_rows[slot][pos++] = (uint16_t)((sq0 + (sh >> 2)) * 14 + (int)((w[r] >> sh) & 15u) - 1);      // src/chessai.cpp:278-282
+        }
+    }
+    if (sub < 4) s_rows[slot][total + sub] = (uint16_t)kIn;           // pad the last group of 4
+    __syncwarp();
+    if (fresh) {
+#pragma unroll
+        for (int i = 0; i < 4; ++i) a[i] = reinterpret_cast<const uint4*>(b0Q)[i * 8 + sub];
+        for (int k = 0; k < total; k += 4) {                          // the gather over all occupied squares: 4 rows in flight
+            const uint2 l = *reinterpret_cast<const uint2*>(&s_rows[slot][k]);
+            const uint32_t idx[4] = {l.x & 0xFFFFu, l.x >> 16, l.y & 0xFFFFu, l.y >> 16};
+            uint4 v[4][4];
+#pragma unroll
+            for (int u = 0; u < 4; ++u)
+#pragma unroll
+                for (int i = 0; i < 4; ++i) v[u][i] = W[(size_t)idx[u] * (kHid / 4) + i * 8];
+#pragma unroll
+            for (int u = 0; u < 4; ++u)
+#pragma unroll
+                for (int i = 0; i < 4; ++i) { a[i].x += v[u][i].x; a[i].y += v[u][i].y; a[i].z += v[u][i].z; a[i].w += v[u][i].w; }
+        }
+    } else {
+        for (int k = 0; k < total; k += 4) {                          // the carried sum: 2 rows for a quiet move, 3 for a capture
+            const uint2 l = *reinterpret_cast<const uint2*>(&s_rows[slot][k]);
+            const uint32_t idx[4] = {l.x & 0xFFFFu, l.x >> 16, l.y & 0xFFFFu, l.y >> 16};
+            uint4 v[4][4];
+#pragma unroll
+            for (int u = 0; u < 4; ++u)
+#pragma unroll
+                for (int i = 0; i < 4; ++i) v[u][i] = W[(size_t)(idx[u] & 0x7FFFu) * (kHid / 4) + i * 8];
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                const uint32_t sg = 0u - (idx[u] >> 15);              // 0 or ~0: (x ^ sg) - sg negates
+#pragma unroll
+                for (int i = 0; i < 4; ++i) {
+                    a[i].x += (v[u][i].x ^ sg) - sg; a[i].y += (v[u][i].y ^ sg) - sg; a[i].z += (v[u][i].z ^ sg) - sg; a[i].w += (v[u][i].w ^ sg) - sg;
+                }
+            }
+        }
+    }
+    if (!live) return;
+    const float is = *inv_scale_p;
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        reinterpret_cast<uint4*>(Z + e * kHid)[i * 8 + sub] = a[i];
+        const float h0 = act_tanh((float)(int)a[i].x * is), h1 = act_tanh((float)(int)a[i].y * is), h2 = act_tanh((float)(int)a[i].z * is),
+                    h3 = act_tanh((float)(int)a[i].w * is);
+        const __nv_bfloat162 hi01 = __floats2bfloat162_rn(h0, h1), hi23 = __floats2bfloat162_rn(h2, h3);
+        const __nv_bfloat162 lo01 = __floats2bfloat162_rn(h0 - __bfloat162float(hi01.x), h1 - __bfloat162float(hi01.y)),
+                             lo23 = __floats2bfloat162_rn(h2 - __bfloat162float(hi23.x), h3 - __bfloat162float(hi23.y));
+        uint2 ph, pl;
+        ph.x = *reinterpret_cast<const uint32_t*>(&hi01); ph.y = *reinterpret_cast<const uint32_t*>(&hi23);
+        pl.x = *reinterpret_cast<const uint32_t*>(&lo01); pl.y = *reinterpret_cast<const uint32_t*>(&lo23);
+        reinterpret_cast<uint2*>(Hhi + e * kHid)[i * 8 + sub] = ph;
+        reinterpret_cast<uint2*>(Hlo + e * kHid)[i * 8 + sub] = pl;
+    }
+    Prev[e * 12 + sub] = w[0];
+    if (sub < 4) Prev[e * 12 + 8 + sub] = w[1];
 }
 
 // Both states of every transition in one launch, ONE WARP PER TRANSITION: the 128-byte replay record is read once
@@ -1140,6 +1267,7 @@ void dqn_fast_destroy(xq_dqn_s* h) {
     for (int r = 0; r < f->world; ++r) if (f->connected && r != f->rank && f->peer[r]) cudaIpcCloseMemHandle(f->peer[r]);
     cudaFree(f->exch);
     cudaFree(f->W0T); cudaFree(f->b0); cudaFree(f->W1); cudaFree(f->b1); cudaFree(f->W1bf); cudaFree(f->W1lo); cudaFree(f->actHhi); cudaFree(f->actHlo);
+    cudaFree(f->W0Q); cudaFree(f->b0Q); cudaFree(f->actMax); cudaFree(f->actZ); cudaFree(f->actPrev);
     cudaFree(f->tW0T); cudaFree(f->tb0); cudaFree(f->tW1); cudaFree(f->tb1); cudaFree(f->tW1bf);
     cudaFree(f->grad); cudaFree(f->boards); cudaFree(f->Hbf); cudaFree(f->H2bf); cudaFree(f->Hf); cudaFree(f->zpart);
     cudaFree(f->cb); cudaFree(f->d0hi); cudaFree(f->d0lo); cudaFree(f->ghi); cudaFree(f->glo); cudaFree(f->q); cudaFree(f->part); cudaFree(f->dbpart); cudaFree(f->info_slots);
@@ -1223,7 +1351,7 @@ static int ensure_fast(xq_dqn_s* h) {
     if (!h->fast_current) {
         f64_to_fast_kernel<<<blocks((int64_t)kOut * kHid, 256), 256, 0, h->stream>>>(h->d_w, h->d_b, f->W0T, f->b0, f->W1, f->b1, f->W1bf, f->W1lo);
         XQ_LAUNCH_CHECK();
-        h->fast_current = true;
+        h->fast_current = true; ++f->w_version;
     }
     if (!f->target_current) {
         f64_to_fast_kernel<<<blocks((int64_t)kOut * kHid, 256), 256, 0, h->stream>>>(h->d_tw, h->d_tb, f->tW0T, f->tb0, f->tW1, f->tb1, f->tW1bf, (__nv_bfloat16*)nullptr);
@@ -1273,9 +1401,11 @@ int dqn_q90_device(xq_dqn_s* h, const xq_env_rec* envs_dev, int64_t n, float* q9
     if (int rc = ensure_fast(h)) return rc;
     Fast* f = h->fast;
     if (n > f->act_cap) {
-        cudaFree(f->actHhi); cudaFree(f->actHlo); f->actHhi = f->actHlo = nullptr; f->act_cap = 0; f->act_rows = 0;
+        cudaFree(f->actHhi); cudaFree(f->actHlo); cudaFree(f->actZ); cudaFree(f->actPrev);
+        f->actHhi = f->actHlo = nullptr; f->actZ = nullptr; f->actPrev = nullptr; f->act_cap = 0; f->act_rows = 0; f->actz_version = 0;
         const int64_t rows = (n + BM - 1) / BM * BM;
         XQ_CUDA(cudaMalloc(&f->actHhi, sizeof(__nv_bfloat16) * rows * kHid)); XQ_CUDA(cudaMalloc(&f->actHlo, sizeof(__nv_bfloat16) * rows * kHid));
+        XQ_CUDA(cudaMalloc(&f->actZ, sizeof(int32_t) * n * kHid)); XQ_CUDA(cudaMalloc(&f->actPrev, sizeof(uint32_t) * n * 12));
         f->act_cap = n;
     }
     if (n != f->act_rows) {
@@ -1283,8 +1413,26 @@ int dqn_q90_device(xq_dqn_s* h, const xq_env_rec* envs_dev, int64_t n, float* q9
         if (int rc = make_tmap(&f->tmActLo, f->actHlo, n, BM)) return rc;
         f->act_rows = n;
     }
-    l0_act_kernel<<<blocks(n, 8), 256, 0, stream>>>(envs_dev, n, f->W0T, f->b0, f->actHhi, f->actHlo);
+    if (!f->W0Q) {
+        XQ_CUDA(cudaMalloc(&f->W0Q, sizeof(int32_t) * (kIn + 1) * kHid)); XQ_CUDA(cudaMalloc(&f->b0Q, sizeof(int32_t) * kHid));
+        XQ_CUDA(cudaMalloc(&f->actMax, sizeof(uint32_t) * 4));
+        XQ_CUDA(cudaMemsetAsync(f->actMax, 0, sizeof(uint32_t) * 4, stream));
+    }
+    if (f->actq_version != f->w_version) {       // the online W0 / b0 changed: new fixed-point table (scale from max |w|), every sum starts over
+        act_quant_max_kernel<<<148, 256, 0, stream>>>(f->W0T, f->b0, f->actMax + f->act_slot);
+        XQ_LAUNCH_CHECK();
+        act_quant_kernel<<<148, 256, 0, stream>>>(f->W0T, f->b0, f->actMax + f->act_slot, f->actMax + (f->act_slot ^ 1), f->W0Q, f->b0Q,
+                                                  reinterpret_cast<float*>(f->actMax + 2));
+        XQ_LAUNCH_CHECK();
+        f->act_slot ^= 1;
+        f->actq_version = f->w_version;
+    }
+    static const bool incremental = [] { const char* e = getenv("XQ_ACT_INCREMENTAL"); return !(e && atoi(e) == 0); }();     // 0: gather every ply (A/B runs; same results)
+    const int fresh_all = (!incremental || f->actz_version != f->w_version) ? 1 : 0;
+    l0_act_kernel<<<blocks(n, 32), 256, 0, stream>>>(envs_dev, n, f->W0Q, f->b0Q, reinterpret_cast<const float*>(f->actMax + 2), f->actZ, f->actPrev, fresh_all,
+                                                    f->actHhi, f->actHlo);
     XQ_LAUNCH_CHECK();
+    f->actz_version = f->w_version;
     const int m_tiles = (int)((n + BM - 1) / BM);
     XQ_CUDA(launch_pdl(q90_gemm_kernel, dim3(m_tiles < 148 ? m_tiles : 148), dim3(kGemmThreads), kQSmem, stream, 1, f->tmActHi, f->tmActLo, f->tmW1q,
                        f->tmW1loq, (const float*)f->b1, (int)n, m_tiles, q90_dev));
@@ -1343,7 +1491,7 @@ int td_update_core(xq_dqn_s* h, const BatchRef& ref, int64_t n, int use_target_n
     XQ_CUDA(launch_pdl(dw_gemm_kernel, dim3(kDwMTiles, kDwSplits), dim3(kDwThreads), kDwSmem, h->stream, kDwSplits, f->tmD0hi, f->tmD0lo, f->tmGhi,
                        f->tmGlo, f->tmCb, (int)n, f->part, f->dbpart, f->info_slots, f->info, cur_grad(f), f->W0T, f->b0, f->W1, f->b1, f->W1bf,
                        f->W1lo, (float)lr, apply ? 1 : 0));
-    if (apply) h->f64_current = false;
+    if (apply) { h->f64_current = false; ++f->w_version; }
     return XQ_OK;
 }
 
@@ -1412,7 +1560,7 @@ int dqn_td_update_pipelined(xq_dqn_s* h, const void* ring, int64_t size, uint64_
         XQ_CUDA(cudaEventRecord(f->ev_free[slot], main));
         if (i + 1 < n_updates) if (int rc = aux_gemm(i + 1)) return rc;
     }
-    h->f64_current = false;
+    h->f64_current = false; ++f->w_version;
     return XQ_OK;
 }
 
@@ -1455,7 +1603,7 @@ int xq_dqn_apply_grads(xq_dqn_t h, double lr) {
     if (lr <= 0) lr = h->lr;
     apply_kernel<<<blocks(kGradSize, 256), 256, 0, h->stream>>>(f->W0T, f->b0, f->W1, f->b1, f->W1bf, f->W1lo, cur_grad(f), (float)lr);
     XQ_LAUNCH_CHECK();
-    h->f64_current = false;
+    h->f64_current = false; ++f->w_version;
     return XQ_OK;
 }
 
@@ -1513,7 +1661,7 @@ int dqn_exchange_apply(xq_dqn_s* h, double lr) {
                                                                                 f->W1bf, f->W1lo, (float)lr);
     XQ_LAUNCH_CHECK();
     f->parity ^= 1;
-    h->f64_current = false;
+    h->f64_current = false; ++f->w_version;
     return XQ_OK;
 }
 }  // namespace xq

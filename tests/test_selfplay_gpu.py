@@ -88,6 +88,45 @@ def test_act_stepwise_vs_oracle(xq, O, oracle_lib):
     assert 0.05 * n * plies < explored < 0.15 * n * plies
 
 
+@pytest.mark.parametrize("w0_scale", [1.0, 8.0])
+def test_acting_q_is_a_pure_function_of_board_and_weights(xq, O, oracle_lib, w0_scale):
+    """The acting path carries the layer-0 sum from ply to ply in fixed point and updates it from the squares a ply changed
+    (l0_act_kernel).  Integer sums are associative, so the carried sum must equal a gather over all rows BIT FOR BIT: net A is
+    used ply after ply (incremental, across captures, resets at the move cap / general captures and an injected position),
+    net B is handed its weights again before every call (new weight version => full gather).  Both stay within 2e-5 of the FP64
+    oracle at every checked ply (the scale of the fixed-point table follows max |W0|: second parameter set)."""
+    n, plies, seed, eps = 600, 215, 23, 0.3
+    w, b = rand_params(12)
+    w = w.copy(); w[:1260 * 128] *= w0_scale
+    netA = xq.DQN(LAYERS); netA.set_params(w, b)
+    netB = xq.DQN(LAYERS)
+    env = xq.BatchedEnv(n, seed=seed)
+    st = np.zeros(1260); qq = np.zeros(8100)
+    worst, finished = 0.0, 0
+    for p in range(plies):
+        if p == 40:      # an injected position (endgame-like: most squares change) in some envs
+            recs = env.get_boards()
+            recs["sq"][::7] = 0
+            recs["sq"][::7, 0] = 0x00010000          # Red General on square 4
+            recs["sq"][::7, 10] = 0x00000008 << 20   # Black General on square 85
+            recs["sq"][::7, 5] = 0x0000C005          # a Red chariot and a Black chariot mid-board
+            env.set_boards(recs)
+        aA, qA = xq.act(netA, env, eps, want_q=True)
+        netB.set_params(w, b)
+        aB, qB = xq.act(netB, env, eps, want_q=True)
+        assert np.array_equal(qA.view(np.uint32), qB.view(np.uint32)), p
+        assert (aA == aB).all()
+        if p in (0, 1, 2, 17, 41, 42, 120, 214):
+            recs = env.get_boards()
+            for i in range(0, n, 53):
+                oracle_lib.xqo_state(recs[i:i + 1].ctypes.data, st)
+                oracle_lib.xqo_nn_forward(LA, 3, w, b, st, qq)
+                worst = max(worst, float(np.abs(qA[i, :90] - qq[:90]).max()))
+        finished += int(env.step(aA, auto_reset=True)[1].sum())
+    assert worst < 2e-5, worst
+    assert finished > n          # resets happened (move cap at ply 200 + general captures)
+
+
 @pytest.mark.parametrize("train_done", [True, False])
 def test_collect_fills_replay_like_the_train_loop(xq, O, oracle_lib, train_done):
     n, plies, seed, eps = 300, 230, 5, 0.1              # > 200 plies: crosses the move cap and the done-one-ply-early quirk
