@@ -103,6 +103,16 @@ def cpu_reference_leg(n_threads, plies_per_thread, seed=1):
     return tot.value / s, kind, what, tot.value, s
 
 
+def reference_train_leg(games=3, timeout=240):
+    """the reference's OWN training loop (ChessAI::train: batch 1, its own CUDA kernels from src/dqn.cu compiled unmodified when a GPU
+    is visible, else the CPU definition of its NeuralNetwork) for a bounded number of games, in a subprocess (oracle/ref_train_bench.py)"""
+    try:
+        r = subprocess.run([sys.executable, "-m", "oracle.ref_train_bench", str(games)], cwd=ROOT, capture_output=True, text=True, timeout=timeout)
+        return json.loads(r.stdout.strip().splitlines()[-1])
+    except Exception as ex:      # a reported baseline, never a reason to lose the bench line
+        return {"unavailable": f"{type(ex).__name__}: {ex}"[:200]}
+
+
 def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
@@ -125,6 +135,9 @@ def run_reference(args):
             "cpu_baseline": {"value": value, "unit": "steps/s", "cores": cores, "kind": kind, "sample": what},
             "e2e": {"value": value, "unit": "steps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0}
+    if not args.no_dqn:      # the DQN half of the metric through the reference's own loop
+        line["dqn"] = {"metric": "transitions trained/s through the reference's ChessAI::train (selectAction + movePiece + 2-3 forwards + backpropagate per ply)",
+                       "reference_train": reference_train_leg()}
     emit(line)
     return 0
 
@@ -296,6 +309,8 @@ def main():
         # the DQN half of the metric: every rank takes part (gradient all-reduce at N > 1), rank 0 reports
         d = xq.bench_dqn(stream, pk, world=world, local=local, dist=dist)
         line["dqn"] = d
+        if rank == 0 and world == 1 and not args.no_cpu_baseline:
+            d["reference_train"] = reference_train_leg()      # the reference's own batch-1 loop on this box, next to transitions_per_s
         launches_total = L.xq_launch_count()
         line["gpu_launches_total"] = int(launches_total)
 

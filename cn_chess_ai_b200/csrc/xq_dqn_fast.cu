@@ -594,7 +594,7 @@ __global__ void __launch_bounds__(kGemmThreads, 1) l1_gemm_kernel(const __grid_c
 // near-ties where they are, the contraction runs in SPLIT precision on the tensor cores: h = h_hi + h_lo and
 // W = W_hi + W_lo in BF16, z = h_hi W_hi + h_lo W_hi + h_hi W_lo (FP32 accumulate; the dropped lo*lo term is
 // < 2^-17 relative) -- 24 UMMA (M128 x N96 x K16) per 128-env tile.  Persistent CTAs stride over the tiles;
-// 8 epilogue warps add the FP32 bias, apply tanhf and write FP32 rows [env][96] through a small per-warp
+// 8 epilogue warps add the FP32 bias, apply tanh (act_tanh: SFU exp2 + rcp, |error| ~1e-7) and write FP32 rows [env][96] through a small per-warp
 // shared-memory transpose so that every store instruction covers contiguous 96-byte row pieces.
 constexpr int QN = 96;
 constexpr int kQStages = 2;
@@ -701,8 +701,8 @@ __global__ void __launch_bounds__(kGemmThreads, 1) q90_gemm_kernel(const __grid_
 #pragma unroll
                 for (int j = 0; j < 24; j += 4) {
                     const float4 b4 = *reinterpret_cast<const float4*>(sBias + half * 48 + c0 + j);
-                    *reinterpret_cast<float4*>(xw + lane * 24 + j) = make_float4(tanhf(__uint_as_float(r[c0 + j]) + b4.x), tanhf(__uint_as_float(r[c0 + j + 1]) + b4.y),
-                                                                                 tanhf(__uint_as_float(r[c0 + j + 2]) + b4.z), tanhf(__uint_as_float(r[c0 + j + 3]) + b4.w));
+                    *reinterpret_cast<float4*>(xw + lane * 24 + j) = make_float4(act_tanh(__uint_as_float(r[c0 + j]) + b4.x), act_tanh(__uint_as_float(r[c0 + j + 1]) + b4.y),
+                                                                                 act_tanh(__uint_as_float(r[c0 + j + 2]) + b4.z), act_tanh(__uint_as_float(r[c0 + j + 3]) + b4.w));
                 }
                 __syncwarp();
                 // lane = (row within a group of 5 rows, 16-byte chunk): 30 lanes move 5 rows x 96 bytes per step

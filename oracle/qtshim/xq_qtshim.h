@@ -67,24 +67,25 @@ public:
 
 // qDebug()/qWarning(): collected into a per-thread line buffer, printed only
 // when XQ_REF_VERBOSE is set (the reference prints one line per game).
-class QDebug {
-    std::ostringstream os_;
+class QDebug {      // no iostreams: the library carries a private libstdc++ whose locale facets are not initialised under dlopen
+    std::string os_;
     bool first_ = true;
-    void sep() { if (!first_) os_ << ' '; first_ = false; }
+    void sep() { if (!first_) os_ += ' '; first_ = false; }
+    template <class T> QDebug& num(const char* fmt, T v) { char b[48]; std::snprintf(b, sizeof b, fmt, v); sep(); os_ += b; return *this; }
 public:
     QDebug() = default;
     QDebug(const QDebug&) {}
-    ~QDebug() { if (std::getenv("XQ_REF_VERBOSE")) std::fprintf(stderr, "%s\n", os_.str().c_str()); }
-    QDebug& operator<<(const char* s) { sep(); os_ << (s ? s : ""); return *this; }
-    QDebug& operator<<(const std::string& s) { sep(); os_ << s; return *this; }
-    QDebug& operator<<(const QString& s) { sep(); os_ << '"' << s.str() << '"'; return *this; }
-    QDebug& operator<<(int v) { sep(); os_ << v; return *this; }
-    QDebug& operator<<(unsigned v) { sep(); os_ << v; return *this; }
-    QDebug& operator<<(long v) { sep(); os_ << v; return *this; }
-    QDebug& operator<<(unsigned long v) { sep(); os_ << v; return *this; }
-    QDebug& operator<<(long long v) { sep(); os_ << v; return *this; }
-    QDebug& operator<<(double v) { sep(); os_ << v; return *this; }
-    QDebug& operator<<(bool v) { sep(); os_ << (v ? "true" : "false"); return *this; }
+    ~QDebug() { if (std::getenv("XQ_REF_VERBOSE")) std::fprintf(stderr, "%s\n", os_.c_str()); }
+    QDebug& operator<<(const char* s) { sep(); os_ += (s ? s : ""); return *this; }
+    QDebug& operator<<(const std::string& s) { sep(); os_ += s; return *this; }
+    QDebug& operator<<(const QString& s) { sep(); os_ += '"'; os_ += s.str(); os_ += '"'; return *this; }
+    QDebug& operator<<(int v) { return num("%d", v); }
+    QDebug& operator<<(unsigned v) { return num("%u", v); }
+    QDebug& operator<<(long v) { return num("%ld", v); }
+    QDebug& operator<<(unsigned long v) { return num("%lu", v); }
+    QDebug& operator<<(long long v) { return num("%lld", v); }
+    QDebug& operator<<(double v) { return num("%g", v); }
+    QDebug& operator<<(bool v) { sep(); os_ += (v ? "true" : "false"); return *this; }
 };
 inline QDebug qDebug() { return QDebug(); }
 inline QDebug qWarning() { return QDebug(); }

@@ -1,9 +1,26 @@
 // Drives the C++ adapter classes (cn_chess_ai_b200/adapter/xq_adapter.hpp) the way MainWindow / Worker drive the
 // reference classes; prints a transcript that tests/test_adapter_gpu.py compares with the reference build.
+#include <string>
+#include <cstdlib>
 #include <cstdio>
 #include "../../cn_chess_ai_b200/adapter/xq_adapter.hpp"
 
-int main() {
+// `test_adapter trainparity|selfplayparity <model in> <episodes> <model out>`: ChessAI::train / startSelfPlay from a given model file; prints one `event g red black` line per
+// finished game -- tests/test_adapter_gpu.py runs the reference's own ChessAI::train on the same weights and the same rand() stream
+static int train_parity(bool self_play, const char* in, int episodes, const char* out) {
+    ChessBoard board;
+    ChessAI ai(&board);
+    ai.initializeDQN();
+    ai.loadModel(in);
+    ai.on_game_completed = [](int g, int r, int b) { std::printf("event %d %d %d\n", g, r, b); };
+    if (self_play) ai.startSelfPlay(episodes); else ai.train(episodes);
+    ai.saveModel(out);
+    return 0;
+}
+
+int main(int argc, char** argv) {
+    if (argc == 5 && (std::string(argv[1]) == "trainparity" || std::string(argv[1]) == "selfplayparity"))
+        return train_parity(std::string(argv[1]) == "selfplayparity", argv[2], std::atoi(argv[3]), argv[4]);
     ChessBoard board;
     ChessAI ai(&board);
     auto acts = ai.getAllValidActions(PieceColor::Red);

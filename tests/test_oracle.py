@@ -7,6 +7,7 @@
 import ctypes as C
 
 import numpy as np
+import pytest
 
 from conftest import recs_from_codes
 
@@ -196,3 +197,69 @@ def test_rollout_vs_reference_driver(O, oracle_lib, ref_lib):
     assert ((out["flags"][:, 0] & 1) == tr[:, 4]).all() and (((out["flags"][:, 0] >> 1) & 3) == tr[:, 5]).all()
     assert st[0]["games"] == games.value
     ref_lib.ref_env_free(h)
+
+
+@pytest.mark.parametrize("self_play", [False, True])
+def test_train_loop_vs_reference(O, oracle_lib, ref_lib, self_play, tmp_path, monkeypatch):
+    """SURVEY 8(a) rows a12-a18 end to end: the reference's OWN ChessAI::train / startSelfPlay (src/chessai.cpp:85-170, :191-266: selectAction with its rand()
+    stream injected, movePiece, evaluateBoard, done one ply early, TD target from the ONLINE network over all 8100 outputs,
+    backpropagate as written, gameCompleted) against the same loop composed from the oracle's restatements.  Same events, same games,
+    final weights equal to rounding (the reference network here is oracle/nn_cpu.cpp's CPU definition of NeuralNetwork)."""
+    LA = np.array([1260, 128, 8100], np.int32)
+    rng = np.random.default_rng(5)
+    w = rng.uniform(-0.05, 0.05, 1260 * 128 + 128 * 8100)
+    b = rng.uniform(-0.05, 0.05, 128 + 8100)
+    draws = rng.integers(0, 2 ** 31 - 1, 2000, dtype=np.int64).astype(np.int32)
+    episodes = 2
+    h = C.c_void_p(ref_lib.ref_env_new())
+    ref_lib.ref_rand_load(draws, len(draws))
+    w_ref, b_ref = np.zeros_like(w), np.zeros_like(b)
+    P = C.c_void_p
+    monkeypatch.chdir(tmp_path)              # the reference appends to game_log.txt in the working directory
+    assert (ref_lib.ref_ai_selfplay if self_play else ref_lib.ref_ai_train)(h, episodes, w.ctypes.data_as(P), b.ctypes.data_as(P), w_ref.ctypes.data_as(P), b_ref.ctypes.data_as(P)) == 0
+    n_ev = ref_lib.ref_events_count()
+    ev_ref = np.zeros(3 * n_ev, np.int32)
+    ref_lib.ref_events_get(ev_ref)
+    consumed = ref_lib.ref_rand_consumed()
+    ref_lib.ref_env_free(h)
+
+    w2, b2 = w.copy(), b.copy()
+    pos, events, plies = 0, [], 0
+    acts = np.zeros(128, np.uint16)
+    state, nxt, q, qs, qn, tgt = np.zeros(1260), np.zeros(1260), np.zeros(8100), np.zeros(8100), np.zeros(8100), np.zeros(8100)
+    for ep in range(episodes):
+        e = O.new_envs(1)
+        player, move_count = 0, 0                                             # chessai.cpp:90-94
+        oracle_lib.xqo_state(e.ctypes.data, state)
+        while not oracle_lib.xqo_game_over(e.ctypes.data) and (self_play or move_count < 200):
+            if self_play:
+                player = int(e[0]["player"])                                  # :198 board->getCurrentPlayer()
+            n = oracle_lib.xqo_all_actions(e.ctypes.data, player, acts)
+            if n == 0:
+                break
+            coin = int(draws[pos]); pos += 1
+            idx = 0
+            if coin / 2147483647.0 < 0.1:                                     # dqn.cpp:30-33: the second rand() only when exploring
+                idx = int(draws[pos]); pos += 1
+            else:
+                oracle_lib.xqo_nn_forward(LA, 3, w2, b2, state, q)
+            a = int(acts[oracle_lib.xqo_select_action(q, acts, n, coin, idx, 0.1)])
+            f, t = a >> 7, a & 127
+            oracle_lib.xqo_move(e.ctypes.data, f // 9, f % 9, t // 9, t % 9)
+            move_count = int(e[0]["move_count"])
+            reward = oracle_lib.xqo_evaluate(e.ctypes.data, player, move_count)
+            oracle_lib.xqo_state(e.ctypes.data, nxt)
+            done = bool(oracle_lib.xqo_game_over(e.ctypes.data)) or (not self_play and move_count + 1 >= 200)      # :119 vs :227
+            oracle_lib.xqo_nn_forward(LA, 3, w2, b2, state, qs)
+            if not done:
+                oracle_lib.xqo_nn_forward(LA, 3, w2, b2, nxt, qn)
+            oracle_lib.xqo_td_target(qs, qn, 8100, t, float(reward), int(done), 0.99, tgt)
+            oracle_lib.xqo_nn_backprop(LA, 3, w2, b2, state, tgt, 0.001, 0)
+            state[:] = nxt
+            player ^= 1
+            plies += 1
+        events += [ep + 1, int(e[0]["red_score"]), int(e[0]["black_score"])]
+    assert pos == consumed and plies > 20
+    assert list(ev_ref) == events
+    assert np.abs(w2 - w_ref).max() < 1e-12 and np.abs(b2 - b_ref).max() < 1e-12
+    assert np.abs(w2 - w).max() > 1e-6                                        # the weights did move
