@@ -9,12 +9,14 @@
 // slots + bitboards; all 128 threads transpose the Q tile [32 envs][96] into shared memory [to][board] (coalesced reads,
 // conflict-free stores and loads); phase A counts moves and finds each piece's first Q maximum; phase B selects; warp 0 then
 // applies the move on the packed nibble board it kept in shared memory -- a one-ply kernel needs no replicated apply.
+#include "xq_act_l0.cuh"
 #include "xq_act_team.cuh"
 #include "xq_common.cuh"
 
 namespace xq {
 
 constexpr int kAB = 32;   // boards per CTA
+constexpr uint32_t kUpdRestart = 1u << 22, kUpdValid = 1u << 23, kUpdFresh = 1u << 24;
 
 struct ActTransition {    // == xq_transition
     uint32_t s[12], s2[12];
@@ -32,6 +34,7 @@ struct ActIo {            // [item][board]
     uint32_t words[12 * kAB];     // the packed nibble board: warp 0 applies the move here
     uint32_t mat[2 * kAB];        // material per side (ChessAI::evaluateBoard :313-341)
     uint8_t ok[2 * kAB];          // per colour: the piece set fits the 16 slots
+    uint32_t upd[kAB];            // what the ply did to the board, for the carried layer-0 sums: from | to << 7 | code << 14 | cap << 18 | flags
 };
 
 template <bool APPLY>
@@ -40,7 +43,7 @@ __global__ void __launch_bounds__(kAB * 4) act_team_kernel(xq_env_rec* __restric
                                                           uint16_t* __restrict__ actions_out, ActTransition* __restrict__ ring, int64_t ring_cap,
                                                           int64_t ring_pos, xq_env_stats* __restrict__ stats, xq_game_event* __restrict__ events,
                                                           unsigned long long* __restrict__ event_count, int64_t event_cap, uint32_t event_ply,
-                                                          uint8_t* __restrict__ nonstd) {
+                                                          uint8_t* __restrict__ nonstd, const ActCarry carry) {
     __shared__ TeamShared<kAB> sh;
     __shared__ ActShared<kAB> as;
     __shared__ ActIo io;
@@ -49,6 +52,8 @@ __global__ void __launch_bounds__(kAB * 4) act_team_kernel(xq_env_rec* __restric
     const int64_t env0 = (int64_t)blockIdx.x * kAB, env = env0 + lane;
     for (int d = tid + 1; d <= XQ_MAX_ACTIONS; d += kAB * 4) sh.magic[d] = team_mod_magic((uint32_t)d);
     if (tid < kAB) sh.move[tid] = 0;
+    if (APPLY && carry.Z != nullptr && env0 + (tid >> 2) < n)      // the CTA's 32 sums (16 KB) towards L2 now: the tail reads them ~20 us later
+        asm volatile("prefetch.global.L2 [%0];" ::"l"(carry.Z + env0 * 128 + tid * 32));
 
     // ---- Q tile: q90[env0 .. env0+32)[96] -> qt[to][board], by warps 2 and 3 while warps 0 and 1 unpack the boards ------------
     if (R.role >= 2) {
@@ -126,9 +131,12 @@ __global__ void __launch_bounds__(kAB * 4) act_team_kernel(xq_env_rec* __restric
     __syncthreads();
 
     // ---- warp 0: the chosen action, then the rest of the ply on the nibble board ---------------------------------------------
-    if (R.role != 0) return;
+    const bool carrying = APPLY && carry.Z != nullptr;             // kernel-uniform
+    if (R.role != 0 && !carrying) return;
+    if (R.role == 0) {
     unsigned long long a_steps = 0, a_games = 0, a_red = 0, a_black = 0, a_capg = 0, a_caps = 0, a_legal = 0;
     long long a_reward = 0;
+    uint32_t upd = 0;                                              // bit 23: the env has a carried sum to update
     if (active) {
         const uint32_t mv = sh.move[lane];
         const int from = (int)(mv & 0xFFu), to = (int)((mv >> 8) & 0xFFu);
@@ -167,6 +175,7 @@ __global__ void __launch_bounds__(kAB * 4) act_team_kernel(xq_env_rec* __restric
                 }
                 ctr++; a_games++;
                 restart = true;
+                upd = kUpdValid | kUpdRestart;
             } else {
                 // ChessBoard::movePiece on the nibble board (src/chessboard.cpp:43-63), through shared memory: run-time word index
                 uint32_t* wf = &io.words[(from >> 3) * kAB + lane];
@@ -206,6 +215,7 @@ __global__ void __launch_bounds__(kAB * 4) act_team_kernel(xq_env_rec* __restric
                     }
                 }
                 restart = over;
+                upd = kUpdValid | (uint32_t)from | ((uint32_t)to << 7) | ((uint32_t)code << 14) | ((uint32_t)cap << 18) | (over ? kUpdRestart : 0u) | (fresh ? kUpdFresh : 0u);
             }
             if (ring) {
 #pragma unroll
@@ -218,15 +228,23 @@ __global__ void __launch_bounds__(kAB * 4) act_team_kernel(xq_env_rec* __restric
             uint4* rec = reinterpret_cast<uint4*>(envs + env);
             if (restart) {      // ChessBoard::reset (src/chessboard.cpp:95-102)
 #pragma unroll
-                for (int i = 0; i < 3; ++i) rec[i] = make_uint4(kOpening[4 * i], kOpening[4 * i + 1], kOpening[4 * i + 2], kOpening[4 * i + 3]);
+                for (int i = 0; i < 12; ++i) t.s2[i] = kOpening[i];
                 rec[3] = make_uint4(m0 & 0xFF000000u, 0u, 0u, ctr);
             } else {
-#pragma unroll
-                for (int i = 0; i < 3; ++i) rec[i] = make_uint4(t.s2[4 * i], t.s2[4 * i + 1], t.s2[4 * i + 2], t.s2[4 * i + 3]);
                 rec[3] = make_uint4((uint32_t)(move_count & 0xFFFF) | ((uint32_t)player << 16) | (m0 & 0xFF000000u), (uint32_t)red_score, (uint32_t)black_score, ctr);
+            }
+#pragma unroll
+            for (int i = 0; i < 3; ++i) rec[i] = make_uint4(t.s2[4 * i], t.s2[4 * i + 1], t.s2[4 * i + 2], t.s2[4 * i + 3]);
+            if (carrying) {     // the board the carried sum will belong to (sanitised the way l0_act_kernel remembers boards)
+                uint4* pv = reinterpret_cast<uint4*>(carry.Prev + env * 12);
+#pragma unroll
+                for (int i = 0; i < 3; ++i)
+                    pv[i] = make_uint4(act_sanitize(t.s2[4 * i]), act_sanitize(t.s2[4 * i + 1]), act_sanitize(t.s2[4 * i + 2]),
+                                       act_sanitize(t.s2[4 * i + 3]) & (i == 2 ? 0xFFu : 0xFFFFFFFFu));
             }
         }
     }
+    if (carrying) io.upd[lane] = upd;
     if (APPLY && stats) {      // every counter of a warp fits 32 bits: one REDUX each
         const unsigned v[8] = {(unsigned)a_steps, (unsigned)a_games, (unsigned)a_red, (unsigned)a_black, (unsigned)a_capg, (unsigned)a_caps, 0u, (unsigned)a_legal};
 #pragma unroll
@@ -238,18 +256,47 @@ __global__ void __launch_bounds__(kAB * 4) act_team_kernel(xq_env_rec* __restric
         const int rs = __reduce_add_sync(0xFFFFFFFFu, (int)a_reward);
         if (lane == 0 && rs != 0) atomicAdd(reinterpret_cast<unsigned long long*>(stats) + 6, (unsigned long long)(long long)rs);
     }
+    }   // warp 0
+    if (!carrying) return;
+    __syncthreads();
+    // ---- all 4 warps: carry the fixed-point layer-0 sums of the CTA's 32 envs across the ply (xq_act_l0.cuh) -- the moved piece's row
+    // leaves at `from` and enters at `to`, a captured piece's row leaves; a restarted env takes the sum of the opening position --
+    // and emit h(s) of the new position for the next ply's contraction.  Warp w handles envs w, w + 4, ...; lane = 4 hidden units.
+    {
+        const int w = tid >> 5;
+        const float is = *carry.inv_scale;
+        const uint4* W = reinterpret_cast<const uint4*>(carry.W0Q) + lane;
+        const uint4 zo = reinterpret_cast<const uint4*>(carry.zOpen)[lane];
+#pragma unroll 2
+        for (int b = w; b < kAB; b += 4) {
+            const uint32_t u = io.upd[b];
+            if (!(u & kUpdValid)) continue;                         // warp-uniform
+            const int64_t e = env0 + b;
+            uint4 z = zo;
+            if (!(u & kUpdRestart)) {
+                const int from = (int)(u & 127u), to = (int)((u >> 7) & 127u), code = (int)((u >> 14) & 15u), cap = (int)((u >> 18) & 15u);
+                const uint4 base = (u & kUpdFresh) ? zo : reinterpret_cast<const uint4*>(carry.Z + e * 128)[lane];
+                const uint4 r0 = W[(size_t)(from * 14 + code - 1) * 32], r1 = W[(size_t)(to * 14 + code - 1) * 32];
+                const uint4 r2 = W[(size_t)(cap ? to * 14 + cap - 1 : XQ_STATE_SIZE) * 32];      // row 1260 = zeros
+                z = make_uint4(base.x - r0.x + r1.x - r2.x, base.y - r0.y + r1.y - r2.y, base.z - r0.z + r1.z - r2.z, base.w - r0.w + r1.w - r2.w);
+            }
+            reinterpret_cast<uint4*>(carry.Z + e * 128)[lane] = z;
+            act_emit_h(z, is, carry.Hhi, carry.Hlo, e, lane);
+        }
+    }
 }
 
 cudaError_t launch_act_team(bool apply, xq_env_rec* envs, int64_t n, uint64_t env_id0, uint64_t seed, const float* q90, uint32_t eps_thr, int train_done,
                             uint16_t* actions_out, void* ring, int64_t ring_cap, int64_t ring_pos, xq_env_stats* stats, xq_game_event* events,
-                            unsigned long long* event_count, int64_t event_cap, uint32_t event_ply, uint8_t* nonstd, cudaStream_t stream) {
+                            unsigned long long* event_count, int64_t event_cap, uint32_t event_ply, uint8_t* nonstd, const ActCarry* carry, cudaStream_t stream) {
+    const ActCarry cy = carry ? *carry : ActCarry{};
     const unsigned grid = (unsigned)((n + kAB - 1) / kAB);
     if (apply)
         act_team_kernel<true><<<grid, kAB * 4, 0, stream>>>(envs, n, env_id0, seed, q90, eps_thr, train_done, actions_out, (ActTransition*)ring, ring_cap,
-                                                           ring_pos, stats, events, event_count, event_cap, event_ply, nonstd);
+                                                           ring_pos, stats, events, event_count, event_cap, event_ply, nonstd, cy);
     else
         act_team_kernel<false><<<grid, kAB * 4, 0, stream>>>(envs, n, env_id0, seed, q90, eps_thr, train_done, actions_out, (ActTransition*)ring, ring_cap,
-                                                            ring_pos, stats, events, event_count, event_cap, event_ply, nonstd);
+                                                            ring_pos, stats, events, event_count, event_cap, event_ply, nonstd, cy);
     ++g_launches;
     return cudaGetLastError();
 }

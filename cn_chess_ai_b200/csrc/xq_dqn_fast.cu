@@ -21,6 +21,7 @@
 #include <stdlib.h>
 #include <string.h>
 
+#include "xq_act_l0.cuh"
 #include "xq_dqn_internal.cuh"
 #include "xq_tc.cuh"
 
@@ -101,11 +102,13 @@ struct Fast {
     int64_t act_cap = 0, act_rows = 0;
     // fixed-point layer-0 sums carried from ply to ply (l0_act_kernel)
     int32_t *W0Q = nullptr, *b0Q = nullptr;            // [(1260 + 1)][128], [128]: rint(W0^T * 2^k), rint(b0 * 2^k)
+    int32_t* zOpen = nullptr;                          // [128] sum of the opening position
     uint32_t* actMax = nullptr;                        // two slots of max |w| bits (alternating per weight version) | inv_scale (float) at [2]
     int32_t* actZ = nullptr;                           // [act_cap][128] fixed-point z0 of the board in actPrev
     uint32_t* actPrev = nullptr;                       // [act_cap][12] board words actZ belongs to
     uint64_t w_version = 1, actq_version = 0, actz_version = 0;   // online W0 / b0 version; version W0Q / actZ were built from
     int act_slot = 0;
+    int64_t act_carried_n = -1;
     CUtensorMap tmActHi, tmActLo, tmW1q, tmW1loq;
     int64_t tm_rows = 0;
 };
@@ -198,21 +201,20 @@ __global__ void __launch_bounds__(256) act_quant_kernel(const float* __restrict_
     }
     if (blockIdx.x == 0 && threadIdx.x == 0) { *inv_scale = ldexpf(1.0f, -k); *next_slot = 0u; }     // the other slot serves the next weight version
 }
+// the sum of the opening position (ChessBoard::reset): what a restarted env carries into its next ply
+__global__ void __launch_bounds__(kHid) act_zopen_kernel(const int32_t* __restrict__ W0Q, const int32_t* __restrict__ b0Q, int32_t* __restrict__ zOpen) {
+    uint32_t z = (uint32_t)b0Q[threadIdx.x];
+    for (int q = 0; q < XQ_SQUARES; ++q) {
+        const int code = (int)((kOpening[q >> 3] >> (4 * (q & 7))) & 15u);
+        if (code != 0) z += (uint32_t)W0Q[(q * 14 + code - 1) * kHid + threadIdx.x];
+    }
+    zOpen[threadIdx.x] = (int32_t)z;
+}
 // Mapping: 8 lanes per env, 4 envs per warp (the bookkeeping that finds the changed squares is warp-uniform work: 8 lanes amortise it
 // four times better than 32), lane `sub` owns hidden units (i*8 + sub)*4 .. +3 for i < 4, so one load instruction reads 128
 // contiguous bytes of a row per env.  tanh is evaluated as 1 - 2 / (1 + 2^(2 log2(e) |z|)) on the SFU (absolute error ~1e-7, below
 // the 2^-17 relative error of the hi + lo operand split that follows).
-__device__ __forceinline__ uint32_t act_sanitize(uint32_t w) {      // code 15 is not a piece (getStateRepresentation has no channel for it)
-    const uint32_t t = w & (w >> 1) & (w >> 2) & (w >> 3) & 0x11111111u;
-    return w & ~(t * 15u);
-}
 __device__ __forceinline__ uint32_t act_nibble_flags(uint32_t x) { return (x | (x >> 1) | (x >> 2) | (x >> 3)) & 0x11111111u; }     // bit 4i: nibble i != 0
-__device__ __forceinline__ float act_tanh(float z) {
-    float e, r;
-    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e) : "f"(fabsf(z) * 2.8853900817779268f));
-    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(e + 1.0f));
-    return copysignf(fmaf(-2.0f, r, 1.0f), z);
-}
 __global__ void __launch_bounds__(256) l0_act_kernel(const xq_env_rec* __restrict__ envs, int64_t n, const int32_t* __restrict__ W0Q,
                                                     const int32_t* __restrict__ b0Q, const float* __restrict__ inv_scale_p,
                                                     int32_t* __restrict__ Z, uint32_t* __restrict__ Prev, int fresh_all,
@@ -306,16 +308,7 @@ __global__ void __launch_bounds__(256) l0_act_kernel(const xq_env_rec* __restric
 #pragma unroll
     for (int i = 0; i < 4; ++i) {
         reinterpret_cast<uint4*>(Z + e * kHid)[i * 8 + sub] = a[i];
-        const float h0 = act_tanh((float)(int)a[i].x * is), h1 = act_tanh((float)(int)a[i].y * is), h2 = act_tanh((float)(int)a[i].z * is),
-                    h3 = act_tanh((float)(int)a[i].w * is);
-        const __nv_bfloat162 hi01 = __floats2bfloat162_rn(h0, h1), hi23 = __floats2bfloat162_rn(h2, h3);
-        const __nv_bfloat162 lo01 = __floats2bfloat162_rn(h0 - __bfloat162float(hi01.x), h1 - __bfloat162float(hi01.y)),
-                             lo23 = __floats2bfloat162_rn(h2 - __bfloat162float(hi23.x), h3 - __bfloat162float(hi23.y));
-        uint2 ph, pl;
-        ph.x = *reinterpret_cast<const uint32_t*>(&hi01); ph.y = *reinterpret_cast<const uint32_t*>(&hi23);
-        pl.x = *reinterpret_cast<const uint32_t*>(&lo01); pl.y = *reinterpret_cast<const uint32_t*>(&lo23);
-        reinterpret_cast<uint2*>(Hhi + e * kHid)[i * 8 + sub] = ph;
-        reinterpret_cast<uint2*>(Hlo + e * kHid)[i * 8 + sub] = pl;
+        act_emit_h(a[i], is, Hhi, Hlo, e, i * 8 + sub);
     }
     Prev[e * 12 + sub] = w[0];
     if (sub < 4) Prev[e * 12 + 8 + sub] = w[1];
@@ -1267,7 +1260,7 @@ void dqn_fast_destroy(xq_dqn_s* h) {
     for (int r = 0; r < f->world; ++r) if (f->connected && r != f->rank && f->peer[r]) cudaIpcCloseMemHandle(f->peer[r]);
     cudaFree(f->exch);
     cudaFree(f->W0T); cudaFree(f->b0); cudaFree(f->W1); cudaFree(f->b1); cudaFree(f->W1bf); cudaFree(f->W1lo); cudaFree(f->actHhi); cudaFree(f->actHlo);
-    cudaFree(f->W0Q); cudaFree(f->b0Q); cudaFree(f->actMax); cudaFree(f->actZ); cudaFree(f->actPrev);
+    cudaFree(f->W0Q); cudaFree(f->b0Q); cudaFree(f->zOpen); cudaFree(f->actMax); cudaFree(f->actZ); cudaFree(f->actPrev);
     cudaFree(f->tW0T); cudaFree(f->tb0); cudaFree(f->tW1); cudaFree(f->tb1); cudaFree(f->tW1bf);
     cudaFree(f->grad); cudaFree(f->boards); cudaFree(f->Hbf); cudaFree(f->H2bf); cudaFree(f->Hf); cudaFree(f->zpart);
     cudaFree(f->cb); cudaFree(f->d0hi); cudaFree(f->d0lo); cudaFree(f->ghi); cudaFree(f->glo); cudaFree(f->q); cudaFree(f->part); cudaFree(f->dbpart); cudaFree(f->info_slots);
@@ -1397,7 +1390,7 @@ static int launch_gemm(xq_dqn_s* h, int mode, const CUtensorMap& tmA, const CUte
 
 // Q(s)[0..95] (row-major [n][96] FP32, device) for n env records resident on the device, on `stream`:
 // layer-0 gather (FP32) + split-precision tensor-core contraction with W1 rows 0..95
-int dqn_q90_device(xq_dqn_s* h, const xq_env_rec* envs_dev, int64_t n, float* q90_dev, cudaStream_t stream) {
+int dqn_q90_device(xq_dqn_s* h, const xq_env_rec* envs_dev, int64_t n, float* q90_dev, cudaStream_t stream, bool carried, ActCarry* carry) {
     if (int rc = ensure_fast(h)) return rc;
     Fast* f = h->fast;
     if (n > f->act_cap) {
@@ -1414,7 +1407,7 @@ int dqn_q90_device(xq_dqn_s* h, const xq_env_rec* envs_dev, int64_t n, float* q9
         f->act_rows = n;
     }
     if (!f->W0Q) {
-        XQ_CUDA(cudaMalloc(&f->W0Q, sizeof(int32_t) * (kIn + 1) * kHid)); XQ_CUDA(cudaMalloc(&f->b0Q, sizeof(int32_t) * kHid));
+        XQ_CUDA(cudaMalloc(&f->W0Q, sizeof(int32_t) * (kIn + 1) * kHid)); XQ_CUDA(cudaMalloc(&f->b0Q, sizeof(int32_t) * kHid)); XQ_CUDA(cudaMalloc(&f->zOpen, sizeof(int32_t) * kHid));
         XQ_CUDA(cudaMalloc(&f->actMax, sizeof(uint32_t) * 4));
         XQ_CUDA(cudaMemsetAsync(f->actMax, 0, sizeof(uint32_t) * 4, stream));
     }
@@ -1424,15 +1417,26 @@ int dqn_q90_device(xq_dqn_s* h, const xq_env_rec* envs_dev, int64_t n, float* q9
         act_quant_kernel<<<148, 256, 0, stream>>>(f->W0T, f->b0, f->actMax + f->act_slot, f->actMax + (f->act_slot ^ 1), f->W0Q, f->b0Q,
                                                   reinterpret_cast<float*>(f->actMax + 2));
         XQ_LAUNCH_CHECK();
+        act_zopen_kernel<<<1, kHid, 0, stream>>>(f->W0Q, f->b0Q, f->zOpen);
+        XQ_LAUNCH_CHECK();
         f->act_slot ^= 1;
         f->actq_version = f->w_version;
     }
     static const bool incremental = [] { const char* e = getenv("XQ_ACT_INCREMENTAL"); return !(e && atoi(e) == 0); }();     // 0: gather every ply (A/B runs; same results)
     const int fresh_all = (!incremental || f->actz_version != f->w_version) ? 1 : 0;
-    l0_act_kernel<<<blocks(n, 32), 256, 0, stream>>>(envs_dev, n, f->W0Q, f->b0Q, reinterpret_cast<const float*>(f->actMax + 2), f->actZ, f->actPrev, fresh_all,
-                                                    f->actHhi, f->actHlo);
-    XQ_LAUNCH_CHECK();
+    // `carried`: the caller's act_team_kernel has already brought the sums, the remembered boards and h(s) of these n envs up to date
+    // (tail of the previous ply of the same xq_selfplay_collect call); only valid while nothing else could have touched them
+    if (!(carried && !fresh_all && n == f->act_carried_n)) {
+        l0_act_kernel<<<blocks(n, 32), 256, 0, stream>>>(envs_dev, n, f->W0Q, f->b0Q, reinterpret_cast<const float*>(f->actMax + 2), f->actZ, f->actPrev, fresh_all,
+                                                        f->actHhi, f->actHlo);
+        XQ_LAUNCH_CHECK();
+    }
     f->actz_version = f->w_version;
+    f->act_carried_n = n;
+    if (carry) {
+        carry->W0Q = f->W0Q; carry->zOpen = f->zOpen; carry->inv_scale = reinterpret_cast<const float*>(f->actMax + 2);
+        carry->Z = incremental ? f->actZ : nullptr; carry->Prev = f->actPrev; carry->Hhi = f->actHhi; carry->Hlo = f->actHlo;
+    }
     const int m_tiles = (int)((n + BM - 1) / BM);
     XQ_CUDA(launch_pdl(q90_gemm_kernel, dim3(m_tiles < 148 ? m_tiles : 148), dim3(kGemmThreads), kQSmem, stream, 1, f->tmActHi, f->tmActLo, f->tmW1q,
                        f->tmW1loq, (const float*)f->b1, (int)n, m_tiles, q90_dev));

@@ -15,6 +15,7 @@
 
 #include <algorithm>
 
+#include "xq_act_l0.cuh"
 #include "xq_dqn_internal.cuh"
 #include "xq_env_dev.cuh"
 
@@ -32,7 +33,7 @@ static_assert(sizeof(Transition) == sizeof(xq_transition), "transition layout");
 
 cudaError_t launch_act_team(bool apply, xq_env_rec* envs, int64_t n, uint64_t env_id0, uint64_t seed, const float* q90, uint32_t eps_thr, int train_done,
                             uint16_t* actions_out, void* ring, int64_t ring_cap, int64_t ring_pos, xq_env_stats* stats, xq_game_event* events,
-                            unsigned long long* event_count, int64_t event_cap, uint32_t event_ply, uint8_t* nonstd, cudaStream_t stream);
+                            unsigned long long* event_count, int64_t event_cap, uint32_t event_ply, uint8_t* nonstd, const ActCarry* carry, cudaStream_t stream);
 
 // Action selection (+ optional application), generic thread-per-board version (ordered list staged in shared memory): the fallback
 // of act_team_kernel (xq_act_team.cu) for boards with non-standard piece sets, or for every env with XQ_ACT_TEAM=0 (A/B runs).
@@ -199,10 +200,10 @@ static cudaEvent_t g_ev[64];
 // the generic thread-per-board kernel for the boards it flagged (only possible after xq_env_set_boards injected exotic positions).
 // XQ_ACT_TEAM=0 runs the generic kernel on every env (A/B runs); both give the same results.
 static int launch_act(bool apply, const EnvInfo& ei, const float* q90, uint32_t thr, int train_done, uint16_t* actions, Transition* ring, int64_t ring_cap,
-                      int64_t ring_pos, xq_env_stats* stats, uint32_t event_ply) {
+                      int64_t ring_pos, xq_env_stats* stats, uint32_t event_ply, const ActCarry* carry = nullptr) {
     static const bool team = [] { const char* e = getenv("XQ_ACT_TEAM"); return !(e && atoi(e) == 0); }();
     if (team) XQ_CUDA(launch_act_team(apply, ei.d_envs, ei.n, ei.env_id0, ei.seed, q90, thr, train_done, actions, ring, ring_cap, ring_pos, stats,
-                                      ei.d_events, ei.d_event_count, ei.event_cap, event_ply, ei.d_nonstd, ei.stream));
+                                      ei.d_events, ei.d_event_count, ei.event_cap, event_ply, ei.d_nonstd, carry, ei.stream));
     if (!team || ei.maybe_nonstd) {
         const uint8_t* only = team ? ei.d_nonstd : nullptr;
         if (apply)
@@ -333,10 +334,18 @@ int xq_selfplay_collect(xq_dqn_t h, xq_env_t env, xq_replay_t r, int n_plies, do
     if (int rc = order_after(ei.stream, h->stream, &g_ev[h->device & 63])) return rc;    // see the latest weights
     xq_env_stats* d_stats = ei.d_stats;
     const uint32_t thr = xq_eps_threshold(eps);
+    // the team kernel carries the layer-0 sums and h(s) of its envs into the next ply (tail of act_team_kernel): from the second ply of
+    // this call on, the layer-0 kernel is not launched.  Not when boards with non-standard piece sets may go through the generic kernel.
+    static const bool team = [] { const char* e = getenv("XQ_ACT_TEAM"); return !(e && atoi(e) == 0); }();
+    static const bool carry_on = [] { const char* e = getenv("XQ_ACT_CARRY"); return !(e && atoi(e) == 0); }();
+    const bool can_carry = team && carry_on && !ei.maybe_nonstd;
+    bool carried = false;
     for (int p = 0; p < n_plies; ++p) {
-        if (int rc = dqn_q90_device(h, ei.d_envs, ei.n, sc->q90, ei.stream)) return rc;
+        ActCarry cy;
+        if (int rc = dqn_q90_device(h, ei.d_envs, ei.n, sc->q90, ei.stream, carried, &cy)) return rc;
         if (int rc = launch_act(true, ei, sc->q90, thr, train_done, nullptr, r ? r->d_ring : nullptr, r ? r->capacity : 1, r ? r->total % r->capacity : 0,
-                                d_stats, ei.event_ply + (uint32_t)p)) return rc;
+                                d_stats, ei.event_ply + (uint32_t)p, can_carry ? &cy : nullptr)) return rc;
+        carried = can_carry && cy.Z != nullptr;
         if (r) r->total += ei.n;
     }
     env_advance_event_ply(env, (uint32_t)n_plies);
