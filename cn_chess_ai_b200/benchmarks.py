@@ -90,6 +90,22 @@ def bench_dqn(stream, peaks, world=1, local=0, dist=None, envs=65536, replay_cap
                         "traffic": _td_traffic(), "peak_source": peaks["source"],
                         "note": "achieved = ALGORITHMIC dense FLOPs (9,262,080 per transition) / time of the whole update (4 kernels chained by programmatic dependent launch, replay draws resolved in place); "
                                 "the kernels exploit the one-hot input and one-hot TD error, so far fewer FLOPs are issued (DESIGN.md)"}}
+    if world == 1:
+        # BASELINE config 4 end to end through the public episode driver (xq_train_run = the batched ChessAI::train): rounds of
+        # [4 collector plies over all envs -> 64 batch-4096 TD updates] (replay ratio 1), finished games drained to the host every
+        # round; wall clock around the whole call, host work included
+        from .trainer import train
+        import time
+        train(net, env, rb, n_games=2000, plies_per_round=4, updates_per_round=64, batch=batch, lr=1e-6, autosave_games=0)      # warm-up round
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        rep = train(net, env, rb, n_games=150000, plies_per_round=4, updates_per_round=64, batch=batch, lr=1e-6, autosave_games=0)
+        torch.cuda.synchronize()
+        dt = time.perf_counter() - t0
+        out["train_loop"] = {"what": "xq_train_run: rounds of 4 eps-greedy plies x %d envs + 64 TD updates of batch %d (target-net bootstrap, target sync every 100 plies), "
+                                     "game events drained per round; wall clock" % (envs, batch),
+                             "seconds": dt, "rounds": rep["plies"] // 4, "ms_per_round": 1e3 * dt / max(1, rep["plies"] // 4), "games": rep["games"], "games_per_s": rep["games"] / dt, "env_steps_per_s": rep["transitions"] / dt,
+                             "td_updates_per_s": rep["updates"] / dt, "trained_transitions_per_s": rep["updates"] * batch / dt}
     env.close(); net.close(); rb.close()
     return out
 
