@@ -267,21 +267,27 @@ __global__ void __launch_bounds__(kAB * 4) act_team_kernel(xq_env_rec* __restric
         const float is = *carry.inv_scale;
         const uint4* W = reinterpret_cast<const uint4*>(carry.W0Q) + lane;
         const uint4 zo = reinterpret_cast<const uint4*>(carry.zOpen)[lane];
-#pragma unroll 2
-        for (int b = w; b < kAB; b += 4) {
-            const uint32_t u = io.upd[b];
-            if (!(u & kUpdValid)) continue;                         // warp-uniform
-            const int64_t e = env0 + b;
-            uint4 z = zo;
-            if (!(u & kUpdRestart)) {
-                const int from = (int)(u & 127u), to = (int)((u >> 7) & 127u), code = (int)((u >> 14) & 15u), cap = (int)((u >> 18) & 15u);
-                const uint4 base = (u & kUpdFresh) ? zo : reinterpret_cast<const uint4*>(carry.Z + e * 128)[lane];
+        // all 8 sums of the warp first (one round trip to L2 / HBM instead of eight), then env by env: rows, tanh, stores
+        uint32_t u[kAB / 4];
+        uint4 z[kAB / 4];
+#pragma unroll
+        for (int i = 0; i < kAB / 4; ++i) {
+            u[i] = io.upd[w + 4 * i];
+            const bool carried_sum = (u[i] & (kUpdValid | kUpdRestart | kUpdFresh)) == kUpdValid;
+            z[i] = carried_sum ? reinterpret_cast<const uint4*>(carry.Z + (env0 + w + 4 * i) * 128)[lane] : zo;
+        }
+#pragma unroll
+        for (int i = 0; i < kAB / 4; ++i) {
+            if (!(u[i] & kUpdValid)) continue;                      // warp-uniform
+            const int64_t e = env0 + w + 4 * i;
+            if (!(u[i] & kUpdRestart)) {
+                const int from = (int)(u[i] & 127u), to = (int)((u[i] >> 7) & 127u), code = (int)((u[i] >> 14) & 15u), cap = (int)((u[i] >> 18) & 15u);
                 const uint4 r0 = W[(size_t)(from * 14 + code - 1) * 32], r1 = W[(size_t)(to * 14 + code - 1) * 32];
                 const uint4 r2 = W[(size_t)(cap ? to * 14 + cap - 1 : XQ_STATE_SIZE) * 32];      // row 1260 = zeros
-                z = make_uint4(base.x - r0.x + r1.x - r2.x, base.y - r0.y + r1.y - r2.y, base.z - r0.z + r1.z - r2.z, base.w - r0.w + r1.w - r2.w);
+                z[i] = make_uint4(z[i].x - r0.x + r1.x - r2.x, z[i].y - r0.y + r1.y - r2.y, z[i].z - r0.z + r1.z - r2.z, z[i].w - r0.w + r1.w - r2.w);
             }
-            reinterpret_cast<uint4*>(carry.Z + e * 128)[lane] = z;
-            act_emit_h(z, is, carry.Hhi, carry.Hlo, e, lane);
+            reinterpret_cast<uint4*>(carry.Z + e * 128)[lane] = z[i];
+            act_emit_h(z[i], is, carry.Hhi, carry.Hlo, e, lane);
         }
     }
 }
