@@ -1130,6 +1130,8 @@ __global__ void __launch_bounds__(256) grad_exchange_apply_kernel(PeerPtrs peers
                                                                  float* __restrict__ b1, __nv_bfloat16* __restrict__ W1bf,
                                                                  __nv_bfloat16* __restrict__ W1lo, float lr) {
     uint32_t* my_flags = reinterpret_cast<uint32_t*>(peers.p[rank] + kExchFlagsOff);
+    tc::pdl_wait();                                            // launched under the tail of the gradient contraction (programmatic dependent launch)
+    tc::pdl_launch_dependents();                               // the next update's layer-0 kernel waits for this grid's completion before it reads W0T
     if (blockIdx.x == 0 && (int)threadIdx.x < world) {         // 1. my gradient (written by the previous kernel of this stream) is complete
         __threadfence_system();
         uint32_t* f = reinterpret_cast<uint32_t*>(peers.p[threadIdx.x] + kExchFlagsOff) + rank;
@@ -1661,9 +1663,8 @@ int dqn_exchange_apply(xq_dqn_s* h, double lr) {
     PeerPtrs pp;
     for (int r = 0; r < kMaxRanks; ++r) pp.p[r] = f->peer[r];
     ++f->epoch;
-    grad_exchange_apply_kernel<<<blocks(kGradPad / 4, 256), 256, 0, h->stream>>>(pp, f->rank, f->world, f->parity, f->epoch, f->W0T, f->b0, f->W1, f->b1,
-                                                                                f->W1bf, f->W1lo, (float)lr);
-    XQ_LAUNCH_CHECK();
+    XQ_CUDA(launch_pdl(grad_exchange_apply_kernel, dim3(blocks(kGradPad / 4, 256)), dim3(256), 0, h->stream, 1, pp, f->rank, f->world, f->parity, f->epoch, f->W0T,
+                       f->b0, f->W1, f->b1, f->W1bf, f->W1lo, (float)lr));
     f->parity ^= 1;
     h->f64_current = false; ++f->w_version;
     return XQ_OK;
