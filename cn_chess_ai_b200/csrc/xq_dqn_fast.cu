@@ -802,6 +802,22 @@ __global__ void __launch_bounds__(256) td_delta_kernel(uint32_t* __restrict__ cb
     }
 }
 
+// ---- multi-GPU exchange buffer (one per rank, IPC-mapped by every peer; see grad_exchange_apply_kernel) ----
+// [2 parities][kMaxRanks source ranks][kGradPad] FP32: slot (parity, r) of rank q's buffer is WRITTEN BY RANK r (its gradient contraction pushes
+// the finished rows over NVLink) and read by rank q only | flags[kMaxRanks] u32: epoch of the last complete gradient of each source rank |
+// status u32 | completion counter of the local contraction u32
+constexpr int kMaxRanks = 16;
+constexpr int kGradPad = (kGradSize + 3) / 4 * 4;
+constexpr size_t kExchFlagsOff = sizeof(float) * 2 * (size_t)kMaxRanks * kGradPad;                 // 16-byte aligned
+constexpr size_t kExchBytes = kExchFlagsOff + sizeof(uint32_t) * (kMaxRanks + 4);
+__host__ __device__ constexpr size_t exch_slot_floats(int parity, int src_rank) { return ((size_t)parity * kMaxRanks + (size_t)src_rank) * kGradPad; }
+struct PeerPtrs { uint8_t* p[kMaxRanks]; };
+struct DwPush {               // world == 0: the gradient stays local (grad)
+    PeerPtrs peers;
+    int rank = 0, world = 0, parity = 0;
+    uint32_t epoch = 0;
+};
+
 // ---------------------------------------------------------------------------------------------
 // dW0^T = X^T . delta0 on tcgen05: C[feature 0..1279][hidden 0..127] = sum_b onehot_b[feature] * delta0_b[hidden].
 // (updateWeightsBiasesKernel for layer 0, src/dqn.cu:310-319, summed over the batch.)  Feature 1260 is a constant
@@ -840,7 +856,7 @@ __global__ void __launch_bounds__(kDwThreads, 1) dw_gemm_kernel(const __grid_con
                                                                float* __restrict__ grad,
                                                                float* __restrict__ W0T, float* __restrict__ b0, float* __restrict__ W1,
                                                                float* __restrict__ b1, __nv_bfloat16* __restrict__ W1bf,
-                                                               __nv_bfloat16* __restrict__ W1lo, float lr, int apply) {
+                                                               __nv_bfloat16* __restrict__ W1lo, float lr, int apply, const DwPush push) {
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
     uint8_t* sA = smem;                                        // [stage][128 features][64 samples]
@@ -1055,7 +1071,15 @@ __global__ void __launch_bounds__(kDwThreads, 1) dw_gemm_kernel(const __grid_con
 #pragma unroll
     for (int u = 0; u < 2; ++u) {
         if (e[u] < 0) continue;
-        if (!apply) { *reinterpret_cast<float4*>(grad + e[u]) = acc[u]; continue; }
+        if (!apply) {
+            if (push.world > 0) {      // multi-GPU: the finished rows go straight into slot (parity, my rank) of EVERY rank's exchange buffer (posted NVLink stores)
+                const size_t off = sizeof(float) * (exch_slot_floats(push.parity, push.rank) + (size_t)e[u]);
+                for (int r = 0; r < push.world; ++r) *reinterpret_cast<float4*>(push.peers.p[r] + off) = acc[u];
+            } else {
+                *reinterpret_cast<float4*>(grad + e[u]) = acc[u];
+            }
+            continue;
+        }
         float* dst = e[u] < kGradB0 ? W0T + e[u] : (e[u] < kGradW1 ? b0 + (e[u] - kGradB0) : W1 + (e[u] - kGradW1));
         float4 w = wold[u];
         w.x -= lr * acc[u].x; w.y -= lr * acc[u].y; w.z -= lr * acc[u].z; w.w -= lr * acc[u].w;
@@ -1075,7 +1099,12 @@ __global__ void __launch_bounds__(kDwThreads, 1) dw_gemm_kernel(const __grid_con
             float g = 0.0f;
 #pragma unroll
             for (int p = 0; p < kDwSplits; ++p) g += __ldcg(dbpart + p * BM + threadIdx.x);
-            grad[kGradB1 + threadIdx.x] = g;
+            if (!apply && push.world > 0) {
+                const size_t off = sizeof(float) * (exch_slot_floats(push.parity, push.rank) + (size_t)(kGradB1 + threadIdx.x));
+                for (int r = 0; r < push.world; ++r) *reinterpret_cast<float*>(push.peers.p[r] + off) = g;
+            } else {
+                grad[kGradB1 + threadIdx.x] = g;
+            }
             if (apply) b1[threadIdx.x] -= lr * g;
         } else if (threadIdx.x >= 128 && threadIdx.x < 131) {   // loss statistics: fold the slots td_delta_kernel accumulated into
             float a = 0.0f;
@@ -1084,6 +1113,27 @@ __global__ void __launch_bounds__(kDwThreads, 1) dw_gemm_kernel(const __grid_con
         }
     }
     if (threadIdx.x == 32) XQ_TL(1, 37);
+    if (!apply && push.world > 0) {
+        // "gradient `epoch` of this rank has landed everywhere": every CTA fences its stores at system scope and counts itself; the last one
+        // raises this rank's flag in every rank's buffer (release, system scope) -- grad_exchange_apply_kernel spins on those flags locally
+        __shared__ int s_last;
+        __threadfence_system();
+        __syncthreads();
+        unsigned* counter = reinterpret_cast<unsigned*>(push.peers.p[push.rank] + kExchFlagsOff) + kMaxRanks + 1;
+        if (threadIdx.x == 0) {
+            const unsigned prev = atomicAdd(counter, 1u);
+            s_last = prev == gridDim.x * gridDim.y - 1u;
+        }
+        __syncthreads();
+        if (s_last) {
+            __threadfence_system();
+            if ((int)threadIdx.x < push.world) {
+                uint32_t* f = reinterpret_cast<uint32_t*>(push.peers.p[threadIdx.x] + kExchFlagsOff) + push.rank;
+                asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(f), "r"(push.epoch) : "memory");
+            }
+            if (threadIdx.x == 0) *counter = 0u;
+        }
+    }
 }
 
 // SGD: W -= lr * grad on the compact gradient (src/dqn.cu:310-319), refresh the BF16 operand rows, clear the gradient
@@ -1105,20 +1155,15 @@ __global__ void __launch_bounds__(256) apply_kernel(float* __restrict__ W0T, flo
 }
 
 // ---------------------------------------------------------------------------------------------
-// Multi-GPU TD update, the ONE exchange step of the path, fused with the SGD step: every rank has written its compact
-// gradient into slot `parity` of its exchange buffer (IPC-mapped by all peers).  This kernel (same launch on every rank)
-//   1. signals "gradient `epoch` of rank r is complete" into EVERY rank's flag array (release, system scope, over NVLink),
-//   2. waits until all `world` flags in its OWN memory carry `epoch` (acquire, system scope; the spin is local),
-//   3. sums the `world` gradients in rank order straight out of peer memory (volatile 16-byte loads over NVLink / NVSwitch)
-//      -- the order is the same on every rank, so the replicas stay bit-identical -- and applies W -= lr * g.
-// Two gradient slots alternate: a rank can only reach the signal of epoch e+1 after its own kernel of epoch e has finished
-// reading, so when all flags of e+1 are in, slot (e+2)&1 == e&1 is free to be rewritten.  No NCCL call, no separate apply.
-constexpr int kMaxRanks = 16;
-constexpr int kGradPad = (kGradSize + 3) / 4 * 4;
-constexpr size_t kExchFlagsOff = sizeof(float) * 2 * kGradPad;                 // 16-byte aligned
-constexpr size_t kExchBytes = kExchFlagsOff + sizeof(uint32_t) * (kMaxRanks + 4);
-struct PeerPtrs { uint8_t* p[kMaxRanks]; };
-
+// Multi-GPU TD update, the ONE exchange step of the path, fused on both sides: the gradient contraction (dw_gemm_kernel, apply = 0) PUSHES every
+// finished 16-row block of its compact gradient into slot (parity, its rank) of EVERY rank's exchange buffer -- posted stores over NVLink 5 /
+// NVSwitch while the other row tiles are still being reduced -- and its last CTA raises "gradient `epoch` of rank r has landed" in every
+// rank's flag array (fence + release at system scope).  This kernel (same launch on every rank, programmatic dependent launch)
+//   1. waits until all `world` flags in its OWN memory carry `epoch` (acquire, system scope; the spin and everything after it is local),
+//   2. sums the `world` slots in rank order -- the same order on every rank, so the replicas stay bit-identical -- and applies W -= lr * g.
+// Two parities alternate: a rank can only push epoch e+1 after its own kernel of epoch e has finished, i.e. after every rank's flag of epoch e
+// was in, i.e. after every rank's kernel of epoch e-1 had finished reading slot parity (e-1)&1 == (e+1)&1.  No NCCL call, no remote loads,
+// no separate apply.
 __device__ __forceinline__ float4 ld_peer_f4(const float* p) {
     float4 v;
     asm volatile("ld.volatile.global.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "l"(p) : "memory");
@@ -1132,11 +1177,6 @@ __global__ void __launch_bounds__(256) grad_exchange_apply_kernel(PeerPtrs peers
     uint32_t* my_flags = reinterpret_cast<uint32_t*>(peers.p[rank] + kExchFlagsOff);
     tc::pdl_wait();                                            // launched under the tail of the gradient contraction (programmatic dependent launch)
     tc::pdl_launch_dependents();                               // the next update's layer-0 kernel waits for this grid's completion before it reads W0T
-    if (blockIdx.x == 0 && (int)threadIdx.x < world) {         // 1. my gradient (written by the previous kernel of this stream) is complete
-        __threadfence_system();
-        uint32_t* f = reinterpret_cast<uint32_t*>(peers.p[threadIdx.x] + kExchFlagsOff) + rank;
-        asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(f), "r"(epoch) : "memory");
-    }
     if ((int)threadIdx.x < world) {                            // 2. all gradients of this epoch are complete
         const long long t0 = clock64();
         uint32_t v;
@@ -1149,10 +1189,9 @@ __global__ void __launch_bounds__(256) grad_exchange_apply_kernel(PeerPtrs peers
     __syncthreads();
     const int i = blockIdx.x * blockDim.x + threadIdx.x;       // 3. float4 index over the compact gradient
     if (i >= kGradPad / 4) return;
-    const size_t off = sizeof(float) * ((size_t)parity * kGradPad + 4 * (size_t)i);
     float4 g = make_float4(0.f, 0.f, 0.f, 0.f);
-    for (int r = 0; r < world; ++r) {
-        const float4 v = ld_peer_f4(reinterpret_cast<const float*>(peers.p[r] + off));
+    for (int r = 0; r < world; ++r) {                          // slot (parity, r) of MY buffer: pushed by rank r's contraction
+        const float4 v = ld_peer_f4(reinterpret_cast<const float*>(peers.p[rank]) + exch_slot_floats(parity, r) + 4 * (size_t)i);
         g.x += v.x; g.y += v.y; g.z += v.z; g.w += v.w;
     }
     const float gv[4] = {g.x, g.y, g.z, g.w};
@@ -1252,7 +1291,19 @@ static cudaError_t launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, s
 }
 
 // where the compact gradient of the current update goes: the rank's exchange slot once xq_dqn_dist_connect has run
-static inline float* cur_grad(Fast* f) { return f->connected ? reinterpret_cast<float*>(f->exch) + (size_t)f->parity * kGradPad : f->grad; }
+static inline float* cur_grad(Fast* f) { return f->connected ? reinterpret_cast<float*>(f->exch) + exch_slot_floats(f->parity, f->rank) : f->grad; }
+// multi-GPU: the contraction of an update whose SGD step is left to the exchange pushes its gradient to every rank (epoch = the one
+// the following grad_exchange_apply_kernel waits for)
+static inline DwPush dw_push(Fast* f, bool apply) {
+    DwPush p;
+    if (!apply && f->connected) {
+        for (int r = 0; r < kMaxRanks; ++r) p.peers.p[r] = f->peer[r];
+        p.rank = f->rank; p.world = f->world; p.parity = f->parity; p.epoch = f->epoch + 1;
+    } else {
+        for (int r = 0; r < kMaxRanks; ++r) p.peers.p[r] = nullptr;
+    }
+    return p;
+}
 
 static inline unsigned blocks(int64_t n, int per) { return (unsigned)((n + per - 1) / per); }
 
@@ -1496,7 +1547,7 @@ int td_update_core(xq_dqn_s* h, const BatchRef& ref, int64_t n, int use_target_n
     // 4. dW0 / db0 / dW1 / db1 contraction, cluster reduction and the SGD step (or the compact gradient)
     XQ_CUDA(launch_pdl(dw_gemm_kernel, dim3(kDwMTiles, kDwSplits), dim3(kDwThreads), kDwSmem, h->stream, kDwSplits, f->tmD0hi, f->tmD0lo, f->tmGhi,
                        f->tmGlo, f->tmCb, (int)n, f->part, f->dbpart, f->info_slots, f->info, cur_grad(f), f->W0T, f->b0, f->W1, f->b1, f->W1bf,
-                       f->W1lo, (float)lr, apply ? 1 : 0));
+                       f->W1lo, (float)lr, apply ? 1 : 0, dw_push(f, apply != 0)));
     if (apply) { h->f64_current = false; ++f->w_version; }
     return XQ_OK;
 }
@@ -1561,7 +1612,7 @@ int dqn_td_update_pipelined(xq_dqn_s* h, const void* ring, int64_t size, uint64_
                            ld, kParts, (float)h->gamma, h->mode, f->d0hi, f->d0lo, f->ghi, f->glo, ld, f->info_slots));
         XQ_CUDA(launch_pdl(dw_gemm_kernel, dim3(kDwMTiles, kDwSplits), dim3(kDwThreads), kDwSmem, main, kDwSplits, f->tmD0hi, f->tmD0lo, f->tmGhi,
                            f->tmGlo, f->tmCb, (int)n, f->part, f->dbpart, f->info_slots, f->info, cur_grad(f), f->W0T, f->b0, f->W1, f->b1, f->W1bf,
-                           f->W1lo, (float)lr, f->connected ? 0 : 1));
+                           f->W1lo, (float)lr, f->connected ? 0 : 1, dw_push(f, !f->connected)));
         if (f->connected) if (int rc = dqn_exchange_apply(h, lr)) return rc;      // multi-GPU: sum the ranks' gradients over peer memory + SGD, one kernel
         XQ_CUDA(cudaEventRecord(f->ev_free[slot], main));
         if (i + 1 < n_updates) if (int rc = aux_gemm(i + 1)) return rc;
