@@ -127,6 +127,46 @@ def test_acting_q_is_a_pure_function_of_board_and_weights(xq, O, oracle_lib, w0_
     assert finished > n          # resets happened (move cap at ply 200 + general captures)
 
 
+def test_carried_sums_follow_every_weight_change(xq, O):
+    """The per-env layer-0 sums (and the fixed-point table they are built from) belong to ONE version of W0 / b0.  Every way the online
+    weights can change -- a TD update from the replay ring, the pipelined multi-update call, a host batch update, apply_grads after a
+    gradient-only update, set_params, load_model, an FP64 reference-semantics step -- must invalidate them: after each, the Q the collector
+    would act on equals, bit for bit, the Q of a second network that was just handed the same parameters (full gather, new table)."""
+    import tempfile, os
+    n = 500
+    w, b = rand_params(21)
+    net = xq.DQN(LAYERS, lr=1e-3); net.set_params(w, b)
+    env = xq.BatchedEnv(n, seed=9)
+    rb = xq.ReplayBuffer(1 << 15)
+    probe = xq.DQN(LAYERS)
+
+    def check(tag):
+        xq.collect(net, env, rb, 3, 0.2)                     # carried plies under the current weights
+        _, q1 = xq.act(net, env, 0.0, want_q=True)
+        probe.set_params(*net.get_params())
+        _, q2 = xq.act(probe, env, 0.0, want_q=True)
+        assert np.array_equal(q1.view(np.uint32), q2.view(np.uint32)), tag
+
+    check("initial")
+    changes = {
+        "td_update_replay": lambda: xq.td_update_replay(net, rb, 512, 3, 0, True, 1e-2, apply=True),
+        "td_update_replay_n": lambda: xq.td_update_replay_n(net, rb, 512, 3, 10, 3, True, 1e-2),
+        "td_update (host batch)": lambda: net.td_update(rb.get(0, 256), lr=1e-2),
+        "gradient only + apply_grads": lambda: (xq.td_update_replay(net, rb, 512, 3, 50, True, 1e-2, apply=False), net.apply_grads(1e-2)),
+        "set_params": lambda: net.set_params(*rand_params(22)),
+        "fp64 backpropagate": lambda: net.backpropagate(np.eye(1, 1260, 7)[0], np.full(8100, 0.25), 0.05),
+    }
+    for tag, change in changes.items():
+        before = net.get_params()[0][:1260 * 128].copy()
+        change()
+        assert np.abs(net.get_params()[0][:1260 * 128] - before).max() > 0, tag      # W0 did change
+        check(tag)
+    with tempfile.TemporaryDirectory() as d:
+        other = xq.DQN(LAYERS); other.set_params(*rand_params(23)); other.save_model(os.path.join(d, "m.bin"))
+        net.load_model(os.path.join(d, "m.bin"))
+        check("load_model")
+
+
 @pytest.mark.parametrize("train_done", [True, False])
 def test_collect_fills_replay_like_the_train_loop(xq, O, oracle_lib, train_done):
     n, plies, seed, eps = 300, 230, 5, 0.1              # > 200 plies: crosses the move cap and the done-one-ply-early quirk
