@@ -88,7 +88,7 @@ struct Fast {
     float* zpart_b = nullptr;
     CUtensorMap tmH2_b;
     cudaStream_t aux = nullptr;
-    cudaEvent_t ev_fork = nullptr, ev_aux[2] = {nullptr, nullptr}, ev_free[2] = {nullptr, nullptr};
+    cudaEvent_t ev_fork = nullptr, ev_aux[2] = {nullptr, nullptr}, ev_free[2] = {nullptr, nullptr}, ev_td[2] = {nullptr, nullptr};
     // multi-GPU gradient exchange over peer memory (xq_dqn_dist_*): when connected, the compact gradient of an update is written
     // into slot `parity` of this rank's exchange buffer, which every peer maps through CUDA IPC
     uint8_t* exch = nullptr;                           // [2][kGradPad] FP32 gradient slots | flags[kMaxRanks] u32 | status u32
@@ -1423,12 +1423,12 @@ int dqn_fast_weights(xq_dqn_s* h, FastWeights* out) {
 void dqn_target_changed(xq_dqn_s* h) { if (h->fast) h->fast->target_current = false; }
 
 static int launch_gemm(xq_dqn_s* h, int mode, const CUtensorMap& tmA, const CUtensorMap& tmB, const float* b1, int64_t n, float* q,
-                       cudaStream_t stream = nullptr, float* zpart = nullptr) {
+                       cudaStream_t stream = nullptr, float* zpart = nullptr, int row_splits = 0) {
     Fast* f = h->fast;
     if (!stream) stream = h->stream;
     if (!zpart) zpart = f->zpart;
     const int m_tiles = (int)((n + BM - 1) / BM);
-    int n_splits = 148 / kNTiles;                  // 4 row splits x 37 column tiles = 148 CTAs
+    int n_splits = row_splits > 0 ? row_splits : 148 / kNTiles;      // default: 4 row splits x 37 column tiles = 148 CTAs
     if (n_splits > m_tiles) n_splits = m_tiles;
     const dim3 grid(kNTiles, n_splits);
     const int64_t zstride = (f->cap + BM - 1) / BM * BM;
@@ -1576,7 +1576,7 @@ int dqn_td_update_pipelined(xq_dqn_s* h, const void* ring, int64_t size, uint64_
         XQ_CUDA(cudaDeviceGetStreamPriorityRange(&lo, &hi));
         XQ_CUDA(cudaStreamCreateWithPriority(&f->aux, cudaStreamNonBlocking, lo));       // lowest priority: the online branch is the critical path
         XQ_CUDA(cudaEventCreateWithFlags(&f->ev_fork, cudaEventDisableTiming));
-        for (int i = 0; i < 2; ++i) { XQ_CUDA(cudaEventCreateWithFlags(&f->ev_aux[i], cudaEventDisableTiming)); XQ_CUDA(cudaEventCreateWithFlags(&f->ev_free[i], cudaEventDisableTiming)); }
+        for (int i = 0; i < 2; ++i) { XQ_CUDA(cudaEventCreateWithFlags(&f->ev_aux[i], cudaEventDisableTiming)); XQ_CUDA(cudaEventCreateWithFlags(&f->ev_free[i], cudaEventDisableTiming)); XQ_CUDA(cudaEventCreateWithFlags(&f->ev_td[i], cudaEventDisableTiming)); }
     }
     const int64_t ld = (f->cap + BM - 1) / BM * BM;
     cudaStream_t main = h->stream, aux = f->aux;
@@ -1592,10 +1592,18 @@ int dqn_td_update_pipelined(xq_dqn_s* h, const void* ring, int64_t size, uint64_
                            slot ? f->H2bf_b : f->H2bf, f->cb, ld, f->info_slots, 0, 2));
         return XQ_OK;
     };
+    // XQ_TD_EARLY_GEMM (default 1): the row-max GEMM of update i is released as soon as the TD-error kernel of update i-1 has run, i.e. while the
+    // gradient contraction of update i-1 -- whose 88 CTAs are already resident by then (programmatic dependent launch) and leave 60 SMs idle --
+    // is still working; cut into 5 row splits (185 shorter CTAs instead of 148) a good part of it is done on those 60 SMs before the contraction
+    // ends and the rest fits under update i's h(s) gather.  Measured (batch 4096, XQ_TD_GEMM_SPLITS sweep): 36.4 us per update with the
+    // release at "update i-1 complete" and 4 splits, 36.4 / 34.0 / 34.8 / 36.2 / 36.6 us with the early release and 4 / 5 / 6 / 7 / 10 splits.
+    static const int early = [] { const char* e = getenv("XQ_TD_EARLY_GEMM"); return e ? atoi(e) : 1; }();
+    static const int splits = [] { const char* e = getenv("XQ_TD_GEMM_SPLITS"); return e ? atoi(e) : 0; }();
     auto aux_gemm = [&](int i) -> int {
         const int slot = i & 1;
-        if (i >= 1) XQ_CUDA(cudaStreamWaitEvent(aux, f->ev_free[(i - 1) & 1], 0));      // update i-1 complete (so update i-2 has consumed this slot)
-        if (int rc = launch_gemm(h, EPI_ROWMAX, slot ? f->tmH2_b : f->tmH2, f->tmTW1, f->tb1, n, nullptr, aux, slot ? f->zpart_b : f->zpart)) return rc;
+        if (i >= 1) XQ_CUDA(cudaStreamWaitEvent(aux, early ? f->ev_td[(i - 1) & 1] : f->ev_free[(i - 1) & 1], 0));   // (update i-2 has consumed this slot either way)
+        if (int rc = launch_gemm(h, EPI_ROWMAX, slot ? f->tmH2_b : f->tmH2, f->tmTW1, f->tb1, n, nullptr, aux, slot ? f->zpart_b : f->zpart,
+                                 splits > 0 ? splits : (early ? 5 : 0))) return rc;
         XQ_CUDA(cudaEventRecord(f->ev_aux[slot], aux));
         return XQ_OK;
     };
@@ -1610,12 +1618,14 @@ int dqn_td_update_pipelined(xq_dqn_s* h, const void* ring, int64_t size, uint64_
         XQ_CUDA(cudaStreamWaitEvent(main, f->ev_aux[slot], 0));  // the row-max partials of this update
         XQ_CUDA(launch_pdl(td_delta_kernel, dim3(blocks(n * 32, 256)), dim3(256), 0, main, 1, f->cb, n, f->Hf, f->W1, f->b1, slot ? f->zpart_b : f->zpart,
                            ld, kParts, (float)h->gamma, h->mode, f->d0hi, f->d0lo, f->ghi, f->glo, ld, f->info_slots));
+        XQ_CUDA(cudaEventRecord(f->ev_td[slot], main));
+        if (early && i + 1 < n_updates) if (int rc = aux_gemm(i + 1)) return rc;
         XQ_CUDA(launch_pdl(dw_gemm_kernel, dim3(kDwMTiles, kDwSplits), dim3(kDwThreads), kDwSmem, main, kDwSplits, f->tmD0hi, f->tmD0lo, f->tmGhi,
                            f->tmGlo, f->tmCb, (int)n, f->part, f->dbpart, f->info_slots, f->info, cur_grad(f), f->W0T, f->b0, f->W1, f->b1, f->W1bf,
                            f->W1lo, (float)lr, f->connected ? 0 : 1, dw_push(f, !f->connected)));
         if (f->connected) if (int rc = dqn_exchange_apply(h, lr)) return rc;      // multi-GPU: sum the ranks' gradients over peer memory + SGD, one kernel
         XQ_CUDA(cudaEventRecord(f->ev_free[slot], main));
-        if (i + 1 < n_updates) if (int rc = aux_gemm(i + 1)) return rc;
+        if (!early && i + 1 < n_updates) if (int rc = aux_gemm(i + 1)) return rc;
     }
     h->f64_current = false; ++f->w_version;
     return XQ_OK;
