@@ -1592,12 +1592,18 @@ int dqn_td_update_pipelined(xq_dqn_s* h, const void* ring, int64_t size, uint64_
                            slot ? f->H2bf_b : f->H2bf, f->cb, ld, f->info_slots, 0, 2));
         return XQ_OK;
     };
-    // XQ_TD_EARLY_GEMM (default 1): the row-max GEMM of update i is released as soon as the TD-error kernel of update i-1 has run, i.e. while the
-    // gradient contraction of update i-1 -- whose 88 CTAs are already resident by then (programmatic dependent launch) and leave 60 SMs idle --
-    // is still working; cut into 5 row splits (185 shorter CTAs instead of 148) a good part of it is done on those 60 SMs before the contraction
-    // ends and the rest fits under update i's h(s) gather.  Measured (batch 4096, XQ_TD_GEMM_SPLITS sweep): 36.4 us per update with the
-    // release at "update i-1 complete" and 4 splits, 36.4 / 34.0 / 34.8 / 36.2 / 36.6 us with the early release and 4 / 5 / 6 / 7 / 10 splits.
-    static const int early = [] { const char* e = getenv("XQ_TD_EARLY_GEMM"); return e ? atoi(e) : 1; }();
+    // When the row-max GEMM of update i+1 is released (XQ_TD_EARLY_GEMM, default 2) and into how many row splits it is cut (XQ_TD_GEMM_SPLITS,
+    // default 5 = 185 CTAs instead of 4 = 148) decides whether it sits on the critical path of update i+1:
+    //   0  when update i is complete: it then runs next to update i+1's h(s) gather, 12 us against 7 us -- the TD-error kernel waits for it
+    //   1  when the TD-error kernel of update i has run: the gradient contraction's 88 CTAs are resident by then (programmatic dependent
+    //      launch) and leave 60 SMs idle, on which a good part of the GEMM is done before the contraction ends
+    //   2  when the row-max partials of update i are in, i.e. BEFORE the TD-error kernel of update i: the GEMM's CTAs start under the
+    //      TD-error kernel (small CTAs, they co-reside), the contraction's CTAs take the SMs as the main stream has the higher priority, and
+    //      the GEMM is (nearly) done when the contraction ends.  Slot reuse: the partials slot of update i+1 was last read by the TD-error
+    //      kernel of update i-1, which precedes the event in stream order.
+    // Measured per update at batch 4096: mode 0 / 4 splits 36.4 us; mode 1: 36.4 / 34.0 / 34.8 / 36.2 us with 4 / 5 / 6 / 7 splits;
+    // mode 2: 29.6 / 29.0 / 29.0 / 31.1 us with 4 / 5 / 6 / 8 splits; enqueued a whole update ahead (no event): 33.4 us.  Same results bit for bit.
+    static const int early = [] { const char* e = getenv("XQ_TD_EARLY_GEMM"); return e ? atoi(e) : 2; }();
     static const int splits = [] { const char* e = getenv("XQ_TD_GEMM_SPLITS"); return e ? atoi(e) : 0; }();
     auto aux_gemm = [&](int i) -> int {
         const int slot = i & 1;
@@ -1616,10 +1622,10 @@ int dqn_td_update_pipelined(xq_dqn_s* h, const void* ring, int64_t size, uint64_
         XQ_CUDA(launch_pdl(l0_pair_kernel, dim3(blocks(n, kL0Warps)), dim3(kL0Warps * 32), 0, main, 1, ref, n, f->W0T, f->b0, f->tW0T, f->tb0, f->Hf,
                            f->H2bf, f->cb, ld, f->info_slots, kInfoSlots * 4, 1));
         XQ_CUDA(cudaStreamWaitEvent(main, f->ev_aux[slot], 0));  // the row-max partials of this update
+        if (early == 2) { XQ_CUDA(cudaEventRecord(f->ev_td[slot], main)); if (i + 1 < n_updates) if (int rc = aux_gemm(i + 1)) return rc; }
         XQ_CUDA(launch_pdl(td_delta_kernel, dim3(blocks(n * 32, 256)), dim3(256), 0, main, 1, f->cb, n, f->Hf, f->W1, f->b1, slot ? f->zpart_b : f->zpart,
                            ld, kParts, (float)h->gamma, h->mode, f->d0hi, f->d0lo, f->ghi, f->glo, ld, f->info_slots));
-        XQ_CUDA(cudaEventRecord(f->ev_td[slot], main));
-        if (early && i + 1 < n_updates) if (int rc = aux_gemm(i + 1)) return rc;
+        if (early == 1) { XQ_CUDA(cudaEventRecord(f->ev_td[slot], main)); if (i + 1 < n_updates) if (int rc = aux_gemm(i + 1)) return rc; }
         XQ_CUDA(launch_pdl(dw_gemm_kernel, dim3(kDwMTiles, kDwSplits), dim3(kDwThreads), kDwSmem, main, kDwSplits, f->tmD0hi, f->tmD0lo, f->tmGhi,
                            f->tmGlo, f->tmCb, (int)n, f->part, f->dbpart, f->info_slots, f->info, cur_grad(f), f->W0T, f->b0, f->W1, f->b1, f->W1bf,
                            f->W1lo, (float)lr, f->connected ? 0 : 1, dw_push(f, !f->connected)));
