@@ -294,6 +294,7 @@ struct xq_env_s {
     bool maybe_nonstd = false;        // set once boards were injected (xq_env_set_boards)
     // finished-game events of the self-play collector (xq_env_enable_game_events)
     xq_game_event* d_events = nullptr; unsigned long long* d_event_count = nullptr; int64_t event_cap = 0; uint32_t event_ply = 0;
+    xq_game_event* h_events = nullptr; unsigned long long* h_event_count = nullptr; int64_t last_events = 0;      // pinned staging of the drain; size of the last drain
 };
 
 static inline unsigned grid_for(int64_t n, int per_block) { return (unsigned)((n + per_block - 1) / per_block); }
@@ -364,7 +365,7 @@ int xq_env_destroy(xq_env_t h) {
     if (!h) return XQ_OK;
     cudaSetDevice(h->device);
     cudaFree(h->d_envs); cudaFree(h->d_stats); cudaFree(h->d_actions); cudaFree(h->d_i32); cudaFree(h->d_lists);
-    cudaFree(h->d_trace); cudaFree(h->d_state); cudaFree(h->d_nonstd); cudaFree(h->d_events); cudaFree(h->d_event_count);
+    cudaFree(h->d_trace); cudaFree(h->d_state); cudaFree(h->d_nonstd); cudaFree(h->d_events); cudaFree(h->d_event_count); cudaFreeHost(h->h_events); cudaFreeHost(h->h_event_count);
     for (auto p : h->d_u8) cudaFree(p);
     if (h->own_stream && h->stream) cudaStreamDestroy(h->stream);
     delete h;
@@ -522,11 +523,16 @@ int xq_env_enable_game_events(xq_env_t h, int64_t capacity) {
     XQ_ENV_ENTER(h);
     if (capacity <= 0) return fail(XQ_ERR_INVALID, "xq_env_enable_game_events: capacity must be > 0");
     XQ_CUDA(cudaStreamSynchronize(h->stream));
-    cudaFree(h->d_events); cudaFree(h->d_event_count); h->d_events = nullptr; h->d_event_count = nullptr; h->event_cap = 0;
-    XQ_CUDA(cudaMalloc(&h->d_events, sizeof(xq_game_event) * capacity));
-    XQ_CUDA(cudaMalloc(&h->d_event_count, sizeof(unsigned long long)));
+    if (capacity != h->event_cap) {
+        cudaFree(h->d_events); cudaFree(h->d_event_count); cudaFreeHost(h->h_events); cudaFreeHost(h->h_event_count);
+        h->d_events = nullptr; h->d_event_count = nullptr; h->h_events = nullptr; h->h_event_count = nullptr; h->event_cap = 0;
+        XQ_CUDA(cudaMalloc(&h->d_events, sizeof(xq_game_event) * capacity));
+        XQ_CUDA(cudaMalloc(&h->d_event_count, sizeof(unsigned long long)));
+        XQ_CUDA(cudaHostAlloc(&h->h_events, sizeof(xq_game_event) * capacity, cudaHostAllocDefault));
+        XQ_CUDA(cudaHostAlloc(&h->h_event_count, sizeof(unsigned long long), cudaHostAllocDefault));
+    }
     XQ_CUDA(cudaMemset(h->d_event_count, 0, sizeof(unsigned long long)));
-    h->event_cap = capacity; h->event_ply = 0;
+    h->event_cap = capacity; h->event_ply = 0; h->last_events = 0;
     return XQ_OK;
 }
 
@@ -534,13 +540,21 @@ int xq_env_drain_game_events(xq_env_t h, xq_game_event* out_host, int64_t max_ev
     XQ_ENV_ENTER(h);
     if (!h->d_events) return fail(XQ_ERR_STATE, "xq_env_drain_game_events: call xq_env_enable_game_events first");
     if (!out_host || !n_out || max_events < h->event_cap) return fail(XQ_ERR_INVALID, "xq_env_drain_game_events: the output must hold the ring's capacity");
-    unsigned long long count = 0;
-    XQ_CUDA(cudaMemcpyAsync(&count, h->d_event_count, sizeof(count), cudaMemcpyDeviceToHost, h->stream));
-    XQ_CUDA(cudaStreamSynchronize(h->stream));
-    const int64_t n = (int64_t)count < h->event_cap ? (int64_t)count : h->event_cap;
-    if (n > 0) XQ_CUDA(cudaMemcpyAsync(out_host, h->d_events, sizeof(xq_game_event) * n, cudaMemcpyDeviceToHost, h->stream));
+    // one synchronisation in the common case: the counter and a prefix of the ring sized from the previous drain travel together into
+    // pinned staging memory; only a drain that turns out to be larger than the guess needs a second copy
+    const int64_t guess = std::min<int64_t>(h->event_cap, std::max<int64_t>(1024, 2 * h->last_events));
+    XQ_CUDA(cudaMemcpyAsync(h->h_event_count, h->d_event_count, sizeof(unsigned long long), cudaMemcpyDeviceToHost, h->stream));
+    XQ_CUDA(cudaMemcpyAsync(h->h_events, h->d_events, sizeof(xq_game_event) * guess, cudaMemcpyDeviceToHost, h->stream));
     XQ_CUDA(cudaMemsetAsync(h->d_event_count, 0, sizeof(unsigned long long), h->stream));
     XQ_CUDA(cudaStreamSynchronize(h->stream));
+    const unsigned long long count = *h->h_event_count;
+    const int64_t n = (int64_t)count < h->event_cap ? (int64_t)count : h->event_cap;
+    if (n > guess) {      // the ring keeps its contents until the next collector ply writes into it
+        XQ_CUDA(cudaMemcpyAsync(h->h_events + guess, h->d_events + guess, sizeof(xq_game_event) * (n - guess), cudaMemcpyDeviceToHost, h->stream));
+        XQ_CUDA(cudaStreamSynchronize(h->stream));
+    }
+    memcpy(out_host, h->h_events, sizeof(xq_game_event) * n);
+    h->last_events = n;
     // slots were claimed with an atomic counter: restore the order of the batched loop, (ply, env)
     std::sort(out_host, out_host + n, [](const xq_game_event& a, const xq_game_event& b) { return a.ply != b.ply ? a.ply < b.ply : a.env < b.env; });
     *n_out = n;
