@@ -809,13 +809,21 @@ __global__ void __launch_bounds__(256) td_delta_kernel(uint32_t* __restrict__ cb
 constexpr int kMaxRanks = 16;
 constexpr int kGradPad = (kGradSize + 3) / 4 * 4;
 constexpr size_t kExchFlagsOff = sizeof(float) * 2 * (size_t)kMaxRanks * kGradPad;                 // 16-byte aligned
-constexpr size_t kExchBytes = kExchFlagsOff + sizeof(uint32_t) * (kMaxRanks + 4);
+constexpr int kExchBlocks = 96;                                                                      // >= 11 row tiles x 8 splits of the gradient contraction
+constexpr size_t kExchBlockFlagsOff = kExchFlagsOff + sizeof(uint32_t) * (kMaxRanks + 4);           // [kMaxRanks source ranks][kExchBlocks] u32: epoch of the last landed row block
+constexpr size_t kExchBytes = kExchBlockFlagsOff + sizeof(uint32_t) * kMaxRanks * kExchBlocks;
 __host__ __device__ constexpr size_t exch_slot_floats(int parity, int src_rank) { return ((size_t)parity * kMaxRanks + (size_t)src_rank) * kGradPad; }
 struct PeerPtrs { uint8_t* p[kMaxRanks]; };
+__device__ __forceinline__ float4 ld_peer_f4(const float* p) {
+    float4 v;
+    asm volatile("ld.volatile.global.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "l"(p) : "memory");
+    return v;
+}
 struct DwPush {               // world == 0: the gradient stays local (grad)
     PeerPtrs peers;
     int rank = 0, world = 0, parity = 0;
     uint32_t epoch = 0;
+    int fused = 0;            // 1: the contraction itself waits for the peers' row blocks, sums them and applies the SGD step (no exchange kernel)
 };
 
 // ---------------------------------------------------------------------------------------------
@@ -917,7 +925,7 @@ __global__ void __launch_bounds__(kDwThreads, 1) dw_gemm_kernel(const __grid_con
             else if (f == kBiasFeat) e[u] = kGradB0 + chunk * 4;
         }
         wold[u] = make_float4(0.f, 0.f, 0.f, 0.f);
-        if (apply && e[u] >= 0)
+        if ((apply || push.fused) && e[u] >= 0)
             wold[u] = *reinterpret_cast<const float4*>(e[u] < kGradB0 ? W0T + e[u] : (e[u] < kGradW1 ? b0 + (e[u] - kGradB0) : W1 + (e[u] - kGradW1)));
     }
     const int bt = threadIdx.x - 128;
@@ -1068,10 +1076,67 @@ __global__ void __launch_bounds__(kDwThreads, 1) dw_gemm_kernel(const __grid_con
             }
         }
     }
+    if (push.fused) {
+        // ===== multi-GPU, ONE kernel: contraction -> exchange over peer memory -> SGD, row block by row block =====
+        // 1. push this CTA's 16 reduced rows (and db1, for the CTA that owns it) into slot (parity, my rank) of every rank's buffer
+        const size_t slot = exch_slot_floats(push.parity, push.rank);
+#pragma unroll
+        for (int u = 0; u < 2; ++u)
+            if (e[u] >= 0)
+                for (int r = 0; r < push.world; ++r) *reinterpret_cast<float4*>(push.peers.p[r] + sizeof(float) * (slot + (size_t)e[u])) = acc[u];
+        float db1 = 0.0f;
+        const bool owns_db1 = w1_tile && ks == 0 && threadIdx.x < kQRows;
+        if (owns_db1) {
+#pragma unroll
+            for (int p = 0; p < kDwSplits; ++p) db1 += __ldcg(dbpart + p * BM + threadIdx.x);
+            for (int r = 0; r < push.world; ++r) *reinterpret_cast<float*>(push.peers.p[r] + sizeof(float) * (slot + (size_t)(kGradB1 + threadIdx.x))) = db1;
+        }
+        // 2. "row block b of gradient `epoch` of this rank has landed": CTA barrier, then one release store at system scope per peer (the release is
+        //    cumulative over everything the barrier ordered before it -- the pattern of a semaphore release)
+        const int blk = mt * kDwSplits + ks;
+        __syncthreads();
+        if ((int)threadIdx.x < push.world) {
+            uint32_t* f = reinterpret_cast<uint32_t*>(push.peers.p[threadIdx.x] + kExchBlockFlagsOff) + push.rank * kExchBlocks + blk;
+            asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(f), "r"(push.epoch) : "memory");
+            // 3. the same row block of every rank has landed HERE (the spin is on local memory; every rank pushes before it waits, and
+            //    all 88 CTAs of a contraction are resident, so nobody waits for a CTA that cannot run)
+            const uint32_t* mine = reinterpret_cast<const uint32_t*>(push.peers.p[push.rank] + kExchBlockFlagsOff) + threadIdx.x * kExchBlocks + blk;
+            const long long t0 = clock64();
+            uint32_t v;
+            do {
+                asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(mine) : "memory");
+                if ((int32_t)(v - push.epoch) >= 0) break;
+                if (clock64() - t0 > (1ll << 32)) { reinterpret_cast<uint32_t*>(push.peers.p[push.rank] + kExchFlagsOff)[kMaxRanks] = 1u; break; }   // ~2 s: flag it, do not hang
+            } while (true);
+        }
+        __syncthreads();
+        // 4. sum the `world` copies in rank order (the same order on every rank: bit-identical replicas) and apply W -= lr * g
+        const float* base = reinterpret_cast<const float*>(push.peers.p[push.rank]);
+#pragma unroll
+        for (int u = 0; u < 2; ++u) {
+            if (e[u] < 0) continue;
+            float4 g = make_float4(0.f, 0.f, 0.f, 0.f);
+            for (int r = 0; r < push.world; ++r) {               // this rank's own rows are still in registers (same values as its slot)
+                const float4 v = r == push.rank ? acc[u] : ld_peer_f4(base + exch_slot_floats(push.parity, r) + (size_t)e[u]);
+                g.x += v.x; g.y += v.y; g.z += v.z; g.w += v.w;
+            }
+            acc[u] = g;
+        }
+        if (owns_db1) {
+            float g = 0.0f;
+            for (int r = 0; r < push.world; ++r) {
+                float v = db1;
+                if (r != push.rank) asm volatile("ld.volatile.global.f32 %0, [%1];" : "=f"(v) : "l"(base + exch_slot_floats(push.parity, r) + (size_t)(kGradB1 + threadIdx.x)) : "memory");
+                g += v;
+            }
+            b1[threadIdx.x] -= lr * g;
+        }
+    }
+    const bool do_apply = apply || push.fused;
 #pragma unroll
     for (int u = 0; u < 2; ++u) {
         if (e[u] < 0) continue;
-        if (!apply) {
+        if (!do_apply) {
             if (push.world > 0) {      // multi-GPU: the finished rows go straight into slot (parity, my rank) of EVERY rank's exchange buffer (posted NVLink stores)
                 const size_t off = sizeof(float) * (exch_slot_floats(push.parity, push.rank) + (size_t)e[u]);
                 for (int r = 0; r < push.world; ++r) *reinterpret_cast<float4*>(push.peers.p[r] + off) = acc[u];
@@ -1095,7 +1160,7 @@ __global__ void __launch_bounds__(kDwThreads, 1) dw_gemm_kernel(const __grid_con
         }
     }
     if (w1_tile && ks == 0) {
-        if (threadIdx.x < kQRows) {                             // db1: the 8 per-CTA sums in fixed order
+        if (threadIdx.x < kQRows && !push.fused) {              // db1: the 8 per-CTA sums in fixed order
             float g = 0.0f;
 #pragma unroll
             for (int p = 0; p < kDwSplits; ++p) g += __ldcg(dbpart + p * BM + threadIdx.x);
@@ -1113,7 +1178,7 @@ __global__ void __launch_bounds__(kDwThreads, 1) dw_gemm_kernel(const __grid_con
         }
     }
     if (threadIdx.x == 32) XQ_TL(1, 37);
-    if (!apply && push.world > 0) {
+    if (!apply && push.world > 0 && !push.fused) {
         // "gradient `epoch` of this rank has landed everywhere": every CTA fences its stores at system scope and counts itself; the last one
         // raises this rank's flag in every rank's buffer (release, system scope) -- grad_exchange_apply_kernel spins on those flags locally
         __shared__ int s_last;
@@ -1164,11 +1229,6 @@ __global__ void __launch_bounds__(256) apply_kernel(float* __restrict__ W0T, flo
 // Two parities alternate: a rank can only push epoch e+1 after its own kernel of epoch e has finished, i.e. after every rank's flag of epoch e
 // was in, i.e. after every rank's kernel of epoch e-1 had finished reading slot parity (e-1)&1 == (e+1)&1.  No NCCL call, no remote loads,
 // no separate apply.
-__device__ __forceinline__ float4 ld_peer_f4(const float* p) {
-    float4 v;
-    asm volatile("ld.volatile.global.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "l"(p) : "memory");
-    return v;
-}
 
 __global__ void __launch_bounds__(256) grad_exchange_apply_kernel(PeerPtrs peers, int rank, int world, int parity, uint32_t epoch,
                                                                  float* __restrict__ W0T, float* __restrict__ b0, float* __restrict__ W1,
@@ -1294,11 +1354,11 @@ static cudaError_t launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, s
 static inline float* cur_grad(Fast* f) { return f->connected ? reinterpret_cast<float*>(f->exch) + exch_slot_floats(f->parity, f->rank) : f->grad; }
 // multi-GPU: the contraction of an update whose SGD step is left to the exchange pushes its gradient to every rank (epoch = the one
 // the following grad_exchange_apply_kernel waits for)
-static inline DwPush dw_push(Fast* f, bool apply) {
+static inline DwPush dw_push(Fast* f, bool apply, bool fused = false) {
     DwPush p;
     if (!apply && f->connected) {
         for (int r = 0; r < kMaxRanks; ++r) p.peers.p[r] = f->peer[r];
-        p.rank = f->rank; p.world = f->world; p.parity = f->parity; p.epoch = f->epoch + 1;
+        p.rank = f->rank; p.world = f->world; p.parity = f->parity; p.epoch = f->epoch + 1; p.fused = fused ? 1 : 0;
     } else {
         for (int r = 0; r < kMaxRanks; ++r) p.peers.p[r] = nullptr;
     }
@@ -1605,6 +1665,7 @@ int dqn_td_update_pipelined(xq_dqn_s* h, const void* ring, int64_t size, uint64_
     // mode 2: 29.6 / 29.0 / 29.0 / 31.1 us with 4 / 5 / 6 / 8 splits; enqueued a whole update ahead (no event): 33.4 us.  Same results bit for bit.
     static const int early = [] { const char* e = getenv("XQ_TD_EARLY_GEMM"); return e ? atoi(e) : 2; }();
     static const int splits = [] { const char* e = getenv("XQ_TD_GEMM_SPLITS"); return e ? atoi(e) : 0; }();
+    static const bool fuse_exchange = [] { const char* e = getenv("XQ_DIST_FUSED_GEMM"); return !(e && atoi(e) == 0); }();   // 0: exchange in a kernel of its own (A/B runs)
     auto aux_gemm = [&](int i) -> int {
         const int slot = i & 1;
         if (i >= 1) XQ_CUDA(cudaStreamWaitEvent(aux, early ? f->ev_td[(i - 1) & 1] : f->ev_free[(i - 1) & 1], 0));   // (update i-2 has consumed this slot either way)
@@ -1628,8 +1689,11 @@ int dqn_td_update_pipelined(xq_dqn_s* h, const void* ring, int64_t size, uint64_
         if (early == 1) { XQ_CUDA(cudaEventRecord(f->ev_td[slot], main)); if (i + 1 < n_updates) if (int rc = aux_gemm(i + 1)) return rc; }
         XQ_CUDA(launch_pdl(dw_gemm_kernel, dim3(kDwMTiles, kDwSplits), dim3(kDwThreads), kDwSmem, main, kDwSplits, f->tmD0hi, f->tmD0lo, f->tmGhi,
                            f->tmGlo, f->tmCb, (int)n, f->part, f->dbpart, f->info_slots, f->info, cur_grad(f), f->W0T, f->b0, f->W1, f->b1, f->W1bf,
-                           f->W1lo, (float)lr, f->connected ? 0 : 1, dw_push(f, !f->connected)));
-        if (f->connected) if (int rc = dqn_exchange_apply(h, lr)) return rc;      // multi-GPU: sum the ranks' gradients over peer memory + SGD, one kernel
+                           f->W1lo, (float)lr, f->connected ? 0 : 1, dw_push(f, !f->connected, fuse_exchange)));
+        if (f->connected) {      // multi-GPU
+            if (fuse_exchange) { ++f->epoch; f->parity ^= 1; }                  // the contraction exchanged the gradient and applied the SGD step itself
+            else if (int rc = dqn_exchange_apply(h, lr)) return rc;              // two kernels: push + [wait, sum, SGD]
+        }
         XQ_CUDA(cudaEventRecord(f->ev_free[slot], main));
         if (!early && i + 1 < n_updates) if (int rc = aux_gemm(i + 1)) return rc;
     }
