@@ -12,7 +12,7 @@ def _td_traffic():
     return json.load(open(p)).get("td_update_dram_bytes_per_update") if os.path.exists(p) else None
 
 
-def bench_dqn(stream, peaks, world=1, local=0, dist=None, envs=65536, replay_cap=1 << 20, batch=4096, updates=30, warmup=5):
+def bench_dqn(stream, peaks, world=1, local=0, dist=None, envs=65536, replay_cap=1 << 20, batch=4096, updates=64, warmup=5):
     """BASELINE configs 3+4 on this rank: eps-greedy self-play with batched Q-net inference fills a 1M-transition
     replay ring, then batch-4096 TD updates (per GPU) are timed with CUDA events on `stream`.
     With world > 1 every update all-reduces the compact gradient over NCCL before the identical SGD step."""
