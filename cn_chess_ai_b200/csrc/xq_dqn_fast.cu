@@ -1634,7 +1634,9 @@ int dqn_td_update_pipelined(xq_dqn_s* h, const void* ring, int64_t size, uint64_
     if (!f->aux) {
         int lo = 0, hi = 0;
         XQ_CUDA(cudaDeviceGetStreamPriorityRange(&lo, &hi));
-        XQ_CUDA(cudaStreamCreateWithPriority(&f->aux, cudaStreamNonBlocking, lo));       // lowest priority: the online branch is the critical path
+        XQ_CUDA(cudaStreamCreateWithPriority(&f->aux, cudaStreamNonBlocking, lo));       // lowest priority = the priority of a default-created stream: measured best
+                                                                                          // when both branches have EQUAL priority (29.0 us per update; 34.4 with the
+                                                                                          // online branch on a higher-priority stream, 41 with the bootstrap branch higher)
         XQ_CUDA(cudaEventCreateWithFlags(&f->ev_fork, cudaEventDisableTiming));
         for (int i = 0; i < 2; ++i) { XQ_CUDA(cudaEventCreateWithFlags(&f->ev_aux[i], cudaEventDisableTiming)); XQ_CUDA(cudaEventCreateWithFlags(&f->ev_free[i], cudaEventDisableTiming)); XQ_CUDA(cudaEventCreateWithFlags(&f->ev_td[i], cudaEventDisableTiming)); }
     }
@@ -1658,7 +1660,7 @@ int dqn_td_update_pipelined(xq_dqn_s* h, const void* ring, int64_t size, uint64_
     //   1  when the TD-error kernel of update i has run: the gradient contraction's 88 CTAs are resident by then (programmatic dependent
     //      launch) and leave 60 SMs idle, on which a good part of the GEMM is done before the contraction ends
     //   2  when the row-max partials of update i are in, i.e. BEFORE the TD-error kernel of update i: the GEMM's CTAs start under the
-    //      TD-error kernel (small CTAs, they co-reside), the contraction's CTAs take the SMs as the main stream has the higher priority, and
+    //      TD-error kernel (small CTAs, they co-reside), the contraction's 88 CTAs take their SMs as they become free, and
     //      the GEMM is (nearly) done when the contraction ends.  Slot reuse: the partials slot of update i+1 was last read by the TD-error
     //      kernel of update i-1, which precedes the event in stream order.
     // Measured per update at batch 4096: mode 0 / 4 splits 36.4 us; mode 1: 36.4 / 34.0 / 34.8 / 36.2 us with 4 / 5 / 6 / 7 splits;
