@@ -62,12 +62,14 @@ def bench_dqn(stream, peaks, world=1, local=0, dist=None, envs=65536, replay_cap
         if dist is not None:
             dist.barrier()
         torch.cuda.synchronize()
+    calls = 3          # timed: `calls` x `updates` sequential updates
     a.record(stream)
-    if pipelined:      # one call = `updates` sequential updates (each with its gradient exchange when world > 1), the target-net branch of
-        td_update_replay_n(net, rb, batch, 1000 + local, warmup, updates, True, 1e-6)      # update i+1 under the online branch of update i
-    else:
-        for i in range(updates):
-            one(warmup + i)
+    for c in range(calls):
+        if pipelined:  # one call = `updates` sequential updates (each with its gradient exchange when world > 1), the target-net branch of
+            td_update_replay_n(net, rb, batch, 1000 + local, warmup + c * updates, updates, True, 1e-6)      # update i+1 under the online branch of update i
+        else:
+            for i in range(updates):
+                one(warmup + c * updates + i)
     b.record(stream)
     if dist is not None:
         dist.barrier()
@@ -79,7 +81,7 @@ def bench_dqn(stream, peaks, world=1, local=0, dist=None, envs=65536, replay_cap
     if dist is not None:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     ms, collect_ms = float(t[0]), float(t[1])
-    us = 1e3 * ms / updates
+    us = 1e3 * ms / (updates * calls)
     tflops = FLOP_PER_TRANSITION * batch / (us * 1e-6) / 1e12          # per GPU
     out = {"metric": "DQN TD updates/s (batch 4096 per GPU, target-net bootstrap, SGD applied)",
            "td_updates_per_s": 1e6 / us, "pipelined_over_two_streams": pipelined, "transitions_per_s": 1e6 / us * batch * world, "us_per_update": us, "batch_per_gpu": batch,
