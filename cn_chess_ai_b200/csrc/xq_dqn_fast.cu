@@ -162,7 +162,7 @@ __global__ void __launch_bounds__(256) l0_forward_kernel(const uint8_t* __restri
     if (Hf) reinterpret_cast<float4*>(Hf + s * kHid)[lane] = h;
     store_h_bf16(Hbf, s, lane, h);
 }
-// Acting: h(s) for every env of a shard, one warp per board, written as BF16 hi + lo (h = hi + lo to ~16 mantissa bits) for the
+// Acting: h(s) for every env of a shard (8 lanes per board), written as BF16 hi + lo (h = hi + lo to ~16 mantissa bits) for the
 // split-precision layer-1 contraction of q90_gemm_kernel.
 //
 // The pre-activation z0 = b0 + (sum of the <= 32 rows of W0^T a board selects, src/chessai.cpp:268-289) is kept PER ENV between plies

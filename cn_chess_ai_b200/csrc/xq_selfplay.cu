@@ -8,9 +8,10 @@
 //   done = checkGameOver() || moveCount+1 >= 200         (:119)
 // The reference then trains on that single transition at once; here it is appended to a replay ring in
 // HBM and consumed in batches by the tensor-core TD update (xq_dqn_fast.cu).
-// Q(s)[to] only needs outputs 0..89 of layer 1 (src/dqn.cpp:47 indexes by action.to), so acting costs a
-// <=32-row FP32 gather for layer 0 plus a [n x 128] x [128 x 96] split-precision tensor-core contraction
-// (dqn_q90_device in xq_dqn_fast.cu), then one thread per board picks the action.
+// Q(s)[to] only needs outputs 0..89 of layer 1 (src/dqn.cpp:47 indexes by action.to), so acting costs the
+// layer-0 sums -- carried from ply to ply in fixed point (xq_act_l0.cuh), 2-3 row updates per ply instead of a
+// <=32-row gather -- plus a [n x 128] x [128 x 96] split-precision tensor-core contraction (dqn_q90_device in
+// xq_dqn_fast.cu), then a team of 4 threads per board picks and applies the action (xq_act_team.cu).
 #include <stdlib.h>
 
 #include <algorithm>
