@@ -43,7 +43,7 @@ __global__ void __launch_bounds__(kAB * 4) act_team_kernel(xq_env_rec* __restric
                                                           uint16_t* __restrict__ actions_out, ActTransition* __restrict__ ring, int64_t ring_cap,
                                                           int64_t ring_pos, xq_env_stats* __restrict__ stats, xq_game_event* __restrict__ events,
                                                           unsigned long long* __restrict__ event_count, int64_t event_cap, uint32_t event_ply,
-                                                          uint8_t* __restrict__ nonstd, const ActCarry carry) {
+                                                          uint8_t* __restrict__ nonstd, const ActCarry carry, uint32_t event_env0) {
     __shared__ TeamShared<kAB> sh;
     __shared__ ActShared<kAB> as;
     __shared__ ActIo io;
@@ -171,7 +171,7 @@ __global__ void __launch_bounds__(kAB * 4) act_team_kernel(xq_env_rec* __restric
                     const int win = (gr == kDeadSq && gb == kDeadSq) ? NOCOLOR : (gr < gb ? RED : BLACK);
                     const unsigned long long slot = atomicAdd(event_count, 1ull);
                     if ((int64_t)slot < event_cap)
-                        events[slot] = xq_game_event{event_ply, (uint32_t)env, red_score, black_score, (uint16_t)move_count, (uint8_t)win, 2, 0u};
+                        events[slot] = xq_game_event{event_ply, event_env0 + (uint32_t)env, red_score, black_score, (uint16_t)move_count, (uint8_t)win, 2, 0u};
                 }
                 ctr++; a_games++;
                 restart = true;
@@ -210,7 +210,7 @@ __global__ void __launch_bounds__(kAB * 4) act_team_kernel(xq_env_rec* __restric
                     if (events) {   // gameCompleted(game, board->getRedScore(), board->getBlackScore()), chessai.cpp:161
                         const unsigned long long slot = atomicAdd(event_count, 1ull);
                         if ((int64_t)slot < event_cap)
-                            events[slot] = xq_game_event{event_ply, (uint32_t)env, red_score, black_score, (uint16_t)move_count, (uint8_t)win,
+                            events[slot] = xq_game_event{event_ply, event_env0 + (uint32_t)env, red_score, black_score, (uint16_t)move_count, (uint8_t)win,
                                                          (uint8_t)(took_general ? 0 : 1), 0u};
                     }
                 }
@@ -294,15 +294,15 @@ __global__ void __launch_bounds__(kAB * 4) act_team_kernel(xq_env_rec* __restric
 
 cudaError_t launch_act_team(bool apply, xq_env_rec* envs, int64_t n, uint64_t env_id0, uint64_t seed, const float* q90, uint32_t eps_thr, int train_done,
                             uint16_t* actions_out, void* ring, int64_t ring_cap, int64_t ring_pos, xq_env_stats* stats, xq_game_event* events,
-                            unsigned long long* event_count, int64_t event_cap, uint32_t event_ply, uint8_t* nonstd, const ActCarry* carry, cudaStream_t stream) {
+                            unsigned long long* event_count, int64_t event_cap, uint32_t event_ply, uint8_t* nonstd, const ActCarry* carry, uint32_t event_env0, cudaStream_t stream) {
     const ActCarry cy = carry ? *carry : ActCarry{};
     const unsigned grid = (unsigned)((n + kAB - 1) / kAB);
     if (apply)
         act_team_kernel<true><<<grid, kAB * 4, 0, stream>>>(envs, n, env_id0, seed, q90, eps_thr, train_done, actions_out, (ActTransition*)ring, ring_cap,
-                                                           ring_pos, stats, events, event_count, event_cap, event_ply, nonstd, cy);
+                                                           ring_pos, stats, events, event_count, event_cap, event_ply, nonstd, cy, event_env0);
     else
         act_team_kernel<false><<<grid, kAB * 4, 0, stream>>>(envs, n, env_id0, seed, q90, eps_thr, train_done, actions_out, (ActTransition*)ring, ring_cap,
-                                                            ring_pos, stats, events, event_count, event_cap, event_ply, nonstd, cy);
+                                                            ring_pos, stats, events, event_count, event_cap, event_ply, nonstd, cy, event_env0);
     ++g_launches;
     return cudaGetLastError();
 }

@@ -109,6 +109,8 @@ struct Fast {
     uint64_t w_version = 1, actq_version = 0, actz_version = 0;   // online W0 / b0 version; version W0Q / actZ were built from
     int act_slot = 0;
     int64_t act_carried_n = -1;
+    CUtensorMap tmActHiS[2], tmActLoS[2];              // the two halves of the collector's env range (two-stream plies)
+    int64_t act_sub_n = -1, act_sub_off = -1;
     CUtensorMap tmActHi, tmActLo, tmW1q, tmW1loq;
     int64_t tm_rows = 0;
 };
@@ -1553,6 +1555,32 @@ int dqn_q90_device(xq_dqn_s* h, const xq_env_rec* envs_dev, int64_t n, float* q9
     const int m_tiles = (int)((n + BM - 1) / BM);
     XQ_CUDA(launch_pdl(q90_gemm_kernel, dim3(m_tiles < 148 ? m_tiles : 148), dim3(kGemmThreads), kQSmem, stream, 1, f->tmActHi, f->tmActLo, f->tmW1q,
                        f->tmW1loq, (const float*)f->b1, (int)n, m_tiles, q90_dev));
+    return XQ_OK;
+}
+
+// One half [off, off + m) of the n envs of a collector call whose layer-0 sums are carried by the act kernel (dqn_q90_device has run for the
+// whole range in this call): only the contraction, on `stream`, with tensor maps over the half's rows of h(s)
+int dqn_q90_half(xq_dqn_s* h, int64_t n, int sub, int64_t off, int64_t m, float* q90_dev, cudaStream_t stream, ActCarry* carry) {
+    Fast* f = h->fast;
+    if (!f || n != f->act_rows || n != f->act_carried_n) return fail(XQ_ERR_STATE, "dqn_q90_half: the whole range has not been prepared");
+    const int64_t off1 = sub ? off : f->act_sub_off;
+    if (f->act_sub_n != n || (sub && f->act_sub_off != off)) {
+        if (!sub) return fail(XQ_ERR_STATE, "dqn_q90_half: half 1 defines the split");
+        const int64_t m0 = off, m1 = n - off;
+        if (int rc = make_tmap(&f->tmActHiS[0], f->actHhi, m0, BM)) return rc;
+        if (int rc = make_tmap(&f->tmActLoS[0], f->actHlo, m0, BM)) return rc;
+        if (int rc = make_tmap(&f->tmActHiS[1], f->actHhi + off * kHid, m1, BM)) return rc;
+        if (int rc = make_tmap(&f->tmActLoS[1], f->actHlo + off * kHid, m1, BM)) return rc;
+        f->act_sub_n = n; f->act_sub_off = off;
+    }
+    (void)off1;
+    if (carry) {
+        carry->W0Q = f->W0Q; carry->zOpen = f->zOpen; carry->inv_scale = reinterpret_cast<const float*>(f->actMax + 2);
+        carry->Z = f->actZ + off * kHid; carry->Prev = f->actPrev + off * 12; carry->Hhi = f->actHhi + off * kHid; carry->Hlo = f->actHlo + off * kHid;
+    }
+    const int m_tiles = (int)((m + BM - 1) / BM);
+    XQ_CUDA(launch_pdl(q90_gemm_kernel, dim3(m_tiles < 148 ? m_tiles : 148), dim3(kGemmThreads), kQSmem, stream, 1, f->tmActHiS[sub], f->tmActLoS[sub], f->tmW1q,
+                       f->tmW1loq, (const float*)f->b1, (int)m, m_tiles, q90_dev + off * QN));
     return XQ_OK;
 }
 

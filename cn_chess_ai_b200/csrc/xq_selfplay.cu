@@ -34,7 +34,7 @@ static_assert(sizeof(Transition) == sizeof(xq_transition), "transition layout");
 
 cudaError_t launch_act_team(bool apply, xq_env_rec* envs, int64_t n, uint64_t env_id0, uint64_t seed, const float* q90, uint32_t eps_thr, int train_done,
                             uint16_t* actions_out, void* ring, int64_t ring_cap, int64_t ring_pos, xq_env_stats* stats, xq_game_event* events,
-                            unsigned long long* event_count, int64_t event_cap, uint32_t event_ply, uint8_t* nonstd, const ActCarry* carry, cudaStream_t stream);
+                            unsigned long long* event_count, int64_t event_cap, uint32_t event_ply, uint8_t* nonstd, const ActCarry* carry, uint32_t event_env0, cudaStream_t stream);
 
 // Action selection (+ optional application), generic thread-per-board version (ordered list staged in shared memory): the fallback
 // of act_team_kernel (xq_act_team.cu) for boards with non-standard piece sets, or for every env with XQ_ACT_TEAM=0 (A/B runs).
@@ -172,7 +172,7 @@ struct xq_replay_s {
     cudaEvent_t ev = nullptr;
 };
 
-struct SelfplayScratch { float* q90 = nullptr; int64_t cap = 0; uint16_t* actions = nullptr; };
+struct SelfplayScratch { float* q90 = nullptr; int64_t cap = 0; uint16_t* actions = nullptr; cudaStream_t aux = nullptr; cudaEvent_t ev_fork = nullptr, ev_join = nullptr; };
 static SelfplayScratch& scratch_for(int device) { static SelfplayScratch s[64]; return s[device & 63]; }
 
 static inline unsigned blocks(int64_t n, int per) { return (unsigned)((n + per - 1) / per); }
@@ -201,10 +201,10 @@ static cudaEvent_t g_ev[64];
 // the generic thread-per-board kernel for the boards it flagged (only possible after xq_env_set_boards injected exotic positions).
 // XQ_ACT_TEAM=0 runs the generic kernel on every env (A/B runs); both give the same results.
 static int launch_act(bool apply, const EnvInfo& ei, const float* q90, uint32_t thr, int train_done, uint16_t* actions, Transition* ring, int64_t ring_cap,
-                      int64_t ring_pos, xq_env_stats* stats, uint32_t event_ply, const ActCarry* carry = nullptr) {
+                      int64_t ring_pos, xq_env_stats* stats, uint32_t event_ply, const ActCarry* carry = nullptr, uint32_t event_env0 = 0) {
     static const bool team = [] { const char* e = getenv("XQ_ACT_TEAM"); return !(e && atoi(e) == 0); }();
     if (team) XQ_CUDA(launch_act_team(apply, ei.d_envs, ei.n, ei.env_id0, ei.seed, q90, thr, train_done, actions, ring, ring_cap, ring_pos, stats,
-                                      ei.d_events, ei.d_event_count, ei.event_cap, event_ply, ei.d_nonstd, carry, ei.stream));
+                                      ei.d_events, ei.d_event_count, ei.event_cap, event_ply, ei.d_nonstd, carry, event_env0, ei.stream));
     if (!team || ei.maybe_nonstd) {
         const uint8_t* only = team ? ei.d_nonstd : nullptr;
         if (apply)
@@ -340,15 +340,42 @@ int xq_selfplay_collect(xq_dqn_t h, xq_env_t env, xq_replay_t r, int n_plies, do
     static const bool team = [] { const char* e = getenv("XQ_ACT_TEAM"); return !(e && atoi(e) == 0); }();
     static const bool carry_on = [] { const char* e = getenv("XQ_ACT_CARRY"); return !(e && atoi(e) == 0); }();
     const bool can_carry = team && carry_on && !ei.maybe_nonstd;
-    bool carried = false;
+    // Two-stream plies (XQ_COLLECT_STREAMS, default 2): once the sums are carried, the env range is cut in two halves that run their
+    // [contraction -> act] chains on two streams of equal priority, half a ply apart by themselves: the contraction of one half (tensor /
+    // HBM) and the tail of an act kernel (HBM) fill the SMs the other half's act kernel (instruction issue) leaves idle between its waves
+    static const int n_streams = [] { const char* e = getenv("XQ_COLLECT_STREAMS"); return e ? atoi(e) : 2; }();
+    const bool two = can_carry && n_streams == 2 && ei.n >= 16384;
+    const int64_t off = ((ei.n / 2 + 127) / 128) * 128;              // a multiple of the 128-env tiles of the contraction and of the 32-env act CTAs
+    if (two && !sc->aux) {
+        XQ_CUDA(cudaStreamCreateWithFlags(&sc->aux, cudaStreamNonBlocking));
+        XQ_CUDA(cudaEventCreateWithFlags(&sc->ev_fork, cudaEventDisableTiming));
+        XQ_CUDA(cudaEventCreateWithFlags(&sc->ev_join, cudaEventDisableTiming));
+    }
+    bool carried = false, forked = false;
     for (int p = 0; p < n_plies; ++p) {
-        ActCarry cy;
-        if (int rc = dqn_q90_device(h, ei.d_envs, ei.n, sc->q90, ei.stream, carried, &cy)) return rc;
-        if (int rc = launch_act(true, ei, sc->q90, thr, train_done, nullptr, r ? r->d_ring : nullptr, r ? r->capacity : 1, r ? r->total % r->capacity : 0,
-                                d_stats, ei.event_ply + (uint32_t)p, can_carry ? &cy : nullptr)) return rc;
-        carried = can_carry && cy.Z != nullptr;
+        const int64_t ring_pos = r ? r->total % r->capacity : 0;
+        if (two && carried) {
+            if (!forked) { XQ_CUDA(cudaEventRecord(sc->ev_fork, ei.stream)); XQ_CUDA(cudaStreamWaitEvent(sc->aux, sc->ev_fork, 0)); forked = true; }
+            for (int sub = 1; sub >= 0; --sub) {
+                EnvInfo eh = ei;
+                const int64_t o = sub ? off : 0, m = sub ? ei.n - off : off;
+                eh.d_envs = ei.d_envs + o; eh.n = m; eh.env_id0 = ei.env_id0 + (uint64_t)o; eh.d_nonstd = ei.d_nonstd ? ei.d_nonstd + o : nullptr;
+                eh.stream = sub ? sc->aux : ei.stream;
+                ActCarry cy;
+                if (int rc = dqn_q90_half(h, ei.n, sub, o, m, sc->q90, eh.stream, &cy)) return rc;
+                if (int rc = launch_act(true, eh, sc->q90 + o * kQPad, thr, train_done, nullptr, r ? r->d_ring : nullptr, r ? r->capacity : 1,
+                                        r ? (ring_pos + o) % r->capacity : 0, d_stats, ei.event_ply + (uint32_t)p, &cy, (uint32_t)o)) return rc;
+            }
+        } else {
+            ActCarry cy;
+            if (int rc = dqn_q90_device(h, ei.d_envs, ei.n, sc->q90, ei.stream, carried, &cy)) return rc;
+            if (int rc = launch_act(true, ei, sc->q90, thr, train_done, nullptr, r ? r->d_ring : nullptr, r ? r->capacity : 1, ring_pos,
+                                    d_stats, ei.event_ply + (uint32_t)p, can_carry ? &cy : nullptr)) return rc;
+            carried = can_carry && cy.Z != nullptr;
+        }
         if (r) r->total += ei.n;
     }
+    if (forked) { XQ_CUDA(cudaEventRecord(sc->ev_join, sc->aux)); XQ_CUDA(cudaStreamWaitEvent(ei.stream, sc->ev_join, 0)); }
     env_advance_event_ply(env, (uint32_t)n_plies);
     if (int rc = order_after(h->stream, ei.stream, &g_ev[h->device & 63])) return rc;    // later TD updates see the new transitions
     return XQ_OK;

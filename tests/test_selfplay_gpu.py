@@ -199,6 +199,41 @@ def test_collect_fills_replay_like_the_train_loop(xq, O, oracle_lib, train_done)
     assert stats["games"] >= n                              # every env finished at least one game
 
 
+def test_two_stream_collector_plies(xq, O, oracle_lib):
+    """At >= 16,384 envs the collector cuts the env range in two halves that run their [contraction -> act] chains on two streams
+    (xq_selfplay_collect).  Same transitions, same finished-game events (with the env index of the whole range) and same final boards as
+    the step-by-step path: GPU act (same Q, same draws) + oracle rules."""
+    from cn_chess_ai_b200.trainer import drain_game_events, enable_game_events
+    n, plies, seed, eps = 16500, 44, 17, 0.6            # not a multiple of 128: the second half ends in partial tiles / CTAs
+    w, b = rand_params(31)
+    net = xq.DQN(LAYERS); net.set_params(w, b)
+    envA = xq.BatchedEnv(n, seed=seed, env_id0=1000)
+    rb = xq.ReplayBuffer(n * plies)
+    enable_game_events(envA, n * plies)
+    xq.collect(net, envA, rb, plies, eps, train_done=True)
+    envA.sync()
+    events, dropped = drain_game_events(envA)
+    ring = rb.get(0, n * plies).reshape(plies, n)
+    envB = xq.BatchedEnv(n, seed=seed, env_id0=1000)
+    ref = O.new_envs(n)
+    finished = []
+    for p in range(plies):
+        actions = xq.act(net, envB, eps)
+        before = ref.copy()
+        r0 = np.zeros(n, np.int32); d0, w0, c0, v0 = (np.zeros(n, np.uint8) for _ in range(4))
+        oracle_lib.xqo_batch_step(ref.ctypes.data, n, actions, r0, d0, w0, c0, v0)
+        t = ring[p]
+        assert (t["action"] == actions).all() and (t["reward"] == r0).all(), p
+        assert t["s"].tobytes() == before["sq"].tobytes() and t["s2"].tobytes() == ref["sq"].tobytes(), p
+        for i in np.nonzero(d0)[0]:
+            finished.append((p, int(i), int(ref[i]["red_score"]), int(ref[i]["black_score"])))
+            oracle_lib.xqo_reset(ref[i:i + 1].ctypes.data)
+        envB.step(actions, auto_reset=True)
+    assert envA.get_boards().tobytes() == ref.tobytes()
+    assert dropped == 0 and len(finished) > 20
+    assert [(int(e["ply"]), int(e["env"]), int(e["red_score"]), int(e["black_score"])) for e in events] == finished
+
+
 def test_td_update_from_replay_matches_host_batch(xq, O):
     w, b = rand_params(8)
     net1 = xq.DQN(LAYERS); net1.set_params(w, b)
