@@ -17,6 +17,8 @@
 //   SGD       W -= lr * sum of per-sample gradients (B = 1 reproduces one reference step)     [apply_kernel]
 // FP32 master weights; BF16 only as MMA operands.  Tolerance vs the FP64 oracle: |dQ| <= 2e-3.
 #include <cuda.h>
+
+#include <algorithm>
 #include <math.h>
 #include <stdlib.h>
 #include <string.h>
@@ -109,8 +111,8 @@ struct Fast {
     uint64_t w_version = 1, actq_version = 0, actz_version = 0;   // online W0 / b0 version; version W0Q / actZ were built from
     int act_slot = 0;
     int64_t act_carried_n = -1;
-    CUtensorMap tmActHiS[2], tmActLoS[2];              // the two halves of the collector's env range (two-stream plies)
-    int64_t act_sub_n = -1, act_sub_off = -1;
+    CUtensorMap tmActHiS[4], tmActLoS[4];              // the parts of the collector's env range (multi-stream plies)
+    int64_t act_sub_n = -1; int act_sub_parts = 0;
     CUtensorMap tmActHi, tmActLo, tmW1q, tmW1loq;
     int64_t tm_rows = 0;
 };
@@ -1558,29 +1560,32 @@ int dqn_q90_device(xq_dqn_s* h, const xq_env_rec* envs_dev, int64_t n, float* q9
     return XQ_OK;
 }
 
-// One half [off, off + m) of the n envs of a collector call whose layer-0 sums are carried by the act kernel (dqn_q90_device has run for the
-// whole range in this call): only the contraction, on `stream`, with tensor maps over the half's rows of h(s)
-int dqn_q90_half(xq_dqn_s* h, int64_t n, int sub, int64_t off, int64_t m, float* q90_dev, cudaStream_t stream, ActCarry* carry) {
+// Part `part` of `n_parts` of the n envs of a collector call whose layer-0 sums are carried by the act kernel (dqn_q90_device has run for the
+// whole range in this call): only the contraction, on `stream`, with tensor maps over the part's rows of h(s).  Parts are equal multiples of
+// the 128-env tile (the last one takes the rest); *off / *m return the part's env range.
+int dqn_q90_part(xq_dqn_s* h, int64_t n, int n_parts, int part, float* q90_dev, cudaStream_t stream, ActCarry* carry, int64_t* off_out, int64_t* m_out) {
     Fast* f = h->fast;
-    if (!f || n != f->act_rows || n != f->act_carried_n) return fail(XQ_ERR_STATE, "dqn_q90_half: the whole range has not been prepared");
-    const int64_t off1 = sub ? off : f->act_sub_off;
-    if (f->act_sub_n != n || (sub && f->act_sub_off != off)) {
-        if (!sub) return fail(XQ_ERR_STATE, "dqn_q90_half: half 1 defines the split");
-        const int64_t m0 = off, m1 = n - off;
-        if (int rc = make_tmap(&f->tmActHiS[0], f->actHhi, m0, BM)) return rc;
-        if (int rc = make_tmap(&f->tmActLoS[0], f->actHlo, m0, BM)) return rc;
-        if (int rc = make_tmap(&f->tmActHiS[1], f->actHhi + off * kHid, m1, BM)) return rc;
-        if (int rc = make_tmap(&f->tmActLoS[1], f->actHlo + off * kHid, m1, BM)) return rc;
-        f->act_sub_n = n; f->act_sub_off = off;
+    if (!f || n != f->act_rows || n != f->act_carried_n) return fail(XQ_ERR_STATE, "dqn_q90_part: the whole range has not been prepared");
+    if (n_parts < 1 || n_parts > 4 || part < 0 || part >= n_parts) return fail(XQ_ERR_INVALID, "dqn_q90_part: bad part");
+    const int64_t size = ((n + n_parts - 1) / n_parts + BM - 1) / BM * BM;
+    if (size * (n_parts - 1) >= n) return fail(XQ_ERR_INVALID, "dqn_q90_part: too few envs for %d parts", n_parts);
+    if (f->act_sub_n != n || f->act_sub_parts != n_parts) {
+        for (int k = 0; k < n_parts; ++k) {
+            const int64_t o = k * size, m = std::min<int64_t>(size, n - o);
+            if (int rc = make_tmap(&f->tmActHiS[k], f->actHhi + o * kHid, m, BM)) return rc;
+            if (int rc = make_tmap(&f->tmActLoS[k], f->actHlo + o * kHid, m, BM)) return rc;
+        }
+        f->act_sub_n = n; f->act_sub_parts = n_parts;
     }
-    (void)off1;
+    const int64_t off = part * size, m = std::min<int64_t>(size, n - off);
     if (carry) {
         carry->W0Q = f->W0Q; carry->zOpen = f->zOpen; carry->inv_scale = reinterpret_cast<const float*>(f->actMax + 2);
         carry->Z = f->actZ + off * kHid; carry->Prev = f->actPrev + off * 12; carry->Hhi = f->actHhi + off * kHid; carry->Hlo = f->actHlo + off * kHid;
     }
     const int m_tiles = (int)((m + BM - 1) / BM);
-    XQ_CUDA(launch_pdl(q90_gemm_kernel, dim3(m_tiles < 148 ? m_tiles : 148), dim3(kGemmThreads), kQSmem, stream, 1, f->tmActHiS[sub], f->tmActLoS[sub], f->tmW1q,
+    XQ_CUDA(launch_pdl(q90_gemm_kernel, dim3(m_tiles < 148 ? m_tiles : 148), dim3(kGemmThreads), kQSmem, stream, 1, f->tmActHiS[part], f->tmActLoS[part], f->tmW1q,
                        f->tmW1loq, (const float*)f->b1, (int)m, m_tiles, q90_dev + off * QN));
+    *off_out = off; *m_out = m;
     return XQ_OK;
 }
 

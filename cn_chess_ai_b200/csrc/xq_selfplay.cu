@@ -172,7 +172,7 @@ struct xq_replay_s {
     cudaEvent_t ev = nullptr;
 };
 
-struct SelfplayScratch { float* q90 = nullptr; int64_t cap = 0; uint16_t* actions = nullptr; cudaStream_t aux = nullptr; cudaEvent_t ev_fork = nullptr, ev_join = nullptr; };
+struct SelfplayScratch { float* q90 = nullptr; int64_t cap = 0; uint16_t* actions = nullptr; cudaStream_t aux[3] = {nullptr, nullptr, nullptr}; cudaEvent_t ev_fork = nullptr, ev_join[3] = {nullptr, nullptr, nullptr}; };
 static SelfplayScratch& scratch_for(int device) { static SelfplayScratch s[64]; return s[device & 63]; }
 
 static inline unsigned blocks(int64_t n, int per) { return (unsigned)((n + per - 1) / per); }
@@ -340,29 +340,31 @@ int xq_selfplay_collect(xq_dqn_t h, xq_env_t env, xq_replay_t r, int n_plies, do
     static const bool team = [] { const char* e = getenv("XQ_ACT_TEAM"); return !(e && atoi(e) == 0); }();
     static const bool carry_on = [] { const char* e = getenv("XQ_ACT_CARRY"); return !(e && atoi(e) == 0); }();
     const bool can_carry = team && carry_on && !ei.maybe_nonstd;
-    // Two-stream plies (XQ_COLLECT_STREAMS, default 2): once the sums are carried, the env range is cut in two halves that run their
-    // [contraction -> act] chains on two streams of equal priority, half a ply apart by themselves: the contraction of one half (tensor /
-    // HBM) and the tail of an act kernel (HBM) fill the SMs the other half's act kernel (instruction issue) leaves idle between its waves
-    static const int n_streams = [] { const char* e = getenv("XQ_COLLECT_STREAMS"); return e ? atoi(e) : 2; }();
-    const bool two = can_carry && n_streams == 2 && ei.n >= 16384;
-    const int64_t off = ((ei.n / 2 + 127) / 128) * 128;              // a multiple of the 128-env tiles of the contraction and of the 32-env act CTAs
-    if (two && !sc->aux) {
-        XQ_CUDA(cudaStreamCreateWithFlags(&sc->aux, cudaStreamNonBlocking));
+    // Multi-stream plies (XQ_COLLECT_STREAMS, default 2): once the sums are carried, the env range is cut in equal parts that run their
+    // [contraction -> act] chains on streams of equal priority, out of step by themselves: the contraction of one part (tensor / HBM) and
+    // the tail of an act kernel (HBM) fill the SMs the other part's act kernel (instruction issue) leaves idle between its waves
+    static const int n_streams = [] { const char* e = getenv("XQ_COLLECT_STREAMS"); const int v = e ? atoi(e) : 2; return v < 1 ? 1 : (v > 4 ? 4 : v); }();
+    const bool multi = can_carry && n_streams > 1 && ei.n >= 4096 * n_streams;
+    if (multi && !sc->ev_fork) {
+        for (int k = 0; k < 3; ++k) { XQ_CUDA(cudaStreamCreateWithFlags(&sc->aux[k], cudaStreamNonBlocking)); XQ_CUDA(cudaEventCreateWithFlags(&sc->ev_join[k], cudaEventDisableTiming)); }
         XQ_CUDA(cudaEventCreateWithFlags(&sc->ev_fork, cudaEventDisableTiming));
-        XQ_CUDA(cudaEventCreateWithFlags(&sc->ev_join, cudaEventDisableTiming));
     }
     bool carried = false, forked = false;
     for (int p = 0; p < n_plies; ++p) {
         const int64_t ring_pos = r ? r->total % r->capacity : 0;
-        if (two && carried) {
-            if (!forked) { XQ_CUDA(cudaEventRecord(sc->ev_fork, ei.stream)); XQ_CUDA(cudaStreamWaitEvent(sc->aux, sc->ev_fork, 0)); forked = true; }
-            for (int sub = 1; sub >= 0; --sub) {
+        if (multi && carried) {
+            if (!forked) {
+                XQ_CUDA(cudaEventRecord(sc->ev_fork, ei.stream));
+                for (int k = 1; k < n_streams; ++k) XQ_CUDA(cudaStreamWaitEvent(sc->aux[k - 1], sc->ev_fork, 0));
+                forked = true;
+            }
+            for (int part = n_streams - 1; part >= 0; --part) {
                 EnvInfo eh = ei;
-                const int64_t o = sub ? off : 0, m = sub ? ei.n - off : off;
-                eh.d_envs = ei.d_envs + o; eh.n = m; eh.env_id0 = ei.env_id0 + (uint64_t)o; eh.d_nonstd = ei.d_nonstd ? ei.d_nonstd + o : nullptr;
-                eh.stream = sub ? sc->aux : ei.stream;
+                eh.stream = part ? sc->aux[part - 1] : ei.stream;
                 ActCarry cy;
-                if (int rc = dqn_q90_half(h, ei.n, sub, o, m, sc->q90, eh.stream, &cy)) return rc;
+                int64_t o = 0, m = 0;
+                if (int rc = dqn_q90_part(h, ei.n, n_streams, part, sc->q90, eh.stream, &cy, &o, &m)) return rc;
+                eh.d_envs = ei.d_envs + o; eh.n = m; eh.env_id0 = ei.env_id0 + (uint64_t)o; eh.d_nonstd = ei.d_nonstd ? ei.d_nonstd + o : nullptr;
                 if (int rc = launch_act(true, eh, sc->q90 + o * kQPad, thr, train_done, nullptr, r ? r->d_ring : nullptr, r ? r->capacity : 1,
                                         r ? (ring_pos + o) % r->capacity : 0, d_stats, ei.event_ply + (uint32_t)p, &cy, (uint32_t)o)) return rc;
             }
@@ -375,7 +377,8 @@ int xq_selfplay_collect(xq_dqn_t h, xq_env_t env, xq_replay_t r, int n_plies, do
         }
         if (r) r->total += ei.n;
     }
-    if (forked) { XQ_CUDA(cudaEventRecord(sc->ev_join, sc->aux)); XQ_CUDA(cudaStreamWaitEvent(ei.stream, sc->ev_join, 0)); }
+    if (forked)
+        for (int k = 1; k < n_streams; ++k) { XQ_CUDA(cudaEventRecord(sc->ev_join[k - 1], sc->aux[k - 1])); XQ_CUDA(cudaStreamWaitEvent(ei.stream, sc->ev_join[k - 1], 0)); }
     env_advance_event_ply(env, (uint32_t)n_plies);
     if (int rc = order_after(h->stream, ei.stream, &g_ev[h->device & 63])) return rc;    // later TD updates see the new transitions
     return XQ_OK;

@@ -200,7 +200,7 @@ def test_collect_fills_replay_like_the_train_loop(xq, O, oracle_lib, train_done)
 
 
 def test_two_stream_collector_plies(xq, O, oracle_lib):
-    """At >= 16,384 envs the collector cuts the env range in two halves that run their [contraction -> act] chains on two streams
+    """At >= 4,096 envs per stream the collector cuts the env range in parts that run their [contraction -> act] chains on 2..4 streams
     (xq_selfplay_collect).  Same transitions, same finished-game events (with the env index of the whole range) and same final boards as
     the step-by-step path: GPU act (same Q, same draws) + oracle rules."""
     from cn_chess_ai_b200.trainer import drain_game_events, enable_game_events
