@@ -263,3 +263,15 @@ def test_train_loop_vs_reference(O, oracle_lib, ref_lib, self_play, tmp_path, mo
     assert list(ev_ref) == events
     assert np.abs(w2 - w_ref).max() < 1e-12 and np.abs(b2 - b_ref).max() < 1e-12
     assert np.abs(w2 - w).max() > 1e-6                                        # the weights did move
+
+
+def test_reference_train_bench_leg(ref_lib):
+    """bench.py's `reference_train` leg: the reference's own ChessAI::train timed for one game (CPU definition of its network without a GPU)"""
+    import json
+    import os
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    r = subprocess.run([sys.executable, "-m", "oracle.ref_train_bench", "1"], cwd=root, capture_output=True, text=True, timeout=600)
+    out = json.loads(r.stdout.strip().splitlines()[-1])
+    assert r.returncode == 0 and out.get("plies", 0) > 0 and out["transitions_per_s"] > 0 and out["batch"] == 1, (out, r.stderr[-500:])
