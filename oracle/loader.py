@@ -29,6 +29,10 @@ def build(force=False):
         targets.append("ref")
     args = ["make", "-C", HERE] + (["-B"] if force else []) + targets
     subprocess.run(args, check=True, stdout=subprocess.DEVNULL)
+    if os.path.isdir(REF_SRC) and os.path.exists("/usr/local/cuda/bin/nvcc"):
+        # the reference's own CUDA network (src/dqn.cu unmodified, sm_100a): golden generation on a GPU box and bench.py's reference_train leg;
+        # optional -- without it that leg times the CPU definition of the network
+        subprocess.run(["make", "-C", HERE] + (["-B"] if force else []) + ["refcuda"], check=False, stdout=subprocess.DEVNULL, stderr=subprocess.DEVNULL)
 
 
 _P = C.c_void_p
