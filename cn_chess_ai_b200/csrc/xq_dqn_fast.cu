@@ -24,6 +24,7 @@
 #include <string.h>
 
 #include "xq_act_l0.cuh"
+#include "xq_act_quant.cuh"
 #include "xq_dqn_internal.cuh"
 #include "xq_tc.cuh"
 
@@ -187,21 +188,14 @@ __global__ void __launch_bounds__(256) act_quant_max_kernel(const float* __restr
     for (int o = 16; o > 0; o >>= 1) m = max(m, __shfl_xor_sync(0xFFFFFFFFu, m, o));
     if ((threadIdx.x & 31) == 0 && m) atomicMax(slot, m);
 }
-__device__ __forceinline__ int act_quant_shift(uint32_t max_bits) {
-    int e = 0;
-    const float top = 92.0f * __uint_as_float(max_bits);      // 90 squares + bias + slack
-    if (top > 0.0f && top < INFINITY) frexpf(top, &e); else e = top > 0.0f || top != top ? 120 : -60;     // top < 2^e
-    return min(max(30 - e, -90), 90);                          // |sum| * 2^k < 2^30
-}
 __global__ void __launch_bounds__(256) act_quant_kernel(const float* __restrict__ W0T, const float* __restrict__ b0, const uint32_t* __restrict__ slot,
                                                        uint32_t* __restrict__ next_slot, int32_t* __restrict__ W0Q, int32_t* __restrict__ b0Q,
                                                        float* __restrict__ inv_scale) {
     const int k = act_quant_shift(*slot);
-    const float scale = ldexpf(1.0f, k);
     for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < (kIn + 1) * kHid + kHid; i += gridDim.x * blockDim.x) {
-        if (i < kIn * kHid) W0Q[i] = __float2int_rn(W0T[i] * scale);
+        if (i < kIn * kHid) W0Q[i] = act_quantize(W0T[i], k);
         else if (i < (kIn + 1) * kHid) W0Q[i] = 0;                                     // row kIn = zeros: the padding row of the lists
-        else b0Q[i - (kIn + 1) * kHid] = __float2int_rn(b0[i - (kIn + 1) * kHid] * scale);
+        else b0Q[i - (kIn + 1) * kHid] = act_quantize(b0[i - (kIn + 1) * kHid], k);
     }
     if (blockIdx.x == 0 && threadIdx.x == 0) { *inv_scale = ldexpf(1.0f, -k); *next_slot = 0u; }     // the other slot serves the next weight version
 }

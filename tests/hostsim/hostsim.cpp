@@ -224,3 +224,13 @@ int hs_reward(int material_diff, int move_count) { return xq::reward_from_materi
 int hs_piece_score(int type) { return xq::piece_score(type); }
 uint64_t hs_rng(uint64_t seed, uint64_t env, uint32_t ctr) { return xq::rng(seed, env, ctr); }
 }
+
+// ---- the scale and the entries of the acting path's fixed-point layer-0 table (xq_act_quant.cuh) ----
+#include "../../cn_chess_ai_b200/csrc/xq_act_quant.cuh"
+extern "C" int hs_act_quant(const float* w, long n, int32_t* q_out) {
+    uint32_t m = 0;
+    for (long i = 0; i < n; ++i) { uint32_t b; std::memcpy(&b, &w[i], 4); b &= 0x7FFFFFFFu; if (b > m) m = b; }      // act_quant_max_kernel
+    const int k = xq::act_quant_shift(m);
+    for (long i = 0; i < n; ++i) q_out[i] = xq::act_quantize(w[i], k);                                             // act_quant_kernel
+    return k;
+}

@@ -159,3 +159,39 @@ def test_team_phases_under_sanitizers(tmp_path):
     env = dict(os.environ, LD_PRELOAD=pre, ASAN_OPTIONS="detect_leaks=0")
     r = subprocess.run([sys.executable, os.path.join(root, "tests", "hostsim", "asan_run.py"), so], env=env, capture_output=True, text=True, timeout=600)
     assert r.returncode == 0 and "asan/ubsan clean" in r.stdout, r.stdout[-2000:] + r.stderr[-4000:]
+
+
+def test_fixed_point_layer0_table(hostsim):
+    """The acting path carries the layer-0 sum in int32 fixed point (xq_act_quant.cuh: the device functions, compiled for the host).  For weight
+    scales from 1e-30 to 1e30 a sum over up to 90 rows + bias (a) never leaves the int32 range -- checked against an int64 sum of the same
+    entries -- and (b) equals the FP64 sum to the quantum: |sum * 2^-k - exact| <= one half-quantum per term, a quantum being < 1.8e-7 of the largest weight.
+    Non-finite and all-zero weights give a defined scale and defined (saturated / zero) entries."""
+    rng = np.random.default_rng(4)
+    n_rows, hid = 1260, 128
+    for scale in (1e-30, 1e-12, 1e-3, 0.05, 1.0, 37.0, 1e6, 1e30):
+        w = (rng.uniform(-scale, scale, (n_rows + 1, hid))).astype(np.float32)          # last row = the bias
+        q = np.zeros_like(w, dtype=np.int32)
+        k = hostsim.hs_act_quant(w.ctypes.data, w.size, q.ctypes.data)
+        assert -100 <= k <= 124
+        wmax = float(np.abs(w).max())
+        assert 92.0 * wmax * 2.0 ** k < 2.0 ** 30 and (k == 124 or 92.0 * wmax * 2.0 ** k >= 2.0 ** 29), (scale, k)      # the largest scale that fits
+        assert np.abs(q.astype(np.float64) - w.astype(np.float64) * 2.0 ** k).max() <= 0.5                              # rint
+        for pieces in (1, 32, 90):
+            rows = np.concatenate([rng.choice(n_rows, pieces, replace=False), [n_rows]])
+            s64 = q[rows].astype(np.int64).sum(axis=0)
+            s32 = q[rows].sum(axis=0, dtype=np.int32)                                    # wrap-around arithmetic, as on the device
+            assert (s64 == s32).all() and np.abs(s64).max() < 2 ** 30, (scale, pieces)
+            exact = w[rows].astype(np.float64).sum(axis=0)
+            assert np.abs(s64 * 2.0 ** -k - exact).max() <= (pieces + 1) * 0.5 * 2.0 ** -k
+            assert np.abs(s64 * 2.0 ** -k - exact).max() <= (pieces + 1) * 1e-7 * wmax          # a quantum is < 1.8e-7 of the largest weight
+        # carried == gathered: remove a row, add another one, in any order (integer sums are associative)
+        rows = list(rng.choice(n_rows, 30, replace=False))
+        z = q[rows].sum(axis=0, dtype=np.int32)
+        z2 = z - q[rows[3]] + q[7] - q[rows[11]]
+        rows2 = [r for i, r in enumerate(rows) if i not in (3, 11)] + [7]
+        assert (z2 == q[rows2].sum(axis=0, dtype=np.int32)).all()
+    for special in (np.zeros(8, np.float32), np.array([np.inf, 1, -2], np.float32), np.array([np.nan, 0.5], np.float32),
+                    np.array([3.4e38, -3.4e38, 1.0], np.float32)):
+        q = np.zeros(len(special), np.int32)
+        k = hostsim.hs_act_quant(special.ctypes.data, len(special), q.ctypes.data)
+        assert -100 <= k <= 124
