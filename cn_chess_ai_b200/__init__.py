@@ -8,4 +8,4 @@ from .env import BatchedEnv, action  # noqa: F401
 from .dqn import AS_WRITTEN, CORRECTED, DQN  # noqa: F401
 from .replay import ReplayBuffer, act, collect, td_update_replay, td_update_replay_n  # noqa: F401
 from .trainer import GAME_EVENT_DTYPE, drain_game_events, enable_game_events, train  # noqa: F401
-from .benchmarks import bench_dqn, smoke_dqn  # noqa: F401
+from .benchmarks import bench_dqn  # noqa: F401

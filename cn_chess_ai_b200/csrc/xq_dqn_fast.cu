@@ -99,6 +99,11 @@ struct Fast {
     int rank = 0, world = 1, parity = 0;
     uint32_t epoch = 0;
     bool connected = false;
+    uint32_t *status_host = nullptr, *status_dev = nullptr;   // mapped pinned word: epoch of the first exchange that timed out (sticky; read without a sync)
+    long long timeout_ticks = 0;                       // clock64 ticks (XQ_DIST_TIMEOUT_MS, default 20 s)
+    int fused_mode = 2;                                // DW_FUSED_OWNER, or DW_FUSED_ALLGATHER with XQ_DIST_FUSED_MODE=allgather
+    uint8_t* hg_stage = nullptr;                       // device staging of dist_host_allgather
+    uint32_t hg_seq = 0;
     // acting (Q(s)[0..89] for every env of a self-play shard): split-precision operands, see q90_gemm_kernel
     __nv_bfloat16* W1lo = nullptr;                     // [96][128] BF16 residual of W1 rows 0..95 (W1 = W1bf + W1lo to ~16 mantissa bits)
     __nv_bfloat16 *actHhi = nullptr, *actHlo = nullptr;   // [act_cap][128] h(s) as BF16 hi + lo
@@ -809,9 +814,40 @@ constexpr int kGradPad = (kGradSize + 3) / 4 * 4;
 constexpr size_t kExchFlagsOff = sizeof(float) * 2 * (size_t)kMaxRanks * kGradPad;                 // 16-byte aligned
 constexpr int kExchBlocks = 96;                                                                      // >= 11 row tiles x 8 splits of the gradient contraction
 constexpr size_t kExchBlockFlagsOff = kExchFlagsOff + sizeof(uint32_t) * (kMaxRanks + 4);           // [kMaxRanks source ranks][kExchBlocks] u32: epoch of the last landed row block
-constexpr size_t kExchBytes = kExchBlockFlagsOff + sizeof(uint32_t) * kMaxRanks * kExchBlocks;
+constexpr size_t kExchOldBytes = kExchBlockFlagsOff + sizeof(uint32_t) * kMaxRanks * kExchBlocks;
+// Owner mode (the default fused exchange): reduce-scatter + all-gather of the 16-row blocks with the flag carried INSIDE the data
+// (the "LL" protocol of collective libraries): a 16-byte line holds two FP32 values and two copies of the epoch, each 8-byte half
+// {value, epoch} is written by one store and therefore arrives whole -- the receiver polls the data itself, no fence, no separate flag.
+//   inbox 1 (reduce-scatter): [2 parities][kMaxRanks source ranks][kLLBlocks][kLLLinesPerBlock] lines, written by the source rank, read by the block's owner
+//   inbox 2 (all-gather):     [2 parities][kLLBlocks][kLLLinesPerBlock] lines, written by the block's owner, read by everybody else
+// A block = the 16 x 128 FP32 rows one CTA of the contraction reduces (4 lines per reducing thread) + one more line per thread for db1.
+constexpr int kLLBlocks = 88;                                                                        // 11 row tiles x 8 splits
+constexpr int kLLLinesPerThread = 5;
+constexpr int kLLLinesPerBlock = kLLLinesPerThread * 256;
+constexpr size_t kLLBlockBytes = (size_t)kLLLinesPerBlock * 16;                                      // 20 KB
+constexpr size_t kExchLL1Off = (kExchOldBytes + 255) / 256 * 256;
+constexpr size_t kExchLL1Bytes = 2 * (size_t)kMaxRanks * kLLBlocks * kLLBlockBytes;                  // 55 MB
+constexpr size_t kExchLL2Off = kExchLL1Off + kExchLL1Bytes;
+constexpr size_t kExchLL2Bytes = 2 * (size_t)kLLBlocks * kLLBlockBytes;                              // 3.4 MB
+// host-level all-gather of small messages between the ranks' processes (the multi-GPU episode driver: finished-game events, round totals)
+constexpr size_t kHgCap = 64 << 10;                                                                  // bytes per rank per call
+constexpr size_t kExchHgOff = kExchLL2Off + kExchLL2Bytes;                                           // [2 parities][kMaxRanks][kHgCap] | flags[kMaxRanks] u32
+constexpr size_t kExchHgFlagsOff = kExchHgOff + 2 * (size_t)kMaxRanks * kHgCap;
+constexpr size_t kExchBytes = kExchHgFlagsOff + 256;
 __host__ __device__ constexpr size_t exch_slot_floats(int parity, int src_rank) { return ((size_t)parity * kMaxRanks + (size_t)src_rank) * kGradPad; }
+__host__ __device__ constexpr size_t exch_ll1_off(int parity, int src_rank, int blk) {
+    return kExchLL1Off + (((size_t)parity * kMaxRanks + (size_t)src_rank) * kLLBlocks + (size_t)blk) * kLLBlockBytes;
+}
+__host__ __device__ constexpr size_t exch_ll2_off(int parity, int blk) { return kExchLL2Off + ((size_t)parity * kLLBlocks + (size_t)blk) * kLLBlockBytes; }
 struct PeerPtrs { uint8_t* p[kMaxRanks]; };
+__device__ __forceinline__ void ll_store(uint8_t* line, float a, float b, uint32_t flag) {
+    asm volatile("st.volatile.global.v4.u32 [%0], {%1, %2, %3, %2};" ::"l"(line), "r"(__float_as_uint(a)), "r"(flag), "r"(__float_as_uint(b)) : "memory");
+}
+__device__ __forceinline__ uint4 ll_load(const uint8_t* line) {
+    uint4 v;
+    asm volatile("ld.volatile.global.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "l"(line) : "memory");
+    return v;
+}
 __device__ __forceinline__ float4 ld_peer_f4(const float* p) {
     float4 v;
     asm volatile("ld.volatile.global.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "l"(p) : "memory");
@@ -821,8 +857,12 @@ struct DwPush {               // world == 0: the gradient stays local (grad)
     PeerPtrs peers;
     int rank = 0, world = 0, parity = 0;
     uint32_t epoch = 0;
-    int fused = 0;            // 1: the contraction itself waits for the peers' row blocks, sums them and applies the SGD step (no exchange kernel)
+    int fused = 0;            // the contraction itself exchanges its row blocks, sums them and applies the SGD step (no exchange kernel):
+                              // 2 = owner mode (reduce-scatter + all-gather of the blocks, flag-in-data lines), 1 = every block to every rank + flags
+    long long timeout = 0;    // clock64 ticks a wait for a peer may last; then the update is NOT applied and *status is raised (sticky)
+    uint32_t* status = nullptr;   // host-mapped word: epoch of the first exchange that timed out (0 = none)
 };
+enum { DW_FUSED_ALLGATHER = 1, DW_FUSED_OWNER = 2 };
 
 // ---------------------------------------------------------------------------------------------
 // dW0^T = X^T . delta0 on tcgen05: C[feature 0..1279][hidden 0..127] = sum_b onehot_b[feature] * delta0_b[hidden].
@@ -1074,24 +1114,119 @@ __global__ void __launch_bounds__(kDwThreads, 1) dw_gemm_kernel(const __grid_con
             }
         }
     }
-    if (push.fused) {
-        // ===== multi-GPU, ONE kernel: contraction -> exchange over peer memory -> SGD, row block by row block =====
+    bool exch_ok = true;           // false: a peer never arrived -- this thread's part of the update is skipped and *push.status is raised
+    float db1 = 0.0f;
+    const bool owns_db1 = push.fused && w1_tile && ks == 0 && threadIdx.x < kQRows;
+    if (owns_db1) {
+#pragma unroll
+        for (int p = 0; p < kDwSplits; ++p) db1 += __ldcg(dbpart + p * BM + threadIdx.x);      // the 8 per-CTA sums in fixed order
+    }
+    if (push.fused == DW_FUSED_OWNER) {
+        // ===== multi-GPU, ONE kernel: contraction -> reduce-scatter -> all-gather -> SGD, row block by row block, over peer memory =====
+        // Block blk (the 16 rows this CTA reduced) is OWNED by rank blk % world.  The same CTA (mt, ks) of every rank handles the same block and
+        // the same thread the same elements, so the exchange is thread to thread:
+        //   non-owner: 5 flag-in-data lines per thread into the owner's inbox 1 (posted 16-byte stores over NVLink 5 / NVSwitch, a warp
+        //              covers 512 contiguous bytes per store instruction), then polls its own inbox 2 for the owner's sum;
+        //   owner:     polls inbox 1 for the `world - 1` other copies (the loads of up to four source ranks in flight together), adds the
+        //              copies IN RANK ORDER (its own from registers) -- every rank applies the very same bits -- and stores the sum into
+        //              inbox 2 of every other rank.
+        // No fence, no flag array, no barrier: a line is valid when both of its epoch words match.  Traffic per rank and update:
+        // 2 x (world - 1) / world x 0.69 MB x 2 (line format) instead of (world - 1) x 0.69 MB -- 2.4 MB instead of 4.8 MB at 8 GPUs, and the
+        // critical path is two one-way NVLink hops instead of [stores -> system-scope fence -> flag -> acquire].
+        // Slot reuse: a rank writes epoch e + 2 into the slots of epoch e only after it completed update e + 1, for which it needed every
+        // rank's lines of epoch e + 1, which they sent after completing update e, i.e. after their last read of the epoch-e slots.
+        const int blk = mt * kDwSplits + ks, owner = blk % push.world, tid = threadIdx.x;
+        const uint32_t flag = push.epoch;
+        const bool need[3] = {e[0] >= 0, e[1] >= 0, owns_db1};          // lines 0,1 = acc[0] | 2,3 = acc[1] | 4 = db1
+        const float mine[10] = {acc[0].x, acc[0].y, acc[0].z, acc[0].w, acc[1].x, acc[1].y, acc[1].z, acc[1].w, db1, 0.0f};
+        const long long t0 = clock64();
+        float g[10] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+        if (owner == push.rank) {
+            const uint8_t* inbox = push.peers.p[push.rank] + (size_t)tid * 16;
+            for (int r0 = 0; r0 < push.world; r0 += 4) {
+                uint4 l[4][kLLLinesPerThread];
+                bool ready;
+                do {
+                    ready = true;
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) {
+                        const int r = r0 + j;
+                        if (r >= push.world || r == push.rank) continue;
+                        const uint8_t* src = inbox + exch_ll1_off(push.parity, r, blk);
+#pragma unroll
+                        for (int k = 0; k < kLLLinesPerThread; ++k)
+                            if (need[k >> 1]) l[j][k] = ll_load(src + (size_t)k * 256 * 16);
+                    }
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) {
+                        const int r = r0 + j;
+                        if (r >= push.world || r == push.rank) continue;
+#pragma unroll
+                        for (int k = 0; k < kLLLinesPerThread; ++k)
+                            if (need[k >> 1] && (l[j][k].y != flag || l[j][k].w != flag)) ready = false;
+                    }
+                } while (!ready && clock64() - t0 < push.timeout);
+                if (!ready) exch_ok = false;
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {                       // rank order
+                    const int r = r0 + j;
+                    if (r >= push.world) break;
+#pragma unroll
+                    for (int k = 0; k < kLLLinesPerThread; ++k) {
+                        if (!need[k >> 1]) continue;
+                        g[2 * k] += r == push.rank ? mine[2 * k] : __uint_as_float(l[j][k].x);
+                        g[2 * k + 1] += r == push.rank ? mine[2 * k + 1] : __uint_as_float(l[j][k].z);
+                    }
+                }
+            }
+            if (exch_ok)
+                for (int r = 0; r < push.world; ++r) {
+                    if (r == push.rank) continue;
+                    uint8_t* dst = push.peers.p[r] + exch_ll2_off(push.parity, blk) + (size_t)tid * 16;
+#pragma unroll
+                    for (int k = 0; k < kLLLinesPerThread; ++k)
+                        if (need[k >> 1]) ll_store(dst + (size_t)k * 256 * 16, g[2 * k], g[2 * k + 1], flag);
+                }
+        } else {
+            uint8_t* dst = push.peers.p[owner] + exch_ll1_off(push.parity, push.rank, blk) + (size_t)tid * 16;
+#pragma unroll
+            for (int k = 0; k < kLLLinesPerThread; ++k)
+                if (need[k >> 1]) ll_store(dst + (size_t)k * 256 * 16, mine[2 * k], mine[2 * k + 1], flag);
+            const uint8_t* src = push.peers.p[push.rank] + exch_ll2_off(push.parity, blk) + (size_t)tid * 16;
+            uint4 l[kLLLinesPerThread];
+            bool ready;
+            do {
+                ready = true;
+#pragma unroll
+                for (int k = 0; k < kLLLinesPerThread; ++k)
+                    if (need[k >> 1]) l[k] = ll_load(src + (size_t)k * 256 * 16);
+#pragma unroll
+                for (int k = 0; k < kLLLinesPerThread; ++k)
+                    if (need[k >> 1] && (l[k].y != flag || l[k].w != flag)) ready = false;
+            } while (!ready && clock64() - t0 < push.timeout);
+            if (!ready) exch_ok = false;
+#pragma unroll
+            for (int k = 0; k < kLLLinesPerThread; ++k)
+                if (need[k >> 1]) { g[2 * k] = __uint_as_float(l[k].x); g[2 * k + 1] = __uint_as_float(l[k].z); }
+        }
+        if (!exch_ok) { *push.status = flag; __threadfence_system(); }
+        acc[0] = make_float4(g[0], g[1], g[2], g[3]); acc[1] = make_float4(g[4], g[5], g[6], g[7]);
+        if (owns_db1 && exch_ok) b1[threadIdx.x] -= lr * g[8];
+    } else if (push.fused) {
+        // ===== A/B alternative (XQ_DIST_FUSED_MODE=allgather): every block to every rank, then a flag per (rank, block) =====
         // 1. push this CTA's 16 reduced rows (and db1, for the CTA that owns it) into slot (parity, my rank) of every rank's buffer
         const size_t slot = exch_slot_floats(push.parity, push.rank);
 #pragma unroll
         for (int u = 0; u < 2; ++u)
             if (e[u] >= 0)
                 for (int r = 0; r < push.world; ++r) *reinterpret_cast<float4*>(push.peers.p[r] + sizeof(float) * (slot + (size_t)e[u])) = acc[u];
-        float db1 = 0.0f;
-        const bool owns_db1 = w1_tile && ks == 0 && threadIdx.x < kQRows;
-        if (owns_db1) {
-#pragma unroll
-            for (int p = 0; p < kDwSplits; ++p) db1 += __ldcg(dbpart + p * BM + threadIdx.x);
+        if (owns_db1)
             for (int r = 0; r < push.world; ++r) *reinterpret_cast<float*>(push.peers.p[r] + sizeof(float) * (slot + (size_t)(kGradB1 + threadIdx.x))) = db1;
-        }
         // 2. "row block b of gradient `epoch` of this rank has landed": CTA barrier, then one release store at system scope per peer (the release is
         //    cumulative over everything the barrier ordered before it -- the pattern of a semaphore release)
         const int blk = mt * kDwSplits + ks;
+        __shared__ int s_timed_out;
+        if (threadIdx.x == 0) s_timed_out = 0;
         __syncthreads();
         if ((int)threadIdx.x < push.world) {
             uint32_t* f = reinterpret_cast<uint32_t*>(push.peers.p[threadIdx.x] + kExchBlockFlagsOff) + push.rank * kExchBlocks + blk;
@@ -1104,10 +1239,11 @@ __global__ void __launch_bounds__(kDwThreads, 1) dw_gemm_kernel(const __grid_con
             do {
                 asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(mine) : "memory");
                 if ((int32_t)(v - push.epoch) >= 0) break;
-                if (clock64() - t0 > (1ll << 32)) { reinterpret_cast<uint32_t*>(push.peers.p[push.rank] + kExchFlagsOff)[kMaxRanks] = 1u; break; }   // ~2 s: flag it, do not hang
+                if (clock64() - t0 > push.timeout) { s_timed_out = 1; *push.status = push.epoch; __threadfence_system(); break; }   // sticky: the update is not applied
             } while (true);
         }
         __syncthreads();
+        if (s_timed_out) exch_ok = false;
         // 4. sum the `world` copies in rank order (the same order on every rank: bit-identical replicas) and apply W -= lr * g
         const float* base = reinterpret_cast<const float*>(push.peers.p[push.rank]);
 #pragma unroll
@@ -1127,14 +1263,13 @@ __global__ void __launch_bounds__(kDwThreads, 1) dw_gemm_kernel(const __grid_con
                 if (r != push.rank) asm volatile("ld.volatile.global.f32 %0, [%1];" : "=f"(v) : "l"(base + exch_slot_floats(push.parity, r) + (size_t)(kGradB1 + threadIdx.x)) : "memory");
                 g += v;
             }
-            b1[threadIdx.x] -= lr * g;
+            if (exch_ok) b1[threadIdx.x] -= lr * g;
         }
     }
-    const bool do_apply = apply || push.fused;
 #pragma unroll
     for (int u = 0; u < 2; ++u) {
         if (e[u] < 0) continue;
-        if (!do_apply) {
+        if (!apply && !push.fused) {
             if (push.world > 0) {      // multi-GPU: the finished rows go straight into slot (parity, my rank) of EVERY rank's exchange buffer (posted NVLink stores)
                 const size_t off = sizeof(float) * (exch_slot_floats(push.parity, push.rank) + (size_t)e[u]);
                 for (int r = 0; r < push.world; ++r) *reinterpret_cast<float4*>(push.peers.p[r] + off) = acc[u];
@@ -1143,6 +1278,7 @@ __global__ void __launch_bounds__(kDwThreads, 1) dw_gemm_kernel(const __grid_con
             }
             continue;
         }
+        if (!exch_ok) continue;
         float* dst = e[u] < kGradB0 ? W0T + e[u] : (e[u] < kGradW1 ? b0 + (e[u] - kGradB0) : W1 + (e[u] - kGradW1));
         float4 w = wold[u];
         w.x -= lr * acc[u].x; w.y -= lr * acc[u].y; w.z -= lr * acc[u].z; w.w -= lr * acc[u].w;
@@ -1231,20 +1367,24 @@ __global__ void __launch_bounds__(256) apply_kernel(float* __restrict__ W0T, flo
 __global__ void __launch_bounds__(256) grad_exchange_apply_kernel(PeerPtrs peers, int rank, int world, int parity, uint32_t epoch,
                                                                  float* __restrict__ W0T, float* __restrict__ b0, float* __restrict__ W1,
                                                                  float* __restrict__ b1, __nv_bfloat16* __restrict__ W1bf,
-                                                                 __nv_bfloat16* __restrict__ W1lo, float lr) {
+                                                                 __nv_bfloat16* __restrict__ W1lo, float lr, long long timeout, uint32_t* __restrict__ status) {
     uint32_t* my_flags = reinterpret_cast<uint32_t*>(peers.p[rank] + kExchFlagsOff);
+    __shared__ int s_timed_out;
+    if (threadIdx.x == 0) s_timed_out = 0;
     tc::pdl_wait();                                            // launched under the tail of the gradient contraction (programmatic dependent launch)
     tc::pdl_launch_dependents();                               // the next update's layer-0 kernel waits for this grid's completion before it reads W0T
+    __syncthreads();
     if ((int)threadIdx.x < world) {                            // 2. all gradients of this epoch are complete
         const long long t0 = clock64();
         uint32_t v;
         do {
             asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(my_flags + threadIdx.x) : "memory");
             if ((int32_t)(v - epoch) >= 0) break;
-            if (clock64() - t0 > (1ll << 32)) { my_flags[kMaxRanks] = 1u; break; }      // ~2 s: a peer never arrived; flag it, do not hang the GPU
+            if (clock64() - t0 > timeout) { s_timed_out = 1; *status = epoch; __threadfence_system(); break; }   // a peer never arrived: sticky, nothing is applied
         } while (true);
     }
     __syncthreads();
+    if (s_timed_out) return;
     const int i = blockIdx.x * blockDim.x + threadIdx.x;       // 3. float4 index over the compact gradient
     if (i >= kGradPad / 4) return;
     float4 g = make_float4(0.f, 0.f, 0.f, 0.f);
@@ -1266,6 +1406,32 @@ __global__ void __launch_bounds__(256) grad_exchange_apply_kernel(PeerPtrs peers
             const __nv_bfloat16 hi = __float2bfloat16_rn(v);
             W1bf[j] = hi; W1lo[j] = __float2bfloat16_rn(v - __bfloat162float(hi));
         } else b1[e - kGradB1] -= lr * gv[k];
+    }
+}
+
+// Host-level all-gather of one small message per rank (the multi-GPU episode driver's round totals and finished-game events): every rank
+// stores its message into inbox (parity, its rank) of every rank, fences at system scope, releases its sequence number into every rank's
+// flag array and waits for all `world` flags in its own memory.  One CTA; same double-buffering argument as the gradient slots.
+__global__ void __launch_bounds__(256) host_gather_kernel(PeerPtrs peers, int rank, int world, int parity, uint32_t seq, const uint4* __restrict__ src,
+                                                         int n16, long long timeout, uint32_t* __restrict__ status) {
+    const size_t off = kExchHgOff + ((size_t)parity * kMaxRanks + (size_t)rank) * kHgCap;
+    for (int r = 0; r < world; ++r) {
+        uint4* dst = reinterpret_cast<uint4*>(peers.p[r] + off);
+        for (int i = threadIdx.x; i < n16; i += blockDim.x) dst[i] = src[i];
+    }
+    __threadfence_system();
+    __syncthreads();
+    if ((int)threadIdx.x < world) {
+        uint32_t* f = reinterpret_cast<uint32_t*>(peers.p[threadIdx.x] + kExchHgFlagsOff) + rank;
+        asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(f), "r"(seq) : "memory");
+        const uint32_t* mine = reinterpret_cast<const uint32_t*>(peers.p[rank] + kExchHgFlagsOff) + threadIdx.x;
+        const long long t0 = clock64();
+        uint32_t v;
+        do {
+            asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(mine) : "memory");
+            if ((int32_t)(v - seq) >= 0) break;
+            if (clock64() - t0 > timeout) { *status = 0x80000000u | seq; __threadfence_system(); break; }
+        } while (true);
     }
 }
 
@@ -1356,7 +1522,8 @@ static inline DwPush dw_push(Fast* f, bool apply, bool fused = false) {
     DwPush p;
     if (!apply && f->connected) {
         for (int r = 0; r < kMaxRanks; ++r) p.peers.p[r] = f->peer[r];
-        p.rank = f->rank; p.world = f->world; p.parity = f->parity; p.epoch = f->epoch + 1; p.fused = fused ? 1 : 0;
+        p.rank = f->rank; p.world = f->world; p.parity = f->parity; p.epoch = f->epoch + 1; p.fused = fused ? f->fused_mode : 0;
+        p.timeout = f->timeout_ticks; p.status = f->status_dev;
     } else {
         for (int r = 0; r < kMaxRanks; ++r) p.peers.p[r] = nullptr;
     }
@@ -1369,7 +1536,12 @@ void dqn_fast_destroy(xq_dqn_s* h) {
     Fast* f = h->fast;
     if (!f) return;
     for (int r = 0; r < f->world; ++r) if (f->connected && r != f->rank && f->peer[r]) cudaIpcCloseMemHandle(f->peer[r]);
-    cudaFree(f->exch);
+    cudaFree(f->exch); cudaFree(f->hg_stage);
+    if (f->status_host) cudaFreeHost(f->status_host);
+    cudaFree(f->H2bf_b); cudaFree(f->zpart_b);
+    if (f->aux) cudaStreamDestroy(f->aux);
+    if (f->ev_fork) cudaEventDestroy(f->ev_fork);
+    for (int i = 0; i < 2; ++i) { if (f->ev_aux[i]) cudaEventDestroy(f->ev_aux[i]); if (f->ev_free[i]) cudaEventDestroy(f->ev_free[i]); if (f->ev_td[i]) cudaEventDestroy(f->ev_td[i]); }
     cudaFree(f->W0T); cudaFree(f->b0); cudaFree(f->W1); cudaFree(f->b1); cudaFree(f->W1bf); cudaFree(f->W1lo); cudaFree(f->actHhi); cudaFree(f->actHlo);
     cudaFree(f->W0Q); cudaFree(f->b0Q); cudaFree(f->zOpen); cudaFree(f->actMax); cudaFree(f->actZ); cudaFree(f->actPrev);
     cudaFree(f->tW0T); cudaFree(f->tb0); cudaFree(f->tW1); cudaFree(f->tb1); cudaFree(f->tW1bf);
@@ -1379,6 +1551,7 @@ void dqn_fast_destroy(xq_dqn_s* h) {
     h->fast = nullptr;
 }
 
+static int fast_init_alloc(xq_dqn_s* h, Fast* f);
 static int fast_init(xq_dqn_s* h) {
     if (h->fast) return XQ_OK;
     if (h->layers.size() != 3 || h->layers[0] != kIn || h->layers[1] != kHid || h->layers[2] != kOut)
@@ -1386,6 +1559,10 @@ static int fast_init(xq_dqn_s* h) {
     Fast* f = new (std::nothrow) Fast();
     if (!f) return fail(XQ_ERR_NOMEM, "out of host memory");
     h->fast = f;
+    if (int rc = fast_init_alloc(h, f)) { dqn_fast_destroy(h); return rc; }      // never leave a half-built object behind: later calls would launch on null pointers
+    return XQ_OK;
+}
+static int fast_init_alloc(xq_dqn_s* h, Fast* f) {
     XQ_CUDA(cudaMalloc(&f->W0T, sizeof(float) * (kIn + 1) * kHid)); XQ_CUDA(cudaMalloc(&f->b0, sizeof(float) * kHid));
     XQ_CUDA(cudaMalloc(&f->W1, sizeof(float) * kOut * kHid)); XQ_CUDA(cudaMalloc(&f->b1, sizeof(float) * kOut));
     XQ_CUDA(cudaMalloc(&f->W1bf, sizeof(__nv_bfloat16) * kOut * kHid));
@@ -1613,10 +1790,22 @@ int xq_dqn_forward_boards(xq_dqn_t h, const xq_env_rec* boards_host, int64_t n, 
 }  // extern "C" (reopened below)
 namespace xq {
 // one batched TD update on the batch described by `ref` (contiguous transitions or in-place replay draws): 4 kernels
+// a gradient exchange of this handle timed out earlier: the replicas may differ, every later update call fails (sticky)
+static int dist_check(xq_dqn_s* h) {
+    Fast* f = h->fast;
+    if (f && f->status_host && *reinterpret_cast<volatile uint32_t*>(f->status_host) != 0)
+        return fail(XQ_ERR_STATE, "multi-GPU gradient exchange %u timed out (a peer never arrived): the update was not applied and the replicas may differ; "
+                                  "recreate the handles on every rank", *reinterpret_cast<volatile uint32_t*>(f->status_host));
+    return XQ_OK;
+}
+
 int td_update_core(xq_dqn_s* h, const BatchRef& ref, int64_t n, int use_target_net, double lr, int apply) {
     if (int rc = ensure_fast(h)) return rc;
     if (int rc = fast_reserve(h, n)) return rc;
     Fast* f = h->fast;
+    if (int rc = dist_check(h)) return rc;
+    // on a handle connected to its peers EVERY applied update exchanges its gradient (include/xq.h): the contraction itself does it
+    const bool exchange = apply && f->connected;
     if (int rc = fast_maps(h, n)) return rc;
     if (lr <= 0) lr = h->lr;
     const int64_t ld = (f->cap + BM - 1) / BM * BM;
@@ -1634,7 +1823,8 @@ int td_update_core(xq_dqn_s* h, const BatchRef& ref, int64_t n, int use_target_n
     // 4. dW0 / db0 / dW1 / db1 contraction, cluster reduction and the SGD step (or the compact gradient)
     XQ_CUDA(launch_pdl(dw_gemm_kernel, dim3(kDwMTiles, kDwSplits), dim3(kDwThreads), kDwSmem, h->stream, kDwSplits, f->tmD0hi, f->tmD0lo, f->tmGhi,
                        f->tmGlo, f->tmCb, (int)n, f->part, f->dbpart, f->info_slots, f->info, cur_grad(f), f->W0T, f->b0, f->W1, f->b1, f->W1bf,
-                       f->W1lo, (float)lr, apply ? 1 : 0, dw_push(f, apply != 0)));
+                       f->W1lo, (float)lr, (apply && !exchange) ? 1 : 0, dw_push(f, apply != 0 && !exchange, exchange)));
+    if (exchange) { ++f->epoch; f->parity ^= 1; }
     if (apply) { h->f64_current = false; ++f->w_version; }
     return XQ_OK;
 }
@@ -1657,6 +1847,7 @@ int dqn_td_update_pipelined(xq_dqn_s* h, const void* ring, int64_t size, uint64_
     if (int rc = fast_reserve(h, n)) return rc;
     Fast* f = h->fast;
     if (int rc = fast_maps(h, n)) return rc;
+    if (int rc = dist_check(h)) return rc;
     if (lr <= 0) lr = h->lr;
     if (!f->aux) {
         int lo = 0, hi = 0;
@@ -1781,6 +1972,10 @@ int xq_dqn_dist_export(xq_dqn_t h, void* handle_out) {
     if (!f->exch) {
         XQ_CUDA(cudaMalloc(&f->exch, kExchBytes));
         XQ_CUDA(cudaMemset(f->exch, 0, kExchBytes));
+        XQ_CUDA(cudaMalloc(&f->hg_stage, kHgCap));
+        XQ_CUDA(cudaHostAlloc(reinterpret_cast<void**>(&f->status_host), 64, cudaHostAllocMapped));
+        memset(f->status_host, 0, 64);
+        XQ_CUDA(cudaHostGetDevicePointer(reinterpret_cast<void**>(&f->status_dev), f->status_host, 0));
     }
     static_assert(sizeof(cudaIpcMemHandle_t) == XQ_IPC_HANDLE_BYTES, "CUDA IPC handle size");
     cudaIpcMemHandle_t ipc;
@@ -1806,12 +2001,23 @@ int xq_dqn_dist_connect(xq_dqn_t h, int rank, int world, const void* handles) {
         f->peer[r] = static_cast<uint8_t*>(p);
     }
     f->rank = rank; f->world = world; f->parity = 0; f->epoch = 0; f->connected = true;
+    {   // how long a wait for a peer may last (XQ_DIST_TIMEOUT_MS, default 20 s: host-side callbacks, logging, a first-call allocation on a
+        // peer are legitimate skew), in clock64 ticks of this device
+        const char* e = getenv("XQ_DIST_TIMEOUT_MS");
+        const double ms = e && atof(e) > 0 ? atof(e) : 20000.0;
+        int khz = 0;
+        XQ_CUDA(cudaDeviceGetAttribute(&khz, cudaDevAttrClockRate, h->device));
+        f->timeout_ticks = (long long)(ms * (double)(khz > 0 ? khz : 2000000));
+        const char* m = getenv("XQ_DIST_FUSED_MODE");
+        f->fused_mode = (m && !strcmp(m, "allgather")) ? DW_FUSED_ALLGATHER : DW_FUSED_OWNER;
+    }
     return XQ_OK;
 }
 
 int xq_dqn_dist_allreduce_apply(xq_dqn_t h, double lr) {
     XQ_DQN_ENTER(h);
     if (!h->fast || !h->fast->connected) return fail(XQ_ERR_STATE, "xq_dqn_dist_allreduce_apply: not connected (xq_dqn_dist_connect)");
+    if (int rc = dist_check(h)) return rc;
     return dqn_exchange_apply(h, lr);
 }
 
@@ -1824,7 +2030,7 @@ int dqn_exchange_apply(xq_dqn_s* h, double lr) {
     for (int r = 0; r < kMaxRanks; ++r) pp.p[r] = f->peer[r];
     ++f->epoch;
     XQ_CUDA(launch_pdl(grad_exchange_apply_kernel, dim3(blocks(kGradPad / 4, 256)), dim3(256), 0, h->stream, 1, pp, f->rank, f->world, f->parity, f->epoch, f->W0T,
-                       f->b0, f->W1, f->b1, f->W1bf, f->W1lo, (float)lr));
+                       f->b0, f->W1, f->b1, f->W1bf, f->W1lo, (float)lr, f->timeout_ticks, f->status_dev));
     f->parity ^= 1;
     h->f64_current = false; ++f->w_version;
     return XQ_OK;
@@ -1832,13 +2038,41 @@ int dqn_exchange_apply(xq_dqn_s* h, double lr) {
 }  // namespace xq
 extern "C" {
 
+int xq_dqn_dist_info(xq_dqn_t h, int* rank, int* world) {
+    if (!h) return fail(XQ_ERR_INVALID, "xq_dqn_dist_info: null handle");
+    const bool c = h->fast && h->fast->connected;
+    if (rank) *rank = c ? h->fast->rank : 0;
+    if (world) *world = c ? h->fast->world : 1;
+    return XQ_OK;
+}
+
+int xq_dqn_dist_allgather(xq_dqn_t h, const void* send_host, int64_t bytes, void* recv_host) {
+    XQ_DQN_ENTER(h);
+    if (!h->fast || !h->fast->connected) return fail(XQ_ERR_STATE, "xq_dqn_dist_allgather: not connected (xq_dqn_dist_connect)");
+    if (!send_host || !recv_host || bytes <= 0 || bytes > (int64_t)kHgCap) return fail(XQ_ERR_INVALID, "xq_dqn_dist_allgather: 1..%d bytes per rank", (int)kHgCap);
+    Fast* f = h->fast;
+    if (int rc = dist_check(h)) return rc;
+    const int n16 = (int)((bytes + 15) / 16);
+    XQ_CUDA(cudaMemsetAsync(f->hg_stage, 0, (size_t)n16 * 16, h->stream));
+    XQ_CUDA(cudaMemcpyAsync(f->hg_stage, send_host, (size_t)bytes, cudaMemcpyHostToDevice, h->stream));
+    PeerPtrs pp;
+    for (int r = 0; r < kMaxRanks; ++r) pp.p[r] = f->peer[r];
+    const uint32_t seq = ++f->hg_seq;
+    const int parity = (int)(seq & 1u);
+    host_gather_kernel<<<1, 256, 0, h->stream>>>(pp, f->rank, f->world, parity, seq, reinterpret_cast<const uint4*>(f->hg_stage), n16, f->timeout_ticks, f->status_dev);
+    XQ_LAUNCH_CHECK();
+    for (int r = 0; r < f->world; ++r)
+        XQ_CUDA(cudaMemcpyAsync(static_cast<uint8_t*>(recv_host) + (size_t)r * (size_t)bytes, f->exch + kExchHgOff + ((size_t)parity * kMaxRanks + (size_t)r) * kHgCap,
+                                (size_t)bytes, cudaMemcpyDeviceToHost, h->stream));
+    XQ_CUDA(cudaStreamSynchronize(h->stream));
+    return dist_check(h);
+}
+
 int xq_dqn_dist_status(xq_dqn_t h, int* timed_out) {
     XQ_DQN_ENTER(h);
     if (!h->fast || !h->fast->exch || !timed_out) return fail(XQ_ERR_STATE, "xq_dqn_dist_status: no exchange buffer");
-    uint32_t v = 0;
     XQ_CUDA(cudaStreamSynchronize(h->stream));
-    XQ_CUDA(cudaMemcpy(&v, h->fast->exch + kExchFlagsOff + sizeof(uint32_t) * kMaxRanks, sizeof(v), cudaMemcpyDeviceToHost));
-    *timed_out = (int)v;
+    *timed_out = (int)*reinterpret_cast<volatile uint32_t*>(h->fast->status_host);      // epoch of the first exchange that timed out, 0 = none
     return XQ_OK;
 }
 

@@ -511,6 +511,24 @@ int xq_env_rollout_random_async(xq_env_t h, int n_plies) {
     return XQ_OK;
 }
 
+static int reserve_trace(xq_env_s* h, int64_t need) {
+    if (need > h->trace_cap) {
+        cudaFree(h->d_trace); h->d_trace = nullptr; h->trace_cap = 0;
+        XQ_CUDA(cudaMalloc(&h->d_trace, sizeof(xq_trace_rec) * need));
+        h->trace_cap = need;
+    }
+    return XQ_OK;
+}
+
+int xq_env_rollout_random_traced_async(xq_env_t h, int n_plies, void** trace_dev) {
+    XQ_ENV_ENTER(h);
+    if (n_plies < 0) return fail(XQ_ERR_INVALID, "xq_env_rollout_random_traced_async: n_plies < 0");
+    if (int rc = reserve_trace(h, (int64_t)n_plies * h->n)) return rc;
+    if (int rc = launch_rollout(h, n_plies, h->d_trace)) return rc;
+    if (trace_dev) *trace_dev = h->d_trace;
+    return XQ_OK;
+}
+
 int xq_env_get_stats(xq_env_t h, xq_env_stats* stats_host, int reset) {
     XQ_ENV_ENTER(h);
     if (stats_host) XQ_CUDA(cudaMemcpyAsync(stats_host, h->d_stats, sizeof(xq_env_stats), cudaMemcpyDeviceToHost, h->stream));
@@ -567,11 +585,7 @@ int xq_env_rollout_random_io(xq_env_t h, const xq_env_rec* boards_in_host, int n
     XQ_ENV_ENTER(h);
     if (n_plies < 0) return fail(XQ_ERR_INVALID, "xq_env_rollout_random: n_plies < 0");
     const int64_t need = (int64_t)n_plies * h->n;
-    if (trace_host && need > h->trace_cap) {
-        cudaFree(h->d_trace); h->d_trace = nullptr; h->trace_cap = 0;
-        XQ_CUDA(cudaMalloc(&h->d_trace, sizeof(xq_trace_rec) * need));
-        h->trace_cap = need;
-    }
+    if (trace_host) if (int rc = reserve_trace(h, need)) return rc;
     if (boards_in_host) {
         XQ_CUDA(cudaMemcpyAsync(h->d_envs, boards_in_host, sizeof(xq_env_rec) * h->n, cudaMemcpyHostToDevice, h->stream));
         h->maybe_nonstd = true;

@@ -10,6 +10,13 @@
 // updates_per_round batched TD updates]; the games that finished during the round are reported in the
 // deterministic order (ply, env) with consecutive game numbers, each through the same callback / log line /
 // autosave cadence.  Host logic only: every device operation goes through the library's own C ABI.
+//
+// Multi-GPU (the network handle is connected to its peers, xq_dqn_dist_connect; one process per GPU, every rank makes the same call
+// with its own env / replay shard): the collector and the replay ring stay rank-local, every TD update exchanges its gradient inside
+// the contraction kernel, and once per round the ranks all-gather their finished games through the peer-mapped exchange buffer
+// (xq_dqn_dist_allgather).  Every rank merges them in (ply, GLOBAL env) order -- the same stream on every rank and for every GPU
+// count -- so all ranks count the same games and stop after the same round; the log file and the autosaves are written by rank 0.
+#include <algorithm>
 #include <chrono>
 #include <string>
 #include <vector>
@@ -17,6 +24,45 @@
 #include "xq_common.cuh"
 
 using namespace xq;
+
+extern "C" int xq_dqn_dist_info(xq_dqn_t h, int* rank, int* world);
+extern "C" int xq_dqn_dist_allgather(xq_dqn_t h, const void* send_host, int64_t bytes, void* recv_host);
+
+namespace {
+struct RoundHeader { int64_t n_events, n_envs; uint64_t env_id0; int64_t dropped; };      // 32 B per rank per round
+struct GlobalEvent { uint64_t genv; xq_game_event e; };
+constexpr int64_t kEventsPerChunk = 2728;                        // x 24 B = 65,472 B <= the 64 KB message of xq_dqn_dist_allgather
+
+// the finished games of all ranks of this round, in (ply, global env) order
+int gather_round(xq_dqn_t h, int world, const std::vector<xq_game_event>& ev, int64_t n, uint64_t env_id0, int64_t n_envs, int64_t dropped,
+                 std::vector<GlobalEvent>* merged, int64_t* envs_total, int64_t* dropped_total) {
+    std::vector<RoundHeader> hd((size_t)world);
+    const RoundHeader mine{n, n_envs, env_id0, dropped};
+    if (int rc = xq_dqn_dist_allgather(h, &mine, sizeof(mine), hd.data())) return rc;
+    int64_t max_n = 0;
+    *envs_total = 0; *dropped_total = 0;
+    for (const RoundHeader& x : hd) { max_n = std::max(max_n, x.n_events); *envs_total += x.n_envs; *dropped_total += x.dropped; }
+    merged->clear();
+    std::vector<xq_game_event> send((size_t)kEventsPerChunk), recv((size_t)(kEventsPerChunk * world));
+    for (int64_t c0 = 0; c0 < max_n; c0 += kEventsPerChunk) {
+        const int64_t m = std::max<int64_t>(0, std::min(kEventsPerChunk, n - c0));
+        std::fill(send.begin(), send.end(), xq_game_event{});
+        std::copy(ev.begin() + (ptrdiff_t)std::min(c0, n), ev.begin() + (ptrdiff_t)(std::min(c0, n) + m), send.begin());
+        if (int rc = xq_dqn_dist_allgather(h, send.data(), kEventsPerChunk * (int64_t)sizeof(xq_game_event), recv.data())) return rc;
+        for (int r = 0; r < world; ++r) {
+            const int64_t mr = std::max<int64_t>(0, std::min(kEventsPerChunk, hd[(size_t)r].n_events - c0));
+            for (int64_t i = 0; i < mr; ++i) {
+                const xq_game_event& e = recv[(size_t)(r * kEventsPerChunk + i)];
+                merged->push_back(GlobalEvent{hd[(size_t)r].env_id0 + e.env, e});
+            }
+        }
+    }
+    std::stable_sort(merged->begin(), merged->end(), [](const GlobalEvent& a, const GlobalEvent& b) {
+        return a.e.ply != b.e.ply ? a.e.ply < b.e.ply : a.genv < b.genv;
+    });
+    return XQ_OK;
+}
+}  // namespace
 
 extern "C" int xq_train_run(xq_dqn_t h, xq_env_t env, xq_replay_t r, const xq_train_config* cfg, xq_game_completed_fn cb, void* user,
                             xq_train_report* report) {
@@ -26,15 +72,22 @@ extern "C" int xq_train_run(xq_dqn_t h, xq_env_t env, xq_replay_t r, const xq_tr
     if (cfg->updates_per_round > 0 && (!r || cfg->batch <= 0)) return fail(XQ_ERR_INVALID, "xq_train_run: training needs a replay buffer and batch > 0");
     int64_t n_envs = 0;
     if (int rc = xq_env_count(env, &n_envs)) return rc;
+    int rank = 0, world = 1;
+    if (int rc = xq_dqn_dist_info(h, &rank, &world)) return rc;
+    EnvInfo ei;
+    if (int rc = env_info(env, &ei)) return rc;
     const int64_t cap = n_envs * (int64_t)cfg->plies_per_round;      // at most one finished game per env per ply
     if (int rc = xq_env_enable_game_events(env, cap)) return rc;
     std::vector<xq_game_event> ev((size_t)cap);
+    std::vector<GlobalEvent> merged;
     FILE* log = nullptr;
-    if (cfg->log_path) {
+    if (cfg->log_path && rank == 0) {
         log = fopen(cfg->log_path, "a");                             // QIODevice::Append (src/chessai.cpp:197-201)
         if (!log) return fail(XQ_ERR_IO, "xq_train_run: cannot open log file %s", cfg->log_path);
     }
     const std::string prefix = cfg->autosave_prefix ? cfg->autosave_prefix : "model_after_";
+    // every rank draws from its own ring: decorrelate the draws of the ranks
+    const uint64_t sample_seed = cfg->sample_seed + 0x9E3779B97F4A7C15ull * (uint64_t)rank;
     xq_train_report rep = {};
     const auto t0 = std::chrono::steady_clock::now();
     int64_t next_sync = cfg->target_sync_plies > 0 ? cfg->target_sync_plies : -1;
@@ -42,12 +95,11 @@ extern "C" int xq_train_run(xq_dqn_t h, xq_env_t env, xq_replay_t r, const xq_tr
     while (rc == XQ_OK && rep.games < cfg->n_games) {
         if ((rc = xq_selfplay_collect(h, env, r, cfg->plies_per_round, cfg->eps, cfg->train_done))) break;
         rep.plies += cfg->plies_per_round;
-        rep.transitions += n_envs * (int64_t)cfg->plies_per_round;
         if (cfg->updates_per_round > 0) {
             int64_t size = 0;
             if ((rc = xq_replay_info(r, &size, nullptr, nullptr))) break;
             if (size > 0) {      // counters rep.updates, +1, ...; pipelined over two streams when the bootstrap net is the target net
-                if ((rc = xq_dqn_td_update_replay_n(h, r, cfg->batch, cfg->sample_seed, (uint32_t)rep.updates, cfg->updates_per_round, cfg->use_target_net,
+                if ((rc = xq_dqn_td_update_replay_n(h, r, cfg->batch, sample_seed, (uint32_t)rep.updates, cfg->updates_per_round, cfg->use_target_net,
                                                     cfg->lr))) break;
                 rep.updates += cfg->updates_per_round;
             }
@@ -58,11 +110,17 @@ extern "C" int xq_train_run(xq_dqn_t h, xq_env_t env, xq_replay_t r, const xq_tr
             next_sync += cfg->target_sync_plies;
         }
         if (rc) break;
-        int64_t n = 0, dropped = 0;
+        int64_t n = 0, dropped = 0, envs_round = n_envs;
         if ((rc = xq_env_drain_game_events(env, ev.data(), cap, &n, &dropped))) break;
+        if (world > 1) {         // the round's games of ALL ranks, merged; also where a timed-out exchange surfaces (sticky status)
+            if ((rc = gather_round(h, world, ev, n, ei.env_id0, n_envs, dropped, &merged, &envs_round, &dropped))) break;
+            n = (int64_t)merged.size();
+        }
+        rep.transitions += envs_round * (int64_t)cfg->plies_per_round;
         rep.events_dropped += dropped;
+        const int64_t games_before = rep.games;
         for (int64_t i = 0; i < n && rep.games < cfg->n_games; ++i) {
-            const xq_game_event& e = ev[(size_t)i];
+            const xq_game_event& e = world > 1 ? merged[(size_t)i].e : ev[(size_t)i];
             ++rep.games;
             if (e.red_score > e.black_score) ++rep.red_wins; else if (e.black_score > e.red_score) ++rep.black_wins;
             if (cb) cb(user, rep.games, e.red_score, e.black_score);
@@ -70,13 +128,18 @@ extern "C" int xq_train_run(xq_dqn_t h, xq_env_t env, xq_replay_t r, const xq_tr
                 const char* result = e.red_score > e.black_score ? "Red wins!" : (e.black_score > e.red_score ? "Black wins!" : "It's a draw!");
                 fprintf(log, "Game %lld completed. Red Score: %d, Black Score: %d. %s\n", (long long)rep.games, e.red_score, e.black_score, result);
                 if (rep.games == cfg->n_games) fprintf(log, "AI self-play session completed. Total games: %lld\n\n", (long long)cfg->n_games);
-                fflush(log);
             }
-            if (cfg->autosave_games > 0 && rep.games % cfg->autosave_games == 0) {     // :165-167
-                const std::string path = prefix + std::to_string(rep.games) + "_games.bin";
+        }
+        if (log) fflush(log);
+        // saveModel every autosave_games games (:165-167).  Thousands of games finish per round and the weights only change between
+        // rounds, so ONE snapshot per round in which a multiple was crossed, named after the last crossed multiple: it holds the weights
+        // at the end of that round (the reference's file holds them after exactly N games of a one-game-at-a-time loop).
+        if (cfg->autosave_games > 0 && rep.games / cfg->autosave_games > games_before / cfg->autosave_games) {
+            if (rank == 0) {
+                const std::string path = prefix + std::to_string(rep.games / cfg->autosave_games * cfg->autosave_games) + "_games.bin";
                 if ((rc = xq_dqn_save(h, path.c_str()))) break;
-                ++rep.autosaves;
             }
+            ++rep.autosaves;
         }
     }
     if (log) fclose(log);

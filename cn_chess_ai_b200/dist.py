@@ -1,8 +1,9 @@
 """Multi-GPU plumbing: one process per GPU (torch.distributed), env / replay shards per rank with no
 data-path collective, and ONE exchange step per TD update: the sum of the compact gradient buffers
 (173,018 FP32 = 0.69 MB) over the ranks followed by the identical SGD step on every rank.  Two ways:
-  * fused (default): the library's own kernel reads the peers' gradients over NVLink / NVSwitch peer memory (CUDA IPC),
-    sums them in rank order and applies the step -- connect_peers() + DQN.dist_allreduce_apply();
+  * fused (default): after connect_peers() every applied update of the library exchanges its gradient INSIDE the gradient
+    contraction kernel over NVLink / NVSwitch peer memory (CUDA IPC): reduce-scatter of the 16-row blocks to their owner
+    ranks, all-gather of the sums, SGD -- td_update_replay(apply=True) / td_update_replay_n / train();
   * baseline: ncclAllReduce through torch.distributed + DQN.apply_grads().
 torch is plumbing here (process group, stream, handle exchange); the kernels are the library's."""
 import os
@@ -85,10 +86,26 @@ class DataParallelLearner:
 
     def update(self, use_target_net=True):
         from . import td_update_replay
-        td_update_replay(self.dqn, self.replay, self.batch, self.seed + 1000003 * self.rank, self.updates, use_target_net, self.lr, apply=False)
-        if self.fused:
-            self.dqn.dist_allreduce_apply(self.lr)
+        if self.fused:          # contraction -> exchange -> SGD in one kernel; a timed-out exchange makes the call fail (sticky)
+            td_update_replay(self.dqn, self.replay, self.batch, self.seed + 1000003 * self.rank, self.updates, use_target_net, self.lr, apply=True)
         else:
+            td_update_replay(self.dqn, self.replay, self.batch, self.seed + 1000003 * self.rank, self.updates, use_target_net, self.lr, apply=False)
             allreduce_sum_(self.grads)
             self.dqn.apply_grads(self.lr)
         self.updates += 1
+
+    def replicas_identical(self):
+        """every rank holds the same parameter bytes (digest all-gathered through the library's own peer-memory exchange)"""
+        d = self.dqn.params_digest()
+        if self.world == 1:
+            return True
+        if self.fused:
+            allv = self.dqn.dist_allgather(d)
+        else:
+            import torch
+            import torch.distributed as dist
+            t = torch.from_numpy(d).to(self.device)
+            g = [torch.empty_like(t) for _ in range(self.world)]
+            dist.all_gather(g, t)
+            allv = torch.stack(g).cpu().numpy()
+        return bool((allv == allv[0]).all())

@@ -39,6 +39,8 @@ def _bind():
     L.xq_dqn_dist_connect.argtypes = [_P, C.c_int, C.c_int, _P]
     L.xq_dqn_dist_allreduce_apply.argtypes = [_P, C.c_double]
     L.xq_dqn_dist_status.argtypes = [_P, C.POINTER(C.c_int)]
+    L.xq_dqn_dist_info.argtypes = [_P, C.POINTER(C.c_int), C.POINTER(C.c_int)]
+    L.xq_dqn_dist_allgather.argtypes = [_P, _P, C.c_int64, _P]
     L.xq_dqn_save.argtypes = [_P, C.c_char_p]
     L.xq_dqn_load.argtypes = [_P, C.c_char_p]
     _bound = True
@@ -168,6 +170,26 @@ class DQN:
         check(self._L.xq_dqn_dist_allreduce_apply(self._h, lr))
 
     def dist_timed_out(self):
+        """epoch of the first gradient exchange that timed out (0 = none; sticky: later update calls fail)"""
         v = C.c_int()
         check(self._L.xq_dqn_dist_status(self._h, C.byref(v)))
         return bool(v.value)
+
+    def dist_info(self):
+        r, w = C.c_int(), C.c_int()
+        check(self._L.xq_dqn_dist_info(self._h, C.byref(r), C.byref(w)))
+        return r.value, w.value
+
+    def dist_allgather(self, message):
+        """host-level all-gather of one small message (<= 64 KB) per rank through the peer-mapped exchange buffer: [world, len] uint8"""
+        m = np.ascontiguousarray(message).view(np.uint8).reshape(-1)
+        _, world = self.dist_info()
+        out = np.zeros((world, m.size), dtype=np.uint8)
+        check(self._L.xq_dqn_dist_allgather(self._h, ptr(m), m.size, ptr(out)))
+        return out
+
+    def params_digest(self):
+        """128-bit digest of the trained parameters' bytes (replica comparison across ranks)"""
+        import hashlib
+        w, b = self.get_params()
+        return np.frombuffer(hashlib.blake2b(w.tobytes() + b.tobytes(), digest_size=16).digest(), dtype=np.uint8).copy()

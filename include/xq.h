@@ -134,6 +134,9 @@ int xq_env_rollout_random_io(xq_env_t h, const xq_env_rec* boards_in_host, int n
                              xq_trace_rec* trace_host, xq_env_stats* stats_host);
 /* same, device-resident and asynchronous: no host traffic; stats accumulate on the device */
 int xq_env_rollout_random_async(xq_env_t h, int n_plies);
+/* same with the per-ply trace [n_plies][n_envs] written to a device buffer owned by the handle (*trace_dev, valid until the next traced
+ * call; may be NULL): the traced mode without host traffic */
+int xq_env_rollout_random_traced_async(xq_env_t h, int n_plies, void** trace_dev);
 int xq_env_get_stats(xq_env_t h, xq_env_stats* stats_host, int reset);
 /* ChessAI::getStateRepresentation, src/chessai.cpp:268-289: out_host[n][1260] doubles */
 int xq_env_state_onehot(xq_env_t h, double* out_host);
@@ -217,12 +220,24 @@ int xq_dqn_apply_grads(xq_dqn_t h, double lr);
  * of them, in rank order, to xq_dqn_dist_connect.  From then on xq_dqn_td_update_*(apply = 0) leaves the compact gradient in
  * the exchange buffer and xq_dqn_dist_allreduce_apply launches ONE kernel per rank that signals / waits through flags in
  * peer memory, sums the world gradients in rank order over NVLink (bit-identical on every rank) and applies W -= lr * sum.
- * It replaces ncclAllReduce + xq_dqn_apply_grads.  xq_dqn_dist_status: timed_out != 0 if a peer never arrived (~2 s). */
+ * It replaces ncclAllReduce + xq_dqn_apply_grads.
+ * EVERY applied update on a connected handle exchanges its gradient: xq_dqn_td_update / xq_dqn_td_update_device / _replay with apply = 1 and
+ * xq_dqn_td_update_replay_n run the exchange INSIDE the gradient contraction kernel (contraction -> reduce-scatter of the 16-row blocks to
+ * their owner ranks -> all-gather of the sums -> SGD, flag-in-data lines over peer memory; XQ_DIST_FUSED_MODE=allgather selects the older
+ * every-block-to-every-rank variant for A/B runs).  Every rank must make the same sequence of update calls.
+ * A wait for a peer that lasts longer than XQ_DIST_TIMEOUT_MS (default 20000) does NOT apply the update and makes the handle fail
+ * (XQ_ERR_STATE, sticky) on every later update / exchange call: the replicas may differ, recreate the handles.
+ * xq_dqn_dist_status: timed_out = epoch of the first exchange that timed out (0 = none).
+ * xq_dqn_dist_info: rank / world of a connected handle (0 / 1 otherwise).
+ * xq_dqn_dist_allgather: host-level all-gather of one message of `bytes` (<= 65536) per rank through the same peer-mapped buffer
+ * (recv_host[world][bytes], rank order); collective and synchronous -- what xq_train_run uses to merge the ranks' finished games. */
 #define XQ_IPC_HANDLE_BYTES 64
 int xq_dqn_dist_export(xq_dqn_t h, void* handle_out);
 int xq_dqn_dist_connect(xq_dqn_t h, int rank, int world, const void* handles);
 int xq_dqn_dist_allreduce_apply(xq_dqn_t h, double lr);
 int xq_dqn_dist_status(xq_dqn_t h, int* timed_out);
+int xq_dqn_dist_info(xq_dqn_t h, int* rank, int* world);
+int xq_dqn_dist_allgather(xq_dqn_t h, const void* send_host, int64_t bytes, void* recv_host);
 
 /* ---- GPU-resident replay buffer + epsilon-greedy self-play (new capabilities: the reference trains online at
  * batch 1 and has no replay buffer; semantics are per transition those of ChessAI::train) ---- */
@@ -255,7 +270,7 @@ int xq_dqn_td_update_replay(xq_dqn_t h, xq_replay_t r, int64_t batch, uint64_t s
  * xq_dqn_td_update_replay(..., apply = 1).  With use_target_net != 0 the updates are software-pipelined: the bootstrap branch
  * (h(s') with the target net + the [batch x 128] x [128 x 8100] row-max GEMM) of the next updates does not depend on the online
  * weights and runs on a second stream underneath the online branch of the current one.  On a handle connected to its peers
- * (xq_dqn_dist_connect) every update exchanges its gradient: gradient kernels -> xq_dqn_dist_allreduce_apply, per update. */
+ * (xq_dqn_dist_connect) every update exchanges its gradient inside its contraction kernel. */
 int xq_dqn_td_update_replay_n(xq_dqn_t h, xq_replay_t r, int64_t batch, uint64_t seed, uint32_t counter0, int n_updates, int use_target_net,
                               double lr);
 
@@ -300,7 +315,13 @@ typedef struct {
     double seconds;
 } xq_train_report;
 /* Runs rounds of [collect plies_per_round plies over all envs -> updates_per_round TD updates -> drain the finished games in
- * (ply, env) order: callback (gameCompleted), log line, autosave] until n_games games have finished.  Synchronous. */
+ * (ply, env) order: callback (gameCompleted), log line, autosave] until n_games games have finished.  Synchronous.
+ * autosave: one snapshot per round in which a multiple of autosave_games was crossed, named after the last crossed multiple (the
+ * weights at the end of that round).
+ * Multi-GPU = BASELINE config 4 as ONE call per rank: when `h` is connected to its peers (xq_dqn_dist_connect) every rank calls this
+ * with its own env / replay shard and the same cfg; n_games, the game numbers, the report's games / transitions / wins count the games
+ * of ALL ranks merged in (ply, global env) order (identical on every rank and for every GPU count of the same total env range); the
+ * callback fires on every rank that passes one, the log file and the autosaves are written by rank 0 only. */
 int xq_train_run(xq_dqn_t h, xq_env_t env, xq_replay_t r, const xq_train_config* cfg, xq_game_completed_fn cb, void* user, xq_train_report* report);
 
 /* number of kernels this library has launched in this process (bench.py's gpu_launches) */
