@@ -304,20 +304,31 @@ cudaError_t launch_rollout_slots(xq_env_rec* envs, int64_t n, uint64_t env_id0, 
                                  xq_env_stats* stats, uint8_t* nonstd, cudaStream_t stream);
 cudaError_t launch_rollout_team(int team, xq_env_rec* envs, int64_t n, uint64_t env_id0, uint64_t seed, int n_plies, xq_trace_rec* trace,
                                 xq_env_stats* stats, uint8_t* nonstd, cudaStream_t stream);
+cudaError_t launch_rollout_lane(xq_env_rec* envs, int64_t n, uint64_t env_id0, uint64_t seed, int n_plies, xq_trace_rec* trace, xq_env_stats* stats,
+                                uint8_t* nonstd, cudaStream_t stream);
 }
-// threads per board of the fused rollout kernel: 4 = rollout_team_kernel<4> (xq_rollout_team.cu), the default at every env count;
-// 8 = rollout_team_kernel<8> (twice the warps per board: measured equal at 4096 envs, slower from 8192 envs on) and
-// 16 = rollout_slots_kernel (xq_rollout.cu) are kept for A/B runs: XQ_ROLLOUT_TEAM=8|16.  All three are bit-identical.
-static int rollout_team() {
+// threads per board of the fused rollout kernel: 1 = rollout_lane_kernel (xq_rollout_lane.cu: the whole board in one thread's registers,
+// no barrier, nothing replicated), the default above 12,288 envs; 4 = rollout_team_kernel<4> (xq_rollout_team.cu), the default below;
+// 8 = rollout_team_kernel<8> and 16 = rollout_slots_kernel (xq_rollout.cu) are kept for A/B runs: XQ_ROLLOUT_TEAM=1|4|8|16 forces one.
+// All four are bit-identical.
+// Measured on one B200 (steps/s, 200 / 200 / 100 / 32 plies per launch):   envs      4096     16,384    65,536    1M
+//   board per thread (1)                                                             1.94e9   7.71e9    1.14e10   1.30e10
+//   team of 4 (4)                                                                    3.69e9   7.18e9    8.80e9    8.60e9
+// Up to ~16k envs every warp sits alone on its scheduler and a launch lasts as long as ONE warp's plies: the team kernel's shorter
+// per-thread ply (~700 instructions against ~1800) wins there; beyond that the kernels are issue-bound and the one that executes
+// fewer instructions per env step (56 against 87 warp-instructions) wins.
+static int rollout_team(int64_t n) {
     static const int forced = [] { const char* e = getenv("XQ_ROLLOUT_TEAM"); return e ? atoi(e) : 0; }();
-    return forced == 8 || forced == 16 ? forced : 4;
+    if (forced == 1 || forced == 4 || forced == 8 || forced == 16) return forced;
+    return n <= 12288 ? 4 : 1;
 }
 // Fused rollout = team kernel (xq_rollout_team.cu; or the 16-thread slot kernel, xq_rollout.cu) for every board with a standard piece set, then the generic
 // thread-per-board kernel for the boards it flagged (only possible after xq_env_set_boards injected exotic positions).
 static int launch_rollout(xq_env_s* h, int n_plies, xq_trace_rec* d_trace) {
     if (n_plies >= (1 << 24)) return fail(XQ_ERR_INVALID, "rollout: n_plies must be < 2^24 per launch");
-    const int team = rollout_team();
-    if (team == 16) XQ_CUDA(launch_rollout_slots(h->d_envs, h->n, h->env_id0, h->seed, n_plies, d_trace, h->d_stats, h->d_nonstd, h->stream));
+    const int team = rollout_team(h->n);
+    if (team == 1) XQ_CUDA(launch_rollout_lane(h->d_envs, h->n, h->env_id0, h->seed, n_plies, d_trace, h->d_stats, h->d_nonstd, h->stream));
+    else if (team == 16) XQ_CUDA(launch_rollout_slots(h->d_envs, h->n, h->env_id0, h->seed, n_plies, d_trace, h->d_stats, h->d_nonstd, h->stream));
     else XQ_CUDA(launch_rollout_team(team, h->d_envs, h->n, h->env_id0, h->seed, n_plies, d_trace, h->d_stats, h->d_nonstd, h->stream));
     if (h->maybe_nonstd) {
         rollout_random_kernel<<<grid_for(h->n, kThreads), kThreads, 0, h->stream>>>(h->d_envs, h->n, h->env_id0, h->seed, n_plies, d_trace,

@@ -44,7 +44,7 @@ def hostsim():
     import ctypes as C
     src = os.path.join(ROOT, "tests", "hostsim", "hostsim.cpp")
     so = os.path.join(ROOT, "tests", "hostsim", "libxq_hostsim.so")
-    hdrs = [os.path.join(ROOT, "cn_chess_ai_b200", "csrc", h) for h in ("xq_rules.cuh", "xq_bitboard.cuh", "xq_rollout_team.cuh", "xq_act_team.cuh", "xq_act_quant.cuh")]
+    hdrs = [os.path.join(ROOT, "cn_chess_ai_b200", "csrc", h) for h in ("xq_rules.cuh", "xq_bitboard.cuh", "xq_rollout_team.cuh", "xq_rollout_lane.cuh", "xq_act_team.cuh", "xq_act_quant.cuh")]
     if not os.path.exists(so) or os.path.getmtime(so) < max([os.path.getmtime(src)] + [os.path.getmtime(h) for h in hdrs]):
         subprocess.run(["g++", "-std=c++17", "-O2", "-fPIC", "-shared", "-Wno-unknown-pragmas", "-o", so, src], check=True)
     H = C.CDLL(so)
@@ -58,6 +58,7 @@ def hostsim():
     H.hs_is_valid_move.argtypes = [P, C.c_int, C.c_int, C.c_int, C.c_int]
     H.hs_act_team.argtypes = [P, C.c_long, C.c_uint64, C.c_uint64, P, C.c_uint32, P]
     H.hs_team_rollout.argtypes = [C.c_int, P, C.c_long, C.c_uint64, C.c_uint64, C.c_int, P, P]
+    H.hs_lane_rollout.argtypes = [P, C.c_long, C.c_uint64, C.c_uint64, C.c_int, P, P]
     H.hs_act_quant.argtypes = [P, C.c_long, P]
     return H
 

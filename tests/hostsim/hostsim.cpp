@@ -7,6 +7,7 @@
 #include "../../cn_chess_ai_b200/csrc/xq_rules.cuh"
 #include "../../cn_chess_ai_b200/csrc/xq_bitboard.cuh"
 #include "../../cn_chess_ai_b200/csrc/xq_rollout_team.cuh"
+#include "../../cn_chess_ai_b200/csrc/xq_rollout_lane.cuh"
 #include "../../cn_chess_ai_b200/csrc/xq_act_team.cuh"
 #include "../../include/xq.h"
 
@@ -96,6 +97,39 @@ int team_rollout_host(xq_env_rec* recs, long n, uint64_t env_id0, uint64_t seed,
 }
 }
 
+// ---- the board-per-thread rollout kernel's ply (xq_rollout_lane.cuh), one board at a time ----
+namespace {
+int lane_rollout_host(xq_env_rec* recs, long n, uint64_t env_id0, uint64_t seed, int n_plies, xq_trace_rec* trace, xq_env_stats* stats) {
+    int nonstd = 0;
+    uint32_t magic[XQ_MAX_ACTIONS + 1] = {0};
+    for (int d = 1; d <= XQ_MAX_ACTIONS; ++d) magic[d] = team_mod_magic((uint32_t)d);
+    for (long env = 0; env < n; ++env) {
+        uint8_t slot[32];
+        for (int i = 0; i < 32; ++i) slot[i] = kDeadSq;
+        uint32_t w[12];
+        std::memcpy(w, recs[env].sq, 48);
+        Bits90 red, black, occT;
+        if (!team_unpack_record(w, red, black, occT, [&](int s, int q) { slot[s] = (uint8_t)q; })) { ++nonstd; continue; }
+        LaneState st;
+        LaneStats a{0, 0, 0, 0, 0, 0, 0, 0};
+        lane_load(st, [&](int s) { return (int)slot[s]; }, red, black, occT, recs[env].move_count, recs[env].player, recs[env].red_score,
+                  recs[env].black_score, recs[env].ctr);
+        const uint64_t base = seed + (env_id0 + (uint64_t)env) * 0x9E3779B97F4A7C15ull;
+        for (int p = 0; p < n_plies; ++p) lane_ply(st, a, base, magic, trace ? trace + ((long)p * n + env) : nullptr);
+        uint32_t words[12];
+        lane_store_words(st, words);
+        std::memcpy(recs[env].sq, words, 48);
+        recs[env].move_count = (uint16_t)st.move_count; recs[env].player = (uint8_t)st.player;
+        recs[env].red_score = st.red; recs[env].black_score = st.black; recs[env].ctr = st.ctr;
+        if (stats) {
+            stats->steps += a.steps; stats->games += a.games; stats->red_wins += a.red; stats->black_wins += a.black;
+            stats->cap_games += a.capg; stats->captures += a.caps; stats->reward_sum += a.reward; stats->legal_sum += a.legal;
+        }
+    }
+    return nonstd;
+}
+}
+
 // ---- DQN::selectAction through the team act phases (xq_act_team.cuh), one board at a time ----
 namespace {
 int act_team_host(const xq_env_rec* recs, long n, uint64_t env_id0, uint64_t seed, const float* q90, uint32_t eps_thr, uint16_t* actions) {
@@ -143,6 +177,9 @@ int act_team_host(const xq_env_rec* recs, long n, uint64_t env_id0, uint64_t see
 extern "C" {
 int hs_act_team(const xq_env_rec* recs, long n, uint64_t env_id0, uint64_t seed, const float* q90, uint32_t eps_thr, uint16_t* actions) {
     return act_team_host(recs, n, env_id0, seed, q90, eps_thr, actions);
+}
+int hs_lane_rollout(xq_env_rec* recs, long n, uint64_t env_id0, uint64_t seed, int n_plies, xq_trace_rec* trace, xq_env_stats* stats) {
+    return lane_rollout_host(recs, n, env_id0, seed, n_plies, trace, stats);
 }
 // whole fused rollout through the team kernel's phases; returns the number of boards it does not handle (non-standard piece sets)
 int hs_team_rollout(int team, xq_env_rec* recs, long n, uint64_t env_id0, uint64_t seed, int n_plies, xq_trace_rec* trace, xq_env_stats* stats) {

@@ -136,6 +136,41 @@ def test_rollout_from_injected_boards(xq, O, oracle_lib):
     assert same_recs(env.get_boards(), ref) and stats.tobytes() == st0[0].tobytes()
 
 
+def test_board_per_thread_kernel_traces(xq, O, oracle_lib):
+    """above 12,288 envs the fused rollout is rollout_lane_kernel (one thread per board, the board in registers): every ply of every
+    env against the oracle -- from the opening over more than one game, and resumed from mid-game / arbitrary (non-standard piece
+    sets go to the generic kernel) / finished boards; ragged env counts"""
+    n, plies, seed, id0 = 16411, 230, 21, 5
+    env = xq.BatchedEnv(n, seed=seed, env_id0=id0)
+    stats, tr = env.rollout_random(plies, trace=True)
+    ref = O.new_envs(n)
+    tr0 = np.zeros((plies, n), O.TRACE_DTYPE)
+    st0 = np.zeros(1, O.STATS_DTYPE)
+    oracle_lib.xqo_rollout_random(ref.ctypes.data, n, id0, seed, plies, tr0.ctypes.data, st0.ctypes.data)
+    bad = np.nonzero((tr.view(np.uint64) != tr0.view(np.uint64)).any(0))[0]
+    assert len(bad) == 0, f"{len(bad)} envs differ, first {bad[:5]}"
+    assert same_recs(env.get_boards(), ref) and stats.tobytes() == st0[0].tobytes()
+    mid = harvest_positions(O, 400, 9, 23)
+    fin = O.new_envs(64)
+    fin["move_count"][:32] = 200
+    fin["sq"][32:, 0] &= np.uint32(0xFFF0FFFF)          # Red general gone: restarted, never stepped (chessai.cpp:90,96)
+    base = np.concatenate([mid, random_boards(O, 900, seed=4), fin])
+    recs = np.concatenate([base] * (12500 // len(base) + 1))
+    recs["ctr"] = np.arange(len(recs)) % 1000
+    n = len(recs)
+    assert n > 12288 and n % 128 != 0
+    env = xq.BatchedEnv(n, seed=6)
+    env.set_boards(recs)
+    stats, tr = env.rollout_random(48, trace=True)
+    ref = recs.copy()
+    tr0 = np.zeros((48, n), O.TRACE_DTYPE)
+    st0 = np.zeros(1, O.STATS_DTYPE)
+    oracle_lib.xqo_rollout_random(ref.ctypes.data, n, 0, 6, 48, tr0.ctypes.data, st0.ctypes.data)
+    bad = np.nonzero((tr.view(np.uint64) != tr0.view(np.uint64)).any(0))[0]
+    assert len(bad) == 0, f"{len(bad)} envs differ, first {bad[:5]}"
+    assert same_recs(env.get_boards(), ref) and stats.tobytes() == st0[0].tobytes()
+
+
 def test_step_rejects_invalid_moves(xq, O, oracle_lib):
     recs = np.concatenate([harvest_positions(O, 256, 4, 31), random_boards(O, 1024, seed=8)])
     n = len(recs)

@@ -97,7 +97,10 @@ def _team_vs_oracle(O, L, H, team, recs, seed, id0, plies):
     L.xqo_rollout_random(a.ctypes.data, n, id0, seed, plies, tr0.ctypes.data, st0.ctypes.data)
     tr1 = np.zeros((plies, n), O.TRACE_DTYPE)
     st1 = np.zeros(1, O.STATS_DTYPE)
-    assert H.hs_team_rollout(team, b.ctypes.data, n, id0, seed, plies, tr1.ctypes.data, st1.ctypes.data) == 0
+    if team == 1:      # the board-per-thread kernel
+        assert H.hs_lane_rollout(b.ctypes.data, n, id0, seed, plies, tr1.ctypes.data, st1.ctypes.data) == 0
+    else:
+        assert H.hs_team_rollout(team, b.ctypes.data, n, id0, seed, plies, tr1.ctypes.data, st1.ctypes.data) == 0
     bad = np.nonzero((tr0.view(np.uint64) != tr1.view(np.uint64)).any(0))[0]
     assert len(bad) == 0, f"team {team}: {len(bad)} envs differ, first env {bad[:3]}, first ply {np.nonzero(tr0.view(np.uint64)[:, bad[0]] != tr1.view(np.uint64)[:, bad[0]])[0][:3]}"
     assert a.tobytes() == b.tobytes()
@@ -117,6 +120,19 @@ def test_team_rollout_phases(O, oracle_lib, hostsim):
         _team_vs_oracle(O, oracle_lib, hostsim, team, mid, 77, 0, 230)
         _team_vs_oracle(O, oracle_lib, hostsim, team, mid, 78, 123456789012, 1)
         _team_vs_oracle(O, oracle_lib, hostsim, team, fin, 3, 9, 40)
+
+
+def test_lane_rollout_ply(O, oracle_lib, hostsim):
+    """xq_rollout_lane.cuh (rollout_lane_kernel): the board-per-thread ply run on the host reproduces the oracle's fused rollout record
+    for record -- same cases as the team kernel (from the opening over several games, resumed mid-game, finished boards)"""
+    mid = harvest_positions(O, 600, 6, 37, seed=5)
+    fin = O.new_envs(8)
+    fin["move_count"][:4] = 200
+    fin["sq"][4:, 0] &= np.uint32(0xFFF0FFFF)
+    _team_vs_oracle(O, oracle_lib, hostsim, 1, O.new_envs(1500), 11, 5000, 450)
+    _team_vs_oracle(O, oracle_lib, hostsim, 1, mid, 77, 0, 230)
+    _team_vs_oracle(O, oracle_lib, hostsim, 1, mid, 78, 123456789012, 1)
+    _team_vs_oracle(O, oracle_lib, hostsim, 1, fin, 3, 9, 40)
 
 
 def test_team_act_selection(O, oracle_lib, hostsim):
