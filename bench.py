@@ -338,6 +338,29 @@ def main():
         if dist is not None:
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
         aux["traced_steps_per_s"] = E * P * 20 * world / (float(t[0]) * 1e-3)
+        # API mode (what a drop-in caller of getAllValidActions -> movePiece does, src/chessai.cpp:347-368, src/chessboard.cpp:38-64), device-resident:
+        # per ply three launches -- ordered lists materialised in HBM, random-policy pick from the list, step (movePiece + reward + terminal)
+        aux["api_mode"] = {}
+        for n_api, p_api in ((E, 200), (65536, 50)):
+            ae = xq.BatchedEnv(n_api, device=local, seed=2024, env_id0=rank * n_api)
+            ae.set_stream(stream.cuda_stream)
+            for _ in range(5):
+                ae.api_ply_device()
+            barrier()
+            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a.record(stream)
+            for _ in range(p_api):
+                ae.api_ply_device()
+            b.record(stream)
+            barrier()
+            t = torch.tensor([a.elapsed_time(b)], dtype=torch.float64, device="cuda")
+            if dist is not None:
+                dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            sps = n_api * p_api * world / (float(t[0]) * 1e-3)
+            aux["api_mode"][str(n_api)] = {"envs_per_gpu": n_api, "plies": p_api, "launches": 3 * p_api, "steps_per_s": sps, "us_per_ply": 1e3 * float(t[0]) / p_api,
+                                           "roofline": {"bound": "hbm", "achieved": 215 * sps / world / 1e9, "peak": pk["hbm_gbs"], "unit": "GB/s",
+                                                        "frac": 215 * sps / world / 1e9 / pk["hbm_gbs"], "algorithmic_bytes_per_step": 215, "traffic": None}}
+            ae.close()
         # BASELINE config 5: 1M envs in total (1M / N per GPU), random policy, 32 plies per launch
         per_gpu = (1 << 20) // world
         big = xq.BatchedEnv(per_gpu, device=local, seed=7, env_id0=rank * per_gpu)

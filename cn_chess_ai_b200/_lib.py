@@ -66,6 +66,9 @@ def lib():
     L.xq_env_rollout_random_io.argtypes = [_P, _P, C.c_int, _P, _P, _P]
     L.xq_env_rollout_random_async.argtypes = [_P, C.c_int]
     L.xq_env_rollout_random_traced_async.argtypes = [_P, C.c_int, C.POINTER(_P)]
+    L.xq_env_legal_moves_device.argtypes = [_P, C.POINTER(_P), C.POINTER(_P)]
+    L.xq_env_pick_random_device.argtypes = [_P, C.POINTER(_P)]
+    L.xq_env_step_device.argtypes = [_P, _P, C.c_int] + [C.POINTER(_P)] * 5
     L.xq_env_get_stats.argtypes = [_P, _P, C.c_int]
     L.xq_env_state_onehot.argtypes = [_P, _P]
     _lib = L

@@ -102,7 +102,8 @@ struct Fast {
     uint32_t *status_host = nullptr, *status_dev = nullptr;   // mapped pinned word: epoch of the first exchange that timed out (sticky; read without a sync)
     long long timeout_ticks = 0;                       // clock64 ticks (XQ_DIST_TIMEOUT_MS, default 20 s)
     int fused_mode = 2;                                // DW_FUSED_OWNER, or DW_FUSED_ALLGATHER with XQ_DIST_FUSED_MODE=allgather
-    uint8_t* hg_stage = nullptr;                       // device staging of dist_host_allgather
+    uint8_t* hg_stage = nullptr;                       // device staging of xq_dqn_dist_allgather
+    uint8_t* hg_pin = nullptr;                         // pinned host staging: [send kHgCap | recv kMaxRanks x kHgCap]
     uint32_t hg_seq = 0;
     // acting (Q(s)[0..89] for every env of a self-play shard): split-precision operands, see q90_gemm_kernel
     __nv_bfloat16* W1lo = nullptr;                     // [96][128] BF16 residual of W1 rows 0..95 (W1 = W1bf + W1lo to ~16 mantissa bits)
@@ -1538,6 +1539,7 @@ void dqn_fast_destroy(xq_dqn_s* h) {
     for (int r = 0; r < f->world; ++r) if (f->connected && r != f->rank && f->peer[r]) cudaIpcCloseMemHandle(f->peer[r]);
     cudaFree(f->exch); cudaFree(f->hg_stage);
     if (f->status_host) cudaFreeHost(f->status_host);
+    if (f->hg_pin) cudaFreeHost(f->hg_pin);
     cudaFree(f->H2bf_b); cudaFree(f->zpart_b);
     if (f->aux) cudaStreamDestroy(f->aux);
     if (f->ev_fork) cudaEventDestroy(f->ev_fork);
@@ -1973,6 +1975,7 @@ int xq_dqn_dist_export(xq_dqn_t h, void* handle_out) {
         XQ_CUDA(cudaMalloc(&f->exch, kExchBytes));
         XQ_CUDA(cudaMemset(f->exch, 0, kExchBytes));
         XQ_CUDA(cudaMalloc(&f->hg_stage, kHgCap));
+        XQ_CUDA(cudaHostAlloc(reinterpret_cast<void**>(&f->hg_pin), (size_t)(kMaxRanks + 1) * kHgCap, cudaHostAllocDefault));
         XQ_CUDA(cudaHostAlloc(reinterpret_cast<void**>(&f->status_host), 64, cudaHostAllocMapped));
         memset(f->status_host, 0, 64);
         XQ_CUDA(cudaHostGetDevicePointer(reinterpret_cast<void**>(&f->status_dev), f->status_host, 0));
@@ -2053,18 +2056,19 @@ int xq_dqn_dist_allgather(xq_dqn_t h, const void* send_host, int64_t bytes, void
     Fast* f = h->fast;
     if (int rc = dist_check(h)) return rc;
     const int n16 = (int)((bytes + 15) / 16);
-    XQ_CUDA(cudaMemsetAsync(f->hg_stage, 0, (size_t)n16 * 16, h->stream));
-    XQ_CUDA(cudaMemcpyAsync(f->hg_stage, send_host, (size_t)bytes, cudaMemcpyHostToDevice, h->stream));
+    memset(f->hg_pin, 0, (size_t)n16 * 16);            // pinned staging on both sides: one H2D copy, one kernel, one strided D2H copy, one synchronisation
+    memcpy(f->hg_pin, send_host, (size_t)bytes);
+    XQ_CUDA(cudaMemcpyAsync(f->hg_stage, f->hg_pin, (size_t)n16 * 16, cudaMemcpyHostToDevice, h->stream));
     PeerPtrs pp;
     for (int r = 0; r < kMaxRanks; ++r) pp.p[r] = f->peer[r];
     const uint32_t seq = ++f->hg_seq;
     const int parity = (int)(seq & 1u);
     host_gather_kernel<<<1, 256, 0, h->stream>>>(pp, f->rank, f->world, parity, seq, reinterpret_cast<const uint4*>(f->hg_stage), n16, f->timeout_ticks, f->status_dev);
     XQ_LAUNCH_CHECK();
-    for (int r = 0; r < f->world; ++r)
-        XQ_CUDA(cudaMemcpyAsync(static_cast<uint8_t*>(recv_host) + (size_t)r * (size_t)bytes, f->exch + kExchHgOff + ((size_t)parity * kMaxRanks + (size_t)r) * kHgCap,
-                                (size_t)bytes, cudaMemcpyDeviceToHost, h->stream));
+    XQ_CUDA(cudaMemcpy2DAsync(f->hg_pin + kHgCap, (size_t)n16 * 16, f->exch + kExchHgOff + (size_t)parity * kMaxRanks * kHgCap, kHgCap, (size_t)n16 * 16, (size_t)f->world,
+                              cudaMemcpyDeviceToHost, h->stream));
     XQ_CUDA(cudaStreamSynchronize(h->stream));
+    for (int r = 0; r < f->world; ++r) memcpy(static_cast<uint8_t*>(recv_host) + (size_t)r * (size_t)bytes, f->hg_pin + kHgCap + (size_t)r * (size_t)n16 * 16, (size_t)bytes);
     return dist_check(h);
 }
 

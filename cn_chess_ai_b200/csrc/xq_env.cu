@@ -44,7 +44,8 @@ int fail(int code, const char* fmt, ...) {
 // The list is staged in shared memory (one padded row per thread) and written out with
 // fully coalesced 4-byte stores: 256 B per env.
 __global__ void __launch_bounds__(kThreads) legal_moves_kernel(const xq_env_rec* __restrict__ envs, int64_t n,
-                                                              uint8_t* __restrict__ counts, uint32_t* __restrict__ actions) {
+                                                              uint8_t* __restrict__ counts, uint32_t* __restrict__ actions,
+                                                              const uint8_t* __restrict__ only /* boards the register-resident kernel flagged; null = all */) {
     __shared__ uint32_t s_board[12 * kThreads];
     __shared__ uint32_t s_list[kThreads * kListStride];
     const int tid = threadIdx.x;
@@ -52,7 +53,7 @@ __global__ void __launch_bounds__(kThreads) legal_moves_kernel(const xq_env_rec*
     const int64_t env = env0 + tid;
     uint16_t* my = reinterpret_cast<uint16_t*>(&s_list[tid * kListStride]);
     for (int i = 0; i < 64; ++i) s_list[tid * kListStride + i] = 0xFFFFFFFFu;
-    if (env < n) {
+    if (env < n && (only == nullptr || only[env] != 0)) {
         SmemBoard b{s_board + tid, kThreads};
         b.load(envs + env);
         Meta m; m.load(envs + env);
@@ -62,7 +63,8 @@ __global__ void __launch_bounds__(kThreads) legal_moves_kernel(const xq_env_rec*
     }
     __syncthreads();
     const int64_t live = min((int64_t)kThreads, n - env0);
-    for (int j = tid; j < live * 64; j += kThreads) actions[env0 * 64 + j] = s_list[(j >> 6) * kListStride + (j & 63)];
+    for (int j = tid; j < live * 64; j += kThreads)
+        if (only == nullptr || only[env0 + (j >> 6)] != 0) actions[env0 * 64 + j] = s_list[(j >> 6) * kListStride + (j & 63)];
 }
 
 // K1s: the same list filtered by the opt-in strict legality test (xq_rules.cuh: leaves_general_safe): self-check and
@@ -306,6 +308,22 @@ cudaError_t launch_rollout_team(int team, xq_env_rec* envs, int64_t n, uint64_t 
                                 xq_env_stats* stats, uint8_t* nonstd, cudaStream_t stream);
 cudaError_t launch_rollout_lane(xq_env_rec* envs, int64_t n, uint64_t env_id0, uint64_t seed, int n_plies, xq_trace_rec* trace, xq_env_stats* stats,
                                 uint8_t* nonstd, cudaStream_t stream);
+cudaError_t launch_legal_moves_lane(const xq_env_rec* envs, int64_t n, uint8_t* counts, uint32_t* actions, uint8_t* nonstd, cudaStream_t stream);
+cudaError_t launch_pick_random(const xq_env_rec* envs, int64_t n, uint64_t env_id0, uint64_t seed, const uint8_t* counts, const uint16_t* lists, uint16_t* out,
+                               cudaStream_t stream);
+}
+// ordered action lists of every env into h->d_u8[0] (counts) and h->d_lists ([n][128] u16): the register-resident kernel (xq_rollout_lane.cu)
+// for every board with a standard piece set, then the generic thread-per-board kernel for the boards it flagged (only possible after
+// xq_env_set_boards injected exotic positions).  XQ_LEGAL_LANE=0 runs the generic kernel on every env (A/B runs); same results.
+static int launch_legal_moves(xq_env_s* h) {
+    static const bool lane = [] { const char* e = getenv("XQ_LEGAL_LANE"); return !(e && atoi(e) == 0); }();
+    if (!h->d_lists) XQ_CUDA(cudaMalloc(&h->d_lists, sizeof(uint32_t) * 64 * h->n));
+    if (lane) XQ_CUDA(launch_legal_moves_lane(h->d_envs, h->n, h->d_u8[0], h->d_lists, h->d_nonstd, h->stream));
+    if (!lane || h->maybe_nonstd) {
+        legal_moves_kernel<<<grid_for(h->n, kThreads), kThreads, 0, h->stream>>>(h->d_envs, h->n, h->d_u8[0], h->d_lists, lane ? h->d_nonstd : nullptr);
+        XQ_LAUNCH_CHECK();
+    }
+    return XQ_OK;
 }
 // threads per board of the fused rollout kernel: 1 = rollout_lane_kernel (xq_rollout_lane.cu: the whole board in one thread's registers,
 // no barrier, nothing replicated), the default above 12,288 envs; 4 = rollout_team_kernel<4> (xq_rollout_team.cu), the default below;
@@ -455,9 +473,7 @@ int xq_env_get_boards(xq_env_t h, xq_env_rec* recs, int64_t first, int64_t n) {
 int xq_env_legal_moves(xq_env_t h, uint8_t* counts_host, xq_action* actions_host) {
     XQ_ENV_ENTER(h);
     if (!counts_host || !actions_host) return fail(XQ_ERR_INVALID, "xq_env_legal_moves: null output");
-    if (!h->d_lists) XQ_CUDA(cudaMalloc(&h->d_lists, sizeof(uint32_t) * 64 * h->n));
-    legal_moves_kernel<<<grid_for(h->n, kThreads), kThreads, 0, h->stream>>>(h->d_envs, h->n, h->d_u8[0], h->d_lists);
-    XQ_LAUNCH_CHECK();
+    if (int rc = launch_legal_moves(h)) return rc;
     XQ_CUDA(cudaMemcpyAsync(counts_host, h->d_u8[0], (size_t)h->n, cudaMemcpyDeviceToHost, h->stream));
     XQ_CUDA(cudaMemcpyAsync(actions_host, h->d_lists, sizeof(uint32_t) * 64 * h->n, cudaMemcpyDeviceToHost, h->stream));
     XQ_CUDA(cudaStreamSynchronize(h->stream));
@@ -512,6 +528,36 @@ int xq_env_step(xq_env_t h, const xq_action* actions_host, int32_t* reward_host,
     for (int i = 0; i < 4; ++i)
         if (outs[i]) XQ_CUDA(cudaMemcpyAsync(outs[i], h->d_u8[i], (size_t)h->n, cudaMemcpyDeviceToHost, h->stream));
     XQ_CUDA(cudaStreamSynchronize(h->stream));
+    return XQ_OK;
+}
+
+int xq_env_legal_moves_device(xq_env_t h, void** counts_dev, void** actions_dev) {
+    XQ_ENV_ENTER(h);
+    if (int rc = launch_legal_moves(h)) return rc;
+    if (counts_dev) *counts_dev = h->d_u8[0];
+    if (actions_dev) *actions_dev = h->d_lists;
+    return XQ_OK;
+}
+
+int xq_env_pick_random_device(xq_env_t h, void** actions_dev) {
+    XQ_ENV_ENTER(h);
+    if (!h->d_lists) return fail(XQ_ERR_STATE, "xq_env_pick_random_device: call xq_env_legal_moves_device first");
+    XQ_CUDA(launch_pick_random(h->d_envs, h->n, h->env_id0, h->seed, h->d_u8[0], reinterpret_cast<const uint16_t*>(h->d_lists), h->d_actions, h->stream));
+    if (actions_dev) *actions_dev = h->d_actions;
+    return XQ_OK;
+}
+
+int xq_env_step_device(xq_env_t h, const void* actions_dev, int auto_reset, void** reward_dev, void** done_dev, void** winner_dev, void** captured_dev,
+                       void** valid_dev) {
+    XQ_ENV_ENTER(h);
+    const uint16_t* a = actions_dev ? static_cast<const uint16_t*>(actions_dev) : h->d_actions;
+    step_kernel<<<grid_for(h->n, kThreads), kThreads, 0, h->stream>>>(h->d_envs, h->n, a, h->d_i32, h->d_u8[1], h->d_u8[2], h->d_u8[3], h->d_u8[4], auto_reset);
+    XQ_LAUNCH_CHECK();
+    if (reward_dev) *reward_dev = h->d_i32;
+    if (done_dev) *done_dev = h->d_u8[1];
+    if (winner_dev) *winner_dev = h->d_u8[2];
+    if (captured_dev) *captured_dev = h->d_u8[3];
+    if (valid_dev) *valid_dev = h->d_u8[4];
     return XQ_OK;
 }
 

@@ -66,6 +66,79 @@ __global__ void __launch_bounds__(kLaneMaxThreads) rollout_lane_kernel(xq_env_re
     }
 }
 
+// ---------------------------------------------------------------------------------------------------------------------------------
+// API mode: ChessAI::getAllValidActions(currentPlayer) for every env (src/chessai.cpp:347-368) as ORDERED LISTS in HBM, with the same
+// register-resident generator.  One thread per board: counts + descriptors of the 16 pieces (lane_movegen), every piece's place in the
+// reference order from the byte-SIMD prefix (four dp4a on the (squares, counts) words), its actions written into a per-thread row of
+// shared memory ([u16 pair j][thread], row stride = threads + 1 words: conflict-free for the thread-major writes and for the
+// board-major reads), then the CTA streams the rows out as 16-byte stores, 256 contiguous bytes per board.  No board-in-shared-memory
+// walk, no per-square loop: the loops run over (position, direction) with the same trip structure in every lane.
+// Boards with a non-standard piece set are flagged and left to the generic kernel (legal_moves_kernel, xq_env.cu).
+constexpr int kLmThreads = 128;
+constexpr int kLmStride = kLmThreads + 1;
+__global__ void __launch_bounds__(kLmThreads) legal_moves_lane_kernel(const xq_env_rec* __restrict__ envs, int64_t n, uint8_t* __restrict__ counts,
+                                                                     uint4* __restrict__ actions, uint8_t* __restrict__ nonstd) {
+    __shared__ uint8_t s_slot[32 * kLmThreads];
+    __shared__ uint32_t s_list[64 * kLmStride];
+    __shared__ uint8_t s_ok[kLmThreads];
+    const int tid = threadIdx.x;
+    const int64_t env0 = (int64_t)blockIdx.x * kLmThreads, env = env0 + tid;
+#pragma unroll 8
+    for (int j = 0; j < 64; ++j) s_list[j * kLmStride + tid] = 0xFFFFFFFFu;      // XQ_ACTION_NONE past the count
+    bool ok = env < n;
+    if (ok) {
+        const uint4* rec = reinterpret_cast<const uint4*>(envs + env);
+        uint32_t w[12];
+#pragma unroll
+        for (int i = 0; i < 3; ++i) { const uint4 v = rec[i]; w[4 * i] = v.x; w[4 * i + 1] = v.y; w[4 * i + 2] = v.z; w[4 * i + 3] = v.w; }
+        const int player = (int)((rec[3].x >> 16) & 0xFFu);
+        for (int i = 0; i < 32; ++i) s_slot[i * kLmThreads + tid] = kDeadSq;
+        Bits90 red, black, occT;
+        ok = team_unpack_record(w, red, black, occT, [&](int s, int q) { s_slot[s * kLmThreads + tid] = (uint8_t)q; });
+        if (nonstd) nonstd[env] = ok ? 0 : 1;
+        if (ok) {
+            uint32_t own_sq[4] = {0, 0, 0, 0};
+#pragma unroll
+            for (int pos = 0; pos < 16; ++pos)
+                own_sq[pos >> 2] |= (uint32_t)s_slot[((player ? 16 : 0) + lane_pos_slot(pos)) * kLmThreads + tid] << (8 * (pos & 3));
+            uint32_t sdesc[4], cw[4], dw[4];
+            lane_movegen(own_sq, player ? black : red, player ? red : black, occT, player, sdesc, cw, dw);
+            uint16_t* row = reinterpret_cast<uint16_t*>(s_list);
+            const int cnt = lane_emit_actions(own_sq, player, sdesc, cw, dw, [&](int idx, int a) { row[((idx >> 1) * kLmStride + tid) * 2 + (idx & 1)] = (uint16_t)a; });
+            counts[env] = (uint8_t)cnt;
+        }
+    }
+    s_ok[tid] = ok ? 1 : 0;
+    __syncthreads();
+    const int live = (int)min((int64_t)kLmThreads, n - env0);
+    for (int c = tid; c < live * 16; c += kLmThreads) {      // 16-byte chunk c & 15 of board c >> 4
+        const int b = c >> 4, j = (c & 15) * 4;
+        if (s_ok[b]) actions[(env0 + b) * 16 + (c & 15)] = make_uint4(s_list[j * kLmStride + b], s_list[(j + 1) * kLmStride + b], s_list[(j + 2) * kLmStride + b], s_list[(j + 3) * kLmStride + b]);
+    }
+}
+cudaError_t launch_legal_moves_lane(const xq_env_rec* envs, int64_t n, uint8_t* counts, uint32_t* actions, uint8_t* nonstd, cudaStream_t stream) {
+    legal_moves_lane_kernel<<<(unsigned)((n + kLmThreads - 1) / kLmThreads), kLmThreads, 0, stream>>>(envs, n, counts, reinterpret_cast<uint4*>(actions), nonstd);
+    ++g_launches;
+    return cudaGetLastError();
+}
+
+// DQN::selectAction's exploring branch for every env (src/dqn.cpp:30-34) = the random policy of the fused rollout: list[idx31 % count]
+// with idx31 from xq_rng(seed, env id, the env's ply counter); XQ_ACTION_NONE for an empty list
+__global__ void __launch_bounds__(256) pick_random_kernel(const xq_env_rec* __restrict__ envs, int64_t n, uint64_t env_id0, uint64_t seed,
+                                                         const uint8_t* __restrict__ counts, const uint16_t* __restrict__ lists, uint16_t* __restrict__ out) {
+    const int64_t env = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (env >= n) return;
+    const uint32_t cnt = counts[env];
+    const uint32_t idx31 = (uint32_t)(rng(seed, env_id0 + (uint64_t)env, envs[env].ctr) >> 33);
+    out[env] = cnt ? lists[env * XQ_MAX_ACTIONS + idx31 % cnt] : (uint16_t)XQ_ACTION_NONE;
+}
+cudaError_t launch_pick_random(const xq_env_rec* envs, int64_t n, uint64_t env_id0, uint64_t seed, const uint8_t* counts, const uint16_t* lists, uint16_t* out,
+                               cudaStream_t stream) {
+    pick_random_kernel<<<(unsigned)((n + 255) / 256), 256, 0, stream>>>(envs, n, env_id0, seed, counts, lists, out);
+    ++g_launches;
+    return cudaGetLastError();
+}
+
 cudaError_t launch_rollout_lane(xq_env_rec* envs, int64_t n, uint64_t env_id0, uint64_t seed, int n_plies, xq_trace_rec* trace, xq_env_stats* stats,
                                 uint8_t* nonstd, cudaStream_t stream) {
     const int bs = n <= 148 * 4 * 32 ? 32 : kLaneMaxThreads;

@@ -88,21 +88,19 @@ XQ_HD uint32_t lane_actions_below(const uint32_t (&sq)[4], const uint32_t (&cw)[
     return acc >> 7;
 }
 
-// One ply of ChessAI::train's loop body without the network (src/chessai.cpp:96-119) on one board.
-// magic[d] = team_mod_magic(d) for d = 1..128.  trace (may be null) -> the record of this ply.
-XQ_HD void lane_ply(LaneState& st, LaneStats& a, uint64_t rng_base, const uint32_t* magic, xq_trace_rec* trace) {
+// Every piece of the side to move: move counts (cw, one byte per position), the sliders' descriptors (sdesc, xq_bitboard.cuh) and the
+// leapers' direction masks (dw, one byte per position; dw[0] = 0).  A captured piece (square 127) reads garbage bits, its count is discarded.
+XQ_HD void lane_movegen(const uint32_t (&own_sq)[4], const Bits90& own, const Bits90& opp, const Bits90& occT, int color,
+                        uint32_t (&sdesc)[4], uint32_t (&cw)[4], uint32_t (&dw)[4]) {
     Pos P;
-    P.own = st.own;
-    P.occ = Bits90{st.own.w0 | st.opp.w0, st.own.w1 | st.opp.w1, st.own.w2 | st.opp.w2};
-    P.occT = st.occT;
-    const int color = st.player;
-    // ---- every piece of the side to move: count + descriptor (a captured piece reads garbage bits, its count is discarded) ----
-    uint32_t sdesc[4], cw[4], dw[4];
+    P.own = own;
+    P.occ = Bits90{own.w0 | opp.w0, own.w1 | opp.w1, own.w2 | opp.w2};
+    P.occT = occT;
     {
         int c[4];
 #pragma unroll
         for (int i = 0; i < 4; ++i) {
-            const int q = (int)((st.own_sq[0] >> (8 * i)) & 0xFFu);
+            const int q = (int)((own_sq[0] >> (8 * i)) & 0xFFu);
             const int n = i < 2 ? slider_desc<false>(P, q, &sdesc[i]) : slider_desc<true>(P, q, &sdesc[i]);      // :198-246
             c[i] = q == kDeadSq ? 0 : n;
         }
@@ -114,7 +112,7 @@ XQ_HD void lane_ply(LaneState& st, LaneStats& a, uint64_t rng_base, const uint32
         uint32_t m[4];
 #pragma unroll
         for (int i = 0; i < 4; ++i) {
-            const int q = (int)((st.own_sq[w] >> (8 * i)) & 0xFFu);
+            const int q = (int)((own_sq[w] >> (8 * i)) & 0xFFu);
             const int pos = 4 * w + i;
             uint32_t v;
             if (pos < 6) v = horse_mask(P, q);                       // :248-263
@@ -127,6 +125,61 @@ XQ_HD void lane_ply(LaneState& st, LaneStats& a, uint64_t rng_base, const uint32
         dw[w] = m[0] | (m[1] << 8) | (m[2] << 16) | (m[3] << 24);
         cw[w] = (uint32_t)popc32(m[0]) | ((uint32_t)popc32(m[1]) << 8) | ((uint32_t)popc32(m[2]) << 16) | ((uint32_t)popc32(m[3]) << 24);
     }
+}
+// destination offsets of a leaper at position `pos`, one signed byte per direction in the order of generate*Moves
+// (src/chessboard.cpp:150,163,180,249,267-281); `hi` = directions 4..7 of a Horse
+XQ_HD uint32_t lane_dir_table(int pos, int color, uint32_t* hi) {
+    *hi = (pos == 4 || pos == 5) ? 0xEDEF1113u : 0u;               // Horse: 11,7,-7,-11 | 19,17,-17,-19
+    return (pos == 4 || pos == 5) ? 0xF5F9070Bu
+         : ((pos == 6 || pos == 7) ? 0xECF01014u                    // Elephant: 20,16,-16,-20
+         : ((pos == 8 || pos == 9) ? 0xF6F8080Au                    // Advisor: 10,8,-8,-10
+         : (pos == 10 ? 0xFF01F709u                                 // General: 9,-9,1,-1
+         : (0x0001FF09u ^ (color ? 0xFEu : 0u)))));                 // Soldier: 9,-1,1; a Black Soldier moves towards row 0
+}
+
+// ChessAI::getAllValidActions(side to move) (src/chessai.cpp:347-368) from the movegen words: emit(index, action) for every action, index =
+// its place in the reference-ordered list (squares row-major, then the direction order of generate*Moves); returns the list size.
+// The loops run over positions and directions, the same trip structure in every lane of a warp; only the slide lengths differ.
+template <class EMIT>
+XQ_HD int lane_emit_actions(const uint32_t (&own_sq)[4], int color, const uint32_t (&sdesc)[4], const uint32_t (&cw)[4], const uint32_t (&dw)[4], EMIT&& emit) {
+    uint32_t tot = 0;
+#pragma unroll
+    for (int w = 0; w < 4; ++w) tot = dp4a_u(cw[w], 0x01010101u, tot);
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {              // Chariots and Cannons: per ray the empty squares, then the capture
+        const int sq = (int)((own_sq[0] >> (8 * i)) & 0xFFu);
+        if (((cw[0] >> (8 * i)) & 0xFFu) == 0) continue;
+        int off = (int)lane_actions_below(own_sq, cw, (uint32_t)sq);
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            const int e = (int)((sdesc[i] >> (8 * k)) & 15u), capdist = (int)((sdesc[i] >> (8 * k + 4)) & 15u);
+            const int step = k == 0 ? 1 : (k == 1 ? -1 : (k == 2 ? 9 : -9));
+            for (int d = 1; d <= e; ++d) emit(off++, (int)XQ_ACTION(sq, sq + step * d));
+            if (capdist) emit(off++, (int)XQ_ACTION(sq, sq + step * capdist));
+        }
+    }
+#pragma unroll
+    for (int pos = 4; pos < 16; ++pos) {
+        const int sq = (int)((own_sq[pos >> 2] >> (8 * (pos & 3))) & 0xFFu);
+        const uint32_t m = (dw[pos >> 2] >> (8 * (pos & 3))) & 0xFFu;
+        if (m == 0) continue;
+        int off = (int)lane_actions_below(own_sq, cw, (uint32_t)sq);
+        uint32_t hi;
+        const uint32_t lo = lane_dir_table(pos, color, &hi);
+        const int ndir = pos < 6 ? 8 : (pos < 11 ? 4 : 3);
+#pragma unroll
+        for (int k = 0; k < ndir; ++k)
+            if ((m >> k) & 1u) emit(off++, (int)XQ_ACTION(sq, sq + (int)(int8_t)(uint8_t)((k < 4 ? lo : hi) >> (8 * (k & 3)))));
+    }
+    return (int)tot;
+}
+
+// One ply of ChessAI::train's loop body without the network (src/chessai.cpp:96-119) on one board.
+// magic[d] = team_mod_magic(d) for d = 1..128.  trace (may be null) -> the record of this ply.
+XQ_HD void lane_ply(LaneState& st, LaneStats& a, uint64_t rng_base, const uint32_t* magic, xq_trace_rec* trace) {
+    const int color = st.player;
+    uint32_t sdesc[4], cw[4], dw[4];
+    lane_movegen(st.own_sq, st.own, st.opp, st.occT, color, sdesc, cw, dw);
     uint32_t tot = 0;
 #pragma unroll
     for (int w = 0; w < 4; ++w) tot = dp4a_u(cw[w], 0x01010101u, tot);

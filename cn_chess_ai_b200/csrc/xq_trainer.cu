@@ -18,6 +18,8 @@
 // count -- so all ranks count the same games and stop after the same round; the log file and the autosaves are written by rank 0.
 #include <algorithm>
 #include <chrono>
+#include <stdlib.h>
+#include <string.h>
 #include <string>
 #include <vector>
 
@@ -31,28 +33,46 @@ extern "C" int xq_dqn_dist_allgather(xq_dqn_t h, const void* send_host, int64_t 
 namespace {
 struct RoundHeader { int64_t n_events, n_envs; uint64_t env_id0; int64_t dropped; };      // 32 B per rank per round
 struct GlobalEvent { uint64_t genv; xq_game_event e; };
-constexpr int64_t kEventsPerChunk = 2728;                        // x 24 B = 65,472 B <= the 64 KB message of xq_dqn_dist_allgather
+constexpr int64_t kMsgBytes = 64 << 10;                          // the message of xq_dqn_dist_allgather
+constexpr int64_t kEventsFirst = (kMsgBytes - (int64_t)sizeof(RoundHeader)) / (int64_t)sizeof(xq_game_event);      // events next to the header
+constexpr int64_t kEventsPerChunk = kMsgBytes / (int64_t)sizeof(xq_game_event);
 
-// the finished games of all ranks of this round, in (ply, global env) order
+// the finished games of all ranks of this round, in (ply, global env) order.  ONE all-gather in the common case: the message is the
+// round header followed by as many events as fit (2,729); only a round with more finished games on some rank needs further calls.
 int gather_round(xq_dqn_t h, int world, const std::vector<xq_game_event>& ev, int64_t n, uint64_t env_id0, int64_t n_envs, int64_t dropped,
-                 std::vector<GlobalEvent>* merged, int64_t* envs_total, int64_t* dropped_total) {
-    std::vector<RoundHeader> hd((size_t)world);
+                 std::vector<GlobalEvent>* merged, int64_t* envs_total, int64_t* dropped_total, std::vector<uint8_t>* send, std::vector<uint8_t>* recv) {
+    send->assign((size_t)kMsgBytes, 0);
+    recv->resize((size_t)(kMsgBytes * world));
     const RoundHeader mine{n, n_envs, env_id0, dropped};
-    if (int rc = xq_dqn_dist_allgather(h, &mine, sizeof(mine), hd.data())) return rc;
+    memcpy(send->data(), &mine, sizeof(mine));
+    const int64_t m0 = std::min(n, kEventsFirst);
+    if (m0 > 0) memcpy(send->data() + sizeof(RoundHeader), ev.data(), (size_t)m0 * sizeof(xq_game_event));
+    // fixed message size (the ranks cannot know each other's counts beforehand): 64 KB is ~0.1 us of NVLink bandwidth
+    if (int rc = xq_dqn_dist_allgather(h, send->data(), kMsgBytes, recv->data())) return rc;
+    std::vector<RoundHeader> hd((size_t)world);
     int64_t max_n = 0;
     *envs_total = 0; *dropped_total = 0;
-    for (const RoundHeader& x : hd) { max_n = std::max(max_n, x.n_events); *envs_total += x.n_envs; *dropped_total += x.dropped; }
     merged->clear();
-    std::vector<xq_game_event> send((size_t)kEventsPerChunk), recv((size_t)(kEventsPerChunk * world));
-    for (int64_t c0 = 0; c0 < max_n; c0 += kEventsPerChunk) {
+    for (int r = 0; r < world; ++r) {
+        memcpy(&hd[(size_t)r], recv->data() + (size_t)r * kMsgBytes, sizeof(RoundHeader));
+        max_n = std::max(max_n, hd[(size_t)r].n_events); *envs_total += hd[(size_t)r].n_envs; *dropped_total += hd[(size_t)r].dropped;
+        const int64_t mr = std::min(hd[(size_t)r].n_events, kEventsFirst);
+        for (int64_t i = 0; i < mr; ++i) {
+            xq_game_event e;
+            memcpy(&e, recv->data() + (size_t)r * kMsgBytes + sizeof(RoundHeader) + (size_t)i * sizeof(xq_game_event), sizeof(e));
+            merged->push_back(GlobalEvent{hd[(size_t)r].env_id0 + e.env, e});
+        }
+    }
+    for (int64_t c0 = kEventsFirst; c0 < max_n; c0 += kEventsPerChunk) {
         const int64_t m = std::max<int64_t>(0, std::min(kEventsPerChunk, n - c0));
-        std::fill(send.begin(), send.end(), xq_game_event{});
-        std::copy(ev.begin() + (ptrdiff_t)std::min(c0, n), ev.begin() + (ptrdiff_t)(std::min(c0, n) + m), send.begin());
-        if (int rc = xq_dqn_dist_allgather(h, send.data(), kEventsPerChunk * (int64_t)sizeof(xq_game_event), recv.data())) return rc;
+        send->assign((size_t)kMsgBytes, 0);
+        if (m > 0) memcpy(send->data(), ev.data() + c0, (size_t)m * sizeof(xq_game_event));
+        if (int rc = xq_dqn_dist_allgather(h, send->data(), kMsgBytes, recv->data())) return rc;
         for (int r = 0; r < world; ++r) {
             const int64_t mr = std::max<int64_t>(0, std::min(kEventsPerChunk, hd[(size_t)r].n_events - c0));
             for (int64_t i = 0; i < mr; ++i) {
-                const xq_game_event& e = recv[(size_t)(r * kEventsPerChunk + i)];
+                xq_game_event e;
+                memcpy(&e, recv->data() + (size_t)r * kMsgBytes + (size_t)i * sizeof(xq_game_event), sizeof(e));
                 merged->push_back(GlobalEvent{hd[(size_t)r].env_id0 + e.env, e});
             }
         }
@@ -62,6 +82,7 @@ int gather_round(xq_dqn_t h, int world, const std::vector<xq_game_event>& ev, in
     });
     return XQ_OK;
 }
+double now_s() { return std::chrono::duration<double>(std::chrono::steady_clock::now().time_since_epoch()).count(); }
 }  // namespace
 
 extern "C" int xq_train_run(xq_dqn_t h, xq_env_t env, xq_replay_t r, const xq_train_config* cfg, xq_game_completed_fn cb, void* user,
@@ -80,6 +101,9 @@ extern "C" int xq_train_run(xq_dqn_t h, xq_env_t env, xq_replay_t r, const xq_tr
     if (int rc = xq_env_enable_game_events(env, cap)) return rc;
     std::vector<xq_game_event> ev((size_t)cap);
     std::vector<GlobalEvent> merged;
+    std::vector<uint8_t> msg_send, msg_recv;
+    const bool profile = getenv("XQ_TRAIN_PROFILE") != nullptr;      // where a round's wall time goes (stderr)
+    double t_collect = 0, t_update = 0, t_drain = 0, t_gather = 0, t_host = 0;
     FILE* log = nullptr;
     if (cfg->log_path && rank == 0) {
         log = fopen(cfg->log_path, "a");                             // QIODevice::Append (src/chessai.cpp:197-201)
@@ -93,7 +117,9 @@ extern "C" int xq_train_run(xq_dqn_t h, xq_env_t env, xq_replay_t r, const xq_tr
     int64_t next_sync = cfg->target_sync_plies > 0 ? cfg->target_sync_plies : -1;
     int rc = XQ_OK;
     while (rc == XQ_OK && rep.games < cfg->n_games) {
+        double tp = now_s();
         if ((rc = xq_selfplay_collect(h, env, r, cfg->plies_per_round, cfg->eps, cfg->train_done))) break;
+        t_collect += now_s() - tp; tp = now_s();
         rep.plies += cfg->plies_per_round;
         if (cfg->updates_per_round > 0) {
             int64_t size = 0;
@@ -110,12 +136,15 @@ extern "C" int xq_train_run(xq_dqn_t h, xq_env_t env, xq_replay_t r, const xq_tr
             next_sync += cfg->target_sync_plies;
         }
         if (rc) break;
+        t_update += now_s() - tp; tp = now_s();
         int64_t n = 0, dropped = 0, envs_round = n_envs;
         if ((rc = xq_env_drain_game_events(env, ev.data(), cap, &n, &dropped))) break;
+        t_drain += now_s() - tp; tp = now_s();
         if (world > 1) {         // the round's games of ALL ranks, merged; also where a timed-out exchange surfaces (sticky status)
-            if ((rc = gather_round(h, world, ev, n, ei.env_id0, n_envs, dropped, &merged, &envs_round, &dropped))) break;
+            if ((rc = gather_round(h, world, ev, n, ei.env_id0, n_envs, dropped, &merged, &envs_round, &dropped, &msg_send, &msg_recv))) break;
             n = (int64_t)merged.size();
         }
+        t_gather += now_s() - tp; tp = now_s();
         rep.transitions += envs_round * (int64_t)cfg->plies_per_round;
         rep.events_dropped += dropped;
         const int64_t games_before = rep.games;
@@ -141,7 +170,9 @@ extern "C" int xq_train_run(xq_dqn_t h, xq_env_t env, xq_replay_t r, const xq_tr
             }
             ++rep.autosaves;
         }
+        t_host += now_s() - tp;
     }
+    if (profile) fprintf(stderr, "xq_train_run rank %d: collect (enqueue) %.3f s, updates (enqueue) %.3f s, drain (sync) %.3f s, gather %.3f s, host %.3f s over %lld rounds\n", rank, t_collect, t_update, t_drain, t_gather, t_host, (long long)(rep.plies / cfg->plies_per_round));
     if (log) fclose(log);
     if (rc == XQ_OK) rc = xq_env_sync(env);
     rep.seconds = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();

@@ -106,6 +106,15 @@ class BatchedEnv:
         check(self._L.xq_env_rollout_random_io(self._h, ptr(boards_in), n_plies, ptr(boards_out), ptr(tr), ptr(stats)))
         return stats[0], tr
 
+    def api_ply_device(self, auto_reset=True):
+        """one ply of the API-mode path entirely on the device: ordered lists -> random-policy pick -> movePiece / reward / terminal"""
+        check(self._L.xq_env_legal_moves_device(self._h, None, None))
+        check(self._L.xq_env_pick_random_device(self._h, None))
+        check(self._L.xq_env_step_device(self._h, None, 1 if auto_reset else 0, None, None, None, None, None))
+
+    def legal_moves_device(self):
+        check(self._L.xq_env_legal_moves_device(self._h, None, None))
+
     def rollout_random_async(self, n_plies):
         check(self._L.xq_env_rollout_random_async(self._h, n_plies))
 

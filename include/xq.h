@@ -122,6 +122,16 @@ int xq_env_is_valid_move(xq_env_t h, const int32_t* moves_host, uint8_t* valid_h
  * Any output pointer may be NULL. */
 int xq_env_step(xq_env_t h, const xq_action* actions_host, int32_t* reward_host, uint8_t* done_host,
                 uint8_t* winner_host, uint8_t* captured_host, uint8_t* valid_host, int auto_reset);
+/* API mode without host traffic (a caller whose policy also lives on the device): the same three steps, asynchronous on the handle's stream,
+ * results in device buffers owned by the handle (valid until the next call of the same kind; any output pointer may be NULL).
+ * xq_env_legal_moves_device: counts u8 [n], actions xq_action [n][XQ_MAX_ACTIONS] (xq_env_legal_moves).
+ * xq_env_pick_random_device: the random policy of xq_env_rollout_random on the lists of the last xq_env_legal_moves_device call:
+ *   action = list[idx31 % count] with idx31 from xq_rng(seed, env id, the env's ply counter) (XQ_ACTION_NONE for an empty list) -> xq_action [n].
+ * xq_env_step_device: xq_env_step on device actions (NULL = the actions xq_env_pick_random_device chose); reward i32 [n], the rest u8 [n]. */
+int xq_env_legal_moves_device(xq_env_t h, void** counts_dev, void** actions_dev);
+int xq_env_pick_random_device(xq_env_t h, void** actions_dev);
+int xq_env_step_device(xq_env_t h, const void* actions_dev, int auto_reset, void** reward_dev, void** done_dev, void** winner_dev,
+                       void** captured_dev, void** valid_dev);
 /* Fused random-policy self-play: n_plies iterations of the ChessAI::train loop body without the
  * network (src/chessai.cpp:96-119): ordered list -> list[idx31 % n] -> movePiece -> evaluateBoard
  * -> checkGameOver, reset on terminal.  One launch; boards stay on chip between plies.

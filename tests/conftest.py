@@ -59,6 +59,7 @@ def hostsim():
     H.hs_act_team.argtypes = [P, C.c_long, C.c_uint64, C.c_uint64, P, C.c_uint32, P]
     H.hs_team_rollout.argtypes = [C.c_int, P, C.c_long, C.c_uint64, C.c_uint64, C.c_int, P, P]
     H.hs_lane_rollout.argtypes = [P, C.c_long, C.c_uint64, C.c_uint64, C.c_int, P, P]
+    H.hs_lane_all_actions.argtypes = [P, C.c_long, P, P]
     H.hs_act_quant.argtypes = [P, C.c_long, P]
     return H
 

@@ -178,6 +178,28 @@ extern "C" {
 int hs_act_team(const xq_env_rec* recs, long n, uint64_t env_id0, uint64_t seed, const float* q90, uint32_t eps_thr, uint16_t* actions) {
     return act_team_host(recs, n, env_id0, seed, q90, eps_thr, actions);
 }
+// the register-resident list kernel's generator + emission (legal_moves_lane_kernel); returns the number of non-standard boards (skipped)
+int hs_lane_all_actions(const xq_env_rec* recs, long n, uint8_t* counts, uint16_t* actions) {
+    int nonstd = 0;
+    for (long i = 0; i < n; ++i) {
+        uint16_t* out = actions + i * XQ_MAX_ACTIONS;
+        for (int k = 0; k < XQ_MAX_ACTIONS; ++k) out[k] = XQ_ACTION_NONE;
+        counts[i] = 0xFF;
+        uint8_t slot[32];
+        for (int k = 0; k < 32; ++k) slot[k] = xq::kDeadSq;
+        uint32_t w[12];
+        std::memcpy(w, recs[i].sq, 48);
+        xq::Bits90 red, black, occT;
+        if (!xq::team_unpack_record(w, red, black, occT, [&](int s, int q) { slot[s] = (uint8_t)q; })) { ++nonstd; continue; }
+        const int player = recs[i].player;
+        uint32_t own_sq[4] = {0, 0, 0, 0};
+        for (int pos = 0; pos < 16; ++pos) own_sq[pos >> 2] |= (uint32_t)slot[(player ? 16 : 0) + xq::lane_pos_slot(pos)] << (8 * (pos & 3));
+        uint32_t sdesc[4], cw[4], dw[4];
+        xq::lane_movegen(own_sq, player ? black : red, player ? red : black, occT, player, sdesc, cw, dw);
+        counts[i] = (uint8_t)xq::lane_emit_actions(own_sq, player, sdesc, cw, dw, [&](int idx, int a) { out[idx] = (uint16_t)a; });
+    }
+    return nonstd;
+}
 int hs_lane_rollout(xq_env_rec* recs, long n, uint64_t env_id0, uint64_t seed, int n_plies, xq_trace_rec* trace, xq_env_stats* stats) {
     return lane_rollout_host(recs, n, env_id0, seed, n_plies, trace, stats);
 }

@@ -171,6 +171,39 @@ def test_board_per_thread_kernel_traces(xq, O, oracle_lib):
     assert same_recs(env.get_boards(), ref) and stats.tobytes() == st0[0].tobytes()
 
 
+def test_api_mode_on_the_device_equals_fused_rollout(xq, O, oracle_lib):
+    """the API-mode path without host traffic -- xq_env_legal_moves_device -> xq_env_pick_random_device -> xq_env_step_device, three
+    launches per ply -- walks the very trajectories of the fused kernel and of the oracle (same draws: xq_rng(seed, env id, ply counter));
+    the lists of the register-resident list kernel against the oracle's on the way, standard and injected boards"""
+    n, plies, seed, id0 = 5000, 150, 13, 40
+    env = xq.BatchedEnv(n, seed=seed, env_id0=id0)
+    for p in range(plies):
+        if p in (0, 37, 149):
+            counts, acts = env.legal_moves()
+            cur = env.get_boards()
+            c0 = np.zeros(n, np.uint8); a0 = np.zeros((n, 128), np.uint16)
+            oracle_lib.xqo_batch_all_actions(cur.ctypes.data, n, c0, a0)
+            a0[np.arange(128)[None, :] >= c0[:, None]] = 0xFFFF
+            assert (counts == c0).all() and (acts == a0).all()
+        env.api_ply_device()
+    ref = O.new_envs(n)
+    st0 = np.zeros(1, O.STATS_DTYPE)
+    oracle_lib.xqo_rollout_random(ref.ctypes.data, n, id0, seed, plies, None, st0.ctypes.data)
+    assert same_recs(env.get_boards(), ref)
+    fused = xq.BatchedEnv(n, seed=seed, env_id0=id0)
+    fused.rollout_random(plies)
+    assert same_recs(env.get_boards(), fused.get_boards())
+    # injected boards: arbitrary piece sets go through the generic kernel, standard ones through the register-resident kernel, in one call
+    recs = np.concatenate([harvest_positions(O, 300, 7, 23), random_boards(O, 2001, seed=3)])
+    env = xq.BatchedEnv(len(recs), seed=1)
+    env.set_boards(recs)
+    counts, acts = env.legal_moves()
+    c0 = np.zeros(len(recs), np.uint8); a0 = np.zeros((len(recs), 128), np.uint16)
+    oracle_lib.xqo_batch_all_actions(recs.ctypes.data, len(recs), c0, a0)
+    a0[np.arange(128)[None, :] >= c0[:, None]] = 0xFFFF
+    assert (counts == c0).all() and (acts == a0).all()
+
+
 def test_step_rejects_invalid_moves(xq, O, oracle_lib):
     recs = np.concatenate([harvest_positions(O, 256, 4, 31), random_boards(O, 1024, seed=8)])
     n = len(recs)

@@ -122,6 +122,22 @@ def test_team_rollout_phases(O, oracle_lib, hostsim):
         _team_vs_oracle(O, oracle_lib, hostsim, team, fin, 3, 9, 40)
 
 
+def test_lane_list_emission(O, oracle_lib, hostsim, golden):
+    """xq_rollout_lane.cuh (legal_moves_lane_kernel): register-resident generator + reference-order emission == the oracle's ordered
+    lists on reachable positions over whole games (both colours, captured pieces, finished boards keep their lists), on arbitrary
+    boards with a standard piece set (the others are flagged for the generic kernel) and on the golden positions"""
+    for recs in (harvest_positions(O, 800, 45, 5), random_boards(O, 4000, seed=21), recs_from_codes(O, golden["pos_codes"], golden["pos_meta"])):
+        n = len(recs)
+        c1, a1 = _oracle_lists(oracle_lib, recs)
+        c2 = np.zeros(n, np.uint8)
+        a2 = np.zeros((n, 128), np.uint16)
+        nonstd = hostsim.hs_lane_all_actions(recs.ctypes.data, n, c2.ctypes.data, a2.ctypes.data)
+        std = c2 != 0xFF
+        assert nonstd == int((~std).sum()) and std.sum() > 500
+        bad = np.nonzero(std & ((c1 != c2) | (a1 != a2).any(1)))[0]
+        assert len(bad) == 0, f"{len(bad)} boards differ, first {bad[:4]}"
+
+
 def test_lane_rollout_ply(O, oracle_lib, hostsim):
     """xq_rollout_lane.cuh (rollout_lane_kernel): the board-per-thread ply run on the host reproduces the oracle's fused rollout record
     for record -- same cases as the team kernel (from the opening over several games, resumed mid-game, finished boards)"""
