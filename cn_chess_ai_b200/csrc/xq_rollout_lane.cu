@@ -75,18 +75,16 @@ __global__ void __launch_bounds__(kLaneMaxThreads) rollout_lane_kernel(xq_env_re
 // walk, no per-square loop: the loops run over (position, direction) with the same trip structure in every lane.
 // Boards with a non-standard piece set are flagged and left to the generic kernel (legal_moves_kernel, xq_env.cu).
 constexpr int kLmThreads = 128;
-constexpr int kLmStride = kLmThreads + 1;
+constexpr int kLmRow = 65;                                   // words per thread row: 64 pairs of actions + 1 (odd stride: bank = (thread + word) % 32)
 __global__ void __launch_bounds__(kLmThreads) legal_moves_lane_kernel(const xq_env_rec* __restrict__ envs, int64_t n, uint8_t* __restrict__ counts,
                                                                      uint4* __restrict__ actions, uint8_t* __restrict__ nonstd) {
     __shared__ uint8_t s_slot[32 * kLmThreads];
-    __shared__ uint32_t s_list[64 * kLmStride];
-    __shared__ uint8_t s_ok[kLmThreads];
+    __shared__ uint32_t s_list[kLmThreads * kLmRow];
+    __shared__ uint8_t s_cnt[kLmThreads];                    // list size; 0xFF = not produced here (tail of the grid, non-standard piece set)
     const int tid = threadIdx.x;
     const int64_t env0 = (int64_t)blockIdx.x * kLmThreads, env = env0 + tid;
-#pragma unroll 8
-    for (int j = 0; j < 64; ++j) s_list[j * kLmStride + tid] = 0xFFFFFFFFu;      // XQ_ACTION_NONE past the count
-    bool ok = env < n;
-    if (ok) {
+    int cnt = 0xFF;
+    if (env < n) {
         const uint4* rec = reinterpret_cast<const uint4*>(envs + env);
         uint32_t w[12];
 #pragma unroll
@@ -94,7 +92,7 @@ __global__ void __launch_bounds__(kLmThreads) legal_moves_lane_kernel(const xq_e
         const int player = (int)((rec[3].x >> 16) & 0xFFu);
         for (int i = 0; i < 32; ++i) s_slot[i * kLmThreads + tid] = kDeadSq;
         Bits90 red, black, occT;
-        ok = team_unpack_record(w, red, black, occT, [&](int s, int q) { s_slot[s * kLmThreads + tid] = (uint8_t)q; });
+        const bool ok = team_unpack_record(w, red, black, occT, [&](int s, int q) { s_slot[s * kLmThreads + tid] = (uint8_t)q; });
         if (nonstd) nonstd[env] = ok ? 0 : 1;
         if (ok) {
             uint32_t own_sq[4] = {0, 0, 0, 0};
@@ -103,17 +101,25 @@ __global__ void __launch_bounds__(kLmThreads) legal_moves_lane_kernel(const xq_e
                 own_sq[pos >> 2] |= (uint32_t)s_slot[((player ? 16 : 0) + lane_pos_slot(pos)) * kLmThreads + tid] << (8 * (pos & 3));
             uint32_t sdesc[4], cw[4], dw[4];
             lane_movegen(own_sq, player ? black : red, player ? red : black, occT, player, sdesc, cw, dw);
-            uint16_t* row = reinterpret_cast<uint16_t*>(s_list);
-            const int cnt = lane_emit_actions(own_sq, player, sdesc, cw, dw, [&](int idx, int a) { row[((idx >> 1) * kLmStride + tid) * 2 + (idx & 1)] = (uint16_t)a; });
+            uint16_t* row = reinterpret_cast<uint16_t*>(s_list + tid * kLmRow);
+            cnt = lane_emit_actions(own_sq, player, sdesc, cw, dw, [&](int idx, int a, bool live) { if (live) row[idx] = (uint16_t)a; });
             counts[env] = (uint8_t)cnt;
         }
     }
-    s_ok[tid] = ok ? 1 : 0;
+    s_cnt[tid] = (uint8_t)cnt;
     __syncthreads();
     const int live = (int)min((int64_t)kLmThreads, n - env0);
-    for (int c = tid; c < live * 16; c += kLmThreads) {      // 16-byte chunk c & 15 of board c >> 4
-        const int b = c >> 4, j = (c & 15) * 4;
-        if (s_ok[b]) actions[(env0 + b) * 16 + (c & 15)] = make_uint4(s_list[j * kLmStride + b], s_list[(j + 1) * kLmStride + b], s_list[(j + 2) * kLmStride + b], s_list[(j + 3) * kLmStride + b]);
+    for (int c = tid; c < live * 16; c += kLmThreads) {      // 16-byte chunk c & 15 of board c >> 4: actions 8 (c & 15) .. + 7
+        const int b = c >> 4, j = (c & 15) * 4, cb = s_cnt[b];
+        if (cb == 0xFF) continue;
+        uint32_t v[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {                        // entries past the count are XQ_ACTION_NONE (the rows are not pre-filled)
+            const int a0 = 2 * (j + u);
+            const uint32_t x = s_list[b * kLmRow + j + u];
+            v[u] = a0 + 1 < cb ? x : (a0 < cb ? (x | 0xFFFF0000u) : 0xFFFFFFFFu);
+        }
+        actions[(env0 + b) * 16 + (c & 15)] = make_uint4(v[0], v[1], v[2], v[3]);
     }
 }
 cudaError_t launch_legal_moves_lane(const xq_env_rec* envs, int64_t n, uint8_t* counts, uint32_t* actions, uint8_t* nonstd, cudaStream_t stream) {

@@ -137,9 +137,11 @@ XQ_HD uint32_t lane_dir_table(int pos, int color, uint32_t* hi) {
          : (0x0001FF09u ^ (color ? 0xFEu : 0u)))));                 // Soldier: 9,-1,1; a Black Soldier moves towards row 0
 }
 
-// ChessAI::getAllValidActions(side to move) (src/chessai.cpp:347-368) from the movegen words: emit(index, action) for every action, index =
-// its place in the reference-ordered list (squares row-major, then the direction order of generate*Moves); returns the list size.
-// The loops run over positions and directions, the same trip structure in every lane of a warp; only the slide lengths differ.
+// ChessAI::getAllValidActions(side to move) (src/chessai.cpp:347-368) from the movegen words: emit(index, action, live) for every SLOT
+// (piece, direction, distance) a piece could use; `live` slots are the actions, `index` their place in the reference-ordered list (squares
+// row-major, then the direction order of generate*Moves, distance ascending along a ray); returns the list size.
+// Straight-line: every lane of a warp walks the same 198 slots with predicated stores -- no data-dependent loop, nothing diverges
+// (a first version looped `for d = 1..empties` per ray: a warp then ran the longest slide of its 32 boards around a 13-instruction body).
 template <class EMIT>
 XQ_HD int lane_emit_actions(const uint32_t (&own_sq)[4], int color, const uint32_t (&sdesc)[4], const uint32_t (&cw)[4], const uint32_t (&dw)[4], EMIT&& emit) {
     uint32_t tot = 0;
@@ -148,28 +150,33 @@ XQ_HD int lane_emit_actions(const uint32_t (&own_sq)[4], int color, const uint32
 #pragma unroll
     for (int i = 0; i < 4; ++i) {              // Chariots and Cannons: per ray the empty squares, then the capture
         const int sq = (int)((own_sq[0] >> (8 * i)) & 0xFFu);
-        if (((cw[0] >> (8 * i)) & 0xFFu) == 0) continue;
+        const bool alive = ((cw[0] >> (8 * i)) & 0xFFu) != 0;      // a captured slider's descriptor is garbage
         int off = (int)lane_actions_below(own_sq, cw, (uint32_t)sq);
 #pragma unroll
         for (int k = 0; k < 4; ++k) {
-            const int e = (int)((sdesc[i] >> (8 * k)) & 15u), capdist = (int)((sdesc[i] >> (8 * k + 4)) & 15u);
+            const int e = alive ? (int)((sdesc[i] >> (8 * k)) & 15u) : 0, capdist = alive ? (int)((sdesc[i] >> (8 * k + 4)) & 15u) : 0;
             const int step = k == 0 ? 1 : (k == 1 ? -1 : (k == 2 ? 9 : -9));
-            for (int d = 1; d <= e; ++d) emit(off++, (int)XQ_ACTION(sq, sq + step * d));
-            if (capdist) emit(off++, (int)XQ_ACTION(sq, sq + step * capdist));
+            constexpr int kMaxSlide[4] = {8, 8, 9, 9};
+#pragma unroll
+            for (int d = 1; d <= kMaxSlide[k]; ++d) emit(off + d - 1, (int)XQ_ACTION(sq, sq + step * d), d <= e);
+            emit(off + e, (int)XQ_ACTION(sq, sq + step * capdist), capdist != 0);
+            off += e + (capdist ? 1 : 0);
         }
     }
 #pragma unroll
     for (int pos = 4; pos < 16; ++pos) {
         const int sq = (int)((own_sq[pos >> 2] >> (8 * (pos & 3))) & 0xFFu);
-        const uint32_t m = (dw[pos >> 2] >> (8 * (pos & 3))) & 0xFFu;
-        if (m == 0) continue;
+        const uint32_t m = (dw[pos >> 2] >> (8 * (pos & 3))) & 0xFFu;      // 0 for a captured piece
         int off = (int)lane_actions_below(own_sq, cw, (uint32_t)sq);
         uint32_t hi;
         const uint32_t lo = lane_dir_table(pos, color, &hi);
         const int ndir = pos < 6 ? 8 : (pos < 11 ? 4 : 3);
 #pragma unroll
-        for (int k = 0; k < ndir; ++k)
-            if ((m >> k) & 1u) emit(off++, (int)XQ_ACTION(sq, sq + (int)(int8_t)(uint8_t)((k < 4 ? lo : hi) >> (8 * (k & 3)))));
+        for (int k = 0; k < ndir; ++k) {
+            const bool live = (m >> k) & 1u;
+            emit(off, (int)XQ_ACTION(sq, sq + (int)(int8_t)(uint8_t)((k < 4 ? lo : hi) >> (8 * (k & 3)))), live);
+            off += live ? 1 : 0;
+        }
     }
     return (int)tot;
 }

@@ -196,7 +196,7 @@ int hs_lane_all_actions(const xq_env_rec* recs, long n, uint8_t* counts, uint16_
         for (int pos = 0; pos < 16; ++pos) own_sq[pos >> 2] |= (uint32_t)slot[(player ? 16 : 0) + xq::lane_pos_slot(pos)] << (8 * (pos & 3));
         uint32_t sdesc[4], cw[4], dw[4];
         xq::lane_movegen(own_sq, player ? black : red, player ? red : black, occT, player, sdesc, cw, dw);
-        counts[i] = (uint8_t)xq::lane_emit_actions(own_sq, player, sdesc, cw, dw, [&](int idx, int a) { out[idx] = (uint16_t)a; });
+        counts[i] = (uint8_t)xq::lane_emit_actions(own_sq, player, sdesc, cw, dw, [&](int idx, int a, bool live) { if (live) out[idx] = (uint16_t)a; });
     }
     return nonstd;
 }
