@@ -103,6 +103,36 @@ def cpu_reference_leg(n_threads, plies_per_thread, seed=1):
     return tot.value / s, kind, what, tot.value, s
 
 
+def cpu_legs(cores):
+    """BASELINE.md section 4 on this box's host cores, through the reference's own classes (oracle/_ref): env-only on 1 core; config (i)
+    random policy + one CPU forward per ply on 1 core and on all cores; config (iii) epsilon-greedy with the CPU forward on 1 core;
+    config (iv) one TD step per ply (ChessAI::train) with the network on 1 core.  Bounded samples (a few seconds each); plies/s."""
+    import ctypes as C
+    from oracle import loader as O
+    R = O.ref()
+    if R is None:
+        return {"unavailable": "oracle/_ref is not built"}
+    out = {}
+    tot = C.c_long()
+    s = R.ref_bench_rollout_random(1, 400000, 1, C.byref(tot))
+    out["env_only_1_core"] = {"steps_per_s": tot.value / s, "sample": "400000 random-policy plies, 1 thread"}
+    R.ref_bench_policy.restype = C.c_double
+    R.ref_bench_policy.argtypes = [C.c_int, C.c_int, C.c_double, C.c_uint64, C.POINTER(C.c_long), C.POINTER(C.c_long)]
+    for name, mode, nt, what in (("config_i_forward_per_ply_1_core", 0, 1, "configs[0]: random policy + one FP64 {1260,128,8100} forward per ply on the CPU"),
+                                 ("config_i_forward_per_ply_all_cores", 0, cores, "the same, one independent board + network per thread"),
+                                 ("config_iii_eps_greedy_1_core", 1, 1, "DQN::selectAction(eps = 0.1): a CPU forward on 90 % of the plies")):
+        p, g = C.c_long(), C.c_long()
+        s = R.ref_bench_policy(mode, nt, 4.0, 7, C.byref(p), C.byref(g))
+        out[name] = {"steps_per_s": p.value / s, "threads": nt, "plies": p.value, "games": g.value, "seconds": s, "what": what,
+                     "seconds_for_1000_games": 1000 * 153.25 / (p.value / s) if p.value else None}
+    try:
+        r = subprocess.run([sys.executable, "-m", "oracle.ref_train_bench", "2", "--cpu"], cwd=ROOT, capture_output=True, text=True, timeout=120)
+        out["config_iv_td_step_per_ply_1_core"] = json.loads(r.stdout.strip().splitlines()[-1])
+    except Exception as ex:
+        out["config_iv_td_step_per_ply_1_core"] = {"unavailable": f"{type(ex).__name__}: {ex}"[:200]}
+    return out
+
+
 def reference_train_leg(games=3, timeout=240):
     """the reference's OWN training loop (ChessAI::train: batch 1, its own CUDA kernels from src/dqn.cu compiled unmodified when a GPU
     is visible, else the CPU definition of its NeuralNetwork) for a bounded number of games, in a subprocess (oracle/ref_train_bench.py)"""
@@ -394,7 +424,7 @@ def main():
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         cores = os.cpu_count() or 1
         v, kind, what, _, _ = cpu_reference_leg(cores, 400000)
-        line["cpu_baseline"] = {"value": v, "unit": "steps/s", "cores": cores, "kind": kind, "sample": what}
+        line["cpu_baseline"] = {"value": v, "unit": "steps/s", "cores": cores, "kind": kind, "sample": what, "legs": cpu_legs(cores)}
 
     if rank == 0:
         emit(line)

@@ -5,6 +5,7 @@
 //   chessboard.h:8-31   PieceType / PieceColor / ChessPiece / PieceScore
 //   chessboard.h:33-57  ChessBoard        -> one-env view of xq_env_* (N = 1)
 //   action.h:4-11       Action
+//   dqn.h:43-74         NeuralNetwork     -> the online network of an xq_dqn handle (FP64 path), public host_weights / host_biases / offsets
 //   dqn.h:97-110        DQN               -> xq_dqn_* (FP64 path; the batched tensor-core path is xq_dqn_td_update ...)
 //   chessai.h:21-37     ChessAI           -> getAIMove / train / startSelfPlay over the batched engine
 //
@@ -17,6 +18,7 @@
 #include <cstdint>
 #include <functional>
 #include <memory>
+#include <random>
 #include <stdexcept>
 #include <string>
 #include <utility>
@@ -123,6 +125,89 @@ private:
     void push() { xq_adapter::check(xq_env_set_boards(env_, &rec_, 0, 1)); }
     xq_env_t env_ = nullptr;
     xq_env_rec rec_{};
+};
+
+// NeuralNetwork (include/dqn.h:43-74, src/dqn.cu): flat FP64 host copies `host_weights` ([layer][out][in] row-major, layers concatenated) and
+// `host_biases` with their per-layer offsets are PUBLIC in the reference -- DQN::saveModel reads them directly (src/dqn.cpp:87-95) -- and the device
+// copy is a separate object: forward / backpropagate work on the DEVICE parameters and never touch the host vectors (src/dqn.cu:199-260, 323-467),
+// copyToDevice / copyFromDevice move between the two (:480-492), copyWeightsAndBiasesFrom takes the other network's HOST copy (:507-515).
+// Initialisation: U(-0.05, 0.05) weights from mt19937, zero biases, fill order layer -> out -> in (:96-123); the reference seeds from
+// random_device, here a seed may be given (default: random_device, like the reference).
+class NeuralNetwork {
+public:
+    std::vector<double> host_weights, host_biases;
+    std::vector<size_t> weightOffsets, biasOffsets;
+    std::vector<int> layerSizes;
+
+    NeuralNetwork() = delete;
+    explicit NeuralNetwork(const std::vector<int>& layerSizes_, uint64_t seed = 0, bool seeded = false) : layerSizes(layerSizes_), seed_(seed), seeded_(seeded) {
+        if (layerSizes.size() < 2) throw std::invalid_argument("NeuralNetwork must have at least two layers (input and output).");      // :17-19
+        create();
+        initializeHostWeightsAndBiases();
+        copyToDevice();
+    }
+    NeuralNetwork(const NeuralNetwork& o) : host_weights(o.host_weights), host_biases(o.host_biases), weightOffsets(o.weightOffsets), biasOffsets(o.biasOffsets),
+                                           layerSizes(o.layerSizes), seed_(o.seed_), seeded_(o.seeded_) { create(); copyToDevice(); }
+    NeuralNetwork(NeuralNetwork&& o) noexcept : host_weights(std::move(o.host_weights)), host_biases(std::move(o.host_biases)), weightOffsets(std::move(o.weightOffsets)),
+                                                 biasOffsets(std::move(o.biasOffsets)), layerSizes(std::move(o.layerSizes)), seed_(o.seed_), seeded_(o.seeded_), h_(o.h_) { o.h_ = nullptr; }
+    ~NeuralNetwork() { if (h_) xq_dqn_destroy(h_); }
+    NeuralNetwork& operator=(const NeuralNetwork& o) {
+        if (this != &o) {
+            if (layerSizes != o.layerSizes) { if (h_) xq_dqn_destroy(h_); h_ = nullptr; layerSizes = o.layerSizes; create(); }
+            host_weights = o.host_weights; host_biases = o.host_biases; weightOffsets = o.weightOffsets; biasOffsets = o.biasOffsets;
+            copyToDevice();
+        }
+        return *this;
+    }
+    NeuralNetwork& operator=(NeuralNetwork&& o) noexcept {
+        if (this != &o) {
+            if (h_) xq_dqn_destroy(h_);
+            host_weights = std::move(o.host_weights); host_biases = std::move(o.host_biases); weightOffsets = std::move(o.weightOffsets);
+            biasOffsets = std::move(o.biasOffsets); layerSizes = std::move(o.layerSizes); h_ = o.h_; o.h_ = nullptr;
+        }
+        return *this;
+    }
+
+    std::vector<double> forward(const std::vector<double>& input) {                                                  // :199-260
+        if (input.size() != (size_t)layerSizes.front()) throw std::invalid_argument("Input size does not match network input layer size.");
+        std::vector<double> q(layerSizes.back());
+        xq_adapter::check(xq_dqn_forward(h_, input.data(), 1, q.data()));
+        return q;
+    }
+    void backpropagate(const std::vector<double>& input, const std::vector<double>& target, double learningRate) {   // :323-467
+        if (input.size() != (size_t)layerSizes.front()) throw std::invalid_argument("Input size does not match network input layer size.");
+        if (target.size() != (size_t)layerSizes.back()) throw std::invalid_argument("Target size does not match network output layer size.");
+        xq_adapter::check(xq_dqn_backprop(h_, input.data(), target.data(), 1, learningRate));
+    }
+    void copyToDevice() { xq_adapter::check(xq_dqn_set_params(h_, host_weights.data(), host_biases.data())); }        // :480-485
+    void copyFromDevice() { xq_adapter::check(xq_dqn_get_params(h_, host_weights.data(), host_biases.data())); }      // :487-492
+    void initializeHostWeightsAndBiases() {                                                                           // :96-146
+        std::mt19937 gen(seeded_ ? (std::mt19937::result_type)seed_ : std::random_device{}());
+        std::uniform_real_distribution<> dis(-0.05, 0.05);
+        host_weights.clear(); host_biases.clear();
+        weightOffsets.assign(layerSizes.size() - 1, 0); biasOffsets.assign(layerSizes.size() - 1, 0);
+        for (size_t l = 0; l + 1 < layerSizes.size(); ++l) {
+            weightOffsets[l] = host_weights.size(); biasOffsets[l] = host_biases.size();
+            for (int o = 0; o < layerSizes[l + 1]; ++o) for (int i = 0; i < layerSizes[l]; ++i) host_weights.push_back(dis(gen));
+            for (int o = 0; o < layerSizes[l + 1]; ++o) host_biases.push_back(0.0);
+        }
+    }
+    void copyWeightsAndBiasesFrom(const NeuralNetwork& other) {                                                       // :507-515: the other's HOST copy
+        if (other.host_weights.size() != host_weights.size() || other.host_biases.size() != host_biases.size())
+            throw std::invalid_argument("copyWeightsAndBiasesFrom: layer sizes differ");
+        host_weights = other.host_weights; host_biases = other.host_biases;
+        copyToDevice();
+    }
+    xq_dqn_t handle() const { return h_; }
+
+private:
+    void create() {
+        std::vector<int32_t> l(layerSizes.begin(), layerSizes.end());
+        xq_adapter::check(xq_dqn_create(l.data(), (int)l.size(), 0.001, 0.99, 0, seed_, XQ_DQN_AS_WRITTEN, &h_));
+    }
+    uint64_t seed_ = 0;
+    bool seeded_ = false;
+    xq_dqn_t h_ = nullptr;
 };
 
 class DQN {

@@ -43,9 +43,9 @@ def run(libname, games):
 
 def main():
     games = int(sys.argv[1]) if len(sys.argv) > 1 else 2
+    cpu_only = "--cpu" in sys.argv          # the same loop with the network on ONE host core
     out = None
-    for lib, kind in (("libxq_ref_cuda.so", "reference ChessAI::train, its own CUDA kernels (src/dqn.cu unmodified, sm_100a) on this GPU"),
-                      ("libxq_ref.so", "reference ChessAI::train, NeuralNetwork defined on the CPU (oracle/nn_cpu.cpp), 1 host thread")):
+    for lib, kind in (() if cpu_only else (("libxq_ref_cuda.so", "reference ChessAI::train, its own CUDA kernels (src/dqn.cu unmodified, sm_100a) on this GPU"),)) + (("libxq_ref.so", "reference ChessAI::train, NeuralNetwork defined on the CPU (oracle/nn_cpu.cpp), 1 host thread"),):
         if not os.path.exists(os.path.join(HERE, "_ref", lib)):
             continue
         try:

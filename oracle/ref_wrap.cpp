@@ -193,6 +193,48 @@ double ref_bench_rollout_random(int n_threads, long n_plies, uint64_t seed, long
     return s;
 }
 
+// CPU legs of BASELINE.md section 4 that include the network, through the reference's own classes (DQN over the CPU NeuralNetwork of
+// oracle/nn_cpu.cpp in libxq_ref.so), each thread an independent board + network, for `seconds` of wall time:
+//   mode 0 = config (i): random policy + ONE forward per ply (getAllValidActions -> getStateRepresentation -> getQValues -> movePiece ->
+//            evaluateBoard -> checkGameOver), any number of threads;
+//   mode 1 = config (iii): DQN::selectAction(state, 0.1, valid) -- epsilon-greedy, a forward on 90 % of the plies -- ONE thread only
+//            (the injected rand() stream is a process global).
+// Returns the wall seconds; *plies_out / *games_out = totals over the threads.
+double ref_bench_policy(int mode, int n_threads, double seconds, uint64_t seed, long* plies_out, long* games_out) {
+    if (mode == 1) n_threads = 1;
+    std::vector<long> plies(n_threads, 0), games(n_threads, 0);
+    const auto t0 = std::chrono::steady_clock::now();
+    auto work = [&](int t) {
+        Env e;
+        DQN net(std::vector<int>{90 * 14, 128, 90 * 90});
+        uint64_t x = seed + 0x9E3779B97F4A7C15ull * (t + 1);
+        auto next = [&]() { x += 0x9E3779B97F4A7C15ull; uint64_t z = x; z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ull; z = (z ^ (z >> 27)) * 0x94D049BB133111EBull; z ^= z >> 31; return static_cast<uint32_t>(z >> 33); };
+        ChessBoard& b = e.board;
+        while (std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count() < seconds) {
+            const PieceColor mover = b.getCurrentPlayer();
+            auto acts = e.ai->getAllValidActions(mover);
+            if (acts.empty()) { b.reset(); continue; }
+            const std::vector<double> state = e.ai->getStateRepresentation();
+            Action a;
+            if (mode == 0) { const std::vector<double> q = net.getQValues(state); a = acts[next() % acts.size()]; (void)q; }
+            else { g_rand.assign({static_cast<int>(next() & 0x7FFFFFFF), static_cast<int>(next() & 0x7FFFFFFF)}); g_rand_pos = 0; a = net.selectAction(state, 0.1, acts); }
+            b.movePiece(a.from / 9, a.from % 9, a.to / 9, a.to % 9);
+            (void)e.ai->evaluateBoard(mover, b.getMoveCount());
+            ++plies[t];
+            if (b.checkGameOver()) { ++games[t]; b.reset(); }
+        }
+    };
+    std::vector<std::thread> th;
+    for (int t = 0; t < n_threads; ++t) th.emplace_back(work, t);
+    for (auto& t : th) t.join();
+    const double s = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
+    long tp = 0, tg = 0;
+    for (int t = 0; t < n_threads; ++t) { tp += plies[t]; tg += games[t]; }
+    if (plies_out) *plies_out = tp;
+    if (games_out) *games_out = tg;
+    return s;
+}
+
 // ---- DQN (reference src/dqn.cpp verbatim over oracle/nn_cpu.cpp or, in the
 // CUDA flavour of this library, over the reference's own src/dqn.cu) ----------
 void* ref_dqn_new(const int* layers, int n) {

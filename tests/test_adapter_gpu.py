@@ -29,10 +29,13 @@ def test_cpp_adapter_transcript(tmp_path, O):
             "captured": ["4", "1", "red_score", "40", "eval", "39", "-40", "37"],
             "moves_9_0": ["3", "player", "1", "movecount", "1", "over", "0"], "copy_movecount": ["0", "orig_movecount", "1"],
             "state": ["1260", "ones", "31"], "q_size": ["8100", "q_in_range", "1"], "trained_games": ["1", "red_score_nonneg", "1", "dqn", "1"],
-            "ai_move_valid": ["1"], "batched_games": ["300", "last", "300", "finished", "1", "report", "300", "updates_positive", "1"]}
+            "ai_move_valid": ["1"], "ai_move_other_colour_valid": ["12"], "ai_move_sentinel": ["-1", "-1", "-1", "-1"],
+            "nn_sizes": ["50", "9", "offsets", "0", "30", "0", "5"],
+            "nn_init_ok": ["1", "1", "trained", "1", "host_untouched", "1", "host_changed", "1", "copy_from_equal", "1", "copy_ctor_equal", "1"],
+            "batched_games": ["300", "last", "300", "finished", "1", "report", "300", "updates_positive", "1"]}
     for k, v in want.items():
         assert got[k] == v, (k, got[k], v)
-    assert out.stdout.count("invalid_argument") == 1 and out.stdout.count("runtime_error") == 1
+    assert out.stdout.count("invalid_argument") == 3 and out.stdout.count("runtime_error") == 1
     log = (tmp_path / "game_log.txt").read_text().splitlines()
     assert len(log) == 302 and log[0].startswith("Game 1 completed. Red Score: ") and log[300] == "AI self-play session completed. Total games: 300"
     R = O.ref()
