@@ -9,7 +9,7 @@ import sys
 
 PKG = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(PKG, "csrc")
-LIB = os.path.join(PKG, "libxq_b200.so")
+LIB = os.environ.get("XQ_LIB_PATH") or os.path.join(PKG, "libxq_b200.so")      # XQ_LIB_PATH: a profiling build (-DXQ_TIMELINE) next to the product library
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
 FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17", "-shared",
          "-Xcompiler", "-fPIC,-Wall,-Wno-unused-function,-Wno-unknown-pragmas", "-Xptxas", "-v", "--expt-relaxed-constexpr"]
@@ -37,7 +37,7 @@ def build_native(force=False, verbose=False):
         sys.stderr.write(r.stdout + r.stderr)
     if r.returncode != 0:
         raise RuntimeError("nvcc failed building libxq_b200.so")
-    with open(os.path.join(PKG, "build_ptxas.log"), "w") as f:
+    with open(os.path.join(PKG, "build_ptxas.log"), "w") as f:      # git-ignored
         f.write(r.stdout + r.stderr)
     return LIB
 

@@ -39,6 +39,7 @@ struct EnvInfo {
 };
 int env_info(xq_env_t h, EnvInfo* out);
 void env_advance_event_ply(xq_env_t h, uint32_t plies);   // the collector applied `plies` more plies
+void** env_scratch_slot(xq_env_t h, void (*free_fn)(void*));   // the env handle's slot for the collector's scratch; free_fn runs when the handle is destroyed
 
 // ---- device helpers ---------------------------------------------------------------------------
 #if defined(__CUDACC__)

@@ -211,6 +211,7 @@ int xq_dqn_destroy(xq_dqn_t h) {
     if (!h) return XQ_OK;
     cudaSetDevice(h->device);
     dqn_fast_destroy(h);
+    if (h->act_ev) cudaEventDestroy(h->act_ev);
     cudaFree(h->d_w); cudaFree(h->d_b); cudaFree(h->d_tw); cudaFree(h->d_tb); cudaFree(h->d_act); cudaFree(h->d_z);
     cudaFree(h->d_delta); cudaFree(h->d_target); cudaFree(h->d_tmp); cudaFree(h->d_sel); cudaFree(h->d_actions); cudaFree(h->d_scalar);
     if (h->own_stream && h->stream) cudaStreamDestroy(h->stream);

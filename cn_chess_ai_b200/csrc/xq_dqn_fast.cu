@@ -35,8 +35,10 @@ namespace xq {
 #ifdef XQ_TIMELINE
 __device__ long long g_tl[2 * 160 * 64];
 #define XQ_TL(kern, slot) (g_tl[((kern) * 160 + blockIdx.y * gridDim.x + blockIdx.x) * 64 + (slot)] = clock64())
+#define XQ_TLV(kern, slot, v) (g_tl[((kern) * 160 + blockIdx.y * gridDim.x + blockIdx.x) * 64 + (slot)] = (v))
 #else
 #define XQ_TL(kern, slot) ((void)0)
+#define XQ_TLV(kern, slot, v) ((void)0)
 #endif
 
 constexpr int kIn = XQ_STATE_SIZE, kHid = 128, kOut = 8100, kQRows = 90;   // Q is indexed by `to` < 90 (src/dqn.cpp:47)
@@ -817,19 +819,22 @@ constexpr int kExchBlocks = 96;                                                 
 constexpr size_t kExchBlockFlagsOff = kExchFlagsOff + sizeof(uint32_t) * (kMaxRanks + 4);           // [kMaxRanks source ranks][kExchBlocks] u32: epoch of the last landed row block
 constexpr size_t kExchOldBytes = kExchBlockFlagsOff + sizeof(uint32_t) * kMaxRanks * kExchBlocks;
 // Owner mode (the default fused exchange): reduce-scatter + all-gather of the 16-row blocks with the flag carried INSIDE the data
-// (the "LL" protocol of collective libraries): a 16-byte line holds two FP32 values and two copies of the epoch, each 8-byte half
-// {value, epoch} is written by one store and therefore arrives whole -- the receiver polls the data itself, no fence, no separate flag.
+// (the idea of the "LL" / "LL128" protocols of collective libraries): a 16-byte line holds three FP32 values x, y, z and the word
+// epoch ^ x ^ y ^ z, written by one 16-byte vector store and read by one 16-byte vector load -- the receiver polls the data itself, no
+// fence, no separate flag.  A line is accepted when x ^ y ^ z ^ w equals the epoch it waits for, so a line caught half-written (old and
+// new words mixed) is simply polled again: no assumption about the atomicity of vector accesses beyond single words, 75 % of the bytes
+// on the wire are payload (LL: 50 %).  tests/test_dist_gpu.py compares every exchanged bit with NCCL's sum over many updates.
 //   inbox 1 (reduce-scatter): [2 parities][kMaxRanks source ranks][kLLBlocks][kLLLinesPerBlock] lines, written by the source rank, read by the block's owner
 //   inbox 2 (all-gather):     [2 parities][kLLBlocks][kLLLinesPerBlock] lines, written by the block's owner, read by everybody else
-// A block = the 16 x 128 FP32 rows one CTA of the contraction reduces (4 lines per reducing thread) + one more line per thread for db1.
+// A block = the 16 x 128 FP32 rows one CTA of the contraction reduces: 8 values per reducing thread + 1 (db1) = 3 lines per thread.
 constexpr int kLLBlocks = 88;                                                                        // 11 row tiles x 8 splits
-constexpr int kLLLinesPerThread = 5;
+constexpr int kLLLinesPerThread = 3;
 constexpr int kLLLinesPerBlock = kLLLinesPerThread * 256;
-constexpr size_t kLLBlockBytes = (size_t)kLLLinesPerBlock * 16;                                      // 20 KB
+constexpr size_t kLLBlockBytes = (size_t)kLLLinesPerBlock * 16;                                      // 12 KB for 8.4 KB of payload
 constexpr size_t kExchLL1Off = (kExchOldBytes + 255) / 256 * 256;
-constexpr size_t kExchLL1Bytes = 2 * (size_t)kMaxRanks * kLLBlocks * kLLBlockBytes;                  // 55 MB
+constexpr size_t kExchLL1Bytes = 2 * (size_t)kMaxRanks * kLLBlocks * kLLBlockBytes;                  // 33 MB
 constexpr size_t kExchLL2Off = kExchLL1Off + kExchLL1Bytes;
-constexpr size_t kExchLL2Bytes = 2 * (size_t)kLLBlocks * kLLBlockBytes;                              // 3.4 MB
+constexpr size_t kExchLL2Bytes = 2 * (size_t)kLLBlocks * kLLBlockBytes;                              // 2 MB
 // host-level all-gather of small messages between the ranks' processes (the multi-GPU episode driver: finished-game events, round totals)
 constexpr size_t kHgCap = 64 << 10;                                                                  // bytes per rank per call
 constexpr size_t kExchHgOff = kExchLL2Off + kExchLL2Bytes;                                           // [2 parities][kMaxRanks][kHgCap] | flags[kMaxRanks] u32
@@ -841,9 +846,11 @@ __host__ __device__ constexpr size_t exch_ll1_off(int parity, int src_rank, int 
 }
 __host__ __device__ constexpr size_t exch_ll2_off(int parity, int blk) { return kExchLL2Off + ((size_t)parity * kLLBlocks + (size_t)blk) * kLLBlockBytes; }
 struct PeerPtrs { uint8_t* p[kMaxRanks]; };
-__device__ __forceinline__ void ll_store(uint8_t* line, float a, float b, uint32_t flag) {
-    asm volatile("st.volatile.global.v4.u32 [%0], {%1, %2, %3, %2};" ::"l"(line), "r"(__float_as_uint(a)), "r"(flag), "r"(__float_as_uint(b)) : "memory");
+__device__ __forceinline__ void ll_store(uint8_t* line, float a, float b, float c, uint32_t flag) {
+    const uint32_t x = __float_as_uint(a), y = __float_as_uint(b), z = __float_as_uint(c);
+    asm volatile("st.volatile.global.v4.u32 [%0], {%1, %2, %3, %4};" ::"l"(line), "r"(x), "r"(y), "r"(z), "r"(flag ^ x ^ y ^ z) : "memory");
 }
+__device__ __forceinline__ bool ll_valid(const uint4& l, uint32_t flag) { return (l.x ^ l.y ^ l.z ^ l.w) == flag; }
 __device__ __forceinline__ uint4 ll_load(const uint8_t* line) {
     uint4 v;
     asm volatile("ld.volatile.global.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "l"(line) : "memory");
@@ -1126,22 +1133,24 @@ __global__ void __launch_bounds__(kDwThreads, 1) dw_gemm_kernel(const __grid_con
         // ===== multi-GPU, ONE kernel: contraction -> reduce-scatter -> all-gather -> SGD, row block by row block, over peer memory =====
         // Block blk (the 16 rows this CTA reduced) is OWNED by rank blk % world.  The same CTA (mt, ks) of every rank handles the same block and
         // the same thread the same elements, so the exchange is thread to thread:
-        //   non-owner: 5 flag-in-data lines per thread into the owner's inbox 1 (posted 16-byte stores over NVLink 5 / NVSwitch, a warp
+        //   non-owner: 3 flag-in-data lines per thread into the owner's inbox 1 (posted 16-byte stores over NVLink 5 / NVSwitch, a warp
         //              covers 512 contiguous bytes per store instruction), then polls its own inbox 2 for the owner's sum;
         //   owner:     polls inbox 1 for the `world - 1` other copies (the loads of up to four source ranks in flight together), adds the
         //              copies IN RANK ORDER (its own from registers) -- every rank applies the very same bits -- and stores the sum into
         //              inbox 2 of every other rank.
-        // No fence, no flag array, no barrier: a line is valid when both of its epoch words match.  Traffic per rank and update:
-        // 2 x (world - 1) / world x 0.69 MB x 2 (line format) instead of (world - 1) x 0.69 MB -- 2.4 MB instead of 4.8 MB at 8 GPUs, and the
+        // No fence, no flag array, no barrier: a line is valid when its check word matches the epoch.  Traffic per rank and update:
+        // 2 x (world - 1) / world x 0.69 MB x 4/3 (line format) instead of (world - 1) x 0.69 MB -- 1.6 MB instead of 4.8 MB at 8 GPUs, and the
         // critical path is two one-way NVLink hops instead of [stores -> system-scope fence -> flag -> acquire].
         // Slot reuse: a rank writes epoch e + 2 into the slots of epoch e only after it completed update e + 1, for which it needed every
         // rank's lines of epoch e + 1, which they sent after completing update e, i.e. after their last read of the epoch-e slots.
         const int blk = mt * kDwSplits + ks, owner = blk % push.world, tid = threadIdx.x;
         const uint32_t flag = push.epoch;
-        const bool need[3] = {e[0] >= 0, e[1] >= 0, owns_db1};          // lines 0,1 = acc[0] | 2,3 = acc[1] | 4 = db1
-        const float mine[10] = {acc[0].x, acc[0].y, acc[0].z, acc[0].w, acc[1].x, acc[1].y, acc[1].z, acc[1].w, db1, 0.0f};
+        // line k of a thread = values 3k .. 3k + 2 of (acc[0], acc[1], db1); it travels if any of them is a real gradient entry
+        const bool line[kLLLinesPerThread] = {e[0] >= 0, e[0] >= 0 || e[1] >= 0, e[1] >= 0 || owns_db1};
+        const float mine[9] = {acc[0].x, acc[0].y, acc[0].z, acc[0].w, acc[1].x, acc[1].y, acc[1].z, acc[1].w, db1};
         const long long t0 = clock64();
-        float g[10] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+        float g[9] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+        if (threadIdx.x == 0) { XQ_TL(1, 41); XQ_TLV(1, 45, owner == push.rank ? 1 : 0); }
         if (owner == push.rank) {
             const uint8_t* inbox = push.peers.p[push.rank] + (size_t)tid * 16;
             for (int r0 = 0; r0 < push.world; r0 += 4) {
@@ -1156,7 +1165,7 @@ __global__ void __launch_bounds__(kDwThreads, 1) dw_gemm_kernel(const __grid_con
                         const uint8_t* src = inbox + exch_ll1_off(push.parity, r, blk);
 #pragma unroll
                         for (int k = 0; k < kLLLinesPerThread; ++k)
-                            if (need[k >> 1]) l[j][k] = ll_load(src + (size_t)k * 256 * 16);
+                            if (line[k]) l[j][k] = ll_load(src + (size_t)k * 256 * 16);
                     }
 #pragma unroll
                     for (int j = 0; j < 4; ++j) {
@@ -1164,19 +1173,21 @@ __global__ void __launch_bounds__(kDwThreads, 1) dw_gemm_kernel(const __grid_con
                         if (r >= push.world || r == push.rank) continue;
 #pragma unroll
                         for (int k = 0; k < kLLLinesPerThread; ++k)
-                            if (need[k >> 1] && (l[j][k].y != flag || l[j][k].w != flag)) ready = false;
+                            if (line[k] && !ll_valid(l[j][k], flag)) ready = false;
                     }
                 } while (!ready && clock64() - t0 < push.timeout);
                 if (!ready) exch_ok = false;
+                if (threadIdx.x == 0) XQ_TL(1, 48 + (r0 >> 2));     // sources r0 .. r0 + 3 are in
 #pragma unroll
                 for (int j = 0; j < 4; ++j) {                       // rank order
                     const int r = r0 + j;
                     if (r >= push.world) break;
 #pragma unroll
                     for (int k = 0; k < kLLLinesPerThread; ++k) {
-                        if (!need[k >> 1]) continue;
-                        g[2 * k] += r == push.rank ? mine[2 * k] : __uint_as_float(l[j][k].x);
-                        g[2 * k + 1] += r == push.rank ? mine[2 * k + 1] : __uint_as_float(l[j][k].z);
+                        if (!line[k]) continue;
+                        g[3 * k] += r == push.rank ? mine[3 * k] : __uint_as_float(l[j][k].x);
+                        g[3 * k + 1] += r == push.rank ? mine[3 * k + 1] : __uint_as_float(l[j][k].y);
+                        g[3 * k + 2] += r == push.rank ? mine[3 * k + 2] : __uint_as_float(l[j][k].z);
                     }
                 }
             }
@@ -1186,13 +1197,15 @@ __global__ void __launch_bounds__(kDwThreads, 1) dw_gemm_kernel(const __grid_con
                     uint8_t* dst = push.peers.p[r] + exch_ll2_off(push.parity, blk) + (size_t)tid * 16;
 #pragma unroll
                     for (int k = 0; k < kLLLinesPerThread; ++k)
-                        if (need[k >> 1]) ll_store(dst + (size_t)k * 256 * 16, g[2 * k], g[2 * k + 1], flag);
+                        if (line[k]) ll_store(dst + (size_t)k * 256 * 16, g[3 * k], g[3 * k + 1], g[3 * k + 2], flag);
                 }
+            if (threadIdx.x == 0) XQ_TL(1, 43);                     // owner: the sum is on its way to the peers
         } else {
             uint8_t* dst = push.peers.p[owner] + exch_ll1_off(push.parity, push.rank, blk) + (size_t)tid * 16;
 #pragma unroll
             for (int k = 0; k < kLLLinesPerThread; ++k)
-                if (need[k >> 1]) ll_store(dst + (size_t)k * 256 * 16, mine[2 * k], mine[2 * k + 1], flag);
+                if (line[k]) ll_store(dst + (size_t)k * 256 * 16, mine[3 * k], mine[3 * k + 1], mine[3 * k + 2], flag);
+            if (threadIdx.x == 0) XQ_TL(1, 42);                     // non-owner: my copy is on its way to the owner
             const uint8_t* src = push.peers.p[push.rank] + exch_ll2_off(push.parity, blk) + (size_t)tid * 16;
             uint4 l[kLLLinesPerThread];
             bool ready;
@@ -1200,15 +1213,16 @@ __global__ void __launch_bounds__(kDwThreads, 1) dw_gemm_kernel(const __grid_con
                 ready = true;
 #pragma unroll
                 for (int k = 0; k < kLLLinesPerThread; ++k)
-                    if (need[k >> 1]) l[k] = ll_load(src + (size_t)k * 256 * 16);
+                    if (line[k]) l[k] = ll_load(src + (size_t)k * 256 * 16);
 #pragma unroll
                 for (int k = 0; k < kLLLinesPerThread; ++k)
-                    if (need[k >> 1] && (l[k].y != flag || l[k].w != flag)) ready = false;
+                    if (line[k] && !ll_valid(l[k], flag)) ready = false;
             } while (!ready && clock64() - t0 < push.timeout);
             if (!ready) exch_ok = false;
+            if (threadIdx.x == 0) XQ_TL(1, 44);                     // non-owner: the owner's sum is in
 #pragma unroll
             for (int k = 0; k < kLLLinesPerThread; ++k)
-                if (need[k >> 1]) { g[2 * k] = __uint_as_float(l[k].x); g[2 * k + 1] = __uint_as_float(l[k].z); }
+                if (line[k]) { g[3 * k] = __uint_as_float(l[k].x); g[3 * k + 1] = __uint_as_float(l[k].y); g[3 * k + 2] = __uint_as_float(l[k].z); }
         }
         if (!exch_ok) { *push.status = flag; __threadfence_system(); }
         acc[0] = make_float4(g[0], g[1], g[2], g[3]); acc[1] = make_float4(g[4], g[5], g[6], g[7]);

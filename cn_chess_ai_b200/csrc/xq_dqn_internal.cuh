@@ -35,6 +35,11 @@ struct xq_dqn_s {
 
     // ---- batched BF16 path, {1260,128,8100} only (xq_dqn_fast.cu) ----
     xq::Fast* fast = nullptr;
+    // the acting state of the tensor-core path (carried layer-0 sums, h(s) operands) belongs to the network handle and is written on the
+    // ENV's stream: collectors / xq_dqn_act calls that share this network are ordered one after the other across env handles and streams
+    cudaEvent_t act_ev = nullptr;
+    cudaStream_t act_stream = nullptr;
+    bool act_pending = false;
 };
 
 namespace xq {
@@ -42,6 +47,17 @@ int dqn_ensure_f64(xq_dqn_s* h);      // refresh the FP64 parameters from the fa
 void dqn_fast_destroy(xq_dqn_s* h);
 void dqn_target_changed(xq_dqn_s* h);
 struct FastWeights { const float *W0T, *b0, *W1, *b1; };
+// bracket every use of the network's acting state on `stream`: enter waits for the previous user (if it ran on another stream), leave records
+inline int dqn_act_enter(xq_dqn_s* h, cudaStream_t stream) {
+    if (h->act_pending && h->act_stream != stream) XQ_CUDA(cudaStreamWaitEvent(stream, h->act_ev, 0));
+    return XQ_OK;
+}
+inline int dqn_act_leave(xq_dqn_s* h, cudaStream_t stream) {
+    if (!h->act_ev) XQ_CUDA(cudaEventCreateWithFlags(&h->act_ev, cudaEventDisableTiming));
+    XQ_CUDA(cudaEventRecord(h->act_ev, stream));
+    h->act_stream = stream; h->act_pending = true;
+    return XQ_OK;
+}
 int dqn_fast_weights(xq_dqn_s* h, FastWeights* out);
 // Q(s)[0..95] ([n][96] FP32 on the device) for n resident env records: the acting path of the self-play collector
 // `carried`: skip the layer-0 kernel because the caller's act_team_kernel kept the per-env sums and h(s) current; `carry` receives what it needs to do so

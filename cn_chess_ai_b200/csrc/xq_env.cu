@@ -297,6 +297,8 @@ struct xq_env_s {
     // finished-game events of the self-play collector (xq_env_enable_game_events)
     xq_game_event* d_events = nullptr; unsigned long long* d_event_count = nullptr; int64_t event_cap = 0; uint32_t event_ply = 0;
     xq_game_event* h_events = nullptr; unsigned long long* h_event_count = nullptr; int64_t last_events = 0;      // pinned staging of the drain; size of the last drain
+    // per-env scratch of the self-play collector (xq_selfplay.cu: Q(s) rows, chosen actions, auxiliary streams and events), released with the handle
+    void* sp_scratch = nullptr; void (*sp_scratch_free)(void*) = nullptr;
 };
 
 static inline unsigned grid_for(int64_t n, int per_block) { return (unsigned)((n + per_block - 1) / per_block); }
@@ -365,6 +367,7 @@ int env_info(xq_env_t h, EnvInfo* out) {
     return XQ_OK;
 }
 void env_advance_event_ply(xq_env_t h, uint32_t plies) { if (h) h->event_ply += plies; }
+void** env_scratch_slot(xq_env_t h, void (*free_fn)(void*)) { h->sp_scratch_free = free_fn; return &h->sp_scratch; }
 }  // namespace xq
 
 extern "C" {
@@ -393,6 +396,7 @@ int xq_device_count(int* count) {
 int xq_env_destroy(xq_env_t h) {
     if (!h) return XQ_OK;
     cudaSetDevice(h->device);
+    if (h->sp_scratch && h->sp_scratch_free) { cudaStreamSynchronize(h->stream); h->sp_scratch_free(h->sp_scratch); }
     cudaFree(h->d_envs); cudaFree(h->d_stats); cudaFree(h->d_actions); cudaFree(h->d_i32); cudaFree(h->d_lists);
     cudaFree(h->d_trace); cudaFree(h->d_state); cudaFree(h->d_nonstd); cudaFree(h->d_events); cudaFree(h->d_event_count); cudaFreeHost(h->h_events); cudaFreeHost(h->h_event_count);
     for (auto p : h->d_u8) cudaFree(p);

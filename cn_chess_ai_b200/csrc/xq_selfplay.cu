@@ -172,13 +172,31 @@ struct xq_replay_s {
     cudaEvent_t ev = nullptr;
 };
 
-struct SelfplayScratch { float* q90 = nullptr; int64_t cap = 0; uint16_t* actions = nullptr; cudaStream_t aux[3] = {nullptr, nullptr, nullptr}; cudaEvent_t ev_fork = nullptr, ev_join[3] = {nullptr, nullptr, nullptr}; };
-static SelfplayScratch& scratch_for(int device) { static SelfplayScratch s[64]; return s[device & 63]; }
+// Scratch of the collector / xq_dqn_act, OWNED BY THE ENV HANDLE (two env handles on one device -- on different streams, or driven by two
+// host threads -- never share Q(s) rows, action buffers, auxiliary streams or fork / join events), released with it.
+struct SelfplayScratch {
+    float* q90 = nullptr; int64_t cap = 0; uint16_t* actions = nullptr;
+    cudaStream_t aux[3] = {nullptr, nullptr, nullptr};
+    cudaEvent_t ev_fork = nullptr, ev_join[3] = {nullptr, nullptr, nullptr}, ev_order = nullptr;
+};
+static void free_scratch(void* p) {
+    SelfplayScratch* s = static_cast<SelfplayScratch*>(p);
+    cudaFree(s->q90); cudaFree(s->actions);
+    for (int k = 0; k < 3; ++k) { if (s->aux[k]) cudaStreamDestroy(s->aux[k]); if (s->ev_join[k]) cudaEventDestroy(s->ev_join[k]); }
+    if (s->ev_fork) cudaEventDestroy(s->ev_fork);
+    if (s->ev_order) cudaEventDestroy(s->ev_order);
+    delete s;
+}
 
 static inline unsigned blocks(int64_t n, int per) { return (unsigned)((n + per - 1) / per); }
-static int reserve_scratch(int device, int64_t n, SelfplayScratch** out) {
-    SelfplayScratch& s = scratch_for(device);
-    if (n > s.cap) {
+static int reserve_scratch(xq_env_t env, int64_t n, SelfplayScratch** out) {
+    void** slot = env_scratch_slot(env, free_scratch);
+    if (!*slot) {
+        *slot = new (std::nothrow) SelfplayScratch();
+        if (!*slot) return fail(XQ_ERR_NOMEM, "out of host memory");
+    }
+    SelfplayScratch& s = *static_cast<SelfplayScratch*>(*slot);
+    if (n > s.cap) {        // only ever grows on the env's own stream, after the work that used the old buffers
         cudaFree(s.q90); cudaFree(s.actions); s.q90 = nullptr; s.actions = nullptr; s.cap = 0;
         XQ_CUDA(cudaMalloc(&s.q90, sizeof(float) * kQPad * n));
         XQ_CUDA(cudaMalloc(&s.actions, sizeof(uint16_t) * n));
@@ -195,7 +213,6 @@ static int order_after(cudaStream_t waiter, cudaStream_t producer, cudaEvent_t* 
     XQ_CUDA(cudaStreamWaitEvent(waiter, *ev, 0));
     return XQ_OK;
 }
-static cudaEvent_t g_ev[64];
 
 // One ply of selection (+ application) for every env: the team kernel (xq_act_team.cu) for boards with a standard piece set, then
 // the generic thread-per-board kernel for the boards it flagged (only possible after xq_env_set_boards injected exotic positions).
@@ -313,10 +330,12 @@ int xq_dqn_act(xq_dqn_t h, xq_env_t env, double eps, xq_action* actions_host, fl
     XQ_CUDA(cudaSetDevice(h->device));
     { FastWeights fw; if (int rc = dqn_fast_weights(h, &fw)) return rc; }      // refresh the FP32 / BF16 copies on h->stream before ordering after it
     SelfplayScratch* sc;
-    if (int rc = reserve_scratch(h->device, ei.n, &sc)) return rc;
-    if (int rc = order_after(ei.stream, h->stream, &g_ev[h->device & 63])) return rc;
+    if (int rc = reserve_scratch(env, ei.n, &sc)) return rc;
+    if (int rc = order_after(ei.stream, h->stream, &sc->ev_order)) return rc;
+    if (int rc = dqn_act_enter(h, ei.stream)) return rc;
     if (int rc = dqn_q90_device(h, ei.d_envs, ei.n, sc->q90, ei.stream)) return rc;
     if (int rc = launch_act(false, ei, sc->q90, xq_eps_threshold(eps), 0, sc->actions, nullptr, 1, 0, nullptr, 0u)) return rc;
+    if (int rc = dqn_act_leave(h, ei.stream)) return rc;
     XQ_CUDA(cudaMemcpyAsync(actions_host, sc->actions, sizeof(uint16_t) * ei.n, cudaMemcpyDeviceToHost, ei.stream));
     if (q_host) XQ_CUDA(cudaMemcpyAsync(q_host, sc->q90, sizeof(float) * kQPad * ei.n, cudaMemcpyDeviceToHost, ei.stream));
     XQ_CUDA(cudaStreamSynchronize(ei.stream));
@@ -331,8 +350,9 @@ int xq_selfplay_collect(xq_dqn_t h, xq_env_t env, xq_replay_t r, int n_plies, do
     XQ_CUDA(cudaSetDevice(h->device));
     { FastWeights fw; if (int rc = dqn_fast_weights(h, &fw)) return rc; }      // refresh the FP32 / BF16 copies on h->stream before ordering after it
     SelfplayScratch* sc;
-    if (int rc = reserve_scratch(h->device, ei.n, &sc)) return rc;
-    if (int rc = order_after(ei.stream, h->stream, &g_ev[h->device & 63])) return rc;    // see the latest weights
+    if (int rc = reserve_scratch(env, ei.n, &sc)) return rc;
+    if (int rc = order_after(ei.stream, h->stream, &sc->ev_order)) return rc;    // see the latest weights
+    if (int rc = dqn_act_enter(h, ei.stream)) return rc;                           // ... and the previous user of the network's acting state
     xq_env_stats* d_stats = ei.d_stats;
     const uint32_t thr = xq_eps_threshold(eps);
     // the team kernel carries the layer-0 sums and h(s) of its envs into the next ply (tail of act_team_kernel): from the second ply of
@@ -380,7 +400,8 @@ int xq_selfplay_collect(xq_dqn_t h, xq_env_t env, xq_replay_t r, int n_plies, do
     if (forked)
         for (int k = 1; k < n_streams; ++k) { XQ_CUDA(cudaEventRecord(sc->ev_join[k - 1], sc->aux[k - 1])); XQ_CUDA(cudaStreamWaitEvent(ei.stream, sc->ev_join[k - 1], 0)); }
     env_advance_event_ply(env, (uint32_t)n_plies);
-    if (int rc = order_after(h->stream, ei.stream, &g_ev[h->device & 63])) return rc;    // later TD updates see the new transitions
+    if (int rc = dqn_act_leave(h, ei.stream)) return rc;
+    if (int rc = order_after(h->stream, ei.stream, &sc->ev_order)) return rc;    // later TD updates see the new transitions
     return XQ_OK;
 }
 
