@@ -92,7 +92,8 @@ struct Fast {
     __nv_bfloat16* H2bf_b = nullptr;
     float* zpart_b = nullptr;
     CUtensorMap tmH2_b;
-    cudaStream_t aux = nullptr;
+    cudaStream_t aux = nullptr, main_hi = nullptr;
+    cudaEvent_t ev_join = nullptr;
     cudaEvent_t ev_fork = nullptr, ev_aux[2] = {nullptr, nullptr}, ev_free[2] = {nullptr, nullptr}, ev_td[2] = {nullptr, nullptr};
     // multi-GPU gradient exchange over peer memory (xq_dqn_dist_*): when connected, the compact gradient of an update is written
     // into slot `parity` of this rank's exchange buffer, which every peer maps through CUDA IPC
@@ -1135,7 +1136,7 @@ __global__ void __launch_bounds__(kDwThreads, 1) dw_gemm_kernel(const __grid_con
         // the same thread the same elements, so the exchange is thread to thread:
         //   non-owner: 3 flag-in-data lines per thread into the owner's inbox 1 (posted 16-byte stores over NVLink 5 / NVSwitch, a warp
         //              covers 512 contiguous bytes per store instruction), then polls its own inbox 2 for the owner's sum;
-        //   owner:     polls inbox 1 for the `world - 1` other copies (the loads of up to four source ranks in flight together), adds the
+        //   owner:     polls inbox 1 for the `world - 1` other copies (the loads of up to eight source ranks in flight together), adds the
         //              copies IN RANK ORDER (its own from registers) -- every rank applies the very same bits -- and stores the sum into
         //              inbox 2 of every other rank.
         // No fence, no flag array, no barrier: a line is valid when its check word matches the epoch.  Traffic per rank and update:
@@ -1153,13 +1154,14 @@ __global__ void __launch_bounds__(kDwThreads, 1) dw_gemm_kernel(const __grid_con
         if (threadIdx.x == 0) { XQ_TL(1, 41); XQ_TLV(1, 45, owner == push.rank ? 1 : 0); }
         if (owner == push.rank) {
             const uint8_t* inbox = push.peers.p[push.rank] + (size_t)tid * 16;
-            for (int r0 = 0; r0 < push.world; r0 += 4) {
-                uint4 l[4][kLLLinesPerThread];
+            constexpr int kG = 8;                                   // source ranks polled together: all 24 line loads of a thread in flight at once
+            for (int r0 = 0; r0 < push.world; r0 += kG) {
+                uint4 l[kG][kLLLinesPerThread];
                 bool ready;
                 do {
                     ready = true;
 #pragma unroll
-                    for (int j = 0; j < 4; ++j) {
+                    for (int j = 0; j < kG; ++j) {
                         const int r = r0 + j;
                         if (r >= push.world || r == push.rank) continue;
                         const uint8_t* src = inbox + exch_ll1_off(push.parity, r, blk);
@@ -1168,7 +1170,7 @@ __global__ void __launch_bounds__(kDwThreads, 1) dw_gemm_kernel(const __grid_con
                             if (line[k]) l[j][k] = ll_load(src + (size_t)k * 256 * 16);
                     }
 #pragma unroll
-                    for (int j = 0; j < 4; ++j) {
+                    for (int j = 0; j < kG; ++j) {
                         const int r = r0 + j;
                         if (r >= push.world || r == push.rank) continue;
 #pragma unroll
@@ -1177,9 +1179,9 @@ __global__ void __launch_bounds__(kDwThreads, 1) dw_gemm_kernel(const __grid_con
                     }
                 } while (!ready && clock64() - t0 < push.timeout);
                 if (!ready) exch_ok = false;
-                if (threadIdx.x == 0) XQ_TL(1, 48 + (r0 >> 2));     // sources r0 .. r0 + 3 are in
+                if (threadIdx.x == 0) XQ_TL(1, 48 + (r0 >> 3));     // sources r0 .. r0 + 7 are in
 #pragma unroll
-                for (int j = 0; j < 4; ++j) {                       // rank order
+                for (int j = 0; j < kG; ++j) {                      // rank order
                     const int r = r0 + j;
                     if (r >= push.world) break;
 #pragma unroll
@@ -1556,6 +1558,8 @@ void dqn_fast_destroy(xq_dqn_s* h) {
     if (f->hg_pin) cudaFreeHost(f->hg_pin);
     cudaFree(f->H2bf_b); cudaFree(f->zpart_b);
     if (f->aux) cudaStreamDestroy(f->aux);
+    if (f->main_hi) cudaStreamDestroy(f->main_hi);
+    if (f->ev_join) cudaEventDestroy(f->ev_join);
     if (f->ev_fork) cudaEventDestroy(f->ev_fork);
     for (int i = 0; i < 2; ++i) { if (f->ev_aux[i]) cudaEventDestroy(f->ev_aux[i]); if (f->ev_free[i]) cudaEventDestroy(f->ev_free[i]); if (f->ev_td[i]) cudaEventDestroy(f->ev_td[i]); }
     cudaFree(f->W0T); cudaFree(f->b0); cudaFree(f->W1); cudaFree(f->b1); cudaFree(f->W1bf); cudaFree(f->W1lo); cudaFree(f->actHhi); cudaFree(f->actHlo);
@@ -1875,9 +1879,18 @@ int dqn_td_update_pipelined(xq_dqn_s* h, const void* ring, int64_t size, uint64_
         for (int i = 0; i < 2; ++i) { XQ_CUDA(cudaEventCreateWithFlags(&f->ev_aux[i], cudaEventDisableTiming)); XQ_CUDA(cudaEventCreateWithFlags(&f->ev_free[i], cudaEventDisableTiming)); XQ_CUDA(cudaEventCreateWithFlags(&f->ev_td[i], cudaEventDisableTiming)); }
     }
     const int64_t ld = (f->cap + BM - 1) / BM * BM;
-    cudaStream_t main = h->stream, aux = f->aux;
-    XQ_CUDA(cudaEventRecord(f->ev_fork, main));                  // the target net and the ring are final for the aux stream
+    // XQ_TD_MAIN_PRIO=1: the online branch (the critical path) runs on a stream of the library with a higher priority than the bootstrap branch
+    static const int main_prio = [] { const char* e = getenv("XQ_TD_MAIN_PRIO"); return e ? atoi(e) : 0; }();
+    if (main_prio && !f->main_hi) {
+        int lo = 0, hi = 0;
+        XQ_CUDA(cudaDeviceGetStreamPriorityRange(&lo, &hi));
+        XQ_CUDA(cudaStreamCreateWithPriority(&f->main_hi, cudaStreamNonBlocking, hi));
+    }
+    if (!f->ev_join) XQ_CUDA(cudaEventCreateWithFlags(&f->ev_join, cudaEventDisableTiming));
+    cudaStream_t main = main_prio ? f->main_hi : h->stream, aux = f->aux;
+    XQ_CUDA(cudaEventRecord(f->ev_fork, h->stream));             // the target net and the ring are final for the other streams
     XQ_CUDA(cudaStreamWaitEvent(aux, f->ev_fork, 0));
+    if (main != h->stream) XQ_CUDA(cudaStreamWaitEvent(main, f->ev_fork, 0));
     // bootstrap branch of update i into slot i & 1, in two parts.  h(s') (small CTAs) is enqueued early and runs under the online branch of
     // update i-1; the row-max GEMM needs a whole SM's shared memory per CTA, exactly like the gradient contraction of the online branch, so it
     // is released only when update i-1 is complete and then runs next to update i's h(s) gather (which leaves the shared memory free).
@@ -1902,27 +1915,38 @@ int dqn_td_update_pipelined(xq_dqn_s* h, const void* ring, int64_t size, uint64_
     static const int early = [] { const char* e = getenv("XQ_TD_EARLY_GEMM"); return e ? atoi(e) : 2; }();
     static const int splits = [] { const char* e = getenv("XQ_TD_GEMM_SPLITS"); return e ? atoi(e) : 0; }();
     static const bool fuse_exchange = [] { const char* e = getenv("XQ_DIST_FUSED_GEMM"); return !(e && atoi(e) == 0); }();   // 0: exchange in a kernel of its own (A/B runs)
-    auto aux_gemm = [&](int i) -> int {
+    //   3  TWO updates ahead, when update i is complete: the GEMM of update i+2 then runs under the h(s) gather and the TD-error kernel of update
+    //      i+1 -- small CTAs it co-resides with on all 148 SMs -- and is out of the way when the contraction of update i+1 wants 88 whole SMs (11
+    //      clusters of 8 in one GPC each): nothing races for SMs any more.  Slot reuse: the partials slot of update i+2 was last read by the
+    //      TD-error kernel of update i, h(s') of update i+2 is written after the GEMM of update i in stream order.
+    auto aux_gemm = [&](int i, cudaEvent_t gate) -> int {
         const int slot = i & 1;
-        if (i >= 1) XQ_CUDA(cudaStreamWaitEvent(aux, early ? f->ev_td[(i - 1) & 1] : f->ev_free[(i - 1) & 1], 0));   // (update i-2 has consumed this slot either way)
+        if (gate) XQ_CUDA(cudaStreamWaitEvent(aux, gate, 0));
         if (int rc = launch_gemm(h, EPI_ROWMAX, slot ? f->tmH2_b : f->tmH2, f->tmTW1, f->tb1, n, nullptr, aux, slot ? f->zpart_b : f->zpart,
                                  splits > 0 ? splits : (early ? 5 : 0))) return rc;
         XQ_CUDA(cudaEventRecord(f->ev_aux[slot], aux));
         return XQ_OK;
     };
+    // the update before update i has consumed the slot of update i in modes 0-2: gate on its TD-error kernel (modes 1, 2) or its completion (mode 0)
+    auto gate_of = [&](int i) -> cudaEvent_t { return i >= 1 ? (early ? f->ev_td[(i - 1) & 1] : f->ev_free[(i - 1) & 1]) : nullptr; };
     if (int rc = aux_l0(0)) return rc;
-    if (int rc = aux_gemm(0)) return rc;
+    if (int rc = aux_gemm(0, nullptr)) return rc;
+    if (early == 3 && n_updates > 1) {      // fill: the first two bootstrap branches start at once
+        if (int rc = aux_l0(1)) return rc;
+        if (int rc = aux_gemm(1, nullptr)) return rc;
+    }
     for (int i = 0; i < n_updates; ++i) {
         const int slot = i & 1;
         const BatchRef ref{reinterpret_cast<const uint8_t*>(ring), size, seed, counter0 + (uint32_t)i, 1};
-        if (i + 1 < n_updates) if (int rc = aux_l0(i + 1)) return rc;
+        if (early == 3) { if (i + 2 < n_updates) if (int rc = aux_l0(i + 2)) return rc; }
+        else if (i + 1 < n_updates) if (int rc = aux_l0(i + 1)) return rc;
         XQ_CUDA(launch_pdl(l0_pair_kernel, dim3(blocks(n, kL0Warps)), dim3(kL0Warps * 32), 0, main, 1, ref, n, f->W0T, f->b0, f->tW0T, f->tb0, f->Hf,
                            f->H2bf, f->cb, ld, f->info_slots, kInfoSlots * 4, 1));
         XQ_CUDA(cudaStreamWaitEvent(main, f->ev_aux[slot], 0));  // the row-max partials of this update
-        if (early == 2) { XQ_CUDA(cudaEventRecord(f->ev_td[slot], main)); if (i + 1 < n_updates) if (int rc = aux_gemm(i + 1)) return rc; }
+        if (early == 2) { XQ_CUDA(cudaEventRecord(f->ev_td[slot], main)); if (i + 1 < n_updates) if (int rc = aux_gemm(i + 1, gate_of(i + 1))) return rc; }
         XQ_CUDA(launch_pdl(td_delta_kernel, dim3(blocks(n * 32, 256)), dim3(256), 0, main, 1, f->cb, n, f->Hf, f->W1, f->b1, slot ? f->zpart_b : f->zpart,
                            ld, kParts, (float)h->gamma, h->mode, f->d0hi, f->d0lo, f->ghi, f->glo, ld, f->info_slots));
-        if (early == 1) { XQ_CUDA(cudaEventRecord(f->ev_td[slot], main)); if (i + 1 < n_updates) if (int rc = aux_gemm(i + 1)) return rc; }
+        if (early == 1) { XQ_CUDA(cudaEventRecord(f->ev_td[slot], main)); if (i + 1 < n_updates) if (int rc = aux_gemm(i + 1, gate_of(i + 1))) return rc; }
         XQ_CUDA(launch_pdl(dw_gemm_kernel, dim3(kDwMTiles, kDwSplits), dim3(kDwThreads), kDwSmem, main, kDwSplits, f->tmD0hi, f->tmD0lo, f->tmGhi,
                            f->tmGlo, f->tmCb, (int)n, f->part, f->dbpart, f->info_slots, f->info, cur_grad(f), f->W0T, f->b0, f->W1, f->b1, f->W1bf,
                            f->W1lo, (float)lr, f->connected ? 0 : 1, dw_push(f, !f->connected, fuse_exchange)));
@@ -1931,7 +1955,12 @@ int dqn_td_update_pipelined(xq_dqn_s* h, const void* ring, int64_t size, uint64_
             else if (int rc = dqn_exchange_apply(h, lr)) return rc;              // two kernels: push + [wait, sum, SGD]
         }
         XQ_CUDA(cudaEventRecord(f->ev_free[slot], main));
-        if (!early && i + 1 < n_updates) if (int rc = aux_gemm(i + 1)) return rc;
+        if (!early && i + 1 < n_updates) if (int rc = aux_gemm(i + 1, gate_of(i + 1))) return rc;
+        if (early == 3 && i + 2 < n_updates) if (int rc = aux_gemm(i + 2, f->ev_free[slot])) return rc;
+    }
+    if (main != h->stream) {                // the online branch ran on the library's own high-priority stream: join
+        XQ_CUDA(cudaEventRecord(f->ev_join, main));
+        XQ_CUDA(cudaStreamWaitEvent(h->stream, f->ev_join, 0));
     }
     h->f64_current = false; ++f->w_version;
     return XQ_OK;

@@ -67,6 +67,8 @@ def oracle():
         L.xqo_nn_backprop.argtypes = [_i32p, C.c_int, _f64p, _f64p, _f64p, _f64p, C.c_double, C.c_int]
         L.xqo_nn_grad.argtypes = [_i32p, C.c_int, _f64p, _f64p, _f64p, _f64p, C.c_int, _f64p, _f64p]
         L.xqo_td_target.argtypes = [_f64p, _f64p, C.c_int, C.c_int, C.c_double, C.c_int, C.c_double, _f64p]
+        L.xqo_td_batch_grad.argtypes = [_i32p, C.c_int, _f64p, _f64p, _f64p, _f64p, _f64p, _f64p, _i32p, _i32p, _u8p, C.c_double, C.c_int, C.c_long,
+                                        C.c_int, _f64p, _f64p, C.POINTER(C.c_double)]
         L.xqo_state.argtypes = [_P, _f64p]
         for f in ("xqo_is_valid_move", "xqo_move"):
             getattr(L, f).argtypes = [_P, C.c_int, C.c_int, C.c_int, C.c_int]

@@ -607,3 +607,58 @@ void xqo_td_target(const double* q_s, const double* q_next, int n_out, int a_to,
     for (int i = 1; i < n_out; ++i) if (q_next[i] > m) m = q_next[i];
     target[a_to] = reward + gamma * m;
 }
+
+/* TD gradient of a BATCH: the per-sample steps of ChessAI::train's body (src/chessai.cpp:121-131) / DQN::train (src/dqn.cpp:157-172)
+ * at frozen weights, summed over the samples -- getQValues(s) with the online net, getQValues(s') with the bootstrap net (tw, tb; pass
+ * w, b for the live loop), xqo_td_target, xqo_nn_grad -- on n_threads host threads (samples split in contiguous chunks, partial sums
+ * added in chunk order).  x, x2: [n][layers[0]] states; to / reward / done: [n].  gw / gb: full-size sums; *loss = sum of 1/2 (q[to] - t)^2. */
+typedef struct {
+    const int* layers; int n_layers; const double *w, *b, *tw, *tb, *x, *x2; const int32_t *to, *reward; const uint8_t* done;
+    double gamma; int corrected; long first, count; double *gw, *gb; double loss;
+} xqo_td_job;
+static void* td_batch_thread(void* p) {
+    xqo_td_job* j = (xqo_td_job*)p;
+    const int nin = j->layers[0], nout = j->layers[j->n_layers - 1];
+    size_t nw = 0, nb = 0;
+    for (int l = 0; l + 1 < j->n_layers; ++l) { nw += (size_t)j->layers[l] * j->layers[l + 1]; nb += (size_t)j->layers[l + 1]; }
+    double *qs = (double*)malloc(sizeof(double) * nout), *qn = (double*)malloc(sizeof(double) * nout), *tg = (double*)malloc(sizeof(double) * nout);
+    double *g1 = (double*)malloc(sizeof(double) * nw), *g2 = (double*)malloc(sizeof(double) * nb);
+    for (long i = j->first; i < j->first + j->count; ++i) {
+        xqo_nn_forward(j->layers, j->n_layers, j->w, j->b, j->x + (size_t)i * nin, qs);
+        xqo_nn_forward(j->layers, j->n_layers, j->tw, j->tb, j->x2 + (size_t)i * nin, qn);
+        xqo_td_target(qs, qn, nout, j->to[i], (double)j->reward[i], j->done[i], j->gamma, tg);
+        xqo_nn_grad(j->layers, j->n_layers, j->w, j->b, j->x + (size_t)i * nin, tg, j->corrected, g1, g2);
+        for (size_t k = 0; k < nw; ++k) j->gw[k] += g1[k];
+        for (size_t k = 0; k < nb; ++k) j->gb[k] += g2[k];
+        j->loss += 0.5 * (qs[j->to[i]] - tg[j->to[i]]) * (qs[j->to[i]] - tg[j->to[i]]);
+    }
+    free(qs); free(qn); free(tg); free(g1); free(g2);
+    return NULL;
+}
+void xqo_td_batch_grad(const int* layers, int n_layers, const double* w, const double* b, const double* tw, const double* tb, const double* x,
+                       const double* x2, const int32_t* to, const int32_t* reward, const uint8_t* done, double gamma, int corrected, long n,
+                       int n_threads, double* gw, double* gb, double* loss) {
+    size_t nw = 0, nb = 0;
+    for (int l = 0; l + 1 < n_layers; ++l) { nw += (size_t)layers[l] * layers[l + 1]; nb += (size_t)layers[l + 1]; }
+    if (n_threads < 1) n_threads = 1;
+    if (n_threads > 256) n_threads = 256;
+    if ((long)n_threads > n) n_threads = (int)(n > 0 ? n : 1);
+    pthread_t th[256];
+    xqo_td_job* jobs = (xqo_td_job*)calloc((size_t)n_threads, sizeof(xqo_td_job));
+    for (int t = 0; t < n_threads; ++t) {
+        const long first = n * t / n_threads, last = n * (t + 1) / n_threads;
+        jobs[t] = (xqo_td_job){layers, n_layers, w, b, tw, tb, x, x2, to, reward, done, gamma, corrected, first, last - first,
+                               (double*)calloc(nw, sizeof(double)), (double*)calloc(nb, sizeof(double)), 0.0};
+        pthread_create(&th[t], NULL, td_batch_thread, &jobs[t]);
+    }
+    memset(gw, 0, sizeof(double) * nw); memset(gb, 0, sizeof(double) * nb);
+    *loss = 0.0;
+    for (int t = 0; t < n_threads; ++t) {
+        pthread_join(th[t], NULL);
+        for (size_t k = 0; k < nw; ++k) gw[k] += jobs[t].gw[k];
+        for (size_t k = 0; k < nb; ++k) gb[k] += jobs[t].gb[k];
+        *loss += jobs[t].loss;
+        free(jobs[t].gw); free(jobs[t].gb);
+    }
+    free(jobs);
+}

@@ -95,6 +95,11 @@ uint32_t xqo_eps_threshold(double eps);
 void xqo_td_target(const double* q_s, const double* q_next, int n_out, int a_to, double reward, int done, double gamma,
                    double* target);
 
+/* the TD gradient of a batch: per-sample forward x2 + xqo_td_target + xqo_nn_grad at frozen weights, summed, on n_threads host threads */
+void xqo_td_batch_grad(const int* layers, int n_layers, const double* w, const double* b, const double* tw, const double* tb, const double* x,
+                       const double* x2, const int32_t* to, const int32_t* reward, const uint8_t* done, double gamma, int corrected, long n,
+                       int n_threads, double* gw, double* gb, double* loss);
+
 #ifdef __cplusplus
 }
 #endif
