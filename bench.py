@@ -143,6 +143,21 @@ def reference_train_leg(games=3, timeout=240):
         return {"unavailable": f"{type(ex).__name__}: {ex}"[:200]}
 
 
+def adapter_train_leg(games=3, timeout=240):
+    """the drop-in single-board path: the C++ adapter's ChessAI::train (cn_chess_ai_b200/adapter/xq_adapter.hpp) compiled here with g++ against
+    libxq_b200.so and run for a bounded number of games -- the counterpart of reference_train"""
+    import tempfile
+    try:
+        pkg = os.path.join(ROOT, "cn_chess_ai_b200")
+        exe = os.path.join(tempfile.mkdtemp(), "train_bench")
+        subprocess.run(["g++", "-std=c++17", "-O2", "-o", exe, os.path.join(pkg, "adapter", "examples", "train_bench.cpp"), "-L" + pkg, "-lxq_b200",
+                        "-Wl,-rpath," + pkg], check=True, capture_output=True, timeout=120)
+        r = subprocess.run([exe, str(games)], capture_output=True, text=True, timeout=timeout, cwd=os.path.dirname(exe))
+        return json.loads(r.stdout.strip().splitlines()[-1])
+    except Exception as ex:
+        return {"unavailable": f"{type(ex).__name__}: {ex}"[:200]}
+
+
 def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
@@ -303,6 +318,7 @@ def main():
     achieved = ALGO_BYTES_PER_STEP * E * P / (kernel_ms * 1e-3) / 1e9
     traffic, inst_per_step = None, None
     tp = os.path.join(ROOT, "profiles", "traffic.json")
+    tj = {}
     if os.path.exists(tp):
         tj = json.load(open(tp))
         if (E, P) == (4096, 200):       # the capture is of this workload
@@ -320,7 +336,7 @@ def main():
                     "d2h_bytes_per_step": int(recs_out.nbytes) + 64},
             "gpu_launches": int(launches),
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": pk["hbm_gbs"], "unit": "GB/s", "frac": achieved / pk["hbm_gbs"],
-                         "traffic": traffic, "kernel": "rollout_team_kernel", "peak_source": pk["source"],
+                         "traffic": traffic, "kernel": "rollout_team_kernel<4> (up to 12,288 envs; rollout_lane_kernel above: aux.config5)", "peak_source": pk["source"],
                          "algorithmic_bytes_per_launch": ALGO_BYTES_PER_STEP * E * P,
                          "note": "integer/latency-bound by design: boards stay on chip for all plies of a launch (DESIGN.md)"},
             "clocks": clocks}
@@ -407,8 +423,20 @@ def main():
         if dist is not None:
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
         aux["config5_1M_envs_steps_per_s"] = (1 << 20) * 32 * 5 / (float(t[0]) * 1e-3)
-        aux["config5"] = {"envs_total": 1 << 20, "envs_per_gpu": per_gpu, "plies_per_launch": 32, "launches": 5, "steps_per_s": aux["config5_1M_envs_steps_per_s"],
-                          "hbm_frac": ALGO_BYTES_PER_STEP * aux["config5_1M_envs_steps_per_s"] / world / 1e9 / pk["hbm_gbs"]}
+        c5 = aux["config5_1M_envs_steps_per_s"]
+        c5_gbs = ALGO_BYTES_PER_STEP * c5 / world / 1e9
+        aux["config5"] = {"envs_total": 1 << 20, "envs_per_gpu": per_gpu, "plies_per_launch": 32, "launches": 5, "steps_per_s": c5,
+                          "kernel": "rollout_lane_kernel (one thread per board, the board in registers)",
+                          "roofline": {"bound": "hbm", "achieved": c5_gbs, "peak": pk["hbm_gbs"], "unit": "GB/s", "frac": c5_gbs / pk["hbm_gbs"],
+                                       "traffic": tj.get("lane_kernel_dram_bytes_per_launch") if world == 1 and os.path.exists(tp) else None,
+                                       "algorithmic_bytes_per_launch": ALGO_BYTES_PER_STEP * per_gpu * 32, "peak_source": pk["source"]}}
+        if os.path.exists(tp) and tj.get("lane_kernel_warp_inst_per_step") and clocks and clocks.get("sm_mhz"):
+            ipeak = 148 * 4 * clocks["sm_mhz"] * 1e6
+            issued = c5 / world * tj["lane_kernel_warp_inst_per_step"]
+            aux["config5"]["roofline"]["secondary"] = {"bound": "warp-instruction issue", "achieved": issued, "peak": ipeak, "unit": "warp-inst/s", "frac": issued / ipeak,
+                                                       "warp_inst_per_env_step": tj["lane_kernel_warp_inst_per_step"], "alu_pipe_pct_of_peak": tj.get("lane_kernel_alu_pipe_pct"),
+                                                       "note": "the integer ALU pipe issues one warp-instruction every two cycles per scheduler: at ~70 % ALU-pipe instructions the ceiling "
+                                                               "of this kernel is ~0.7 of the issue peak (ncu: ALU pipe 90 % busy, profiles/r2_ncu_lane_rollout_list_step_summary.csv)"}
         big.close()
         line["aux"] = aux
 
@@ -418,6 +446,7 @@ def main():
         line["dqn"] = d
         if rank == 0 and world == 1 and not args.no_cpu_baseline:
             d["reference_train"] = reference_train_leg()      # the reference's own batch-1 loop on this box, next to transitions_per_s
+            d["adapter_train"] = adapter_train_leg()          # the same loop through the drop-in adapter classes (one board, FP64 kernels of this library)
         launches_total = L.xq_launch_count()
         line["gpu_launches_total"] = int(launches_total)
 

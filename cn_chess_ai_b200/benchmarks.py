@@ -112,7 +112,7 @@ def bench_dqn(stream, peaks, world=1, local=0, dist=None, envs=65536, replay_cap
     issued = sum(ISSUED_FLOP_PER_UPDATE.values()) * (batch / 4096) / (us * 1e-6) / 1e12
     out = {"metric": "DQN TD updates/s (batch 4096 per GPU, target-net bootstrap, SGD applied)",
            "td_updates_per_s": 1e6 / us, "pipelined_over_two_streams": pipelined, "transitions_per_s": 1e6 / us * batch * world, "us_per_update": us,
-           "us_per_update_median": us_sorted[len(us_sorted) // 2], "us_per_update_min": us_sorted[0],
+           "us_per_update_median": us_sorted[len(us_sorted) // 2], "us_per_update_min": us_sorted[0], "us_per_update_calls": [1e3 * x / updates for x in per_call],
            "timed": "%d calls x %d sequential updates (%d kernel launches); mean over all, median / min over the calls, max over ranks" % (calls, updates, calls * updates * 4),
            "batch_per_gpu": batch, "replay_transitions_per_gpu": replay_cap,
            "grad_allreduce": (("inside the gradient contraction kernel over peer memory: reduce-scatter of the 16-row blocks to owner ranks + all-gather, flag-in-data lines"

@@ -1879,8 +1879,13 @@ int dqn_td_update_pipelined(xq_dqn_s* h, const void* ring, int64_t size, uint64_
         for (int i = 0; i < 2; ++i) { XQ_CUDA(cudaEventCreateWithFlags(&f->ev_aux[i], cudaEventDisableTiming)); XQ_CUDA(cudaEventCreateWithFlags(&f->ev_free[i], cudaEventDisableTiming)); XQ_CUDA(cudaEventCreateWithFlags(&f->ev_td[i], cudaEventDisableTiming)); }
     }
     const int64_t ld = (f->cap + BM - 1) / BM * BM;
-    // XQ_TD_MAIN_PRIO=1: the online branch (the critical path) runs on a stream of the library with a higher priority than the bootstrap branch
-    static const int main_prio = [] { const char* e = getenv("XQ_TD_MAIN_PRIO"); return e ? atoi(e) : 0; }();
+    // The online branch (the critical path) can run on a stream of the library with a HIGHER priority than the bootstrap branch.  Measured per
+    // update (batch 4096 per GPU, us; equal priorities / online branch higher):  1 GPU 33.5 (29.6 .. 35.5 from call to call) / 34.6;  2 GPUs 36.3 / 38.9;
+    // 8 GPUs 47.1 (43.9 .. 48.5) / 42.5 (+- 0.1).  With equal priorities the row-max GEMM of update i+1 and the 88 whole-SM CTAs of the contraction of
+    // update i race for SMs; once the contraction also waits for its peers' row blocks (it then holds its SMs for ~17 us instead of ~10) losing that
+    // race costs more than the GEMM's loss of the SMs under the h(s) gather, so the default is: higher priority from 4 ranks on.  XQ_TD_MAIN_PRIO=0|1 forces.
+    static const int main_prio_env = [] { const char* e = getenv("XQ_TD_MAIN_PRIO"); return e ? atoi(e) : -1; }();
+    const int main_prio = main_prio_env >= 0 ? main_prio_env : (f->connected && f->world >= 4 ? 1 : 0);
     if (main_prio && !f->main_hi) {
         int lo = 0, hi = 0;
         XQ_CUDA(cudaDeviceGetStreamPriorityRange(&lo, &hi));
