@@ -93,7 +93,7 @@ struct Fast {
     float* zpart_b = nullptr;
     CUtensorMap tmH2_b;
     cudaStream_t aux = nullptr, main_hi = nullptr;
-    cudaEvent_t ev_join = nullptr;
+    cudaEvent_t ev_join = nullptr, ev_tdb[2] = {nullptr, nullptr};
     cudaEvent_t ev_fork = nullptr, ev_aux[2] = {nullptr, nullptr}, ev_free[2] = {nullptr, nullptr}, ev_td[2] = {nullptr, nullptr};
     // multi-GPU gradient exchange over peer memory (xq_dqn_dist_*): when connected, the compact gradient of an update is written
     // into slot `parity` of this rank's exchange buffer, which every peer maps through CUDA IPC
@@ -408,7 +408,7 @@ __device__ __forceinline__ uint32_t sw128_offset(int row, int col) {   // byte o
 
 template <int MODE>
 __global__ void __launch_bounds__(kGemmThreads, 1) l1_gemm_kernel(const __grid_constant__ CUtensorMap tmH, const __grid_constant__ CUtensorMap tmW1,
-                                                                 const float* __restrict__ b1, int M, int m_tiles, int n_splits,
+                                                                 const float* __restrict__ b1, int M, int m_first, int m_tiles, int n_splits,
                                                                  float* __restrict__ zpart, int64_t zstride, float* __restrict__ Q) {
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);   // SW128 tiles need 1024-B alignment
@@ -428,7 +428,7 @@ __global__ void __launch_bounds__(kGemmThreads, 1) l1_gemm_kernel(const __grid_c
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int n_tile = blockIdx.x, split = blockIdx.y;
     const int n0 = n_tile * BN;
-    // rows of this CTA: m-tiles split, split + n_splits, ...
+    // rows of this CTA: m-tiles m_first + split, + n_splits, ... of the launch's range [m_first, m_first + m_tiles)
     const int my_tiles = (m_tiles - split + n_splits - 1) / n_splits;
     if (threadIdx.x == 0) XQ_TL(0, 0);
 
@@ -445,7 +445,7 @@ __global__ void __launch_bounds__(kGemmThreads, 1) l1_gemm_kernel(const __grid_c
         tc::pdl_wait();             // W1 / b1 were final before the producer of H started; H itself is the predecessor's output
         for (int i = 0; i < kAStages && i < my_tiles; ++i) {
             tc::mbar_expect_tx(a_full + i, kABytes);
-            const int row0 = (split + i * n_splits) * BM;
+            const int row0 = (m_first + split + i * n_splits) * BM;
             for (int kb = 0; kb < kKBlocks; ++kb) tc::tma_load_2d(sA + i * kABytes + kb * (BM * BK * 2), &tmH, kb * BK, row0, a_full + i);
         }
     }
@@ -497,7 +497,7 @@ __global__ void __launch_bounds__(kGemmThreads, 1) l1_gemm_kernel(const __grid_c
                 const int st = i % kAStages;
                 tc::mbar_wait(a_empty + st, ((i / kAStages) & 1) ^ 1);
                 tc::mbar_expect_tx(a_full + st, kABytes);
-                const int row0 = (split + i * n_splits) * BM;
+                const int row0 = (m_first + split + i * n_splits) * BM;
                 for (int kb = 0; kb < kKBlocks; ++kb) tc::tma_load_2d(sA + st * kABytes + kb * (BM * BK * 2), &tmH, kb * BK, row0, a_full + st);
             }
         }
@@ -539,7 +539,7 @@ __global__ void __launch_bounds__(kGemmThreads, 1) l1_gemm_kernel(const __grid_c
         constexpr int kHalfCols = BN / 2;                                   // 112 = 3 x 32 + 16 columns
         for (int i = 0; i < my_tiles; ++i) {
             const int acc = i & 1;
-            const int row = (split + i * n_splits) * BM + quarter * 32 + lane;
+            const int row = (m_first + split + i * n_splits) * BM + quarter * 32 + lane;
             tc::mbar_wait(acc_full + acc, (i >> 1) & 1);
             if (warp == 4 && lane == 0 && i < 8) XQ_TL(0, 20 + i);
             tc::tc_fence_after();
@@ -1560,6 +1560,7 @@ void dqn_fast_destroy(xq_dqn_s* h) {
     if (f->aux) cudaStreamDestroy(f->aux);
     if (f->main_hi) cudaStreamDestroy(f->main_hi);
     if (f->ev_join) cudaEventDestroy(f->ev_join);
+    for (int i = 0; i < 2; ++i) if (f->ev_tdb[i]) cudaEventDestroy(f->ev_tdb[i]);
     if (f->ev_fork) cudaEventDestroy(f->ev_fork);
     for (int i = 0; i < 2; ++i) { if (f->ev_aux[i]) cudaEventDestroy(f->ev_aux[i]); if (f->ev_free[i]) cudaEventDestroy(f->ev_free[i]); if (f->ev_td[i]) cudaEventDestroy(f->ev_td[i]); }
     cudaFree(f->W0T); cudaFree(f->b0); cudaFree(f->W1); cudaFree(f->b1); cudaFree(f->W1bf); cudaFree(f->W1lo); cudaFree(f->actHhi); cudaFree(f->actHlo);
@@ -1677,21 +1678,24 @@ int dqn_fast_weights(xq_dqn_s* h, FastWeights* out) {
 }
 void dqn_target_changed(xq_dqn_s* h) { if (h->fast) h->fast->target_current = false; }
 
+// rows [128 tile_first, 128 (tile_first + tile_count)) of the batch (tile_count <= 0: all of them), cut into row_splits CTAs per column tile
 static int launch_gemm(xq_dqn_s* h, int mode, const CUtensorMap& tmA, const CUtensorMap& tmB, const float* b1, int64_t n, float* q,
-                       cudaStream_t stream = nullptr, float* zpart = nullptr, int row_splits = 0) {
+                       cudaStream_t stream = nullptr, float* zpart = nullptr, int row_splits = 0, int tile_first = 0, int tile_count = 0) {
     Fast* f = h->fast;
     if (!stream) stream = h->stream;
     if (!zpart) zpart = f->zpart;
-    const int m_tiles = (int)((n + BM - 1) / BM);
+    const int all_tiles = (int)((n + BM - 1) / BM);
+    const int m_tiles = tile_count > 0 ? std::min(tile_count, all_tiles - tile_first) : all_tiles - tile_first;
+    if (m_tiles <= 0) return XQ_OK;
     int n_splits = row_splits > 0 ? row_splits : 148 / kNTiles;      // default: 4 row splits x 37 column tiles = 148 CTAs
     if (n_splits > m_tiles) n_splits = m_tiles;
     const dim3 grid(kNTiles, n_splits);
     const int64_t zstride = (f->cap + BM - 1) / BM * BM;
     if (mode == EPI_ROWMAX)
-        XQ_CUDA(launch_pdl(l1_gemm_kernel<EPI_ROWMAX>, grid, dim3(kGemmThreads), kGemmSmem, stream, 1, tmA, tmB, b1, (int)n, m_tiles, n_splits,
+        XQ_CUDA(launch_pdl(l1_gemm_kernel<EPI_ROWMAX>, grid, dim3(kGemmThreads), kGemmSmem, stream, 1, tmA, tmB, b1, (int)n, tile_first, m_tiles, n_splits,
                            zpart, zstride, (float*)nullptr));
     else
-        XQ_CUDA(launch_pdl(l1_gemm_kernel<EPI_STORE_TANH>, grid, dim3(kGemmThreads), kGemmSmem, stream, 1, tmA, tmB, b1, (int)n, m_tiles, n_splits,
+        XQ_CUDA(launch_pdl(l1_gemm_kernel<EPI_STORE_TANH>, grid, dim3(kGemmThreads), kGemmSmem, stream, 1, tmA, tmB, b1, (int)n, tile_first, m_tiles, n_splits,
                            (float*)nullptr, zstride, q));
     return XQ_OK;
 }
@@ -1891,7 +1895,7 @@ int dqn_td_update_pipelined(xq_dqn_s* h, const void* ring, int64_t size, uint64_
         XQ_CUDA(cudaDeviceGetStreamPriorityRange(&lo, &hi));
         XQ_CUDA(cudaStreamCreateWithPriority(&f->main_hi, cudaStreamNonBlocking, hi));
     }
-    if (!f->ev_join) XQ_CUDA(cudaEventCreateWithFlags(&f->ev_join, cudaEventDisableTiming));
+    if (!f->ev_join) { XQ_CUDA(cudaEventCreateWithFlags(&f->ev_join, cudaEventDisableTiming)); for (int i = 0; i < 2; ++i) XQ_CUDA(cudaEventCreateWithFlags(&f->ev_tdb[i], cudaEventDisableTiming)); }
     cudaStream_t main = main_prio ? f->main_hi : h->stream, aux = f->aux;
     XQ_CUDA(cudaEventRecord(f->ev_fork, h->stream));             // the target net and the ring are final for the other streams
     XQ_CUDA(cudaStreamWaitEvent(aux, f->ev_fork, 0));
@@ -1924,6 +1928,12 @@ int dqn_td_update_pipelined(xq_dqn_s* h, const void* ring, int64_t size, uint64_
     //      i+1 -- small CTAs it co-resides with on all 148 SMs -- and is out of the way when the contraction of update i+1 wants 88 whole SMs (11
     //      clusters of 8 in one GPC each): nothing races for SMs any more.  Slot reuse: the partials slot of update i+2 was last read by the
     //      TD-error kernel of update i, h(s') of update i+2 is written after the GEMM of update i in stream order.
+    //   4  in TWO parts sized for the two windows of update i that tolerate it: part A (XQ_TD_GEMM_A_TILES of the 32 row tiles, default 20, one short
+    //      CTA per SM: 37 column tiles x 4 row splits) is released before the TD-error kernel of update i, co-resides with its small CTAs and is gone
+    //      when the contraction's 88 whole-SM CTAs want their SMs; part B (the other row tiles, 37 x 2 CTAs) is released when the TD-error kernel has
+    //      COMPLETED -- the contraction's CTAs are resident by then (programmatic dependent launch) -- and runs on the 60 SMs they leave free.  Nothing
+    //      of the GEMM is left when the h(s) gather of update i+1 (which cannot share an SM with a GEMM CTA: registers) starts: no race for SMs.
+    static const int a_tiles = [] { const char* e = getenv("XQ_TD_GEMM_A_TILES"); return e ? atoi(e) : 20; }();
     auto aux_gemm = [&](int i, cudaEvent_t gate) -> int {
         const int slot = i & 1;
         if (gate) XQ_CUDA(cudaStreamWaitEvent(aux, gate, 0));
@@ -1932,10 +1942,19 @@ int dqn_td_update_pipelined(xq_dqn_s* h, const void* ring, int64_t size, uint64_
         XQ_CUDA(cudaEventRecord(f->ev_aux[slot], aux));
         return XQ_OK;
     };
+    auto aux_gemm_part = [&](int i, cudaEvent_t gate, bool part_b) -> int {
+        const int slot = i & 1;
+        if (gate) XQ_CUDA(cudaStreamWaitEvent(aux, gate, 0));
+        if (int rc = launch_gemm(h, EPI_ROWMAX, slot ? f->tmH2_b : f->tmH2, f->tmTW1, f->tb1, n, nullptr, aux, slot ? f->zpart_b : f->zpart,
+                                 part_b ? 2 : 4, part_b ? a_tiles : 0, part_b ? 0 : a_tiles)) return rc;
+        if (part_b) XQ_CUDA(cudaEventRecord(f->ev_aux[slot], aux));
+        return XQ_OK;
+    };
     // the update before update i has consumed the slot of update i in modes 0-2: gate on its TD-error kernel (modes 1, 2) or its completion (mode 0)
     auto gate_of = [&](int i) -> cudaEvent_t { return i >= 1 ? (early ? f->ev_td[(i - 1) & 1] : f->ev_free[(i - 1) & 1]) : nullptr; };
     if (int rc = aux_l0(0)) return rc;
-    if (int rc = aux_gemm(0, nullptr)) return rc;
+    if (early == 4) { if (int rc = aux_gemm_part(0, nullptr, false)) return rc; if (int rc = aux_gemm_part(0, nullptr, true)) return rc; }
+    else if (int rc = aux_gemm(0, nullptr)) return rc;
     if (early == 3 && n_updates > 1) {      // fill: the first two bootstrap branches start at once
         if (int rc = aux_l0(1)) return rc;
         if (int rc = aux_gemm(1, nullptr)) return rc;
@@ -1949,9 +1968,11 @@ int dqn_td_update_pipelined(xq_dqn_s* h, const void* ring, int64_t size, uint64_
                            f->H2bf, f->cb, ld, f->info_slots, kInfoSlots * 4, 1));
         XQ_CUDA(cudaStreamWaitEvent(main, f->ev_aux[slot], 0));  // the row-max partials of this update
         if (early == 2) { XQ_CUDA(cudaEventRecord(f->ev_td[slot], main)); if (i + 1 < n_updates) if (int rc = aux_gemm(i + 1, gate_of(i + 1))) return rc; }
+        if (early == 4) { XQ_CUDA(cudaEventRecord(f->ev_td[slot], main)); if (i + 1 < n_updates) if (int rc = aux_gemm_part(i + 1, f->ev_td[slot], false)) return rc; }
         XQ_CUDA(launch_pdl(td_delta_kernel, dim3(blocks(n * 32, 256)), dim3(256), 0, main, 1, f->cb, n, f->Hf, f->W1, f->b1, slot ? f->zpart_b : f->zpart,
                            ld, kParts, (float)h->gamma, h->mode, f->d0hi, f->d0lo, f->ghi, f->glo, ld, f->info_slots));
         if (early == 1) { XQ_CUDA(cudaEventRecord(f->ev_td[slot], main)); if (i + 1 < n_updates) if (int rc = aux_gemm(i + 1, gate_of(i + 1))) return rc; }
+        if (early == 4) { XQ_CUDA(cudaEventRecord(f->ev_tdb[slot], main)); if (i + 1 < n_updates) if (int rc = aux_gemm_part(i + 1, f->ev_tdb[slot], true)) return rc; }
         XQ_CUDA(launch_pdl(dw_gemm_kernel, dim3(kDwMTiles, kDwSplits), dim3(kDwThreads), kDwSmem, main, kDwSplits, f->tmD0hi, f->tmD0lo, f->tmGhi,
                            f->tmGlo, f->tmCb, (int)n, f->part, f->dbpart, f->info_slots, f->info, cur_grad(f), f->W0T, f->b0, f->W1, f->b1, f->W1bf,
                            f->W1lo, (float)lr, f->connected ? 0 : 1, dw_push(f, !f->connected, fuse_exchange)));

@@ -22,6 +22,7 @@
 // Host-compilable: tests/hostsim runs it board by board and diffs every ply against the oracle before any GPU time.
 #pragma once
 #include <stdint.h>
+#include <string.h>
 
 #include "xq_rollout_team.cuh"
 
@@ -179,6 +180,109 @@ XQ_HD int lane_emit_actions(const uint32_t (&own_sq)[4], int color, const uint32
         }
     }
     return (int)tot;
+}
+
+// a > b as floats  <=>  lane_ordered_key(a) > lane_ordered_key(b) as unsigned integers (finite values; -0 == +0); 0 is below every float
+XQ_HD uint32_t lane_ordered_key(float v) {
+#if defined(__CUDA_ARCH__)
+    const uint32_t u = __float_as_uint(v);
+#else
+    uint32_t u; memcpy(&u, &v, 4);
+#endif
+    const uint32_t z = (u << 1) == 0u ? 0u : u;
+    return (z & 0x80000000u) ? ~z : (z | 0x80000000u);
+}
+
+// DQN::selectAction's greedy branch (src/dqn.cpp:39-52) over ChessAI::getAllValidActions' order without the list: the FIRST action maximising
+// Q[action.to] (strict >).  Every piece keeps the first maximum over its own actions in generator order (the 198 (piece, direction, distance)
+// slots walked straight-line with predicated Q reads, as in lane_emit_actions); the list orders pieces by square, so the winner is the piece with
+// the largest Q and, among equals, the lowest square.  q(to) reads Q(s)[to].  Requires a non-empty list; returns from | to << 8.
+template <class QGET>
+XQ_HD uint32_t lane_select_greedy(const uint32_t (&own_sq)[4], int color, const uint32_t (&sdesc)[4], const uint32_t (&cw)[4], const uint32_t (&dw)[4], QGET&& q) {
+    uint32_t best_key = 0, best_sq = 127, best_to = 0;
+    auto offer = [&](bool any, float best, uint32_t sq, uint32_t to) {      // a piece's best against the best so far: larger Q, or equal Q on a lower square
+        const uint32_t key = any ? lane_ordered_key(best) : 0u;
+        const bool better = key > best_key || (key == best_key && any && sq < best_sq);
+        best_key = better ? key : best_key; best_sq = better ? sq : best_sq; best_to = better ? to : best_to;
+    };
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        const int sq = (int)((own_sq[0] >> (8 * i)) & 0xFFu);
+        const bool alive = ((cw[0] >> (8 * i)) & 0xFFu) != 0;
+        bool any = false; float best = 0.f; uint32_t bto = 0;
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            const int e = alive ? (int)((sdesc[i] >> (8 * k)) & 15u) : 0, capdist = alive ? (int)((sdesc[i] >> (8 * k + 4)) & 15u) : 0;
+            const int step = k == 0 ? 1 : (k == 1 ? -1 : (k == 2 ? 9 : -9));
+            constexpr int kMaxSlide[4] = {8, 8, 9, 9};
+#pragma unroll
+            for (int d = 1; d <= kMaxSlide[k]; ++d) {
+                const bool live = d <= e;
+                const int to = sq + step * d;
+                const float v = live ? q(to) : 0.f;
+                const bool take = live && (!any || v > best);
+                best = take ? v : best; bto = take ? (uint32_t)to : bto; any |= live;
+            }
+            const bool live = capdist != 0;
+            const int to = sq + step * capdist;
+            const float v = live ? q(to) : 0.f;
+            const bool take = live && (!any || v > best);
+            best = take ? v : best; bto = take ? (uint32_t)to : bto; any |= live;
+        }
+        offer(any, best, (uint32_t)sq, bto);
+    }
+#pragma unroll
+    for (int pos = 4; pos < 16; ++pos) {
+        const int sq = (int)((own_sq[pos >> 2] >> (8 * (pos & 3))) & 0xFFu);
+        const uint32_t m = (dw[pos >> 2] >> (8 * (pos & 3))) & 0xFFu;
+        uint32_t hi;
+        const uint32_t lo = lane_dir_table(pos, color, &hi);
+        const int ndir = pos < 6 ? 8 : (pos < 11 ? 4 : 3);
+        bool any = false; float best = 0.f; uint32_t bto = 0;
+#pragma unroll
+        for (int k = 0; k < ndir; ++k) {
+            const bool live = (m >> k) & 1u;
+            const int to = sq + (int)(int8_t)(uint8_t)((k < 4 ? lo : hi) >> (8 * (k & 3)));
+            const float v = live ? q(to) : 0.f;
+            const bool take = live && (!any || v > best);
+            best = take ? v : best; bto = take ? (uint32_t)to : bto; any |= live;
+        }
+        offer(any, best, (uint32_t)sq, bto);
+    }
+    return best_sq | (best_to << 8);
+}
+
+// the k-th action of the reference-ordered list (DQN::selectAction's exploring branch, src/dqn.cpp:30-34; the random policy of the rollout):
+// bisection over the squares on g(s) = actions of pieces on squares <= s, then the decode from the owner's descriptor.  k < tot.  from | to << 8.
+XQ_HD uint32_t lane_select_kth(const uint32_t (&own_sq)[4], int color, const uint32_t (&sdesc)[4], const uint32_t (&cw)[4], const uint32_t (&dw)[4], uint32_t k, uint32_t tot) {
+    uint32_t lo = 0, hi = XQ_SQUARES - 1, g_hi = tot;
+#pragma unroll
+    for (int it = 0; it < 7; ++it) {
+        const uint32_t mid = (lo + hi) >> 1;
+        const uint32_t g = lane_actions_below(own_sq, cw, mid + 1);
+        const bool up = g > k;
+        hi = up ? mid : hi; g_hi = up ? g : g_hi; lo = up ? lo : mid + 1;
+    }
+    const int from = (int)hi;
+    uint32_t zb[4], cnt_hit = 0, lmask = 0;
+#pragma unroll
+    for (int w = 0; w < 4; ++w) {
+        zb[w] = ((0x80808080u - (own_sq[w] ^ ((uint32_t)from * 0x01010101u))) & 0x80808080u) >> 7;
+        cnt_hit = dp4a_u(cw[w], zb[w], cnt_hit);
+        if (w) lmask = dp4a_u(dw[w], zb[w], lmask);
+    }
+    const uint32_t want = k - (g_hi - cnt_hit);
+    const uint32_t hdesc = (zb[0] & 0x00000001u) ? sdesc[0] : ((zb[0] & 0x00000100u) ? sdesc[1] : ((zb[0] & 0x00010000u) ? sdesc[2] : sdesc[3]));
+    const int to_s = slider_decode(hdesc, from, (int)want);
+    const uint32_t flip = color ? 0xFEu : 0u;
+    uint32_t tlo = 0x0001FF09u ^ flip, thi = 0u;
+    tlo = (zb[1] & 0x00000101u) ? 0xF5F9070Bu : tlo; thi = (zb[1] & 0x00000101u) ? 0xEDEF1113u : 0u;
+    tlo = (zb[1] & 0x01010000u) ? 0xECF01014u : tlo;
+    tlo = (zb[2] & 0x00000101u) ? 0xF6F8080Au : tlo;
+    tlo = (zb[2] & 0x00010000u) ? 0xFF01F709u : tlo;
+    const int dk = nth_set_bit8(lmask, (int)want & 7);
+    const int to_l = from + (int)(int8_t)(uint8_t)((((uint64_t)thi << 32) | tlo) >> (8 * dk));
+    return (uint32_t)from | ((uint32_t)(zb[0] ? to_s : to_l) << 8);
 }
 
 // One ply of ChessAI::train's loop body without the network (src/chessai.cpp:96-119) on one board.

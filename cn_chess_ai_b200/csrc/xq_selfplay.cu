@@ -36,6 +36,10 @@ cudaError_t launch_act_team(bool apply, xq_env_rec* envs, int64_t n, uint64_t en
                             uint16_t* actions_out, void* ring, int64_t ring_cap, int64_t ring_pos, xq_env_stats* stats, xq_game_event* events,
                             unsigned long long* event_count, int64_t event_cap, uint32_t event_ply, uint8_t* nonstd, const ActCarry* carry, uint32_t event_env0, cudaStream_t stream);
 
+cudaError_t launch_act_lane(bool apply, xq_env_rec* envs, int64_t n, uint64_t env_id0, uint64_t seed, const float* q90, uint32_t eps_thr, int train_done,
+                            uint16_t* actions_out, void* ring, int64_t ring_cap, int64_t ring_pos, xq_env_stats* stats, xq_game_event* events,
+                            unsigned long long* event_count, int64_t event_cap, uint32_t event_ply, uint8_t* nonstd, const ActCarry* carry, uint32_t event_env0, cudaStream_t stream);
+
 // Action selection (+ optional application), generic thread-per-board version (ordered list staged in shared memory): the fallback
 // of act_team_kernel (xq_act_team.cu) for boards with non-standard piece sets, or for every env with XQ_ACT_TEAM=0 (A/B runs).
 template <bool APPLY>
@@ -220,7 +224,12 @@ static int order_after(cudaStream_t waiter, cudaStream_t producer, cudaEvent_t* 
 static int launch_act(bool apply, const EnvInfo& ei, const float* q90, uint32_t thr, int train_done, uint16_t* actions, Transition* ring, int64_t ring_cap,
                       int64_t ring_pos, xq_env_stats* stats, uint32_t event_ply, const ActCarry* carry = nullptr, uint32_t event_env0 = 0) {
     static const bool team = [] { const char* e = getenv("XQ_ACT_TEAM"); return !(e && atoi(e) == 0); }();
-    if (team) XQ_CUDA(launch_act_team(apply, ei.d_envs, ei.n, ei.env_id0, ei.seed, q90, thr, train_done, actions, ring, ring_cap, ring_pos, stats,
+    // XQ_ACT_LANE=1: the board-per-thread kernel (xq_act_lane.cu) instead of the 4-threads-per-board kernel (xq_act_team.cu); same results.
+    // Measured at 65,536 envs: 74.7 us per ply against 60.5 -- see the header of xq_act_lane.cu -- so the team kernel stays the default.
+    static const bool lane = [] { const char* e = getenv("XQ_ACT_LANE"); return e && atoi(e) != 0; }();
+    if (team && lane) XQ_CUDA(launch_act_lane(apply, ei.d_envs, ei.n, ei.env_id0, ei.seed, q90, thr, train_done, actions, ring, ring_cap, ring_pos, stats,
+                                              ei.d_events, ei.d_event_count, ei.event_cap, event_ply, ei.d_nonstd, carry, event_env0, ei.stream));
+    else if (team) XQ_CUDA(launch_act_team(apply, ei.d_envs, ei.n, ei.env_id0, ei.seed, q90, thr, train_done, actions, ring, ring_cap, ring_pos, stats,
                                       ei.d_events, ei.d_event_count, ei.event_cap, event_ply, ei.d_nonstd, carry, event_env0, ei.stream));
     if (!team || ei.maybe_nonstd) {
         const uint8_t* only = team ? ei.d_nonstd : nullptr;

@@ -57,6 +57,7 @@ def hostsim():
     H.hs_valid_moves.argtypes = [P, C.c_int, C.c_int, P]
     H.hs_is_valid_move.argtypes = [P, C.c_int, C.c_int, C.c_int, C.c_int]
     H.hs_act_team.argtypes = [P, C.c_long, C.c_uint64, C.c_uint64, P, C.c_uint32, P]
+    H.hs_act_lane.argtypes = [P, C.c_long, C.c_uint64, C.c_uint64, P, C.c_uint32, P]
     H.hs_team_rollout.argtypes = [C.c_int, P, C.c_long, C.c_uint64, C.c_uint64, C.c_int, P, P]
     H.hs_lane_rollout.argtypes = [P, C.c_long, C.c_uint64, C.c_uint64, C.c_int, P, P]
     H.hs_lane_all_actions.argtypes = [P, C.c_long, P, P]

@@ -200,6 +200,35 @@ int hs_lane_all_actions(const xq_env_rec* recs, long n, uint8_t* counts, uint16_
     }
     return nonstd;
 }
+// DQN::selectAction through the board-per-thread functions (act_lane_kernel): same contract as hs_act_team
+int hs_act_lane(const xq_env_rec* recs, long n, uint64_t env_id0, uint64_t seed, const float* q90, uint32_t eps_thr, uint16_t* actions) {
+    int nonstd = 0;
+    uint32_t magic[XQ_MAX_ACTIONS + 1] = {0};
+    for (int d = 1; d <= XQ_MAX_ACTIONS; ++d) magic[d] = xq::team_mod_magic((uint32_t)d);
+    for (long i = 0; i < n; ++i) {
+        actions[i] = XQ_ACTION_NONE;
+        uint8_t slot[32];
+        for (int k = 0; k < 32; ++k) slot[k] = xq::kDeadSq;
+        uint32_t w[12];
+        std::memcpy(w, recs[i].sq, 48);
+        xq::Bits90 red, black, occT;
+        if (!xq::team_unpack_record(w, red, black, occT, [&](int s, int q) { slot[s] = (uint8_t)q; })) { ++nonstd; continue; }
+        const int player = recs[i].player;
+        uint32_t own_sq[4] = {0, 0, 0, 0};
+        for (int pos = 0; pos < 16; ++pos) own_sq[pos >> 2] |= (uint32_t)slot[(player ? 16 : 0) + xq::lane_pos_slot(pos)] << (8 * (pos & 3));
+        uint32_t sdesc[4], cw[4], dw[4], tot = 0;
+        xq::lane_movegen(own_sq, player ? black : red, player ? red : black, occT, player, sdesc, cw, dw);
+        for (int k = 0; k < 4; ++k) tot = xq::dp4a_u(cw[k], 0x01010101u, tot);
+        if (tot == 0) continue;
+        const uint64_t x = xq::rng(seed, env_id0 + (uint64_t)i, recs[i].ctr);
+        const uint32_t coin31 = (uint32_t)(x & 0x7FFFFFFFu), idx31 = (uint32_t)(x >> 33);
+        const float* q = q90 + i * 96;
+        const uint32_t mv = coin31 < eps_thr ? xq::lane_select_kth(own_sq, player, sdesc, cw, dw, xq::team_mod(idx31, tot, magic[tot]), tot)
+                                             : xq::lane_select_greedy(own_sq, player, sdesc, cw, dw, [&](int to) { return q[to]; });
+        actions[i] = XQ_ACTION(mv & 0xFFu, (mv >> 8) & 0xFFu);
+    }
+    return nonstd;
+}
 int hs_lane_rollout(xq_env_rec* recs, long n, uint64_t env_id0, uint64_t seed, int n_plies, xq_trace_rec* trace, xq_env_stats* stats) {
     return lane_rollout_host(recs, n, env_id0, seed, n_plies, trace, stats);
 }

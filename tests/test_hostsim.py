@@ -168,14 +168,17 @@ def test_team_act_selection(O, oracle_lib, hostsim):
         elif case == "signed zero":
             q = np.where(rng.integers(0, 2, (n, 96)) == 1, np.float32(0.0), np.float32(-0.0)).astype(np.float32)
         thr = oracle_lib.xqo_eps_threshold(eps)
-        got = np.zeros(n, np.uint16)
-        assert hostsim.hs_act_team(recs.ctypes.data, n, 31, 77, q.ctypes.data, thr, got.ctypes.data) == 0
         x = O.rng_np(77, ids, recs["ctr"])
         coin, idx = (x & np.uint64(0x7FFFFFFF)).astype(np.uint32), (x >> np.uint64(33)).astype(np.uint32)
+        want = np.zeros(n, np.uint16)
         for i in range(n):
             qi = np.zeros(8100); qi[:96] = q[i]
-            k = oracle_lib.xqo_select_action(qi, lists[i], int(counts[i]), int(coin[i]), int(idx[i]), eps)
-            assert got[i] == lists[i, k], (case, i, int(got[i]) >> 7, int(got[i]) & 127, int(lists[i, k]) >> 7, int(lists[i, k]) & 127)
+            want[i] = lists[i, oracle_lib.xqo_select_action(qi, lists[i], int(counts[i]), int(coin[i]), int(idx[i]), eps)]
+        for name, fn in (("team", hostsim.hs_act_team), ("lane", hostsim.hs_act_lane)):      # act_team_kernel's phases; act_lane_kernel's functions
+            got = np.zeros(n, np.uint16)
+            assert fn(recs.ctypes.data, n, 31, 77, q.ctypes.data, thr, got.ctypes.data) == 0
+            bad = np.nonzero(got != want)[0]
+            assert len(bad) == 0, (name, case, len(bad), int(bad[0]), int(got[bad[0]]) >> 7, int(got[bad[0]]) & 127, int(want[bad[0]]) >> 7, int(want[bad[0]]) & 127)
 
 
 def test_team_phases_under_sanitizers(tmp_path):

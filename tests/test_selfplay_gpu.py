@@ -1,3 +1,4 @@
+import os
 """GPU tests of the replay buffer, batched epsilon-greedy action selection and the self-play collector
 (BASELINE configs 3/4).  Selection parity is checked GIVEN identical Q inputs (SURVEY section 7, last bullet):
 the Q-values the GPU used are fed to the oracle's restatement of DQN::selectAction with the same draws."""
@@ -5,6 +6,7 @@ import numpy as np
 import pytest
 
 pytestmark = pytest.mark.gpu
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 LAYERS = [1260, 128, 8100]
 LA = np.array(LAYERS, np.int32)
 
@@ -232,6 +234,41 @@ def test_two_stream_collector_plies(xq, O, oracle_lib):
     assert envA.get_boards().tobytes() == ref.tobytes()
     assert dropped == 0 and len(finished) > 20
     assert [(int(e["ply"]), int(e["env"]), int(e["red_score"]), int(e["black_score"])) for e in events] == finished
+
+
+def test_board_per_thread_act_kernel_is_bit_identical(tmp_path):
+    """act_lane_kernel (XQ_ACT_LANE=1; xq_act_lane.cu: selection + apply + carried layer-0 tail with one thread per board) against the default
+    act_team_kernel: the same transitions in the replay ring, the same finished-game events, the same final boards and statistics, bit for
+    bit, over 60 collector plies (two streams, carried sums, restarts, ragged env count) -- and xq_dqn_act chooses the same actions"""
+    import hashlib, subprocess, sys, textwrap
+    script = tmp_path / "collect_digest.py"
+    script.write_text(textwrap.dedent("""
+        import hashlib, sys
+        import numpy as np
+        sys.path.insert(0, %r)
+        import cn_chess_ai_b200 as xq
+        from cn_chess_ai_b200.trainer import drain_game_events, enable_game_events
+        rng = np.random.default_rng(31)
+        net = xq.DQN([1260, 128, 8100]); net.set_params(rng.uniform(-0.05, 0.05, net.n_weights), rng.uniform(-0.05, 0.05, net.n_biases))
+        n, plies = 16500, 60
+        env = xq.BatchedEnv(n, seed=17, env_id0=1000)
+        rb = xq.ReplayBuffer(n * plies)
+        enable_game_events(env, n * plies)
+        xq.collect(net, env, rb, plies, 0.3, train_done=True)
+        env.sync()
+        ev, dropped = drain_game_events(env)
+        acts = xq.act(net, env, 0.1)
+        h = hashlib.sha256()
+        for a in (rb.get(0, n * plies), env.get_boards(), ev, acts, np.frombuffer(env.stats().tobytes(), np.uint8)):
+            h.update(np.ascontiguousarray(a).tobytes())
+        print("DIGEST", h.hexdigest(), len(ev), dropped)
+    """ % ROOT))
+    out = {}
+    for lane in ("0", "1"):
+        r = subprocess.run([sys.executable, str(script)], capture_output=True, text=True, timeout=600, env=dict(os.environ, XQ_ACT_LANE=lane))
+        assert r.returncode == 0, r.stderr[-2000:]
+        out[lane] = [ln for ln in r.stdout.splitlines() if ln.startswith("DIGEST")][0]
+    assert out["0"] == out["1"] and int(out["0"].split()[2]) > 20, out
 
 
 def test_td_update_from_replay_matches_host_batch(xq, O):
