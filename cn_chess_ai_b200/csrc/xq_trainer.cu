@@ -77,9 +77,19 @@ int gather_round(xq_dqn_t h, int world, const std::vector<xq_game_event>& ev, in
             }
         }
     }
-    std::stable_sort(merged->begin(), merged->end(), [](const GlobalEvent& a, const GlobalEvent& b) {
-        return a.e.ply != b.e.ply ? a.e.ply < b.e.ply : a.genv < b.genv;
-    });
+    // every rank's events arrive sorted by (ply, env) (xq_env_drain_game_events): group them by rank (chunks of one rank may be interleaved with other
+    // ranks' chunks), then merge the `world` sorted runs pairwise -- n log(world) comparisons instead of a full sort of thousands of records per round
+    auto less = [](const GlobalEvent& a, const GlobalEvent& b) { return a.e.ply != b.e.ply ? a.e.ply < b.e.ply : a.genv < b.genv; };
+    if (max_n > kEventsFirst) {
+        std::stable_sort(merged->begin(), merged->end(), less);      // rare: some rank finished more than 2,729 games in one round
+    } else {
+        std::vector<size_t> bound((size_t)world + 1, 0);
+        for (int r = 0; r < world; ++r) bound[(size_t)r + 1] = bound[(size_t)r] + (size_t)std::min(hd[(size_t)r].n_events, kEventsFirst);
+        for (int width = 1; width < world; width *= 2)
+            for (int r = 0; r + width < world; r += 2 * width)
+                std::inplace_merge(merged->begin() + (ptrdiff_t)bound[(size_t)r], merged->begin() + (ptrdiff_t)bound[(size_t)(r + width)],
+                                   merged->begin() + (ptrdiff_t)bound[(size_t)std::min(r + 2 * width, world)], less);
+    }
     return XQ_OK;
 }
 double now_s() { return std::chrono::duration<double>(std::chrono::steady_clock::now().time_since_epoch()).count(); }

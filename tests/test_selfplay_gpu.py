@@ -1,7 +1,8 @@
-import os
 """GPU tests of the replay buffer, batched epsilon-greedy action selection and the self-play collector
 (BASELINE configs 3/4).  Selection parity is checked GIVEN identical Q inputs (SURVEY section 7, last bullet):
 the Q-values the GPU used are fed to the oracle's restatement of DQN::selectAction with the same draws."""
+import os
+
 import numpy as np
 import pytest
 
