@@ -201,7 +201,8 @@ __device__ __forceinline__ unsigned long long warp_sum(unsigned long long v) {
 
 __global__ void __launch_bounds__(kThreads) rollout_random_kernel(xq_env_rec* __restrict__ envs, int64_t n, uint64_t env_id0,
                                                                  uint64_t seed, int n_plies, xq_trace_rec* __restrict__ trace,
-                                                                 xq_env_stats* __restrict__ stats, const uint8_t* __restrict__ only) {
+                                                                 xq_env_stats* __restrict__ stats, const uint8_t* __restrict__ only,
+                                                                 xq_env_rec* __restrict__ mirror /* mapped host copy of the final boards, or null */) {
     __shared__ uint32_t s_board[12 * kThreads];
     __shared__ uint32_t s_list[64 * kThreads];   // action list, u16 pairs, word-interleaved by thread
     const int tid = threadIdx.x;
@@ -258,6 +259,7 @@ __global__ void __launch_bounds__(kThreads) rollout_random_kernel(xq_env_rec* __
         }
         b.store(envs + env);
         m.store(envs + env);
+        if (mirror) { b.store(mirror + env); m.store(mirror + env); }
     }
     if (stats) {
         unsigned long long v[8] = {st.steps, st.games, st.red_wins, st.black_wins, st.cap_games, st.captures,
@@ -307,9 +309,9 @@ namespace xq {
 cudaError_t launch_rollout_slots(xq_env_rec* envs, int64_t n, uint64_t env_id0, uint64_t seed, int n_plies, xq_trace_rec* trace,
                                  xq_env_stats* stats, uint8_t* nonstd, cudaStream_t stream);
 cudaError_t launch_rollout_team(int team, xq_env_rec* envs, int64_t n, uint64_t env_id0, uint64_t seed, int n_plies, xq_trace_rec* trace,
-                                xq_env_stats* stats, uint8_t* nonstd, cudaStream_t stream);
+                                xq_env_stats* stats, uint8_t* nonstd, cudaStream_t stream, const xq_env_rec* src, xq_env_rec* mirror);
 cudaError_t launch_rollout_lane(xq_env_rec* envs, int64_t n, uint64_t env_id0, uint64_t seed, int n_plies, xq_trace_rec* trace, xq_env_stats* stats,
-                                uint8_t* nonstd, cudaStream_t stream);
+                                uint8_t* nonstd, cudaStream_t stream, const xq_env_rec* src, xq_env_rec* mirror);
 cudaError_t launch_legal_moves_lane(const xq_env_rec* envs, int64_t n, uint8_t* counts, uint32_t* actions, uint8_t* nonstd, cudaStream_t stream);
 cudaError_t launch_pick_random(const xq_env_rec* envs, int64_t n, uint64_t env_id0, uint64_t seed, const uint8_t* counts, const uint16_t* lists, uint16_t* out,
                                cudaStream_t stream);
@@ -344,18 +346,29 @@ static int rollout_team(int64_t n) {
 }
 // Fused rollout = team kernel (xq_rollout_team.cu; or the 16-thread slot kernel, xq_rollout.cu) for every board with a standard piece set, then the generic
 // thread-per-board kernel for the boards it flagged (only possible after xq_env_set_boards injected exotic positions).
-static int launch_rollout(xq_env_s* h, int n_plies, xq_trace_rec* d_trace) {
+// src / mirror (optional, xq_env_rollout_random_io with pinned host buffers): the kernels read the boards straight from MAPPED host memory and
+// write the final boards to mapped host memory as well as to the device array -- no copy launches on the stream.  A board the first kernel leaves
+// to the generic one is copied host -> device by the first kernel, so the generic kernel always starts from the device array.
+static int launch_rollout(xq_env_s* h, int n_plies, xq_trace_rec* d_trace, const xq_env_rec* src = nullptr, xq_env_rec* mirror = nullptr) {
     if (n_plies >= (1 << 24)) return fail(XQ_ERR_INVALID, "rollout: n_plies must be < 2^24 per launch");
     const int team = rollout_team(h->n);
-    if (team == 1) XQ_CUDA(launch_rollout_lane(h->d_envs, h->n, h->env_id0, h->seed, n_plies, d_trace, h->d_stats, h->d_nonstd, h->stream));
+    if (team == 1) XQ_CUDA(launch_rollout_lane(h->d_envs, h->n, h->env_id0, h->seed, n_plies, d_trace, h->d_stats, h->d_nonstd, h->stream, src, mirror));
     else if (team == 16) XQ_CUDA(launch_rollout_slots(h->d_envs, h->n, h->env_id0, h->seed, n_plies, d_trace, h->d_stats, h->d_nonstd, h->stream));
-    else XQ_CUDA(launch_rollout_team(team, h->d_envs, h->n, h->env_id0, h->seed, n_plies, d_trace, h->d_stats, h->d_nonstd, h->stream));
+    else XQ_CUDA(launch_rollout_team(team, h->d_envs, h->n, h->env_id0, h->seed, n_plies, d_trace, h->d_stats, h->d_nonstd, h->stream, src, mirror));
     if (h->maybe_nonstd) {
         rollout_random_kernel<<<grid_for(h->n, kThreads), kThreads, 0, h->stream>>>(h->d_envs, h->n, h->env_id0, h->seed, n_plies, d_trace,
-                                                                                    h->d_stats, h->d_nonstd);
+                                                                                    h->d_stats, h->d_nonstd, mirror);
         XQ_LAUNCH_CHECK();
     }
     return XQ_OK;
+}
+// device alias of a pinned, mapped, 16-byte aligned host buffer (cudaHostAlloc / cudaHostRegister under unified addressing), or null
+static void* mapped_alias(const void* host) {
+    static const bool on = [] { const char* e = getenv("XQ_IO_ZEROCOPY"); return !(e && atoi(e) == 0); }();
+    if (!on || !host || (reinterpret_cast<uintptr_t>(host) & 15u)) return nullptr;
+    cudaPointerAttributes a;
+    if (cudaPointerGetAttributes(&a, host) != cudaSuccess) { cudaGetLastError(); return nullptr; }
+    return a.type == cudaMemoryTypeHost ? a.devicePointer : nullptr;
 }
 
 namespace xq {
@@ -647,13 +660,17 @@ int xq_env_rollout_random_io(xq_env_t h, const xq_env_rec* boards_in_host, int n
     if (n_plies < 0) return fail(XQ_ERR_INVALID, "xq_env_rollout_random: n_plies < 0");
     const int64_t need = (int64_t)n_plies * h->n;
     if (trace_host) if (int rc = reserve_trace(h, need)) return rc;
+    // pinned (mapped) host buffers are read / written by the rollout kernel itself: two copy launches less on the stream (XQ_IO_ZEROCOPY=0: always copy)
+    const bool direct = rollout_team(h->n) != 16;
+    const xq_env_rec* src = direct ? static_cast<const xq_env_rec*>(mapped_alias(boards_in_host)) : nullptr;
+    xq_env_rec* mirror = direct ? static_cast<xq_env_rec*>(mapped_alias(boards_out_host)) : nullptr;
     if (boards_in_host) {
-        XQ_CUDA(cudaMemcpyAsync(h->d_envs, boards_in_host, sizeof(xq_env_rec) * h->n, cudaMemcpyHostToDevice, h->stream));
+        if (!src) XQ_CUDA(cudaMemcpyAsync(h->d_envs, boards_in_host, sizeof(xq_env_rec) * h->n, cudaMemcpyHostToDevice, h->stream));
         h->maybe_nonstd = true;
     }
     XQ_CUDA(cudaMemsetAsync(h->d_stats, 0, sizeof(xq_env_stats), h->stream));
-    if (int rc = launch_rollout(h, n_plies, trace_host ? h->d_trace : nullptr)) return rc;
-    if (boards_out_host) XQ_CUDA(cudaMemcpyAsync(boards_out_host, h->d_envs, sizeof(xq_env_rec) * h->n, cudaMemcpyDeviceToHost, h->stream));
+    if (int rc = launch_rollout(h, n_plies, trace_host ? h->d_trace : nullptr, src, mirror)) return rc;
+    if (boards_out_host && !mirror) XQ_CUDA(cudaMemcpyAsync(boards_out_host, h->d_envs, sizeof(xq_env_rec) * h->n, cudaMemcpyDeviceToHost, h->stream));
     if (trace_host) XQ_CUDA(cudaMemcpyAsync(trace_host, h->d_trace, sizeof(xq_trace_rec) * need, cudaMemcpyDeviceToHost, h->stream));
     if (stats_host) XQ_CUDA(cudaMemcpyAsync(stats_host, h->d_stats, sizeof(xq_env_stats), cudaMemcpyDeviceToHost, h->stream));
     XQ_CUDA(cudaStreamSynchronize(h->stream));

@@ -15,7 +15,8 @@ constexpr int kLaneMaxThreads = 128;
 
 __global__ void __launch_bounds__(kLaneMaxThreads) rollout_lane_kernel(xq_env_rec* __restrict__ envs, int64_t n, uint64_t env_id0, uint64_t seed, int n_plies,
                                                                       xq_trace_rec* __restrict__ trace, xq_env_stats* __restrict__ stats,
-                                                                      uint8_t* __restrict__ nonstd) {
+                                                                      uint8_t* __restrict__ nonstd, const xq_env_rec* __restrict__ src,
+                                                                      xq_env_rec* __restrict__ mirror) {
     __shared__ uint8_t s_slot[32 * kLaneMaxThreads];      // [slot][thread]
     __shared__ uint32_t s_magic[XQ_MAX_ACTIONS + 1];
     const int tid = threadIdx.x, bs = blockDim.x;
@@ -26,11 +27,17 @@ __global__ void __launch_bounds__(kLaneMaxThreads) rollout_lane_kernel(xq_env_re
     bool active = env < n;
     uint32_t flags = 0;
     if (active) {
-        const uint4* rec = reinterpret_cast<const uint4*>(envs + env);
+        const uint4* rec = reinterpret_cast<const uint4*>((src ? src : envs) + env);      // src: mapped host boards (xq_env_rollout_random_io)
         uint32_t w[12];
 #pragma unroll
         for (int i = 0; i < 3; ++i) { const uint4 v = rec[i]; w[4 * i] = v.x; w[4 * i + 1] = v.y; w[4 * i + 2] = v.z; w[4 * i + 3] = v.w; }
         const uint4 m = rec[3];
+        if (src) {      // the device array follows the host boards (a board left to the generic kernel is read from there)
+            uint4* d = reinterpret_cast<uint4*>(envs + env);
+#pragma unroll
+            for (int i = 0; i < 3; ++i) d[i] = make_uint4(w[4 * i], w[4 * i + 1], w[4 * i + 2], w[4 * i + 3]);
+            d[3] = m;
+        }
         for (int i = 0; i < 32; ++i) s_slot[i * bs + tid] = kDeadSq;
         Bits90 red, black, occT;
         active = team_unpack_record(w, red, black, occT, [&](int s, int q) { s_slot[s * bs + tid] = (uint8_t)q; });
@@ -53,6 +60,12 @@ __global__ void __launch_bounds__(kLaneMaxThreads) rollout_lane_kernel(xq_env_re
 #pragma unroll
         for (int i = 0; i < 3; ++i) rec[i] = make_uint4(words[4 * i], words[4 * i + 1], words[4 * i + 2], words[4 * i + 3]);
         rec[3] = make_uint4((uint32_t)(st.move_count & 0xFFFF) | ((uint32_t)st.player << 16) | flags, (uint32_t)st.red, (uint32_t)st.black, st.ctr);
+        if (mirror) {   // the same record into the caller's mapped host buffer
+            uint4* mr = reinterpret_cast<uint4*>(mirror + env);
+#pragma unroll
+            for (int i = 0; i < 3; ++i) mr[i] = make_uint4(words[4 * i], words[4 * i + 1], words[4 * i + 2], words[4 * i + 3]);
+            mr[3] = make_uint4((uint32_t)(st.move_count & 0xFFFF) | ((uint32_t)st.player << 16) | flags, (uint32_t)st.red, (uint32_t)st.black, st.ctr);
+        }
     }
     if (stats) {
         unsigned long long v[8] = {a.steps, a.games, a.red, a.black, a.capg, a.caps, (unsigned long long)a.reward, a.legal};
@@ -146,9 +159,9 @@ cudaError_t launch_pick_random(const xq_env_rec* envs, int64_t n, uint64_t env_i
 }
 
 cudaError_t launch_rollout_lane(xq_env_rec* envs, int64_t n, uint64_t env_id0, uint64_t seed, int n_plies, xq_trace_rec* trace, xq_env_stats* stats,
-                                uint8_t* nonstd, cudaStream_t stream) {
+                                uint8_t* nonstd, cudaStream_t stream, const xq_env_rec* src, xq_env_rec* mirror) {
     const int bs = n <= 148 * 4 * 32 ? 32 : kLaneMaxThreads;
-    rollout_lane_kernel<<<(unsigned)((n + bs - 1) / bs), bs, 0, stream>>>(envs, n, env_id0, seed, n_plies, trace, stats, nonstd);
+    rollout_lane_kernel<<<(unsigned)((n + bs - 1) / bs), bs, 0, stream>>>(envs, n, env_id0, seed, n_plies, trace, stats, nonstd, src, mirror);
     ++g_launches;
     return cudaGetLastError();
 }

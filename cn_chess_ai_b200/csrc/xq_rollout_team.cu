@@ -25,7 +25,8 @@ struct TeamIo {           // conversion buffers, [item][board]
 template <int T>
 __global__ void __launch_bounds__(kTB * T) rollout_team_kernel(xq_env_rec* __restrict__ envs, int64_t n, uint64_t env_id0, uint64_t seed, int n_plies,
                                                                   xq_trace_rec* __restrict__ trace, xq_env_stats* __restrict__ stats,
-                                                                  uint8_t* __restrict__ nonstd) {
+                                                                  uint8_t* __restrict__ nonstd, const xq_env_rec* __restrict__ src,
+                                                                  xq_env_rec* __restrict__ mirror) {
     __shared__ TeamShared<kTB> sh;
     __shared__ TeamIo io;
     const int tid = threadIdx.x, lane = tid & 31;
@@ -38,11 +39,17 @@ __global__ void __launch_bounds__(kTB * T) rollout_team_kernel(xq_env_rec* __res
     if (R.role == 0) {
         bool ok = env < n;
         if (ok) {
-            const uint4* rec = reinterpret_cast<const uint4*>(envs + env);
+            const uint4* rec = reinterpret_cast<const uint4*>((src ? src : envs) + env);      // src: mapped host boards (xq_env_rollout_random_io)
             uint32_t w[12];
 #pragma unroll
             for (int i = 0; i < 3; ++i) { const uint4 v = rec[i]; w[4 * i] = v.x; w[4 * i + 1] = v.y; w[4 * i + 2] = v.z; w[4 * i + 3] = v.w; }
             const uint4 m = rec[3];
+            if (src) {      // the device array follows the host boards (a board left to the generic kernel is read from there)
+                uint4* d = reinterpret_cast<uint4*>(envs + env);
+#pragma unroll
+                for (int i = 0; i < 3; ++i) d[i] = make_uint4(w[4 * i], w[4 * i + 1], w[4 * i + 2], w[4 * i + 3]);
+                d[3] = m;
+            }
             for (int i = 0; i < 32; ++i) io.slot[i * kTB + lane] = kDeadSq;
             Bits90 red, black, occT;
             ok = team_unpack_record(w, red, black, occT, [&](int s, int q) { io.slot[s * kTB + lane] = (uint8_t)q; });
@@ -142,6 +149,14 @@ __global__ void __launch_bounds__(kTB * T) rollout_team_kernel(xq_env_rec* __res
                                     io.words[(4 * i + 3) * kTB + lane]);
             const uint32_t flags = io.meta[0 * kTB + lane] & 0xFF000000u;
             rec[3] = make_uint4((uint32_t)(st.move_count & 0xFFFF) | ((uint32_t)st.player << 16) | flags, (uint32_t)bk.red, (uint32_t)bk.black, st.ctr);
+            if (mirror) {   // the same record into the caller's mapped host buffer
+                uint4* mr = reinterpret_cast<uint4*>(mirror + env);
+#pragma unroll
+                for (int i = 0; i < 3; ++i)
+                    mr[i] = make_uint4(io.words[(4 * i) * kTB + lane], io.words[(4 * i + 1) * kTB + lane], io.words[(4 * i + 2) * kTB + lane],
+                                       io.words[(4 * i + 3) * kTB + lane]);
+                mr[3] = make_uint4((uint32_t)(st.move_count & 0xFFFF) | ((uint32_t)st.player << 16) | flags, (uint32_t)bk.red, (uint32_t)bk.black, st.ctr);
+            }
         } else {
             bk = TeamBook{0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0};
         }
@@ -159,10 +174,10 @@ __global__ void __launch_bounds__(kTB * T) rollout_team_kernel(xq_env_rec* __res
 }
 
 cudaError_t launch_rollout_team(int team, xq_env_rec* envs, int64_t n, uint64_t env_id0, uint64_t seed, int n_plies, xq_trace_rec* trace,
-                                xq_env_stats* stats, uint8_t* nonstd, cudaStream_t stream) {
+                                xq_env_stats* stats, uint8_t* nonstd, cudaStream_t stream, const xq_env_rec* src, xq_env_rec* mirror) {
     const unsigned grid = (unsigned)((n + kTB - 1) / kTB);
-    if (team == 8) rollout_team_kernel<8><<<grid, kTB * 8, 0, stream>>>(envs, n, env_id0, seed, n_plies, trace, stats, nonstd);
-    else rollout_team_kernel<4><<<grid, kTB * 4, 0, stream>>>(envs, n, env_id0, seed, n_plies, trace, stats, nonstd);
+    if (team == 8) rollout_team_kernel<8><<<grid, kTB * 8, 0, stream>>>(envs, n, env_id0, seed, n_plies, trace, stats, nonstd, src, mirror);
+    else rollout_team_kernel<4><<<grid, kTB * 4, 0, stream>>>(envs, n, env_id0, seed, n_plies, trace, stats, nonstd, src, mirror);
     ++g_launches;
     return cudaGetLastError();
 }

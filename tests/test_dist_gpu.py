@@ -122,3 +122,59 @@ def test_peer_memory_exchange_matches_nccl(tmp_path):
     r = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", str(n), "--master-addr", "127.0.0.1",
                         "--master-port", "29533", str(script)], capture_output=True, text=True, timeout=600)
     assert r.returncode == 0 and "DIST_GPU_OK" in r.stdout, r.stdout[-2000:] + r.stderr[-4000:]
+
+
+TIMEOUT_WORKER = textwrap.dedent("""
+    import os, sys, time
+    import numpy as np
+    import torch
+    import torch.distributed as dist
+    sys.path.insert(0, %r)
+    import cn_chess_ai_b200 as xq
+    from cn_chess_ai_b200.dist import connect_peers
+    rank, world, local = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"]), int(os.environ["LOCAL_RANK"])
+    torch.cuda.set_device(local)
+    dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    dev = torch.device("cuda", local)
+    net = xq.DQN(device=local, lr=1e-4, seed=2)
+    env = xq.BatchedEnv(1024, device=local, seed=5, env_id0=rank * 1024)
+    rb = xq.ReplayBuffer(1 << 14, device=local)
+    xq.collect(net, env, rb, 8, 0.3)
+    connect_peers(net, dev)
+    xq.td_update_replay(net, rb, 512, 1 + rank, 0, True, 1e-4, apply=True)      # a healthy exchange first
+    net.sync()
+    assert not net.dist_timed_out()
+    w_ok, b_ok = net.get_params()
+    dist.barrier()
+    if rank == 0:       # rank 1 never makes this call: every wait of rank 0's contraction for a peer's row block runs into the time-out
+        xq.td_update_replay(net, rb, 512, 1 + rank, 1, True, 1e-4, apply=True)
+        net.sync()
+        assert net.dist_timed_out(), "the missing peer went unnoticed"
+        w1, b1 = net.get_params()
+        assert w1.tobytes() == w_ok.tobytes() and b1.tobytes() == b_ok.tobytes(), "a partial sum was applied"
+        for call in (lambda: xq.td_update_replay(net, rb, 512, 1, 2, True, 1e-4, apply=True), lambda: xq.td_update_replay_n(net, rb, 512, 1, 2, 3, True, 1e-4),
+                     lambda: net.dist_allgather(np.zeros(4, np.uint8))):
+            try:
+                call()
+                raise SystemExit("a call on the failed handle succeeded")
+            except xq.XQError as ex:
+                assert "timed out" in str(ex), str(ex)
+        print("DIST_TIMEOUT_OK")
+    else:
+        time.sleep(2.0)
+    dist.barrier()
+    dist.destroy_process_group()
+""")
+
+
+def test_exchange_timeout_is_sticky_and_applies_nothing(tmp_path):
+    """a peer that never arrives: the wait inside the contraction kernel ends after XQ_DIST_TIMEOUT_MS, the update is NOT applied (no partial
+    sum), and every later update / exchange call on the handle fails with XQ_ERR_STATE (round 1 carried on with stale data after ~2 s)"""
+    import torch
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs")
+    script = tmp_path / "worker_timeout.py"
+    script.write_text(TIMEOUT_WORKER % ROOT)
+    r = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2", "--master-addr", "127.0.0.1",
+                        "--master-port", "29537", str(script)], capture_output=True, text=True, timeout=600, env=dict(os.environ, XQ_DIST_TIMEOUT_MS="300"))
+    assert r.returncode == 0 and "DIST_TIMEOUT_OK" in r.stdout, r.stdout[-2000:] + r.stderr[-4000:]

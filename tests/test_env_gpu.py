@@ -306,3 +306,20 @@ def test_rollout_random_io_one_call(xq, O, oracle_lib):
     st2, _ = env.rollout_random_io(None, 5, None)          # continue on the device, nothing copied back
     oracle_lib.xqo_rollout_random(ref.ctypes.data, n, 77, seed, 5, None, st0.ctypes.data)
     assert same_recs(env.get_boards(), ref) and int(st2["steps"]) == 5 * n
+    # PINNED host buffers are read / written by the rollout kernel itself (mapped memory, no copy launches): same results, for the team kernel
+    # (1,500 envs) and the board-per-thread kernel (13,000 envs), including boards with non-standard piece sets (generic kernel) and finished ones
+    import torch
+    for n2 in (1500, 13000):
+        base = np.concatenate([harvest_positions(O, 200, 3, 41, seed=6), random_boards(O, 333, seed=9)])
+        start2 = np.concatenate([base] * (n2 // len(base) + 1))[:n2].copy()
+        start2["ctr"] = np.arange(n2) % 500
+        pin_in = torch.from_numpy(start2.view(np.uint8).copy()).pin_memory()
+        pin_out = torch.zeros(n2 * 64, dtype=torch.uint8).pin_memory()
+        e2 = xq.BatchedEnv(n2, seed=23, env_id0=5)
+        st3, tr3 = e2.rollout_random_io(pin_in.numpy().view(xq.ENV_DTYPE), 40, pin_out.numpy().view(xq.ENV_DTYPE), trace=True)
+        ref2 = start2.copy()
+        tr4 = np.zeros((40, n2), O.TRACE_DTYPE); st4 = np.zeros(1, O.STATS_DTYPE)
+        oracle_lib.xqo_rollout_random(ref2.ctypes.data, n2, 5, 23, 40, tr4.ctypes.data, st4.ctypes.data)
+        assert tr3.tobytes() == tr4.tobytes() and st3.tobytes() == st4[0].tobytes(), n2
+        assert same_recs(pin_out.numpy().view(xq.ENV_DTYPE), ref2) and same_recs(e2.get_boards(), ref2), n2
+        assert pin_in.numpy().tobytes() == start2.tobytes()                     # the input buffer is only read
