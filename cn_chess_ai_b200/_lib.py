@@ -64,6 +64,8 @@ def lib():
     L.xq_env_step.argtypes = [_P, _P, _P, _P, _P, _P, _P, C.c_int]
     L.xq_env_rollout_random.argtypes = [_P, C.c_int, _P, _P]
     L.xq_env_rollout_random_io.argtypes = [_P, _P, C.c_int, _P, _P, _P]
+    L.xq_env_rollout_random_io_submit.argtypes = [_P, _P, C.c_int, _P, _P, _P]
+    L.xq_env_rollout_random_io_wait.argtypes = [_P]
     L.xq_env_rollout_random_async.argtypes = [_P, C.c_int]
     L.xq_env_rollout_random_traced_async.argtypes = [_P, C.c_int, C.POINTER(_P)]
     L.xq_env_legal_moves_device.argtypes = [_P, C.POINTER(_P), C.POINTER(_P)]

@@ -1518,14 +1518,21 @@ static int make_tmap_cb(CUtensorMap* m, const void* base, int64_t n, int64_t ld)
 }
 
 // launch with programmatic stream serialization (PDL), optionally as thread-block clusters along y
+// g_launched_event (set by the caller for ONE launch, then cleared here): an event recorded once every CTA of the grid has begun execution
+// (cudaLaunchAttributeLaunchCompletionEvent) -- "this kernel holds its SMs now"
+static thread_local cudaEvent_t g_launched_event = nullptr;
 template <typename... KArgs, typename... Args>
 static cudaError_t launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t stream, int cluster_y, Args&&... args) {
     cudaLaunchConfig_t cfg = {};
     cfg.gridDim = grid; cfg.blockDim = block; cfg.dynamicSmemBytes = smem; cfg.stream = stream;
-    cudaLaunchAttribute at[2];
+    cudaLaunchAttribute at[3];
     int na = 0;
     at[na].id = cudaLaunchAttributeProgrammaticStreamSerialization; at[na].val.programmaticStreamSerializationAllowed = 1; ++na;
     if (cluster_y > 1) { at[na].id = cudaLaunchAttributeClusterDimension; at[na].val.clusterDim.x = 1; at[na].val.clusterDim.y = cluster_y; at[na].val.clusterDim.z = 1; ++na; }
+    if (g_launched_event) {
+        at[na].id = cudaLaunchAttributeLaunchCompletionEvent; at[na].val.launchCompletionEvent.event = g_launched_event; at[na].val.launchCompletionEvent.flags = 0; ++na;
+        g_launched_event = nullptr;
+    }
     cfg.attrs = at; cfg.numAttrs = na;
     ++g_launches;
     return cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);
@@ -1933,6 +1940,10 @@ int dqn_td_update_pipelined(xq_dqn_s* h, const void* ring, int64_t size, uint64_
     //      when the contraction's 88 whole-SM CTAs want their SMs; part B (the other row tiles, 37 x 2 CTAs) is released when the TD-error kernel has
     //      COMPLETED -- the contraction's CTAs are resident by then (programmatic dependent launch) -- and runs on the 60 SMs they leave free.  Nothing
     //      of the GEMM is left when the h(s) gather of update i+1 (which cannot share an SM with a GEMM CTA: registers) starts: no race for SMs.
+    //   5  when every CTA of the gradient contraction of update i has BEGUN execution (cudaLaunchAttributeLaunchCompletionEvent on that launch):
+    //      with programmatic dependent launch the contraction's 88 CTAs become resident while the TD-error kernel still runs, so the GEMM is
+    //      released a few microseconds after mode 2 would release it -- but never before the contraction holds its SMs: the order the "fast"
+    //      calls of mode 2 happen to get, made the only order.
     static const int a_tiles = [] { const char* e = getenv("XQ_TD_GEMM_A_TILES"); return e ? atoi(e) : 20; }();
     auto aux_gemm = [&](int i, cudaEvent_t gate) -> int {
         const int slot = i & 1;
@@ -1973,9 +1984,11 @@ int dqn_td_update_pipelined(xq_dqn_s* h, const void* ring, int64_t size, uint64_
                            ld, kParts, (float)h->gamma, h->mode, f->d0hi, f->d0lo, f->ghi, f->glo, ld, f->info_slots));
         if (early == 1) { XQ_CUDA(cudaEventRecord(f->ev_td[slot], main)); if (i + 1 < n_updates) if (int rc = aux_gemm(i + 1, gate_of(i + 1))) return rc; }
         if (early == 4) { XQ_CUDA(cudaEventRecord(f->ev_tdb[slot], main)); if (i + 1 < n_updates) if (int rc = aux_gemm_part(i + 1, f->ev_tdb[slot], true)) return rc; }
+        if (early == 5 && i + 1 < n_updates) g_launched_event = f->ev_tdb[slot];
         XQ_CUDA(launch_pdl(dw_gemm_kernel, dim3(kDwMTiles, kDwSplits), dim3(kDwThreads), kDwSmem, main, kDwSplits, f->tmD0hi, f->tmD0lo, f->tmGhi,
                            f->tmGlo, f->tmCb, (int)n, f->part, f->dbpart, f->info_slots, f->info, cur_grad(f), f->W0T, f->b0, f->W1, f->b1, f->W1bf,
                            f->W1lo, (float)lr, f->connected ? 0 : 1, dw_push(f, !f->connected, fuse_exchange)));
+        if (early == 5 && i + 1 < n_updates) if (int rc = aux_gemm(i + 1, f->ev_tdb[slot])) return rc;
         if (f->connected) {      // multi-GPU
             if (fuse_exchange) { ++f->epoch; f->parity ^= 1; }                  // the contraction exchanged the gradient and applied the SGD step itself
             else if (int rc = dqn_exchange_apply(h, lr)) return rc;              // two kernels: push + [wait, sum, SGD]

@@ -301,6 +301,7 @@ struct xq_env_s {
     xq_game_event* h_events = nullptr; unsigned long long* h_event_count = nullptr; int64_t last_events = 0;      // pinned staging of the drain; size of the last drain
     // per-env scratch of the self-play collector (xq_selfplay.cu: Q(s) rows, chosen actions, auxiliary streams and events), released with the handle
     void* sp_scratch = nullptr; void (*sp_scratch_free)(void*) = nullptr;
+    cudaEvent_t ev_io = nullptr; bool io_pending = false;      // xq_env_rollout_random_io_submit / _wait
 };
 
 static inline unsigned grid_for(int64_t n, int per_block) { return (unsigned)((n + per_block - 1) / per_block); }
@@ -410,6 +411,7 @@ int xq_env_destroy(xq_env_t h) {
     if (!h) return XQ_OK;
     cudaSetDevice(h->device);
     if (h->sp_scratch && h->sp_scratch_free) { cudaStreamSynchronize(h->stream); h->sp_scratch_free(h->sp_scratch); }
+    if (h->ev_io) cudaEventDestroy(h->ev_io);
     cudaFree(h->d_envs); cudaFree(h->d_stats); cudaFree(h->d_actions); cudaFree(h->d_i32); cudaFree(h->d_lists);
     cudaFree(h->d_trace); cudaFree(h->d_state); cudaFree(h->d_nonstd); cudaFree(h->d_events); cudaFree(h->d_event_count); cudaFreeHost(h->h_events); cudaFreeHost(h->h_event_count);
     for (auto p : h->d_u8) cudaFree(p);
@@ -654,10 +656,12 @@ int xq_env_drain_game_events(xq_env_t h, xq_game_event* out_host, int64_t max_ev
     return XQ_OK;
 }
 
-int xq_env_rollout_random_io(xq_env_t h, const xq_env_rec* boards_in_host, int n_plies, xq_env_rec* boards_out_host,
-                             xq_trace_rec* trace_host, xq_env_stats* stats_host) {
+int xq_env_rollout_random_io_submit(xq_env_t h, const xq_env_rec* boards_in_host, int n_plies, xq_env_rec* boards_out_host,
+                                    xq_trace_rec* trace_host, xq_env_stats* stats_host) {
     XQ_ENV_ENTER(h);
     if (n_plies < 0) return fail(XQ_ERR_INVALID, "xq_env_rollout_random: n_plies < 0");
+    if (h->io_pending) return fail(XQ_ERR_STATE, "xq_env_rollout_random_io_submit: the previous submission of this handle has not been waited for");
+    if (!h->ev_io) XQ_CUDA(cudaEventCreateWithFlags(&h->ev_io, cudaEventDisableTiming));
     const int64_t need = (int64_t)n_plies * h->n;
     if (trace_host) if (int rc = reserve_trace(h, need)) return rc;
     // pinned (mapped) host buffers are read / written by the rollout kernel itself: two copy launches less on the stream (XQ_IO_ZEROCOPY=0: always copy)
@@ -673,8 +677,21 @@ int xq_env_rollout_random_io(xq_env_t h, const xq_env_rec* boards_in_host, int n
     if (boards_out_host && !mirror) XQ_CUDA(cudaMemcpyAsync(boards_out_host, h->d_envs, sizeof(xq_env_rec) * h->n, cudaMemcpyDeviceToHost, h->stream));
     if (trace_host) XQ_CUDA(cudaMemcpyAsync(trace_host, h->d_trace, sizeof(xq_trace_rec) * need, cudaMemcpyDeviceToHost, h->stream));
     if (stats_host) XQ_CUDA(cudaMemcpyAsync(stats_host, h->d_stats, sizeof(xq_env_stats), cudaMemcpyDeviceToHost, h->stream));
-    XQ_CUDA(cudaStreamSynchronize(h->stream));
+    XQ_CUDA(cudaEventRecord(h->ev_io, h->stream));
+    h->io_pending = true;
     return XQ_OK;
+}
+int xq_env_rollout_random_io_wait(xq_env_t h) {
+    XQ_ENV_ENTER(h);
+    if (!h->io_pending) return fail(XQ_ERR_STATE, "xq_env_rollout_random_io_wait: nothing was submitted on this handle");
+    h->io_pending = false;
+    XQ_CUDA(cudaEventSynchronize(h->ev_io));
+    return XQ_OK;
+}
+int xq_env_rollout_random_io(xq_env_t h, const xq_env_rec* boards_in_host, int n_plies, xq_env_rec* boards_out_host,
+                             xq_trace_rec* trace_host, xq_env_stats* stats_host) {
+    if (int rc = xq_env_rollout_random_io_submit(h, boards_in_host, n_plies, boards_out_host, trace_host, stats_host)) return rc;
+    return xq_env_rollout_random_io_wait(h);
 }
 int xq_env_rollout_random(xq_env_t h, int n_plies, xq_trace_rec* trace_host, xq_env_stats* stats_host) {
     return xq_env_rollout_random_io(h, nullptr, n_plies, nullptr, trace_host, stats_host);

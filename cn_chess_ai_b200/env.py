@@ -106,6 +106,14 @@ class BatchedEnv:
         check(self._L.xq_env_rollout_random_io(self._h, ptr(boards_in), n_plies, ptr(boards_out), ptr(tr), ptr(stats)))
         return stats[0], tr
 
+    def rollout_random_io_submit(self, boards_in, n_plies, boards_out, stats_out=None, trace_out=None):
+        """first half of rollout_random_io: enqueue and return; the buffers (pinned for the overlap to be real) belong to the library until
+        rollout_random_io_wait()"""
+        check(self._L.xq_env_rollout_random_io_submit(self._h, ptr(boards_in), n_plies, ptr(boards_out), ptr(trace_out), ptr(stats_out)))
+
+    def rollout_random_io_wait(self):
+        check(self._L.xq_env_rollout_random_io_wait(self._h))
+
     def api_ply_device(self, auto_reset=True):
         """one ply of the API-mode path entirely on the device: ordered lists -> random-policy pick -> movePiece / reward / terminal"""
         check(self._L.xq_env_legal_moves_device(self._h, None, None))

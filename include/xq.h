@@ -142,6 +142,14 @@ int xq_env_rollout_random(xq_env_t h, int n_plies, xq_trace_rec* trace_host, xq_
  * boards_in_host may be NULL (continue from the boards on the device), as may boards_out_host, trace_host and stats_host. */
 int xq_env_rollout_random_io(xq_env_t h, const xq_env_rec* boards_in_host, int n_plies, xq_env_rec* boards_out_host,
                              xq_trace_rec* trace_host, xq_env_stats* stats_host);
+/* The same call in two halves, for a double-buffered caller (two env handles on one stream: the host submits the step of handle B before
+ * it waits for the step of handle A, so launch latency and the host's wake-up hide under the other handle's kernel; the kernels of one
+ * stream never overlap).  _submit enqueues [boards in -> rollout -> boards / trace / stats out] and returns; _wait blocks until that
+ * step's outputs are in host memory.  The host buffers belong to the library between the two calls; one submission per handle at a
+ * time (XQ_ERR_STATE otherwise).  xq_env_rollout_random_io == _submit + _wait. */
+int xq_env_rollout_random_io_submit(xq_env_t h, const xq_env_rec* boards_in_host, int n_plies, xq_env_rec* boards_out_host,
+                                    xq_trace_rec* trace_host, xq_env_stats* stats_host);
+int xq_env_rollout_random_io_wait(xq_env_t h);
 /* same, device-resident and asynchronous: no host traffic; stats accumulate on the device */
 int xq_env_rollout_random_async(xq_env_t h, int n_plies);
 /* same with the per-ply trace [n_plies][n_envs] written to a device buffer owned by the handle (*trace_dev, valid until the next traced

@@ -323,3 +323,42 @@ def test_rollout_random_io_one_call(xq, O, oracle_lib):
         assert tr3.tobytes() == tr4.tobytes() and st3.tobytes() == st4[0].tobytes(), n2
         assert same_recs(pin_out.numpy().view(xq.ENV_DTYPE), ref2) and same_recs(e2.get_boards(), ref2), n2
         assert pin_in.numpy().tobytes() == start2.tobytes()                     # the input buffer is only read
+
+
+def test_rollout_random_io_submit_wait_double_buffered(xq, O, oracle_lib):
+    """xq_env_rollout_random_io_submit / _wait: two env handles alternate on ONE stream, step i + 1 submitted before step i is waited for;
+    every step's boards and statistics equal the oracle's, a second submission without a wait is refused (XQ_ERR_STATE)"""
+    import torch
+    n, plies, rounds = 2048, 25, 4
+    s = torch.cuda.Stream()
+    envs, pins, refs = [], [], []
+    for k in range(2):
+        e = xq.BatchedEnv(n, seed=31 + k, env_id0=1000 * k)
+        e.set_stream(s.cuda_stream)
+        start = harvest_positions(O, n // 4, 3, 41, seed=11 + k)
+        start = np.concatenate([start] * (n // len(start) + 1))[:n].copy()
+        start["ctr"] = (np.arange(n) * 7 + k) % 900
+        pin_in = torch.from_numpy(start.view(np.uint8).copy()).pin_memory()
+        pin_out = torch.zeros(n * 64, dtype=torch.uint8).pin_memory()
+        pin_st = torch.zeros(64, dtype=torch.uint8).pin_memory()
+        envs.append(e); refs.append(start.copy())
+        pins.append((pin_in.numpy().view(xq.ENV_DTYPE), pin_out.numpy().view(xq.ENV_DTYPE), pin_st.numpy().view(xq.STATS_DTYPE), (pin_in, pin_out, pin_st)))
+
+    def check_step(k):
+        st0 = np.zeros(1, O.STATS_DTYPE)
+        oracle_lib.xqo_rollout_random(refs[k].ctypes.data, n, 1000 * k, 31 + k, plies, None, st0.ctypes.data)
+        assert same_recs(pins[k][1], refs[k]), k
+        assert pins[k][2][0].tobytes() == st0[0].tobytes(), k
+        pins[k][0][:] = pins[k][1]                       # the next step of this handle continues from its own output, through the host
+
+    envs[0].rollout_random_io_submit(pins[0][0], plies, pins[0][1], stats_out=pins[0][2])
+    with pytest.raises(xq.XQError):
+        envs[0].rollout_random_io_submit(pins[0][0], plies, pins[0][1], stats_out=pins[0][2])
+    for r in range(rounds):
+        envs[1].rollout_random_io_submit(pins[1][0], plies, pins[1][1], stats_out=pins[1][2])
+        envs[0].rollout_random_io_wait(); check_step(0)
+        if r + 1 < rounds:
+            envs[0].rollout_random_io_submit(pins[0][0], plies, pins[0][1], stats_out=pins[0][2])
+        envs[1].rollout_random_io_wait(); check_step(1)
+    with pytest.raises(xq.XQError):
+        envs[1].rollout_random_io_wait()
