@@ -292,6 +292,95 @@ __global__ void __launch_bounds__(kAB * 4) act_team_kernel(xq_env_rec* __restric
     }
 }
 
+// ---------------------------------------------------------------------------------------------------------------------------------
+// API mode: ChessAI::getAllValidActions(currentPlayer) for every env as ORDERED LISTS in HBM with the team of 4 threads per board
+// (src/chessai.cpp:347-368).  The board-per-thread list kernel (legal_moves_lane_kernel) walks ~7,300 instructions per thread: with few
+// envs (one warp per scheduler) a launch lasts as long as that one chain.  Here the chain is ~1/4: warps 0 / 1 unpack the Red / Black half
+// of 32 records, every thread generates the moves of its 4 pieces (team_phase_a), finds their place in the reference order with the
+// byte-SIMD prefix and writes their actions into the board's row of shared memory (team_emit_actions); the CTA then streams the rows
+// out as 16-byte stores, 256 contiguous bytes per board, entries past the count filled on the way out.
+constexpr int kLtRow = 65;                                   // words per board row: 64 pairs of actions + 1 (odd stride)
+__global__ void __launch_bounds__(kAB * 4) legal_moves_team_kernel(const xq_env_rec* __restrict__ envs, int64_t n, uint8_t* __restrict__ counts,
+                                                                  uint4* __restrict__ actions, uint8_t* __restrict__ nonstd) {
+    __shared__ TeamShared<kAB> sh;
+    __shared__ uint8_t s_slot[32 * kAB];
+    __shared__ uint32_t s_bb[6 * kAB], s_occT[6 * kAB], s_player[kAB];
+    __shared__ uint8_t s_ok[2 * kAB], s_cnt[kAB];
+    __shared__ uint32_t s_list[kAB * kLtRow];
+    const int tid = threadIdx.x, lane = tid & 31;
+    const TeamRole R = team_role<4>(tid >> 5);
+    const int64_t env0 = (int64_t)blockIdx.x * kAB, env = env0 + lane;
+    if (R.role < 2) {
+        const int side = R.role;
+        bool ok = env < n;
+        if (ok) {
+            const uint4* rec = reinterpret_cast<const uint4*>(envs + env);
+            uint32_t w[12];
+#pragma unroll
+            for (int i = 0; i < 3; ++i) { const uint4 v = rec[i]; w[4 * i] = v.x; w[4 * i + 1] = v.y; w[4 * i + 2] = v.z; w[4 * i + 3] = v.w; }
+            for (int i = 0; i < 16; ++i) s_slot[(side * 16 + i) * kAB + lane] = kDeadSq;
+            Bits90 bb, occT;
+            ok = team_unpack_side(w, side, bb, occT, [&](int s, int q) { s_slot[(side * 16 + s) * kAB + lane] = (uint8_t)q; });
+            s_bb[(3 * side + 0) * kAB + lane] = bb.w0; s_bb[(3 * side + 1) * kAB + lane] = bb.w1; s_bb[(3 * side + 2) * kAB + lane] = bb.w2;
+            s_occT[(3 * side + 0) * kAB + lane] = occT.w0; s_occT[(3 * side + 1) * kAB + lane] = occT.w1; s_occT[(3 * side + 2) * kAB + lane] = occT.w2;
+            if (side == 0) s_player[lane] = (rec[3].x >> 16) & 0xFFu;
+        }
+        s_ok[side * kAB + lane] = ok ? 1 : 0;
+    }
+    __syncthreads();
+    // lanes without a board (tail of the last CTA, non-standard piece sets: left to the generic kernel) work on the opening position, unused
+    const bool active = (s_ok[lane] & s_ok[kAB + lane]) != 0;
+    if (R.role == 0 && env < n && nonstd) nonstd[env] = active ? 0 : 1;
+    TeamState st;
+    team_reset(R, st);
+    st.ctr = 0;
+    if (active) {
+        uint32_t wr = 0, wb = 0;
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            const int s = (int)((R.slots >> (8 * i)) & 0xFFu);
+            wr |= (uint32_t)s_slot[s * kAB + lane] << (8 * i);
+            wb |= (uint32_t)s_slot[(16 + s) * kAB + lane] << (8 * i);
+        }
+        const Bits90 red{s_bb[0 * kAB + lane], s_bb[1 * kAB + lane], s_bb[2 * kAB + lane]};
+        const Bits90 black{s_bb[3 * kAB + lane], s_bb[4 * kAB + lane], s_bb[5 * kAB + lane]};
+        st.occT = Bits90{s_occT[0 * kAB + lane] | s_occT[3 * kAB + lane], s_occT[1 * kAB + lane] | s_occT[4 * kAB + lane],
+                         s_occT[2 * kAB + lane] | s_occT[5 * kAB + lane]};
+        st.player = (int)s_player[lane];
+        const bool redp = st.player == RED;
+        st.sq_own = redp ? wr : wb; st.sq_opp = redp ? wb : wr;
+        st.own = redp ? red : black; st.opp = redp ? black : red;
+    }
+    TeamPly pl;
+    team_phase_a<4, kAB>(R, st, pl, sh, lane, 0);
+    __syncthreads();
+    uint16_t* row = reinterpret_cast<uint16_t*>(s_list + lane * kLtRow);
+    const uint32_t tot = team_emit_actions<kAB>(R, st, pl, sh, lane, [&](int idx, int a) { row[idx] = (uint16_t)a; });
+    if (R.role == 0) {
+        s_cnt[lane] = active ? (uint8_t)tot : (uint8_t)0xFF;
+        if (active) counts[env] = (uint8_t)tot;
+    }
+    __syncthreads();
+    const int live = (int)min((int64_t)kAB, n - env0);
+    for (int c = tid; c < live * 16; c += kAB * 4) {         // 16-byte chunk c & 15 of board c >> 4: actions 8 (c & 15) .. + 7
+        const int b = c >> 4, j = (c & 15) * 4, cb = s_cnt[b];
+        if (cb == 0xFF) continue;
+        uint32_t v[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {                        // entries past the count are XQ_ACTION_NONE (the rows are not pre-filled)
+            const int a0 = 2 * (j + u);
+            const uint32_t x = s_list[b * kLtRow + j + u];
+            v[u] = a0 + 1 < cb ? x : (a0 < cb ? (x | 0xFFFF0000u) : 0xFFFFFFFFu);
+        }
+        actions[(env0 + b) * 16 + (c & 15)] = make_uint4(v[0], v[1], v[2], v[3]);
+    }
+}
+cudaError_t launch_legal_moves_team(const xq_env_rec* envs, int64_t n, uint8_t* counts, uint32_t* actions, uint8_t* nonstd, cudaStream_t stream) {
+    legal_moves_team_kernel<<<(unsigned)((n + kAB - 1) / kAB), kAB * 4, 0, stream>>>(envs, n, counts, reinterpret_cast<uint4*>(actions), nonstd);
+    ++g_launches;
+    return cudaGetLastError();
+}
+
 cudaError_t launch_act_team(bool apply, xq_env_rec* envs, int64_t n, uint64_t env_id0, uint64_t seed, const float* q90, uint32_t eps_thr, int train_done,
                             uint16_t* actions_out, void* ring, int64_t ring_cap, int64_t ring_pos, xq_env_stats* stats, xq_game_event* events,
                             unsigned long long* event_count, int64_t event_cap, uint32_t event_ply, uint8_t* nonstd, const ActCarry* carry, uint32_t event_env0, cudaStream_t stream) {

@@ -86,6 +86,46 @@ XQ_HD void act_best(const TeamRole& R, const TeamState& st, const TeamPly& pl, A
     }
 }
 
+// API mode (legal_moves_team_kernel): ChessAI::getAllValidActions(side to move) as the ORDERED LIST (src/chessai.cpp:347-368), after team_phase_a.
+// Every thread finds the place of each of its 4 pieces in the reference order (byte-SIMD prefix over the published (squares, counts) words, as
+// in team_phase_b) and emits the piece's actions in generator order: emit(index in the list, action).  Returns the list size.
+template <int KB, class EMIT>
+XQ_HD uint32_t team_emit_actions(const TeamRole& R, const TeamState& st, const TeamPly& pl, const TeamShared<KB>& sh, int lane, EMIT&& emit) {
+    uint32_t qw[4], cw[4], tot = 0;
+#pragma unroll
+    for (int w = 0; w < 4; ++w) { qw[w] = sh.q[w * KB + lane]; cw[w] = sh.c[w * KB + lane]; tot = dp4a_u(cw[w], 0x01010101u, tot); }
+    const uint32_t flip = st.player ? 0xFFFFFFFFu : 0u;
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        const int sq = (int)((st.sq_own >> (8 * i)) & 0xFFu);
+        const uint32_t cnt = (pl.cntw >> (8 * i)) & 0xFFu;             // 0 for a captured piece (its descriptor is garbage)
+        const uint32_t base = (uint32_t)sq * 0x01010101u + 0x7F7F7F7Fu;
+        uint32_t acc = 0;
+#pragma unroll
+        for (int w = 0; w < 4; ++w) acc = dp4a_u(cw[w], (base - qw[w]) & 0x80808080u, acc);
+        int idx = (int)(acc >> 7);
+        if (i == 0) {      // the slider: per ray the empty squares, then the capture (slider_desc, xq_bitboard.cuh)
+            const uint32_t desc = cnt ? pl.desc[0] : 0u;
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+                const int e = (int)((desc >> (8 * k)) & 15u), capdist = (int)((desc >> (8 * k + 4)) & 15u);
+                const int step = k == 0 ? 1 : (k == 1 ? -1 : (k == 2 ? 9 : -9));
+                const int c = e + (capdist ? 1 : 0);
+                for (int j = 0; j < c; ++j) emit(idx++, (int)XQ_ACTION(sq, sq + step * (j < e ? j + 1 : capdist)));
+            }
+        } else {           // a leaper: the playable directions in the order of generate*Moves
+            uint32_t mask = cnt ? (pl.desc[i] & 0xFFu) : 0u;
+            const uint64_t tab = ((uint64_t)(i == 1 ? R.tab_hi : 0u) << 32) | (R.tab_lo[i] ^ (R.sold[i] & flip));
+            while (mask) {
+                const int k = ffs32(mask) - 1;
+                mask &= mask - 1;
+                emit(idx++, (int)XQ_ACTION(sq, sq + (int)(int8_t)(uint8_t)(tab >> (8 * k))));
+            }
+        }
+    }
+    return tot;
+}
+
 // phase B: the chosen action; the owning thread decodes it and publishes from | to << 8 in sh.move.  Returns the list size
 // (0: no legal action, nothing published).  x = xq_rng(seed, env id, ctr) of this ply.
 template <int KB>

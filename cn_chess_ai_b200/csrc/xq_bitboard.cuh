@@ -282,6 +282,57 @@ XQ_HD int piece_moves_dyn(int type, const Pos& P, int sq, int color, int want, i
     return n;
 }
 
+// Board summary straight from the 12 nibble words of a record, without a per-square loop (step_kernel): material per colour
+// (ChessAI::evaluateBoard, src/chessai.cpp:311-342) and the lowest square holding each General (ChessBoard::checkGameOver :286-309,
+// getWinner :312-320), 127 = none.  Bit-plane SIMD: plane j of the words 4g .. 4g+3 is packed into ONE word (bit 4i + k = bit j of
+// nibble i of word 4g + k), a piece code is then a 4-input boolean function of the planes and its count a popcount.
+struct WordSummary { int mat_red, mat_black, gen_red, gen_black; };
+XQ_HD WordSummary summarize_words(const uint32_t (&w)[12]) {
+    uint32_t P[3][4];
+#pragma unroll
+    for (int g = 0; g < 3; ++g)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            uint32_t acc = 0;
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+                const uint32_t x = w[4 * g + k];
+                acc |= (k >= j ? x << (k - j) : x >> (j - k)) & (0x11111111u << k);
+            }
+            P[g][j] = acc;
+        }
+    int n[15];      // pieces per code 1..14
+#pragma unroll
+    for (int code = 1; code <= 14; ++code) {
+        int c = 0;
+#pragma unroll
+        for (int g = 0; g < 3; ++g) {
+            uint32_t m = 0xFFFFFFFFu;
+#pragma unroll
+            for (int j = 0; j < 4; ++j) m &= ((code >> j) & 1) ? P[g][j] : ~P[g][j];
+            c += popc32(m);
+        }
+        n[code] = c;
+    }
+    WordSummary s;      // piece_score / 5: 200, 4, 4, 8, 18, 9, 2
+    s.mat_red = 5 * (200 * n[1] + 4 * (n[2] + n[3]) + 8 * n[4] + 18 * n[5] + 9 * n[6] + 2 * n[7]);
+    s.mat_black = 5 * (200 * n[8] + 4 * (n[9] + n[10]) + 8 * n[11] + 18 * n[12] + 9 * n[13] + 2 * n[14]);
+    int gen[2] = {127, 127};
+#pragma unroll
+    for (int side = 0; side < 2; ++side) {
+        const uint32_t pat = side ? 0x88888888u : 0x11111111u;      // nibble == 1 (Red General) / == 8 (Black General)
+#pragma unroll
+        for (int i = 11; i >= 0; --i) {                              // descending: the lowest word with a match is written last
+            const uint32_t x = w[i] ^ pat;
+            const uint32_t nz = (x | (x >> 1) | (x >> 2) | (x >> 3)) & 0x11111111u;      // 1 per NON-matching nibble
+            const uint32_t hit = nz ^ 0x11111111u;
+            gen[side] = hit ? 8 * i + ((ffs32(hit) - 1) >> 2) : gen[side];
+        }
+    }
+    s.gen_red = gen[0]; s.gen_black = gen[1];
+    return s;
+}
+
 // Piece slots: every side has 16 fixed slots (no promotion in Xiangqi); slot -> type is static,
 // which is what makes warps type-uniform.  0,1 Chariot | 2,3 Horse | 4,5 Elephant | 6,7 Advisor |
 // 8 General | 9,10 Cannon | 11..15 Soldier.

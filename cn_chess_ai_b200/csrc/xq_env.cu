@@ -23,6 +23,7 @@
 #include <algorithm>
 
 #include "xq_env_dev.cuh"
+#include "xq_bitboard.cuh"
 
 namespace xq {
 
@@ -145,12 +146,17 @@ __global__ void __launch_bounds__(kThreads) step_kernel(xq_env_rec* __restrict__
     const bool ok = from < 90 && to < 90 && is_valid_move(b, from / 9, from % 9, to / 9, to % 9);
     int cap = 0;
     if (ok) { cap = apply_move(b, m, from, to); m.ctr++; }
-    const Summary s = summarize(b);
+    // material / Generals from the 12 packed words in registers (bit-plane SIMD, xq_bitboard.cuh) instead of a scan over the 90 squares
+    uint32_t wd[12];
+#pragma unroll
+    for (int i = 0; i < 12; ++i) wd[i] = b.base[i * b.stride];
+    const WordSummary s = summarize_words(wd);
     const int diff = mover == RED ? s.mat_red - s.mat_black : s.mat_black - s.mat_red;
-    const bool over = m.move_count >= XQ_MAX_MOVES || !(s.red_alive && s.black_alive);
+    const bool over = m.move_count >= XQ_MAX_MOVES || s.gen_red == 127 || s.gen_black == 127;
+    const int win = (s.gen_red == 127 && s.gen_black == 127) ? NOCOLOR : (s.gen_red < s.gen_black ? RED : BLACK);      // first General in square order
     if (reward) reward[env] = reward_from_material(diff, m.move_count);
     if (done) done[env] = over ? 1 : 0;
-    if (winner) winner[env] = (uint8_t)s.winner;
+    if (winner) winner[env] = (uint8_t)win;
     if (captured) captured[env] = (uint8_t)cap;
     if (valid) valid[env] = ok ? 1 : 0;
     if (over && auto_reset) { reset_board(b); m.reset(); }
@@ -302,6 +308,9 @@ struct xq_env_s {
     // per-env scratch of the self-play collector (xq_selfplay.cu: Q(s) rows, chosen actions, auxiliary streams and events), released with the handle
     void* sp_scratch = nullptr; void (*sp_scratch_free)(void*) = nullptr;
     cudaEvent_t ev_io = nullptr; bool io_pending = false;      // xq_env_rollout_random_io_submit / _wait
+    cudaStream_t io_in = nullptr, io_out = nullptr;            // its copy streams: boards in / results out move under the OTHER handle's kernel
+    cudaEvent_t ev_in = nullptr, ev_run = nullptr, ev_prev = nullptr;
+    bool async_dirty = false;                                   // asynchronous work on `stream` since the last synchronisation of the handle
 };
 
 static inline unsigned grid_for(int64_t n, int per_block) { return (unsigned)((n + per_block - 1) / per_block); }
@@ -311,6 +320,7 @@ cudaError_t launch_rollout_slots(xq_env_rec* envs, int64_t n, uint64_t env_id0, 
                                  xq_env_stats* stats, uint8_t* nonstd, cudaStream_t stream);
 cudaError_t launch_rollout_team(int team, xq_env_rec* envs, int64_t n, uint64_t env_id0, uint64_t seed, int n_plies, xq_trace_rec* trace,
                                 xq_env_stats* stats, uint8_t* nonstd, cudaStream_t stream, const xq_env_rec* src, xq_env_rec* mirror);
+cudaError_t launch_legal_moves_team(const xq_env_rec* envs, int64_t n, uint8_t* counts, uint32_t* actions, uint8_t* nonstd, cudaStream_t stream);
 cudaError_t launch_rollout_lane(xq_env_rec* envs, int64_t n, uint64_t env_id0, uint64_t seed, int n_plies, xq_trace_rec* trace, xq_env_stats* stats,
                                 uint8_t* nonstd, cudaStream_t stream, const xq_env_rec* src, xq_env_rec* mirror);
 cudaError_t launch_legal_moves_lane(const xq_env_rec* envs, int64_t n, uint8_t* counts, uint32_t* actions, uint8_t* nonstd, cudaStream_t stream);
@@ -322,8 +332,17 @@ cudaError_t launch_pick_random(const xq_env_rec* envs, int64_t n, uint64_t env_i
 // xq_env_set_boards injected exotic positions).  XQ_LEGAL_LANE=0 runs the generic kernel on every env (A/B runs); same results.
 static int launch_legal_moves(xq_env_s* h) {
     static const bool lane = [] { const char* e = getenv("XQ_LEGAL_LANE"); return !(e && atoi(e) == 0); }();
+    h->async_dirty = true;
     if (!h->d_lists) XQ_CUDA(cudaMalloc(&h->d_lists, sizeof(uint32_t) * 64 * h->n));
-    if (lane) XQ_CUDA(launch_legal_moves_lane(h->d_envs, h->n, h->d_u8[0], h->d_lists, h->d_nonstd, h->stream));
+    // few envs: the team kernel (4 threads per board, a quarter of the per-thread chain); many: one thread per board.  XQ_LEGAL_TEAM=0|1 forces.
+    // (read per call: the tests switch kernels inside one process)
+    const char* te = getenv("XQ_LEGAL_TEAM");
+    const char* tm = getenv("XQ_LEGAL_TEAM_MAX");
+    const int team_env = te ? atoi(te) : -1;
+    const int64_t team_max = tm ? (int64_t)atoll(tm) : (int64_t)12288;
+    const bool team = team_env >= 0 ? team_env != 0 : h->n <= team_max;
+    if (lane && team) XQ_CUDA(launch_legal_moves_team(h->d_envs, h->n, h->d_u8[0], h->d_lists, h->d_nonstd, h->stream));
+    else if (lane) XQ_CUDA(launch_legal_moves_lane(h->d_envs, h->n, h->d_u8[0], h->d_lists, h->d_nonstd, h->stream));
     if (!lane || h->maybe_nonstd) {
         legal_moves_kernel<<<grid_for(h->n, kThreads), kThreads, 0, h->stream>>>(h->d_envs, h->n, h->d_u8[0], h->d_lists, lane ? h->d_nonstd : nullptr);
         XQ_LAUNCH_CHECK();
@@ -352,6 +371,7 @@ static int rollout_team(int64_t n) {
 // to the generic one is copied host -> device by the first kernel, so the generic kernel always starts from the device array.
 static int launch_rollout(xq_env_s* h, int n_plies, xq_trace_rec* d_trace, const xq_env_rec* src = nullptr, xq_env_rec* mirror = nullptr) {
     if (n_plies >= (1 << 24)) return fail(XQ_ERR_INVALID, "rollout: n_plies must be < 2^24 per launch");
+    h->async_dirty = true;
     const int team = rollout_team(h->n);
     if (team == 1) XQ_CUDA(launch_rollout_lane(h->d_envs, h->n, h->env_id0, h->seed, n_plies, d_trace, h->d_stats, h->d_nonstd, h->stream, src, mirror));
     else if (team == 16) XQ_CUDA(launch_rollout_slots(h->d_envs, h->n, h->env_id0, h->seed, n_plies, d_trace, h->d_stats, h->d_nonstd, h->stream));
@@ -375,6 +395,7 @@ static void* mapped_alias(const void* host) {
 namespace xq {
 int env_info(xq_env_t h, EnvInfo* out) {
     if (!h || !out) return fail(XQ_ERR_INVALID, "env_info: null handle");
+    h->async_dirty = true;      // the collector / trainer launch on the handle's stream and boards
     out->n = h->n; out->device = h->device; out->seed = h->seed; out->env_id0 = h->env_id0; out->stream = h->stream; out->d_envs = h->d_envs; out->d_stats = h->d_stats;
     out->d_events = h->d_events; out->d_event_count = h->d_event_count; out->event_cap = h->event_cap; out->event_ply = h->event_ply;
     out->d_nonstd = h->d_nonstd; out->maybe_nonstd = h->maybe_nonstd;
@@ -412,6 +433,11 @@ int xq_env_destroy(xq_env_t h) {
     cudaSetDevice(h->device);
     if (h->sp_scratch && h->sp_scratch_free) { cudaStreamSynchronize(h->stream); h->sp_scratch_free(h->sp_scratch); }
     if (h->ev_io) cudaEventDestroy(h->ev_io);
+    if (h->ev_in) cudaEventDestroy(h->ev_in);
+    if (h->ev_run) cudaEventDestroy(h->ev_run);
+    if (h->ev_prev) cudaEventDestroy(h->ev_prev);
+    if (h->io_in) cudaStreamDestroy(h->io_in);
+    if (h->io_out) cudaStreamDestroy(h->io_out);
     cudaFree(h->d_envs); cudaFree(h->d_stats); cudaFree(h->d_actions); cudaFree(h->d_i32); cudaFree(h->d_lists);
     cudaFree(h->d_trace); cudaFree(h->d_state); cudaFree(h->d_nonstd); cudaFree(h->d_events); cudaFree(h->d_event_count); cudaFreeHost(h->h_events); cudaFreeHost(h->h_event_count);
     for (auto p : h->d_u8) cudaFree(p);
@@ -448,9 +474,13 @@ int xq_env_create(int64_t n_envs, int device, uint64_t seed, uint64_t env_id0, x
     return XQ_OK;
 }
 
-#define XQ_ENV_ENTER(h)                                                        \
+#define XQ_ENV_ENTER_IO(h)                                                     \
     if (!(h)) return fail(XQ_ERR_INVALID, "%s: null handle", __func__);        \
     XQ_CUDA(cudaSetDevice((h)->device))
+// between xq_env_rollout_random_io_submit and _wait the handle's boards and buffers are in flight on its copy streams: every other call is refused
+#define XQ_ENV_ENTER(h)                                                        \
+    XQ_ENV_ENTER_IO(h);                                                        \
+    if ((h)->io_pending) return fail(XQ_ERR_STATE, "%s: a submission of this handle has not been waited for (xq_env_rollout_random_io_wait)", __func__)
 
 int xq_env_count(xq_env_t h, int64_t* n) { if (!h || !n) return fail(XQ_ERR_INVALID, "xq_env_count: null"); *n = h->n; return XQ_OK; }
 
@@ -462,7 +492,7 @@ int xq_env_set_stream(xq_env_t h, void* s) {
     return XQ_OK;
 }
 int xq_env_sync(xq_env_t h) { XQ_ENV_ENTER(h); XQ_CUDA(cudaStreamSynchronize(h->stream)); return XQ_OK; }
-int xq_env_device_boards(xq_env_t h, void** p) { if (!h || !p) return fail(XQ_ERR_INVALID, "xq_env_device_boards: null"); *p = h->d_envs; return XQ_OK; }
+int xq_env_device_boards(xq_env_t h, void** p) { if (!h || !p) return fail(XQ_ERR_INVALID, "xq_env_device_boards: null"); h->async_dirty = true; *p = h->d_envs; return XQ_OK; }
 
 int xq_env_reset(xq_env_t h, const uint8_t* mask_host) {
     XQ_ENV_ENTER(h);
@@ -570,6 +600,7 @@ int xq_env_step_device(xq_env_t h, const void* actions_dev, int auto_reset, void
                        void** valid_dev) {
     XQ_ENV_ENTER(h);
     const uint16_t* a = actions_dev ? static_cast<const uint16_t*>(actions_dev) : h->d_actions;
+    h->async_dirty = true;
     step_kernel<<<grid_for(h->n, kThreads), kThreads, 0, h->stream>>>(h->d_envs, h->n, a, h->d_i32, h->d_u8[1], h->d_u8[2], h->d_u8[3], h->d_u8[4], auto_reset);
     XQ_LAUNCH_CHECK();
     if (reward_dev) *reward_dev = h->d_i32;
@@ -656,14 +687,44 @@ int xq_env_drain_game_events(xq_env_t h, xq_game_event* out_host, int64_t max_ev
     return XQ_OK;
 }
 
-int xq_env_rollout_random_io_submit(xq_env_t h, const xq_env_rec* boards_in_host, int n_plies, xq_env_rec* boards_out_host,
-                                    xq_trace_rec* trace_host, xq_env_stats* stats_host) {
-    XQ_ENV_ENTER(h);
+// side_streams: the copies run on the handle's own copy streams, ordered against the rollout by events -- with two handles alternating on one
+// compute stream the boards of the next step arrive and the results of the previous step leave while the other handle's kernel runs.
+// Otherwise (the one-call form) pinned buffers are read / written by the rollout kernel itself through mapped memory: no copy launches at all.
+static int rollout_io_enqueue(xq_env_s* h, const xq_env_rec* boards_in_host, int n_plies, xq_env_rec* boards_out_host, xq_trace_rec* trace_host,
+                              xq_env_stats* stats_host, bool side_streams) {
     if (n_plies < 0) return fail(XQ_ERR_INVALID, "xq_env_rollout_random: n_plies < 0");
     if (h->io_pending) return fail(XQ_ERR_STATE, "xq_env_rollout_random_io_submit: the previous submission of this handle has not been waited for");
     if (!h->ev_io) XQ_CUDA(cudaEventCreateWithFlags(&h->ev_io, cudaEventDisableTiming));
     const int64_t need = (int64_t)n_plies * h->n;
     if (trace_host) if (int rc = reserve_trace(h, need)) return rc;
+    static const bool side_on = [] { const char* e = getenv("XQ_IO_SIDE_STREAMS"); return !(e && atoi(e) == 0); }();
+    if (side_streams && side_on) {
+        if (!h->io_in) {
+            XQ_CUDA(cudaStreamCreateWithFlags(&h->io_in, cudaStreamNonBlocking)); XQ_CUDA(cudaStreamCreateWithFlags(&h->io_out, cudaStreamNonBlocking));
+            XQ_CUDA(cudaEventCreateWithFlags(&h->ev_in, cudaEventDisableTiming)); XQ_CUDA(cudaEventCreateWithFlags(&h->ev_run, cudaEventDisableTiming));
+            XQ_CUDA(cudaEventCreateWithFlags(&h->ev_prev, cudaEventDisableTiming));
+        }
+        if (boards_in_host) {
+            if (h->async_dirty) {      // asynchronous device-resident calls on this handle since its last synchronisation may still use the boards
+                XQ_CUDA(cudaEventRecord(h->ev_prev, h->stream));
+                XQ_CUDA(cudaStreamWaitEvent(h->io_in, h->ev_prev, 0));
+            }
+            XQ_CUDA(cudaMemcpyAsync(h->d_envs, boards_in_host, sizeof(xq_env_rec) * h->n, cudaMemcpyHostToDevice, h->io_in));
+            XQ_CUDA(cudaEventRecord(h->ev_in, h->io_in));
+            XQ_CUDA(cudaStreamWaitEvent(h->stream, h->ev_in, 0));
+            h->maybe_nonstd = true;
+        }
+        XQ_CUDA(cudaMemsetAsync(h->d_stats, 0, sizeof(xq_env_stats), h->stream));
+        if (int rc = launch_rollout(h, n_plies, trace_host ? h->d_trace : nullptr)) return rc;
+        XQ_CUDA(cudaEventRecord(h->ev_run, h->stream));
+        XQ_CUDA(cudaStreamWaitEvent(h->io_out, h->ev_run, 0));
+        if (boards_out_host) XQ_CUDA(cudaMemcpyAsync(boards_out_host, h->d_envs, sizeof(xq_env_rec) * h->n, cudaMemcpyDeviceToHost, h->io_out));
+        if (trace_host) XQ_CUDA(cudaMemcpyAsync(trace_host, h->d_trace, sizeof(xq_trace_rec) * need, cudaMemcpyDeviceToHost, h->io_out));
+        if (stats_host) XQ_CUDA(cudaMemcpyAsync(stats_host, h->d_stats, sizeof(xq_env_stats), cudaMemcpyDeviceToHost, h->io_out));
+        XQ_CUDA(cudaEventRecord(h->ev_io, h->io_out));
+        h->io_pending = true;      // nothing else may be called on the handle until _wait: the copies out are not ordered against the compute stream
+        return XQ_OK;
+    }
     // pinned (mapped) host buffers are read / written by the rollout kernel itself: two copy launches less on the stream (XQ_IO_ZEROCOPY=0: always copy)
     const bool direct = rollout_team(h->n) != 16;
     const xq_env_rec* src = direct ? static_cast<const xq_env_rec*>(mapped_alias(boards_in_host)) : nullptr;
@@ -681,16 +742,23 @@ int xq_env_rollout_random_io_submit(xq_env_t h, const xq_env_rec* boards_in_host
     h->io_pending = true;
     return XQ_OK;
 }
-int xq_env_rollout_random_io_wait(xq_env_t h) {
+int xq_env_rollout_random_io_submit(xq_env_t h, const xq_env_rec* boards_in_host, int n_plies, xq_env_rec* boards_out_host,
+                                    xq_trace_rec* trace_host, xq_env_stats* stats_host) {
     XQ_ENV_ENTER(h);
+    return rollout_io_enqueue(h, boards_in_host, n_plies, boards_out_host, trace_host, stats_host, true);
+}
+int xq_env_rollout_random_io_wait(xq_env_t h) {
+    XQ_ENV_ENTER_IO(h);
     if (!h->io_pending) return fail(XQ_ERR_STATE, "xq_env_rollout_random_io_wait: nothing was submitted on this handle");
     h->io_pending = false;
     XQ_CUDA(cudaEventSynchronize(h->ev_io));
+    h->async_dirty = false;
     return XQ_OK;
 }
 int xq_env_rollout_random_io(xq_env_t h, const xq_env_rec* boards_in_host, int n_plies, xq_env_rec* boards_out_host,
                              xq_trace_rec* trace_host, xq_env_stats* stats_host) {
-    if (int rc = xq_env_rollout_random_io_submit(h, boards_in_host, n_plies, boards_out_host, trace_host, stats_host)) return rc;
+    XQ_ENV_ENTER(h);
+    if (int rc = rollout_io_enqueue(h, boards_in_host, n_plies, boards_out_host, trace_host, stats_host, false)) return rc;
     return xq_env_rollout_random_io_wait(h);
 }
 int xq_env_rollout_random(xq_env_t h, int n_plies, xq_trace_rec* trace_host, xq_env_stats* stats_host) {

@@ -145,8 +145,10 @@ int xq_env_rollout_random_io(xq_env_t h, const xq_env_rec* boards_in_host, int n
 /* The same call in two halves, for a double-buffered caller (two env handles on one stream: the host submits the step of handle B before
  * it waits for the step of handle A, so launch latency and the host's wake-up hide under the other handle's kernel; the kernels of one
  * stream never overlap).  _submit enqueues [boards in -> rollout -> boards / trace / stats out] and returns; _wait blocks until that
- * step's outputs are in host memory.  The host buffers belong to the library between the two calls; one submission per handle at a
- * time (XQ_ERR_STATE otherwise).  xq_env_rollout_random_io == _submit + _wait. */
+ * step's outputs are in host memory.  The copies run on copy streams owned by the handle, ordered against the rollout by events: the boards
+ * of the next step arrive and the results of the previous step leave while the other handle's kernel runs.  The host buffers and the handle
+ * belong to the library between the two calls: one submission per handle at a time, every other call on the handle is refused until _wait
+ * (XQ_ERR_STATE).  Results are identical to xq_env_rollout_random_io (which reads / writes pinned buffers from inside the kernel instead). */
 int xq_env_rollout_random_io_submit(xq_env_t h, const xq_env_rec* boards_in_host, int n_plies, xq_env_rec* boards_out_host,
                                     xq_trace_rec* trace_host, xq_env_stats* stats_host);
 int xq_env_rollout_random_io_wait(xq_env_t h);

@@ -61,6 +61,8 @@ def hostsim():
     H.hs_team_rollout.argtypes = [C.c_int, P, C.c_long, C.c_uint64, C.c_uint64, C.c_int, P, P]
     H.hs_lane_rollout.argtypes = [P, C.c_long, C.c_uint64, C.c_uint64, C.c_int, P, P]
     H.hs_lane_all_actions.argtypes = [P, C.c_long, P, P]
+    H.hs_team_all_actions.argtypes = [P, C.c_long, P, P]
+    H.hs_summarize_words.argtypes = [P, C.c_long, P]
     H.hs_act_quant.argtypes = [P, C.c_long, P]
     return H
 

@@ -200,6 +200,49 @@ int hs_lane_all_actions(const xq_env_rec* recs, long n, uint8_t* counts, uint16_
     }
     return nonstd;
 }
+// the team list kernel's phases (legal_moves_team_kernel: team_phase_a + team_emit_actions), the 4 threads of a board one after the other
+int hs_team_all_actions(const xq_env_rec* recs, long n, uint8_t* counts, uint16_t* actions) {
+    using namespace xq;
+    int nonstd = 0;
+    for (long env = 0; env < n; ++env) {
+        uint16_t* out = actions + env * XQ_MAX_ACTIONS;
+        for (int k = 0; k < XQ_MAX_ACTIONS; ++k) out[k] = XQ_ACTION_NONE;
+        counts[env] = 0xFF;
+        TeamShared<1> sh;
+        uint8_t slot[32];
+        for (int i = 0; i < 32; ++i) slot[i] = kDeadSq;
+        uint32_t w[12];
+        std::memcpy(w, recs[env].sq, 48);
+        // the kernel unpacks the two colours in two warps (team_unpack_side)
+        Bits90 bb[2], oT[2];
+        bool ok = true;
+        for (int side = 0; side < 2; ++side) ok &= team_unpack_side(w, side, bb[side], oT[side], [&](int s, int q) { slot[side * 16 + s] = (uint8_t)q; });
+        if (!ok) { ++nonstd; continue; }
+        TeamRole R[4];
+        TeamState st[4];
+        TeamPly pl[4];
+        for (int r = 0; r < 4; ++r) {
+            R[r] = team_role<4>(r);
+            team_reset(R[r], st[r]);
+            uint32_t wr = 0, wb = 0;
+            for (int i = 0; i < 4; ++i) {
+                const int s = (int)((R[r].slots >> (8 * i)) & 0xFFu);
+                wr |= (uint32_t)slot[s] << (8 * i);
+                wb |= (uint32_t)slot[16 + s] << (8 * i);
+            }
+            const bool redp = recs[env].player == 0;
+            st[r].occT = Bits90{oT[0].w0 | oT[1].w0, oT[0].w1 | oT[1].w1, oT[0].w2 | oT[1].w2};
+            st[r].move_count = recs[env].move_count; st[r].player = recs[env].player; st[r].ctr = recs[env].ctr;
+            st[r].sq_own = redp ? wr : wb; st[r].sq_opp = redp ? wb : wr;
+            st[r].own = redp ? bb[0] : bb[1]; st[r].opp = redp ? bb[1] : bb[0];
+        }
+        for (int r = 0; r < 4; ++r) team_phase_a<4, 1>(R[r], st[r], pl[r], sh, 0, 0);
+        uint32_t tot = 0;
+        for (int r = 0; r < 4; ++r) tot = team_emit_actions<1>(R[r], st[r], pl[r], sh, 0, [&](int idx, int a) { out[idx] = (uint16_t)a; });
+        counts[env] = (uint8_t)tot;
+    }
+    return nonstd;
+}
 // DQN::selectAction through the board-per-thread functions (act_lane_kernel): same contract as hs_act_team
 int hs_act_lane(const xq_env_rec* recs, long n, uint64_t env_id0, uint64_t seed, const float* q90, uint32_t eps_thr, uint16_t* actions) {
     int nonstd = 0;
@@ -306,6 +349,15 @@ void hs_bb_all_actions(const xq_env_rec* recs, long n, uint8_t* counts, uint16_t
             }
         }
         counts[i] = (uint8_t)cnt;
+    }
+}
+// step_kernel's board summary (summarize_words, xq_bitboard.cuh): out[i] = {mat_red, mat_black, lowest square of the Red General or 127, same for Black}
+void hs_summarize_words(const xq_env_rec* recs, long n, int* out) {
+    for (long i = 0; i < n; ++i) {
+        uint32_t w[12];
+        std::memcpy(w, recs[i].sq, 48);
+        const xq::WordSummary s = xq::summarize_words(w);
+        out[4 * i] = s.mat_red; out[4 * i + 1] = s.mat_black; out[4 * i + 2] = s.gen_red; out[4 * i + 3] = s.gen_black;
     }
 }
 int hs_reward(int material_diff, int move_count) { return xq::reward_from_material(material_diff, move_count); }

@@ -204,6 +204,25 @@ def test_api_mode_on_the_device_equals_fused_rollout(xq, O, oracle_lib):
     assert (counts == c0).all() and (acts == a0).all()
 
 
+def test_list_kernels_team_and_board_per_thread(xq, O, oracle_lib, monkeypatch):
+    """xq_env_legal_moves through BOTH list kernels -- the team of 4 threads per board (legal_moves_team_kernel, the default up to 12,288 envs)
+    and one thread per board (legal_moves_lane_kernel) -- forced in turn on the same boards: ordered lists == the oracle's, bit for bit, for
+    reachable positions, arbitrary standard boards, arbitrary piece sets (generic kernel) and a grid whose last CTA is partly empty"""
+    base = np.concatenate([harvest_positions(O, 700, 9, 33, seed=4), random_boards(O, 1500, seed=17)])
+    for n in (len(base) - 13, 3 * len(base) + 5):
+        recs = np.concatenate([base] * 4)[:n].copy()
+        c0 = np.zeros(n, np.uint8); a0 = np.zeros((n, 128), np.uint16)
+        oracle_lib.xqo_batch_all_actions(recs.ctypes.data, n, c0, a0)
+        a0[np.arange(128)[None, :] >= c0[:, None]] = 0xFFFF
+        env = xq.BatchedEnv(n, seed=1)
+        env.set_boards(recs)
+        for team in ("1", "0"):
+            monkeypatch.setenv("XQ_LEGAL_TEAM", team)
+            counts, acts = env.legal_moves()
+            assert (counts == c0).all() and (acts == a0).all(), (n, team)
+        monkeypatch.delenv("XQ_LEGAL_TEAM")
+
+
 def test_step_rejects_invalid_moves(xq, O, oracle_lib):
     recs = np.concatenate([harvest_positions(O, 256, 4, 31), random_boards(O, 1024, seed=8)])
     n = len(recs)

@@ -138,6 +138,42 @@ def test_lane_list_emission(O, oracle_lib, hostsim, golden):
         assert len(bad) == 0, f"{len(bad)} boards differ, first {bad[:4]}"
 
 
+def test_team_list_emission(O, oracle_lib, hostsim, golden):
+    """xq_act_team.cuh (legal_moves_team_kernel): the team's generator (team_unpack_side per colour, team_phase_a) + team_emit_actions ==
+    the oracle's ordered lists -- same cases as the board-per-thread list kernel"""
+    for recs in (harvest_positions(O, 800, 45, 5), random_boards(O, 4000, seed=21), recs_from_codes(O, golden["pos_codes"], golden["pos_meta"])):
+        n = len(recs)
+        c1, a1 = _oracle_lists(oracle_lib, recs)
+        c2 = np.zeros(n, np.uint8)
+        a2 = np.zeros((n, 128), np.uint16)
+        nonstd = hostsim.hs_team_all_actions(recs.ctypes.data, n, c2.ctypes.data, a2.ctypes.data)
+        std = c2 != 0xFF
+        assert nonstd == int((~std).sum()) and std.sum() > 500
+        bad = np.nonzero(std & ((c1 != c2) | (a1 != a2).any(1)))[0]
+        assert len(bad) == 0, f"{len(bad)} boards differ, first {bad[:4]}"
+
+
+def test_summarize_words(O, hostsim):
+    """xq_bitboard.cuh: summarize_words (step_kernel's material / General search on the packed nibble words, bit-plane SIMD) == a plain
+    per-square scan -- reachable positions, arbitrary piece sets (several Generals, none), full and empty boards, padding nibbles ignored"""
+    recs = np.concatenate([harvest_positions(O, 500, 6, 37, seed=8), random_boards(O, 5000, seed=33, max_pieces=60), O.new_envs(3)])
+    recs["sq"][-1] = 0                                        # empty board
+    recs["sq"][-2] = np.uint32(0x88888888)                    # a Black General on every square; the padding nibbles of word 11 must not count ...
+    recs["sq"][-2, 11] = np.uint32(0x00000088)                # ... so they are kept zero, as every record has them
+    n = len(recs)
+    out = np.zeros((n, 4), np.int32)
+    hostsim.hs_summarize_words(recs.ctypes.data, n, out.ctypes.data)
+    score = np.array([0, 1000, 20, 20, 40, 90, 45, 10, 1000, 20, 20, 40, 90, 45, 10, 0])
+    sq = recs["sq"]
+    codes = np.stack([(sq[:, s >> 3] >> (4 * (s & 7))) & 15 for s in range(90)], 1).astype(np.int64)
+    mat_red = (score[codes] * ((codes >= 1) & (codes <= 7))).sum(1)
+    mat_black = (score[codes] * (codes >= 8)).sum(1)
+    first = lambda c: np.where((codes == c).any(1), (codes == c).argmax(1), 127)
+    assert (out[:, 0] == mat_red).all() and (out[:, 1] == mat_black).all()
+    assert (out[:, 2] == first(1)).all() and (out[:, 3] == first(8)).all()
+    assert out[-2, 1] == 90 * 1000 and out[-2, 3] == 0 and out[-1].tolist() == [0, 0, 127, 127]
+
+
 def test_lane_rollout_ply(O, oracle_lib, hostsim):
     """xq_rollout_lane.cuh (rollout_lane_kernel): the board-per-thread ply run on the host reproduces the oracle's fused rollout record
     for record -- same cases as the team kernel (from the opening over several games, resumed mid-game, finished boards)"""
