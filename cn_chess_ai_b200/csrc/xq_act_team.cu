@@ -50,7 +50,7 @@ __global__ void __launch_bounds__(kAB * 4) act_team_kernel(xq_env_rec* __restric
     const int tid = threadIdx.x, lane = tid & 31;
     const TeamRole R = team_role<4>(tid >> 5);
     const int64_t env0 = (int64_t)blockIdx.x * kAB, env = env0 + lane;
-    for (int d = tid + 1; d <= XQ_MAX_ACTIONS; d += kAB * 4) sh.magic[d] = team_mod_magic((uint32_t)d);
+    team_tables_init(sh, tid, kAB * 4);
     if (tid < kAB) sh.move[tid] = 0;
     if (APPLY && carry.Z != nullptr && env0 + (tid >> 2) < n)      // the CTA's 32 sums (16 KB) towards L2 now: the tail reads them ~20 us later
         asm volatile("prefetch.global.L2 [%0];" ::"l"(carry.Z + env0 * 128 + tid * 32));
@@ -310,6 +310,7 @@ __global__ void __launch_bounds__(kAB * 4) legal_moves_team_kernel(const xq_env_
     const int tid = threadIdx.x, lane = tid & 31;
     const TeamRole R = team_role<4>(tid >> 5);
     const int64_t env0 = (int64_t)blockIdx.x * kAB, env = env0 + lane;
+    team_tables_init(sh, tid, kAB * 4);
     if (R.role < 2) {
         const int side = R.role;
         bool ok = env < n;

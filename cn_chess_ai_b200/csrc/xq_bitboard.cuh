@@ -215,6 +215,105 @@ XQ_HD uint32_t soldier_mask(const Pos& P, int sq, int color) {                  
     m |= (crossed & (c < 8 ? 1u : 0u) & ~own.at(1)) << 2;
     return m;
 }
+// ---- geometry table (shared-memory piece table) ---------------------------------------------------------------------------------
+// Everything a leaper's mask needs that depends on the SQUARE and the colour only -- board bounds, palaces, the river -- is one table
+// word per (colour, square): the kernels keep the 2 x 128 words in shared memory and the *_mask_g functions AND it onto the bits taken
+// from the bitboards.  In the rollout kernels (bound by the integer ALU pipe) this moves ~10 % of a ply's instructions -- the row /
+// column arithmetic and 3-7 compares per direction -- to one shared-memory load per piece.  Entries 90..127 are 0: a captured piece
+// (square 127) gets an empty mask without a select.
+//   bits 0-7 Horse | 8-11 Elephant | 12-15 Advisor | 16-19 General | 20-22 Soldier   (direction order of generate*Moves)
+constexpr int kGeoWords = 256;                     // [colour][128]
+XQ_HD constexpr uint32_t geo_entry(int color, int sq) {
+    if (sq >= 90) return 0u;
+    const int r = sq / 9, c = sq - 9 * r;
+    uint32_t g = 0;
+    for (int k = 0; k < 8; ++k) {                  // :248-263
+        const int a = (k & 2) ? -1 : 1, b = (k & 1) ? -1 : 1;
+        const int nr = r + (k < 4 ? a : 2 * a), nc = c + (k < 4 ? 2 * b : b);
+        g |= (inside(nr, nc) ? 1u : 0u) << k;
+    }
+    for (int k = 0; k < 4; ++k) {
+        {                                          // Elephant :179-196, :355-367
+            const int nr = r + (k < 2 ? 2 : -2), nc = c + ((k & 1) ? -2 : 2);
+            const bool side_ok = color == RED ? (nr <= 4 && r < 5) : (nr >= 5 && r >= 5);
+            g |= ((inside(nr, nc) & side_ok) ? 1u : 0u) << (8 + k);
+        }
+        {                                          // Advisor :162-177
+            const int nr = r + (k < 2 ? 1 : -1), nc = c + ((k & 1) ? -1 : 1);
+            g |= (in_palace_of(color, nr, nc) ? 1u : 0u) << (12 + k);
+        }
+        {                                          // General :149-160, :328-343
+            const int nr = r + (k == 0 ? 1 : (k == 1 ? -1 : 0)), nc = c + (k == 2 ? 1 : (k == 3 ? -1 : 0));
+            g |= ((in_any_palace(nr, nc) & in_any_palace(r, c)) ? 1u : 0u) << (16 + k);
+        }
+    }
+    {                                              // Soldier :265-283
+        const int nr = r + (color == RED ? 1 : -1);
+        const bool crossed = color == RED ? r > 4 : r < 5;
+        g |= ((unsigned)nr < 10u ? 1u : 0u) << 20;
+        g |= ((crossed && c > 0) ? 1u : 0u) << 21;
+        g |= ((crossed && c < 8) ? 1u : 0u) << 22;
+    }
+    return g;
+}
+struct GeoTable { uint32_t v[kGeoWords]; };
+constexpr GeoTable make_geo_table() {
+    GeoTable t{};
+    for (int i = 0; i < kGeoWords; ++i) t.v[i] = geo_entry(i >> 7, i & 127);
+    return t;
+}
+#if defined(__CUDACC__)
+static __device__ const GeoTable d_geo = make_geo_table();       // built by the compiler; the kernels copy it into shared memory
+#endif
+XQ_HD uint32_t geo_word(int i) {
+#if defined(__CUDA_ARCH__)
+    return d_geo.v[i];
+#else
+    return geo_entry(i >> 7, i & 127);
+#endif
+}
+// the same masks as *_mask above with the geometry from the table word g = geo[colour * 128 + sq]
+XQ_HD uint32_t horse_mask_g(const Pos& P, int sq, uint32_t g) {
+    const Win41 own = window(P.own, sq), occ = window(P.occ, sq);
+    uint32_t m = 0;
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+        const int a = (k & 2) ? -1 : 1, b = (k & 1) ? -1 : 1;
+        const int leg = k < 4 ? b : 9 * a, dest = k < 4 ? 9 * a + 2 * b : 18 * a + b;
+        m |= (occ.at(leg) | own.at(dest)) << k;
+    }
+    return ~m & g & 0xFFu;
+}
+XQ_HD uint32_t elephant_mask_g(const Pos& P, int sq, uint32_t g) {
+    const Win41 own = window(P.own, sq), occ = window(P.occ, sq);
+    uint32_t m = 0;
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+        const int d = k == 0 ? 20 : (k == 1 ? 16 : (k == 2 ? -16 : -20));
+        m |= (occ.at(d / 2) | own.at(d)) << k;
+    }
+    return ~m & (g >> 8) & 0xFu;
+}
+XQ_HD uint32_t advisor_mask_g(const Pos& P, int sq, uint32_t g) {
+    const Win41 own = window(P.own, sq);
+    uint32_t m = 0;
+#pragma unroll
+    for (int k = 0; k < 4; ++k) m |= own.at(k == 0 ? 10 : (k == 1 ? 8 : (k == 2 ? -8 : -10))) << k;
+    return ~m & (g >> 12) & 0xFu;
+}
+XQ_HD uint32_t general_mask_g(const Pos& P, int sq, uint32_t g) {
+    const Win41 own = window(P.own, sq);
+    uint32_t m = 0;
+#pragma unroll
+    for (int k = 0; k < 4; ++k) m |= own.at(k == 0 ? 9 : (k == 1 ? -9 : (k == 2 ? 1 : -1))) << k;
+    return ~m & (g >> 16) & 0xFu;
+}
+XQ_HD uint32_t soldier_mask_g(const Pos& P, int sq, int color, uint32_t g) {
+    const Win41 own = window(P.own, sq);
+    const uint32_t m = (color == RED ? own.at(9) : own.at(-9)) | (own.at(-1) << 1) | (own.at(1) << 2);
+    return ~m & (g >> 20) & 0x7u;
+}
+
 // index of the j-th (0-based) set bit of an 8-bit mask
 XQ_HD int nth_set_bit(uint32_t m, int j) {
 #pragma unroll

@@ -19,9 +19,11 @@ __global__ void __launch_bounds__(kLaneMaxThreads) rollout_lane_kernel(xq_env_re
                                                                       xq_env_rec* __restrict__ mirror) {
     __shared__ uint8_t s_slot[32 * kLaneMaxThreads];      // [slot][thread]
     __shared__ uint32_t s_magic[XQ_MAX_ACTIONS + 1];
+    __shared__ uint32_t s_geo[kGeoWords];                 // geometry table of the leapers (xq_bitboard.cuh)
     const int tid = threadIdx.x, bs = blockDim.x;
     const int64_t env = (int64_t)blockIdx.x * bs + tid;
     for (int d = tid + 1; d <= XQ_MAX_ACTIONS; d += bs) s_magic[d] = team_mod_magic((uint32_t)d);
+    for (int i = tid; i < kGeoWords; i += bs) s_geo[i] = geo_word(i);
     LaneState st;
     LaneStats a{0, 0, 0, 0, 0, 0, 0, 0};
     bool active = env < n;
@@ -45,13 +47,13 @@ __global__ void __launch_bounds__(kLaneMaxThreads) rollout_lane_kernel(xq_env_re
         flags = m.x & 0xFF000000u;
         lane_load(st, [&](int s) { return (int)s_slot[s * bs + tid]; }, red, black, occT, (int)(m.x & 0xFFFFu), (int)((m.x >> 16) & 0xFFu), (int)m.y, (int)m.z, m.w);
     }
-    __syncthreads();                                      // the modulo table
+    __syncthreads();                                      // the modulo and geometry tables
     if (active) {
         const uint64_t rng_base = seed + (env_id0 + (uint64_t)env) * 0x9E3779B97F4A7C15ull;
         xq_trace_rec* t = trace ? trace + env : nullptr;
 #pragma unroll 1
         for (int p = 0; p < n_plies; ++p) {
-            lane_ply(st, a, rng_base, s_magic, t);
+            lane_ply(st, a, rng_base, s_magic, s_geo, t);
             if (t) t += n;
         }
         uint32_t words[12];
@@ -94,8 +96,11 @@ __global__ void __launch_bounds__(kLmThreads) legal_moves_lane_kernel(const xq_e
     __shared__ uint8_t s_slot[32 * kLmThreads];
     __shared__ uint32_t s_list[kLmThreads * kLmRow];
     __shared__ uint8_t s_cnt[kLmThreads];                    // list size; 0xFF = not produced here (tail of the grid, non-standard piece set)
+    __shared__ uint32_t s_geo[kGeoWords];
     const int tid = threadIdx.x;
     const int64_t env0 = (int64_t)blockIdx.x * kLmThreads, env = env0 + tid;
+    for (int i = tid; i < kGeoWords; i += kLmThreads) s_geo[i] = geo_word(i);
+    __syncthreads();
     int cnt = 0xFF;
     if (env < n) {
         const uint4* rec = reinterpret_cast<const uint4*>(envs + env);
@@ -113,7 +118,7 @@ __global__ void __launch_bounds__(kLmThreads) legal_moves_lane_kernel(const xq_e
             for (int pos = 0; pos < 16; ++pos)
                 own_sq[pos >> 2] |= (uint32_t)s_slot[((player ? 16 : 0) + lane_pos_slot(pos)) * kLmThreads + tid] << (8 * (pos & 3));
             uint32_t sdesc[4], cw[4], dw[4];
-            lane_movegen(own_sq, player ? black : red, player ? red : black, occT, player, sdesc, cw, dw);
+            lane_movegen(own_sq, player ? black : red, player ? red : black, occT, player, s_geo, sdesc, cw, dw);
             uint16_t* row = reinterpret_cast<uint16_t*>(s_list + tid * kLmRow);
             cnt = lane_emit_actions(own_sq, player, sdesc, cw, dw, [&](int idx, int a, bool live) { if (live) row[idx] = (uint16_t)a; });
             counts[env] = (uint8_t)cnt;

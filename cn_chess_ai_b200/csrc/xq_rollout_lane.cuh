@@ -91,8 +91,9 @@ XQ_HD uint32_t lane_actions_below(const uint32_t (&sq)[4], const uint32_t (&cw)[
 
 // Every piece of the side to move: move counts (cw, one byte per position), the sliders' descriptors (sdesc, xq_bitboard.cuh) and the
 // leapers' direction masks (dw, one byte per position; dw[0] = 0).  A captured piece (square 127) reads garbage bits, its count is discarded.
-XQ_HD void lane_movegen(const uint32_t (&own_sq)[4], const Bits90& own, const Bits90& opp, const Bits90& occT, int color,
+XQ_HD void lane_movegen(const uint32_t (&own_sq)[4], const Bits90& own, const Bits90& opp, const Bits90& occT, int color, const uint32_t* geo,
                         uint32_t (&sdesc)[4], uint32_t (&cw)[4], uint32_t (&dw)[4]) {
+    const uint32_t* gq = geo + color * 128;      // geometry table of the side to move (xq_bitboard.cuh: geo_entry), entries 90..127 = 0
     Pos P;
     P.own = own;
     P.occ = Bits90{own.w0 | opp.w0, own.w1 | opp.w1, own.w2 | opp.w2};
@@ -115,13 +116,14 @@ XQ_HD void lane_movegen(const uint32_t (&own_sq)[4], const Bits90& own, const Bi
         for (int i = 0; i < 4; ++i) {
             const int q = (int)((own_sq[w] >> (8 * i)) & 0xFFu);
             const int pos = 4 * w + i;
+            const uint32_t g = gq[q];                                // 0 for a captured piece (square 127): its mask is empty
             uint32_t v;
-            if (pos < 6) v = horse_mask(P, q);                       // :248-263
-            else if (pos < 8) v = elephant_mask(P, q, color);        // :179-196
-            else if (pos < 10) v = advisor_mask(P, q, color);        // :162-177
-            else if (pos == 10) v = general_mask(P, q);              // :149-160
-            else v = soldier_mask(P, q, color);                      // :265-283
-            m[i] = q == kDeadSq ? 0u : v;
+            if (pos < 6) v = horse_mask_g(P, q, g);                  // :248-263
+            else if (pos < 8) v = elephant_mask_g(P, q, g);          // :179-196
+            else if (pos < 10) v = advisor_mask_g(P, q, g);          // :162-177
+            else if (pos == 10) v = general_mask_g(P, q, g);         // :149-160
+            else v = soldier_mask_g(P, q, color, g);                 // :265-283
+            m[i] = v;
         }
         dw[w] = m[0] | (m[1] << 8) | (m[2] << 16) | (m[3] << 24);
         cw[w] = (uint32_t)popc32(m[0]) | ((uint32_t)popc32(m[1]) << 8) | ((uint32_t)popc32(m[2]) << 16) | ((uint32_t)popc32(m[3]) << 24);
@@ -286,11 +288,11 @@ XQ_HD uint32_t lane_select_kth(const uint32_t (&own_sq)[4], int color, const uin
 }
 
 // One ply of ChessAI::train's loop body without the network (src/chessai.cpp:96-119) on one board.
-// magic[d] = team_mod_magic(d) for d = 1..128.  trace (may be null) -> the record of this ply.
-XQ_HD void lane_ply(LaneState& st, LaneStats& a, uint64_t rng_base, const uint32_t* magic, xq_trace_rec* trace) {
+// magic[d] = team_mod_magic(d) for d = 1..128; geo = the geometry table (kGeoWords words, geo_entry).  trace (may be null) -> the record of this ply.
+XQ_HD void lane_ply(LaneState& st, LaneStats& a, uint64_t rng_base, const uint32_t* magic, const uint32_t* geo, xq_trace_rec* trace) {
     const int color = st.player;
     uint32_t sdesc[4], cw[4], dw[4];
-    lane_movegen(st.own_sq, st.own, st.opp, st.occT, color, sdesc, cw, dw);
+    lane_movegen(st.own_sq, st.own, st.opp, st.occT, color, geo, sdesc, cw, dw);
     uint32_t tot = 0;
 #pragma unroll
     for (int w = 0; w < 4; ++w) tot = dp4a_u(cw[w], 0x01010101u, tot);

@@ -32,7 +32,7 @@ __global__ void __launch_bounds__(kTB * T) rollout_team_kernel(xq_env_rec* __res
     const int tid = threadIdx.x, lane = tid & 31;
     const TeamRole R = team_role<T>(tid >> 5);
     const int64_t env = (int64_t)blockIdx.x * kTB + lane;
-    for (int d = tid + 1; d <= XQ_MAX_ACTIONS; d += kTB * T) sh.magic[d] = team_mod_magic((uint32_t)d);
+    team_tables_init(sh, tid, kTB * T);
     if (tid < kTB) sh.move[tid] = 0;
 
     // ---- load: warp 0 converts 32 records to slots + bitboards ----------------------------------

@@ -115,7 +115,14 @@ struct TeamShared {
     uint32_t cap[2 * KB];          // value | code << 16 of the captured piece, double-buffered by ply parity
     uint32_t rng[2 * 16 * KB];     // idx31 draws of 16 plies, double-buffered by chunk parity
     uint32_t magic[XQ_MAX_ACTIONS + 1];
+    uint32_t geo[kGeoWords];       // geometry table of the leapers (xq_bitboard.cuh: geo_entry), [colour][128]
 };
+// the two tables of a CTA: magic[d] = team_mod_magic(d), geo[colour * 128 + sq] = geo_entry(colour, sq); a barrier must follow
+template <class SH>
+XQ_HD void team_tables_init(SH& sh, int tid, int n_threads) {
+    for (int d = tid + 1; d <= XQ_MAX_ACTIONS; d += n_threads) sh.magic[d] = (0xFFFFFFFFu / (uint32_t)d) + 1u;
+    for (int i = tid; i < kGeoWords; i += n_threads) sh.geo[i] = geo_word(i);
+}
 
 struct TeamState {
     uint32_t sq_own, sq_opp;       // packed squares of my 4 slots: side to move / the other side
@@ -209,20 +216,22 @@ XQ_HD void team_phase_a(const TeamRole& R, const TeamState& st, TeamPly& pl, Tea
     P.occT = st.occT;
     const int color = st.player;
     const int q0 = (int)(st.sq_own & 0xFFu), q1 = (int)((st.sq_own >> 8) & 0xFFu);
-    // a captured piece (square 127) reads garbage bits: its count is discarded
+    // a captured piece (square 127) reads garbage bits: a slider's count is discarded, a leaper's table word is 0
     if (T == 4) {
         const bool hi = R.role >= 2;
         const int q2 = (int)((st.sq_own >> 16) & 0xFFu), q3 = (int)(st.sq_own >> 24);
+        const uint32_t* gq = sh.geo + color * 128;
+        const uint32_t g1 = gq[q1], g2 = gq[q2], g3 = gq[q3];
         int c0 = slider_desc_rt(P, q0, hi, &pl.desc[0]);
         uint32_t m1, m2, m3;
-        if (!hi) { m1 = horse_mask(P, q1); m2 = soldier_mask(P, q2, color); m3 = soldier_mask(P, q3, color); }
+        if (!hi) { m1 = horse_mask_g(P, q1, g1); m2 = soldier_mask_g(P, q2, color, g2); m3 = soldier_mask_g(P, q3, color, g3); }
         else {
-            m1 = advisor_mask(P, q1, color); m2 = elephant_mask(P, q2, color);
-            m3 = R.role == 2 ? general_mask(P, q3) : soldier_mask(P, q3, color);
+            m1 = advisor_mask_g(P, q1, g1); m2 = elephant_mask_g(P, q2, g2);
+            m3 = R.role == 2 ? general_mask_g(P, q3, g3) : soldier_mask_g(P, q3, color, g3);
         }
         pl.desc[1] = m1; pl.desc[2] = m2; pl.desc[3] = m3;
         c0 = q0 == kDeadSq ? 0 : c0;
-        const int c1 = q1 == kDeadSq ? 0 : popc32(m1), c2 = q2 == kDeadSq ? 0 : popc32(m2), c3 = q3 == kDeadSq ? 0 : popc32(m3);
+        const int c1 = popc32(m1), c2 = popc32(m2), c3 = popc32(m3);
         pl.cntw = (uint32_t)c0 | ((uint32_t)c1 << 8) | ((uint32_t)c2 << 16) | ((uint32_t)c3 << 24);
         sh.q[R.role * KB + lane] = st.sq_own;
         sh.c[R.role * KB + lane] = pl.cntw;

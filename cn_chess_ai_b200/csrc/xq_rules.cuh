@@ -27,11 +27,11 @@ enum : int { RED = 0, BLACK = 1, NOCOLOR = 2 };
 XQ_HD int type_of(int code) { return code >= 8 ? code - 7 : code; }
 XQ_HD int color_of(int code) { return code == 0 ? NOCOLOR : (code >= 8 ? BLACK : RED); }
 // (bitwise &, | on purpose: short-circuit operators became branch regions in the generators)
-XQ_HD bool inside(int r, int c) { return ((unsigned)r < 10u) & ((unsigned)c < 9u); }  // :323-325
-XQ_HD bool in_palace_of(int color, int r, int c) {                                  // chessboard.h:65-71
+XQ_HD constexpr bool inside(int r, int c) { return ((unsigned)r < 10u) & ((unsigned)c < 9u); }  // :323-325
+XQ_HD constexpr bool in_palace_of(int color, int r, int c) {                                  // chessboard.h:65-71
     return ((unsigned)(c - 3) < 3u) & ((unsigned)(r - (color == RED ? 0 : 7)) < 3u);
 }
-XQ_HD bool in_any_palace(int r, int c) { return ((unsigned)(c - 3) < 3u) & (((unsigned)r < 3u) | ((unsigned)(r - 7) < 3u)); }
+XQ_HD constexpr bool in_any_palace(int r, int c) { return ((unsigned)(c - 3) < 3u) & (((unsigned)r < 3u) | ((unsigned)(r - 7) < 3u)); }
 
 // getPieceScore / PieceScore, src/chessboard.cpp:443-454, include/chessboard.h:23-31.
 // Packed table: scores are multiples of 5 -> score/5 fits a byte (200,4,4,8,18,9,2).

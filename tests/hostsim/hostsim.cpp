@@ -27,7 +27,7 @@ int team_rollout_host(xq_env_rec* recs, long n, uint64_t env_id0, uint64_t seed,
     int nonstd = 0;
     for (long env = 0; env < n; ++env) {
         TeamShared<1> sh;
-        for (int d = 1; d <= XQ_MAX_ACTIONS; ++d) sh.magic[d] = team_mod_magic((uint32_t)d);
+        team_tables_init(sh, 0, 1);
         uint8_t slot[32];
         for (int i = 0; i < 32; ++i) slot[i] = kDeadSq;
         uint32_t w[12];
@@ -99,6 +99,12 @@ int team_rollout_host(xq_env_rec* recs, long n, uint64_t env_id0, uint64_t seed,
 
 // ---- the board-per-thread rollout kernel's ply (xq_rollout_lane.cuh), one board at a time ----
 namespace {
+const uint32_t* host_geo() {
+    static uint32_t g[xq::kGeoWords];
+    static bool init = false;
+    if (!init) { for (int i = 0; i < xq::kGeoWords; ++i) g[i] = xq::geo_entry(i >> 7, i & 127); init = true; }
+    return g;
+}
 int lane_rollout_host(xq_env_rec* recs, long n, uint64_t env_id0, uint64_t seed, int n_plies, xq_trace_rec* trace, xq_env_stats* stats) {
     int nonstd = 0;
     uint32_t magic[XQ_MAX_ACTIONS + 1] = {0};
@@ -115,7 +121,7 @@ int lane_rollout_host(xq_env_rec* recs, long n, uint64_t env_id0, uint64_t seed,
         lane_load(st, [&](int s) { return (int)slot[s]; }, red, black, occT, recs[env].move_count, recs[env].player, recs[env].red_score,
                   recs[env].black_score, recs[env].ctr);
         const uint64_t base = seed + (env_id0 + (uint64_t)env) * 0x9E3779B97F4A7C15ull;
-        for (int p = 0; p < n_plies; ++p) lane_ply(st, a, base, magic, trace ? trace + ((long)p * n + env) : nullptr);
+        for (int p = 0; p < n_plies; ++p) lane_ply(st, a, base, magic, host_geo(), trace ? trace + ((long)p * n + env) : nullptr);
         uint32_t words[12];
         lane_store_words(st, words);
         std::memcpy(recs[env].sq, words, 48);
@@ -138,7 +144,7 @@ int act_team_host(const xq_env_rec* recs, long n, uint64_t env_id0, uint64_t see
         actions[env] = XQ_ACTION_NONE;
         TeamShared<1> sh;
         ActShared<1> as;
-        for (int d = 1; d <= XQ_MAX_ACTIONS; ++d) sh.magic[d] = team_mod_magic((uint32_t)d);
+        team_tables_init(sh, 0, 1);
         for (int t = 0; t < kQStride; ++t) as.qt[t * 2] = q90[env * kQStride + t];
         uint8_t slot[32];
         for (int i = 0; i < 32; ++i) slot[i] = kDeadSq;
@@ -195,7 +201,7 @@ int hs_lane_all_actions(const xq_env_rec* recs, long n, uint8_t* counts, uint16_
         uint32_t own_sq[4] = {0, 0, 0, 0};
         for (int pos = 0; pos < 16; ++pos) own_sq[pos >> 2] |= (uint32_t)slot[(player ? 16 : 0) + xq::lane_pos_slot(pos)] << (8 * (pos & 3));
         uint32_t sdesc[4], cw[4], dw[4];
-        xq::lane_movegen(own_sq, player ? black : red, player ? red : black, occT, player, sdesc, cw, dw);
+        xq::lane_movegen(own_sq, player ? black : red, player ? red : black, occT, player, host_geo(), sdesc, cw, dw);
         counts[i] = (uint8_t)xq::lane_emit_actions(own_sq, player, sdesc, cw, dw, [&](int idx, int a, bool live) { if (live) out[idx] = (uint16_t)a; });
     }
     return nonstd;
@@ -209,6 +215,7 @@ int hs_team_all_actions(const xq_env_rec* recs, long n, uint8_t* counts, uint16_
         for (int k = 0; k < XQ_MAX_ACTIONS; ++k) out[k] = XQ_ACTION_NONE;
         counts[env] = 0xFF;
         TeamShared<1> sh;
+        team_tables_init(sh, 0, 1);
         uint8_t slot[32];
         for (int i = 0; i < 32; ++i) slot[i] = kDeadSq;
         uint32_t w[12];
@@ -260,7 +267,7 @@ int hs_act_lane(const xq_env_rec* recs, long n, uint64_t env_id0, uint64_t seed,
         uint32_t own_sq[4] = {0, 0, 0, 0};
         for (int pos = 0; pos < 16; ++pos) own_sq[pos >> 2] |= (uint32_t)slot[(player ? 16 : 0) + xq::lane_pos_slot(pos)] << (8 * (pos & 3));
         uint32_t sdesc[4], cw[4], dw[4], tot = 0;
-        xq::lane_movegen(own_sq, player ? black : red, player ? red : black, occT, player, sdesc, cw, dw);
+        xq::lane_movegen(own_sq, player ? black : red, player ? red : black, occT, player, host_geo(), sdesc, cw, dw);
         for (int k = 0; k < 4; ++k) tot = xq::dp4a_u(cw[k], 0x01010101u, tot);
         if (tot == 0) continue;
         const uint64_t x = xq::rng(seed, env_id0 + (uint64_t)i, recs[i].ctr);
