@@ -53,6 +53,7 @@ __global__ void __launch_bounds__(kLB) act_lane_kernel(xq_env_rec* __restrict__ 
     __shared__ uint32_t s_upd[kLB];               // what the ply did to the board, for the carried sums: from | to << 7 | code << 14 | cap << 18 | flags
     __shared__ uint32_t s_magic[XQ_MAX_ACTIONS + 1];
     __shared__ uint32_t s_geo[kGeoWords];
+    __shared__ uint32_t s_view[kViewWords * kLB];
     const int tid = threadIdx.x, lane = tid & 31;
     const int64_t env0 = (int64_t)blockIdx.x * kLB, env = env0 + tid;
     for (int d = tid + 1; d <= XQ_MAX_ACTIONS; d += kLB) s_magic[d] = team_mod_magic((uint32_t)d);
@@ -133,7 +134,9 @@ __global__ void __launch_bounds__(kLB) act_lane_kernel(xq_env_rec* __restrict__ 
     }
     // lanes without a board (tail of the last CTA, non-standard piece sets) act on the opening position and are never stored
     uint32_t sdesc[4], cw[4], dw[4], tot = 0;
-    lane_movegen(own_sq, own, opp, oT, player, s_geo, sdesc, cw, dw);
+    view_init(s_view + tid, kLB);
+    view_store(s_view + tid, kLB, own, opp, oT);
+    lane_movegen(own_sq, MemView{s_view + tid, kLB}, player, s_geo, sdesc, cw, dw);
 #pragma unroll
     for (int w = 0; w < 4; ++w) tot = dp4a_u(cw[w], 0x01010101u, tot);
     __syncthreads();                                               // the Q tile and the modulo table

@@ -272,9 +272,61 @@ XQ_HD uint32_t geo_word(int i) {
     return geo_entry(i >> 7, i & 127);
 #endif
 }
-// the same masks as *_mask above with the geometry from the table word g = geo[colour * 128 + sq]
-XQ_HD uint32_t horse_mask_g(const Pos& P, int sq, uint32_t g) {
-    const Win41 own = window(P.own, sq), occ = window(P.occ, sq);
+// ---- board views: where the generators read the three bitboards from -------------------------------------------------------------
+// RegView: the bitboards live in registers (three words each); a run-time word index costs arithmetic -- two mask builds and two to four
+// LOP3 per selected word (mux above), ~12 integer-ALU instructions per 41-bit window, ~10 per rank / file, ~8 per bit test.
+struct RegView {
+    Bits90 own, occ, occT;
+    XQ_HD Win41 win_own(int sq) const { return window(own, sq); }
+    XQ_HD Win41 win_occ(int sq) const { return window(occ, sq); }
+    XQ_HD uint32_t rank(int r) const { return occ.field(9 * r, 9); }
+    XQ_HD uint32_t file(int c) const { return occT.field(10 * c, 10); }
+    XQ_HD bool own_test(int s) const { return own.test(s); }
+};
+// MemView: a copy of the same bitboards in (shared) memory, one private slice per thread laid out [word][thread]: the bank of an access is
+// the thread's lane whatever the word index, so a RUN-TIME word index is conflict-free and costs one address computation -- the word
+// selection moves from the integer ALU (the pipe that bounds the rollout kernels) to the load / store unit.  Three arrays of 8 words,
+// own | occ (= own | opp) | occT, each stored padded as {0, w0, w1, w2, 0, 0, 0, 0}: a window or a field that hangs over either end of
+// the board (and every access of a captured piece, square 127) reads zeros.  The registers stay the master copy; view_store writes the
+// arrays after every change of the board.
+constexpr int kViewWords = 24;
+struct MemView {
+    const uint32_t* m;       // this thread's slice: word i of array a at m[(8 a + i) * stride]
+    int stride;
+    XQ_HD uint32_t w(int a, int i) const { return m[(8 * a + i) * stride]; }
+    XQ_HD Win41 win(int a, int sq) const {
+        const int q = sq + 12, wi = q >> 5;             // bit (sq - 20) + 32 of the padded array; wi = 0..4
+        const uint32_t x0 = w(a, wi), x1 = w(a, wi + 1), x2 = w(a, wi + 2);
+        return Win41{funnel_r(x0, x1, q & 31), funnel_r(x1, x2, q & 31)};
+    }
+    XQ_HD Win41 win_own(int sq) const { return win(0, sq); }
+    XQ_HD Win41 win_occ(int sq) const { return win(1, sq); }
+    XQ_HD uint32_t fld(int a, int pos, int nbits) const {
+        const int wi = pos >> 5;                         // 0..3
+        return funnel_r(w(a, 1 + wi), w(a, 2 + wi), pos & 31) & ((1u << nbits) - 1u);
+    }
+    XQ_HD uint32_t rank(int r) const { return fld(1, 9 * r, 9); }
+    XQ_HD uint32_t file(int c) const { return fld(2, 10 * c, 10); }
+    XQ_HD bool own_test(int s) const { return (w(0, 1 + ((s >> 5) & 3)) >> (s & 31)) & 1u; }      // an index off the board reads some bit: callers discard it
+};
+XQ_HD void view_init(uint32_t* m, int stride) {          // the padding words, once
+#pragma unroll
+    for (int a = 0; a < 3; ++a) {
+        m[(8 * a) * stride] = 0u;
+#pragma unroll
+        for (int i = 4; i < 8; ++i) m[(8 * a + i) * stride] = 0u;
+    }
+}
+XQ_HD void view_store(uint32_t* m, int stride, const Bits90& own, const Bits90& opp, const Bits90& occT) {
+    m[1 * stride] = own.w0; m[2 * stride] = own.w1; m[3 * stride] = own.w2;
+    m[9 * stride] = own.w0 | opp.w0; m[10 * stride] = own.w1 | opp.w1; m[11 * stride] = own.w2 | opp.w2;
+    m[17 * stride] = occT.w0; m[18 * stride] = occT.w1; m[19 * stride] = occT.w2;
+}
+
+// the masks of the leapers on a view, with the geometry from the table word g = geo[colour * 128 + sq]
+template <class V>
+XQ_HD uint32_t horse_mask_g(const V& v, int sq, uint32_t g) {
+    const Win41 own = v.win_own(sq), occ = v.win_occ(sq);
     uint32_t m = 0;
 #pragma unroll
     for (int k = 0; k < 8; ++k) {
@@ -284,8 +336,9 @@ XQ_HD uint32_t horse_mask_g(const Pos& P, int sq, uint32_t g) {
     }
     return ~m & g & 0xFFu;
 }
-XQ_HD uint32_t elephant_mask_g(const Pos& P, int sq, uint32_t g) {
-    const Win41 own = window(P.own, sq), occ = window(P.occ, sq);
+template <class V>
+XQ_HD uint32_t elephant_mask_g(const V& v, int sq, uint32_t g) {
+    const Win41 own = v.win_own(sq), occ = v.win_occ(sq);
     uint32_t m = 0;
 #pragma unroll
     for (int k = 0; k < 4; ++k) {
@@ -294,24 +347,49 @@ XQ_HD uint32_t elephant_mask_g(const Pos& P, int sq, uint32_t g) {
     }
     return ~m & (g >> 8) & 0xFu;
 }
-XQ_HD uint32_t advisor_mask_g(const Pos& P, int sq, uint32_t g) {
-    const Win41 own = window(P.own, sq);
+template <class V>
+XQ_HD uint32_t advisor_mask_g(const V& v, int sq, uint32_t g) {
+    const Win41 own = v.win_own(sq);
     uint32_t m = 0;
 #pragma unroll
     for (int k = 0; k < 4; ++k) m |= own.at(k == 0 ? 10 : (k == 1 ? 8 : (k == 2 ? -8 : -10))) << k;
     return ~m & (g >> 12) & 0xFu;
 }
-XQ_HD uint32_t general_mask_g(const Pos& P, int sq, uint32_t g) {
-    const Win41 own = window(P.own, sq);
+template <class V>
+XQ_HD uint32_t general_mask_g(const V& v, int sq, uint32_t g) {
+    const Win41 own = v.win_own(sq);
     uint32_t m = 0;
 #pragma unroll
     for (int k = 0; k < 4; ++k) m |= own.at(k == 0 ? 9 : (k == 1 ? -9 : (k == 2 ? 1 : -1))) << k;
     return ~m & (g >> 16) & 0xFu;
 }
-XQ_HD uint32_t soldier_mask_g(const Pos& P, int sq, int color, uint32_t g) {
-    const Win41 own = window(P.own, sq);
+template <class V>
+XQ_HD uint32_t soldier_mask_g(const V& v, int sq, int color, uint32_t g) {
+    const Win41 own = v.win_own(sq);
     const uint32_t m = (color == RED ? own.at(9) : own.at(-9)) | (own.at(-1) << 1) | (own.at(1) << 2);
     return ~m & (g >> 20) & 0x7u;
+}
+// slider_desc (above) on a view; `cannon`: the capture square is the second blocker
+template <class V>
+XQ_HD int slider_desc_v(const V& v, int sq, bool cannon, uint32_t* desc) {
+    const int r = row_of(sq), c = sq - 9 * r;
+    const uint32_t rank = v.rank(r), file = v.file(c);
+    int total = 0;
+    uint32_t d = 0;
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+        const bool horiz = k < 2;
+        const int p = horiz ? c : r;
+        const Ray ray = (k & 1) ? ray_down(horiz ? rank : file, p, horiz ? 9 : 10) : ray_up(horiz ? rank : file, p, horiz ? 9 : 10);
+        const int tgt = cannon ? ray.second : ray.first;
+        const int s = horiz ? 9 * r + tgt : 9 * tgt + c;                      // tgt == -1 reads some bit: discarded
+        const bool cap = (tgt >= 0) & !v.own_test(s);
+        const int capdist = cap ? ((k & 1) ? p - tgt : tgt - p) : 0;
+        d |= ((uint32_t)ray.empties | ((uint32_t)capdist << 4)) << (8 * k);
+        total += ray.empties + (cap ? 1 : 0);
+    }
+    *desc = d;
+    return total;
 }
 
 // index of the j-th (0-based) set bit of an 8-bit mask

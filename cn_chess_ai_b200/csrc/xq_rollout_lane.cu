@@ -20,6 +20,7 @@ __global__ void __launch_bounds__(kLaneMaxThreads) rollout_lane_kernel(xq_env_re
     __shared__ uint8_t s_slot[32 * kLaneMaxThreads];      // [slot][thread]
     __shared__ uint32_t s_magic[XQ_MAX_ACTIONS + 1];
     __shared__ uint32_t s_geo[kGeoWords];                 // geometry table of the leapers (xq_bitboard.cuh)
+    __shared__ uint32_t s_view[kViewWords * kLaneMaxThreads];      // [word][thread]: the bitboards for run-time word indices (xq_bitboard.cuh: MemView)
     const int tid = threadIdx.x, bs = blockDim.x;
     const int64_t env = (int64_t)blockIdx.x * bs + tid;
     for (int d = tid + 1; d <= XQ_MAX_ACTIONS; d += bs) s_magic[d] = team_mod_magic((uint32_t)d);
@@ -46,6 +47,8 @@ __global__ void __launch_bounds__(kLaneMaxThreads) rollout_lane_kernel(xq_env_re
         if (nonstd) nonstd[env] = active ? 0 : 1;      // a non-standard piece set is left to the generic kernel
         flags = m.x & 0xFF000000u;
         lane_load(st, [&](int s) { return (int)s_slot[s * bs + tid]; }, red, black, occT, (int)(m.x & 0xFFFFu), (int)((m.x >> 16) & 0xFFu), (int)m.y, (int)m.z, m.w);
+        view_init(s_view + tid, bs);
+        view_store(s_view + tid, bs, st.own, st.opp, st.occT);
     }
     __syncthreads();                                      // the modulo and geometry tables
     if (active) {
@@ -53,7 +56,7 @@ __global__ void __launch_bounds__(kLaneMaxThreads) rollout_lane_kernel(xq_env_re
         xq_trace_rec* t = trace ? trace + env : nullptr;
 #pragma unroll 1
         for (int p = 0; p < n_plies; ++p) {
-            lane_ply(st, a, rng_base, s_magic, s_geo, t);
+            lane_ply(st, a, rng_base, s_magic, s_geo, s_view + tid, bs, t);
             if (t) t += n;
         }
         uint32_t words[12];
@@ -89,7 +92,7 @@ __global__ void __launch_bounds__(kLaneMaxThreads) rollout_lane_kernel(xq_env_re
 // board-major reads), then the CTA streams the rows out as 16-byte stores, 256 contiguous bytes per board.  No board-in-shared-memory
 // walk, no per-square loop: the loops run over (position, direction) with the same trip structure in every lane.
 // Boards with a non-standard piece set are flagged and left to the generic kernel (legal_moves_kernel, xq_env.cu).
-constexpr int kLmThreads = 128;
+constexpr int kLmThreads = 64;      // (33 KB of list rows + 12 KB of view memory per 128 boards would exceed the 48 KB of static shared memory)
 constexpr int kLmRow = 65;                                   // words per thread row: 64 pairs of actions + 1 (odd stride: bank = (thread + word) % 32)
 __global__ void __launch_bounds__(kLmThreads) legal_moves_lane_kernel(const xq_env_rec* __restrict__ envs, int64_t n, uint8_t* __restrict__ counts,
                                                                      uint4* __restrict__ actions, uint8_t* __restrict__ nonstd) {
@@ -97,6 +100,7 @@ __global__ void __launch_bounds__(kLmThreads) legal_moves_lane_kernel(const xq_e
     __shared__ uint32_t s_list[kLmThreads * kLmRow];
     __shared__ uint8_t s_cnt[kLmThreads];                    // list size; 0xFF = not produced here (tail of the grid, non-standard piece set)
     __shared__ uint32_t s_geo[kGeoWords];
+    __shared__ uint32_t s_view[kViewWords * kLmThreads];
     const int tid = threadIdx.x;
     const int64_t env0 = (int64_t)blockIdx.x * kLmThreads, env = env0 + tid;
     for (int i = tid; i < kGeoWords; i += kLmThreads) s_geo[i] = geo_word(i);
@@ -118,7 +122,9 @@ __global__ void __launch_bounds__(kLmThreads) legal_moves_lane_kernel(const xq_e
             for (int pos = 0; pos < 16; ++pos)
                 own_sq[pos >> 2] |= (uint32_t)s_slot[((player ? 16 : 0) + lane_pos_slot(pos)) * kLmThreads + tid] << (8 * (pos & 3));
             uint32_t sdesc[4], cw[4], dw[4];
-            lane_movegen(own_sq, player ? black : red, player ? red : black, occT, player, s_geo, sdesc, cw, dw);
+            view_init(s_view + tid, kLmThreads);
+            view_store(s_view + tid, kLmThreads, player ? black : red, player ? red : black, occT);
+            lane_movegen(own_sq, MemView{s_view + tid, kLmThreads}, player, s_geo, sdesc, cw, dw);
             uint16_t* row = reinterpret_cast<uint16_t*>(s_list + tid * kLmRow);
             cnt = lane_emit_actions(own_sq, player, sdesc, cw, dw, [&](int idx, int a, bool live) { if (live) row[idx] = (uint16_t)a; });
             counts[env] = (uint8_t)cnt;

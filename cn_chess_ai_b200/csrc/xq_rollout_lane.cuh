@@ -91,19 +91,18 @@ XQ_HD uint32_t lane_actions_below(const uint32_t (&sq)[4], const uint32_t (&cw)[
 
 // Every piece of the side to move: move counts (cw, one byte per position), the sliders' descriptors (sdesc, xq_bitboard.cuh) and the
 // leapers' direction masks (dw, one byte per position; dw[0] = 0).  A captured piece (square 127) reads garbage bits, its count is discarded.
-XQ_HD void lane_movegen(const uint32_t (&own_sq)[4], const Bits90& own, const Bits90& opp, const Bits90& occT, int color, const uint32_t* geo,
+// P: a view of the bitboards of the position seen by the side to move (xq_bitboard.cuh: MemView in the kernels -- the thread's slice of
+// shared memory, written by view_store after every change of the board)
+template <class V>
+XQ_HD void lane_movegen(const uint32_t (&own_sq)[4], const V& P, int color, const uint32_t* geo,
                         uint32_t (&sdesc)[4], uint32_t (&cw)[4], uint32_t (&dw)[4]) {
     const uint32_t* gq = geo + color * 128;      // geometry table of the side to move (xq_bitboard.cuh: geo_entry), entries 90..127 = 0
-    Pos P;
-    P.own = own;
-    P.occ = Bits90{own.w0 | opp.w0, own.w1 | opp.w1, own.w2 | opp.w2};
-    P.occT = occT;
     {
         int c[4];
 #pragma unroll
         for (int i = 0; i < 4; ++i) {
             const int q = (int)((own_sq[0] >> (8 * i)) & 0xFFu);
-            const int n = i < 2 ? slider_desc<false>(P, q, &sdesc[i]) : slider_desc<true>(P, q, &sdesc[i]);      // :198-246
+            const int n = slider_desc_v(P, q, i >= 2, &sdesc[i]);      // Chariots, then Cannons :198-246
             c[i] = q == kDeadSq ? 0 : n;
         }
         cw[0] = (uint32_t)c[0] | ((uint32_t)c[1] << 8) | ((uint32_t)c[2] << 16) | ((uint32_t)c[3] << 24);
@@ -289,10 +288,12 @@ XQ_HD uint32_t lane_select_kth(const uint32_t (&own_sq)[4], int color, const uin
 
 // One ply of ChessAI::train's loop body without the network (src/chessai.cpp:96-119) on one board.
 // magic[d] = team_mod_magic(d) for d = 1..128; geo = the geometry table (kGeoWords words, geo_entry).  trace (may be null) -> the record of this ply.
-XQ_HD void lane_ply(LaneState& st, LaneStats& a, uint64_t rng_base, const uint32_t* magic, const uint32_t* geo, xq_trace_rec* trace) {
+// vm / vstride: this board's slice of the view memory (kViewWords words, xq_bitboard.cuh), holding the bitboards of st on entry and on return.
+XQ_HD void lane_ply(LaneState& st, LaneStats& a, uint64_t rng_base, const uint32_t* magic, const uint32_t* geo, uint32_t* vm, int vstride,
+                    xq_trace_rec* trace) {
     const int color = st.player;
     uint32_t sdesc[4], cw[4], dw[4];
-    lane_movegen(st.own_sq, st.own, st.opp, st.occT, color, geo, sdesc, cw, dw);
+    lane_movegen(st.own_sq, MemView{vm, vstride}, color, geo, sdesc, cw, dw);
     uint32_t tot = 0;
 #pragma unroll
     for (int w = 0; w < 4; ++w) tot = dp4a_u(cw[w], 0x01010101u, tot);
@@ -302,6 +303,7 @@ XQ_HD void lane_ply(LaneState& st, LaneStats& a, uint64_t rng_base, const uint32
         a.games++;
         if (trace) lane_trace_store(trace, (uint32_t)XQ_ACTION_NONE | ((uint32_t)(1 | (NOCOLOR << 1)) << 24), 0u);
         lane_reset_board(st);
+        view_store(vm, vstride, st.own, st.opp, st.occT);
         return;
     }
     // ---- the k-th action in reference order: the smallest square s with g(s + 1) > k ----
@@ -385,6 +387,7 @@ XQ_HD void lane_ply(LaneState& st, LaneStats& a, uint64_t rng_base, const uint32
     st.move_count = over ? 0 : mc; st.player = over ? RED : (mover ^ 1);
     st.red = over ? 0 : st.red; st.black = over ? 0 : st.black;
     st.mat_red = over ? 1480 : st.mat_red; st.mat_black = over ? 1480 : st.mat_black;
+    view_store(vm, vstride, st.own, st.opp, st.occT);
 }
 
 // ---- record <-> state (once per launch) --------------------------------------------------------------------------------------------

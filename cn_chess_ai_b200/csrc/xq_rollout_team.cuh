@@ -117,6 +117,9 @@ struct TeamShared {
     uint32_t magic[XQ_MAX_ACTIONS + 1];
     uint32_t geo[kGeoWords];       // geometry table of the leapers (xq_bitboard.cuh: geo_entry), [colour][128]
 };
+// teams of 4, kernels that run many plies per launch: every thread's bitboards [word][role * KB + board] for run-time word indices (MemView)
+template <int KB>
+struct TeamViewMem { uint32_t w[kViewWords * 4 * KB]; };
 // the two tables of a CTA: magic[d] = team_mod_magic(d), geo[colour * 128 + sq] = geo_entry(colour, sq); a barrier must follow
 template <class SH>
 XQ_HD void team_tables_init(SH& sh, int tid, int n_threads) {
@@ -131,6 +134,16 @@ struct TeamState {
     int move_count, player;
     uint32_t ctr;
 };
+// a thread's slice of the view memory (teams of 4): written after every change of st.own / st.opp / st.occT, read by its own phase A
+template <int KB>
+XQ_HD void team_view_store(const TeamRole& R, const TeamState& st, uint32_t* view, int lane) {
+    view_store(view + R.role * KB + lane, 4 * KB, st.own, st.opp, st.occT);
+}
+template <int KB>
+XQ_HD void team_view_put(const TeamRole& R, const TeamState& st, uint32_t* view, int lane) {      // padding words + the bitboards
+    view_init(view + R.role * KB + lane, 4 * KB);
+    team_view_store<KB>(R, st, view, lane);
+}
 struct TeamPly {                   // scratch of one ply, phase A -> B -> C
     uint32_t desc[4];
     uint32_t cntw;
@@ -208,8 +221,10 @@ XQ_HD int nth_set_bit8(uint32_t m, int j) {
     return (h4 ? 4 : 0) + (h2 ? 2 : 0) + ((j >= (int)(m & 1u)) ? 1 : 0);
 }
 // ---- phase A: every thread counts the moves of its S pieces of the side to move and publishes (squares, counts) -------------
+// view (teams of 4, optional): TeamViewMem<KB>::w holding the bitboards of st (team_view_store) -- the generators then take run-time word
+// indices from shared memory (MemView) instead of selecting among registers (RegView); same results
 template <int T, int KB>
-XQ_HD void team_phase_a(const TeamRole& R, const TeamState& st, TeamPly& pl, TeamShared<KB>& sh, int lane, int p) {
+XQ_HD void team_phase_a(const TeamRole& R, const TeamState& st, TeamPly& pl, TeamShared<KB>& sh, int lane, int p, const uint32_t* view = nullptr) {
     Pos P;
     P.own = st.own;
     P.occ = Bits90{st.own.w0 | st.opp.w0, st.own.w1 | st.opp.w1, st.own.w2 | st.opp.w2};
@@ -222,13 +237,18 @@ XQ_HD void team_phase_a(const TeamRole& R, const TeamState& st, TeamPly& pl, Tea
         const int q2 = (int)((st.sq_own >> 16) & 0xFFu), q3 = (int)(st.sq_own >> 24);
         const uint32_t* gq = sh.geo + color * 128;
         const uint32_t g1 = gq[q1], g2 = gq[q2], g3 = gq[q3];
-        int c0 = slider_desc_rt(P, q0, hi, &pl.desc[0]);
+        int c0;
         uint32_t m1, m2, m3;
-        if (!hi) { m1 = horse_mask_g(P, q1, g1); m2 = soldier_mask_g(P, q2, color, g2); m3 = soldier_mask_g(P, q3, color, g3); }
-        else {
-            m1 = advisor_mask_g(P, q1, g1); m2 = elephant_mask_g(P, q2, g2);
-            m3 = R.role == 2 ? general_mask_g(P, q3, g3) : soldier_mask_g(P, q3, color, g3);
-        }
+        auto gen = [&](const auto& V) {
+            c0 = slider_desc_v(V, q0, hi, &pl.desc[0]);
+            if (!hi) { m1 = horse_mask_g(V, q1, g1); m2 = soldier_mask_g(V, q2, color, g2); m3 = soldier_mask_g(V, q3, color, g3); }
+            else {
+                m1 = advisor_mask_g(V, q1, g1); m2 = elephant_mask_g(V, q2, g2);
+                m3 = R.role == 2 ? general_mask_g(V, q3, g3) : soldier_mask_g(V, q3, color, g3);
+            }
+        };
+        if (view) gen(MemView{view + R.role * KB + lane, 4 * KB});      // == (st.own, st.own | st.opp, st.occT): team_view_store
+        else gen(RegView{P.own, P.occ, P.occT});
         pl.desc[1] = m1; pl.desc[2] = m2; pl.desc[3] = m3;
         c0 = q0 == kDeadSq ? 0 : c0;
         const int c1 = popc32(m1), c2 = popc32(m2), c3 = popc32(m3);
@@ -324,7 +344,7 @@ XQ_HD void team_phase_b(const TeamRole& R, const TeamState& st, TeamPly& pl, Tea
 // ---- phase C: every thread applies the move to its replica; the thread owning the captured slot publishes value | code -------
 // ChessBoard::movePiece (src/chessboard.cpp:38-64), checkGameOver / getWinner (:286-320), reset (:95-102)
 template <int KB>
-XQ_HD void team_phase_c(const TeamRole& R, TeamState& st, const TeamPly& pl, TeamShared<KB>& sh, TeamBook& bk, int lane, int p) {
+XQ_HD void team_phase_c(const TeamRole& R, TeamState& st, const TeamPly& pl, TeamShared<KB>& sh, TeamBook& bk, int lane, int p, uint32_t* view = nullptr) {
     // straight-line for the common case; with no legal action (pl.total == 0, below) the stale move read here is discarded
     const uint32_t mv = sh.move[lane];
     const int from = (int)(mv & 0xFFu), to = (int)((mv >> 8) & 0xFFu);
@@ -371,6 +391,7 @@ XQ_HD void team_phase_c(const TeamRole& R, TeamState& st, const TeamPly& pl, Tea
         const uint32_t c = st.ctr; team_reset(R, st); st.ctr = c;
         if (R.role == 0) { bk.pend = 2; bk.pend_p = p; bk.pend_tr0 = (uint32_t)XQ_ACTION_NONE | ((uint32_t)(1 | (NOCOLOR << 1)) << 24); }
     }
+    if (view) team_view_store<KB>(R, st, view, lane);
 }
 
 // ---- record <-> slots (once per launch) ---------------------------------------------------------------------------------------

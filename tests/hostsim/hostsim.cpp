@@ -66,12 +66,16 @@ int team_rollout_host(xq_env_rec* recs, long n, uint64_t env_id0, uint64_t seed,
         const uint64_t base = seed + (env_id0 + (uint64_t)env) * 0x9E3779B97F4A7C15ull;
         const uint32_t ctr0 = st[0].ctr;
         for (int r = 0; r < T; ++r) team_rng_chunk<T, 1>(R[r], sh, 0, 0, base, ctr0);
+        // the rollout kernel's teams of 4 read their bitboards through the memory view; the one-ply kernels (below) keep them in registers
+        TeamViewMem<1> vmem;
+        uint32_t* const view = T == 4 ? vmem.w : nullptr;
+        if (view) for (int r = 0; r < T; ++r) team_view_put<1>(R[r], st[r], view, 0);
         for (int p = 0; p < n_plies; ++p) {
             if ((p & 15) == 0) for (int r = 0; r < T; ++r) team_rng_chunk<T, 1>(R[r], sh, 0, (p >> 4) + 1, base, ctr0);
-            for (int r = 0; r < T; ++r) team_phase_a<T, 1>(R[r], st[r], pl[r], sh, 0, p);
+            for (int r = 0; r < T; ++r) team_phase_a<T, 1>(R[r], st[r], pl[r], sh, 0, p, view);
             team_finalize<1>(bk, sh, 0, trace, n, env);
             for (int r = 0; r < T; ++r) team_phase_b<T, 1>(R[r], st[r], pl[r], sh, 0, p);
-            for (int r = 0; r < T; ++r) team_phase_c<1>(R[r], st[r], pl[r], sh, bk, 0, p);
+            for (int r = 0; r < T; ++r) team_phase_c<1>(R[r], st[r], pl[r], sh, bk, 0, p, view);
         }
         team_finalize<1>(bk, sh, 0, trace, n, env);
         // store
@@ -121,7 +125,10 @@ int lane_rollout_host(xq_env_rec* recs, long n, uint64_t env_id0, uint64_t seed,
         lane_load(st, [&](int s) { return (int)slot[s]; }, red, black, occT, recs[env].move_count, recs[env].player, recs[env].red_score,
                   recs[env].black_score, recs[env].ctr);
         const uint64_t base = seed + (env_id0 + (uint64_t)env) * 0x9E3779B97F4A7C15ull;
-        for (int p = 0; p < n_plies; ++p) lane_ply(st, a, base, magic, host_geo(), trace ? trace + ((long)p * n + env) : nullptr);
+        uint32_t vm[kViewWords];
+        view_init(vm, 1);
+        view_store(vm, 1, st.own, st.opp, st.occT);
+        for (int p = 0; p < n_plies; ++p) lane_ply(st, a, base, magic, host_geo(), vm, 1, trace ? trace + ((long)p * n + env) : nullptr);
         uint32_t words[12];
         lane_store_words(st, words);
         std::memcpy(recs[env].sq, words, 48);
@@ -201,7 +208,10 @@ int hs_lane_all_actions(const xq_env_rec* recs, long n, uint8_t* counts, uint16_
         uint32_t own_sq[4] = {0, 0, 0, 0};
         for (int pos = 0; pos < 16; ++pos) own_sq[pos >> 2] |= (uint32_t)slot[(player ? 16 : 0) + xq::lane_pos_slot(pos)] << (8 * (pos & 3));
         uint32_t sdesc[4], cw[4], dw[4];
-        xq::lane_movegen(own_sq, player ? black : red, player ? red : black, occT, player, host_geo(), sdesc, cw, dw);
+        uint32_t vm[xq::kViewWords];
+        xq::view_init(vm, 1);
+        xq::view_store(vm, 1, player ? black : red, player ? red : black, occT);
+        xq::lane_movegen(own_sq, xq::MemView{vm, 1}, player, host_geo(), sdesc, cw, dw);
         counts[i] = (uint8_t)xq::lane_emit_actions(own_sq, player, sdesc, cw, dw, [&](int idx, int a, bool live) { if (live) out[idx] = (uint16_t)a; });
     }
     return nonstd;
@@ -267,7 +277,10 @@ int hs_act_lane(const xq_env_rec* recs, long n, uint64_t env_id0, uint64_t seed,
         uint32_t own_sq[4] = {0, 0, 0, 0};
         for (int pos = 0; pos < 16; ++pos) own_sq[pos >> 2] |= (uint32_t)slot[(player ? 16 : 0) + xq::lane_pos_slot(pos)] << (8 * (pos & 3));
         uint32_t sdesc[4], cw[4], dw[4], tot = 0;
-        xq::lane_movegen(own_sq, player ? black : red, player ? red : black, occT, player, host_geo(), sdesc, cw, dw);
+        uint32_t vm[xq::kViewWords];
+        xq::view_init(vm, 1);
+        xq::view_store(vm, 1, player ? black : red, player ? red : black, occT);
+        xq::lane_movegen(own_sq, xq::MemView{vm, 1}, player, host_geo(), sdesc, cw, dw);
         for (int k = 0; k < 4; ++k) tot = xq::dp4a_u(cw[k], 0x01010101u, tot);
         if (tot == 0) continue;
         const uint64_t x = xq::rng(seed, env_id0 + (uint64_t)i, recs[i].ctr);

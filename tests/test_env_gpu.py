@@ -136,6 +136,28 @@ def test_rollout_from_injected_boards(xq, O, oracle_lib):
     assert same_recs(env.get_boards(), ref) and stats.tobytes() == st0[0].tobytes()
 
 
+def test_team_kernel_both_views(xq, O, oracle_lib, monkeypatch):
+    """rollout_team_kernel<4> in both forms -- bitboards selected among registers (the default up to 8,192 envs) and read through the
+    thread's slice of shared memory (above) -- forced in turn on mid-game, arbitrary and finished boards, and at 9,000 envs by default:
+    traces, boards and statistics == the oracle's"""
+    base = np.concatenate([harvest_positions(O, 300, 7, 23, seed=12), random_boards(O, 600, seed=5)])
+    for n, view in ((len(base) - 7, "0"), (len(base) - 7, "1"), (9000, None)):
+        recs = np.concatenate([base] * (n // len(base) + 1))[:n].copy()
+        recs["ctr"] = np.arange(n) % 700
+        if view is not None:
+            monkeypatch.setenv("XQ_TEAM_VIEW", view)
+        else:
+            monkeypatch.delenv("XQ_TEAM_VIEW", raising=False)
+        env = xq.BatchedEnv(n, seed=13, env_id0=40)
+        env.set_boards(recs)
+        stats, tr = env.rollout_random(70, trace=True)
+        ref = recs.copy()
+        tr0 = np.zeros((70, n), O.TRACE_DTYPE); st0 = np.zeros(1, O.STATS_DTYPE)
+        oracle_lib.xqo_rollout_random(ref.ctypes.data, n, 40, 13, 70, tr0.ctypes.data, st0.ctypes.data)
+        assert tr.tobytes() == tr0.tobytes() and same_recs(env.get_boards(), ref) and stats.tobytes() == st0[0].tobytes(), (n, view)
+    monkeypatch.delenv("XQ_TEAM_VIEW", raising=False)
+
+
 def test_board_per_thread_kernel_traces(xq, O, oracle_lib):
     """above 12,288 envs the fused rollout is rollout_lane_kernel (one thread per board, the board in registers): every ply of every
     env against the oracle -- from the opening over more than one game, and resumed from mid-game / arbitrary (non-standard piece
