@@ -382,7 +382,7 @@ def main():
                     "serial_note": "one xq_env_rollout_random_io call after the other on one handle (launch latency and host wake-up exposed)"},
             "gpu_launches": int(launches),
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": pk["hbm_gbs"], "unit": "GB/s", "frac": achieved / pk["hbm_gbs"],
-                         "traffic": traffic, "kernel": "rollout_team_kernel<4> (up to 12,288 envs; rollout_lane_kernel above: aux.config5)", "peak_source": pk["source"],
+                         "traffic": traffic, "kernel": "rollout_team_kernel<4> (up to 9,472 envs; rollout_lane_kernel above: aux.config5)", "peak_source": pk["source"],
                          "algorithmic_bytes_per_launch": ALGO_BYTES_PER_STEP * E * P,
                          "note": "integer/latency-bound by design: boards stay on chip for all plies of a launch (DESIGN.md)"},
             "clocks": clocks}

@@ -350,19 +350,19 @@ static int launch_legal_moves(xq_env_s* h) {
     return XQ_OK;
 }
 // threads per board of the fused rollout kernel: 1 = rollout_lane_kernel (xq_rollout_lane.cu: the whole board in one thread's registers,
-// no barrier, nothing replicated), the default above 12,288 envs; 4 = rollout_team_kernel<4> (xq_rollout_team.cu), the default below;
+// no barrier, nothing replicated), the default above 9,472 envs (148 SMs x 64); 4 = rollout_team_kernel<4> (xq_rollout_team.cu), the default below;
 // 8 = rollout_team_kernel<8> and 16 = rollout_slots_kernel (xq_rollout.cu) are kept for A/B runs: XQ_ROLLOUT_TEAM=1|4|8|16 forces one.
 // All four are bit-identical.
-// Measured on one B200 (steps/s, 200 / 200 / 100 / 32 plies per launch):   envs      4096     16,384    65,536    1M
-//   board per thread (1)                                                             1.94e9   7.71e9    1.14e10   1.30e10
-//   team of 4 (4)                                                                    3.69e9   7.18e9    8.80e9    8.60e9
+// Measured on one B200 (steps/s, 200 / 200 / 100 / 32 plies per launch):   envs      4096     8192     16,384    65,536    1M
+//   board per thread (1)                                                             2.98e9   5.94e9   1.17e10   1.61e10   1.83e10
+//   team of 4 (4)                                                                    3.90e9   6.45e9   8.6e9     1.04e10   1.01e10
 // Up to ~16k envs every warp sits alone on its scheduler and a launch lasts as long as ONE warp's plies: the team kernel's shorter
 // per-thread ply (~700 instructions against ~1800) wins there; beyond that the kernels are issue-bound and the one that executes
 // fewer instructions per env step (56 against 87 warp-instructions) wins.
 static int rollout_team(int64_t n) {
     static const int forced = [] { const char* e = getenv("XQ_ROLLOUT_TEAM"); return e ? atoi(e) : 0; }();
     if (forced == 1 || forced == 4 || forced == 8 || forced == 16) return forced;
-    return n <= 12288 ? 4 : 1;
+    return n <= 148 * 64 ? 4 : 1;      // up to two team CTAs (32 boards each) per SM; measured (env steps/s, team / lane): 4096 3.9e9 / 3.0e9, 8192 6.4e9 / 5.9e9, 10,240 6.6e9 / 7.4e9
 }
 // Fused rollout = team kernel (xq_rollout_team.cu; or the 16-thread slot kernel, xq_rollout.cu) for every board with a standard piece set, then the generic
 // thread-per-board kernel for the boards it flagged (only possible after xq_env_set_boards injected exotic positions).

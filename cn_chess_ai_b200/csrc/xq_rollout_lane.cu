@@ -12,8 +12,11 @@
 namespace xq {
 
 constexpr int kLaneMaxThreads = 128;
+#ifndef XQ_LANE_MINBLOCKS
+#define XQ_LANE_MINBLOCKS 1      // A/B builds: resident CTAs per SM the register allocation must allow
+#endif
 
-__global__ void __launch_bounds__(kLaneMaxThreads) rollout_lane_kernel(xq_env_rec* __restrict__ envs, int64_t n, uint64_t env_id0, uint64_t seed, int n_plies,
+__global__ void __launch_bounds__(kLaneMaxThreads, XQ_LANE_MINBLOCKS) rollout_lane_kernel(xq_env_rec* __restrict__ envs, int64_t n, uint64_t env_id0, uint64_t seed, int n_plies,
                                                                       xq_trace_rec* __restrict__ trace, xq_env_stats* __restrict__ stats,
                                                                       uint8_t* __restrict__ nonstd, const xq_env_rec* __restrict__ src,
                                                                       xq_env_rec* __restrict__ mirror) {
@@ -60,7 +63,7 @@ __global__ void __launch_bounds__(kLaneMaxThreads) rollout_lane_kernel(xq_env_re
             if (t) t += n;
         }
         uint32_t words[12];
-        lane_store_words(st, words);
+        lane_store_words_mem(st, s_view + tid, bs, words);      // kViewWords >= 16 words per thread
         uint4* rec = reinterpret_cast<uint4*>(envs + env);
 #pragma unroll
         for (int i = 0; i < 3; ++i) rec[i] = make_uint4(words[4 * i], words[4 * i + 1], words[4 * i + 2], words[4 * i + 3]);

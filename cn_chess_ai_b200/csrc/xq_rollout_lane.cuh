@@ -434,4 +434,23 @@ XQ_HD void lane_store_words(const LaneState& st, uint32_t (&words)[12]) {
     }
 }
 
+// the same through a scratch slice of memory laid out [word][thread] (the view memory, free after the last ply): one read-modify-write
+// per piece on a run-time word index instead of 12 predicated ORs per piece (1,500 -> ~250 instructions per launch)
+XQ_HD void lane_store_words_mem(const LaneState& st, uint32_t* m, int stride, uint32_t (&words)[12]) {
+#pragma unroll
+    for (int i = 0; i < 12; ++i) m[i * stride] = 0u;
+    const bool redp = st.player == RED;
+#pragma unroll
+    for (int pos = 0; pos < 16; ++pos) {
+        const uint32_t type = (uint32_t)slot_type(lane_pos_slot(pos));
+        const uint32_t qr = ((redp ? st.own_sq : st.opp_sq)[pos >> 2] >> (8 * (pos & 3))) & 0xFFu;
+        const uint32_t qb = ((redp ? st.opp_sq : st.own_sq)[pos >> 2] >> (8 * (pos & 3))) & 0xFFu;
+        // a captured piece (square 127) lands in word 15 of the slice, beyond the 12 words of the record
+        m[(qr >> 3) * stride] |= type << (4 * (qr & 7));
+        m[(qb >> 3) * stride] |= (type + 7u) << (4 * (qb & 7));
+    }
+#pragma unroll
+    for (int i = 0; i < 12; ++i) words[i] = m[i * stride];
+}
+
 }  // namespace xq

@@ -184,7 +184,7 @@ cudaError_t launch_rollout_team(int team, xq_env_rec* envs, int64_t n, uint64_t 
     const unsigned grid = (unsigned)((n + kTB - 1) / kTB);
     const char* ve = getenv("XQ_TEAM_VIEW");      // A/B and tests (read per call): 0 registers, 1 shared-memory view
     const int view_env = ve ? atoi(ve) : -1;
-    const bool mem = view_env >= 0 ? view_env != 0 : n > 8192;
+    const bool mem = view_env >= 0 ? view_env != 0 : n > 148 * kTB;      // more than one CTA per SM: issue-bound enough for the view to pay (4.84e9 against 4.66e9 at 6144 envs)
     if (team == 8) rollout_team_kernel<8, false><<<grid, kTB * 8, 0, stream>>>(envs, n, env_id0, seed, n_plies, trace, stats, nonstd, src, mirror);
     else if (mem) rollout_team_kernel<4, true><<<grid, kTB * 4, 0, stream>>>(envs, n, env_id0, seed, n_plies, trace, stats, nonstd, src, mirror);
     else rollout_team_kernel<4, false><<<grid, kTB * 4, 0, stream>>>(envs, n, env_id0, seed, n_plies, trace, stats, nonstd, src, mirror);

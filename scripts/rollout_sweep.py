@@ -7,7 +7,10 @@ from cn_chess_ai_b200._lib import check
 s = torch.cuda.current_stream()
 L = xq.lib()
 traced = "--traced" in sys.argv
-for n, plies in ((4096, 200), (16384, 200), (65536, 100), (1 << 20, 32)):
+sizes = ((4096, 200), (16384, 200), (65536, 100), (1 << 20, 32))
+if os.environ.get("XQ_SWEEP_SIZES"):      # e.g. "4096:200,8192:200"
+    sizes = tuple(tuple(int(x) for x in t.split(":")) for t in os.environ["XQ_SWEEP_SIZES"].split(","))
+for n, plies in sizes:
     env = xq.BatchedEnv(n, seed=7)
     env.set_stream(s.cuda_stream)
     run = (lambda: check(L.xq_env_rollout_random_traced_async(env.handle, plies, None))) if traced else (lambda: env.rollout_random_async(plies))

@@ -129,8 +129,10 @@ int lane_rollout_host(xq_env_rec* recs, long n, uint64_t env_id0, uint64_t seed,
         view_init(vm, 1);
         view_store(vm, 1, st.own, st.opp, st.occT);
         for (int p = 0; p < n_plies; ++p) lane_ply(st, a, base, magic, host_geo(), vm, 1, trace ? trace + ((long)p * n + env) : nullptr);
-        uint32_t words[12];
-        lane_store_words(st, words);
+        uint32_t words[12], words2[12];
+        lane_store_words(st, words2);
+        lane_store_words_mem(st, vm, 1, words);
+        if (std::memcmp(words, words2, 48) != 0) return -1;      // the two forms of the record builder must agree
         std::memcpy(recs[env].sq, words, 48);
         recs[env].move_count = (uint16_t)st.move_count; recs[env].player = (uint8_t)st.player;
         recs[env].red_score = st.red; recs[env].black_score = st.black; recs[env].ctr = st.ctr;

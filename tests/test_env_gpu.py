@@ -137,7 +137,7 @@ def test_rollout_from_injected_boards(xq, O, oracle_lib):
 
 
 def test_team_kernel_both_views(xq, O, oracle_lib, monkeypatch):
-    """rollout_team_kernel<4> in both forms -- bitboards selected among registers (the default up to 8,192 envs) and read through the
+    """rollout_team_kernel<4> in both forms -- bitboards selected among registers (the default up to 4,736 envs = one CTA per SM) and read through the
     thread's slice of shared memory (above) -- forced in turn on mid-game, arbitrary and finished boards, and at 9,000 envs by default:
     traces, boards and statistics == the oracle's"""
     base = np.concatenate([harvest_positions(O, 300, 7, 23, seed=12), random_boards(O, 600, seed=5)])
@@ -159,7 +159,7 @@ def test_team_kernel_both_views(xq, O, oracle_lib, monkeypatch):
 
 
 def test_board_per_thread_kernel_traces(xq, O, oracle_lib):
-    """above 12,288 envs the fused rollout is rollout_lane_kernel (one thread per board, the board in registers): every ply of every
+    """above 9,472 envs the fused rollout is rollout_lane_kernel (one thread per board, the board in registers): every ply of every
     env against the oracle -- from the opening over more than one game, and resumed from mid-game / arbitrary (non-standard piece
     sets go to the generic kernel) / finished boards; ragged env counts"""
     n, plies, seed, id0 = 16411, 230, 21, 5
