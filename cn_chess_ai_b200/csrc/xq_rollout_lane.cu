@@ -16,15 +16,18 @@ constexpr int kLaneMaxThreads = 128;
 #define XQ_LANE_MINBLOCKS 1      // A/B builds: resident CTAs per SM the register allocation must allow
 #endif
 
-__global__ void __launch_bounds__(kLaneMaxThreads, XQ_LANE_MINBLOCKS) rollout_lane_kernel(xq_env_rec* __restrict__ envs, int64_t n, uint64_t env_id0, uint64_t seed, int n_plies,
+// BS = threads (boards) per CTA, a compile-time constant: the [word][thread] strides of the shared-memory slices become immediates
+template <int BS>
+__global__ void __launch_bounds__(BS, XQ_LANE_MINBLOCKS) rollout_lane_kernel(xq_env_rec* __restrict__ envs, int64_t n, uint64_t env_id0, uint64_t seed, int n_plies,
                                                                       xq_trace_rec* __restrict__ trace, xq_env_stats* __restrict__ stats,
                                                                       uint8_t* __restrict__ nonstd, const xq_env_rec* __restrict__ src,
                                                                       xq_env_rec* __restrict__ mirror) {
-    __shared__ uint8_t s_slot[32 * kLaneMaxThreads];      // [slot][thread]
+    __shared__ uint8_t s_slot[32 * BS];                   // [slot][thread]
     __shared__ uint32_t s_magic[XQ_MAX_ACTIONS + 1];
     __shared__ uint32_t s_geo[kGeoWords];                 // geometry table of the leapers (xq_bitboard.cuh)
-    __shared__ uint32_t s_view[kViewWords * kLaneMaxThreads];      // [word][thread]: the bitboards for run-time word indices (xq_bitboard.cuh: MemView)
-    const int tid = threadIdx.x, bs = blockDim.x;
+    __shared__ uint32_t s_view[kViewWords * BS];          // [word][thread]: the bitboards for run-time word indices (xq_bitboard.cuh: MemView)
+    constexpr int bs = BS;
+    const int tid = threadIdx.x;
     const int64_t env = (int64_t)blockIdx.x * bs + tid;
     for (int d = tid + 1; d <= XQ_MAX_ACTIONS; d += bs) s_magic[d] = team_mod_magic((uint32_t)d);
     for (int i = tid; i < kGeoWords; i += bs) s_geo[i] = geo_word(i);
@@ -174,8 +177,8 @@ cudaError_t launch_pick_random(const xq_env_rec* envs, int64_t n, uint64_t env_i
 
 cudaError_t launch_rollout_lane(xq_env_rec* envs, int64_t n, uint64_t env_id0, uint64_t seed, int n_plies, xq_trace_rec* trace, xq_env_stats* stats,
                                 uint8_t* nonstd, cudaStream_t stream, const xq_env_rec* src, xq_env_rec* mirror) {
-    const int bs = n <= 148 * 4 * 32 ? 32 : kLaneMaxThreads;
-    rollout_lane_kernel<<<(unsigned)((n + bs - 1) / bs), bs, 0, stream>>>(envs, n, env_id0, seed, n_plies, trace, stats, nonstd, src, mirror);
+    if (n <= 148 * 4 * 32) rollout_lane_kernel<32><<<(unsigned)((n + 31) / 32), 32, 0, stream>>>(envs, n, env_id0, seed, n_plies, trace, stats, nonstd, src, mirror);
+    else rollout_lane_kernel<kLaneMaxThreads><<<(unsigned)((n + kLaneMaxThreads - 1) / kLaneMaxThreads), kLaneMaxThreads, 0, stream>>>(envs, n, env_id0, seed, n_plies, trace, stats, nonstd, src, mirror);
     ++g_launches;
     return cudaGetLastError();
 }
