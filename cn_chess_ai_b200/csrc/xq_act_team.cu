@@ -37,11 +37,8 @@ struct ActIo {            // [item][board]
     uint32_t upd[kAB];            // what the ply did to the board, for the carried layer-0 sums: from | to << 7 | code << 14 | cap << 18 | flags
 };
 
-#ifndef XQ_ACT_MINBLOCKS
-#define XQ_ACT_MINBLOCKS 1      // A/B builds: resident CTAs per SM the register allocation must allow
-#endif
 template <bool APPLY>
-__global__ void __launch_bounds__(kAB * 4, XQ_ACT_MINBLOCKS) act_team_kernel(xq_env_rec* __restrict__ envs, int64_t n, uint64_t env_id0, uint64_t seed,
+__global__ void __launch_bounds__(kAB * 4) act_team_kernel(xq_env_rec* __restrict__ envs, int64_t n, uint64_t env_id0, uint64_t seed,
                                                           const float* __restrict__ q90, uint32_t eps_thr, int train_done,
                                                           uint16_t* __restrict__ actions_out, ActTransition* __restrict__ ring, int64_t ring_cap,
                                                           int64_t ring_pos, xq_env_stats* __restrict__ stats, xq_game_event* __restrict__ events,
@@ -53,16 +50,13 @@ __global__ void __launch_bounds__(kAB * 4, XQ_ACT_MINBLOCKS) act_team_kernel(xq_
     const int tid = threadIdx.x, lane = tid & 31;
     const TeamRole R = team_role<4>(tid >> 5);
     const int64_t env0 = (int64_t)blockIdx.x * kAB, env = env0 + lane;
-    static_assert(kAB * 4 == 128, "team_tables_fetch / _commit");
-    TeamTabRegs tabs;
-    team_tables_fetch(tabs, tid);                                  // committed to shared memory after the loads below
+    team_tables_init(sh, tid, kAB * 4);
     if (tid < kAB) sh.move[tid] = 0;
     if (APPLY && carry.Z != nullptr && env0 + (tid >> 2) < n)      // the CTA's 32 sums (16 KB) towards L2 now: the tail reads them ~20 us later
         asm volatile("prefetch.global.L2 [%0];" ::"l"(carry.Z + env0 * 128 + tid * 32));
 
     // ---- Q tile: q90[env0 .. env0+32)[96] -> qt[to][board], by warps 2 and 3 while warps 0 and 1 unpack the boards ------------
     if (R.role >= 2) {
-#pragma unroll 4
         for (int b = (R.role - 2) * 16; b < (R.role - 1) * 16; ++b) {
             const bool in = env0 + b < n;
             const float* src = q90 + (env0 + b) * kQStride;
@@ -95,7 +89,6 @@ __global__ void __launch_bounds__(kAB * 4, XQ_ACT_MINBLOCKS) act_team_kernel(xq_
         }
         io.ok[side * kAB + lane] = ok ? 1 : 0;
     }
-    team_tables_commit(sh, tabs, tid);
     __syncthreads();
 
     // lanes without a board (tail of the last CTA, non-standard piece sets) act on the opening position and are never stored
@@ -283,29 +276,18 @@ __global__ void __launch_bounds__(kAB * 4, XQ_ACT_MINBLOCKS) act_team_kernel(xq_
             const bool carried_sum = (u[i] & (kUpdValid | kUpdRestart | kUpdFresh)) == kUpdValid;
             z[i] = carried_sum ? reinterpret_cast<const uint4*>(carry.Z + (env0 + w + 4 * i) * 128)[lane] : zo;
         }
-        // The three table rows of an env are loaded UNCONDITIONALLY (an env that did not move, restarted or has no board reads the all-zero
-        // row 1260 three times) and one env AHEAD of their use: the loads of env i + 1 are in flight while env i's tanh / stores run.  With the
-        // loads behind the `valid / restart` branches every env paid its own round trip to L2 (20 % of the kernel's stall samples).
-        auto rows = [&](uint32_t ui, uint4& r0, uint4& r1, uint4& r2) {
-            const bool mv = (ui & (kUpdValid | kUpdRestart)) == kUpdValid;
-            const int from = (int)(ui & 127u), to = (int)((ui >> 7) & 127u), code = (int)((ui >> 14) & 15u), cap = (int)((ui >> 18) & 15u);
-            r0 = W[(size_t)(mv ? from * 14 + code - 1 : XQ_STATE_SIZE) * 32];
-            r1 = W[(size_t)(mv ? to * 14 + code - 1 : XQ_STATE_SIZE) * 32];
-            r2 = W[(size_t)((mv && cap) ? to * 14 + cap - 1 : XQ_STATE_SIZE) * 32];
-        };
-        uint4 r0, r1, r2;
-        rows(u[0], r0, r1, r2);
 #pragma unroll
         for (int i = 0; i < kAB / 4; ++i) {
-            uint4 n0 = r0, n1 = r1, n2 = r2;
-            if (i + 1 < kAB / 4) rows(u[i + 1], n0, n1, n2);
-            z[i] = make_uint4(z[i].x - r0.x + r1.x - r2.x, z[i].y - r0.y + r1.y - r2.y, z[i].z - r0.z + r1.z - r2.z, z[i].w - r0.w + r1.w - r2.w);
-            if (u[i] & kUpdValid) {                                 // warp-uniform
-                const int64_t e = env0 + w + 4 * i;
-                reinterpret_cast<uint4*>(carry.Z + e * 128)[lane] = z[i];
-                act_emit_h(z[i], is, carry.Hhi, carry.Hlo, e, lane);
+            if (!(u[i] & kUpdValid)) continue;                      // warp-uniform
+            const int64_t e = env0 + w + 4 * i;
+            if (!(u[i] & kUpdRestart)) {
+                const int from = (int)(u[i] & 127u), to = (int)((u[i] >> 7) & 127u), code = (int)((u[i] >> 14) & 15u), cap = (int)((u[i] >> 18) & 15u);
+                const uint4 r0 = W[(size_t)(from * 14 + code - 1) * 32], r1 = W[(size_t)(to * 14 + code - 1) * 32];
+                const uint4 r2 = W[(size_t)(cap ? to * 14 + cap - 1 : XQ_STATE_SIZE) * 32];      // row 1260 = zeros
+                z[i] = make_uint4(z[i].x - r0.x + r1.x - r2.x, z[i].y - r0.y + r1.y - r2.y, z[i].z - r0.z + r1.z - r2.z, z[i].w - r0.w + r1.w - r2.w);
             }
-            r0 = n0; r1 = n1; r2 = n2;
+            reinterpret_cast<uint4*>(carry.Z + e * 128)[lane] = z[i];
+            act_emit_h(z[i], is, carry.Hhi, carry.Hlo, e, lane);
         }
     }
 }
@@ -328,9 +310,7 @@ __global__ void __launch_bounds__(kAB * 4) legal_moves_team_kernel(const xq_env_
     const int tid = threadIdx.x, lane = tid & 31;
     const TeamRole R = team_role<4>(tid >> 5);
     const int64_t env0 = (int64_t)blockIdx.x * kAB, env = env0 + lane;
-    static_assert(kAB * 4 == 128, "team_tables_fetch / _commit");
-    TeamTabRegs tabs;
-    team_tables_fetch(tabs, tid);                                  // committed to shared memory after the loads below
+    team_tables_init(sh, tid, kAB * 4);
     if (R.role < 2) {
         const int side = R.role;
         bool ok = env < n;
@@ -348,7 +328,6 @@ __global__ void __launch_bounds__(kAB * 4) legal_moves_team_kernel(const xq_env_
         }
         s_ok[side * kAB + lane] = ok ? 1 : 0;
     }
-    team_tables_commit(sh, tabs, tid);
     __syncthreads();
     // lanes without a board (tail of the last CTA, non-standard piece sets: left to the generic kernel) work on the opening position, unused
     const bool active = (s_ok[lane] & s_ok[kAB + lane]) != 0;

@@ -144,19 +144,6 @@ XQ_HD void team_view_put(const TeamRole& R, const TeamState& st, uint32_t* view,
     view_init(view + R.role * KB + lane, 4 * KB);
     team_view_store<KB>(R, st, view, lane);
 }
-// The same for a CTA of 128 threads in two halves (one-ply kernels, where the table's trip to L2 would sit on the critical path): fetch
-// the geometry words into registers FIRST, do the kernel's own loads and conversion work, commit to shared memory before the barrier.
-struct TeamTabRegs { uint32_t g[kGeoWords / 128]; };
-XQ_HD void team_tables_fetch(TeamTabRegs& t, int tid) {
-#pragma unroll
-    for (int i = 0; i < kGeoWords / 128; ++i) t.g[i] = geo_word(tid + 128 * i);
-}
-template <class SH>
-XQ_HD void team_tables_commit(SH& sh, const TeamTabRegs& t, int tid) {
-    for (int d = tid + 1; d <= XQ_MAX_ACTIONS; d += 128) sh.magic[d] = (0xFFFFFFFFu / (uint32_t)d) + 1u;
-#pragma unroll
-    for (int i = 0; i < kGeoWords / 128; ++i) sh.geo[tid + 128 * i] = t.g[i];
-}
 struct TeamPly {                   // scratch of one ply, phase A -> B -> C
     uint32_t desc[4];
     uint32_t cntw;
