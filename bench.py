@@ -392,8 +392,12 @@ def main():
         issued = value / world * inst_per_step
         line["roofline"]["secondary"] = {"bound": "warp-instruction issue", "achieved": issued, "peak": issue_peak, "unit": "warp-inst/s",
                                          "frac": issued / issue_peak, "warp_inst_per_env_step": inst_per_step,
+                                         "alu_pipe_pct_of_peak": tj.get("rollout_kernel_alu_pipe_pct"),
                                          "source": "instructions per step from the ncu capture in profiles/ (smsp__inst_executed.sum / steps); "
-                                                   "peak = 148 SMs x 4 schedulers x the SM clock sampled during the run"}
+                                                   "peak = 148 SMs x 4 schedulers x the SM clock sampled during the run",
+                                         "note": "4096 envs = 512 warps on 592 schedulers, 128 of 148 SMs: every warp sits alone on its scheduler and a launch lasts as long as "
+                                                 "one warp's 200 plies (~2,000 cycles per ply for ~640 instructions: fixed-latency dependencies 0.95, barrier 0.47 stalled "
+                                                 "warps per issued instruction) -- the kernel is latency-bound, neither roofline binds (DESIGN.md section 4)"}
 
     # ---- timing hygiene: >= 100 further launches of the same step, median / min of the per-launch times, max over ranks ----
     reps = max(100, args.steps)
@@ -472,7 +476,7 @@ def main():
         c5 = aux["config5_1M_envs_steps_per_s"]
         c5_gbs = ALGO_BYTES_PER_STEP * c5 / world / 1e9
         aux["config5"] = {"envs_total": 1 << 20, "envs_per_gpu": per_gpu, "plies_per_launch": 32, "launches": 5, "steps_per_s": c5,
-                          "kernel": "rollout_lane_kernel (one thread per board, the board in registers)",
+                          "kernel": "rollout_lane_kernel (one thread per board: squares in registers, bitboards also in a per-thread shared-memory view, piece tables in shared memory)",
                           "roofline": {"bound": "hbm", "achieved": c5_gbs, "peak": pk["hbm_gbs"], "unit": "GB/s", "frac": c5_gbs / pk["hbm_gbs"],
                                        "traffic": tj.get("lane_kernel_dram_bytes_per_launch") if world == 1 and os.path.exists(tp) else None,
                                        "algorithmic_bytes_per_launch": ALGO_BYTES_PER_STEP * per_gpu * 32, "peak_source": pk["source"]}}
@@ -481,8 +485,9 @@ def main():
             issued = c5 / world * tj["lane_kernel_warp_inst_per_step"]
             aux["config5"]["roofline"]["secondary"] = {"bound": "warp-instruction issue", "achieved": issued, "peak": ipeak, "unit": "warp-inst/s", "frac": issued / ipeak,
                                                        "warp_inst_per_env_step": tj["lane_kernel_warp_inst_per_step"], "alu_pipe_pct_of_peak": tj.get("lane_kernel_alu_pipe_pct"),
-                                                       "note": "the integer ALU pipe issues one warp-instruction every two cycles per scheduler: at ~70 % ALU-pipe instructions the ceiling "
-                                                               "of this kernel is ~0.7 of the issue peak (ncu: ALU pipe 90 % busy, profiles/r2_ncu_lane_rollout_list_step_summary.csv)"}
+                                                       "issue_active_pct_ncu": tj.get("lane_kernel_issue_active_pct"),
+                                                       "note": "the integer ALU pipe issues one warp-instruction every two cycles per scheduler; with ~53 % of the instructions on it "
+                                                               "the ALU pipe (86 % busy) and the issue slots (80 % active) bind together (ncu: profiles/r2b_ncu_rollout_lane_team_summary.csv)"}
         big.close()
         line["aux"] = aux
 
