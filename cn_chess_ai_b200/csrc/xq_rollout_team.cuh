@@ -395,12 +395,50 @@ XQ_HD void team_phase_c(const TeamRole& R, TeamState& st, const TeamPly& pl, Tea
 }
 
 // ---- record <-> slots (once per launch) ---------------------------------------------------------------------------------------
+// The three bitboards of a record come out of the 12 nibble words WITHOUT a per-piece loop (the loop below runs at the densest board of a
+// warp: it used to spend ~35 of its ~70 instructions per piece on single-bit masks):
+//   row-major: a flag per nibble (occupied / Black), 8 flags of a word compressed into a byte (three shift-or-mask steps), four bytes = a word;
+//   column-major: the 9 bits of a rank spread to stride 10 (three multiplications that place bit c at 10 c, cross terms masked away) and
+//   shifted up by the row.
+XQ_HD uint32_t compress_nibble_flags(uint32_t x) {      // flags in bits 0, 4, ..., 28 -> bits 0..7
+    x = (x | (x >> 3)) & 0x03030303u;
+    x = (x | (x >> 6)) & 0x000F000Fu;
+    return (x | (x >> 12)) & 0xFFu;
+}
+// which (0: every piece, 1: Red, 2: Black) of the 12 words as a row-major bitboard
+XQ_HD Bits90 record_bitboard(const uint32_t (&w)[12], int which) {
+    uint32_t b[3] = {0, 0, 0};
+#pragma unroll
+    for (int i = 0; i < 12; ++i) {
+        const uint32_t nz = (w[i] | (w[i] >> 1) | (w[i] >> 2) | (w[i] >> 3)) & 0x11111111u, hi = (w[i] >> 3) & 0x11111111u;
+        uint32_t f = which == 0 ? nz : (which == 1 ? (nz & ~hi) : hi);
+        if (i == 11) f &= 0x00000011u;                 // squares 88, 89; the rest of the last word is padding
+        b[i >> 2] |= compress_nibble_flags(f) << (8 * (i & 3));
+    }
+    return Bits90{b[0], b[1], b[2]};
+}
+// row-major (bit 9 r + c) -> column-major (bit 10 c + r)
+XQ_HD Bits90 transpose_bitboard(const Bits90& o) {
+    uint32_t t0 = 0, t1 = 0, t2 = 0;
+#pragma unroll
+    for (int r = 0; r < 10; ++r) {
+        const int pos = 9 * r;
+        const uint32_t lo = pos < 32 ? o.w0 : (pos < 64 ? o.w1 : o.w2), hi = pos < 32 ? o.w1 : o.w2;
+        const uint32_t x = ((pos & 31) + 9 <= 32 ? lo >> (pos & 31) : funnel_r(lo, hi, pos & 31)) & 0x1FFu;
+        const uint32_t s0 = ((x & 0xFu) * 0x08040201u) & 0x40100401u;             // columns 0..3 -> bits 0, 10, 20, 30
+        const uint32_t s1 = (((x >> 4) & 7u) * 0x04020100u) & 0x10040100u;        // columns 4..6 -> bits 40, 50, 60
+        const uint32_t s2 = ((x >> 7) * 0x00008040u) & 0x00010040u;               // columns 7, 8 -> bits 70, 80
+        if (r == 0) { t0 |= s0; t1 |= s1; t2 |= s2; }
+        else { t0 |= s0 << r; t1 |= funnel_r(s0, s1, 32 - r); t2 |= funnel_r(s1, s2, 32 - r); }
+    }
+    return Bits90{t0, t1, t2};
+}
+
 // put(slot 0..31, square); returns false for a board whose piece counts exceed a standard set (left to the generic kernel)
 template <class PUT>
 XQ_HD bool team_unpack_record(const uint32_t (&w)[12], Bits90& red, Bits90& black, Bits90& occT, PUT&& put) {
     bool ok = true;
     uint64_t cnt = 0;   // 4-bit counter per piece code
-    red = black = occT = Bits90{0, 0, 0};
 #pragma unroll
     for (int wi = 0; wi < 12; ++wi) {
         // one iteration per OCCUPIED square of the word (a board holds <= 32 pieces on 90 squares), lowest square first
@@ -417,13 +455,13 @@ XQ_HD bool team_unpack_record(const uint32_t (&w)[12], Bits90& red, Bits90& blac
             else {
                 put((code >= 8 ? 16 : 0) + slot_base(t) + ord, s);
                 cnt += 1ull << (4 * code);
-                const Bits90 b = Bits90::bit(s);
-                if (code >= 8) black.or_with(b); else red.or_with(b);
-                const int r = row_of(s);
-                occT.or_with(Bits90::bit(cm_index(r, s - 9 * r)));
             }
         }
     }
+    // (a board that is not ok is discarded by the caller: its bitboards may hold pieces the loop did not place)
+    red = record_bitboard(w, 1);
+    black = record_bitboard(w, 2);
+    occT = transpose_bitboard(Bits90{red.w0 | black.w0, red.w1 | black.w1, red.w2 | black.w2});
     return ok;
 }
 
@@ -433,7 +471,6 @@ template <class PUT>
 XQ_HD bool team_unpack_side(const uint32_t (&w)[12], int side, Bits90& bb, Bits90& occT, PUT&& put) {
     bool ok = true;
     uint32_t cnt = 0;   // 4-bit counter per piece type
-    bb = occT = Bits90{0, 0, 0};
 #pragma unroll
     for (int wi = 0; wi < 12; ++wi) {
         const uint32_t hi = (w[wi] >> 3) & 0x11111111u;                                      // nibble >= 8: Black (or the invalid code 15)
@@ -451,12 +488,11 @@ XQ_HD bool team_unpack_side(const uint32_t (&w)[12], int side, Bits90& bb, Bits9
             else {
                 put(slot_base(t) + ord, s);
                 cnt += 1u << (4 * t);
-                bb.or_with(Bits90::bit(s));
-                const int r = row_of(s);
-                occT.or_with(Bits90::bit(cm_index(r, s - 9 * r)));
             }
         }
     }
+    bb = record_bitboard(w, side ? 2 : 1);
+    occT = transpose_bitboard(bb);
     return ok;
 }
 
