@@ -1978,11 +1978,15 @@ int dqn_td_update_pipelined(xq_dqn_s* h, const void* ring, int64_t size, uint64_
         XQ_CUDA(launch_pdl(l0_pair_kernel, dim3(blocks(n, kL0Warps)), dim3(kL0Warps * 32), 0, main, 1, ref, n, f->W0T, f->b0, f->tW0T, f->tb0, f->Hf,
                            f->H2bf, f->cb, ld, f->info_slots, kInfoSlots * 4, 1));
         XQ_CUDA(cudaStreamWaitEvent(main, f->ev_aux[slot], 0));  // the row-max partials of this update
-        if (early == 2) { XQ_CUDA(cudaEventRecord(f->ev_td[slot], main)); if (i + 1 < n_updates) if (int rc = aux_gemm(i + 1, gate_of(i + 1))) return rc; }
+        // XQ_TD_FIRST_LATE=k (probe): the first k updates of a call release the next GEMM AFTER their TD-error kernel (mode 1) -- the contraction of
+        // update 0 then certainly gets its SMs first; does the pipeline stay in that order for the rest of the call?
+        static const int first_late = [] { const char* e = getenv("XQ_TD_FIRST_LATE"); return e ? atoi(e) : 0; }();
+        const bool late = early == 2 && i < first_late;
+        if (early == 2 && !late) { XQ_CUDA(cudaEventRecord(f->ev_td[slot], main)); if (i + 1 < n_updates) if (int rc = aux_gemm(i + 1, gate_of(i + 1))) return rc; }
         if (early == 4) { XQ_CUDA(cudaEventRecord(f->ev_td[slot], main)); if (i + 1 < n_updates) if (int rc = aux_gemm_part(i + 1, f->ev_td[slot], false)) return rc; }
         XQ_CUDA(launch_pdl(td_delta_kernel, dim3(blocks(n * 32, 256)), dim3(256), 0, main, 1, f->cb, n, f->Hf, f->W1, f->b1, slot ? f->zpart_b : f->zpart,
                            ld, kParts, (float)h->gamma, h->mode, f->d0hi, f->d0lo, f->ghi, f->glo, ld, f->info_slots));
-        if (early == 1) { XQ_CUDA(cudaEventRecord(f->ev_td[slot], main)); if (i + 1 < n_updates) if (int rc = aux_gemm(i + 1, gate_of(i + 1))) return rc; }
+        if (early == 1 || late) { XQ_CUDA(cudaEventRecord(f->ev_td[slot], main)); if (i + 1 < n_updates) if (int rc = aux_gemm(i + 1, gate_of(i + 1))) return rc; }
         if (early == 4) { XQ_CUDA(cudaEventRecord(f->ev_tdb[slot], main)); if (i + 1 < n_updates) if (int rc = aux_gemm_part(i + 1, f->ev_tdb[slot], true)) return rc; }
         if (early == 5 && i + 1 < n_updates) g_launched_event = f->ev_tdb[slot];
         XQ_CUDA(launch_pdl(dw_gemm_kernel, dim3(kDwMTiles, kDwSplits), dim3(kDwThreads), kDwSmem, main, kDwSplits, f->tmD0hi, f->tmD0lo, f->tmGhi,

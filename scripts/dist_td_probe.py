@@ -37,7 +37,7 @@ with torch.cuda.stream(s):
     if world > 1:
         dist.all_reduce(per, op=dist.ReduceOp.MAX)
     if rank == 0:
-        knobs = {k: os.environ[k] for k in ("XQ_TD_GEMM_SPLITS", "XQ_TD_EARLY_GEMM", "XQ_PROBE_MAIN_PRIO", "XQ_DIST_FUSED_MODE", "XQ_TD_GRAPH", "XQ_TD_MAIN_PRIO", "XQ_TD_GEMM_A_TILES") if k in os.environ}
+        knobs = {k: os.environ[k] for k in ("XQ_TD_GEMM_SPLITS", "XQ_TD_EARLY_GEMM", "XQ_PROBE_MAIN_PRIO", "XQ_DIST_FUSED_MODE", "XQ_TD_GRAPH", "XQ_TD_MAIN_PRIO", "XQ_TD_GEMM_A_TILES", "XQ_TD_FIRST_LATE") if k in os.environ}
         print(f"world {world} {knobs}: us/update per call {[round(float(x), 1) for x in per[:K]]} mean {float(per[:K].mean()):.2f}; cpu enqueue us/update (max over ranks) {[round(float(x), 1) for x in per[K:]]}", flush=True)
 if world > 1:
     dist.barrier()
