@@ -227,7 +227,7 @@ def test_api_mode_on_the_device_equals_fused_rollout(xq, O, oracle_lib):
 
 
 def test_list_kernels_team_and_board_per_thread(xq, O, oracle_lib, monkeypatch):
-    """xq_env_legal_moves through BOTH list kernels -- the team of 4 threads per board (legal_moves_team_kernel, the default up to 12,288 envs)
+    """xq_env_legal_moves through BOTH list kernels -- the team of 4 threads per board (legal_moves_team_kernel, the default up to 18,944 envs)
     and one thread per board (legal_moves_lane_kernel) -- forced in turn on the same boards: ordered lists == the oracle's, bit for bit, for
     reachable positions, arbitrary standard boards, arbitrary piece sets (generic kernel) and a grid whose last CTA is partly empty"""
     base = np.concatenate([harvest_positions(O, 700, 9, 33, seed=4), random_boards(O, 1500, seed=17)])
