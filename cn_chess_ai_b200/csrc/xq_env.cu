@@ -432,6 +432,7 @@ int xq_env_destroy(xq_env_t h) {
     if (!h) return XQ_OK;
     cudaSetDevice(h->device);
     if (h->sp_scratch && h->sp_scratch_free) { cudaStreamSynchronize(h->stream); h->sp_scratch_free(h->sp_scratch); }
+    if (h->io_pending && h->ev_io) cudaEventSynchronize(h->ev_io);      // a submission never waited for: its copies may still be in flight
     if (h->ev_io) cudaEventDestroy(h->ev_io);
     if (h->ev_in) cudaEventDestroy(h->ev_in);
     if (h->ev_run) cudaEventDestroy(h->ev_run);
