@@ -49,7 +49,7 @@ __global__ void __launch_bounds__(BS, XQ_LANE_MINBLOCKS) rollout_lane_kernel(xq_
         }
         for (int i = 0; i < 32; ++i) s_slot[i * bs + tid] = kDeadSq;
         Bits90 red, black, occT;
-        active = team_unpack_record(w, red, black, occT, [&](int s, int q) { s_slot[s * bs + tid] = (uint8_t)q; });
+        active = team_unpack_record_m(w, s_view + tid, bs, red, black, occT, [&](int s, int q) { s_slot[s * bs + tid] = (uint8_t)q; });      // (the view memory is initialised below)
         if (nonstd) nonstd[env] = active ? 0 : 1;      // a non-standard piece set is left to the generic kernel
         flags = m.x & 0xFF000000u;
         lane_load(st, [&](int s) { return (int)s_slot[s * bs + tid]; }, red, black, occT, (int)(m.x & 0xFFFFu), (int)((m.x >> 16) & 0xFFu), (int)m.y, (int)m.z, m.w);
@@ -120,7 +120,7 @@ __global__ void __launch_bounds__(kLmThreads) legal_moves_lane_kernel(const xq_e
         const int player = (int)((rec[3].x >> 16) & 0xFFu);
         for (int i = 0; i < 32; ++i) s_slot[i * kLmThreads + tid] = kDeadSq;
         Bits90 red, black, occT;
-        const bool ok = team_unpack_record(w, red, black, occT, [&](int s, int q) { s_slot[s * kLmThreads + tid] = (uint8_t)q; });
+        const bool ok = team_unpack_record_m(w, s_view + tid, kLmThreads, red, black, occT, [&](int s, int q) { s_slot[s * kLmThreads + tid] = (uint8_t)q; });
         if (nonstd) nonstd[env] = ok ? 0 : 1;
         if (ok) {
             uint32_t own_sq[4] = {0, 0, 0, 0};

@@ -465,6 +465,38 @@ XQ_HD bool team_unpack_record(const uint32_t (&w)[12], Bits90& red, Bits90& blac
     return ok;
 }
 
+// The same with ONE loop over the pieces of the board, lowest square first, instead of one loop per record word: a warp then runs as many
+// iterations as its densest board has pieces (<= 32 for a standard set) -- the per-word loops add up the densest word of each of the 12
+// word positions over the warp's 32 boards (~50).  The piece code of a square needs the record at a run-time word index: m / stride is a
+// scratch slice of >= 12 words laid out [word][thread] (the view memory of the board-per-thread kernels, free at that point).
+template <class PUT>
+XQ_HD bool team_unpack_record_m(const uint32_t (&w)[12], uint32_t* m, int stride, Bits90& red, Bits90& black, Bits90& occT, PUT&& put) {
+#pragma unroll
+    for (int i = 0; i < 12; ++i) m[i * stride] = w[i];
+    red = record_bitboard(w, 1);
+    black = record_bitboard(w, 2);
+    uint32_t o0 = red.w0 | black.w0, o1 = red.w1 | black.w1, o2 = red.w2 | black.w2;
+    occT = transpose_bitboard(Bits90{o0, o1, o2});
+    bool ok = true;
+    uint64_t cnt = 0;   // 4-bit counter per piece code
+    while ((o0 | o1 | o2) != 0u) {
+        const bool z0 = o0 == 0u, z1 = o1 == 0u;
+        const uint32_t word = z0 ? (z1 ? o2 : o1) : o0;
+        const int s = (z0 ? (z1 ? 64 : 32) : 0) + ffs32(word) - 1;
+        const uint32_t rest = word & (word - 1u);
+        o0 = z0 ? o0 : rest; o1 = (z0 && !z1) ? rest : o1; o2 = (z0 && z1) ? rest : o2;
+        const int code = (int)((m[(s >> 3) * stride] >> (4 * (s & 7))) & 15u);
+        const int t = type_of(code);
+        const int ord = (int)((cnt >> (4 * code)) & 15);
+        if (code == 15 || ord >= slot_cap(t)) { ok = false; }
+        else {
+            put((code >= 8 ? 16 : 0) + slot_base(t) + ord, s);
+            cnt += 1ull << (4 * code);
+        }
+    }
+    return ok;
+}
+
 // one colour only (side 0 Red, 1 Black): its 16 slots put(slot 0..15, square), its bitboard and its part of the column-major
 // occupancy -- the two colours of a board can be unpacked by two warps at once (act_team_kernel)
 template <class PUT>

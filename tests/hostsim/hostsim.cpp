@@ -119,7 +119,8 @@ int lane_rollout_host(xq_env_rec* recs, long n, uint64_t env_id0, uint64_t seed,
         uint32_t w[12];
         std::memcpy(w, recs[env].sq, 48);
         Bits90 red, black, occT;
-        if (!team_unpack_record(w, red, black, occT, [&](int s, int q) { slot[s] = (uint8_t)q; })) { ++nonstd; continue; }
+        uint32_t scratch[12];
+        if (!team_unpack_record_m(w, scratch, 1, red, black, occT, [&](int s, int q) { slot[s] = (uint8_t)q; })) { ++nonstd; continue; }
         LaneState st;
         LaneStats a{0, 0, 0, 0, 0, 0, 0, 0};
         lane_load(st, [&](int s) { return (int)slot[s]; }, red, black, occT, recs[env].move_count, recs[env].player, recs[env].red_score,
@@ -205,7 +206,15 @@ int hs_lane_all_actions(const xq_env_rec* recs, long n, uint8_t* counts, uint16_
         uint32_t w[12];
         std::memcpy(w, recs[i].sq, 48);
         xq::Bits90 red, black, occT;
-        if (!xq::team_unpack_record(w, red, black, occT, [&](int s, int q) { slot[s] = (uint8_t)q; })) { ++nonstd; continue; }
+        uint32_t scratch[12];
+        if (!xq::team_unpack_record_m(w, scratch, 1, red, black, occT, [&](int s, int q) { slot[s] = (uint8_t)q; })) { ++nonstd; continue; }
+        {   // the one-loop unpack places the pieces exactly like the per-word form
+            uint8_t slot2[32];
+            for (int k = 0; k < 32; ++k) slot2[k] = xq::kDeadSq;
+            xq::Bits90 r2, b2, o2;
+            if (!xq::team_unpack_record(w, r2, b2, o2, [&](int s, int q) { slot2[s] = (uint8_t)q; }) || std::memcmp(slot, slot2, 32) != 0 ||
+                r2.w0 != red.w0 || r2.w2 != red.w2 || b2.w1 != black.w1 || o2.w0 != occT.w0 || o2.w1 != occT.w1 || o2.w2 != occT.w2) return -1;
+        }
         const int player = recs[i].player;
         uint32_t own_sq[4] = {0, 0, 0, 0};
         for (int pos = 0; pos < 16; ++pos) own_sq[pos >> 2] |= (uint32_t)slot[(player ? 16 : 0) + xq::lane_pos_slot(pos)] << (8 * (pos & 3));
