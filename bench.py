@@ -487,7 +487,7 @@ def main():
                                                        "warp_inst_per_env_step": tj["lane_kernel_warp_inst_per_step"], "alu_pipe_pct_of_peak": tj.get("lane_kernel_alu_pipe_pct"),
                                                        "issue_active_pct_ncu": tj.get("lane_kernel_issue_active_pct"),
                                                        "note": "the integer ALU pipe issues one warp-instruction every two cycles per scheduler; with ~53 % of the instructions on it "
-                                                               "the ALU pipe (86 % busy) and the issue slots (80 % active) bind together (ncu: profiles/r2b_ncu_rollout_lane_team_summary.csv)"}
+                                                               "the ALU pipe (86 % busy) and the issue slots (80 % active) bind together (ncu: profiles/r2c_ncu_lane_rollout_list_summary.csv)"}
         big.close()
         line["aux"] = aux
 
